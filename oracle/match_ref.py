@@ -1,0 +1,121 @@
+"""Oracle: CPU restatement of the 256-d local-descriptor matching flavours.  TEST INFRASTRUCTURE ONLY.
+
+Follows src/Matcher.cc:
+* ``descriptor_distance``            :1893-1900  (``(a-b).norm()``, fp32)
+* ``search_by_bow``                  :220-263, :561-621  (cv::BFMatcher(NORM_L2, crossCheck=true) then ``dist < TH_LOW``)
+* ``search_for_triangulation_core``  :845-889   (sgemm ``D1*D2^T``, row argmax above ``1-0.5*TH_HIGH^2``, column
+                                                 cross-check; strict ``>`` so the lowest index wins ties)
+* ``best2_masked`` / ``accept_projection``  :40-125 (``SearchByProjection(F, MPs)`` best / second best over the
+                                                 candidate window, level-aware ratio test)
+and the GEMM + ratio + mutual variant of Examples/Utility/test_match_local_feats.cc:48-121 (``search_ratio_mutual``).
+
+Pin: ``search_by_bow`` is checked pair-for-pair against ``cv2.BFMatcher(cv2.NORM_L2, crossCheck=True)`` (the
+function the reference calls) in tests/test_oracle_pins.py.  The floating-point summation order of Eigen's sgemm
+is unpinned; index outputs are exact away from fp32 ties.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TH_HIGH = np.float32(0.75)   # Matcher.cc:33
+TH_LOW = np.float32(0.6)     # Matcher.cc:34
+COS_FLOOR = np.float32(-0.5 * 0.75 * 0.75 + 1)   # Matcher.cc:851  = 0.71875
+
+
+def descriptor_distance(a: np.ndarray, b: np.ndarray) -> np.float32:
+    d = (np.asarray(a, np.float32) - np.asarray(b, np.float32)).astype(np.float32)
+    return np.float32(np.sqrt(np.sum(d * d, dtype=np.float32)))
+
+
+def l2_distance_matrix(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """Explicit ||a_i - b_j||_2 in fp32-of-fp64 (what OpenCV's batchDistance NORM_L2 evaluates, up to rounding)."""
+    A64, B64 = A.astype(np.float64), B.astype(np.float64)
+    d2 = (A64 * A64).sum(1)[:, None] + (B64 * B64).sum(1)[None, :] - 2.0 * (A64 @ B64.T)
+    return np.sqrt(np.maximum(d2, 0.0)).astype(np.float32)
+
+
+def search_by_bow(A: np.ndarray, B: np.ndarray, max_dist: float = float(TH_LOW)):
+    """Mutual nearest neighbours by L2 distance, kept iff dist < max_dist (strict, Matcher.cc:253).
+    Returns (idxA int32[m], idxB int32[m], dist f32[m]) sorted by idxA."""
+    if A.shape[0] == 0 or B.shape[0] == 0:
+        z = np.zeros(0, np.int32)
+        return z, z.copy(), np.zeros(0, np.float32)
+    D = l2_distance_matrix(A, B)
+    nn_ab = D.argmin(axis=1)          # first minimum on ties
+    nn_ba = D.argmin(axis=0)
+    ia = np.arange(A.shape[0])
+    mutual = nn_ba[nn_ab] == ia
+    dist = D[ia, nn_ab]
+    keep = mutual & (dist < np.float32(max_dist))
+    return ia[keep].astype(np.int32), nn_ab[keep].astype(np.int32), dist[keep]
+
+
+def search_for_triangulation_core(D1: np.ndarray, D2: np.ndarray, floor: float = float(COS_FLOOR)):
+    """Matcher.cc:845-889 without the geometric filters.  Returns (idx1, idx2, cos) sorted by idx1."""
+    if D1.shape[0] == 0 or D2.shape[0] == 0:
+        z = np.zeros(0, np.int32)
+        return z, z.copy(), np.zeros(0, np.float32)
+    S = (D1.astype(np.float64) @ D2.astype(np.float64).T).astype(np.float32)
+    fl = np.float32(floor)
+    Sm = np.where(S > fl, S, -np.inf)
+    row_best = Sm.argmax(axis=1)                    # first max on ties == strict '>' scan
+    row_ok = np.isfinite(Sm[np.arange(S.shape[0]), row_best])
+    col_best = Sm.argmax(axis=0)
+    i = np.arange(S.shape[0])
+    keep = row_ok & (col_best[row_best] == i)
+    return i[keep].astype(np.int32), row_best[keep].astype(np.int32), S[i[keep], row_best[keep]]
+
+
+def search_ratio_mutual(D1: np.ndarray, D2: np.ndarray, ratio: float, threshold: float, mutual: bool = True):
+    """Examples/Utility/test_match_local_feats.cc:48-121: dist = 2*(1 - d1.d2); best < threshold, best < ratio*second,
+    optional cross-check (strict '<', first index wins)."""
+    S = (D1.astype(np.float64) @ D2.astype(np.float64).T).astype(np.float32)
+    dist = (np.float32(2) * (np.float32(1) - S)).astype(np.float32)
+    out = []
+    col_best = dist.argmin(axis=0)
+    for i in range(dist.shape[0]):
+        row = dist[i]
+        j = int(row.argmin())
+        b1 = row[j]
+        if row.shape[0] > 1:
+            rest = np.delete(row, j)
+            b2 = rest.min()
+        else:
+            b2 = np.float32(np.finfo(np.float32).max)
+        if b1 < np.float32(threshold) and b1 < np.float32(ratio) * b2:
+            if (not mutual) or col_best[j] == i:
+                out.append((i, j, b1))
+    if not out:
+        z = np.zeros(0, np.int32)
+        return z, z.copy(), np.zeros(0, np.float32)
+    a = np.array(out)
+    return a[:, 0].astype(np.int32), a[:, 1].astype(np.int32), a[:, 2].astype(np.float32)
+
+
+def best2_masked(Q: np.ndarray, F: np.ndarray, cand_ptr: np.ndarray, cand_idx: np.ndarray, f_level: np.ndarray):
+    """Best / second-best L2 distance of each query over its ragged candidate list (Matcher.cc:78-117 inner loop).
+    cand_ptr int[M+1], cand_idx int[...] (visit order kept).  Returns best_idx, best_dist, best_level, second_dist,
+    second_level (idx -1 / dist FLT_MAX / level -1 where absent)."""
+    M = Q.shape[0]
+    fmax = np.finfo(np.float32).max
+    bi = np.full(M, -1, np.int32)
+    bd = np.full(M, fmax, np.float32)
+    bl = np.full(M, -1, np.int32)
+    sd = np.full(M, fmax, np.float32)
+    sl = np.full(M, -1, np.int32)
+    for m in range(M):
+        for idx in cand_idx[cand_ptr[m]:cand_ptr[m + 1]]:
+            d = np.float32(np.sqrt(((Q[m].astype(np.float64) - F[idx].astype(np.float64)) ** 2).sum()))
+            if d < bd[m]:
+                sd[m], sl[m] = bd[m], bl[m]
+                bd[m], bl[m], bi[m] = d, f_level[idx], idx
+            elif d < sd[m]:
+                sd[m], sl[m] = d, f_level[idx]
+    return bi, bd, bl, sd, sl
+
+
+def accept_projection(bd, bl, sd, sl, ratio: float, th_high: float = float(TH_HIGH)):
+    """Matcher.cc:119-125: accept iff best <= TH_HIGH and not (same level and best > ratio*second)."""
+    ok = bd <= np.float32(th_high)
+    reject = (bl == sl) & (bd > np.float32(ratio) * sd)
+    return ok & ~reject
