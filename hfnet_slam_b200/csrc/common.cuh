@@ -1,0 +1,199 @@
+// Shared declarations of libhfnet_b200.so (sm_100a only).  Host-side context, error plumbing, device buffers.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hfnet_b200.h"
+
+#define HFB_CUDA(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                      \
+      return HFB_ERR_CUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+
+#define HFB_CHECK_LAUNCH(ctx, what)                                                              \
+  do {                                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                         \
+    if (_e != cudaSuccess) {                                                                     \
+      (ctx)->set_error(std::string(what) + ": launch failed: " + cudaGetErrorString(_e));        \
+      return HFB_ERR_CUDA;                                                                       \
+    }                                                                                            \
+    (ctx)->launches++;                                                                           \
+  } while (0)
+
+#define HFB_REQUIRE(ctx, cond, msg)                                                              \
+  do {                                                                                           \
+    if (!(cond)) {                                                                               \
+      (ctx)->set_error(msg);                                                                     \
+      return HFB_ERR_INVALID;                                                                    \
+    }                                                                                            \
+  } while (0)
+
+#define HFB_TRY(expr)                                                                            \
+  do {                                                                                           \
+    int _s = (expr);                                                                             \
+    if (_s != HFB_OK) return _s;                                                                 \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
+
+typedef unsigned long long u64;
+
+// A GEMM-shaped layer: weights fp16 [N][Kp] (K-major rows, Kp = K rounded up to 8), bias fp32 [N].
+struct GemmW {
+  int K = 0, Kp = 0, N = 0;
+  const __half* w = nullptr;
+  const float* b = nullptr;
+};
+
+// One inverted-residual block (hfnet/models/backbones/utils/conv_blocks.py:162-312), BatchNorm folded.
+struct BlockW {
+  int layer = 0, cin = 0, cexp = 0, cout = 0, stride = 1;
+  bool has_expand = false, residual = false;
+  GemmW expand, project;
+  const float *wd = nullptr, *bd = nullptr;  // depthwise [9][cexp], [cexp]
+};
+
+struct NetW {
+  int c1 = 0, n_clusters = 0, c_local = 0, c_global = 0;
+  const float *conv1_w = nullptr, *conv1_b = nullptr;  // [9][c1], [c1]
+  std::vector<BlockW> blocks;
+  GemmW head1;      // desc.conv1 (N rows 0..255) and det.conv1 (rows 256..383) concatenated: K = 9*c_local
+  GemmW desc2;      // 256 -> 256
+  GemmW det2;       // 128 -> 65
+  const float *vlad_w = nullptr, *vlad_b = nullptr, *vlad_c = nullptr;  // [c_global][C], [C], [C][c_global]
+  const __half* fc_w = nullptr;                                          // [c_global*C][4096] fp16
+  const float* fc_b = nullptr;
+};
+
+// Per-pyramid-level plan: shapes and device buffers.
+struct LevelPlan {
+  int H = 0, W = 0;    // image size of this level
+  int H8 = 0, W8 = 0;  // cropped to multiples of 8 (hf_net.py:188-190)
+  float scale = 1.f;   // mvScaleFactor[level]
+  bool global = false;
+  uint8_t* d_img = nullptr;  // [H][W]
+  int n_act = 0;             // layers computed for this level (7 or 18)
+  __half* act[19] = {nullptr};
+  int aH[19] = {0}, aW[19] = {0}, aC[19] = {0};
+  __half *d_exp = nullptr, *d_dw = nullptr;  // expand / depthwise scratch
+  __half* d_head1 = nullptr;                 // [Hd*Wd][384] desc.conv1 | det.conv1 (ReLU6)
+  float* d_logits = nullptr;                 // [Hd*Wd][65]
+  float* d_descmap = nullptr;                // [Hd][Wd][256] unit rows
+  float *d_scores = nullptr, *d_nms = nullptr;  // [H8][W8]
+  u64* d_cand = nullptr;      // [max_batch][cand_cap] threshold-scan survivors
+  int* d_cand_count = nullptr;
+  float *d_memb = nullptr, *d_vlad = nullptr, *d_vladn = nullptr, *d_fc_partial = nullptr;
+  int *d_xi = nullptr, *d_yi = nullptr;      // resize tables (from previous level)
+  short *d_xa = nullptr, *d_ya = nullptr;
+};
+
+struct hfb_ctx {
+  hfb_config cfg{};
+  int device = 0;
+  int n_sm = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  // weights
+  void* d_wblob = nullptr;
+  bool weights_loaded = false;
+  NetW net;
+  // levels
+  int n_levels = 0;
+  LevelPlan lv[HFB_MAX_LEVELS];
+  int cand_cap = 0;
+  u64* d_sel = nullptr;     // [max_batch][8192] sorted top-k keys of the level being processed
+  int* d_nsel = nullptr;    // [max_batch]
+  int* d_overflow = nullptr;
+  bool debug = false;       // HFB_DEBUG=1: keep detector logits for hfb_debug_tensor
+  // extraction outputs (device): [max_batch][n_levels*max_keypoints] SoA + global descriptors
+  int kp_cap = 0;  // per frame = n_levels * max_keypoints
+  float *d_kx = nullptr, *d_ky = nullptr, *d_kresp = nullptr, *d_kdesc = nullptr, *d_global = nullptr;
+  int* d_koct = nullptr;
+  int* d_kcount = nullptr;  // [max_batch][HFB_MAX_LEVELS]
+  int last_budget[HFB_MAX_LEVELS] = {0};
+  int last_batch = 0;
+  float last_threshold = 0.f;
+  // pinned staging
+  void* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  // generic device scratch (matcher / lba), grown on demand
+  void* d_scratch = nullptr;
+  size_t d_scratch_bytes = 0;
+  std::vector<void*> allocs;
+  bool use_graph = true;
+  // captured extraction graphs keyed by (batch, budgets, threshold bits)
+  struct GraphEntry { std::vector<int> key; cudaGraphExec_t exec; uint64_t kernels; };
+  std::vector<GraphEntry> graphs;
+  int* d_pair_tab = nullptr;  // single-pair table for the unbatched matcher entry points
+
+  void set_error(const std::string& s) { err = s; }
+  int ensure_scratch(size_t bytes);
+  int ensure_stage(size_t bytes);
+  template <typename T>
+  int dalloc(T** p, size_t n) {
+    void* q = nullptr;
+    size_t bytes = n * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes > 0 ? bytes : 16);
+    if (e != cudaSuccess) {
+      set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+      return HFB_ERR_CUDA;
+    }
+    allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return HFB_OK;
+  }
+};
+
+// ---- launchers implemented in the individual .cu files ------------------------------------------------------
+// postproc.cu
+int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, int B);
+int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const float* d_descmap, int Hd, int Wd,
+                         u64* d_cand, int* d_cand_count, int cand_cap, u64* d_sel, int* d_nsel, int n_keypoints,
+                         float threshold, float level_scale, int level, int B, int kp_cap, float* d_x, float* d_y,
+                         float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow);
+int launch_resize(hfb_ctx* ctx, const uint8_t* d_src, int sh, int sw, uint8_t* d_dst, int dh, int dw, const int* d_xi,
+                  const short* d_xa, const int* d_yi, const short* d_ya, int B);
+void build_resize_tables(int sn, int dn, std::vector<int>& idx, std::vector<short>& coef);
+// encoder.cu
+int encoder_plan(hfb_ctx* ctx);
+void encoder_forget(hfb_ctx* ctx);
+int encoder_forward(hfb_ctx* ctx, int level, int B);
+// match.cu: pair_tab = device int[4][n_pairs] (a_off | a_cnt | b_off | b_cnt)
+int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB, int n_pairs, const int* d_pair_tab,
+                       int max_a, int max_b, float thr, int* d_match_idx, float* d_match_val, int na_total,
+                       int nb_total, int** d_n_matches_out);
+
+// order-preserving float <-> uint32 map (larger float -> larger uint)
+__host__ __device__ static inline unsigned int f2ord(float f) {
+#ifdef __CUDA_ARCH__
+  unsigned int u = __float_as_uint(f);
+#else
+  unsigned int u;
+  memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ static inline float ord2f(unsigned int u) {
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}

@@ -1,0 +1,785 @@
+// libhfnet_b200.so: context, weight loading and the extraction / matching entry points of include/hfnet_b200.h.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+// ================================================================================================ context
+int hfb_ctx::ensure_scratch(size_t bytes) {
+  if (bytes <= d_scratch_bytes) return HFB_OK;
+  if (d_scratch) cudaFree(d_scratch);
+  d_scratch = nullptr;
+  d_scratch_bytes = 0;
+  size_t want = bytes + bytes / 4;
+  cudaError_t e = cudaMalloc(&d_scratch, want);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(scratch): ") + cudaGetErrorString(e));
+    return HFB_ERR_CUDA;
+  }
+  d_scratch_bytes = want;
+  return HFB_OK;
+}
+
+int hfb_ctx::ensure_stage(size_t bytes) {
+  if (bytes <= h_stage_bytes) return HFB_OK;
+  if (h_stage) cudaFreeHost(h_stage);
+  h_stage = nullptr;
+  h_stage_bytes = 0;
+  cudaError_t e = cudaMallocHost(&h_stage, bytes);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    return HFB_ERR_CUDA;
+  }
+  h_stage_bytes = bytes;
+  return HFB_OK;
+}
+
+static int cv_round(double v) { return (int)lrint(v); }  // cvRound: round half to even
+
+extern "C" int hfb_version(void) { return HFB_VERSION; }
+
+extern "C" const char* hfb_last_error(const hfb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
+  if (!cfg || !out) return HFB_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->height < 16 || cfg->width < 16 || cfg->n_levels < 1 || cfg->n_levels > HFB_MAX_LEVELS ||
+      cfg->max_keypoints < 1 || cfg->max_keypoints > 8192 || cfg->max_batch < 1 || cfg->max_batch > 64 ||
+      !(cfg->scale_factor > 1.0f || cfg->n_levels == 1))
+    return HFB_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return HFB_ERR_CUDA;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return HFB_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return HFB_ERR_CUDA;
+  hfb_ctx* ctx = new hfb_ctx();
+  ctx->cfg = *cfg;
+  ctx->device = cfg->device;
+  ctx->n_sm = prop.multiProcessorCount;
+  ctx->n_levels = cfg->n_levels;
+  const char* dbg = getenv("HFB_DEBUG");
+  ctx->debug = dbg && dbg[0] == '1';
+  const char* ng = getenv("HFB_NO_GRAPH");
+  ctx->use_graph = !(ng && ng[0] == '1');
+  *out = ctx;  // returned even on failure so that hfb_last_error works; caller destroys
+  if (prop.major != 10) {
+    ctx->set_error(std::string("this library is built for sm_100a only; device is ") + prop.name + " (sm_" +
+                   std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    return HFB_ERR_CUDA;
+  }
+  HFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  // level shapes: mvScaleFactor[l] = scaleFactor^l accumulated in float (HFextractor.cc:92-103); image size of
+  // level l = cvRound(size * 1/scale) (HFextractor.cc:159-173, BaseModel.cc:35-65)
+  float sf = 1.f;
+  for (int l = 0; l < ctx->n_levels; ++l) {
+    LevelPlan& lv = ctx->lv[l];
+    if (l > 0) sf = sf * cfg->scale_factor;
+    lv.scale = sf;
+    const float inv = 1.0f / sf;
+    lv.H = l == 0 ? cfg->height : cv_round((double)((float)cfg->height * inv));
+    lv.W = l == 0 ? cfg->width : cv_round((double)((float)cfg->width * inv));
+    lv.H8 = lv.H / 8 * 8;
+    lv.W8 = lv.W / 8 * 8;
+    lv.global = (l == 0 && cfg->with_global);
+    if (lv.H8 < 8 || lv.W8 < 8) {
+      ctx->set_error("pyramid level too small");
+      return HFB_ERR_INVALID;
+    }
+    HFB_TRY(ctx->dalloc(&lv.d_img, (size_t)cfg->max_batch * lv.H * lv.W));
+    if (l > 0) {
+      std::vector<int> xi, yi;
+      std::vector<short> xa, ya;
+      build_resize_tables(ctx->lv[l - 1].W, lv.W, xi, xa);
+      build_resize_tables(ctx->lv[l - 1].H, lv.H, yi, ya);
+      HFB_TRY(ctx->dalloc(&lv.d_xi, xi.size()));
+      HFB_TRY(ctx->dalloc(&lv.d_xa, xa.size()));
+      HFB_TRY(ctx->dalloc(&lv.d_yi, yi.size()));
+      HFB_TRY(ctx->dalloc(&lv.d_ya, ya.size()));
+      HFB_CUDA(ctx, cudaMemcpy(lv.d_xi, xi.data(), xi.size() * sizeof(int), cudaMemcpyHostToDevice));
+      HFB_CUDA(ctx, cudaMemcpy(lv.d_xa, xa.data(), xa.size() * sizeof(short), cudaMemcpyHostToDevice));
+      HFB_CUDA(ctx, cudaMemcpy(lv.d_yi, yi.data(), yi.size() * sizeof(int), cudaMemcpyHostToDevice));
+      HFB_CUDA(ctx, cudaMemcpy(lv.d_ya, ya.data(), ya.size() * sizeof(short), cudaMemcpyHostToDevice));
+    }
+  }
+  ctx->cand_cap = std::min(65536, std::max(4096, cfg->height * cfg->width / 8));
+  ctx->kp_cap = ctx->n_levels * cfg->max_keypoints;
+  const size_t nb = (size_t)cfg->max_batch;
+  HFB_TRY(ctx->dalloc(&ctx->d_kx, nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_ky, nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_kresp, nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_koct, nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_kdesc, nb * ctx->kp_cap * HFB_DESC_DIM));
+  HFB_TRY(ctx->dalloc(&ctx->d_global, nb * HFB_GLOBAL_DIM));
+  HFB_TRY(ctx->dalloc(&ctx->d_kcount, nb * HFB_MAX_LEVELS));
+  HFB_TRY(ctx->dalloc(&ctx->d_sel, nb * 8192));
+  HFB_TRY(ctx->dalloc(&ctx->d_nsel, nb));
+  HFB_TRY(ctx->dalloc(&ctx->d_overflow, 1));
+  HFB_TRY(ctx->dalloc(&ctx->d_pair_tab, 4));
+  HFB_CUDA(ctx, cudaMemset(ctx->d_overflow, 0, sizeof(int)));
+  HFB_CUDA(ctx, cudaMemset(ctx->d_kcount, 0, nb * HFB_MAX_LEVELS * sizeof(int)));
+  return HFB_OK;
+}
+
+static void drop_graphs(hfb_ctx* ctx) {
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  ctx->graphs.clear();
+}
+
+extern "C" void hfb_destroy(hfb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  drop_graphs(ctx);
+  encoder_forget(ctx);
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->d_wblob) cudaFree(ctx->d_wblob);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int hfb_sync(hfb_ctx* ctx) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
+}
+extern "C" void* hfb_stream(hfb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t hfb_launch_count(const hfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ================================================================================================ weights
+static int make_divisible(double v, int divisor, int min_value) {
+  int nv = std::max(min_value, (int)(v + divisor / 2.0) / divisor * divisor);
+  if (nv < 0.9 * v) nv += divisor;
+  return nv;
+}
+
+struct ArenaBuilder {
+  std::vector<uint8_t> host;
+  size_t add(const void* src, size_t bytes) {
+    size_t off = (host.size() + 255) & ~(size_t)255;
+    host.resize(off + bytes);
+    memcpy(host.data() + off, src, bytes);
+    return off;
+  }
+};
+
+static __half h_f2h(float f) { return __float2half_rn(f); }
+
+// [K][N] fp32 (blob layout) -> fp16 [N][Kp]
+static size_t add_gemm_w(ArenaBuilder& ab, const float* w, int K, int N, int Kp) {
+  std::vector<__half> t((size_t)N * Kp, h_f2h(0.f));
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < N; ++n) t[(size_t)n * Kp + k] = h_f2h(w[(size_t)k * N + n]);
+  return ab.add(t.data(), t.size() * sizeof(__half));
+}
+
+extern "C" int hfb_load_weights(hfb_ctx* ctx, const void* blob, size_t nbytes) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, !ctx->weights_loaded, "weights already loaded (create a new context)");
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(blob);
+  HFB_REQUIRE(ctx, blob && nbytes >= 32 && memcmp(p, "HFB2WTS1", 8) == 0, "bad weight blob magic");
+  uint32_t version, n_clusters, n_tensors;
+  float dm;
+  uint64_t total;
+  memcpy(&version, p + 8, 4);
+  memcpy(&n_clusters, p + 12, 4);
+  memcpy(&dm, p + 16, 4);
+  memcpy(&n_tensors, p + 20, 4);
+  memcpy(&total, p + 24, 8);
+  HFB_REQUIRE(ctx, version == 1, "unsupported weight blob version");
+  HFB_REQUIRE(ctx, n_clusters >= 1 && n_clusters <= 64, "n_clusters must be in [1,64]");
+  HFB_REQUIRE(ctx, nbytes == 32 + total * 4, "weight blob size mismatch");
+  const float* f = reinterpret_cast<const float*>(p + 32);
+  size_t off = 0;
+  auto take = [&](size_t n) -> const float* {
+    const float* r = f + off;
+    off += n;
+    return off <= total ? r : nullptr;
+  };
+  // architecture (hfnet_slam_b200/weights.py:architecture == hf_net.py:13-52 with depth multiplier dm)
+  static const int nominal[17][2] = {{1, 16}, {2, 24}, {1, 24}, {2, 32}, {1, 64}, {1, 128}, {2, 64}, {1, 64}, {1, 64},
+                                     {1, 64}, {1, 96}, {1, 96}, {1, 96}, {2, 160}, {1, 160}, {1, 160}, {1, 320}};
+  NetW& net = ctx->net;
+  net.c1 = make_divisible(32.0 * dm, 8, 8);
+  net.n_clusters = (int)n_clusters;
+  ArenaBuilder ab;
+  struct Fix { const void** dst; size_t off; };
+  std::vector<Fix> fixes;
+  auto fix = [&](const void** dst, size_t o) { fixes.push_back({dst, o}); };
+#define TAKE(var, n)                                                    \
+  const float* var = take(n);                                           \
+  HFB_REQUIRE(ctx, var != nullptr, "weight blob truncated")
+  {
+    TAKE(w, (size_t)9 * net.c1);
+    TAKE(b, (size_t)net.c1);
+    fix((const void**)&net.conv1_w, ab.add(w, (size_t)9 * net.c1 * 4));
+    fix((const void**)&net.conv1_b, ab.add(b, (size_t)net.c1 * 4));
+  }
+  net.blocks.clear();
+  net.blocks.reserve(17);
+  int cin = net.c1;
+  for (int i = 0; i < 17; ++i) {
+    BlockW bw;
+    bw.layer = i + 2;
+    bw.stride = nominal[i][0];
+    bw.cin = cin;
+    bw.cout = make_divisible(nominal[i][1] * (double)dm, 8, 8);
+    bw.cexp = bw.layer == 2 ? make_divisible(cin * 1.0, 1, 1) : make_divisible(cin * 6.0, 8, 8);
+    bw.has_expand = bw.cexp > bw.cin;
+    bw.residual = bw.stride == 1 && bw.cin == bw.cout;
+    HFB_REQUIRE(ctx, bw.cin % 8 == 0 && bw.cexp % 8 == 0 && bw.cout % 8 == 0, "channel counts must be multiples of 8");
+    net.blocks.push_back(bw);
+    cin = bw.cout;
+  }
+  for (BlockW& bw : net.blocks) {
+    if (bw.has_expand) {
+      TAKE(w, (size_t)bw.cin * bw.cexp);
+      TAKE(b, (size_t)bw.cexp);
+      bw.expand.K = bw.cin; bw.expand.Kp = bw.cin; bw.expand.N = bw.cexp;
+      fix((const void**)&bw.expand.w, add_gemm_w(ab, w, bw.cin, bw.cexp, bw.cin));
+      fix((const void**)&bw.expand.b, ab.add(b, (size_t)bw.cexp * 4));
+    }
+    {
+      TAKE(w, (size_t)9 * bw.cexp);
+      TAKE(b, (size_t)bw.cexp);
+      fix((const void**)&bw.wd, ab.add(w, (size_t)9 * bw.cexp * 4));
+      fix((const void**)&bw.bd, ab.add(b, (size_t)bw.cexp * 4));
+    }
+    {
+      TAKE(w, (size_t)bw.cexp * bw.cout);
+      TAKE(b, (size_t)bw.cout);
+      bw.project.K = bw.cexp; bw.project.Kp = bw.cexp; bw.project.N = bw.cout;
+      fix((const void**)&bw.project.w, add_gemm_w(ab, w, bw.cexp, bw.cout, bw.cexp));
+      fix((const void**)&bw.project.b, ab.add(b, (size_t)bw.cout * 4));
+    }
+  }
+  net.c_local = net.blocks[7 - 2].cout;
+  net.c_global = net.blocks[18 - 2].cout;
+  {
+    const int Kh = 9 * net.c_local;
+    TAKE(wd1, (size_t)Kh * 256);
+    TAKE(bd1, 256);
+    TAKE(wd2, (size_t)256 * 256);
+    TAKE(bd2, 256);
+    TAKE(wt1, (size_t)Kh * 128);
+    TAKE(bt1, 128);
+    TAKE(wt2, (size_t)128 * 65);
+    TAKE(bt2, 65);
+    // head1 = desc.conv1 (rows 0..255) | det.conv1 (rows 256..383), K-major
+    std::vector<__half> t((size_t)384 * Kh);
+    for (int k = 0; k < Kh; ++k) {
+      for (int n = 0; n < 256; ++n) t[(size_t)n * Kh + k] = h_f2h(wd1[(size_t)k * 256 + n]);
+      for (int n = 0; n < 128; ++n) t[(size_t)(256 + n) * Kh + k] = h_f2h(wt1[(size_t)k * 128 + n]);
+    }
+    std::vector<float> hb(384);
+    memcpy(hb.data(), bd1, 256 * 4);
+    memcpy(hb.data() + 256, bt1, 128 * 4);
+    net.head1.K = net.c_local; net.head1.Kp = Kh; net.head1.N = 384;   // K = channels per tap (implicit 3x3)
+    fix((const void**)&net.head1.w, ab.add(t.data(), t.size() * 2));
+    fix((const void**)&net.head1.b, ab.add(hb.data(), 384 * 4));
+    net.desc2.K = 256; net.desc2.Kp = 256; net.desc2.N = 256;
+    fix((const void**)&net.desc2.w, add_gemm_w(ab, wd2, 256, 256, 256));
+    fix((const void**)&net.desc2.b, ab.add(bd2, 256 * 4));
+    net.det2.K = 128; net.det2.Kp = 128; net.det2.N = 65;
+    fix((const void**)&net.det2.w, add_gemm_w(ab, wt2, 128, 65, 128));
+    fix((const void**)&net.det2.b, ab.add(bt2, 65 * 4));
+  }
+  {
+    const int D = net.c_global, C = net.n_clusters;
+    TAKE(mw, (size_t)D * C);
+    TAKE(mb, (size_t)C);
+    TAKE(cl, (size_t)C * D);
+    TAKE(fw, (size_t)D * C * HFB_GLOBAL_DIM);
+    TAKE(fb, (size_t)HFB_GLOBAL_DIM);
+    fix((const void**)&net.vlad_w, ab.add(mw, (size_t)D * C * 4));
+    fix((const void**)&net.vlad_b, ab.add(mb, (size_t)C * 4));
+    fix((const void**)&net.vlad_c, ab.add(cl, (size_t)C * D * 4));
+    std::vector<__half> t((size_t)D * C * HFB_GLOBAL_DIM);
+    for (size_t i = 0; i < t.size(); ++i) t[i] = h_f2h(fw[i]);
+    fix((const void**)&net.fc_w, ab.add(t.data(), t.size() * 2));
+    fix((const void**)&net.fc_b, ab.add(fb, (size_t)HFB_GLOBAL_DIM * 4));
+  }
+#undef TAKE
+  HFB_REQUIRE(ctx, off == total && n_tensors > 0, "weight blob has trailing data");
+  HFB_CUDA(ctx, cudaMalloc(&ctx->d_wblob, ab.host.size()));
+  HFB_CUDA(ctx, cudaMemcpy(ctx->d_wblob, ab.host.data(), ab.host.size(), cudaMemcpyHostToDevice));
+  for (const Fix& fx : fixes) *fx.dst = reinterpret_cast<const uint8_t*>(ctx->d_wblob) + fx.off;
+  HFB_TRY(encoder_plan(ctx));
+  ctx->weights_loaded = true;
+  return HFB_OK;
+}
+
+// ================================================================================================ extraction
+static int check_overflow(hfb_ctx* ctx) {
+  int ov = 0;
+  HFB_CUDA(ctx, cudaMemcpyAsync(&ov, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ov) {
+    cudaMemsetAsync(ctx->d_overflow, 0, sizeof(int), ctx->stream);
+    ctx->set_error("more threshold-scan candidates than the context's candidate capacity (threshold too low)");
+    return HFB_ERR_CAPACITY;
+  }
+  return HFB_OK;
+}
+
+// Enqueues pyramid + encoder + selection of every level for frames already in lv[0].d_img.
+static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float threshold) {
+  for (int l = 0; l < ctx->n_levels; ++l) {
+    LevelPlan& lv = ctx->lv[l];
+    if (l > 0) {
+      LevelPlan& pv = ctx->lv[l - 1];
+      HFB_TRY(launch_resize(ctx, pv.d_img, pv.H, pv.W, lv.d_img, lv.H, lv.W, lv.d_xi, lv.d_xa, lv.d_yi, lv.d_ya, B));
+    }
+    HFB_TRY(encoder_forward(ctx, l, B));
+    HFB_TRY(launch_select_sample(ctx, lv.d_nms, lv.H8, lv.W8, lv.d_descmap, lv.H8 / 8, lv.W8 / 8, lv.d_cand,
+                                 lv.d_cand_count, ctx->cand_cap, ctx->d_sel, ctx->d_nsel, n_per_level[l], threshold,
+                                 lv.scale, l, B, ctx->kp_cap, ctx->d_kx, ctx->d_ky, ctx->d_kresp, ctx->d_koct,
+                                 ctx->d_kdesc, ctx->d_kcount, ctx->d_overflow));
+  }
+  return HFB_OK;
+}
+
+static int run_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float threshold) {
+  HFB_REQUIRE(ctx, ctx->weights_loaded, "weights not loaded");
+  HFB_REQUIRE(ctx, B >= 1 && B <= ctx->cfg.max_batch, "batch size outside [1, max_batch]");
+  for (int l = 0; l < ctx->n_levels; ++l)
+    HFB_REQUIRE(ctx, n_per_level[l] >= 0 && n_per_level[l] <= ctx->cfg.max_keypoints,
+                "per-level keypoint budget outside [0, max_keypoints]");
+  ctx->last_batch = B;
+  ctx->last_threshold = threshold;
+  for (int l = 0; l < ctx->n_levels; ++l) ctx->last_budget[l] = n_per_level[l];
+  if (!ctx->use_graph) return enqueue_extract(ctx, B, n_per_level, threshold);
+  std::vector<int> key;
+  key.push_back(B);
+  for (int l = 0; l < ctx->n_levels; ++l) key.push_back(n_per_level[l]);
+  int tb;
+  memcpy(&tb, &threshold, 4);
+  key.push_back(tb);
+  for (auto& g : ctx->graphs)
+    if (g.key == key) {
+      HFB_CUDA(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+      ctx->launches += g.kernels;
+      return HFB_OK;
+    }
+  // Warm (non-captured) run first: sets kernel attributes and surfaces errors outside of capture.
+  HFB_TRY(enqueue_extract(ctx, B, n_per_level, threshold));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const uint64_t before = ctx->launches;
+  cudaGraph_t graph = nullptr;
+  HFB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_extract(ctx, B, n_per_level, threshold);
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  const uint64_t kernels = ctx->launches - before;
+  ctx->launches = before;  // capture launched nothing
+  if (rc != HFB_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) {
+    ctx->set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    return HFB_ERR_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    ctx->set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    return HFB_ERR_CUDA;
+  }
+  if (ctx->graphs.size() >= 16) drop_graphs(ctx);
+  ctx->graphs.push_back({key, exec, kernels});
+  return HFB_OK;  // results of the warm run are in place
+}
+
+extern "C" int hfb_extract_batch_dev(hfb_ctx* ctx, const uint8_t* d_images, int32_t n_images,
+                                     const int32_t* n_per_level, float threshold) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, d_images && n_per_level, "null argument");
+  HFB_REQUIRE(ctx, n_images >= 1 && n_images <= ctx->cfg.max_batch, "batch size outside [1, max_batch]");
+  LevelPlan& l0 = ctx->lv[0];
+  if (d_images != l0.d_img)
+    HFB_CUDA(ctx, cudaMemcpyAsync(l0.d_img, d_images, (size_t)n_images * l0.H * l0.W, cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+  return run_extract(ctx, n_images, n_per_level, threshold);
+}
+
+extern "C" int hfb_fetch_features(hfb_ctx* ctx, int32_t image_index, hfb_features* out) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, out && image_index >= 0 && image_index < ctx->last_batch, "bad image index");
+  int counts[HFB_MAX_LEVELS];
+  HFB_CUDA(ctx, cudaMemcpyAsync(counts, ctx->d_kcount + (size_t)image_index * HFB_MAX_LEVELS, sizeof(counts),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_TRY(check_overflow(ctx));  // synchronises
+  int total = 0;
+  for (int l = 0; l < HFB_MAX_LEVELS; ++l) {
+    out->n_per_level[l] = l < ctx->n_levels ? counts[l] : 0;
+    total += out->n_per_level[l];
+  }
+  out->n_total = total;
+  const size_t o = (size_t)image_index * ctx->kp_cap;
+  if (total > 0) {
+    HFB_CUDA(ctx, cudaMemcpyAsync(out->x, ctx->d_kx + o, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(out->y, ctx->d_ky + o, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(out->response, ctx->d_kresp + o, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(out->octave, ctx->d_koct + o, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(out->descriptors, ctx->d_kdesc + o * HFB_DESC_DIM, (size_t)total * HFB_DESC_DIM * 4,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (out->global_descriptor && ctx->cfg.with_global)
+    HFB_CUDA(ctx, cudaMemcpyAsync(out->global_descriptor, ctx->d_global + (size_t)image_index * HFB_GLOBAL_DIM,
+                                  HFB_GLOBAL_DIM * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
+}
+
+extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int32_t n_images, int32_t stride,
+                                 const int32_t* n_per_level, float threshold, hfb_features* outs) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, images && n_per_level && outs, "null argument");
+  HFB_REQUIRE(ctx, n_images >= 1 && n_images <= ctx->cfg.max_batch, "batch size outside [1, max_batch]");
+  LevelPlan& l0 = ctx->lv[0];
+  HFB_REQUIRE(ctx, stride >= l0.W, "stride smaller than the image width");
+  // Pinned staging (the reference copies from pageable memory with a synchronous cudaMemcpy, TensorRTBuffers.h:417-435)
+  const size_t img_bytes = (size_t)l0.H * l0.W;
+  const size_t per_frame_out = (size_t)ctx->kp_cap * (4 * 4 + HFB_DESC_DIM * 4) + HFB_GLOBAL_DIM * 4 + 64;
+  HFB_TRY(ctx->ensure_stage((size_t)n_images * (img_bytes + per_frame_out)));
+  uint8_t* hs = reinterpret_cast<uint8_t*>(ctx->h_stage);
+  for (int b = 0; b < n_images; ++b) {
+    HFB_REQUIRE(ctx, images[b] != nullptr, "null image");
+    for (int y = 0; y < l0.H; ++y) memcpy(hs + (size_t)b * img_bytes + (size_t)y * l0.W, images[b] + (size_t)y * stride, l0.W);
+  }
+  HFB_CUDA(ctx, cudaMemcpyAsync(l0.d_img, hs, (size_t)n_images * img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_TRY(run_extract(ctx, n_images, n_per_level, threshold));
+  // one D2H burst of budget-sized slices into pinned memory, one synchronisation
+  int budget = 0;
+  for (int l = 0; l < ctx->n_levels; ++l) budget += n_per_level[l];
+  uint8_t* ho = hs + (size_t)n_images * img_bytes;
+  struct Slot { int* counts; float *x, *y, *r; int* o; float *d, *g; };
+  std::vector<Slot> slots(n_images);
+  for (int b = 0; b < n_images; ++b) {
+    uint8_t* q = ho + (size_t)b * per_frame_out;
+    Slot& s = slots[b];
+    s.counts = reinterpret_cast<int*>(q); q += 64;
+    s.x = reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
+    s.y = reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
+    s.r = reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
+    s.o = reinterpret_cast<int*>(q); q += (size_t)ctx->kp_cap * 4;
+    s.d = reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * HFB_DESC_DIM * 4;
+    s.g = reinterpret_cast<float*>(q);
+    const size_t o = (size_t)b * ctx->kp_cap;
+    HFB_CUDA(ctx, cudaMemcpyAsync(s.counts, ctx->d_kcount + (size_t)b * HFB_MAX_LEVELS, HFB_MAX_LEVELS * 4,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    if (budget > 0) {
+      HFB_CUDA(ctx, cudaMemcpyAsync(s.x, ctx->d_kx + o, (size_t)budget * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      HFB_CUDA(ctx, cudaMemcpyAsync(s.y, ctx->d_ky + o, (size_t)budget * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      HFB_CUDA(ctx, cudaMemcpyAsync(s.r, ctx->d_kresp + o, (size_t)budget * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      HFB_CUDA(ctx, cudaMemcpyAsync(s.o, ctx->d_koct + o, (size_t)budget * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      HFB_CUDA(ctx, cudaMemcpyAsync(s.d, ctx->d_kdesc + o * HFB_DESC_DIM, (size_t)budget * HFB_DESC_DIM * 4,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (ctx->cfg.with_global)
+      HFB_CUDA(ctx, cudaMemcpyAsync(s.g, ctx->d_global + (size_t)b * HFB_GLOBAL_DIM, HFB_GLOBAL_DIM * 4,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  HFB_TRY(check_overflow(ctx));  // synchronises the stream
+  for (int b = 0; b < n_images; ++b) {
+    const Slot& s = slots[b];
+    hfb_features& f = outs[b];
+    int total = 0;
+    for (int l = 0; l < HFB_MAX_LEVELS; ++l) {
+      f.n_per_level[l] = l < ctx->n_levels ? s.counts[l] : 0;
+      total += f.n_per_level[l];
+    }
+    f.n_total = total;
+    if (total > 0) {
+      memcpy(f.x, s.x, (size_t)total * 4);
+      memcpy(f.y, s.y, (size_t)total * 4);
+      memcpy(f.response, s.r, (size_t)total * 4);
+      memcpy(f.octave, s.o, (size_t)total * 4);
+      memcpy(f.descriptors, s.d, (size_t)total * HFB_DESC_DIM * 4);
+    }
+    if (f.global_descriptor && ctx->cfg.with_global) memcpy(f.global_descriptor, s.g, HFB_GLOBAL_DIM * 4);
+  }
+  return HFB_OK;
+}
+
+extern "C" int hfb_extract(hfb_ctx* ctx, const uint8_t* image, int32_t height, int32_t width, int32_t stride,
+                           const int32_t* n_per_level, float threshold, hfb_features* out) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, height == ctx->cfg.height && width == ctx->cfg.width,
+              "image size differs from the context's (the reference builds one engine per fixed shape too, "
+              "BaseModel.cc:35-65)");
+  const uint8_t* imgs[1] = {image};
+  return hfb_extract_batch(ctx, imgs, 1, stride, n_per_level, threshold, out);
+}
+
+// ------------------------------------------------------------------------------------------------ parity hooks
+extern "C" int hfb_nms(hfb_ctx* ctx, const float* scores, int32_t height, int32_t width, float* scores_nms) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, scores && scores_nms && height > 0 && width > 0, "bad argument");
+  const size_t n = (size_t)height * width;
+  HFB_TRY(ctx->ensure_scratch(2 * n * 4));
+  float* d_in = reinterpret_cast<float*>(ctx->d_scratch);
+  float* d_out = d_in + n;
+  HFB_CUDA(ctx, cudaMemcpyAsync(d_in, scores, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_TRY(launch_nms(ctx, d_in, d_out, height, width, 1));
+  HFB_CUDA(ctx, cudaMemcpyAsync(scores_nms, d_out, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
+}
+
+extern "C" int hfb_select_sample(hfb_ctx* ctx, const float* scores_nms, int32_t height, int32_t width,
+                                 const float* desc_map, int32_t desc_h, int32_t desc_w, int32_t n_keypoints,
+                                 float threshold, float* x, float* y, float* response, float* descriptors,
+                                 int32_t* n_out) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, scores_nms && desc_map && n_out && height > 0 && width > 0 && desc_h > 0 && desc_w > 0,
+              "bad argument");
+  HFB_REQUIRE(ctx, n_keypoints >= 0 && n_keypoints <= 8192, "n_keypoints outside [0, 8192]");
+  const size_t n = (size_t)height * width, nd = (size_t)desc_h * desc_w * 256;
+  const int cap = (int)std::min<size_t>(n, 1 << 20);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_desc = al(n * 4), o_cand = o_desc + al(nd * 4), o_cnt = o_cand + al((size_t)cap * 8);
+  const size_t o_x = o_cnt + 256, o_y = o_x + al(8192 * 4), o_r = o_y + al(8192 * 4), o_o = o_r + al(8192 * 4);
+  const size_t o_d = o_o + al(8192 * 4), o_k = o_d + al((size_t)8192 * 256 * 4), total = o_k + 256;
+  HFB_TRY(ctx->ensure_scratch(total));
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->d_scratch);
+  float* d_nms = reinterpret_cast<float*>(base);
+  float* d_dm = reinterpret_cast<float*>(base + o_desc);
+  u64* d_cand = reinterpret_cast<u64*>(base + o_cand);
+  int* d_cnt = reinterpret_cast<int*>(base + o_cnt);
+  float *d_x = reinterpret_cast<float*>(base + o_x), *d_y = reinterpret_cast<float*>(base + o_y);
+  float* d_r = reinterpret_cast<float*>(base + o_r);
+  int* d_o = reinterpret_cast<int*>(base + o_o);
+  float* d_d = reinterpret_cast<float*>(base + o_d);
+  int* d_k = reinterpret_cast<int*>(base + o_k);
+  HFB_CUDA(ctx, cudaMemcpyAsync(d_nms, scores_nms, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(d_dm, desc_map, nd * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemsetAsync(d_k, 0, HFB_MAX_LEVELS * 4, ctx->stream));
+  HFB_TRY(launch_select_sample(ctx, d_nms, height, width, d_dm, desc_h, desc_w, d_cand, d_cnt, cap, ctx->d_sel,
+                               ctx->d_nsel, n_keypoints, threshold, 1.0f, 0, 1, 8192, d_x, d_y, d_r, d_o, d_d, d_k,
+                               ctx->d_overflow));
+  int cnt = 0;
+  HFB_CUDA(ctx, cudaMemcpyAsync(&cnt, d_k, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_TRY(check_overflow(ctx));
+  *n_out = cnt;
+  if (cnt > 0) {
+    HFB_CUDA(ctx, cudaMemcpyAsync(x, d_x, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(y, d_y, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(response, d_r, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(descriptors, d_d, (size_t)cnt * 256 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return HFB_OK;
+}
+
+extern "C" int hfb_resize_linear_u8(hfb_ctx* ctx, const uint8_t* src, int32_t sh, int32_t sw, uint8_t* dst, int32_t dh,
+                                    int32_t dw) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, src && dst && sh > 0 && sw > 0 && dh > 0 && dw > 0, "bad argument");
+  std::vector<int> xi, yi;
+  std::vector<short> xa, ya;
+  build_resize_tables(sw, dw, xi, xa);
+  build_resize_tables(sh, dh, yi, ya);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_dst = al((size_t)sh * sw), o_xi = o_dst + al((size_t)dh * dw), o_xa = o_xi + al(xi.size() * 4);
+  const size_t o_yi = o_xa + al(xa.size() * 2), o_ya = o_yi + al(yi.size() * 4), total = o_ya + al(ya.size() * 2);
+  HFB_TRY(ctx->ensure_scratch(total));
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->d_scratch);
+  HFB_CUDA(ctx, cudaMemcpyAsync(base, src, (size_t)sh * sw, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(base + o_xi, xi.data(), xi.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(base + o_xa, xa.data(), xa.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(base + o_yi, yi.data(), yi.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(base + o_ya, ya.data(), ya.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_TRY(launch_resize(ctx, base, sh, sw, base + o_dst, dh, dw, reinterpret_cast<int*>(base + o_xi),
+                        reinterpret_cast<short*>(base + o_xa), reinterpret_cast<int*>(base + o_yi),
+                        reinterpret_cast<short*>(base + o_ya), 1));
+  HFB_CUDA(ctx, cudaMemcpyAsync(dst, base + o_dst, (size_t)dh * dw, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // also keeps the host tables alive until the copies are done
+  return HFB_OK;
+}
+
+__global__ void h2f_kernel(const __half* __restrict__ in, int ld, int col0, int cols, float* __restrict__ out,
+                           long long rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = (int)(i - r * cols);
+  out[i] = __half2float(in[r * ld + col0 + c]);
+}
+
+extern "C" int hfb_debug_tensor(hfb_ctx* ctx, const char* name, int32_t image_index, int32_t level, float* out,
+                                size_t cap, size_t* n, int32_t* dims4) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, name && n && dims4, "null argument");
+  HFB_REQUIRE(ctx, ctx->weights_loaded && ctx->last_batch > 0, "no extraction has run yet");
+  HFB_REQUIRE(ctx, level >= 0 && level < ctx->n_levels && image_index >= 0 && image_index < ctx->last_batch,
+              "bad level / image index");
+  LevelPlan& lv = ctx->lv[level];
+  const std::string s(name);
+  const int Hd = lv.H8 / 8, Wd = lv.W8 / 8;
+  const __half* hsrc = nullptr;
+  const float* fsrc = nullptr;
+  int ld = 0, col0 = 0;
+  int d[4] = {1, 0, 0, 0};
+  if (s.rfind("layer_", 0) == 0) {
+    const int L = atoi(s.c_str() + 6);
+    HFB_REQUIRE(ctx, L >= 1 && L <= lv.n_act, "layer not computed for this level");
+    d[1] = lv.aH[L]; d[2] = lv.aW[L]; d[3] = lv.aC[L];
+    hsrc = lv.act[L] + (size_t)image_index * d[1] * d[2] * d[3];
+    ld = d[3];
+  } else if (s == "desc_conv1" || s == "det_conv1") {
+    d[1] = Hd; d[2] = Wd; d[3] = s == "desc_conv1" ? 256 : 128;
+    hsrc = lv.d_head1 + (size_t)image_index * Hd * Wd * 384;
+    ld = 384;
+    col0 = s == "desc_conv1" ? 0 : 256;
+  } else if (s == "det_logits") {
+    HFB_REQUIRE(ctx, lv.d_logits != nullptr, "det_logits are only kept with HFB_DEBUG=1");
+    d[1] = Hd; d[2] = Wd; d[3] = 65;
+    fsrc = lv.d_logits + (size_t)image_index * Hd * Wd * 65;
+  } else if (s == "scores_dense" || s == "scores_dense_nms") {
+    d[1] = lv.H8; d[2] = lv.W8; d[3] = 1;
+    fsrc = (s == "scores_dense" ? lv.d_scores : lv.d_nms) + (size_t)image_index * lv.H8 * lv.W8;
+  } else if (s == "local_descriptor_map") {
+    d[1] = Hd; d[2] = Wd; d[3] = 256;
+    fsrc = lv.d_descmap + (size_t)image_index * Hd * Wd * 256;
+  } else if (s == "vlad_norm") {
+    HFB_REQUIRE(ctx, lv.global, "no global head on this level");
+    d[1] = 1; d[2] = 1; d[3] = ctx->net.n_clusters * ctx->net.c_global;
+    fsrc = lv.d_vladn + (size_t)image_index * d[3];
+  } else if (s == "global_descriptor") {
+    HFB_REQUIRE(ctx, lv.global, "no global head on this level");
+    d[1] = 1; d[2] = 1; d[3] = HFB_GLOBAL_DIM;
+    fsrc = ctx->d_global + (size_t)image_index * HFB_GLOBAL_DIM;
+  } else {
+    ctx->set_error("unknown tensor name: " + s);
+    return HFB_ERR_INVALID;
+  }
+  const size_t cnt = (size_t)d[1] * d[2] * d[3];
+  *n = cnt;
+  for (int i = 0; i < 4; ++i) dims4[i] = d[i];
+  HFB_REQUIRE(ctx, out && cap >= cnt, "output buffer too small");
+  if (hsrc) {
+    HFB_TRY(ctx->ensure_scratch(cnt * 4));
+    float* tmp = reinterpret_cast<float*>(ctx->d_scratch);
+    h2f_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(hsrc, ld, col0, d[3], tmp,
+                                                                      (long long)d[1] * d[2]);
+    HFB_CHECK_LAUNCH(ctx, "h2f");
+    fsrc = tmp;
+  }
+  HFB_CUDA(ctx, cudaMemcpyAsync(out, fsrc, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
+}
+
+// ================================================================================================ matching
+extern "C" int hfb_match_batch_dev(hfb_ctx* ctx, int32_t mode, const float* dA_all, int32_t na_total,
+                                   const float* dB_all, int32_t nb_total, int32_t n_pairs, const int32_t* d_pair_tab,
+                                   int32_t max_a_cnt, int32_t max_b_cnt, float thr, int32_t* d_match_idx,
+                                   float* d_match_val) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (l2) or 1 (cos)");
+  HFB_REQUIRE(ctx, dA_all && dB_all && d_pair_tab && d_match_idx && d_match_val, "null argument");
+  HFB_REQUIRE(ctx, na_total >= 0 && nb_total >= 0 && n_pairs >= 0 && max_a_cnt >= 0 && max_b_cnt >= 0, "negative size");
+  return launch_match_batch(ctx, mode, dA_all, dB_all, n_pairs, d_pair_tab, max_a_cnt, max_b_cnt, thr, d_match_idx,
+                            d_match_val, na_total, nb_total, nullptr);
+}
+
+static int match_host(hfb_ctx* ctx, int mode, const float* A_all, int na_total, const float* B_all, int nb_total,
+                      int n_pairs, const int32_t* a_off, const int32_t* a_cnt, const int32_t* b_off,
+                      const int32_t* b_cnt, float thr, int32_t* match_idx, float* match_val, int32_t* n_matches) {
+  HFB_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (l2) or 1 (cos)");
+  HFB_REQUIRE(ctx, na_total >= 0 && nb_total >= 0 && n_pairs >= 0, "negative size");
+  int max_a = 0, max_b = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    HFB_REQUIRE(ctx, a_off[p] >= 0 && a_cnt[p] >= 0 && a_off[p] + a_cnt[p] <= na_total && b_off[p] >= 0 &&
+                         b_cnt[p] >= 0 && b_off[p] + b_cnt[p] <= nb_total,
+                "pair range outside the descriptor arrays");
+    max_a = std::max(max_a, a_cnt[p]);
+    max_b = std::max(max_b, b_cnt[p]);
+  }
+  for (int i = 0; i < na_total; ++i) {
+    match_idx[i] = -1;
+    match_val[i] = 0.f;
+  }
+  if (n_matches)
+    for (int p = 0; p < n_pairs; ++p) n_matches[p] = 0;
+  if (na_total == 0 || nb_total == 0 || n_pairs == 0 || max_a == 0 || max_b == 0) return HFB_OK;
+  // device buffers: A | B | idx | val | tab   (separate from ctx scratch, which launch_match_batch uses)
+  float *dA = nullptr, *dB = nullptr, *dV = nullptr;
+  int *dI = nullptr, *dT = nullptr;
+  int rc = HFB_OK;
+  cudaError_t e = cudaSuccess;
+  auto done = [&]() {
+    cudaFree(dA); cudaFree(dB); cudaFree(dV); cudaFree(dI); cudaFree(dT);
+  };
+#define M_CUDA(expr)                                                       \
+  do {                                                                     \
+    e = (expr);                                                            \
+    if (e != cudaSuccess) {                                                \
+      ctx->set_error(std::string(#expr) + ": " + cudaGetErrorString(e));   \
+      done();                                                              \
+      return HFB_ERR_CUDA;                                                 \
+    }                                                                      \
+  } while (0)
+  M_CUDA(cudaMalloc(&dA, (size_t)na_total * 256 * 4));
+  M_CUDA(cudaMalloc(&dB, (size_t)nb_total * 256 * 4));
+  M_CUDA(cudaMalloc(&dV, (size_t)na_total * 4));
+  M_CUDA(cudaMalloc(&dI, (size_t)na_total * 4));
+  M_CUDA(cudaMalloc(&dT, (size_t)n_pairs * 16));
+  std::vector<int> tab((size_t)4 * n_pairs);
+  for (int p = 0; p < n_pairs; ++p) {
+    tab[p] = a_off[p];
+    tab[n_pairs + p] = a_cnt[p];
+    tab[2 * n_pairs + p] = b_off[p];
+    tab[3 * n_pairs + p] = b_cnt[p];
+  }
+  M_CUDA(cudaMemcpyAsync(dA, A_all, (size_t)na_total * 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  M_CUDA(cudaMemcpyAsync(dB, B_all, (size_t)nb_total * 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  M_CUDA(cudaMemcpyAsync(dT, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  M_CUDA(cudaMemsetAsync(dI, 0xFF, (size_t)na_total * 4, ctx->stream));
+  M_CUDA(cudaMemsetAsync(dV, 0, (size_t)na_total * 4, ctx->stream));
+  int* d_nm = nullptr;
+  rc = launch_match_batch(ctx, mode, dA, dB, n_pairs, dT, max_a, max_b, thr, dI, dV, na_total, nb_total, &d_nm);
+  if (rc == HFB_OK) {
+    M_CUDA(cudaMemcpyAsync(match_idx, dI, (size_t)na_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    M_CUDA(cudaMemcpyAsync(match_val, dV, (size_t)na_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_matches && d_nm)
+      M_CUDA(cudaMemcpyAsync(n_matches, d_nm, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    M_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  done();
+  return rc;
+#undef M_CUDA
+}
+
+extern "C" int hfb_match_batch(hfb_ctx* ctx, int32_t mode, const float* A_all, int32_t na_total, const float* B_all,
+                               int32_t nb_total, int32_t n_pairs, const int32_t* a_off, const int32_t* a_cnt,
+                               const int32_t* b_off, const int32_t* b_cnt, float thr, int32_t* match_idx,
+                               float* match_val) {
+  if (!ctx) return HFB_ERR_INVALID;
+  return match_host(ctx, mode, A_all, na_total, B_all, nb_total, n_pairs, a_off, a_cnt, b_off, b_cnt, thr, match_idx,
+                    match_val, nullptr);
+}
+
+static int match_single(hfb_ctx* ctx, int mode, const float* A, int na, const float* B, int nb, float thr,
+                        int32_t* match_idx, float* match_val, int32_t* n_matches) {
+  const int32_t z = 0;
+  int32_t nm = 0;
+  int rc = match_host(ctx, mode, A, na, B, nb, 1, &z, &na, &z, &nb, thr, match_idx, match_val, &nm);
+  if (n_matches) *n_matches = nm;
+  return rc;
+}
+extern "C" int hfb_match_mutual_l2(hfb_ctx* ctx, const float* A, int32_t na, const float* B, int32_t nb,
+                                   float max_dist, int32_t* match_idx, float* match_val, int32_t* n_matches) {
+  if (!ctx) return HFB_ERR_INVALID;
+  return match_single(ctx, 0, A, na, B, nb, max_dist, match_idx, match_val, n_matches);
+}
+extern "C" int hfb_match_mutual_cos(hfb_ctx* ctx, const float* A, int32_t na, const float* B, int32_t nb, float min_cos,
+                                    int32_t* match_idx, float* match_val, int32_t* n_matches) {
+  if (!ctx) return HFB_ERR_INVALID;
+  return match_single(ctx, 1, A, na, B, nb, min_cos, match_idx, match_val, n_matches);
+}

@@ -1,0 +1,488 @@
+// HF-Net encoder forward on sm_100a (replaces the TensorRT engine of src/Extractors/HFNetRTModel.cc:122-137,208-254).
+// Graph specification: hfnet/models/hf_net.py:13-104,184-237 (MobileNetV2 x0.75 backbone, local head) and
+// hfnet/models/utils/layers.py:57-109 (NetVLAD + dimensionality reduction); BatchNorm folded at weight-load time.
+//
+// Data layout in HBM: activations NHWC fp16 [B][H][W][C] (C multiple of 8 -> 16-byte channel vectors), weights
+// fp16 [Cout][K] K-major (UMMA B operand), fp32 accumulation everywhere, fp32 score / descriptor maps.
+// 1x1 convolutions and the 3x3 head convolutions run on the tcgen05 GEMM (gemm_core.cuh); the first 3x3/2
+// convolution (1 input channel) and the depthwise 3x3 convolutions are bandwidth-bound CUDA-core kernels.
+#include "common.cuh"
+#include "gemm_core.cuh"
+
+int gemm_store(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, int B, void* out,
+               int ldo, int col_off, const float* bias, const __half* residual, int ldr, int relu6, int f32);
+int gemm_l2norm(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* out,
+                const float* bias);
+int gemm_softmax_d2s(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* scores,
+                     float* logits, const float* bias, int Hc, int Wc);
+
+// TensorFlow 'SAME' padding before the first element (asymmetric on stride 2, SURVEY.md section 7 "hard parts").
+static inline int same_pad_before(int n, int k, int s) {
+  const int out = (n + s - 1) / s;
+  int total = (out - 1) * s + k - n;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+// ----------------------------------------------------------------------------------------------- conv1 (layer_1)
+// u8 image -> (x-128)/128 -> 3x3 stride-2 SAME conv to C1 channels + bias + ReLU6 (hf_net.py:185-190,30).
+// One thread = one output pixel x 8 channels.
+__global__ void conv1_kernel(const uint8_t* __restrict__ img, int img_h, int img_w, int H8, int W8,
+                             const float* __restrict__ w, const float* __restrict__ bias, int C1,
+                             __half* __restrict__ out, int Ho, int Wo, int pad_t, int pad_l, long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int groups = C1 >> 3;
+  const int cg = (int)(gid % groups);
+  long long p = gid / groups;
+  const int ox = (int)(p % Wo);
+  p /= Wo;
+  const int oy = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  const uint8_t* src = img + (size_t)b * img_h * img_w;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + cg * 8 + j);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 + ky - pad_t;
+    if (iy < 0 || iy >= H8) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 + kx - pad_l;
+      if (ix < 0 || ix >= W8) continue;
+      const float v = ((float)src[(size_t)iy * img_w + ix] - 128.f) * (1.f / 128.f);
+      const float* wp = w + (ky * 3 + kx) * C1 + cg * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, __ldg(wp + j), acc[j]);
+    }
+  }
+  uint4 q;
+  __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    hq[j] = __floats2half2_rn(fminf(fmaxf(acc[2 * j], 0.f), 6.f), fminf(fmaxf(acc[2 * j + 1], 0.f), 6.f));
+  *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C1 + cg * 8) = q;
+}
+
+// ----------------------------------------------------------------------------------------------- depthwise 3x3
+// NHWC fp16 -> NHWC fp16, + bias + ReLU6 (conv_blocks.py:272-286).  One thread = one output pixel x 8 channels.
+__global__ void dw3x3_kernel(const __half* __restrict__ in, int Hi, int Wi, int C, const float* __restrict__ w,
+                             const float* __restrict__ bias, __half* __restrict__ out, int Ho, int Wo, int stride,
+                             int pad_t, int pad_l, long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int groups = C >> 3;
+  const int cg = (int)(gid % groups);
+  long long p = gid / groups;
+  const int ox = (int)(p % Wo);
+  p /= Wo;
+  const int oy = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  float acc[8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cg * 8) + 1);
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+  const __half* src = in + (size_t)b * Hi * Wi * C + cg * 8;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * stride + ky - pad_t;
+    if (iy < 0 || iy >= Hi) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * stride + kx - pad_l;
+      if (ix < 0 || ix >= Wi) continue;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)iy * Wi + ix) * C));
+      const __half2* hq = reinterpret_cast<const __half2*>(&q);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + cg * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + cg * 8) + 1);
+      float2 f;
+      f = __half22float2(hq[0]); acc[0] = fmaf(f.x, w0.x, acc[0]); acc[1] = fmaf(f.y, w0.y, acc[1]);
+      f = __half22float2(hq[1]); acc[2] = fmaf(f.x, w0.z, acc[2]); acc[3] = fmaf(f.y, w0.w, acc[3]);
+      f = __half22float2(hq[2]); acc[4] = fmaf(f.x, w1.x, acc[4]); acc[5] = fmaf(f.y, w1.y, acc[5]);
+      f = __half22float2(hq[3]); acc[6] = fmaf(f.x, w1.z, acc[6]); acc[7] = fmaf(f.y, w1.w, acc[7]);
+    }
+  }
+  uint4 q;
+  __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    hq[j] = __floats2half2_rn(fminf(fmaxf(acc[2 * j], 0.f), 6.f), fminf(fmaxf(acc[2 * j + 1], 0.f), 6.f));
+  *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + cg * 8) = q;
+}
+
+// ----------------------------------------------------------------------------------------------- NetVLAD
+// (1) memberships: 1x1 conv D -> C + folded BN, softmax over clusters (layers.py:66-71).  Warp = 4 pixels, lane = cluster.
+__global__ void vlad_memberships_kernel(const __half* __restrict__ x, int P, int D, int C, const float* __restrict__ w,
+                                        const float* __restrict__ bias, float* __restrict__ memb) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 4;
+  if (p0 >= P) return;
+  for (int cb = 0; cb < C; cb += 32) {
+    const int c = cb + lane;
+    float acc[4];
+    const float bb = c < C ? __ldg(bias + c) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = bb;
+    const __half* xp = x + ((size_t)b * P + p0) * D;
+    for (int d = 0; d < D; ++d) {
+      const float wv = c < C ? __ldg(w + (size_t)d * C + c) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (p0 + q < P) acc[q] = fmaf(__half2float(xp[(size_t)q * D + d]), wv, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (p0 + q < P && c < C) memb[((size_t)b * P + p0 + q) * C + c] = acc[q];
+  }
+  __syncwarp();
+  // softmax over the C logits of each pixel (C <= 64: each lane holds up to 2)
+  for (int q = 0; q < 4; ++q) {
+    if (p0 + q >= P) break;
+    float* m = memb + ((size_t)b * P + p0 + q) * C;
+    float v0 = lane < C ? m[lane] : -INFINITY, v1 = lane + 32 < C ? m[lane + 32] : -INFINITY;
+    float mx = fmaxf(v0, v1);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    v0 = lane < C ? expf(v0 - mx) : 0.f;
+    v1 = lane + 32 < C ? expf(v1 - mx) : 0.f;
+    float sum = v0 + v1;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    const float inv = 1.f / sum;
+    if (lane < C) m[lane] = v0 * inv;
+    if (lane + 32 < C) m[lane + 32] = v1 * inv;
+  }
+}
+
+// (2) V[c][d] = (sum_p m[p][c]) * centroid[c][d] - sum_p m[p][c] * x[p][d]   (layers.py:81-86: clusters - x)
+__global__ void vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ memb, int P, int D, int C,
+                                      const float* __restrict__ clusters, float* __restrict__ vlad) {
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* m = memb + (size_t)b * P * C + c;
+  const __half* xb = x + (size_t)b * P * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f, msum = 0.f;
+    for (int p = 0; p < P; ++p) {
+      const float mv = __ldg(m + (size_t)p * C);
+      msum += mv;
+      acc = fmaf(mv, __half2float(xb[(size_t)p * D + d]), acc);
+    }
+    vlad[((size_t)b * C + c) * D + d] = msum * __ldg(clusters + (size_t)c * D + d) - acc;
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+// (3) intra-normalisation over the CLUSTER axis (layers.py:87-88, restated literally), flatten [C*D], L2-normalise
+//     (layers.py:89-90) and the L2-normalise at the top of the dimensionality reduction (layers.py:97).
+__global__ void vlad_normalize_kernel(const float* __restrict__ vlad, int C, int D, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* v = vlad + (size_t)b * C * D;
+  float* o = out + (size_t)b * C * D;
+  float ss = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(v[(size_t)c * D + d], v[(size_t)c * D + d], s);
+    const float inv = rsqrtf(fmaxf(s, 1e-12f));
+    for (int c = 0; c < C; ++c) {
+      const float t = v[(size_t)c * D + d] * inv;
+      o[(size_t)c * D + d] = t;
+      ss = fmaf(t, t, ss);
+    }
+  }
+  float tot = block_sum(ss, red);
+  const float inv1 = rsqrtf(fmaxf(tot, 1e-12f));
+  float ss2 = 0.f;
+  for (int i = threadIdx.x; i < C * D; i += blockDim.x) {
+    const float t = o[i] * inv1;
+    o[i] = t;
+    ss2 = fmaf(t, t, ss2);
+  }
+  tot = block_sum(ss2, red);
+  const float inv2 = rsqrtf(fmaxf(tot, 1e-12f));
+  for (int i = threadIdx.x; i < C * D; i += blockDim.x) o[i] *= inv2;
+}
+
+// (4) FC K -> 4096 (layers.py:99-107): split-K GEMV over the fp16 weight [K][4096]; each thread owns 8 columns.
+#define FC_BCH 4
+__global__ void __launch_bounds__(256) fc_partial_kernel(const float* __restrict__ v, int K, int B,
+                                                         const __half* __restrict__ w, int N, int k_per_split,
+                                                         float* __restrict__ partial) {
+  extern __shared__ float s_v[];  // [FC_BCH][k_per_split]
+  const int ks = blockIdx.y;
+  const int k0 = ks * k_per_split;
+  const int kn = min(k_per_split, K - k0);
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  for (int b0 = 0; b0 < B; b0 += FC_BCH) {
+    const int nb = min(FC_BCH, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < FC_BCH * k_per_split; i += blockDim.x) {
+      const int bb = i / k_per_split, kk = i - bb * k_per_split;
+      s_v[i] = (bb < nb && kk < kn) ? v[(size_t)(b0 + bb) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+    if (n < N && kn > 0) {
+      float acc[FC_BCH][8];
+#pragma unroll
+      for (int bb = 0; bb < FC_BCH; ++bb)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[bb][j] = 0.f;
+      const __half* wp = w + (size_t)k0 * N + n;
+#pragma unroll 4
+      for (int kk = 0; kk < kn; ++kk) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)kk * N));
+        const __half2* hq = reinterpret_cast<const __half2*>(&q);
+        float wf[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(hq[j]);
+          wf[2 * j] = f.x;
+          wf[2 * j + 1] = f.y;
+        }
+#pragma unroll
+        for (int bb = 0; bb < FC_BCH; ++bb) {
+          const float xv = s_v[bb * k_per_split + kk];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[bb][j] = fmaf(xv, wf[j], acc[bb][j]);
+        }
+      }
+      for (int bb = 0; bb < nb; ++bb) {
+        float* o = partial + ((size_t)(b0 + bb) * gridDim.y + ks) * N + n;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[bb][0], acc[bb][1], acc[bb][2], acc[bb][3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[bb][4], acc[bb][5], acc[bb][6], acc[bb][7]);
+      }
+    }
+  }
+}
+
+__global__ void fc_finish_kernel(const float* __restrict__ partial, int n_split, int N, const float* __restrict__ bias,
+                                 float* __restrict__ out) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float ss = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float y = __ldg(bias + n);
+    for (int s = 0; s < n_split; ++s) y += partial[((size_t)b * n_split + s) * N + n];
+    out[(size_t)b * N + n] = y;
+    ss = fmaf(y, y, ss);
+  }
+  const float tot = block_sum(ss, red);
+  const float inv = rsqrtf(fmaxf(tot, 1e-12f));
+  for (int n = threadIdx.x; n < N; n += blockDim.x) out[(size_t)b * N + n] *= inv;
+}
+
+// =============================================================================================== plans
+// N tile: split N into the fewest equal tiles (multiples of 16, <= 256) that still give the machine enough CTAs.
+static int pick_bn(int M, int N, int n_sm) {
+  const int mt = (M + 127) / 128;
+  int bn = 16;
+  for (int t = 1; t <= 45; ++t) {
+    bn = ((N + t - 1) / t + 15) / 16 * 16;
+    if (bn > 256) continue;
+    if (mt * t >= n_sm || bn <= 64) break;
+  }
+  return bn;
+}
+
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  GemmGeom g;
+};
+struct BlockPlan {
+  GemmPlan expand, project;
+  int Hi, Wi, Ho, Wo, pad_t, pad_l;
+};
+struct LevelExec {
+  int H1, W1, pad_t1, pad_l1;
+  std::vector<BlockPlan> blocks;
+  GemmPlan head1, desc2, det2;
+  int Hd, Wd;  // descriptor grid = layer_7 size
+  int P, D;    // global endpoint pixels / channels
+  int fc_split, fc_kps;
+};
+
+static std::vector<LevelExec>& execs(hfb_ctx* ctx) {
+  static std::map<hfb_ctx*, std::vector<LevelExec>> m;
+  return m[ctx];
+}
+void encoder_forget(hfb_ctx* ctx) { execs(ctx).clear(); }
+
+static int make_plain(hfb_ctx* ctx, GemmPlan& gp, const void* A, int lda, int a_k_off, long long Mmax, const GemmW& w,
+                      int n_sm, int force_bn) {
+  const int bn = force_bn > 0 ? force_bn : pick_bn((int)Mmax, w.N, n_sm);
+  HFB_TRY(hfb_make_tmap_2d(ctx, &gp.tmA, A, (uint64_t)lda, (uint64_t)Mmax, (uint64_t)lda * 2, 128));
+  HFB_TRY(hfb_make_tmap_2d(ctx, &gp.tmB, w.w, (uint64_t)w.Kp, (uint64_t)w.N, (uint64_t)w.Kp * 2, (uint32_t)bn));
+  gemm_fill_geom(gp.g, (int)Mmax, w.N, w.K, bn, a_k_off);
+  return HFB_OK;
+}
+
+// Allocates the activation buffers of every level and builds all tensor maps.  Called once weights are loaded.
+int encoder_plan(hfb_ctx* ctx) {
+  const NetW& net = ctx->net;
+  const int Bm = ctx->cfg.max_batch;
+  std::vector<LevelExec>& ex = execs(ctx);
+  ex.clear();
+  ex.resize(ctx->n_levels);
+  for (int l = 0; l < ctx->n_levels; ++l) {
+    LevelPlan& lv = ctx->lv[l];
+    LevelExec& le = ex[l];
+    const int n_layers = lv.global ? 18 : 7;
+    lv.n_act = n_layers;
+    // layer_1
+    le.H1 = (lv.H8 + 1) / 2;
+    le.W1 = (lv.W8 + 1) / 2;
+    le.pad_t1 = same_pad_before(lv.H8, 3, 2);
+    le.pad_l1 = same_pad_before(lv.W8, 3, 2);
+    lv.aH[1] = le.H1; lv.aW[1] = le.W1; lv.aC[1] = net.c1;
+    HFB_TRY(ctx->dalloc(&lv.act[1], (size_t)Bm * le.H1 * le.W1 * net.c1));
+    size_t max_exp = 0, max_dw = 0;
+    for (const BlockW& bw : net.blocks) {
+      if (bw.layer > n_layers) break;
+      const int Hi = lv.aH[bw.layer - 1], Wi = lv.aW[bw.layer - 1];
+      const int Ho = (Hi + bw.stride - 1) / bw.stride, Wo = (Wi + bw.stride - 1) / bw.stride;
+      lv.aH[bw.layer] = Ho; lv.aW[bw.layer] = Wo; lv.aC[bw.layer] = bw.cout;
+      HFB_TRY(ctx->dalloc(&lv.act[bw.layer], (size_t)Bm * Ho * Wo * bw.cout));
+      if (bw.has_expand) max_exp = std::max(max_exp, (size_t)Bm * Hi * Wi * bw.cexp);
+      max_dw = std::max(max_dw, (size_t)Bm * Ho * Wo * bw.cexp);
+    }
+    HFB_TRY(ctx->dalloc(&lv.d_exp, max_exp));
+    HFB_TRY(ctx->dalloc(&lv.d_dw, max_dw));
+    for (const BlockW& bw : net.blocks) {
+      if (bw.layer > n_layers) break;
+      BlockPlan bp;
+      bp.Hi = lv.aH[bw.layer - 1]; bp.Wi = lv.aW[bw.layer - 1];
+      bp.Ho = lv.aH[bw.layer]; bp.Wo = lv.aW[bw.layer];
+      bp.pad_t = same_pad_before(bp.Hi, 3, bw.stride);
+      bp.pad_l = same_pad_before(bp.Wi, 3, bw.stride);
+      const long long Min = (long long)Bm * bp.Hi * bp.Wi, Mout = (long long)Bm * bp.Ho * bp.Wo;
+      if (bw.has_expand)
+        HFB_TRY(make_plain(ctx, bp.expand, lv.act[bw.layer - 1], bw.cin, 0, Min, bw.expand, ctx->n_sm, 0));
+      HFB_TRY(make_plain(ctx, bp.project, lv.d_dw, bw.cexp, 0, Mout, bw.project, ctx->n_sm, 0));
+      le.blocks.push_back(bp);
+    }
+    // local head on layer_7
+    le.Hd = lv.aH[7]; le.Wd = lv.aW[7];
+    const int Cl = lv.aC[7];
+    const long long M7 = (long long)Bm * le.Hd * le.Wd;
+    HFB_TRY(ctx->dalloc(&lv.d_head1, (size_t)M7 * net.head1.N));
+    HFB_TRY(ctx->dalloc(&lv.d_descmap, (size_t)M7 * 256));
+    HFB_TRY(ctx->dalloc(&lv.d_scores, (size_t)Bm * lv.H8 * lv.W8));
+    HFB_TRY(ctx->dalloc(&lv.d_nms, (size_t)Bm * lv.H8 * lv.W8));
+    if (ctx->debug) HFB_TRY(ctx->dalloc(&lv.d_logits, (size_t)M7 * 65));
+    HFB_TRY(hfb_make_tmap_nhwc(ctx, &le.head1.tmA, lv.act[7], Cl, le.Wd, le.Hd, Bm));
+    HFB_TRY(hfb_make_tmap_2d(ctx, &le.head1.tmB, net.head1.w, (uint64_t)net.head1.Kp, (uint64_t)net.head1.N,
+                             (uint64_t)net.head1.Kp * 2, 128));
+    gemm_fill_geom_conv(le.head1.g, Bm, le.Hd, le.Wd, Cl, net.head1.N, 128);
+    HFB_TRY(make_plain(ctx, le.desc2, lv.d_head1, net.head1.N, 0, M7, net.desc2, ctx->n_sm, 256));
+    HFB_TRY(make_plain(ctx, le.det2, lv.d_head1, net.head1.N, 256, M7, net.det2, ctx->n_sm, 80));
+    if (le.Hd * 8 != lv.H8 || le.Wd * 8 != lv.W8) {
+      ctx->set_error("internal: layer_7 grid is not H8/8 x W8/8");
+      return HFB_ERR_STATE;
+    }
+    // candidates / selection
+    HFB_TRY(ctx->dalloc(&lv.d_cand, (size_t)Bm * ctx->cand_cap));
+    HFB_TRY(ctx->dalloc(&lv.d_cand_count, (size_t)Bm));
+    // global head
+    if (lv.global) {
+      le.P = lv.aH[18] * lv.aW[18];
+      le.D = lv.aC[18];
+      const int C = net.n_clusters, K = C * le.D;
+      HFB_TRY(ctx->dalloc(&lv.d_memb, (size_t)Bm * le.P * C));
+      HFB_TRY(ctx->dalloc(&lv.d_vlad, (size_t)Bm * K));
+      HFB_TRY(ctx->dalloc(&lv.d_vladn, (size_t)Bm * K));
+      le.fc_split = std::max(1, ctx->n_sm / 2);
+      le.fc_kps = (K + le.fc_split - 1) / le.fc_split;
+      le.fc_split = (K + le.fc_kps - 1) / le.fc_kps;
+      HFB_TRY(ctx->dalloc(&lv.d_fc_partial, (size_t)Bm * le.fc_split * HFB_GLOBAL_DIM));
+    }
+  }
+  return HFB_OK;
+}
+
+static int run_plain(hfb_ctx* ctx, const GemmPlan& gp, long long M, void* out, int ldo, const float* bias,
+                     const __half* residual, int ldr, int relu6) {
+  GemmGeom g = gp.g;
+  g.M = (int)M;
+  return gemm_store(ctx, gp.tmA, gp.tmB, g, 1, out, ldo, 0, bias, residual, ldr, relu6, 0);
+}
+
+// Forward of one pyramid level for `B` frames whose u8 images are in lv.d_img.  Produces d_scores, d_nms (no
+// selection), d_descmap and (level 0) the global descriptors.
+int encoder_forward(hfb_ctx* ctx, int level, int B) {
+  const NetW& net = ctx->net;
+  LevelPlan& lv = ctx->lv[level];
+  LevelExec& le = execs(ctx)[level];
+  {
+    const long long total = (long long)B * le.H1 * le.W1 * (net.c1 / 8);
+    conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+        lv.d_img, lv.H, lv.W, lv.H8, lv.W8, net.conv1_w, net.conv1_b, net.c1, lv.act[1], le.H1, le.W1, le.pad_t1,
+        le.pad_l1, total);
+    HFB_CHECK_LAUNCH(ctx, "conv1");
+  }
+  size_t bi = 0;
+  for (const BlockW& bw : net.blocks) {
+    if (bw.layer > lv.n_act) break;
+    const BlockPlan& bp = le.blocks[bi++];
+    const __half* in = lv.act[bw.layer - 1];
+    const __half* dw_in = in;
+    const long long Min = (long long)B * bp.Hi * bp.Wi, Mout = (long long)B * bp.Ho * bp.Wo;
+    if (bw.has_expand) {
+      HFB_TRY(run_plain(ctx, bp.expand, Min, lv.d_exp, bw.cexp, bw.expand.b, nullptr, 0, 1));
+      dw_in = lv.d_exp;
+    }
+    const long long total = Mout * (bw.cexp / 8);
+    dw3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+        dw_in, bp.Hi, bp.Wi, bw.cexp, bw.wd, bw.bd, lv.d_dw, bp.Ho, bp.Wo, bw.stride, bp.pad_t, bp.pad_l, total);
+    HFB_CHECK_LAUNCH(ctx, "dw3x3");
+    HFB_TRY(run_plain(ctx, bp.project, Mout, lv.act[bw.layer], bw.cout, bw.project.b,
+                      bw.residual ? in : nullptr, bw.cin, 0));
+  }
+  // local head (hf_net.py:74-93)
+  {
+    GemmGeom g = le.head1.g;
+    g.M = B * le.Hd * le.Wd;
+    HFB_TRY(gemm_store(ctx, le.head1.tmA, le.head1.tmB, g, B, lv.d_head1, net.head1.N, 0, net.head1.b, nullptr, 0, 1, 0));
+    GemmGeom gd = le.desc2.g;
+    gd.M = g.M;
+    HFB_TRY(gemm_l2norm(ctx, le.desc2.tmA, le.desc2.tmB, gd, lv.d_descmap, net.desc2.b));
+    GemmGeom gt = le.det2.g;
+    gt.M = g.M;
+    HFB_TRY(gemm_softmax_d2s(ctx, le.det2.tmA, le.det2.tmB, gt, lv.d_scores, lv.d_logits, net.det2.b, le.Hd, le.Wd));
+  }
+  HFB_TRY(launch_nms(ctx, lv.d_scores, lv.d_nms, lv.H8, lv.W8, B));
+  if (lv.global) {
+    const int C = net.n_clusters, K = C * le.D;
+    dim3 g1(ceil_div(le.P, 8 * 4), B);
+    vlad_memberships_kernel<<<g1, 256, 0, ctx->stream>>>(lv.act[18], le.P, le.D, C, net.vlad_w, net.vlad_b, lv.d_memb);
+    HFB_CHECK_LAUNCH(ctx, "vlad_memberships");
+    dim3 g2(C, B);
+    vlad_aggregate_kernel<<<g2, 256, 0, ctx->stream>>>(lv.act[18], lv.d_memb, le.P, le.D, C, net.vlad_c, lv.d_vlad);
+    HFB_CHECK_LAUNCH(ctx, "vlad_aggregate");
+    vlad_normalize_kernel<<<B, 256, 0, ctx->stream>>>(lv.d_vlad, C, le.D, lv.d_vladn);
+    HFB_CHECK_LAUNCH(ctx, "vlad_normalize");
+    dim3 g3(ceil_div(HFB_GLOBAL_DIM, 256 * 8), le.fc_split);
+    const size_t smem = (size_t)FC_BCH * le.fc_kps * sizeof(float);
+    fc_partial_kernel<<<g3, 256, smem, ctx->stream>>>(lv.d_vladn, K, B, net.fc_w, HFB_GLOBAL_DIM, le.fc_kps,
+                                                      lv.d_fc_partial);
+    HFB_CHECK_LAUNCH(ctx, "fc_partial");
+    fc_finish_kernel<<<B, 1024, 0, ctx->stream>>>(lv.d_fc_partial, le.fc_split, HFB_GLOBAL_DIM, net.fc_b, ctx->d_global);
+    HFB_CHECK_LAUNCH(ctx, "fc_finish");
+  }
+  return HFB_OK;
+}

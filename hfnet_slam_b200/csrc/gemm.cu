@@ -1,0 +1,351 @@
+// Tensor-map construction, the store / L2-normalise / softmax+depth_to_space epilogues of the HF-Net encoder GEMMs
+// and their launchers (kernel template in gemm_core.cuh).
+#include "common.cuh"
+#include "gemm_core.cuh"
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode(hfb_ctx* ctx) {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    ctx->set_error("cuTensorMapEncodeTiled entry point not available");
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// fp16 [outer][inner] matrix, rows `row_stride_bytes` apart; box = 64 (inner) x box_outer, 128B swizzle, OOB -> 0.
+int hfb_make_tmap_2d(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                     uint64_t row_stride_bytes, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode(ctx);
+  if (!enc) return HFB_ERR_CUDA;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctx->set_error("cuTensorMapEncodeTiled(2d) failed: code " + std::to_string((int)r) + " inner " +
+                   std::to_string(inner) + " outer " + std::to_string(outer) + " stride " +
+                   std::to_string(row_stride_bytes) + " box_outer " + std::to_string(box_outer));
+    return HFB_ERR_CUDA;
+  }
+  return HFB_OK;
+}
+
+// fp16 NHWC tensor viewed as (C, W, H, B); box = 64 channels x 16 x 8 x 1 (one 128-pixel patch).
+int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B) {
+  PFN_encodeTiled enc = get_encode(ctx);
+  if (!enc) return HFB_ERR_CUDA;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint32_t box[4] = {64, 16, 8, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctx->set_error("cuTensorMapEncodeTiled(4d) failed: code " + std::to_string((int)r));
+    return HFB_ERR_CUDA;
+  }
+  return HFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ epilogues
+// bias (+ReLU6) (+residual) -> fp16 or fp32 rows.
+struct EpiStore {
+  struct Params {
+    void* out;
+    int ldo;        // elements per output row
+    int col_off;    // first output column of this GEMM inside the row
+    const float* bias;
+    const __half* residual;  // [row][ldr] or null
+    int ldr;
+    int relu6;
+    int f32;
+  };
+  static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
+    for (int c0 = 0; c0 < g.BN; c0 += 16) {
+      uint32_t r[16];
+      tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
+      tc::tmem_ld_wait();
+      const int n = tr.n0 + c0;
+      if (!tr.valid || n >= g.N) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float b = (n + j < g.N && p.bias) ? __ldg(p.bias + n + j) : 0.f;
+        v[j] = __uint_as_float(r[j]) + b;
+        if (p.relu6) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int nn = n + 8 * h;
+        if (nn + 8 > g.N) break;
+        if (p.residual) {
+          const uint4 q = *reinterpret_cast<const uint4*>(p.residual + tr.row * p.ldr + nn);
+          const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(hq[j]);
+            v[8 * h + 2 * j] += f.x;
+            v[8 * h + 2 * j + 1] += f.y;
+          }
+        }
+        if (p.f32) {
+          float* o = reinterpret_cast<float*>(p.out) + tr.row * p.ldo + p.col_off + nn;
+          *reinterpret_cast<float4*>(o) = make_float4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
+        } else {
+          uint4 q;
+          __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + tr.row * p.ldo + p.col_off + nn) = q;
+        }
+      }
+    }
+  }
+};
+
+// Descriptor head tail (hfnet/models/hf_net.py:78-80): + bias, tf.nn.l2_normalize over the 256 channels, fp32 rows.
+// The whole row lives in this thread's TMEM lane (BN == N == 256): two passes over TMEM, no cross-thread traffic.
+struct EpiL2Norm {
+  struct Params {
+    float* out;  // [row][N]
+    const float* bias;
+  };
+  static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
+    float ss = 0.f;
+    for (int c0 = 0; c0 < g.N; c0 += 16) {
+      uint32_t r[16];
+      tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v = __uint_as_float(r[j]) + __ldg(p.bias + c0 + j);
+        ss = fmaf(v, v, ss);
+      }
+    }
+    const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+    for (int c0 = 0; c0 < g.N; c0 += 16) {
+      uint32_t r[16];
+      tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
+      tc::tmem_ld_wait();
+      if (!tr.valid) continue;
+      float* o = p.out + tr.row * g.N + c0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 w;
+        w.x = (__uint_as_float(r[4 * q]) + __ldg(p.bias + c0 + 4 * q)) * inv;
+        w.y = (__uint_as_float(r[4 * q + 1]) + __ldg(p.bias + c0 + 4 * q + 1)) * inv;
+        w.z = (__uint_as_float(r[4 * q + 2]) + __ldg(p.bias + c0 + 4 * q + 2)) * inv;
+        w.w = (__uint_as_float(r[4 * q + 3]) + __ldg(p.bias + c0 + 4 * q + 3)) * inv;
+        *reinterpret_cast<float4*>(o + 4 * q) = w;
+      }
+    }
+  }
+};
+
+// Detector head tail (hfnet/models/hf_net.py:88-93): + bias, softmax over 65 logits, drop the dustbin channel,
+// depth_to_space(8): scores[8h+i][8w+j] = prob[h][w][8i+j].  Optionally keeps the raw logits (parity hook).
+struct EpiSoftmaxD2S {
+  struct Params {
+    float* scores;   // [B][Hc*8][Wc*8]
+    float* logits;   // [row][65] or null
+    const float* bias;
+    int Hc, Wc;
+  };
+  static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
+    float v[80];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      uint32_t r[16];
+      tc::tmem_ld16(tr.taddr + (uint32_t)(16 * c), r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[16 * c + j] = __uint_as_float(r[j]);
+    }
+    if (!tr.valid) return;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 65; ++j) {
+      v[j] += __ldg(p.bias + j);
+      mx = fmaxf(mx, v[j]);
+    }
+    if (p.logits) {
+      float* lo = p.logits + tr.row * 65;
+#pragma unroll
+      for (int j = 0; j < 65; ++j) lo[j] = v[j];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 65; ++j) {
+      v[j] = expf(v[j] - mx);
+      sum += v[j];
+    }
+    const float inv = 1.f / sum;
+    const int w = (int)(tr.row % p.Wc);
+    const long long t = tr.row / p.Wc;
+    const int h = (int)(t % p.Hc);
+    const long long b = t / p.Hc;
+    const int W8 = p.Wc * 8;
+    float* o = p.scores + (b * p.Hc * 8 + (long long)h * 8) * W8 + (long long)w * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      *reinterpret_cast<float4*>(o + (long long)i * W8) =
+          make_float4(v[8 * i] * inv, v[8 * i + 1] * inv, v[8 * i + 2] * inv, v[8 * i + 3] * inv);
+      *reinterpret_cast<float4*>(o + (long long)i * W8 + 4) =
+          make_float4(v[8 * i + 4] * inv, v[8 * i + 5] * inv, v[8 * i + 6] * inv, v[8 * i + 7] * inv);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ launchers
+template <class Epi>
+static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, int B,
+                     const typename Epi::Params& ep, const char* what) {
+  const size_t smem = gemm_smem_bytes(g.BN, g.stages);
+  static size_t configured = 0;  // per-instantiation
+  if (smem > configured) {
+    HFB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  gemm_tc_kernel<Epi><<<gemm_grid(g, B), 128, smem, ctx->stream>>>(tmA, tmB, g, ep);
+  HFB_CHECK_LAUNCH(ctx, what);
+  return HFB_OK;
+}
+
+int gemm_store(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, int B, void* out,
+               int ldo, int col_off, const float* bias, const __half* residual, int ldr, int relu6, int f32) {
+  EpiStore::Params p{out, ldo, col_off, bias, residual, ldr, relu6, f32};
+  return launch_tc<EpiStore>(ctx, tmA, tmB, g, B, p, "gemm_store");
+}
+int gemm_l2norm(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* out,
+                const float* bias) {
+  if (g.BN != g.N) {
+    ctx->set_error("gemm_l2norm needs BN == N");
+    return HFB_ERR_INVALID;
+  }
+  EpiL2Norm::Params p{out, bias};
+  return launch_tc<EpiL2Norm>(ctx, tmA, tmB, g, 1, p, "gemm_l2norm");
+}
+int gemm_softmax_d2s(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* scores,
+                     float* logits, const float* bias, int Hc, int Wc) {
+  if (g.N != 65 || g.BN != 80) {
+    ctx->set_error("gemm_softmax_d2s needs N == 65, BN == 80");
+    return HFB_ERR_INVALID;
+  }
+  EpiSoftmaxD2S::Params p{scores, logits, bias, Hc, Wc};
+  return launch_tc<EpiSoftmaxD2S>(ctx, tmA, tmB, g, 1, p, "gemm_softmax_d2s");
+}
+
+// ------------------------------------------------------------------------------------------------ debug / parity
+// CUDA-core restatement of the same contraction, used only by hfb_debug_gemm to cross-check the tensor-core path on
+// the device (never on the product path).
+__global__ void simt_gemm_kernel(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, int ldw, int M,
+                                 int N, int K, const float* __restrict__ bias, int relu6, float* __restrict__ out,
+                                 int conv, int H, int Wd) {
+  const int n = blockIdx.y * blockDim.x + threadIdx.x;
+  const long long m = blockIdx.x;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  if (!conv) {
+    for (int k = 0; k < K; ++k) acc = fmaf(__half2float(A[m * lda + k]), __half2float(Wt[(long long)n * ldw + k]), acc);
+  } else {
+    const int x = (int)(m % Wd);
+    const long long t = m / Wd;
+    const int y = (int)(t % H);
+    const long long b = t / H;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= Wd) continue;
+      const __half* a = A + ((b * H + yy) * Wd + xx) * (long long)K;
+      const __half* w = Wt + (long long)n * ldw + tap * K;
+      for (int k = 0; k < K; ++k) acc = fmaf(__half2float(a[k]), __half2float(w[k]), acc);
+    }
+  }
+  acc += bias ? bias[n] : 0.f;
+  if (relu6) acc = fminf(fmaxf(acc, 0.f), 6.f);
+  out[m * N + n] = acc;
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+
+extern "C" int hfb_debug_gemm(hfb_ctx* ctx, const float* A, int B, int H, int W, int K, const float* Wt, int N,
+                              const float* bias, int relu6, int conv3x3, int use_tc, int BN, float* out) {
+  // A: [B*H*W][K] (NHWC when conv3x3), Wt: [N][Kw] with Kw = conv3x3 ? 9*K : K.  out: [B*H*W][N] fp32.
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, K % 8 == 0 && N % 8 == 0, "hfb_debug_gemm: K and N must be multiples of 8");
+  const long long M = (long long)B * H * W;
+  const int Kw = conv3x3 ? 9 * K : K;
+  float *dAf = nullptr, *dWf = nullptr, *dB = nullptr, *dO = nullptr;
+  __half *dA = nullptr, *dW = nullptr;
+  int rc = HFB_OK;
+  auto cleanup = [&]() {
+    cudaFree(dAf); cudaFree(dWf); cudaFree(dB); cudaFree(dO); cudaFree(dA); cudaFree(dW);
+  };
+#define DBG_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ctx->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+      cleanup();                                                                    \
+      return HFB_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+  DBG_CUDA(cudaMalloc(&dAf, M * K * 4));
+  DBG_CUDA(cudaMalloc(&dWf, (size_t)N * Kw * 4));
+  DBG_CUDA(cudaMalloc(&dB, (size_t)N * 4));
+  DBG_CUDA(cudaMalloc(&dO, M * N * 4));
+  DBG_CUDA(cudaMalloc(&dA, M * K * 2));
+  DBG_CUDA(cudaMalloc(&dW, (size_t)N * Kw * 2));
+  DBG_CUDA(cudaMemcpyAsync(dAf, A, M * K * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DBG_CUDA(cudaMemcpyAsync(dWf, Wt, (size_t)N * Kw * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (bias) DBG_CUDA(cudaMemcpyAsync(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream));
+  f32_to_f16_kernel<<<(unsigned)((M * K + 255) / 256), 256, 0, ctx->stream>>>(dAf, dA, M * K);
+  f32_to_f16_kernel<<<(unsigned)(((long long)N * Kw + 255) / 256), 256, 0, ctx->stream>>>(dWf, dW, (long long)N * Kw);
+  DBG_CUDA(cudaMemsetAsync(dO, 0xFF, M * N * 4, ctx->stream));
+  if (use_tc) {
+    CUtensorMap tmA, tmB;
+    GemmGeom g;
+    if (BN <= 0) BN = ((N + 15) / 16) * 16 > 256 ? 128 : ((N + 15) / 16) * 16;
+    if (conv3x3) {
+      rc = hfb_make_tmap_nhwc(ctx, &tmA, dA, K, W, H, B);
+      gemm_fill_geom_conv(g, B, H, W, K, N, BN);
+    } else {
+      rc = hfb_make_tmap_2d(ctx, &tmA, dA, K, M, (uint64_t)K * 2, 128);
+      gemm_fill_geom(g, (int)M, N, K, BN, 0);
+    }
+    if (rc == HFB_OK) rc = hfb_make_tmap_2d(ctx, &tmB, dW, Kw, N, (uint64_t)Kw * 2, BN);
+    if (rc == HFB_OK) rc = gemm_store(ctx, tmA, tmB, g, B, dO, N, 0, bias ? dB : nullptr, nullptr, 0, relu6, 1);
+  } else {
+    dim3 grid((unsigned)M, (N + 127) / 128);
+    simt_gemm_kernel<<<grid, 128, 0, ctx->stream>>>(dA, K, dW, Kw, (int)M, N, K, bias ? dB : nullptr, relu6, dO,
+                                                    conv3x3, H, W);
+  }
+  if (rc == HFB_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, dO, M * N * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->set_error(std::string("hfb_debug_gemm: ") + cudaGetErrorString(e));
+      rc = HFB_ERR_CUDA;
+    }
+  }
+  cleanup();
+  return rc;
+#undef DBG_CUDA
+}

@@ -1,0 +1,685 @@
+// Local bundle adjustment numeric core on the GPU (fp64), replacing g2o's per-edge linearisation, Hessian assembly,
+// Schur complement and landmark back-substitution inside Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1116-1498):
+//
+//   residual / depth      include/OptimizableTypes.h:99-110, src/CameraModels/Pinhole.cpp:35-41
+//   Jacobians             src/OptimizableTypes.cpp:139-159, src/CameraModels/Pinhole.cpp:71-81
+//   Huber + quadratic form Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp:78-91, base_edge.h:96-102,
+//                          base_binary_edge.hpp:55-121
+//   Schur / back-subst.   Thirdparty/g2o/g2o/core/block_solver.hpp:354-486, setLambda :564-589
+//   Levenberg control     Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-185 (host loop below)
+//
+// Layout: edges sorted by point (SoA), so one thread owns one landmark and walks its contiguous edges: Hll / bl are
+// accumulated in registers in edge order; camera blocks Hpp / bp are summed per camera in a fixed edge order from a
+// camera-sorted edge list; the Schur complement is accumulated per CTA into private upper-triangular block buffers
+// (plain read-modify-write, one point at a time, entries of one point never collide) and reduced over CTAs in a fixed
+// order.  No floating-point atomics anywhere: results are bit-reproducible run to run.  Only the reduced 6n x 6n
+// camera system is factorised on the host (dense Cholesky; the reference uses sparse LDLT on the same system).
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+struct LbaDev {
+  int n_cams = 0, n_points = 0, n_edges = 0, n_opt = 0, n_blk = 0, G = 0;
+  double *poses = nullptr, *poses_t = nullptr, *points = nullptr, *points_t = nullptr;
+  int *edge_cam = nullptr, *pt_ptr = nullptr, *cam_ptr = nullptr, *cam_edges = nullptr, *cam_slot = nullptr,
+      *opt_cams = nullptr;
+  double *obs = nullptr, *invs2 = nullptr;
+  double *Jc = nullptr, *wo = nullptr, *r = nullptr, *Hpl = nullptr, *chi2_a = nullptr, *chi2_b = nullptr;
+  double *Hll = nullptr, *bl = nullptr, *Dinv = nullptr, *rho_pt = nullptr, *scale_pt = nullptr;
+  double *Hpp = nullptr, *bp = nullptr, *partial = nullptr, *Hs = nullptr, *bs = nullptr, *xp = nullptr;
+  double* scal = nullptr;  // [4]: chi, max diag, trial chi, scale_l
+  unsigned char* depth_ok = nullptr;
+  double K[4];
+  double delta;
+};
+
+__device__ __forceinline__ void quat_to_R(const double* q, double* R) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+
+// One thread per landmark: errors, robust weights, Jacobians, Hll/bl, per-edge camera terms.
+// mode 0 = full linearisation; mode 1 = error evaluation only (chi2, rho).
+__global__ void lba_linearize_kernel(LbaDev d, const double* __restrict__ poses, const double* __restrict__ points,
+                                     double* __restrict__ chi2_out, int mode) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.n_points) return;
+  const double X0 = points[3 * p], X1 = points[3 * p + 1], X2 = points[3 * p + 2];
+  const double fx = d.K[0], fy = d.K[1], cx = d.K[2], cy = d.K[3];
+  const double dsqr = d.delta * d.delta;
+  double H0 = 0, H1 = 0, H2 = 0, H3 = 0, H4 = 0, H5 = 0, b0 = 0, b1 = 0, b2 = 0, rho_sum = 0;
+  for (int e = d.pt_ptr[p]; e < d.pt_ptr[p + 1]; ++e) {
+    const int c = d.edge_cam[e];
+    const double* ps = poses + 7 * c;
+    double R[9];
+    quat_to_R(ps, R);
+    const double x = R[0] * X0 + R[1] * X1 + R[2] * X2 + ps[4];
+    const double y = R[3] * X0 + R[4] * X1 + R[5] * X2 + ps[5];
+    const double z = R[6] * X0 + R[7] * X1 + R[8] * X2 + ps[6];
+    const double e0 = d.obs[2 * e] - (fx * x / z + cx);
+    const double e1 = d.obs[2 * e + 1] - (fy * y / z + cy);
+    const double is2 = d.invs2[e];
+    const double chi2 = is2 * (e0 * e0 + e1 * e1);
+    chi2_out[e] = chi2;
+    const bool inl = chi2 <= dsqr;
+    const double sq = sqrt(fmax(chi2, 1e-300));
+    rho_sum += inl ? chi2 : 2 * sq * d.delta - dsqr;
+    if (mode == 1) {
+      if (d.depth_ok) d.depth_ok[e] = z > 0.0 ? 1 : 0;
+      continue;
+    }
+    const double w = inl ? 1.0 : d.delta / sq;
+    const double wo = w * is2;
+    // -Jproj (2x3): [[-fx/z, 0, fx x/z^2], [0, -fy/z, fy y/z^2]]
+    const double iz = 1.0 / z, iz2 = 1.0 / (z * z);
+    const double a00 = -fx * iz, a02 = fx * x * iz2, a11 = -fy * iz, a12 = fy * y * iz2;
+    // Jp = (-Jproj) * R
+    double Jp[6];
+    Jp[0] = a00 * R[0] + a02 * R[6]; Jp[1] = a00 * R[1] + a02 * R[7]; Jp[2] = a00 * R[2] + a02 * R[8];
+    Jp[3] = a11 * R[3] + a12 * R[6]; Jp[4] = a11 * R[4] + a12 * R[7]; Jp[5] = a11 * R[5] + a12 * R[8];
+    // Jc = (-Jproj) * [ -[X]x | I ],  -[X]x = [[0, z, -y], [-z, 0, x], [y, -x, 0]]
+    double Jc[12];
+    Jc[0] = a02 * y;            Jc[1] = a00 * z - a02 * x;  Jc[2] = -a00 * y;  Jc[3] = a00; Jc[4] = 0;   Jc[5] = a02;
+    Jc[6] = -a11 * z + a12 * y; Jc[7] = -a12 * x;           Jc[8] = a11 * x;   Jc[9] = 0;   Jc[10] = a11; Jc[11] = a12;
+    const double r0 = -wo * e0, r1 = -wo * e1;  // -(rho' Omega e)
+    H0 += wo * (Jp[0] * Jp[0] + Jp[3] * Jp[3]);
+    H1 += wo * (Jp[0] * Jp[1] + Jp[3] * Jp[4]);
+    H2 += wo * (Jp[0] * Jp[2] + Jp[3] * Jp[5]);
+    H3 += wo * (Jp[1] * Jp[1] + Jp[4] * Jp[4]);
+    H4 += wo * (Jp[1] * Jp[2] + Jp[4] * Jp[5]);
+    H5 += wo * (Jp[2] * Jp[2] + Jp[5] * Jp[5]);
+    b0 += Jp[0] * r0 + Jp[3] * r1;
+    b1 += Jp[1] * r0 + Jp[4] * r1;
+    b2 += Jp[2] * r0 + Jp[5] * r1;
+    if (d.cam_slot[c] >= 0) {
+      double* jc = d.Jc + 12 * (size_t)e;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) jc[i] = Jc[i];
+      d.wo[e] = wo;
+      d.r[2 * e] = r0;
+      d.r[2 * e + 1] = r1;
+      double* hpl = d.Hpl + 18 * (size_t)e;  // 6x3 = wo * Jc^T Jp
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) hpl[3 * i + j] = wo * (Jc[i] * Jp[j] + Jc[6 + i] * Jp[3 + j]);
+    }
+  }
+  d.rho_pt[p] = rho_sum;
+  if (mode == 0) {
+    double* h = d.Hll + 6 * (size_t)p;
+    h[0] = H0; h[1] = H1; h[2] = H2; h[3] = H3; h[4] = H4; h[5] = H5;
+    d.bl[3 * p] = b0; d.bl[3 * p + 1] = b1; d.bl[3 * p + 2] = b2;
+  }
+}
+
+// One CTA per optimisable camera: Hpp (36) and bp (6) summed over the camera's edges in ascending edge order.
+__global__ void lba_camera_kernel(LbaDev d) {
+  const int s = blockIdx.x, c = d.opt_cams[s], t = threadIdx.x;
+  if (t >= 42) return;
+  double acc = 0;
+  const int a = t < 36 ? t / 6 : t - 36, b = t < 36 ? t % 6 : 0;
+  for (int k = d.cam_ptr[c]; k < d.cam_ptr[c + 1]; ++k) {
+    const int e = d.cam_edges[k];
+    const double* jc = d.Jc + 12 * (size_t)e;
+    if (t < 36) acc += d.wo[e] * (jc[a] * jc[b] + jc[6 + a] * jc[6 + b]);
+    else acc += jc[a] * d.r[2 * e] + jc[6 + a] * d.r[2 * e + 1];
+  }
+  if (t < 36) d.Hpp[36 * (size_t)s + t] = acc;
+  else d.bp[6 * (size_t)s + a] = acc;
+}
+
+// Single-CTA fixed-order reductions: out[0] = sum(v[0..n)), optionally out[1] = max |diag| of Hll and Hpp.
+__global__ void lba_reduce_kernel(const double* __restrict__ v, int n, double* __restrict__ out, int out_idx,
+                                  LbaDev d, int want_maxdiag) {
+  __shared__ double sh[1024];
+  const int t = threadIdx.x;
+  double acc = 0;
+  for (int i = t; i < n; i += 1024) acc += v[i];
+  sh[t] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (t < s) sh[t] += sh[t + s];
+    __syncthreads();
+  }
+  if (t == 0) out[out_idx] = sh[0];
+  if (want_maxdiag) {
+    double m = 0;
+    for (int p = t; p < d.n_points; p += 1024) {
+      const double* h = d.Hll + 6 * (size_t)p;
+      m = fmax(m, fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5]))));
+    }
+    for (int i = t; i < d.n_opt * 6; i += 1024) m = fmax(m, fabs(d.Hpp[36 * (size_t)(i / 6) + 7 * (i % 6)]));
+    __syncthreads();
+    sh[t] = m;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+      if (t < s) sh[t] = fmax(sh[t], sh[t + s]);
+      __syncthreads();
+    }
+    if (t == 0) out[1] = sh[0];
+  }
+}
+
+__device__ __forceinline__ int blk_index(int a, int b, int n) { return a * n - a * (a - 1) / 2 + (b - a); }  // a <= b
+
+#define LBA_MAX_OBS 64
+
+// Schur complement: CTA g walks points g, g+G, ...; for every point adds Hpl_a Dinv Hpl_b^T to block (a,b) of its
+// private upper-triangular buffer and Hpl_a Dinv bl to its private right-hand side.
+__global__ void __launch_bounds__(256) lba_schur_kernel(LbaDev d, double lambda) {
+  __shared__ double sBD[LBA_MAX_OBS][18];
+  __shared__ double sH[LBA_MAX_OBS][18];
+  __shared__ int sSlot[LBA_MAX_OBS];
+  __shared__ double sDinv[6], sDb[3];
+  __shared__ int sK;
+  const int t = threadIdx.x;
+  double* part = d.partial + (size_t)blockIdx.x * ((size_t)d.n_blk * 36 + (size_t)d.n_opt * 6);
+  double* part_b = part + (size_t)d.n_blk * 36;
+  for (int p = blockIdx.x; p < d.n_points; p += gridDim.x) {
+    if (t == 0) {
+      const double* h = d.Hll + 6 * (size_t)p;
+      const double a = h[0] + lambda, b = h[1], c = h[2], e = h[3] + lambda, f = h[4], i = h[5] + lambda;
+      const double A = e * i - f * f, B = -(b * i - c * f), C = b * f - c * e;
+      const double det = a * A + b * B + c * C;
+      const double id = 1.0 / det;
+      const double D0 = A * id, D1 = B * id, D2 = C * id;
+      const double D3 = (a * i - c * c) * id, D4 = -(a * f - b * c) * id, D5 = (a * e - b * b) * id;
+      sDinv[0] = D0; sDinv[1] = D1; sDinv[2] = D2; sDinv[3] = D3; sDinv[4] = D4; sDinv[5] = D5;
+      double* dv = d.Dinv + 6 * (size_t)p;
+      dv[0] = D0; dv[1] = D1; dv[2] = D2; dv[3] = D3; dv[4] = D4; dv[5] = D5;
+      const double l0 = d.bl[3 * p], l1 = d.bl[3 * p + 1], l2 = d.bl[3 * p + 2];
+      sDb[0] = D0 * l0 + D1 * l1 + D2 * l2;
+      sDb[1] = D1 * l0 + D3 * l1 + D4 * l2;
+      sDb[2] = D2 * l0 + D4 * l1 + D5 * l2;
+      int k = 0;
+      for (int e2 = d.pt_ptr[p]; e2 < d.pt_ptr[p + 1] && k < LBA_MAX_OBS; ++e2) {
+        const int s = d.cam_slot[d.edge_cam[e2]];
+        if (s >= 0) {
+          sSlot[k] = s | (e2 - d.pt_ptr[p]) << 16;
+          ++k;
+        }
+      }
+      sK = k;
+    }
+    __syncthreads();
+    const int k = sK;
+    for (int i = t; i < k * 18; i += 256) {
+      const int a = i / 18, ij = i % 18;
+      const int e = d.pt_ptr[p] + (sSlot[a] >> 16);
+      sH[a][ij] = d.Hpl[18 * (size_t)e + ij];
+    }
+    __syncthreads();
+    for (int i = t; i < k * 18; i += 256) {
+      const int a = i / 18, ij = i % 18, r = ij / 3, m = ij % 3;
+      // BD = Hpl * Dinv (Dinv symmetric: rows (0,1,2),(1,3,4),(2,4,5))
+      const double h0 = sH[a][3 * r], h1 = sH[a][3 * r + 1], h2 = sH[a][3 * r + 2];
+      const double c0 = m == 0 ? sDinv[0] : (m == 1 ? sDinv[1] : sDinv[2]);
+      const double c1 = m == 0 ? sDinv[1] : (m == 1 ? sDinv[3] : sDinv[4]);
+      const double c2 = m == 0 ? sDinv[2] : (m == 1 ? sDinv[4] : sDinv[5]);
+      sBD[a][ij] = h0 * c0 + h1 * c1 + h2 * c2;
+    }
+    __syncthreads();
+    const int npairs = k * (k + 1) / 2;
+    for (int i = t; i < npairs * 36; i += 256) {
+      const int pr = i / 36, ij = i % 36, r = ij / 6, c = ij % 6;
+      // unrank pr -> (a <= b) in list order
+      int a = 0, rem = pr;
+      while (rem >= k - a) {
+        rem -= k - a;
+        ++a;
+      }
+      const int b = a + rem;
+      const int sa = sSlot[a] & 0xFFFF, sb = sSlot[b] & 0xFFFF;
+      const double v = sBD[a][3 * r] * sH[b][3 * c] + sBD[a][3 * r + 1] * sH[b][3 * c + 1] +
+                       sBD[a][3 * r + 2] * sH[b][3 * c + 2];
+      if (sa <= sb) part[(size_t)blk_index(sa, sb, d.n_opt) * 36 + r * 6 + c] += v;
+      else part[(size_t)blk_index(sb, sa, d.n_opt) * 36 + c * 6 + r] += v;
+    }
+    for (int i = t; i < k * 6; i += 256) {
+      const int a = i / 6, r = i % 6;
+      part_b[(size_t)(sSlot[a] & 0xFFFF) * 6 + r] +=
+          sH[a][3 * r] * sDb[0] + sH[a][3 * r + 1] * sDb[1] + sH[a][3 * r + 2] * sDb[2];
+    }
+    __syncthreads();
+  }
+}
+
+// Hschur = diag(Hpp + lambda I) - sum_g partial_g (mirrored to the full symmetric matrix), bschur = bp - sum_g.
+__global__ void lba_schur_reduce_kernel(LbaDev d, double lambda, int G) {
+  const int N = 6 * d.n_opt;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)d.n_blk * 36 + (size_t)d.n_opt * 6;
+  if (i < N * N) {
+    const int r = i / N, c = i % N;
+    const int br = r / 6, bc = c / 6, ri = r % 6, ci = c % 6;
+    const size_t idx = br <= bc ? (size_t)blk_index(br, bc, d.n_opt) * 36 + ri * 6 + ci
+                                : (size_t)blk_index(bc, br, d.n_opt) * 36 + ci * 6 + ri;
+    double s = 0;
+    for (int g = 0; g < G; ++g) s += d.partial[g * stride + idx];
+    double base = 0;
+    if (br == bc) base = d.Hpp[36 * (size_t)br + ri * 6 + ci] + (ri == ci ? lambda : 0.0);
+    d.Hs[i] = base - s;
+  } else if (i < N * N + N) {
+    const int r = i - N * N;
+    double s = 0;
+    for (int g = 0; g < G; ++g) s += d.partial[g * stride + (size_t)d.n_blk * 36 + r];
+    d.bs[r] = d.bp[r] - s;
+  }
+}
+
+// Landmark back-substitution xl = Dinv (bl - sum_a Hpl_a^T xp_a), trial point = point + xl, and the landmark part of
+// the gain-ratio denominator sum x (lambda x + b)  (optimization_algorithm_levenberg.cpp:186-199).
+__global__ void lba_backsub_kernel(LbaDev d, double lambda) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.n_points) return;
+  double c0 = d.bl[3 * p], c1 = d.bl[3 * p + 1], c2 = d.bl[3 * p + 2];
+  for (int e = d.pt_ptr[p]; e < d.pt_ptr[p + 1]; ++e) {
+    const int s = d.cam_slot[d.edge_cam[e]];
+    if (s < 0) continue;
+    const double* h = d.Hpl + 18 * (size_t)e;
+    const double* x = d.xp + 6 * (size_t)s;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      c0 -= h[3 * i] * x[i];
+      c1 -= h[3 * i + 1] * x[i];
+      c2 -= h[3 * i + 2] * x[i];
+    }
+  }
+  const double* D = d.Dinv + 6 * (size_t)p;
+  const double x0 = D[0] * c0 + D[1] * c1 + D[2] * c2;
+  const double x1 = D[1] * c0 + D[3] * c1 + D[4] * c2;
+  const double x2 = D[2] * c0 + D[4] * c1 + D[5] * c2;
+  d.points_t[3 * p] = d.points[3 * p] + x0;
+  d.points_t[3 * p + 1] = d.points[3 * p + 1] + x1;
+  d.points_t[3 * p + 2] = d.points[3 * p + 2] + x2;
+  d.scale_pt[p] = x0 * (lambda * x0 + d.bl[3 * p]) + x1 * (lambda * x1 + d.bl[3 * p + 1]) +
+                  x2 * (lambda * x2 + d.bl[3 * p + 2]);
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+static bool cholesky_solve(std::vector<double>& A, std::vector<double>& b, int n) {  // A row-major SPD, in place
+  for (int j = 0; j < n; ++j) {
+    double s = A[(size_t)j * n + j];
+    for (int k = 0; k < j; ++k) s -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+    if (!(s > 0.0) || !std::isfinite(s)) return false;
+    const double l = sqrt(s);
+    A[(size_t)j * n + j] = l;
+    for (int i = j + 1; i < n; ++i) {
+      double t = A[(size_t)i * n + j];
+      for (int k = 0; k < j; ++k) t -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+      A[(size_t)i * n + j] = t / l;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    double t = b[i];
+    for (int k = 0; k < i; ++k) t -= A[(size_t)i * n + k] * b[k];
+    b[i] = t / A[(size_t)i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double t = b[i];
+    for (int k = i + 1; k < n; ++k) t -= A[(size_t)k * n + i] * b[k];
+    b[i] = t / A[(size_t)i * n + i];
+  }
+  return true;
+}
+
+static void h_quat_to_R(const double* q, double* R) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+// Eigen Quaternion(Matrix3) (Shepperd), (x,y,z,w)
+static void h_R_to_quat(const double* R, double* q) {
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t;
+    q[1] = (R[2] - R[6]) * t;
+    q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+}
+static void h_normalize_rot(double* q) {
+  if (q[3] < 0) for (int i = 0; i < 4; ++i) q[i] = -q[i];
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) q[i] /= n;
+}
+static void mat3_mul(const double* A, const double* B, double* C) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+// estimate <- exp(update) * estimate  (types_six_dof_expmap.h:73-76, se3quat.h:223-257); update = [omega, upsilon]
+static void h_pose_oplus(const double* pose, const double* u, double* out) {
+  const double w0 = u[0], w1 = u[1], w2 = u[2];
+  const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+  const double Om[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+  double Om2[9], R[9], V[9];
+  mat3_mul(Om, Om, Om2);
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; ++i) R[i] = I[i] + Om[i] + Om2[i];
+    for (int i = 0; i < 9; ++i) V[i] = R[i];
+  } else {
+    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta);
+    const double c = (theta - sin(theta)) / (theta * theta * theta);
+    for (int i = 0; i < 9; ++i) {
+      R[i] = I[i] + a * Om[i] + b * Om2[i];
+      V[i] = I[i] + b * Om[i] + c * Om2[i];
+    }
+  }
+  double qe[4];
+  h_R_to_quat(R, qe);
+  h_normalize_rot(qe);
+  const double te[3] = {V[0] * u[3] + V[1] * u[4] + V[2] * u[5], V[3] * u[3] + V[4] * u[4] + V[5] * u[5],
+                        V[6] * u[3] + V[7] * u[4] + V[8] * u[5]};
+  // q = qe * q_pose (Hamilton, xyzw)
+  const double ax = qe[0], ay = qe[1], az = qe[2], aw = qe[3];
+  const double bx = pose[0], by = pose[1], bz = pose[2], bw = pose[3];
+  double q[4] = {aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                 aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz};
+  double Re[9];
+  h_quat_to_R(qe, Re);
+  const double* t = pose + 4;
+  out[4] = te[0] + Re[0] * t[0] + Re[1] * t[1] + Re[2] * t[2];
+  out[5] = te[1] + Re[3] * t[0] + Re[4] * t[1] + Re[5] * t[2];
+  out[6] = te[2] + Re[6] * t[0] + Re[7] * t[1] + Re[8] * t[2];
+  h_normalize_rot(q);
+  for (int i = 0; i < 4; ++i) out[i] = q[i];
+}
+
+struct LbaHost {
+  std::vector<int> pt_ptr, cam_ptr, cam_edges, cam_slot, opt_cams;
+};
+
+static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost& h, uint8_t** arena_out) {
+  HFB_REQUIRE(ctx, pr && pr->n_cams > 0 && pr->n_points >= 0 && pr->n_edges >= 0, "bad problem sizes");
+  HFB_REQUIRE(ctx, pr->poses && pr->fixed && (pr->n_points == 0 || pr->points) &&
+                       (pr->n_edges == 0 || (pr->edge_cam && pr->edge_point && pr->obs && pr->inv_sigma2)),
+              "null problem array");
+  const int nc = pr->n_cams, np = pr->n_points, ne = pr->n_edges;
+  h.pt_ptr.assign(np + 1, 0);
+  h.cam_ptr.assign(nc + 1, 0);
+  for (int e = 0; e < ne; ++e) {
+    const int p = pr->edge_point[e], c = pr->edge_cam[e];
+    HFB_REQUIRE(ctx, p >= 0 && p < np && c >= 0 && c < nc, "edge index out of range");
+    HFB_REQUIRE(ctx, e == 0 || p >= pr->edge_point[e - 1], "edges must be sorted by point");
+    h.pt_ptr[p + 1]++;
+    h.cam_ptr[c + 1]++;
+  }
+  for (int p = 0; p < np; ++p) h.pt_ptr[p + 1] += h.pt_ptr[p];
+  for (int c = 0; c < nc; ++c) h.cam_ptr[c + 1] += h.cam_ptr[c];
+  h.cam_edges.resize(ne);
+  {
+    std::vector<int> fill(h.cam_ptr.begin(), h.cam_ptr.end() - 1);
+    for (int e = 0; e < ne; ++e) h.cam_edges[fill[pr->edge_cam[e]]++] = e;
+  }
+  h.cam_slot.assign(nc, -1);
+  h.opt_cams.clear();
+  for (int c = 0; c < nc; ++c)
+    if (!pr->fixed[c]) {
+      h.cam_slot[c] = (int)h.opt_cams.size();
+      h.opt_cams.push_back(c);
+    }
+  const int no = (int)h.opt_cams.size();
+  HFB_REQUIRE(ctx, no <= 4096, "too many optimisable cameras");
+  for (int p = 0; p < np; ++p) {
+    int k = 0;
+    for (int e = h.pt_ptr[p]; e < h.pt_ptr[p + 1]; ++e) k += h.cam_slot[pr->edge_cam[e]] >= 0;
+    HFB_REQUIRE(ctx, k <= LBA_MAX_OBS, "a landmark has more than 64 observations from optimisable keyframes");
+  }
+  d.n_cams = nc; d.n_points = np; d.n_edges = ne; d.n_opt = no;
+  d.n_blk = no * (no + 1) / 2;
+  d.G = std::max(1, std::min(ctx->n_sm, np));
+  for (int i = 0; i < 4; ++i) d.K[i] = (double)pr->K[i];
+  d.delta = pr->huber_delta;
+  // one arena
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t N = (size_t)6 * no;
+  const size_t part_stride = (size_t)d.n_blk * 36 + (size_t)no * 6;
+  const size_t o_poses = take(nc * 7 * 8), o_poses_t = take(nc * 7 * 8), o_points = take((size_t)np * 24),
+               o_points_t = take((size_t)np * 24), o_ecam = take((size_t)ne * 4), o_ptptr = take((size_t)(np + 1) * 4),
+               o_camptr = take((size_t)(nc + 1) * 4), o_camedges = take((size_t)ne * 4), o_slot = take((size_t)nc * 4),
+               o_opt = take((size_t)std::max(no, 1) * 4), o_obs = take((size_t)ne * 16), o_is2 = take((size_t)ne * 8),
+               o_Jc = take((size_t)ne * 96), o_wo = take((size_t)ne * 8), o_r = take((size_t)ne * 16),
+               o_Hpl = take((size_t)ne * 144), o_chia = take((size_t)ne * 8), o_chib = take((size_t)ne * 8),
+               o_Hll = take((size_t)np * 48), o_bl = take((size_t)np * 24), o_Dinv = take((size_t)np * 48),
+               o_rho = take((size_t)np * 8), o_scale = take((size_t)np * 8), o_Hpp = take((size_t)no * 288 + 8),
+               o_bp = take((size_t)no * 48 + 8), o_part = take((size_t)d.G * part_stride * 8 + 8),
+               o_Hs = take(N * N * 8 + 8), o_bs = take(N * 8 + 8), o_xp = take(N * 8 + 8), o_scal = take(64),
+               o_depth = take((size_t)ne + 8);
+  HFB_TRY(ctx->ensure_scratch(off));
+  uint8_t* a = reinterpret_cast<uint8_t*>(ctx->d_scratch);
+  *arena_out = a;
+  d.poses = (double*)(a + o_poses); d.poses_t = (double*)(a + o_poses_t);
+  d.points = (double*)(a + o_points); d.points_t = (double*)(a + o_points_t);
+  d.edge_cam = (int*)(a + o_ecam); d.pt_ptr = (int*)(a + o_ptptr); d.cam_ptr = (int*)(a + o_camptr);
+  d.cam_edges = (int*)(a + o_camedges); d.cam_slot = (int*)(a + o_slot); d.opt_cams = (int*)(a + o_opt);
+  d.obs = (double*)(a + o_obs); d.invs2 = (double*)(a + o_is2);
+  d.Jc = (double*)(a + o_Jc); d.wo = (double*)(a + o_wo); d.r = (double*)(a + o_r); d.Hpl = (double*)(a + o_Hpl);
+  d.chi2_a = (double*)(a + o_chia); d.chi2_b = (double*)(a + o_chib);
+  d.Hll = (double*)(a + o_Hll); d.bl = (double*)(a + o_bl); d.Dinv = (double*)(a + o_Dinv);
+  d.rho_pt = (double*)(a + o_rho); d.scale_pt = (double*)(a + o_scale);
+  d.Hpp = (double*)(a + o_Hpp); d.bp = (double*)(a + o_bp); d.partial = (double*)(a + o_part);
+  d.Hs = (double*)(a + o_Hs); d.bs = (double*)(a + o_bs); d.xp = (double*)(a + o_xp); d.scal = (double*)(a + o_scal);
+  d.depth_ok = (unsigned char*)(a + o_depth);
+  cudaStream_t st = ctx->stream;
+  HFB_CUDA(ctx, cudaMemcpyAsync(d.poses, pr->poses, (size_t)nc * 56, cudaMemcpyHostToDevice, st));
+  if (np) HFB_CUDA(ctx, cudaMemcpyAsync(d.points, pr->points, (size_t)np * 24, cudaMemcpyHostToDevice, st));
+  if (ne) {
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.edge_cam, pr->edge_cam, (size_t)ne * 4, cudaMemcpyHostToDevice, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.cam_edges, h.cam_edges.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.obs, pr->obs, (size_t)ne * 16, cudaMemcpyHostToDevice, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.invs2, pr->inv_sigma2, (size_t)ne * 8, cudaMemcpyHostToDevice, st));
+  }
+  HFB_CUDA(ctx, cudaMemcpyAsync(d.pt_ptr, h.pt_ptr.data(), (size_t)(np + 1) * 4, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(d.cam_ptr, h.cam_ptr.data(), (size_t)(nc + 1) * 4, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(d.cam_slot, h.cam_slot.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+  if (no) HFB_CUDA(ctx, cudaMemcpyAsync(d.opt_cams, h.opt_cams.data(), (size_t)no * 4, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaStreamSynchronize(st));  // host staging vectors may now go out of scope
+  return HFB_OK;
+}
+
+// computeActiveErrors + buildSystem at (d.poses, d.points): fills Hll/bl/Hpl/Hpp/bp, chi2 into chi2_buf,
+// scal[0] = robust chi2, scal[1] = max |diag|.
+static int lba_build(hfb_ctx* ctx, LbaDev& d, double* chi2_buf, int want_maxdiag) {
+  if (d.n_points > 0) {
+    lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, ctx->stream>>>(d, d.poses, d.points, chi2_buf, 0);
+    HFB_CHECK_LAUNCH(ctx, "lba_linearize");
+  }
+  if (d.n_opt > 0) {
+    lba_camera_kernel<<<d.n_opt, 64, 0, ctx->stream>>>(d);
+    HFB_CHECK_LAUNCH(ctx, "lba_camera");
+  }
+  lba_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(d.rho_pt, d.n_points, d.scal, 0, d, want_maxdiag);
+  HFB_CHECK_LAUNCH(ctx, "lba_reduce");
+  return HFB_OK;
+}
+
+static int lba_schur(hfb_ctx* ctx, LbaDev& d, double lambda) {
+  const size_t part_stride = (size_t)d.n_blk * 36 + (size_t)d.n_opt * 6;
+  HFB_CUDA(ctx, cudaMemsetAsync(d.partial, 0, (size_t)d.G * part_stride * 8, ctx->stream));
+  if (d.n_points > 0) {
+    lba_schur_kernel<<<d.G, 256, 0, ctx->stream>>>(d, lambda);
+    HFB_CHECK_LAUNCH(ctx, "lba_schur");
+  }
+  const int N = 6 * d.n_opt;
+  if (N > 0) {
+    lba_schur_reduce_kernel<<<ceil_div(N * N + N, 256), 256, 0, ctx->stream>>>(d, lambda, d.G);
+    HFB_CHECK_LAUNCH(ctx, "lba_schur_reduce");
+  }
+  return HFB_OK;
+}
+
+extern "C" int hfb_lba_build_schur(hfb_ctx* ctx, const hfb_lba_problem* problem, double lambda, double* Hschur,
+                                   double* bschur, double* robust_chi2, int32_t* n_opt_cams) {
+  if (!ctx) return HFB_ERR_INVALID;
+  LbaDev d;
+  LbaHost h;
+  uint8_t* arena = nullptr;
+  HFB_TRY(lba_setup(ctx, problem, d, h, &arena));
+  HFB_TRY(lba_build(ctx, d, d.chi2_a, 0));
+  HFB_TRY(lba_schur(ctx, d, lambda));
+  const size_t N = (size_t)6 * d.n_opt;
+  if (n_opt_cams) *n_opt_cams = d.n_opt;
+  if (N && Hschur) HFB_CUDA(ctx, cudaMemcpyAsync(Hschur, d.Hs, N * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (N && bschur) HFB_CUDA(ctx, cudaMemcpyAsync(bschur, d.bs, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (robust_chi2) HFB_CUDA(ctx, cudaMemcpyAsync(robust_chi2, d.scal, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
+}
+
+extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, int32_t iterations,
+                                double user_lambda_init, const volatile uint8_t* stop_flag, double* poses_out,
+                                double* points_out, double* chi2_out, uint8_t* depth_positive_out,
+                                hfb_lba_stats* stats) {
+  if (!ctx) return HFB_ERR_INVALID;
+  LbaDev d;
+  LbaHost h;
+  uint8_t* arena = nullptr;
+  const uint64_t launches0 = ctx->launches;
+  HFB_TRY(lba_setup(ctx, problem, d, h, &arena));
+  cudaStream_t st = ctx->stream;
+  const int no = d.n_opt, N = 6 * no, nc = d.n_cams;
+  std::vector<double> poses(problem->poses, problem->poses + (size_t)nc * 7), poses_t(poses);
+  std::vector<double> Hs((size_t)N * N), bs(N), bp(N), xp(N);
+  auto terminate = [&]() { return stop_flag && *stop_flag; };
+  const double tau = 1e-5, good_lo = 1.0 / 3.0, good_hi = 2.0 / 3.0;
+  const int max_trials = 10;
+  double lambda = 0.0, ni = 2.0;
+  int n_bad = 0, it_done = 0, trials = 0;
+  double* chi2_last = d.chi2_a;   // buffer holding the most recent computeActiveErrors result
+  double* chi2_other = d.chi2_b;
+  double initial_chi = 0.0, current_chi = 0.0;
+  double scal[4];
+  // chi2 at the initial estimate (iterations == 0 or immediate stop still reports it)
+  if (d.n_points > 0) {
+    lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, d.poses, d.points, chi2_last, 1);
+    HFB_CHECK_LAUNCH(ctx, "lba_errors");
+  }
+  lba_reduce_kernel<<<1, 1024, 0, st>>>(d.rho_pt, d.n_points, d.scal, 0, d, 0);
+  HFB_CHECK_LAUNCH(ctx, "lba_reduce");
+  HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 8, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaStreamSynchronize(st));
+  initial_chi = current_chi = scal[0];
+  for (int it = 0; it < iterations; ++it) {
+    if (terminate()) break;
+    HFB_TRY(lba_build(ctx, d, chi2_last, it == 0));
+    HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 16, cudaMemcpyDeviceToHost, st));
+    if (N) HFB_CUDA(ctx, cudaMemcpyAsync(bp.data(), d.bp, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    HFB_CUDA(ctx, cudaStreamSynchronize(st));
+    current_chi = scal[0];
+    const double ini_chi = current_chi;
+    if (it == 0) {
+      lambda = user_lambda_init > 0 ? user_lambda_init : tau * scal[1];
+      ni = 2.0;
+      n_bad = 0;
+    }
+    double rho = 0.0;
+    int qmax = 0;
+    do {
+      HFB_TRY(lba_schur(ctx, d, lambda));
+      bool ok2 = true;
+      if (N) {
+        HFB_CUDA(ctx, cudaMemcpyAsync(Hs.data(), d.Hs, (size_t)N * N * 8, cudaMemcpyDeviceToHost, st));
+        HFB_CUDA(ctx, cudaMemcpyAsync(bs.data(), d.bs, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+        HFB_CUDA(ctx, cudaStreamSynchronize(st));
+        xp = bs;
+        ok2 = cholesky_solve(Hs, xp, N);
+        if (!ok2) std::fill(xp.begin(), xp.end(), 0.0);
+        HFB_CUDA(ctx, cudaMemcpyAsync(d.xp, xp.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
+      }
+      poses_t = poses;
+      for (int s = 0; s < no; ++s) h_pose_oplus(&poses[(size_t)h.opt_cams[s] * 7], &xp[(size_t)6 * s], &poses_t[(size_t)h.opt_cams[s] * 7]);
+      HFB_CUDA(ctx, cudaMemcpyAsync(d.poses_t, poses_t.data(), (size_t)nc * 56, cudaMemcpyHostToDevice, st));
+      if (d.n_points > 0) {
+        lba_backsub_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, lambda);
+        HFB_CHECK_LAUNCH(ctx, "lba_backsub");
+        lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, d.poses_t, d.points_t, chi2_other, 1);
+        HFB_CHECK_LAUNCH(ctx, "lba_errors");
+      }
+      std::swap(chi2_last, chi2_other);
+      lba_reduce_kernel<<<1, 1024, 0, st>>>(d.rho_pt, d.n_points, d.scal, 2, d, 0);
+      HFB_CHECK_LAUNCH(ctx, "lba_reduce");
+      lba_reduce_kernel<<<1, 1024, 0, st>>>(d.scale_pt, d.n_points, d.scal, 3, d, 0);
+      HFB_CHECK_LAUNCH(ctx, "lba_reduce");
+      HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 32, cudaMemcpyDeviceToHost, st));
+      HFB_CUDA(ctx, cudaStreamSynchronize(st));
+      ++trials;
+      const double temp_chi = ok2 ? scal[2] : 1.7976931348623157e308;
+      double scale = scal[3] + 1e-3;
+      for (int i = 0; i < N; ++i) scale += xp[i] * (lambda * xp[i] + bp[i]);
+      rho = (current_chi - temp_chi) / scale;
+      if (rho > 0 && std::isfinite(temp_chi)) {
+        double alpha = 1.0 - pow(2 * rho - 1, 3);
+        alpha = std::min(alpha, good_hi);
+        lambda *= std::max(good_lo, alpha);
+        ni = 2.0;
+        current_chi = temp_chi;
+        poses = poses_t;
+        std::swap(d.poses, d.poses_t);
+        std::swap(d.points, d.points_t);
+      } else {
+        lambda *= ni;
+        ni *= 2;
+      }
+      ++qmax;
+    } while (rho < 0 && qmax < max_trials && !terminate());
+    ++it_done;
+    if (qmax == max_trials || rho == 0) break;
+    if ((ini_chi - current_chi) * 1e3 < ini_chi) ++n_bad;
+    else n_bad = 0;
+    if (n_bad >= 3) break;
+  }
+  // outputs: final estimate, cached chi2 of the LAST error evaluation (src/Optimizer.cc:1425 quirk), depth test
+  if (d.n_points > 0 && depth_positive_out) {
+    lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, d.poses, d.points, chi2_other, 1);
+    HFB_CHECK_LAUNCH(ctx, "lba_errors");
+    HFB_CUDA(ctx, cudaMemcpyAsync(depth_positive_out, d.depth_ok, (size_t)d.n_edges, cudaMemcpyDeviceToHost, st));
+  }
+  if (poses_out) memcpy(poses_out, poses.data(), (size_t)nc * 56);
+  if (points_out && d.n_points)
+    HFB_CUDA(ctx, cudaMemcpyAsync(points_out, d.points, (size_t)d.n_points * 24, cudaMemcpyDeviceToHost, st));
+  if (chi2_out && d.n_edges)
+    HFB_CUDA(ctx, cudaMemcpyAsync(chi2_out, chi2_last, (size_t)d.n_edges * 8, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaStreamSynchronize(st));
+  if (stats) {
+    stats->iterations = it_done;
+    stats->trials = trials;
+    stats->initial_chi2 = initial_chi;
+    stats->final_chi2 = current_chi;
+    stats->lambda = lambda;
+    stats->n_opt_cams = no;
+    stats->gpu_launches = (int)(ctx->launches - launches0);
+  }
+  return HFB_OK;
+}

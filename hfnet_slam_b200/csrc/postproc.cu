@@ -1,0 +1,377 @@
+// Network-tail stages that the reference runs inside the TensorRT graph (simple_nms) or on the CPU after the D2H copy
+// (threshold scan, top-k, bilinear descriptor resampling, row normalisation) and the image pyramid.  All of it is
+// compare / integer / fixed-expression fp32 work: bit-exact against the oracle given identical dense maps.
+//
+//   simple_nms(radius 4, iterations 2)   hfnet/models/utils/layers.py:10-32, hfnet/export_model.py:35-37
+//   threshold scan + top-k               src/Extractors/HFNetRTModel.cc:150-179
+//   Resampler + cv::normalize            src/Extractors/BaseModel.cc:491-562, src/Extractors/HFNetRTModel.cc:181-195
+//   cv::resize(INTER_LINEAR) on CV_8UC1  src/Extractors/HFextractor.cc:159-173
+#include <math.h>
+
+#include "common.cuh"
+
+// =============================================================================================== simple_nms
+// One CTA produces a 64 x 16 tile.  Dependency radius is 12 (three chained 9x9 max-pools), so the tile is computed
+// from an 88 x 40 halo region held in shared memory; every pool is separable (row pass, column pass).
+#define NMS_TW 64
+#define NMS_TH 16
+#define NMS_R 4
+#define NMS_AW (NMS_TW + 24)
+#define NMS_AH (NMS_TH + 24)
+
+__global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H,
+                                                  int W) {
+  __shared__ float sS[NMS_AH][NMS_AW];   // scores, -inf outside the image
+  __shared__ float sT[NMS_AH][NMS_AW];   // row-pass scratch
+  __shared__ float sM[NMS_AH][NMS_AW];   // max_mask (1/0) on region B, later s' on region C
+  __shared__ unsigned char sSupp[NMS_AH][NMS_AW];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
+  const float* src = scores + (size_t)blockIdx.z * H * W;
+  float* dst = out + (size_t)blockIdx.z * H * W;
+  const int ax0 = x0 - 12, ay0 = y0 - 12;
+  const float NEG = -INFINITY;
+
+  for (int i = tid; i < NMS_AH * NMS_AW; i += 256) {
+    const int r = i / NMS_AW, c = i % NMS_AW;
+    const int y = ay0 + r, x = ax0 + c;
+    sS[r][c] = (y >= 0 && y < H && x >= 0 && x < W) ? src[(size_t)y * W + x] : NEG;
+  }
+  __syncthreads();
+  // --- mp(s): rows [0,40) x cols [4,84) row pass, then rows [4,36) column pass -> mask on B = rows/cols [4,..)
+  for (int i = tid; i < NMS_AH * (NMS_AW - 8); i += 256) {
+    const int r = i / (NMS_AW - 8), c = 4 + i % (NMS_AW - 8);
+    float m = sS[r][c - 4];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sS[r][c + d]);
+    sT[r][c] = m;
+  }
+  __syncthreads();
+  for (int i = tid; i < (NMS_AH - 8) * (NMS_AW - 8); i += 256) {
+    const int r = 4 + i / (NMS_AW - 8), c = 4 + i % (NMS_AW - 8);
+    float m = sT[r - 4][c];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sT[r + d][c]);
+    const int y = ay0 + r, x = ax0 + c;
+    const bool in = (y >= 0 && y < H && x >= 0 && x < W);
+    sM[r][c] = (in && sS[r][c] == m) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  // --- supp = mp(mask) > 0 on C = rows [8,32) x cols [8,80)
+  for (int i = tid; i < (NMS_AH - 8) * (NMS_AW - 16); i += 256) {
+    const int r = 4 + i / (NMS_AW - 16), c = 8 + i % (NMS_AW - 16);
+    float m = sM[r][c - 4];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sM[r][c + d]);
+    sT[r][c] = m;
+  }
+  __syncthreads();
+  // mask of the tile pixels is needed at the end: keep it in registers before sM is overwritten with s'
+  float keep_mask[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = tid + q * 256;
+    const int r = 12 + i / NMS_TW, c = 12 + i % NMS_TW;
+    keep_mask[q] = sM[r][c];
+  }
+  __syncthreads();
+  for (int i = tid; i < (NMS_AH - 16) * (NMS_AW - 16); i += 256) {
+    const int r = 8 + i / (NMS_AW - 16), c = 8 + i % (NMS_AW - 16);
+    float m = sT[r - 4][c];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sT[r + d][c]);
+    const bool supp = m > 0.f;
+    const int y = ay0 + r, x = ax0 + c;
+    const bool in = (y >= 0 && y < H && x >= 0 && x < W);
+    sSupp[r][c] = supp ? 1 : 0;
+    sM[r][c] = in ? (supp ? 0.f : sS[r][c]) : NEG;   // s'
+  }
+  __syncthreads();
+  // --- mp(s') on the tile D = rows [12,28) x cols [12,76)
+  for (int i = tid; i < (NMS_AH - 16) * NMS_TW; i += 256) {
+    const int r = 8 + i / NMS_TW, c = 12 + i % NMS_TW;
+    float m = sM[r][c - 4];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sM[r][c + d]);
+    sT[r][c] = m;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = tid + q * 256;
+    const int r = 12 + i / NMS_TW, c = 12 + i % NMS_TW;
+    const int y = ay0 + r, x = ax0 + c;
+    if (y >= H || x >= W) continue;
+    float m = sT[r - 4][c];
+#pragma unroll
+    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sT[r + d][c]);
+    const bool is_new = (sM[r][c] == m);
+    const bool mx = (keep_mask[q] != 0.f) || (is_new && !sSupp[r][c]);
+    dst[(size_t)y * W + x] = mx ? sS[r][c] : 0.f;
+  }
+}
+
+int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, int B) {
+  dim3 grid(ceil_div(W, NMS_TW), ceil_div(H, NMS_TH), B);
+  nms_kernel<<<grid, 256, 0, ctx->stream>>>(d_scores, d_out, H, W);
+  HFB_CHECK_LAUNCH(ctx, "nms");
+  return HFB_OK;
+}
+
+// =============================================================================================== threshold scan
+// key = (ordered score bits << 32) | (~scan index), scan index = col*H + row (the reference visits column-major,
+// HFNetRTModel.cc:155-168): a larger key is a better keypoint, ties resolved towards the earlier visit.
+__global__ void select_compact_kernel(const float* __restrict__ nms, int H, int W, float threshold, u64* __restrict__ cand,
+                                      int* __restrict__ count, int cap) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const float s = nms[(size_t)b * H * W + i];
+  if (s >= threshold) {
+    const int row = i / W, col = i - row * W;
+    const int pos = atomicAdd(count + b, 1);
+    if (pos < cap) cand[(size_t)b * cap + pos] = ((u64)f2ord(s) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(col * H + row));
+  }
+}
+
+// =============================================================================================== top-k
+// One CTA per frame: radix-select the k-th largest key (8 passes of 8 bits), gather the k survivors (keys are
+// unique), bitonic-sort them descending in shared memory.  k <= SELECT_KMAX.
+#define SELECT_KMAX 8192
+
+__global__ void __launch_bounds__(1024) select_topk_kernel(const u64* __restrict__ cand, const int* __restrict__ count,
+                                                           int cap, int k_req, u64* __restrict__ sel,
+                                                           int* __restrict__ n_sel, int sel_stride,
+                                                           int* __restrict__ overflow) {
+  extern __shared__ u64 s_keys[];  // [P]
+  __shared__ int s_hist[256];
+  __shared__ u64 s_prefix;
+  __shared__ int s_remaining, s_fill;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  int n = count[b];
+  if (n > cap) {
+    if (tid == 0) atomicExch(overflow, 1);
+    n = cap;
+  }
+  const u64* c = cand + (size_t)b * cap;
+  const int k = min(k_req, n);
+  if (tid == 0) n_sel[b] = k;
+  if (k == 0) return;
+  u64 kth = 0ull;
+  if (n > k) {
+    if (tid == 0) {
+      s_prefix = 0ull;
+      s_remaining = k;
+    }
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      if (tid < 256) s_hist[tid] = 0;
+      __syncthreads();
+      const u64 prefix = s_prefix;
+      const u64 himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+      for (int i = tid; i < n; i += 1024) {
+        const u64 key = c[i];
+        if ((key & himask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 0xFF)], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_remaining, bin = 255;
+        for (; bin > 0; --bin) {
+          if (s_hist[bin] >= rem) break;
+          rem -= s_hist[bin];
+        }
+        s_prefix = prefix | ((u64)bin << shift);
+        s_remaining = rem;
+      }
+      __syncthreads();
+    }
+    kth = s_prefix;
+  }
+  int P = 1;
+  while (P < k) P <<= 1;
+  if (tid == 0) s_fill = 0;
+  for (int i = tid; i < P; i += 1024) s_keys[i] = 0ull;
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) {
+    const u64 key = c[i];
+    if (key >= kth) {
+      const int pos = atomicAdd(&s_fill, 1);
+      if (pos < P) s_keys[pos] = key;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < P; i += 1024) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const u64 a = s_keys[i], bb = s_keys[j];
+          const bool desc = ((i & size) == 0);
+          if (desc ? (a < bb) : (a > bb)) {
+            s_keys[i] = bb;
+            s_keys[j] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += 1024) sel[(size_t)b * sel_stride + i] = s_keys[i];
+}
+
+// =============================================================================================== sample
+// One warp per keypoint: warp the coordinates to the descriptor grid, bilinear-sample 256 channels with the
+// reference's expression order (BaseModel.cc:540-550; every product / sum individually rounded, no FMA contraction),
+// then cv::normalize(NORM_L2): norm accumulated in double, scale rounded to fp32, fp32 multiply.
+__global__ void sample_kernel(const u64* __restrict__ sel, const int* __restrict__ n_sel, int sel_stride,
+                              const float* __restrict__ descmap, int H, int W, int Hd, int Wd, float level_scale,
+                              int level, const int* __restrict__ kcount_prev, int kp_cap, float* __restrict__ ox,
+                              float* __restrict__ oy, float* __restrict__ oresp, int* __restrict__ ooct,
+                              float* __restrict__ odesc, int* __restrict__ kcount_out) {
+  const int b = blockIdx.y;
+  const int kp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int n = n_sel[b];
+  int base = 0;
+  for (int l = 0; l < level; ++l) base += kcount_prev[b * HFB_MAX_LEVELS + l];
+  if (kp == 0 && lane == 0) kcount_out[b * HFB_MAX_LEVELS + level] = n;
+  if (kp >= n) return;
+  const u64 key = sel[(size_t)b * sel_stride + kp];
+  const float score = ord2f((unsigned int)(key >> 32));
+  const unsigned int scan = 0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull);
+  const int col = (int)(scan / (unsigned int)H), row = (int)(scan % (unsigned int)H);
+  // HFNetRTModel.cc:147-148,181-188
+  const float scale_w = __fdiv_rn(__fsub_rn((float)Wd, 1.f), __fsub_rn((float)W, 1.f));
+  const float scale_h = __fdiv_rn(__fsub_rn((float)Hd, 1.f), __fsub_rn((float)H, 1.f));
+  const float x = __fmul_rn(scale_w, (float)col), y = __fmul_rn(scale_h, (float)row);
+  const size_t o = (size_t)b * kp_cap + base + kp;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  const float* dm = descmap + (size_t)b * Hd * Wd * 256;
+  if (x > -1.f && y > -1.f && x < (float)Wd && y < (float)Hd) {
+    const int fx = (int)floorf(x), fy = (int)floorf(y);
+    const int cx = fx + 1, cy = fy + 1;
+    const float dx = __fsub_rn((float)cx, x), dy = __fsub_rn((float)cy, y);
+    const float w00 = __fmul_rn(dx, dy);
+    const float w11 = __fmul_rn(__fsub_rn(1.f, dx), __fsub_rn(1.f, dy));
+    const float w01 = __fmul_rn(dx, __fsub_rn(1.f, dy));
+    const float w10 = __fmul_rn(__fsub_rn(1.f, dx), dy);
+    float f00[8], f11[8], f01[8], f10[8];
+    auto fetch = [&](int xx, int yy, float (&f)[8]) {
+      if (xx >= 0 && yy >= 0 && xx <= Wd - 1 && yy <= Hd - 1) {
+        const float4* p = reinterpret_cast<const float4*>(dm + ((size_t)yy * Wd + xx) * 256) + lane * 2;
+        const float4 a = __ldg(p), c4 = __ldg(p + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = c4.x; f[5] = c4.y; f[6] = c4.z; f[7] = c4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+    };
+    fetch(fx, fy, f00);
+    fetch(cx, cy, f11);
+    fetch(fx, cy, f01);
+    fetch(cx, fy, f10);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = __fmul_rn(w00, f00[j]), bq = __fmul_rn(w11, f11[j]);
+      const float c = __fmul_rn(w01, f01[j]), d = __fmul_rn(w10, f10[j]);
+      v[j] = __fadd_rn(__fadd_rn(__fadd_rn(a, bq), c), d);
+    }
+  }
+  double ss = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ss += (double)v[j] * (double)v[j];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+  const double nrm = sqrt(ss);
+  const float sc = nrm > 2.220446049250313e-16 ? (float)(1.0 / nrm) : 0.f;
+  float4* od = reinterpret_cast<float4*>(odesc + o * 256) + lane * 2;
+  od[0] = make_float4(__fmul_rn(v[0], sc), __fmul_rn(v[1], sc), __fmul_rn(v[2], sc), __fmul_rn(v[3], sc));
+  od[1] = make_float4(__fmul_rn(v[4], sc), __fmul_rn(v[5], sc), __fmul_rn(v[6], sc), __fmul_rn(v[7], sc));
+  if (lane == 0) {
+    ox[o] = __fmul_rn((float)col, level_scale);   // HFextractor.cc:272-279: pt *= mvScaleFactor[level]
+    oy[o] = __fmul_rn((float)row, level_scale);
+    oresp[o] = score;
+    ooct[o] = level;
+  }
+}
+
+int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const float* d_descmap, int Hd, int Wd,
+                         u64* d_cand, int* d_cand_count, int cand_cap, u64* d_sel, int* d_nsel, int n_keypoints,
+                         float threshold, float level_scale, int level, int B, int kp_cap, float* d_x, float* d_y,
+                         float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow) {
+  HFB_REQUIRE(ctx, n_keypoints >= 0 && n_keypoints <= SELECT_KMAX, "keypoint budget exceeds SELECT_KMAX (8192)");
+  HFB_CUDA(ctx, cudaMemsetAsync(d_cand_count, 0, sizeof(int) * B, ctx->stream));
+  dim3 g1(ceil_div(H * W, 256), B);
+  select_compact_kernel<<<g1, 256, 0, ctx->stream>>>(d_nms, H, W, threshold, d_cand, d_cand_count, cand_cap);
+  HFB_CHECK_LAUNCH(ctx, "select_compact");
+  int P = 1;
+  while (P < n_keypoints) P <<= 1;
+  const size_t smem = (size_t)P * 8;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    HFB_CUDA(ctx, cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  select_topk_kernel<<<B, 1024, smem, ctx->stream>>>(d_cand, d_cand_count, cand_cap, n_keypoints, d_sel, d_nsel,
+                                                     SELECT_KMAX, d_overflow);
+  HFB_CHECK_LAUNCH(ctx, "select_topk");
+  if (n_keypoints > 0) {
+    dim3 g2(ceil_div(n_keypoints, 8), B);
+    sample_kernel<<<g2, 256, 0, ctx->stream>>>(d_sel, d_nsel, SELECT_KMAX, d_descmap, H, W, Hd, Wd, level_scale, level,
+                                               d_kcount, kp_cap, d_x, d_y, d_resp, d_oct, d_desc, d_kcount);
+    HFB_CHECK_LAUNCH(ctx, "sample");
+  } else {
+    // budget 0: still publish the count
+    dim3 g2(1, B);
+    sample_kernel<<<g2, 32, 0, ctx->stream>>>(d_sel, d_nsel, SELECT_KMAX, d_descmap, H, W, Hd, Wd, level_scale, level,
+                                              d_kcount, kp_cap, d_x, d_y, d_resp, d_oct, d_desc, d_kcount);
+    HFB_CHECK_LAUNCH(ctx, "sample");
+  }
+  return HFB_OK;
+}
+
+// =============================================================================================== pyramid
+// cv::resize(INTER_LINEAR) for CV_8UC1: 11-bit fixed-point coefficients, horizontal pass in int32, vertical pass
+// (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.  Tables come from build_resize_tables (host).
+__global__ void resize_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh,
+                              int dw, const int* __restrict__ xi, const short* __restrict__ xa,
+                              const int* __restrict__ yi, const short* __restrict__ ya) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw) return;
+  const uint8_t* s = src + (size_t)blockIdx.z * sh * sw;
+  const int sx = xi[x], sx1 = min(sx + 1, sw - 1);
+  const int a0 = xa[2 * x], a1 = xa[2 * x + 1];
+  const int sy = yi[y], sy1 = min(sy + 1, sh - 1);
+  const int b0 = ya[2 * y], b1 = ya[2 * y + 1];
+  const int r0 = (int)s[(size_t)sy * sw + sx] * a0 + (int)s[(size_t)sy * sw + sx1] * a1;
+  const int r1 = (int)s[(size_t)sy1 * sw + sx] * a0 + (int)s[(size_t)sy1 * sw + sx1] * a1;
+  int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+  v = v < 0 ? 0 : (v > 255 ? 255 : v);
+  dst[(size_t)blockIdx.z * dh * dw + (size_t)y * dw + x] = (uint8_t)v;
+}
+
+void build_resize_tables(int sn, int dn, std::vector<int>& idx, std::vector<short>& coef) {
+  idx.resize(dn);
+  coef.resize(2 * (size_t)dn);
+  const double scale = (double)sn / (double)dn;
+  for (int d = 0; d < dn; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+    idx[d] = s;
+    coef[2 * d] = (short)lrintf((1.f - f) * 2048.f);      // cvRound: round half to even
+    coef[2 * d + 1] = (short)lrintf(f * 2048.f);
+  }
+}
+
+int launch_resize(hfb_ctx* ctx, const uint8_t* d_src, int sh, int sw, uint8_t* d_dst, int dh, int dw, const int* d_xi,
+                  const short* d_xa, const int* d_yi, const short* d_ya, int B) {
+  dim3 grid(ceil_div(dw, 128), dh, B);
+  resize_kernel<<<grid, 128, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, d_xi, d_xa, d_yi, d_ya);
+  HFB_CHECK_LAUNCH(ctx, "resize");
+  return HFB_OK;
+}

@@ -1,0 +1,314 @@
+"""ctypes binding of ``libhfnet_b200.so`` (include/hfnet_b200.h).
+
+This is the same C-ABI the reference-side C++ shim (include/HFNetB200Model.h) binds; the Python
+host layer in this package (extractor.py, matcher.py, keyframe_database.py, optimizer.py) goes through it and never
+falls back to a CPU path: if the library is missing or the device is not a B200 the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+HFB_DESC_DIM = 256
+HFB_GLOBAL_DIM = 4096
+HFB_MAX_LEVELS = 8
+LIB_PATH = Path(__file__).resolve().parent / "libhfnet_b200.so"
+
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u8p = C.POINTER(C.c_uint8)
+
+
+class HfbError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"hfnet_b200 status {status}: {message}")
+        self.status = status
+
+
+class hfb_config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("n_levels", C.c_int32),
+                ("scale_factor", C.c_float), ("max_keypoints", C.c_int32), ("max_batch", C.c_int32),
+                ("with_global", C.c_int32)]
+
+
+class hfb_features(C.Structure):
+    _fields_ = [("x", _f32p), ("y", _f32p), ("response", _f32p), ("octave", _i32p), ("descriptors", _f32p),
+                ("global_descriptor", _f32p), ("n_per_level", C.c_int32 * HFB_MAX_LEVELS), ("n_total", C.c_int32)]
+
+
+class hfb_lba_problem(C.Structure):
+    _fields_ = [("n_cams", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("poses", _f64p),
+                ("fixed", _u8p), ("points", _f64p), ("edge_cam", _i32p), ("edge_point", _i32p), ("obs", _f64p),
+                ("inv_sigma2", _f64p), ("K", C.c_float * 4), ("huber_delta", C.c_double)]
+
+
+class hfb_lba_stats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("trials", C.c_int32), ("initial_chi2", C.c_double),
+                ("final_chi2", C.c_double), ("lambda_", C.c_double), ("n_opt_cams", C.c_int32),
+                ("gpu_launches", C.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/hfnet_b200.h declares
+SIGNATURES = {
+    "hfb_create": (C.c_int, [C.POINTER(hfb_config), C.POINTER(C.c_void_p)]),
+    "hfb_destroy": (None, [C.c_void_p]),
+    "hfb_last_error": (C.c_char_p, [C.c_void_p]),
+    "hfb_version": (C.c_int, []),
+    "hfb_sync": (C.c_int, [C.c_void_p]),
+    "hfb_stream": (C.c_void_p, [C.c_void_p]),
+    "hfb_launch_count": (C.c_uint64, [C.c_void_p]),
+    "hfb_load_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hfb_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, C.c_float,
+                              C.POINTER(hfb_features)]),
+    "hfb_extract_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _i32p, C.c_float,
+                                    C.POINTER(hfb_features)]),
+    "hfb_extract_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _i32p, C.c_float]),
+    "hfb_fetch_features": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(hfb_features)]),
+    "hfb_nms": (C.c_int, [C.c_void_p, _f32p, C.c_int32, C.c_int32, _f32p]),
+    "hfb_select_sample": (C.c_int, [C.c_void_p, _f32p, C.c_int32, C.c_int32, _f32p, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_float, _f32p, _f32p, _f32p, _f32p, _i32p]),
+    "hfb_resize_linear_u8": (C.c_int, [C.c_void_p, _u8p, C.c_int32, C.c_int32, _u8p, C.c_int32, C.c_int32]),
+    "hfb_debug_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, _f32p, C.c_size_t,
+                                   C.POINTER(C.c_size_t), _i32p]),
+    "hfb_debug_gemm": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _f32p,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
+    "hfb_match_mutual_l2": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, C.c_int32, C.c_float, _i32p, _f32p, _i32p]),
+    "hfb_match_mutual_cos": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, C.c_int32, C.c_float, _i32p, _f32p, _i32p]),
+    "hfb_match_batch": (C.c_int, [C.c_void_p, C.c_int32, _f32p, C.c_int32, _f32p, C.c_int32, C.c_int32, _i32p, _i32p,
+                                  _i32p, _i32p, C.c_float, _i32p, _f32p]),
+    "hfb_match_batch_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "hfb_kfdb_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "hfb_kfdb_destroy": (None, [C.c_void_p]),
+    "hfb_kfdb_add": (C.c_int, [C.c_void_p, _i64p, _f32p, C.c_int32]),
+    "hfb_kfdb_add_dev": (C.c_int, [C.c_void_p, _i64p, C.c_void_p, C.c_int32]),
+    "hfb_kfdb_erase": (C.c_int, [C.c_void_p, C.c_int64]),
+    "hfb_kfdb_clear": (C.c_int, [C.c_void_p]),
+    "hfb_kfdb_size": (C.c_int32, [C.c_void_p]),
+    "hfb_kfdb_query": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_float, _i64p, _f32p, C.c_int32, _i32p, _f32p]),
+    "hfb_kfdb_scores_of": (C.c_int, [C.c_void_p, _i64p, C.c_int32, _f32p]),
+    "hfb_kfdb_scan_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "hfb_kfdb_query_shard": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
+    "hfb_lba_optimize": (C.c_int, [C.c_void_p, C.POINTER(hfb_lba_problem), C.c_int32, C.c_double, _u8p, _f64p, _f64p,
+                                   _f64p, _u8p, C.POINTER(hfb_lba_stats)]),
+    "hfb_lba_build_schur": (C.c_int, [C.c_void_p, C.POINTER(hfb_lba_problem), C.c_double, _f64p, _f64p, _f64p, _i32p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load(path: Optional[Path] = None) -> C.CDLL:
+    """dlopen the library and bind every exported entry point.  Raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise FileNotFoundError(f"{p} not found: build it with `python -m hfnet_slam_b200.build` "
+                                "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def as_f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+class Context:
+    """Owns one ``hfb_ctx`` (one CUDA stream + workspaces)."""
+
+    def __init__(self, height: int = 480, width: int = 752, n_levels: int = 1, scale_factor: float = 1.2,
+                 max_keypoints: int = 1024, max_batch: int = 1, with_global: bool = True, device: int = 0):
+        self.lib = load()
+        self.cfg = hfb_config(device, height, width, n_levels, scale_factor, max_keypoints, max_batch,
+                              1 if with_global else 0)
+        self.handle = C.c_void_p()
+        st = self.lib.hfb_create(C.byref(self.cfg), C.byref(self.handle))
+        if st != 0:
+            msg = self.lib.hfb_last_error(self.handle).decode() if self.handle else "hfb_create failed"
+            if self.handle:
+                self.lib.hfb_destroy(self.handle)
+                self.handle = C.c_void_p()
+            raise HfbError(st, msg)
+        self.height, self.width, self.n_levels = height, width, n_levels
+        self.max_keypoints, self.max_batch, self.with_global = max_keypoints, max_batch, with_global
+        self.kp_cap = n_levels * max_keypoints
+
+    def check(self, st: int):
+        if st != 0:
+            raise HfbError(st, self.lib.hfb_last_error(self.handle).decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.hfb_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def sync(self):
+        self.check(self.lib.hfb_sync(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.hfb_launch_count(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.hfb_stream(self.handle) or 0)
+
+    def load_weights(self, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        self.check(self.lib.hfb_load_weights(self.handle, C.cast(buf, C.c_void_p), len(blob)))
+
+    # ------------------------------------------------------------------------------------------ extraction
+    def _alloc_features(self):
+        cap = self.kp_cap
+        arrs = dict(x=np.zeros(cap, np.float32), y=np.zeros(cap, np.float32), response=np.zeros(cap, np.float32),
+                    octave=np.zeros(cap, np.int32), descriptors=np.zeros((cap, HFB_DESC_DIM), np.float32),
+                    global_descriptor=np.zeros(HFB_GLOBAL_DIM, np.float32))
+        f = hfb_features()
+        f.x, f.y, f.response = ptr(arrs["x"], _f32p), ptr(arrs["y"], _f32p), ptr(arrs["response"], _f32p)
+        f.octave, f.descriptors = ptr(arrs["octave"], _i32p), ptr(arrs["descriptors"], _f32p)
+        f.global_descriptor = ptr(arrs["global_descriptor"], _f32p) if self.with_global else None
+        return f, arrs
+
+    @staticmethod
+    def _trim(f: hfb_features, arrs: dict, with_global: bool) -> dict:
+        n = int(f.n_total)
+        out = {k: arrs[k][:n].copy() for k in ("x", "y", "response", "octave", "descriptors")}
+        out["n_per_level"] = [int(v) for v in f.n_per_level]
+        out["global_descriptor"] = arrs["global_descriptor"].copy() if with_global else None
+        return out
+
+    def extract_batch(self, images, n_per_level, threshold: float):
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        for im in imgs:
+            if im.ndim != 2 or im.shape != (self.height, self.width):
+                raise HfbError(1, f"image shape {im.shape} differs from the context's {(self.height, self.width)}")
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        budgets = (C.c_int32 * HFB_MAX_LEVELS)(*([int(v) for v in n_per_level] + [0] * (HFB_MAX_LEVELS - len(n_per_level))))
+        feats = (hfb_features * n)()
+        keep = []
+        for i in range(n):
+            f, arrs = self._alloc_features()
+            feats[i] = f
+            keep.append(arrs)
+        self.check(self.lib.hfb_extract_batch(self.handle, ptrs, n, self.width, budgets, threshold, feats))
+        return [self._trim(feats[i], keep[i], self.with_global) for i in range(n)]
+
+    def extract(self, image, n_per_level, threshold: float) -> dict:
+        return self.extract_batch([image], n_per_level, threshold)[0]
+
+    def extract_batch_dev(self, d_images_ptr: int, n_images: int, n_per_level, threshold: float):
+        budgets = (C.c_int32 * HFB_MAX_LEVELS)(*([int(v) for v in n_per_level] + [0] * (HFB_MAX_LEVELS - len(n_per_level))))
+        self.check(self.lib.hfb_extract_batch_dev(self.handle, C.c_void_p(d_images_ptr), n_images, budgets, threshold))
+
+    def fetch_features(self, image_index: int) -> dict:
+        f, arrs = self._alloc_features()
+        self.check(self.lib.hfb_fetch_features(self.handle, image_index, C.byref(f)))
+        return self._trim(f, arrs, self.with_global)
+
+    def debug_tensor(self, name: str, image_index: int = 0, level: int = 0) -> np.ndarray:
+        n = C.c_size_t()
+        dims = (C.c_int32 * 4)()
+        st = self.lib.hfb_debug_tensor(self.handle, name.encode(), image_index, level, None, 0, C.byref(n), dims)
+        if n.value == 0:
+            self.check(st)
+        out = np.zeros(n.value, np.float32)
+        self.check(self.lib.hfb_debug_tensor(self.handle, name.encode(), image_index, level, ptr(out, _f32p),
+                                             out.size, C.byref(n), dims))
+        return out.reshape([int(d) for d in dims])
+
+    # ------------------------------------------------------------------------------------------ network tail hooks
+    def nms(self, scores: np.ndarray) -> np.ndarray:
+        s = as_f32(scores)
+        out = np.empty_like(s)
+        self.check(self.lib.hfb_nms(self.handle, ptr(s, _f32p), s.shape[0], s.shape[1], ptr(out, _f32p)))
+        return out
+
+    def select_sample(self, scores_nms: np.ndarray, desc_map: np.ndarray, n_keypoints: int, threshold: float) -> dict:
+        s, d = as_f32(scores_nms), as_f32(desc_map)
+        cap = max(n_keypoints, 1)
+        x, y, r = (np.zeros(cap, np.float32) for _ in range(3))
+        desc = np.zeros((cap, HFB_DESC_DIM), np.float32)
+        n = C.c_int32()
+        self.check(self.lib.hfb_select_sample(self.handle, ptr(s, _f32p), s.shape[0], s.shape[1], ptr(d, _f32p),
+                                              d.shape[0], d.shape[1], n_keypoints, threshold, ptr(x, _f32p),
+                                              ptr(y, _f32p), ptr(r, _f32p), ptr(desc, _f32p), C.byref(n)))
+        k = n.value
+        return {"x": x[:k], "y": y[:k], "response": r[:k], "descriptors": desc[:k]}
+
+    def resize_linear_u8(self, src: np.ndarray, dh: int, dw: int) -> np.ndarray:
+        s = np.ascontiguousarray(src, dtype=np.uint8)
+        out = np.empty((dh, dw), np.uint8)
+        self.check(self.lib.hfb_resize_linear_u8(self.handle, ptr(s, _u8p), s.shape[0], s.shape[1], ptr(out, _u8p),
+                                                 dh, dw))
+        return out
+
+    def debug_gemm(self, A: np.ndarray, Wt: np.ndarray, bias=None, relu6=False, conv3x3=False, use_tc=True,
+                   BN: int = 0) -> np.ndarray:
+        """A: [B,H,W,K] (or [M,K]); Wt: [N, K] (or [N, 9K] for conv3x3).  fp16 operands, fp32 result [.., N]."""
+        a = as_f32(A)
+        if a.ndim == 2:
+            a = a[None, None]
+        B, H, W, K = a.shape
+        w = as_f32(Wt)
+        N = w.shape[0]
+        out = np.empty((B * H * W, N), np.float32)
+        b = as_f32(bias) if bias is not None else None
+        self.check(self.lib.hfb_debug_gemm(self.handle, ptr(a, _f32p), B, H, W, K, ptr(w, _f32p), N,
+                                           ptr(b, _f32p) if b is not None else None, int(relu6), int(conv3x3),
+                                           int(use_tc), BN, ptr(out, _f32p)))
+        return out.reshape(B, H, W, N) if np.asarray(A).ndim == 4 else out
+
+    # ------------------------------------------------------------------------------------------ matching
+    def _match(self, fn, A, B, thr):
+        a, b = as_f32(A).reshape(-1, HFB_DESC_DIM), as_f32(B).reshape(-1, HFB_DESC_DIM)
+        idx = np.full(a.shape[0], -1, np.int32)
+        val = np.zeros(a.shape[0], np.float32)
+        n = C.c_int32()
+        self.check(fn(self.handle, ptr(a, _f32p), a.shape[0], ptr(b, _f32p), b.shape[0], thr, ptr(idx, _i32p),
+                      ptr(val, _f32p), C.byref(n)))
+        return idx, val, n.value
+
+    def match_mutual_l2(self, A, B, max_dist: float):
+        return self._match(self.lib.hfb_match_mutual_l2, A, B, max_dist)
+
+    def match_mutual_cos(self, A, B, min_cos: float):
+        return self._match(self.lib.hfb_match_mutual_cos, A, B, min_cos)
+
+    def match_batch(self, mode: int, A_all, B_all, a_off, a_cnt, b_off, b_cnt, thr: float):
+        a, b = as_f32(A_all).reshape(-1, HFB_DESC_DIM), as_f32(B_all).reshape(-1, HFB_DESC_DIM)
+        tabs = [np.ascontiguousarray(t, dtype=np.int32) for t in (a_off, a_cnt, b_off, b_cnt)]
+        idx = np.full(a.shape[0], -1, np.int32)
+        val = np.zeros(a.shape[0], np.float32)
+        self.check(self.lib.hfb_match_batch(self.handle, mode, ptr(a, _f32p), a.shape[0], ptr(b, _f32p), b.shape[0],
+                                            len(tabs[0]), *[ptr(t, _i32p) for t in tabs], thr, ptr(idx, _i32p),
+                                            ptr(val, _f32p)))
+        return idx, val

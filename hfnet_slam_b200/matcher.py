@@ -1,0 +1,60 @@
+"""Host-side mirror of the brute-force flavours of ``Matcher`` (include/Matcher.h:43-89, src/Matcher.cc) over the GPU
+distance + arg-max kernel.  Constants as in src/Matcher.cc:33-34.  The geometric filters around the descriptor search
+(epipolar test of SearchForTriangulation :894-909, map-point bookkeeping of SearchByBoW :236-262) use the caller's
+map and stay on the host; these methods return the descriptor-level correspondences those loops consume."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from .lib import Context
+
+TH_HIGH = 0.75
+TH_LOW = 0.6
+COS_FLOOR = float(np.float32(-0.5 * 0.75 * 0.75 + 1))   # src/Matcher.cc:851
+
+
+class Matcher:
+    def __init__(self, ctx: Context, nnratio: float = 0.6, check_orientation: bool = True):
+        self.ctx, self.nnratio, self.check_orientation = ctx, nnratio, check_orientation
+
+    @staticmethod
+    def descriptor_distance(a: np.ndarray, b: np.ndarray) -> float:
+        """Matcher::DescriptorDistance (src/Matcher.cc:1893-1900)."""
+        d = np.asarray(a, np.float32) - np.asarray(b, np.float32)
+        return float(np.sqrt(np.sum(d * d, dtype=np.float32)))
+
+    def search_by_bow(self, desc1: np.ndarray, desc2: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """cv::BFMatcher(NORM_L2, crossCheck=true).match + dist < TH_LOW (src/Matcher.cc:229-253, 574-610).
+        Returns (idx1, idx2, distance) sorted by idx1."""
+        idx, val, _ = self.ctx.match_mutual_l2(desc1, desc2, TH_LOW)
+        i = np.flatnonzero(idx >= 0)
+        return i.astype(np.int32), idx[i], val[i]
+
+    def search_for_triangulation(self, desc1: np.ndarray, desc2: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """The descriptor stage of SearchForTriangulation (src/Matcher.cc:845-889): (idx1, idx2, cosine)."""
+        idx, val, _ = self.ctx.match_mutual_cos(desc1, desc2, COS_FLOOR)
+        i = np.flatnonzero(idx >= 0)
+        return i.astype(np.int32), idx[i], val[i]
+
+    def search_for_triangulation_batch(self, desc1: np.ndarray, neighbours: Sequence[np.ndarray]) -> List[tuple]:
+        """One CreateNewMapPoints (src/LocalMapping.cc:513-893): the current keyframe against <= 30 covisible
+        keyframes in ONE launch."""
+        n = len(neighbours)
+        if n == 0:
+            return []
+        a = np.ascontiguousarray(desc1, np.float32).reshape(-1, 256)
+        A_all = np.concatenate([a] * n) if a.shape[0] else a
+        cnt_a = np.full(n, a.shape[0], np.int32)
+        cnt_b = np.array([nb.shape[0] for nb in neighbours], np.int32)
+        B_all = np.concatenate([np.ascontiguousarray(nb, np.float32).reshape(-1, 256) for nb in neighbours])
+        a_off = (np.arange(n) * a.shape[0]).astype(np.int32)
+        b_off = np.concatenate([[0], np.cumsum(cnt_b)[:-1]]).astype(np.int32)
+        idx, val = self.ctx.match_batch(1, A_all, B_all, a_off, cnt_a, b_off, cnt_b, COS_FLOOR)
+        out = []
+        for p in range(n):
+            sl = slice(a_off[p], a_off[p] + cnt_a[p])
+            i = np.flatnonzero(idx[sl] >= 0)
+            out.append((i.astype(np.int32), idx[sl][i], val[sl][i]))
+        return out

@@ -1,0 +1,144 @@
+"""HF-Net encoder + selection through the C-ABI against the fp32 oracle (oracle/hfnet_ref.py) with seeded synthetic
+weights.  Tolerances (fp16 operands / activations, fp32 accumulation; the reference itself runs TensorRT FP16,
+src/Extractors/HFNetRTModel.cc:231):  dense score map |err| <= 3e-3 abs, descriptor map cosine >= 0.999,
+global descriptor cosine >= 0.999; keypoint selection is bit-exact GIVEN the device's own dense maps (re-run through the
+oracle's post-processing) and >= 90 % identical to the all-fp32 oracle selection."""
+import numpy as np
+import pytest
+
+from hfnet_slam_b200 import weights
+from hfnet_slam_b200.lib import Context
+from oracle import hfnet_ref, select_ref
+
+pytestmark = pytest.mark.gpu
+SCORE_TOL = 3e-3
+COS_TOL = 0.999
+
+
+@pytest.fixture(scope="module")
+def ctx_euroc(native_lib, weights_blob):
+    import os
+    os.environ["HFB_DEBUG"] = "1"
+    ctx = Context(height=480, width=752, n_levels=1, max_keypoints=1000, max_batch=2, with_global=True)
+    ctx.load_weights(weights_blob)
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def oracle_euroc(weights_dict):
+    img = weights.synthetic_image(480, 752, seed=1)
+    return img, hfnet_ref.forward(img, weights_dict, want_global=True, return_intermediates=True)
+
+
+def _cos(a, b):
+    a, b = a.reshape(-1, a.shape[-1]).astype(np.float64), b.reshape(-1, b.shape[-1]).astype(np.float64)
+    return (a * b).sum(1) / np.maximum(np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1), 1e-30)
+
+
+def test_layers_track_oracle(ctx_euroc, oracle_euroc):
+    img, ref = oracle_euroc
+    ctx_euroc.extract(img, [1000], 0.01)
+    report = []
+    for name in ["layer_1", "layer_2", "layer_3", "layer_4", "layer_5", "layer_6", "layer_7", "layer_8", "layer_12",
+                 "layer_15", "layer_18", "desc_conv1", "det_conv1", "det_logits"]:
+        got = ctx_euroc.debug_tensor(name)[0]
+        r = ref[name][0]
+        assert got.shape == r.shape, f"{name}: shape {got.shape} vs {r.shape}"
+        scale = np.abs(r).max() + 1e-9
+        err = np.abs(got - r).max() / scale
+        report.append((name, float(err)))
+    msg = ", ".join(f"{n}:{e:.2e}" for n, e in report)
+    assert all(e < 3e-2 for _, e in report), "relative max error per layer: " + msg
+
+
+def test_dense_outputs(ctx_euroc, oracle_euroc):
+    img, ref = oracle_euroc
+    ctx_euroc.extract(img, [1000], 0.01)
+    scores = ctx_euroc.debug_tensor("scores_dense")[0, :, :, 0]
+    err = np.abs(scores - ref["scores_dense"][0]).max()
+    assert err <= SCORE_TOL, f"dense score map max abs err {err}"
+    dm = ctx_euroc.debug_tensor("local_descriptor_map")[0]
+    c = _cos(dm, ref["local_descriptor_map"][0])
+    assert c.min() >= COS_TOL, f"descriptor map min cosine {c.min()}"
+    assert np.abs(np.linalg.norm(dm, axis=-1) - 1).max() < 1e-5
+    g = ctx_euroc.debug_tensor("global_descriptor").reshape(1, -1)
+    cg = _cos(g, ref["global_descriptor"])
+    assert cg.min() >= COS_TOL, f"global descriptor cosine {cg.min()}"
+
+
+def test_selection_exact_on_device_maps(ctx_euroc, oracle_euroc):
+    img, ref = oracle_euroc
+    out = ctx_euroc.extract(img, [1000], 0.01)
+    scores = ctx_euroc.debug_tensor("scores_dense")[0, :, :, 0]
+    nms_dev = ctx_euroc.debug_tensor("scores_dense_nms")[0, :, :, 0]
+    import torch
+    nms_ref = hfnet_ref.simple_nms(torch.from_numpy(scores)[None], 4, 2)[0].numpy()
+    assert np.array_equal(nms_dev, nms_ref), "in-graph NMS differs from the oracle on the device's own score map"
+    dm = ctx_euroc.debug_tensor("local_descriptor_map")[0]
+    exp = select_ref.local_features(nms_dev, dm, 1000, 0.01)
+    assert out["n_per_level"][0] == len(exp["x"]) == len(out["x"])
+    for k in ("x", "y", "response"):
+        assert np.array_equal(out[k], exp[k]), k
+    assert np.array_equal(out["descriptors"], exp["descriptors"])
+    assert (out["octave"] == 0).all()
+    # against the all-fp32 oracle: same keypoints up to score-noise swaps at the cut
+    full = select_ref.local_features(ref["scores_dense_nms"][0], ref["local_descriptor_map"][0], 1000, 0.01)
+    a = set(zip(out["x"].astype(int).tolist(), out["y"].astype(int).tolist()))
+    b = set(zip(full["x"].astype(int).tolist(), full["y"].astype(int).tolist()))
+    iou = len(a & b) / max(len(a | b), 1)
+    assert len(b) > 100, "synthetic weights should give a non-trivial keypoint set"
+    assert iou >= 0.9, f"keypoint set IoU vs fp32 oracle {iou:.3f} ({len(a)} vs {len(b)})"
+    g = out["global_descriptor"].reshape(1, -1)
+    assert _cos(g, ref["global_descriptor"]).min() >= COS_TOL
+
+
+def test_batch_equals_single(ctx_euroc, oracle_euroc):
+    img, _ = oracle_euroc
+    img2 = weights.synthetic_image(480, 752, seed=5)
+    one = ctx_euroc.extract(img, [1000], 0.01)
+    two = ctx_euroc.extract_batch([img2, img], [1000], 0.01)
+    for k in ("x", "y", "response", "descriptors", "global_descriptor"):
+        assert np.array_equal(one[k], two[1][k]), k
+    assert not np.array_equal(two[0]["global_descriptor"], two[1]["global_descriptor"])
+
+
+def test_multilevel_pyramid(native_lib, weights_blob, weights_dict):
+    """4-level EuRoC configuration (Examples/Monocular/EuRoC.yaml:67-80 -> 675 features, 1.2, 4 levels) on a smaller frame."""
+    H, W = 240, 376
+    img = weights.synthetic_image(H, W, seed=2, n_corners=80)
+    budgets = select_ref.features_per_level(675, 4, 1.2)
+    with Context(height=H, width=W, n_levels=4, scale_factor=1.2, max_keypoints=1000, max_batch=1) as ctx:
+        ctx.load_weights(weights_blob)
+        out = ctx.extract(img, budgets, 0.01)
+        pyr = select_ref.compute_pyramid(img, 4, 1.2)
+        per_level = []
+        for l, im in enumerate(pyr):
+            nms = ctx.debug_tensor("scores_dense_nms", level=l)[0, :, :, 0]
+            dm = ctx.debug_tensor("local_descriptor_map", level=l)[0]
+            assert nms.shape == (im.shape[0] // 8 * 8, im.shape[1] // 8 * 8)
+            per_level.append(select_ref.local_features(nms, dm, budgets[l], 0.01))
+            # dense maps of every level track the fp32 oracle run on the cv2 pyramid
+            r = hfnet_ref.forward(im, weights_dict, want_global=False)
+            sc = ctx.debug_tensor("scores_dense", level=l)[0, :, :, 0]
+            assert np.abs(sc - r["scores_dense"][0]).max() <= SCORE_TOL, f"level {l}"
+        exp = select_ref.concat_levels(per_level, 1.2)
+        assert out["n_per_level"][:4] == [len(p["x"]) for p in per_level]
+        for k in ("x", "y", "response", "octave", "descriptors"):
+            assert np.array_equal(out[k], exp[k]), k
+
+
+def test_errors_are_loud(native_lib, weights_blob):
+    from hfnet_slam_b200.lib import HfbError
+    with Context(height=64, width=64, n_levels=1, max_keypoints=100, max_batch=1) as ctx:
+        with pytest.raises(HfbError):
+            ctx.extract(np.zeros((64, 64), np.uint8), [10], 0.01)          # weights not loaded
+        ctx.load_weights(weights_blob)
+        with pytest.raises(HfbError):
+            ctx.extract(np.zeros((32, 64), np.uint8), [10], 0.01)          # wrong shape
+        with pytest.raises(HfbError):
+            ctx.extract(np.zeros((64, 64), np.uint8), [1000], 0.01)        # budget above capacity
+        with pytest.raises(HfbError):
+            ctx.load_weights(b"garbage" * 10)
+        out = ctx.extract(np.zeros((64, 64), np.uint8), [0], 0.01)         # zero budget is legal
+        assert out["x"].size == 0

@@ -1,0 +1,99 @@
+"""Keyframe-database scan through the C-ABI against oracle/kfdb_ref.py: scores within 2e-6 (fp32 vs fp64 norm),
+identical candidate sets except rows within 5e-6 of the relative threshold (summation-order noise, written here),
+identical final loop/merge candidates."""
+import numpy as np
+import pytest
+
+from hfnet_slam_b200 import synthetic
+from hfnet_slam_b200.keyframe_database import KeyFrameDatabase
+from oracle import kfdb_ref
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-6
+
+
+def _covis(n):
+    return lambda kf, k: [j for j in range(kf - 5, kf + 6) if j != kf and 0 <= j < n][:k]
+
+
+@pytest.mark.parametrize("n,seed", [(3000, 2), (257, 3), (1, 4)])
+def test_query_matches_oracle(small_ctx, n, seed):
+    db, q, qi = synthetic.keyframe_db(n, 4096, n_planted=min(50, n // 2), seed=seed, n_queries=1)
+    ids = np.arange(n, dtype=np.int64) * 3 + 7
+    kf = KeyFrameDatabase(small_ctx, capacity=n + 8)
+    kf.add_many(ids, db)
+    cand, scores, best = kf.query(q[0], rel=0.8, floor=0.0)
+    sc_ref = kfdb_ref.scores(q[0], db)
+    sel, best_ref = kfdb_ref.candidate_set(sc_ref, 0.8)
+    assert abs(best - best_ref) <= TOL
+    thr = 0.8 * best_ref
+    sure = {int(ids[i]) for i in sel if sc_ref[i] > thr + 5e-6}
+    maybe = {int(ids[i]) for i in np.flatnonzero(np.abs(sc_ref - thr) <= 5e-6)}
+    got = set(int(c) for c in cand)
+    assert sure <= got <= (sure | maybe), f"{len(got)} vs {len(sure)}"
+    assert list(cand) == sorted(cand)
+    all_sc = kf.scores_of(ids)
+    assert np.abs(all_sc - sc_ref).max() <= TOL
+    assert kf.scores_of(np.array([-5], np.int64))[0] == -1
+
+
+def test_detect_n_best_candidates(small_ctx):
+    n = 2000
+    db, q, qi = synthetic.keyframe_db(n, 4096, n_planted=100, seed=5, n_queries=3)
+    ids = np.arange(n, dtype=np.int64)
+    map_of = {int(i): (0 if i < 1500 else 1) for i in ids}
+    kf = KeyFrameDatabase(small_ctx, capacity=n)
+    kf.add_many(ids, db)
+    for k in range(3):
+        loop, merge = kf.detect_n_best_candidates(q[k], query_map=0, map_of=map_of, covisibles=_covis(n), n_candidates=3)
+        l_ref, m_ref, _ = kfdb_ref.detect_n_best_candidates(q[k], ids, db, map_of, 0, _covis(n), 3)
+        assert set(loop) == set(l_ref) and set(merge) == set(m_ref)
+        reloc = kf.detect_relocalization_candidates(q[k], query_map=0, map_of=map_of, covisibles=_covis(n))
+        r_ref = kfdb_ref.detect_relocalization_candidates(q[k], ids, db, map_of, 0, _covis(n))
+        assert set(reloc) == set(r_ref)
+
+
+def test_add_erase_clear(small_ctx):
+    db, q, _ = synthetic.keyframe_db(64, 4096, n_planted=8, seed=6)
+    ids = np.arange(64, dtype=np.int64)
+    kf = KeyFrameDatabase(small_ctx, capacity=64)
+    kf.add_many(ids[:40], db[:40])
+    for i in range(40, 64):
+        kf.add(int(ids[i]), db[i])
+    assert len(kf) == 64
+    with pytest.raises(Exception):
+        kf.add(0, db[0])                      # duplicate id
+    with pytest.raises(Exception):
+        kf.add(1000, db[0])                   # capacity
+    kf.erase(5); kf.erase(63); kf.erase(12345)
+    assert len(kf) == 62
+    keep = np.array([i for i in range(64) if i not in (5, 63)])
+    cand, scores, best = kf.query(q[0])
+    sc_ref = kfdb_ref.scores(q[0], db[keep])
+    assert np.abs(kf.scores_of(ids[keep]) - sc_ref).max() <= TOL
+    assert kf.scores_of(np.array([5], np.int64))[0] == -1
+    kf.clear()
+    assert len(kf) == 0
+    cand, scores, best = kf.query(q[0])
+    assert len(cand) == 0 and best == 0.0
+
+
+def test_shard_records_merge_to_global_set(small_ctx):
+    """Row-shard by id % world, one fixed-size record per shard, merged == unsharded candidate set."""
+    from hfnet_slam_b200.keyframe_database import merge_shard_records
+    n, world = 4000, 4
+    db, q, _ = synthetic.keyframe_db(n, 4096, n_planted=200, seed=8)
+    ids = np.arange(n, dtype=np.int64)
+    full = KeyFrameDatabase(small_ctx, capacity=n)
+    full.add_many(ids, db)
+    cand, scores, best = full.query(q[0])
+    recs = []
+    for r in range(world):
+        sh = KeyFrameDatabase(small_ctx, capacity=n // world + 1)
+        m = ids % world == r
+        sh.add_many(ids[m], db[m])
+        recs.append(sh.query_shard(q[0], k=64))
+    m_ids, m_scores, m_best, overflow = merge_shard_records(recs, rel=0.8, floor=0.0)
+    assert not overflow and m_best == best
+    assert list(m_ids) == list(cand)
+    assert np.array_equal(m_scores, scores)
