@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the HFNet-SLAM per-frame front-end on B200 (BASELINE.json metric "frames/sec extract+match 752x480;
+local-BA ms/iter; loop-DB queries/sec").
+
+One step = one pass of the hot path over one batch of synthetic 752x480 frames: HF-Net extraction (1 level, 1000
+keypoints + 256-d local + 4096-d global, BASELINE.json configs[1]) followed by the mutual-NN L2 match of every frame
+against its predecessor (configs[0]'s 1000x1000 brute-force match).  ``value`` = frames/s with the u8 frames already in
+HBM (device-resident call chain); ``e2e`` = the same work through the host-buffer C-ABI calls the reference shim binds
+(pinned H2D of the frames, D2H of keypoints / descriptors / matches inside the timed region).  The other two parts of
+the metric (local-BA ms/iter, loop-DB queries/s over a 50 k x 4096 database) are reported under ``extra``.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                      (CPU arm: the oracle port on the host cores)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H, W, NKP, THR = 480, 752, 1000, 0.01
+METRIC = "frames/sec extract+match 752x480"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), tf=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    tf_burst=float(d["bf16_tflops"]), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_frames(n: int, seed0: int):
+    from hfnet_slam_b200 import weights
+    base = [weights.synthetic_image(H, W, seed=seed0 + i, n_corners=300) for i in range(min(n, 4))]
+    out = []
+    for i in range(n):      # cheap variations of a few rendered frames (shifted + flipped), distinct content per frame
+        im = np.roll(base[i % len(base)], (7 * i, 13 * i), axis=(0, 1))
+        out.append(np.ascontiguousarray(im[:, ::-1] if (i // len(base)) % 2 else im))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def cpu_frame_pass(wd, prev_desc, img, cv2):
+    """The reference's per-frame path restated on the CPU (oracle/): fp32 network forward (torch CPU, all threads),
+    CPU threshold / top-k / resample / normalise, cv::BFMatcher(NORM_L2, crossCheck) + dist < 0.6 vs the previous frame."""
+    from oracle import hfnet_ref, select_ref
+    r = hfnet_ref.forward(img, wd, want_global=True)
+    f = select_ref.local_features(r["scores_dense_nms"][0], r["local_descriptor_map"][0], NKP, THR)
+    n = 0
+    if prev_desc is not None and len(prev_desc) and len(f["descriptors"]):
+        ms = cv2.BFMatcher(cv2.NORM_L2, crossCheck=True).match(f["descriptors"], prev_desc)
+        n = sum(1 for m in ms if m.distance < 0.6)
+    return f["descriptors"], n
+
+
+def run_cpu(frames: int, warm: int):
+    import cv2
+    import torch
+    from hfnet_slam_b200 import weights
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cv2.setNumThreads(cores)
+    wd = weights.synthetic(seed=0)
+    imgs = synthetic_frames(frames + warm + 1, 100)
+    prev, _ = cpu_frame_pass(wd, None, imgs[0], cv2)
+    for i in range(warm):
+        prev, _ = cpu_frame_pass(wd, prev, imgs[1 + i], cv2)
+    t0 = time.perf_counter()
+    for i in range(frames):
+        prev, _ = cpu_frame_pass(wd, prev, imgs[1 + warm + i], cv2)
+    dt = time.perf_counter() - t0
+    return frames / dt, cores, dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = 1
+    fps, cores, dt = run_cpu(args.steps * per_step, min(args.warmup, 2))
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "HF-Net extract single 752x480 grayscale -> 1000 kpts + 256-d local + 4096-d global "
+                                   "+ mutual-NN L2 match vs previous frame (BASELINE.json configs[1] + configs[0])",
+                       "frames_per_step": per_step, "threshold": THR},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} frames: oracle fp32 forward (torch CPU) + CPU select/resample + "
+                                       "cv2.BFMatcher crossCheck"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- B200 arm
+def main_gpu(args):
+    import torch
+    from hfnet_slam_b200 import synthetic, weights
+    from hfnet_slam_b200.keyframe_database import KeyFrameDatabase, merge_shard_records
+    from hfnet_slam_b200.lib import Context
+    from hfnet_slam_b200.optimizer import local_bundle_adjustment
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch
+    pk = peaks()
+
+    ctx = Context(height=H, width=W, n_levels=1, max_keypoints=NKP, max_batch=B, with_global=True, device=local)
+    ctx.load_weights(weights.synthetic_blob(seed=0))
+    frames = synthetic_frames(B, 1000 * rank)
+    d_frames = torch.from_numpy(np.stack(frames)).to(dev)            # resident in HBM before the timed region
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    budgets = [NKP]
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_dev():
+        ctx.extract_batch_dev(d_frames.data_ptr(), B, budgets, THR)
+        ctx.match_consecutive_dev(B, 0, 0.6)
+
+    def step_host():
+        feats = ctx.extract_batch(frames, budgets, THR)
+        cnt = np.array([len(f["x"]) for f in feats], np.int32)
+        descs = np.concatenate([f["descriptors"] for f in feats])
+        off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32)
+        prev = (np.arange(B) - 1) % B
+        idx, val = ctx.match_batch(0, descs, descs, off, cnt, off[prev], cnt[prev], 0.6)
+        return feats, cnt, idx
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        lc0 = ctx.launch_count
+        wall0 = time.perf_counter()
+        for s in range(steps):
+            flush.fill_(s & 0xFF)                                    # L2 flush between timed iterations (untimed)
+            torch.cuda.synchronize(dev)
+            ev[s][0].record(stream)
+            fn()
+            ev[s][1].record(stream)
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        return ms, wall, ctx.launch_count - lc0
+
+    warm = max(args.warmup, 3)
+    with ClockSampler(local) as cs:
+        ms_dev, wall_dev, launches = timed(step_dev, args.steps, warm)
+    clocks = cs.summary()
+    ms_host, wall_host, _ = timed(step_host, max(3, args.steps // 4), 2)
+    n_host = max(3, args.steps // 4)
+    # sanity inside the bench: the device chain produced real keypoints and matches
+    f0 = ctx.fetch_features(0)
+    ctx.match_consecutive_dev(B, 0, 0.6)
+    midx, _ = ctx.fetch_matches(0, len(f0["x"]))
+    feats, cnt, hidx = step_host()
+
+    def maxred(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_dev, ms_host = maxred(ms_dev), maxred(ms_host)
+    value = world * B * args.steps / (ms_dev / 1e3)
+    e2e = world * B * n_host / (ms_host / 1e3)
+    h2d = B * H * W + 2 * int(cnt.sum()) * 256 * 4 + 16 * B
+    d2h = int(cnt.sum()) * (16 + 256 * 4) + B * (4096 * 4 + 32) + 2 * int(cnt.sum()) * 4
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the library's stream
+    prof = ctx.profile_extract(B, budgets, THR)
+    prof = ctx.profile_extract(B, budgets, THR)
+    agg = {}
+    for r in prof:
+        a = agg.setdefault(r["name"], dict(ms=0.0, bytes=0.0, flops=0.0, n=0))
+        a["ms"] += r["ms"]; a["bytes"] += r["bytes"]; a["flops"] += r["flops"]; a["n"] += 1
+    total_ms = sum(a["ms"] for a in agg.values())
+    top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    name, a = top
+    t_s = a["ms"] / 1e3 / a["n"]
+    by, fl = a["bytes"] / a["n"], a["flops"] / a["n"]
+    frac_h = by / t_s / 1e9 / pk["hbm"] if t_s > 0 else 0.0
+    frac_t = fl / t_s / 1e12 / pk["tf"] if t_s > 0 else 0.0
+    if frac_t >= frac_h:
+        roof = {"bound": "tensor", "achieved": fl / t_s / 1e12, "peak": pk["tf"], "unit": "TFLOP/s", "frac": frac_t}
+    else:
+        roof = {"bound": "hbm", "achieved": by / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": frac_h}
+    roof.update({"traffic": None, "kernel": name, "ms_per_launch": a["ms"] / a["n"], "share_of_step": a["ms"] / total_ms,
+                 "peak_source": pk["src"], "algorithmic_bytes": by, "algorithmic_flops": fl})
+    kernels = sorted(({"name": k, "ms": v["ms"], "share": v["ms"] / total_ms,
+                       "hbm_frac": (v["bytes"] / (v["ms"] / 1e3) / 1e9 / pk["hbm"]) if v["ms"] > 0 else 0,
+                       "tensor_frac": (v["flops"] / (v["ms"] / 1e3) / 1e12 / pk["tf"]) if v["ms"] > 0 else 0}
+                      for k, v in agg.items()), key=lambda r: -r["ms"])[:12]
+
+    extra = {"keypoints_frame0": int(len(f0["x"])), "matches_frame0": int((midx >= 0).sum()),
+             "host_matches_frame0": int((hidx[:cnt[0]] >= 0).sum()), "ungraphed_step_ms": total_ms, "kernels": kernels}
+
+    # ---- the other two parts of the metric ------------------------------------------------------------------
+    if not args.skip_extra:
+        # loop-DB: 50 k x 4096 fp32 rows sharded by id % world, one all-gather of fixed-size shard records
+        n_db = args.db_rows
+        rows = torch.randn(n_db // world, 4096, device=dev)
+        rows /= rows.norm(dim=1, keepdim=True)
+        kf = KeyFrameDatabase(ctx, capacity=rows.shape[0])
+        ids = (np.arange(rows.shape[0], dtype=np.int64) * world + rank)
+        from hfnet_slam_b200.lib import _i64p, ptr
+        ctx.check(ctx.lib.hfb_kfdb_add_dev(kf.handle, ptr(ids, _i64p), rows.data_ptr(), rows.shape[0]))
+        q = rows[5].cpu().numpy() + 0.002 * np.random.default_rng(0).standard_normal(4096).astype(np.float32)
+        q /= np.linalg.norm(q)
+        nq = 50
+        for _ in range(3):
+            kf.query_shard(q, k=64)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nq):
+            rec = kf.query_shard(q, k=64)
+            if dist is not None:
+                t = torch.frombuffer(bytearray(rec), dtype=torch.uint8).to(dev)
+                out = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(out, t)
+                recs = [bytes(o.cpu().numpy()) for o in out]
+            else:
+                recs = [rec]
+            merge_shard_records(recs)
+        barrier()
+        dt = maxred(time.perf_counter() - t0)
+        # device-only scan (HBM roofline of the scan kernel)
+        dq = torch.from_numpy(q).to(dev)
+        dsc = torch.empty(rows.shape[0], device=dev)
+        dbest = torch.empty(1, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            ctx.check(ctx.lib.hfb_kfdb_scan_dev(kf.handle, dq.data_ptr(), 1, dsc.data_ptr(), dbest.data_ptr()))
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(20):
+            ctx.check(ctx.lib.hfb_kfdb_scan_dev(kf.handle, dq.data_ptr(), 1, dsc.data_ptr(), dbest.data_ptr()))
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        scan_ms = e0.elapsed_time(e1) / 20
+        scan_gbs = rows.shape[0] * 4096 * 4 / (scan_ms / 1e3) / 1e9
+        extra["loopdb"] = {"rows_total": n_db, "rows_per_gpu": int(rows.shape[0]), "queries_per_sec_e2e": nq / dt,
+                           "scan_ms": scan_ms, "scan_gbs": scan_gbs, "scan_hbm_frac": scan_gbs / pk["hbm"],
+                           "collective": "all_gather(16+16*64 B per rank)" if world > 1 else "none"}
+        kf.close()
+        del rows
+        # local BA (C3-shaped problem: 20 optimisable + 40 fixed keyframes, 3000 landmarks), replicas only
+        prob = synthetic.lba_problem(n_opt=20, n_fixed=40, n_points=3000, seed=3)
+        local_bundle_adjustment(ctx, prob, iterations=2)
+        t0 = time.perf_counter()
+        out = local_bundle_adjustment(ctx, prob, iterations=10)
+        dt = time.perf_counter() - t0
+        extra["lba"] = {"ms_per_iter": 1e3 * dt / max(out["iterations"], 1), "ms_total": 1e3 * dt,
+                        "iterations": out["iterations"], "trials": out["trials"], "edges": int(len(prob["cam_idx"])),
+                        "chi2": [out["initial_chi2"], out["final_chi2"]], "gpu_launches": out["gpu_launches"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        fps, cores, dt = run_cpu(args.cpu_frames, 1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_frames} frames of the same workload: oracle fp32 forward (torch CPU, {cores} threads) + CPU "
+                         f"select/resample + cv2.BFMatcher crossCheck, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (network), f32 (select, match recheck)",
+                "data": "synthetic",
+                "config": {"workload": "HF-Net extract single 752x480 grayscale -> 1000 kpts + 256-d local + 4096-d global "
+                                       "+ mutual-NN L2 match vs previous frame (BASELINE.json configs[1] + configs[0])",
+                           "frames_per_step": B, "threshold": THR, "levels": 1, "weights": "seeded random init",
+                           "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"replicas x{world}"},
+                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_host / n_host},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extra": extra,
+                "wall_s": {"device_loop": wall_dev, "host_loop": wall_host}}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="frames per step and GPU")
+    ap.add_argument("--db-rows", type=int, default=50000)
+    ap.add_argument("--cpu-frames", type=int, default=12)
+    ap.add_argument("--skip-extra", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,7 @@
       return HFB_ERR_CUDA;                                                                       \
     }                                                                                            \
     (ctx)->launches++;                                                                           \
+    if ((ctx)->prof_on) (ctx)->prof_mark(what);                                                  \
   } while (0)
 
 #define HFB_REQUIRE(ctx, cond, msg)                                                              \
@@ -139,6 +140,29 @@ struct hfb_ctx {
   struct GraphEntry { std::vector<int> key; cudaGraphExec_t exec; uint64_t kernels; };
   std::vector<GraphEntry> graphs;
   int* d_pair_tab = nullptr;  // single-pair table for the unbatched matcher entry points
+  // consecutive-frame matching of the last extraction (hfb_match_consecutive_dev)
+  int* d_cm_tab = nullptr;     // [4][max_batch]
+  int* d_cm_idx = nullptr;     // [max_batch][kp_cap]
+  float* d_cm_val = nullptr;
+  // per-launch profiling (hfb_profile_extract): one CUDA event after every launch, with the launch's algorithmic
+  // bytes / flops as stated by the launcher
+  bool prof_on = false;
+  struct ProfRec { std::string name; cudaEvent_t ev; double bytes, flops; };
+  std::vector<ProfRec> prof;
+  std::string label;           // set by the launcher before HFB_CHECK_LAUNCH
+  double next_bytes = 0, next_flops = 0;
+  void note(const std::string& l, double bytes, double flops) { label = l; next_bytes = bytes; next_flops = flops; }
+  void prof_mark(const char* what) {
+    ProfRec r;
+    r.name = label.empty() ? std::string(what) : label;
+    r.bytes = next_bytes;
+    r.flops = next_flops;
+    cudaEventCreate(&r.ev);
+    cudaEventRecord(r.ev, stream);
+    prof.push_back(r);
+    label.clear();
+    next_bytes = next_flops = 0;
+  }
 
   void set_error(const std::string& s) { err = s; }
   int ensure_scratch(size_t bytes);

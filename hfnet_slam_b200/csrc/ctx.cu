@@ -116,6 +116,9 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   HFB_TRY(ctx->dalloc(&ctx->d_nsel, nb));
   HFB_TRY(ctx->dalloc(&ctx->d_overflow, 1));
   HFB_TRY(ctx->dalloc(&ctx->d_pair_tab, 4));
+  HFB_TRY(ctx->dalloc(&ctx->d_cm_tab, 4 * nb));
+  HFB_TRY(ctx->dalloc(&ctx->d_cm_idx, nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_cm_val, nb * ctx->kp_cap));
   HFB_CUDA(ctx, cudaMemset(ctx->d_overflow, 0, sizeof(int)));
   HFB_CUDA(ctx, cudaMemset(ctx->d_kcount, 0, nb * HFB_MAX_LEVELS * sizeof(int)));
   return HFB_OK;
@@ -516,6 +519,43 @@ extern "C" int hfb_extract(hfb_ctx* ctx, const uint8_t* image, int32_t height, i
   return hfb_extract_batch(ctx, imgs, 1, stride, n_per_level, threshold, out);
 }
 
+// Per-launch timing of one (un-graphed) extraction of the frames already resident in the context: JSON array of
+// {"name", "ms", "bytes", "flops"} with the launcher-stated algorithmic bytes / flops (bench.py's roofline source).
+extern "C" int hfb_profile_extract(hfb_ctx* ctx, int32_t n_images, const int32_t* n_per_level, float threshold,
+                                   char* json_out, size_t cap) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, ctx->weights_loaded && n_per_level && json_out && cap > 2, "bad argument");
+  HFB_REQUIRE(ctx, n_images >= 1 && n_images <= ctx->cfg.max_batch, "batch size outside [1, max_batch]");
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof.clear();
+  ctx->prof_on = true;
+  ctx->label = "start";
+  ctx->prof_mark("start");
+  int rc = enqueue_extract(ctx, n_images, n_per_level, threshold);
+  ctx->prof_on = false;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  std::string js = "[";
+  for (size_t i = 1; i < ctx->prof.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->prof[i - 1].ev, ctx->prof[i].ev);
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s{\"name\":\"%s\",\"ms\":%.6f,\"bytes\":%.0f,\"flops\":%.0f}", i > 1 ? "," : "",
+             ctx->prof[i].name.c_str(), ms, ctx->prof[i].bytes, ctx->prof[i].flops);
+    js += buf;
+  }
+  js += "]";
+  for (auto& r : ctx->prof) cudaEventDestroy(r.ev);
+  ctx->prof.clear();
+  if (rc != HFB_OK) return rc;
+  if (e != cudaSuccess) {
+    ctx->set_error(std::string("hfb_profile_extract: ") + cudaGetErrorString(e));
+    return HFB_ERR_CUDA;
+  }
+  HFB_REQUIRE(ctx, js.size() + 1 <= cap, "profile buffer too small");
+  memcpy(json_out, js.c_str(), js.size() + 1);
+  return HFB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ parity hooks
 extern "C" int hfb_nms(hfb_ctx* ctx, const float* scores, int32_t height, int32_t width, float* scores_nms) {
   if (!ctx) return HFB_ERR_INVALID;
@@ -686,6 +726,48 @@ extern "C" int hfb_match_batch_dev(hfb_ctx* ctx, int32_t mode, const float* dA_a
   HFB_REQUIRE(ctx, na_total >= 0 && nb_total >= 0 && n_pairs >= 0 && max_a_cnt >= 0 && max_b_cnt >= 0, "negative size");
   return launch_match_batch(ctx, mode, dA_all, dB_all, n_pairs, d_pair_tab, max_a_cnt, max_b_cnt, thr, d_match_idx,
                             d_match_val, na_total, nb_total, nullptr);
+}
+
+// Pair table for "frame b against frame b-1" (cyclic) from the per-level keypoint counts of the last extraction.
+__global__ void consecutive_tab_kernel(const int* __restrict__ kcount, int n_levels, int B, int kp_cap,
+                                       int* __restrict__ tab) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int pb = (b + B - 1) % B;
+  int na = 0, nb = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    na += kcount[b * HFB_MAX_LEVELS + l];
+    nb += kcount[pb * HFB_MAX_LEVELS + l];
+  }
+  tab[b] = b * kp_cap;
+  tab[B + b] = na;
+  tab[2 * B + b] = pb * kp_cap;
+  tab[3 * B + b] = nb;
+}
+
+// Tracking's per-frame descriptor association with the previous frame, device-resident: the descriptors of the last
+// hfb_extract_batch*(n_images) never leave HBM.  Frame b is matched against frame (b-1) mod n_images.
+extern "C" int hfb_match_consecutive_dev(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (l2) or 1 (cos)");
+  HFB_REQUIRE(ctx, n_images >= 1 && n_images <= ctx->last_batch, "n_images exceeds the last extracted batch");
+  consecutive_tab_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_kcount, ctx->n_levels, n_images, ctx->kp_cap, ctx->d_cm_tab);
+  HFB_CHECK_LAUNCH(ctx, "consecutive_tab");
+  int budget = 0;
+  for (int l = 0; l < ctx->n_levels; ++l) budget += ctx->last_budget[l];
+  return launch_match_batch(ctx, mode, ctx->d_kdesc, ctx->d_kdesc, n_images, ctx->d_cm_tab, budget, budget, thr,
+                            ctx->d_cm_idx, ctx->d_cm_val, n_images * ctx->kp_cap, n_images * ctx->kp_cap, nullptr);
+}
+
+extern "C" int hfb_fetch_matches(hfb_ctx* ctx, int32_t image_index, int32_t* match_idx, float* match_val, int32_t n) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, match_idx && match_val && image_index >= 0 && image_index < ctx->last_batch && n >= 0 &&
+                       n <= ctx->kp_cap, "bad argument");
+  const size_t o = (size_t)image_index * ctx->kp_cap;
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_idx, ctx->d_cm_idx + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_val, ctx->d_cm_val + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
 }
 
 static int match_host(hfb_ctx* ctx, int mode, const float* A_all, int na_total, const float* B_all, int nb_total,

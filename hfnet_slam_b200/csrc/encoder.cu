@@ -430,6 +430,7 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
   LevelExec& le = execs(ctx)[level];
   {
     const long long total = (long long)B * le.H1 * le.W1 * (net.c1 / 8);
+    ctx->note("conv1", (double)B * lv.H8 * lv.W8 + (double)total * 16, 2.0 * 9 * total * 8);
     conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
         lv.d_img, lv.H, lv.W, lv.H8, lv.W8, net.conv1_w, net.conv1_b, net.c1, lv.act[1], le.H1, le.W1, le.pad_t1,
         le.pad_l1, total);
@@ -442,14 +443,19 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
     const __half* in = lv.act[bw.layer - 1];
     const __half* dw_in = in;
     const long long Min = (long long)B * bp.Hi * bp.Wi, Mout = (long long)B * bp.Ho * bp.Wo;
+    const std::string ln = "l" + std::to_string(bw.layer);
     if (bw.has_expand) {
+      ctx->note(ln + ".expand", 2.0 * Min * (bw.cin + bw.cexp) + 2.0 * bw.cin * bw.cexp, 2.0 * Min * bw.cin * bw.cexp);
       HFB_TRY(run_plain(ctx, bp.expand, Min, lv.d_exp, bw.cexp, bw.expand.b, nullptr, 0, 1));
       dw_in = lv.d_exp;
     }
     const long long total = Mout * (bw.cexp / 8);
+    ctx->note(ln + ".dw", 2.0 * (Min + Mout) * bw.cexp, 2.0 * 9 * Mout * bw.cexp);
     dw3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
         dw_in, bp.Hi, bp.Wi, bw.cexp, bw.wd, bw.bd, lv.d_dw, bp.Ho, bp.Wo, bw.stride, bp.pad_t, bp.pad_l, total);
     HFB_CHECK_LAUNCH(ctx, "dw3x3");
+    ctx->note(ln + ".project", 2.0 * Mout * (bw.cexp + bw.cout * (bw.residual ? 2 : 1)) + 2.0 * bw.cexp * bw.cout,
+              2.0 * Mout * bw.cexp * bw.cout);
     HFB_TRY(run_plain(ctx, bp.project, Mout, lv.act[bw.layer], bw.cout, bw.project.b,
                       bw.residual ? in : nullptr, bw.cin, 0));
   }
@@ -457,14 +463,19 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
   {
     GemmGeom g = le.head1.g;
     g.M = B * le.Hd * le.Wd;
+    const double M7 = (double)g.M, Cl = (double)net.c_local;
+    ctx->note("head.conv3x3", 2.0 * M7 * (Cl + 384) + 2.0 * 384 * 9 * Cl, 2.0 * M7 * 9 * Cl * 384);
     HFB_TRY(gemm_store(ctx, le.head1.tmA, le.head1.tmB, g, B, lv.d_head1, net.head1.N, 0, net.head1.b, nullptr, 0, 1, 0));
     GemmGeom gd = le.desc2.g;
     gd.M = g.M;
+    ctx->note("head.desc1x1+l2norm", M7 * (256 * 2 + 256 * 4) + 2.0 * 256 * 256, 2.0 * M7 * 256 * 256);
     HFB_TRY(gemm_l2norm(ctx, le.desc2.tmA, le.desc2.tmB, gd, lv.d_descmap, net.desc2.b));
     GemmGeom gt = le.det2.g;
     gt.M = g.M;
+    ctx->note("head.det1x1+softmax+d2s", M7 * (128 * 2 + 64 * 4) + 2.0 * 128 * 65, 2.0 * M7 * 128 * 65);
     HFB_TRY(gemm_softmax_d2s(ctx, le.det2.tmA, le.det2.tmB, gt, lv.d_scores, lv.d_logits, net.det2.b, le.Hd, le.Wd));
   }
+  ctx->note("nms", 8.0 * B * lv.H8 * lv.W8, 0);
   HFB_TRY(launch_nms(ctx, lv.d_scores, lv.d_nms, lv.H8, lv.W8, B));
   if (lv.global) {
     const int C = net.n_clusters, K = C * le.D;
@@ -478,6 +489,7 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
     HFB_CHECK_LAUNCH(ctx, "vlad_normalize");
     dim3 g3(ceil_div(HFB_GLOBAL_DIM, 256 * 8), le.fc_split);
     const size_t smem = (size_t)FC_BCH * le.fc_kps * sizeof(float);
+    ctx->note("global.fc", 2.0 * K * HFB_GLOBAL_DIM + 4.0 * B * K, 2.0 * B * K * HFB_GLOBAL_DIM);
     fc_partial_kernel<<<g3, 256, smem, ctx->stream>>>(lv.d_vladn, K, B, net.fc_w, HFB_GLOBAL_DIM, le.fc_kps,
                                                       lv.d_fc_partial);
     HFB_CHECK_LAUNCH(ctx, "fc_partial");

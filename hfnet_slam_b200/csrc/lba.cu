@@ -261,8 +261,10 @@ __global__ void lba_schur_reduce_kernel(LbaDev d, double lambda, int G) {
   if (i < N * N) {
     const int r = i / N, c = i % N;
     const int br = r / 6, bc = c / 6, ri = r % 6, ci = c % 6;
-    const size_t idx = br <= bc ? (size_t)blk_index(br, bc, d.n_opt) * 36 + ri * 6 + ci
-                                : (size_t)blk_index(bc, br, d.n_opt) * 36 + ci * 6 + ri;
+    // upper triangle is authoritative (also inside diagonal blocks) so that Hschur is bitwise symmetric
+    const bool upper = br < bc || (br == bc && ri <= ci);
+    const size_t idx = upper ? (size_t)blk_index(br, bc, d.n_opt) * 36 + ri * 6 + ci
+                             : (size_t)blk_index(bc, br, d.n_opt) * 36 + ci * 6 + ri;
     double s = 0;
     for (int g = 0; g < G; ++g) s += d.partial[g * stride + idx];
     double base = 0;

@@ -83,6 +83,9 @@ SIGNATURES = {
                                   _i32p, _i32p, C.c_float, _i32p, _f32p]),
     "hfb_match_batch_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "hfb_match_consecutive_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float]),
+    "hfb_fetch_matches": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _f32p, C.c_int32]),
+    "hfb_profile_extract": (C.c_int, [C.c_void_p, C.c_int32, _i32p, C.c_float, C.c_char_p, C.c_size_t]),
     "hfb_kfdb_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "hfb_kfdb_destroy": (None, [C.c_void_p]),
     "hfb_kfdb_add": (C.c_int, [C.c_void_p, _i64p, _f32p, C.c_int32]),
@@ -233,6 +236,22 @@ class Context:
         f, arrs = self._alloc_features()
         self.check(self.lib.hfb_fetch_features(self.handle, image_index, C.byref(f)))
         return self._trim(f, arrs, self.with_global)
+
+    def match_consecutive_dev(self, n_images: int, mode: int, thr: float):
+        self.check(self.lib.hfb_match_consecutive_dev(self.handle, n_images, mode, thr))
+
+    def fetch_matches(self, image_index: int, n: int):
+        idx = np.full(n, -1, np.int32)
+        val = np.zeros(n, np.float32)
+        self.check(self.lib.hfb_fetch_matches(self.handle, image_index, ptr(idx, _i32p), ptr(val, _f32p), n))
+        return idx, val
+
+    def profile_extract(self, n_images: int, n_per_level, threshold: float):
+        import json
+        budgets = (C.c_int32 * HFB_MAX_LEVELS)(*([int(v) for v in n_per_level] + [0] * (HFB_MAX_LEVELS - len(n_per_level))))
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.lib.hfb_profile_extract(self.handle, n_images, budgets, threshold, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     def debug_tensor(self, name: str, image_index: int = 0, level: int = 0) -> np.ndarray:
         n = C.c_size_t()

@@ -103,6 +103,12 @@ int hfb_extract_batch_dev(hfb_ctx* ctx, const uint8_t* d_images, int32_t n_image
                           float threshold);
 int hfb_fetch_features(hfb_ctx* ctx, int32_t image_index, hfb_features* out);
 
+/* Per-launch device timing of one un-graphed extraction of the frames already resident in the context (after
+ * hfb_extract_batch*): JSON array of {"name","ms","bytes","flops"}; bytes / flops are the algorithmic figures of
+ * DESIGN.md.  Replaces the reference's REGISTER_TIMES stage timers (src/Frame.cc:311-319). */
+int hfb_profile_extract(hfb_ctx* ctx, int32_t n_images, const int32_t* n_per_level, float threshold, char* json_out,
+                        size_t cap);
+
 /* Network-tail stages on caller-supplied dense maps (parity hooks; also the reference's CPU stages):
  * hfb_nms            == simple_nms(radius 4, iterations 2) (hfnet/models/utils/layers.py:10-32)
  * hfb_select_sample  == GetLocalFeaturesFromTensor (src/Extractors/HFNetRTModel.cc:139-196): threshold scan,
@@ -115,6 +121,11 @@ int hfb_select_sample(hfb_ctx* ctx, const float* scores_nms, int32_t height, int
                       float* response, float* descriptors, int32_t* n_out);
 int hfb_resize_linear_u8(hfb_ctx* ctx, const uint8_t* src, int32_t sh, int32_t sw, uint8_t* dst, int32_t dh,
                          int32_t dw);
+
+/* Debug / parity hook: the tensor-core GEMM primitive on caller data (fp16 operands, fp32 result [B*H*W][N]).
+ * A: [B*H*W][K] (NHWC when conv3x3), Wt: [N][conv3x3 ? 9K : K]; use_tc = 0 runs the CUDA-core cross-check kernel. */
+int hfb_debug_gemm(hfb_ctx* ctx, const float* A, int B, int H, int W, int K, const float* Wt, int N, const float* bias,
+                   int relu6, int conv3x3, int use_tc, int BN, float* out);
 
 /* Debug / parity hook: copy an intermediate tensor of the LAST extraction to host.  name is one of
  * "layer_1".."layer_18", "desc_conv1", "det_conv1", "det_logits", "scores_dense", "scores_dense_nms",
@@ -149,6 +160,13 @@ int hfb_match_batch(hfb_ctx* ctx, int32_t mode, const float* A_all, int32_t na_t
 int hfb_match_batch_dev(hfb_ctx* ctx, int32_t mode, const float* dA_all, int32_t na_total, const float* dB_all,
                         int32_t nb_total, int32_t n_pairs, const int32_t* d_pair_tab, int32_t max_a_cnt,
                         int32_t max_b_cnt, float thr, int32_t* d_match_idx, float* d_match_val);
+
+/* Tracking's frame-to-previous-frame descriptor association (the brute-force stage behind
+ * Matcher::SearchByBoW / SearchForInitialization call sites, src/Tracking.cc:2030,1796) with the descriptors of the last
+ * hfb_extract_batch* still resident in HBM: frame b is matched against frame (b-1) mod n_images.  No sync. */
+int hfb_match_consecutive_dev(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr);
+/* match_idx / match_val of frame `image_index` (indices into the previous frame's keypoints), first n rows. */
+int hfb_fetch_matches(hfb_ctx* ctx, int32_t image_index, int32_t* match_idx, float* match_val, int32_t n);
 
 /* ------------------------------------------------------------------------------------------------------ keyframe DB
  * Replaces KeyFrameDatabase's linear scan (src/KeyFrameDatabase.cc:75-256).  Rows live in HBM as fp32 [capacity][dim].
