@@ -192,10 +192,10 @@ def main_gpu(args):
         ctx.match_consecutive_dev(B, 0, 0.6)
 
     def step_host():
-        feats = ctx.extract_batch(frames, budgets, THR)
+        feats, block = ctx.extract_batch(frames, budgets, THR, return_block=True)
         cnt = np.array([len(f["x"]) for f in feats], np.int32)
-        descs = np.concatenate([f["descriptors"] for f in feats])
-        off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int32)
+        descs = block["descriptors"].reshape(-1, 256)                 # frame b's rows start at b * kp_cap
+        off = (np.arange(B) * ctx.kp_cap).astype(np.int32)
         prev = (np.arange(B) - 1) % B
         idx, val = ctx.match_batch(0, descs, descs, off, cnt, off[prev], cnt[prev], 0.6)
         return feats, cnt, idx

@@ -134,6 +134,9 @@ struct hfb_ctx {
   // generic device scratch (matcher / lba), grown on demand
   void* d_scratch = nullptr;
   size_t d_scratch_bytes = 0;
+  void* d_io = nullptr;        // persistent device staging of the host-pointer matcher entry points
+  size_t d_io_bytes = 0;
+  bool trace = false;          // HFB_TRACE=1: host-side stage timings of the host-pointer calls on stderr
   std::vector<void*> allocs;
   bool use_graph = true;
   // captured extraction graphs keyed by (batch, budgets, threshold bits)
@@ -166,6 +169,7 @@ struct hfb_ctx {
 
   void set_error(const std::string& s) { err = s; }
   int ensure_scratch(size_t bytes);
+  int ensure_io(size_t bytes);
   int ensure_stage(size_t bytes);
   template <typename T>
   int dalloc(T** p, size_t n) {

@@ -21,6 +21,41 @@ int hfb_ctx::ensure_scratch(size_t bytes) {
   return HFB_OK;
 }
 
+int hfb_ctx::ensure_io(size_t bytes) {
+  if (bytes <= d_io_bytes) return HFB_OK;
+  if (d_io) cudaFree(d_io);
+  d_io = nullptr;
+  d_io_bytes = 0;
+  const size_t want = bytes + bytes / 2;
+  cudaError_t e = cudaMalloc(&d_io, want);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(io): ") + cudaGetErrorString(e));
+    return HFB_ERR_CUDA;
+  }
+  d_io_bytes = want;
+  return HFB_OK;
+}
+
+#include <chrono>
+struct StageTimer {
+  bool on;
+  const char* what;
+  std::chrono::steady_clock::time_point t0;
+  std::string log;
+  StageTimer(bool enabled, const char* w) : on(enabled), what(w), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* stage) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof(buf), " %s=%.3fms", stage, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    log += buf;
+    t0 = t1;
+  }
+  ~StageTimer() {
+    if (on) fprintf(stderr, "[hfb trace] %s:%s\n", what, log.c_str());
+  }
+};
+
 int hfb_ctx::ensure_stage(size_t bytes) {
   if (bytes <= h_stage_bytes) return HFB_OK;
   if (h_stage) cudaFreeHost(h_stage);
@@ -60,6 +95,8 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   ctx->n_levels = cfg->n_levels;
   const char* dbg = getenv("HFB_DEBUG");
   ctx->debug = dbg && dbg[0] == '1';
+  const char* tr = getenv("HFB_TRACE");
+  ctx->trace = tr && tr[0] == '1';
   const char* ng = getenv("HFB_NO_GRAPH");
   ctx->use_graph = !(ng && ng[0] == '1');
   *out = ctx;  // returned even on failure so that hfb_last_error works; caller destroys
@@ -139,6 +176,7 @@ extern "C" void hfb_destroy(hfb_ctx* ctx) {
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->d_wblob) cudaFree(ctx->d_wblob);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_io) cudaFree(ctx->d_io);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -446,6 +484,7 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
   LevelPlan& l0 = ctx->lv[0];
   HFB_REQUIRE(ctx, stride >= l0.W, "stride smaller than the image width");
   // Pinned staging (the reference copies from pageable memory with a synchronous cudaMemcpy, TensorRTBuffers.h:417-435)
+  StageTimer tm(ctx->trace, "hfb_extract_batch");
   const size_t img_bytes = (size_t)l0.H * l0.W;
   const size_t per_frame_out = (size_t)ctx->kp_cap * (4 * 4 + HFB_DESC_DIM * 4) + HFB_GLOBAL_DIM * 4 + 64;
   HFB_TRY(ctx->ensure_stage((size_t)n_images * (img_bytes + per_frame_out)));
@@ -454,8 +493,10 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
     HFB_REQUIRE(ctx, images[b] != nullptr, "null image");
     for (int y = 0; y < l0.H; ++y) memcpy(hs + (size_t)b * img_bytes + (size_t)y * l0.W, images[b] + (size_t)y * stride, l0.W);
   }
+  tm.mark("stage_in");
   HFB_CUDA(ctx, cudaMemcpyAsync(l0.d_img, hs, (size_t)n_images * img_bytes, cudaMemcpyHostToDevice, ctx->stream));
   HFB_TRY(run_extract(ctx, n_images, n_per_level, threshold));
+  tm.mark("enqueue");
   // one D2H burst of budget-sized slices into pinned memory, one synchronisation
   int budget = 0;
   for (int l = 0; l < ctx->n_levels; ++l) budget += n_per_level[l];
@@ -487,7 +528,9 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
       HFB_CUDA(ctx, cudaMemcpyAsync(s.g, ctx->d_global + (size_t)b * HFB_GLOBAL_DIM, HFB_GLOBAL_DIM * 4,
                                     cudaMemcpyDeviceToHost, ctx->stream));
   }
+  tm.mark("enqueue_d2h");
   HFB_TRY(check_overflow(ctx));  // synchronises the stream
+  tm.mark("gpu_wait");
   for (int b = 0; b < n_images; ++b) {
     const Slot& s = slots[b];
     hfb_features& f = outs[b];
@@ -506,6 +549,7 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
     }
     if (f.global_descriptor && ctx->cfg.with_global) memcpy(f.global_descriptor, s.g, HFB_GLOBAL_DIM * 4);
   }
+  tm.mark("copy_out");
   return HFB_OK;
 }
 
@@ -790,28 +834,19 @@ static int match_host(hfb_ctx* ctx, int mode, const float* A_all, int na_total, 
   if (n_matches)
     for (int p = 0; p < n_pairs; ++p) n_matches[p] = 0;
   if (na_total == 0 || nb_total == 0 || n_pairs == 0 || max_a == 0 || max_b == 0) return HFB_OK;
-  // device buffers: A | B | idx | val | tab   (separate from ctx scratch, which launch_match_batch uses)
-  float *dA = nullptr, *dB = nullptr, *dV = nullptr;
-  int *dI = nullptr, *dT = nullptr;
-  int rc = HFB_OK;
-  cudaError_t e = cudaSuccess;
-  auto done = [&]() {
-    cudaFree(dA); cudaFree(dB); cudaFree(dV); cudaFree(dI); cudaFree(dT);
-  };
-#define M_CUDA(expr)                                                       \
-  do {                                                                     \
-    e = (expr);                                                            \
-    if (e != cudaSuccess) {                                                \
-      ctx->set_error(std::string(#expr) + ": " + cudaGetErrorString(e));   \
-      done();                                                              \
-      return HFB_ERR_CUDA;                                                 \
-    }                                                                      \
-  } while (0)
-  M_CUDA(cudaMalloc(&dA, (size_t)na_total * 256 * 4));
-  M_CUDA(cudaMalloc(&dB, (size_t)nb_total * 256 * 4));
-  M_CUDA(cudaMalloc(&dV, (size_t)na_total * 4));
-  M_CUDA(cudaMalloc(&dI, (size_t)na_total * 4));
-  M_CUDA(cudaMalloc(&dT, (size_t)n_pairs * 16));
+  // persistent device staging: A | B | idx | val | tab   (separate from ctx scratch, which launch_match_batch uses)
+  StageTimer tm(ctx->trace, "hfb_match");
+  const bool same = (A_all == B_all && na_total == nb_total);   // self-matching set (frame vs frame of one batch)
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t szA = al((size_t)na_total * 256 * 4), szB = same ? 0 : al((size_t)nb_total * 256 * 4);
+  const size_t szI = al((size_t)na_total * 4), szT = al((size_t)n_pairs * 16);
+  HFB_TRY(ctx->ensure_io(szA + szB + 2 * szI + szT));
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->d_io);
+  float* dA = reinterpret_cast<float*>(base);
+  float* dB = same ? dA : reinterpret_cast<float*>(base + szA);
+  int* dI = reinterpret_cast<int*>(base + szA + szB);
+  float* dV = reinterpret_cast<float*>(base + szA + szB + szI);
+  int* dT = reinterpret_cast<int*>(base + szA + szB + 2 * szI);
   std::vector<int> tab((size_t)4 * n_pairs);
   for (int p = 0; p < n_pairs; ++p) {
     tab[p] = a_off[p];
@@ -819,23 +854,21 @@ static int match_host(hfb_ctx* ctx, int mode, const float* A_all, int na_total, 
     tab[2 * n_pairs + p] = b_off[p];
     tab[3 * n_pairs + p] = b_cnt[p];
   }
-  M_CUDA(cudaMemcpyAsync(dA, A_all, (size_t)na_total * 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
-  M_CUDA(cudaMemcpyAsync(dB, B_all, (size_t)nb_total * 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
-  M_CUDA(cudaMemcpyAsync(dT, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  M_CUDA(cudaMemsetAsync(dI, 0xFF, (size_t)na_total * 4, ctx->stream));
-  M_CUDA(cudaMemsetAsync(dV, 0, (size_t)na_total * 4, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(dA, A_all, (size_t)na_total * 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!same) HFB_CUDA(ctx, cudaMemcpyAsync(dB, B_all, (size_t)nb_total * 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(dT, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemsetAsync(dI, 0xFF, (size_t)na_total * 4, ctx->stream));
+  HFB_CUDA(ctx, cudaMemsetAsync(dV, 0, (size_t)na_total * 4, ctx->stream));
+  tm.mark("h2d");
   int* d_nm = nullptr;
-  rc = launch_match_batch(ctx, mode, dA, dB, n_pairs, dT, max_a, max_b, thr, dI, dV, na_total, nb_total, &d_nm);
-  if (rc == HFB_OK) {
-    M_CUDA(cudaMemcpyAsync(match_idx, dI, (size_t)na_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    M_CUDA(cudaMemcpyAsync(match_val, dV, (size_t)na_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n_matches && d_nm)
-      M_CUDA(cudaMemcpyAsync(n_matches, d_nm, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    M_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
-  done();
-  return rc;
-#undef M_CUDA
+  HFB_TRY(launch_match_batch(ctx, mode, dA, dB, n_pairs, dT, max_a, max_b, thr, dI, dV, na_total, nb_total, &d_nm));
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_idx, dI, (size_t)na_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_val, dV, (size_t)na_total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_matches && d_nm)
+    HFB_CUDA(ctx, cudaMemcpyAsync(n_matches, d_nm, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // also keeps `tab` alive until its copy has been consumed
+  tm.mark("gpu+d2h");
+  return HFB_OK;
 }
 
 extern "C" int hfb_match_batch(hfb_ctx* ctx, int32_t mode, const float* A_all, int32_t na_total, const float* B_all,

@@ -271,20 +271,31 @@ __global__ void __launch_bounds__(256) fc_partial_kernel(const float* __restrict
   }
 }
 
-__global__ void fc_finish_kernel(const float* __restrict__ partial, int n_split, int N, const float* __restrict__ bias,
-                                 float* __restrict__ out) {
+// y = sum of the split-K partials + bias; per-CTA sum of squares.  grid (N/256, B), fixed summation order.
+__global__ void __launch_bounds__(256) fc_finish_kernel(const float* __restrict__ partial, int n_split, int N,
+                                                        const float* __restrict__ bias, float* __restrict__ out,
+                                                        float* __restrict__ ss_part) {
   __shared__ float red[32];
-  const int b = blockIdx.x;
-  float ss = 0.f;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float y = __ldg(bias + n);
-    for (int s = 0; s < n_split; ++s) y += partial[((size_t)b * n_split + s) * N + n];
+  const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
+  float y = 0.f;
+  if (n < N) {
+    y = __ldg(bias + n);
+    const float* p = partial + (size_t)b * n_split * N + n;
+    for (int s = 0; s < n_split; ++s) y += p[(size_t)s * N];
     out[(size_t)b * N + n] = y;
-    ss = fmaf(y, y, ss);
   }
-  const float tot = block_sum(ss, red);
+  const float tot = block_sum(y * y, red);
+  if (threadIdx.x == 0) ss_part[b * gridDim.x + blockIdx.x] = tot;
+}
+
+// final tf.nn.l2_normalize of the 4096-d global descriptor (layers.py:108)
+__global__ void fc_norm_kernel(float* __restrict__ out, int N, const float* __restrict__ ss_part, int n_part) {
+  const int b = blockIdx.y;
+  float tot = 0.f;
+  for (int i = 0; i < n_part; ++i) tot += ss_part[b * n_part + i];
   const float inv = rsqrtf(fmaxf(tot, 1e-12f));
-  for (int n = threadIdx.x; n < N; n += blockDim.x) out[(size_t)b * N + n] *= inv;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) out[(size_t)b * N + n] *= inv;
 }
 
 // =============================================================================================== plans
@@ -409,7 +420,7 @@ int encoder_plan(hfb_ctx* ctx) {
       le.fc_split = std::max(1, ctx->n_sm / 2);
       le.fc_kps = (K + le.fc_split - 1) / le.fc_split;
       le.fc_split = (K + le.fc_kps - 1) / le.fc_kps;
-      HFB_TRY(ctx->dalloc(&lv.d_fc_partial, (size_t)Bm * le.fc_split * HFB_GLOBAL_DIM));
+      HFB_TRY(ctx->dalloc(&lv.d_fc_partial, (size_t)Bm * le.fc_split * HFB_GLOBAL_DIM + (size_t)Bm * 64));
     }
   }
   return HFB_OK;
@@ -493,8 +504,13 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
     fc_partial_kernel<<<g3, 256, smem, ctx->stream>>>(lv.d_vladn, K, B, net.fc_w, HFB_GLOBAL_DIM, le.fc_kps,
                                                       lv.d_fc_partial);
     HFB_CHECK_LAUNCH(ctx, "fc_partial");
-    fc_finish_kernel<<<B, 1024, 0, ctx->stream>>>(lv.d_fc_partial, le.fc_split, HFB_GLOBAL_DIM, net.fc_b, ctx->d_global);
+    const int n_part = ceil_div(HFB_GLOBAL_DIM, 256);
+    float* ss_part = lv.d_fc_partial + (size_t)ctx->cfg.max_batch * le.fc_split * HFB_GLOBAL_DIM;
+    fc_finish_kernel<<<dim3(n_part, B), 256, 0, ctx->stream>>>(lv.d_fc_partial, le.fc_split, HFB_GLOBAL_DIM, net.fc_b,
+                                                               ctx->d_global, ss_part);
     HFB_CHECK_LAUNCH(ctx, "fc_finish");
+    fc_norm_kernel<<<dim3(n_part, B), 256, 0, ctx->stream>>>(ctx->d_global, HFB_GLOBAL_DIM, ss_part, n_part);
+    HFB_CHECK_LAUNCH(ctx, "fc_norm");
   }
   return HFB_OK;
 }

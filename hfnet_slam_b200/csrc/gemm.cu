@@ -62,7 +62,8 @@ int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, 
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
-// bias (+ReLU6) (+residual) -> fp16 or fp32 rows.
+// bias (+ReLU6) (+residual) -> fp16 or fp32 rows.  The tile is staged through the (now idle) operand ring so that
+// global stores are coalesced along the output row instead of one 16-byte piece per thread-row.
 struct EpiStore {
   struct Params {
     void* out;
@@ -74,45 +75,69 @@ struct EpiStore {
     int relu6;
     int f32;
   };
+  static __host__ __device__ __forceinline__ int stage_esz(const Params& p) { return (p.f32 || p.residual) ? 4 : 2; }
+  static __host__ size_t stage_bytes(const Params& p, int BN) { return (size_t)128 * ((size_t)BN * stage_esz(p) + 16) + 1024; }
+
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
+    const int tid = threadIdx.x;
+    const int esz = stage_esz(p);
+    const int pitch = g.BN * esz + 16;                         // odd multiple of 16 B: conflict-free 16-byte rows
+    long long* s_row = reinterpret_cast<long long*>(tr.stage);  // [128] output row or -1
+    uint8_t* tile = tr.stage + 1024;
+    s_row[tid] = tr.valid ? tr.row : -1;
+    uint8_t* my = tile + (size_t)tid * pitch;
     for (int c0 = 0; c0 < g.BN; c0 += 16) {
       uint32_t r[16];
       tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
       tc::tmem_ld_wait();
       const int n = tr.n0 + c0;
-      if (!tr.valid || n >= g.N) continue;
+      if (n >= g.N) continue;   // uniform
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float b = (n + j < g.N && p.bias) ? __ldg(p.bias + n + j) : 0.f;
+        const float b = (n + j < g.N && p.bias) ? __ldg(p.bias + n + j) : 0.f;
         v[j] = __uint_as_float(r[j]) + b;
         if (p.relu6) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
       }
+      if (esz == 4) {
+        float4* d = reinterpret_cast<float4*>(my + (size_t)c0 * 4);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int nn = n + 8 * h;
-        if (nn + 8 > g.N) break;
-        if (p.residual) {
-          const uint4 q = *reinterpret_cast<const uint4*>(p.residual + tr.row * p.ldr + nn);
-          const __half2* hq = reinterpret_cast<const __half2*>(&q);
+        for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else {
+        uint4* d = reinterpret_cast<uint4*>(my + (size_t)c0 * 2);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 f = __half22float2(hq[j]);
-            v[8 * h + 2 * j] += f.x;
-            v[8 * h + 2 * j + 1] += f.y;
-          }
-        }
-        if (p.f32) {
-          float* o = reinterpret_cast<float*>(p.out) + tr.row * p.ldo + p.col_off + nn;
-          *reinterpret_cast<float4*>(o) = make_float4(v[8 * h], v[8 * h + 1], v[8 * h + 2], v[8 * h + 3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[8 * h + 4], v[8 * h + 5], v[8 * h + 6], v[8 * h + 7]);
-        } else {
+        for (int h = 0; h < 2; ++h) {
           uint4 q;
           __half2* hq = reinterpret_cast<__half2*>(&q);
 #pragma unroll
           for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + tr.row * p.ldo + p.col_off + nn) = q;
+          d[h] = q;
         }
+      }
+    }
+    __syncthreads();
+    const int ncols = min(g.BN, g.N - tr.n0);         // multiple of 8
+    const int cpr = ncols * esz / 16;                  // 16-byte chunks per row
+    const int total = 128 * cpr;
+    for (int id = tid; id < total; id += 128) {
+      const int row = id / cpr, ch = id - row * cpr;
+      const long long orow = s_row[row];
+      if (orow < 0) continue;
+      const uint4 q = *reinterpret_cast<const uint4*>(tile + (size_t)row * pitch + (size_t)ch * 16);
+      if (esz == 2) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + orow * p.ldo + p.col_off + tr.n0 + ch * 8) = q;
+      } else if (p.f32) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + p.col_off + tr.n0 + ch * 4) = q;
+      } else {  // fp32 staging + fp16 residual -> fp16 (single rounding)
+        const float* f = reinterpret_cast<const float*>(&q);
+        const uint2 rr = *reinterpret_cast<const uint2*>(p.residual + orow * p.ldr + tr.n0 + ch * 4);
+        const __half2* hr = reinterpret_cast<const __half2*>(&rr);
+        const float2 r0 = __half22float2(hr[0]), r1 = __half22float2(hr[1]);
+        uint2 o;
+        __half2* ho = reinterpret_cast<__half2*>(&o);
+        ho[0] = __floats2half2_rn(f[0] + r0.x, f[1] + r0.y);
+        ho[1] = __floats2half2_rn(f[2] + r1.x, f[3] + r1.y);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + orow * p.ldo + p.col_off + tr.n0 + ch * 4) = o;
       }
     }
   }
@@ -213,9 +238,11 @@ struct EpiSoftmaxD2S {
 
 // ------------------------------------------------------------------------------------------------ launchers
 template <class Epi>
-static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, int B,
-                     const typename Epi::Params& ep, const char* what) {
-  const size_t smem = gemm_smem_bytes(g.BN, g.stages);
+static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g_in, int B,
+                     const typename Epi::Params& ep, const char* what, size_t epi_bytes = 0) {
+  GemmGeom g = g_in;
+  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages, epi_bytes);
+  const size_t smem = gemm_smem_bytes(g.BN, g.stages, epi_bytes);
   static size_t configured = 0;  // per-instantiation
   if (smem > configured) {
     HFB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -229,7 +256,7 @@ static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
 int gemm_store(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, int B, void* out,
                int ldo, int col_off, const float* bias, const __half* residual, int ldr, int relu6, int f32) {
   EpiStore::Params p{out, ldo, col_off, bias, residual, ldr, relu6, f32};
-  return launch_tc<EpiStore>(ctx, tmA, tmB, g, B, p, "gemm_store");
+  return launch_tc<EpiStore>(ctx, tmA, tmB, g, B, p, "gemm_store", EpiStore::stage_bytes(p, g.BN));
 }
 int gemm_l2norm(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* out,
                 const float* bias) {

@@ -24,6 +24,7 @@ struct GemmGeom {
   int stages;         // smem ring depth (<= 8)
   uint32_t idesc;
   uint32_t tmem_cols; // power of two >= max(32, BN)
+  uint32_t ring_bytes; // operand ring size (>= stages * stage bytes); barriers live right behind it
   // Batched independent problems (descriptor matching): blockIdx.z = pair, pair_tab = device int[4][n_pairs] holding
   // a_off | a_cnt | b_off | b_cnt (row ranges inside A's and W's maps).  null = one problem of M x N.
   const int* pair_tab;
@@ -38,12 +39,18 @@ struct TileRow {
   int row_local;      // row inside the problem (== row when not batched)
   int n_cnt;          // columns of the problem (== N when not batched)
   int a_off, b_off;   // batched: first global row of the pair's A / B block
+  uint8_t* stage;     // operand ring (1024-aligned), free for epilogue staging once the accumulator is complete
 };
 
 #define GEMM_TILE_A_BYTES 16384  // 128 rows x 128 B
 
-static inline size_t gemm_smem_bytes(int BN, int stages) {
-  return 1024 + (size_t)stages * (GEMM_TILE_A_BYTES + (size_t)BN * 128) + 256;
+// epi_bytes: shared memory the epilogue wants to reuse from the operand ring (the ring is grown if smaller)
+static inline size_t gemm_ring_bytes(int BN, int stages, size_t epi_bytes = 0) {
+  const size_t ring = (size_t)stages * (GEMM_TILE_A_BYTES + (size_t)BN * 128);
+  return (ring > epi_bytes ? ring : epi_bytes + 1023) & ~(size_t)1023;
+}
+static inline size_t gemm_smem_bytes(int BN, int stages, size_t epi_bytes = 0) {
+  return 1024 + gemm_ring_bytes(BN, stages, epi_bytes) + 256;
 }
 
 template <class Epi>
@@ -53,7 +60,7 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = GEMM_TILE_A_BYTES + (uint32_t)g.BN * 128u;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.ring_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + 8;
   uint64_t* acc_full = bars + 16;
@@ -161,6 +168,7 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ CU
   tr.n_cnt = b_cnt;
   tr.a_off = a_off;
   tr.b_off = b_off;
+  tr.stage = smem;
   Epi::run(ep, g, tr);
 
   tc::fence_before_sync();
@@ -188,6 +196,7 @@ static inline void gemm_fill_geom(GemmGeom& g, int M, int N, int K, int BN, int 
   g.stages = g.num_kb < 4 ? g.num_kb : 4;
   g.idesc = tc::make_idesc_f16(BN);
   g.tmem_cols = tmem_cols_for(BN);
+  g.ring_bytes = (uint32_t)gemm_ring_bytes(BN, g.stages);
   g.pair_tab = nullptr; g.n_pairs = 0;
 }
 static inline void gemm_fill_geom_conv(GemmGeom& g, int B, int H, int W, int C, int N, int BN) {
@@ -198,6 +207,7 @@ static inline void gemm_fill_geom_conv(GemmGeom& g, int B, int H, int W, int C, 
   g.stages = 4;
   g.idesc = tc::make_idesc_f16(BN);
   g.tmem_cols = tmem_cols_for(BN);
+  g.ring_bytes = (uint32_t)gemm_ring_bytes(BN, g.stages);
   g.pair_tab = nullptr; g.n_pairs = 0;
 }
 static inline dim3 gemm_grid(const GemmGeom& g, int B) {

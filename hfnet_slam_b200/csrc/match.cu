@@ -61,16 +61,14 @@ struct EpiArgmax {
     u64* colbest;      // [nb_total], zero-initialised
   };
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
-    __shared__ u64 s_col[MATCH_BN];
+    __shared__ u64 s_col[4][MATCH_BN];   // per-warp column maxima (no shared-memory atomics)
     __shared__ float s_hnb[MATCH_BN];
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncols = min(g.BN, tr.n_cnt - tr.n0);  // valid columns of this tile
-    if (tid < MATCH_BN) {
-      s_col[tid] = 0ull;
-      s_hnb[tid] = tid < ncols ? __ldg(p.hnb + tr.b_off + tr.n0 + tid) : 0.f;
-    }
+    if (tid < MATCH_BN) s_hnb[tid] = tid < ncols ? __ldg(p.hnb + tr.b_off + tr.n0 + tid) : 0.f;
     __syncthreads();
     const float my_hna = tr.valid ? __ldg(p.hna + tr.row) : 0.f;
+    const int warp_row0 = tr.row_local - lane;      // problem-local row of this warp's lane 0
     float best = -INFINITY;
     int best_j = 0;
     for (int c0 = 0; c0 < g.BN; c0 += 16) {
@@ -92,13 +90,20 @@ struct EpiArgmax {
         const uint32_t kc = (cv && tr.valid) ? f2ord(s - my_hna) : 0u;
         const uint32_t mx = __reduce_max_sync(0xffffffffu, kc);
         const uint32_t who = __ballot_sync(0xffffffffu, kc == mx);
-        if (mx != 0u && lane == (__ffs(who) - 1))
-          atomicMax(&s_col[c0 + j], ((u64)mx << 32) | (u64)(0xFFFFFFFFu - (uint32_t)tr.row_local));
+        if (lane == 0)
+          s_col[warp][c0 + j] =
+              mx != 0u ? (((u64)mx << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(warp_row0 + __ffs(who) - 1))) : 0ull;
       }
     }
     if (tr.valid && best > -INFINITY) atomicMax(p.rowbest + tr.row, pack_best(best, best_j));
     __syncthreads();
-    if (tid < ncols && s_col[tid] != 0ull) atomicMax(p.colbest + tr.b_off + tr.n0 + tid, s_col[tid]);
+    if (tid < ncols) {
+      u64 m = s_col[0][tid];
+      m = m > s_col[1][tid] ? m : s_col[1][tid];
+      m = m > s_col[2][tid] ? m : s_col[2][tid];
+      m = m > s_col[3][tid] ? m : s_col[3][tid];
+      if (m != 0ull) atomicMax(p.colbest + tr.b_off + tr.n0 + tid, m);
+    }
   }
 };
 
@@ -199,6 +204,8 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
   gemm_fill_geom(g, max_a, max_b, MATCH_K, MATCH_BN, 0);
   g.pair_tab = d_pair_tab;
   g.n_pairs = n_pairs;
+  g.stages = 2;   // 64 KB of operand ring: three CTAs per SM overlap each other's main loop and epilogue
+  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages);
   const size_t smem = gemm_smem_bytes(g.BN, g.stages);
   static bool configured = false;
   if (!configured) {

@@ -12,103 +12,107 @@
 
 // =============================================================================================== simple_nms
 // One CTA produces a 64 x 16 tile.  Dependency radius is 12 (three chained 9x9 max-pools), so the tile is computed
-// from an 88 x 40 halo region held in shared memory; every pool is separable (row pass, column pass).
+// from an 88 x 40 halo region held in shared memory; every pool is separable (row pass, column pass).  Each thread
+// produces a run of 8 outputs from 16 inputs with a suffix-max / prefix-max split (22 max ops, 2 smem loads per
+// output instead of 9).  Row pitch 89 (odd) keeps the row pass, whose lanes walk down rows, bank-conflict free.
 #define NMS_TW 64
 #define NMS_TH 16
-#define NMS_R 4
 #define NMS_AW (NMS_TW + 24)
 #define NMS_AH (NMS_TH + 24)
+#define NMS_P 89
+
+__device__ __forceinline__ void run9(const float (&v)[16], float (&o)[8]) {
+  float L[8], R[8];
+  L[7] = v[7];
+#pragma unroll
+  for (int j = 6; j >= 0; --j) L[j] = fmaxf(v[j], L[j + 1]);
+  R[0] = v[8];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) R[j] = fmaxf(v[8 + j], R[j - 1]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaxf(L[j], R[j]);
+}
+
+// dst[r][c] = max(src[r][c-4..c+4]) for r in [r0, r0+nrows), c in [c0, c0+ncols), ncols % 8 == 0
+__device__ __forceinline__ void rowmax_pass(const float (*src)[NMS_P], float (*dst)[NMS_P], int r0, int nrows, int c0,
+                                            int ncols) {
+  const int total = nrows * (ncols >> 3);
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int r = r0 + i % nrows, c = c0 + (i / nrows) * 8;
+    float v[16], o[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = src[r][c - 4 + j];
+    run9(v, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[r][c + j] = o[j];
+  }
+}
+
+// f(r, c, max(src[r-4..r+4][c])) for r in [r0, r0+nrows), c in [c0, c0+ncols), nrows % 8 == 0
+template <class F>
+__device__ __forceinline__ void colmax_pass(const float (*src)[NMS_P], int r0, int nrows, int c0, int ncols, F f) {
+  const int total = (nrows >> 3) * ncols;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int c = c0 + i % ncols, r = r0 + (i / ncols) * 8;
+    float v[16], o[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = src[r - 4 + j][c];
+    run9(v, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f(r + j, c, o[j]);
+  }
+}
 
 __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H,
                                                   int W) {
-  __shared__ float sS[NMS_AH][NMS_AW];   // scores, -inf outside the image
-  __shared__ float sT[NMS_AH][NMS_AW];   // row-pass scratch
-  __shared__ float sM[NMS_AH][NMS_AW];   // max_mask (1/0) on region B, later s' on region C
+  __shared__ float sS[NMS_AH][NMS_P];   // scores, -inf outside the image
+  __shared__ float sT[NMS_AH][NMS_P];   // row-pass scratch
+  __shared__ float sM[NMS_AH][NMS_P];   // max_mask (1/0) on region B, later s' on region C
   __shared__ unsigned char sSupp[NMS_AH][NMS_AW];
+  __shared__ unsigned char sKeep[NMS_TH][NMS_TW];   // max_mask of the tile pixels
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
   const float* src = scores + (size_t)blockIdx.z * H * W;
   float* dst = out + (size_t)blockIdx.z * H * W;
   const int ax0 = x0 - 12, ay0 = y0 - 12;
   const float NEG = -INFINITY;
-
+  auto inside = [&](int r, int c) {
+    const int y = ay0 + r, x = ax0 + c;
+    return y >= 0 && y < H && x >= 0 && x < W;
+  };
   for (int i = tid; i < NMS_AH * NMS_AW; i += 256) {
     const int r = i / NMS_AW, c = i % NMS_AW;
-    const int y = ay0 + r, x = ax0 + c;
-    sS[r][c] = (y >= 0 && y < H && x >= 0 && x < W) ? src[(size_t)y * W + x] : NEG;
+    sS[r][c] = inside(r, c) ? src[(size_t)(ay0 + r) * W + (ax0 + c)] : NEG;
   }
   __syncthreads();
-  // --- mp(s): rows [0,40) x cols [4,84) row pass, then rows [4,36) column pass -> mask on B = rows/cols [4,..)
-  for (int i = tid; i < NMS_AH * (NMS_AW - 8); i += 256) {
-    const int r = i / (NMS_AW - 8), c = 4 + i % (NMS_AW - 8);
-    float m = sS[r][c - 4];
-#pragma unroll
-    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sS[r][c + d]);
-    sT[r][c] = m;
-  }
+  // max_mask = (s == mp(s)) on B = rows [4,36) x cols [4,84)
+  rowmax_pass(sS, sT, 0, NMS_AH, 4, NMS_AW - 8);
   __syncthreads();
-  for (int i = tid; i < (NMS_AH - 8) * (NMS_AW - 8); i += 256) {
-    const int r = 4 + i / (NMS_AW - 8), c = 4 + i % (NMS_AW - 8);
-    float m = sT[r - 4][c];
-#pragma unroll
-    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sT[r + d][c]);
-    const int y = ay0 + r, x = ax0 + c;
-    const bool in = (y >= 0 && y < H && x >= 0 && x < W);
-    sM[r][c] = (in && sS[r][c] == m) ? 1.f : 0.f;
-  }
+  colmax_pass(sT, 4, NMS_AH - 8, 4, NMS_AW - 8, [&](int r, int c, float m) {
+    const bool mk = inside(r, c) && sS[r][c] == m;
+    sM[r][c] = mk ? 1.f : 0.f;
+    if (r >= 12 && r < 12 + NMS_TH && c >= 12 && c < 12 + NMS_TW) sKeep[r - 12][c - 12] = mk ? 1 : 0;
+  });
   __syncthreads();
-  // --- supp = mp(mask) > 0 on C = rows [8,32) x cols [8,80)
-  for (int i = tid; i < (NMS_AH - 8) * (NMS_AW - 16); i += 256) {
-    const int r = 4 + i / (NMS_AW - 16), c = 8 + i % (NMS_AW - 16);
-    float m = sM[r][c - 4];
-#pragma unroll
-    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sM[r][c + d]);
-    sT[r][c] = m;
-  }
+  // supp = mp(max_mask) > 0 on C = rows [8,32) x cols [8,80);  s' = supp ? 0 : s  (-inf outside the image)
+  rowmax_pass(sM, sT, 4, NMS_AH - 8, 8, NMS_AW - 16);
   __syncthreads();
-  // mask of the tile pixels is needed at the end: keep it in registers before sM is overwritten with s'
-  float keep_mask[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int i = tid + q * 256;
-    const int r = 12 + i / NMS_TW, c = 12 + i % NMS_TW;
-    keep_mask[q] = sM[r][c];
-  }
-  __syncthreads();
-  for (int i = tid; i < (NMS_AH - 16) * (NMS_AW - 16); i += 256) {
-    const int r = 8 + i / (NMS_AW - 16), c = 8 + i % (NMS_AW - 16);
-    float m = sT[r - 4][c];
-#pragma unroll
-    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sT[r + d][c]);
+  colmax_pass(sT, 8, NMS_AH - 16, 8, NMS_AW - 16, [&](int r, int c, float m) {
     const bool supp = m > 0.f;
-    const int y = ay0 + r, x = ax0 + c;
-    const bool in = (y >= 0 && y < H && x >= 0 && x < W);
     sSupp[r][c] = supp ? 1 : 0;
-    sM[r][c] = in ? (supp ? 0.f : sS[r][c]) : NEG;   // s'
-  }
+    sM[r][c] = inside(r, c) ? (supp ? 0.f : sS[r][c]) : NEG;
+  });
   __syncthreads();
-  // --- mp(s') on the tile D = rows [12,28) x cols [12,76)
-  for (int i = tid; i < (NMS_AH - 16) * NMS_TW; i += 256) {
-    const int r = 8 + i / NMS_TW, c = 12 + i % NMS_TW;
-    float m = sM[r][c - 4];
-#pragma unroll
-    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sM[r][c + d]);
-    sT[r][c] = m;
-  }
+  // new = (s' == mp(s')) on the tile D = rows [12,28) x cols [12,76);  out = (max_mask | (new & !supp)) ? s : 0
+  rowmax_pass(sM, sT, 8, NMS_AH - 16, 12, NMS_TW);
   __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int i = tid + q * 256;
-    const int r = 12 + i / NMS_TW, c = 12 + i % NMS_TW;
+  colmax_pass(sT, 12, NMS_TH, 12, NMS_TW, [&](int r, int c, float m) {
     const int y = ay0 + r, x = ax0 + c;
-    if (y >= H || x >= W) continue;
-    float m = sT[r - 4][c];
-#pragma unroll
-    for (int d = -3; d <= 4; ++d) m = fmaxf(m, sT[r + d][c]);
+    if (y >= H || x >= W) return;
     const bool is_new = (sM[r][c] == m);
-    const bool mx = (keep_mask[q] != 0.f) || (is_new && !sSupp[r][c]);
+    const bool mx = sKeep[r - 12][c - 12] || (is_new && !sSupp[r][c]);
     dst[(size_t)y * W + x] = mx ? sS[r][c] : 0.f;
-  }
+  });
 }
 
 int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, int B) {

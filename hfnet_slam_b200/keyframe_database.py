@@ -167,5 +167,5 @@ def merge_shard_records(records: Sequence[bytes], rel: float = 0.8, floor: float
     ids, sc = ids[keep], sc[keep]
     order = np.argsort(ids, kind="stable")
     # an overflowing shard only matters if its k-th entry is still above the global bar
-    overflow = any(p[3] and len(p[2]) and p[2].min() > thr for p in parsed)
+    overflow = bool(any(p[3] and len(p[2]) and p[2].min() > thr for p in parsed))
     return ids[order], sc[order], float(best), overflow

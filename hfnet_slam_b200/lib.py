@@ -189,53 +189,59 @@ class Context:
         self.check(self.lib.hfb_load_weights(self.handle, C.cast(buf, C.c_void_p), len(blob)))
 
     # ------------------------------------------------------------------------------------------ extraction
-    def _alloc_features(self):
+    def _alloc_features(self, n: int = 1):
+        """One contiguous host block per field for n frames (frame b's rows start at b * kp_cap)."""
         cap = self.kp_cap
-        arrs = dict(x=np.zeros(cap, np.float32), y=np.zeros(cap, np.float32), response=np.zeros(cap, np.float32),
-                    octave=np.zeros(cap, np.int32), descriptors=np.zeros((cap, HFB_DESC_DIM), np.float32),
-                    global_descriptor=np.zeros(HFB_GLOBAL_DIM, np.float32))
-        f = hfb_features()
-        f.x, f.y, f.response = ptr(arrs["x"], _f32p), ptr(arrs["y"], _f32p), ptr(arrs["response"], _f32p)
-        f.octave, f.descriptors = ptr(arrs["octave"], _i32p), ptr(arrs["descriptors"], _f32p)
-        f.global_descriptor = ptr(arrs["global_descriptor"], _f32p) if self.with_global else None
-        return f, arrs
+        arrs = dict(x=np.empty((n, cap), np.float32), y=np.empty((n, cap), np.float32),
+                    response=np.empty((n, cap), np.float32), octave=np.empty((n, cap), np.int32),
+                    descriptors=np.empty((n, cap, HFB_DESC_DIM), np.float32),
+                    global_descriptor=np.empty((n, HFB_GLOBAL_DIM), np.float32))
+        feats = (hfb_features * n)()
+        for b in range(n):
+            f = feats[b]
+            f.x, f.y = ptr(arrs["x"][b], _f32p), ptr(arrs["y"][b], _f32p)
+            f.response, f.octave = ptr(arrs["response"][b], _f32p), ptr(arrs["octave"][b], _i32p)
+            f.descriptors = ptr(arrs["descriptors"][b], _f32p)
+            f.global_descriptor = ptr(arrs["global_descriptor"][b], _f32p) if self.with_global else None
+        return feats, arrs
 
     @staticmethod
-    def _trim(f: hfb_features, arrs: dict, with_global: bool) -> dict:
+    def _view(f: hfb_features, arrs: dict, b: int, with_global: bool) -> dict:
         n = int(f.n_total)
-        out = {k: arrs[k][:n].copy() for k in ("x", "y", "response", "octave", "descriptors")}
+        out = {k: arrs[k][b, :n] for k in ("x", "y", "response", "octave", "descriptors")}
         out["n_per_level"] = [int(v) for v in f.n_per_level]
-        out["global_descriptor"] = arrs["global_descriptor"].copy() if with_global else None
+        out["global_descriptor"] = arrs["global_descriptor"][b] if with_global else None
         return out
 
-    def extract_batch(self, images, n_per_level, threshold: float):
+    def _budgets(self, n_per_level):
+        return (C.c_int32 * HFB_MAX_LEVELS)(*([int(v) for v in n_per_level] + [0] * (HFB_MAX_LEVELS - len(n_per_level))))
+
+    def extract_batch(self, images, n_per_level, threshold: float, return_block: bool = False):
+        """HFextractor::operator() for n frames.  Returns one dict per frame (views into one contiguous host block;
+        with return_block=True also the block itself: frame b's descriptors are block['descriptors'][b, :n_b])."""
         imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
         for im in imgs:
             if im.ndim != 2 or im.shape != (self.height, self.width):
                 raise HfbError(1, f"image shape {im.shape} differs from the context's {(self.height, self.width)}")
         n = len(imgs)
         ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
-        budgets = (C.c_int32 * HFB_MAX_LEVELS)(*([int(v) for v in n_per_level] + [0] * (HFB_MAX_LEVELS - len(n_per_level))))
-        feats = (hfb_features * n)()
-        keep = []
-        for i in range(n):
-            f, arrs = self._alloc_features()
-            feats[i] = f
-            keep.append(arrs)
-        self.check(self.lib.hfb_extract_batch(self.handle, ptrs, n, self.width, budgets, threshold, feats))
-        return [self._trim(feats[i], keep[i], self.with_global) for i in range(n)]
+        feats, arrs = self._alloc_features(n)
+        self.check(self.lib.hfb_extract_batch(self.handle, ptrs, n, self.width, self._budgets(n_per_level), threshold,
+                                              feats))
+        out = [self._view(feats[i], arrs, i, self.with_global) for i in range(n)]
+        return (out, arrs) if return_block else out
 
     def extract(self, image, n_per_level, threshold: float) -> dict:
         return self.extract_batch([image], n_per_level, threshold)[0]
 
     def extract_batch_dev(self, d_images_ptr: int, n_images: int, n_per_level, threshold: float):
-        budgets = (C.c_int32 * HFB_MAX_LEVELS)(*([int(v) for v in n_per_level] + [0] * (HFB_MAX_LEVELS - len(n_per_level))))
-        self.check(self.lib.hfb_extract_batch_dev(self.handle, C.c_void_p(d_images_ptr), n_images, budgets, threshold))
+        self.check(self.lib.hfb_extract_batch_dev(self.handle, C.c_void_p(d_images_ptr), n_images,
+                                                  self._budgets(n_per_level), threshold))
 
     def fetch_features(self, image_index: int) -> dict:
-        f, arrs = self._alloc_features()
-        self.check(self.lib.hfb_fetch_features(self.handle, image_index, C.byref(f)))
-        return self._trim(f, arrs, self.with_global)
+        feats, arrs = self._alloc_features(1)
+        self.check(self.lib.hfb_fetch_features(self.handle, image_index, C.byref(feats[0])))
+        return self._view(feats[0], arrs, 0, self.with_global)
 
     def match_consecutive_dev(self, n_images: int, mode: int, thr: float):
         self.check(self.lib.hfb_match_consecutive_dev(self.handle, n_images, mode, thr))

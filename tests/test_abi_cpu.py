@@ -1,0 +1,75 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports every symbol that
+include/hfnet_b200.h declares (and nothing in the Python binding is missing from the header), and fails loudly --
+never silently falls back -- when there is no B200."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared():
+    text = (ROOT / "include" / "hfnet_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(hfb_[a-z0-9_]+)\s*\(", text))
+
+
+def test_header_symbols_are_exported(native_lib):
+    from hfnet_slam_b200 import lib
+    declared = _declared()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(native_lib, name), f"{name} declared in include/hfnet_b200.h but not exported"
+    assert set(lib.SIGNATURES) == declared, (set(lib.SIGNATURES) ^ declared)
+    assert native_lib.hfb_version() == 100
+
+
+def test_struct_layouts_match_header():
+    from hfnet_slam_b200 import lib
+    assert C.sizeof(lib.hfb_config) == 32
+    assert C.sizeof(lib.hfb_features) == 6 * 8 + 8 * 4 + 4 + 4      # 6 pointers, n_per_level[8], n_total, padding
+    assert lib.hfb_lba_problem.K.offset % 4 == 0 and C.sizeof(lib.hfb_lba_stats) == 40
+
+
+def test_sass_is_blackwell_native():
+    """The shipped cubin must contain tcgen05 / TMA instructions (UTCHMMA, UTMALDG, LDTM), not legacy HMMA."""
+    import shutil
+    import subprocess
+    from hfnet_slam_b200 import lib
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", str(lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert not re.search(r"\bHMMA\b", sass)
+
+
+def test_no_gpu_is_a_loud_error(native_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from hfnet_slam_b200.lib import Context, HfbError
+    with pytest.raises(HfbError):
+        Context(height=64, width=64)
+
+
+def test_bad_config_rejected_without_touching_the_device(native_lib):
+    from hfnet_slam_b200 import lib
+    h = C.c_void_p()
+    cfg = lib.hfb_config(0, 8, 8, 1, 1.2, 100, 1, 1)          # too small
+    assert native_lib.hfb_create(C.byref(cfg), C.byref(h)) == 1 and not h
+    cfg = lib.hfb_config(0, 480, 752, 9, 1.2, 100, 1, 1)      # too many levels
+    assert native_lib.hfb_create(C.byref(cfg), C.byref(h)) == 1
+    assert native_lib.hfb_last_error(None) == b"null context"
+    assert native_lib.hfb_sync(None) == 1 and native_lib.hfb_kfdb_size(None) == 0
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under hfnet_slam_b200/ may import it."""
+    for p in (ROOT / "hfnet_slam_b200").rglob("*.py"):
+        src = p.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), p
