@@ -73,3 +73,29 @@ def test_product_path_never_imports_the_oracle():
     for p in (ROOT / "hfnet_slam_b200").rglob("*.py"):
         src = p.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), p
+
+
+def test_reference_side_shim_compiles_and_links(native_lib, tmp_path):
+    """include/HFNetB200Model.h (the BaseModel subclass a reference maintainer adds) compiles as C++14 against the
+    reference's interface (stand-ins for OpenCV) and links against the C-ABI library."""
+    import shutil
+    import subprocess
+    from hfnet_slam_b200 import lib
+    if not shutil.which("g++"):
+        pytest.skip("g++ not on PATH")
+    exe = tmp_path / "shim_check"
+    r = subprocess.run(["g++", "-std=c++14", "-Wall", f"-I{ROOT / 'include'}", "-o", str(exe),
+                        str(ROOT / "tests" / "native" / "shim_compile_check.cpp"), str(lib.LIB_PATH),
+                        f"-Wl,-rpath,{lib.LIB_PATH.parent}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_header_is_plain_c():
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not on PATH")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-fsyntax-only", "-x", "c",
+                        str(ROOT / "include" / "hfnet_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -63,10 +63,11 @@ def test_shard_merge_equals_unsharded():
         assert not ov and m_best == float(best)
         assert m_ids.tolist() == sel.tolist() and np.array_equal(m_sc, sc[sel])
     # overflow is flagged when a shard has more rows above the global bar than slots
-    recs = [make_record(ids, sc, 0.0, 0.0, 4)]
-    assert merge_shard_records(recs, rel=0.0)[3] is True
+    sc2 = np.linspace(0.5, 0.9, 10).astype(np.float32)            # all ten rows are above 0.5 * best
+    recs = [make_record(np.arange(10, dtype=np.int64), sc2, 0.5, 0.0, 4)]
+    assert merge_shard_records(recs, rel=0.5)[3] is True
     b, i, s, o = parse_shard_record(recs[0])
-    assert len(i) == 4 and o and np.all(np.diff(s) <= 0)
+    assert len(i) == 4 and o and np.all(np.diff(s) <= 0) and i.tolist() == [9, 8, 7, 6]
 
 
 _GLOO_WORKER = r"""
