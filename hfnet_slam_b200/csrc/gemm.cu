@@ -62,8 +62,13 @@ int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, 
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
-// bias (+ReLU6) (+residual) -> fp16 or fp32 rows.  The tile is staged through the (now idle) operand ring so that
-// global stores are coalesced along the output row instead of one 16-byte piece per thread-row.
+// bias (+ReLU6) (+residual) (+L2 normalisation of the whole row) -> fp16 or fp32 rows.  Each epilogue warp owns 32 tile
+// rows; it stages 64-column slabs in its private shared-memory area and writes them out with lanes running along the
+// output row, so global stores are full, contiguous 16-byte pieces instead of one piece per thread-row.
+#define EPI_SLAB 64
+#define EPI_PITCH (EPI_SLAB * 4 + 16)              // bytes per staged row: odd multiple of 16 -> conflict-free
+#define EPI_WARP_BYTES (32 * EPI_PITCH)
+
 struct EpiStore {
   struct Params {
     void* out;
@@ -74,110 +79,86 @@ struct EpiStore {
     int ldr;
     int relu6;
     int f32;
+    int l2norm;     // tf.nn.l2_normalize over the N columns (needs BN == N): descriptor head, hf_net.py:78-80
   };
-  static __host__ __device__ __forceinline__ int stage_esz(const Params& p) { return (p.f32 || p.residual) ? 4 : 2; }
-  static __host__ size_t stage_bytes(const Params& p, int BN) { return (size_t)128 * ((size_t)BN * stage_esz(p) + 16) + 1024; }
 
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
-    const int tid = threadIdx.x;
-    const int esz = stage_esz(p);
-    const int pitch = g.BN * esz + 16;                         // odd multiple of 16 B: conflict-free 16-byte rows
-    long long* s_row = reinterpret_cast<long long*>(tr.stage);  // [128] output row or -1
-    uint8_t* tile = tr.stage + 1024;
-    s_row[tid] = tr.valid ? tr.row : -1;
-    uint8_t* my = tile + (size_t)tid * pitch;
-    for (int c0 = 0; c0 < g.BN; c0 += 16) {
-      uint32_t r[16];
-      tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
-      tc::tmem_ld_wait();
-      const int n = tr.n0 + c0;
-      if (n >= g.N) continue;   // uniform
-      float v[16];
+    const int lane = threadIdx.x & 31;
+    const int esz = (p.f32 || p.residual) ? 4 : 2;   // staging element size
+    uint8_t* my = tr.stage + (size_t)lane * EPI_PITCH;
+    const long long orow = tr.valid ? tr.row : -1;
+    float inv = 1.f;
+    if (p.l2norm) {
+      float ss = 0.f;
+      for (int c0 = 0; c0 < g.N; c0 += 16) {
+        uint32_t r[16];
+        tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
+        tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float b = (n + j < g.N && p.bias) ? __ldg(p.bias + n + j) : 0.f;
-        v[j] = __uint_as_float(r[j]) + b;
-        if (p.relu6) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
-      }
-      if (esz == 4) {
-        float4* d = reinterpret_cast<float4*>(my + (size_t)c0 * 4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      } else {
-        uint4* d = reinterpret_cast<uint4*>(my + (size_t)c0 * 2);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 q;
-          __half2* hq = reinterpret_cast<__half2*>(&q);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
-          d[h] = q;
+        for (int j = 0; j < 16; ++j) {
+          const float v = __uint_as_float(r[j]) + __ldg(p.bias + c0 + j);
+          ss = fmaf(v, v, ss);
         }
       }
+      inv = rsqrtf(fmaxf(ss, 1e-12f));
     }
-    __syncthreads();
-    const int ncols = min(g.BN, g.N - tr.n0);         // multiple of 8
-    const int cpr = ncols * esz / 16;                  // 16-byte chunks per row
-    const int total = 128 * cpr;
-    for (int id = tid; id < total; id += 128) {
-      const int row = id / cpr, ch = id - row * cpr;
-      const long long orow = s_row[row];
-      if (orow < 0) continue;
-      const uint4 q = *reinterpret_cast<const uint4*>(tile + (size_t)row * pitch + (size_t)ch * 16);
-      if (esz == 2) {
-        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + orow * p.ldo + p.col_off + tr.n0 + ch * 8) = q;
-      } else if (p.f32) {
-        *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + p.col_off + tr.n0 + ch * 4) = q;
-      } else {  // fp32 staging + fp16 residual -> fp16 (single rounding)
-        const float* f = reinterpret_cast<const float*>(&q);
-        const uint2 rr = *reinterpret_cast<const uint2*>(p.residual + orow * p.ldr + tr.n0 + ch * 4);
-        const __half2* hr = reinterpret_cast<const __half2*>(&rr);
-        const float2 r0 = __half22float2(hr[0]), r1 = __half22float2(hr[1]);
-        uint2 o;
-        __half2* ho = reinterpret_cast<__half2*>(&o);
-        ho[0] = __floats2half2_rn(f[0] + r0.x, f[1] + r0.y);
-        ho[1] = __floats2half2_rn(f[2] + r1.x, f[3] + r1.y);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + orow * p.ldo + p.col_off + tr.n0 + ch * 4) = o;
-      }
-    }
-  }
-};
-
-// Descriptor head tail (hfnet/models/hf_net.py:78-80): + bias, tf.nn.l2_normalize over the 256 channels, fp32 rows.
-// The whole row lives in this thread's TMEM lane (BN == N == 256): two passes over TMEM, no cross-thread traffic.
-struct EpiL2Norm {
-  struct Params {
-    float* out;  // [row][N]
-    const float* bias;
-  };
-  static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
-    float ss = 0.f;
-    for (int c0 = 0; c0 < g.N; c0 += 16) {
-      uint32_t r[16];
-      tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
-      tc::tmem_ld_wait();
+    const int ncols = min(g.BN, g.N - tr.n0);                 // valid columns of this tile (multiple of 8)
+    for (int s0 = 0; s0 < ncols; s0 += EPI_SLAB) {
+      const int scols = min(EPI_SLAB, ncols - s0);
+      for (int c0 = 0; c0 < scols; c0 += 16) {
+        uint32_t r[16];
+        tc::tmem_ld16(tr.taddr + (uint32_t)(s0 + c0), r);
+        tc::tmem_ld_wait();
+        const int n = tr.n0 + s0 + c0;
+        float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float v = __uint_as_float(r[j]) + __ldg(p.bias + c0 + j);
-        ss = fmaf(v, v, ss);
-      }
-    }
-    const float inv = rsqrtf(fmaxf(ss, 1e-12f));
-    for (int c0 = 0; c0 < g.N; c0 += 16) {
-      uint32_t r[16];
-      tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
-      tc::tmem_ld_wait();
-      if (!tr.valid) continue;
-      float* o = p.out + tr.row * g.N + c0;
+        for (int j = 0; j < 16; ++j) {
+          const float b = (n + j < g.N && p.bias) ? __ldg(p.bias + n + j) : 0.f;
+          v[j] = (__uint_as_float(r[j]) + b) * inv;
+          if (p.relu6) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
+        }
+        if (esz == 4) {
+          float4* d = reinterpret_cast<float4*>(my + (size_t)c0 * 4);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 w;
-        w.x = (__uint_as_float(r[4 * q]) + __ldg(p.bias + c0 + 4 * q)) * inv;
-        w.y = (__uint_as_float(r[4 * q + 1]) + __ldg(p.bias + c0 + 4 * q + 1)) * inv;
-        w.z = (__uint_as_float(r[4 * q + 2]) + __ldg(p.bias + c0 + 4 * q + 2)) * inv;
-        w.w = (__uint_as_float(r[4 * q + 3]) + __ldg(p.bias + c0 + 4 * q + 3)) * inv;
-        *reinterpret_cast<float4*>(o + 4 * q) = w;
+          for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+          uint4* d = reinterpret_cast<uint4*>(my + (size_t)c0 * 2);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint4 q;
+            __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
+            d[h] = q;
+          }
+        }
       }
+      __syncwarp();
+      const int cpr = scols * esz / 16;                        // 16-byte chunks per staged row
+      const int total = 32 * cpr;                              // multiple of 32: every lane iterates equally
+      for (int id = lane; id < total; id += 32) {
+        const int row = id / cpr, ch = id - row * cpr;
+        const long long dst_row = __shfl_sync(0xffffffffu, orow, row);
+        if (dst_row < 0) continue;
+        const uint4 q = *reinterpret_cast<const uint4*>(tr.stage + (size_t)row * EPI_PITCH + (size_t)ch * 16);
+        const long long col = (long long)p.col_off + tr.n0 + s0;
+        if (esz == 2) {
+          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + dst_row * p.ldo + col + ch * 8) = q;
+        } else if (p.f32) {
+          *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + dst_row * p.ldo + col + ch * 4) = q;
+        } else {  // fp32 staging + fp16 residual -> fp16 (single rounding)
+          const float* f = reinterpret_cast<const float*>(&q);
+          const uint2 rr = *reinterpret_cast<const uint2*>(p.residual + dst_row * p.ldr + tr.n0 + s0 + ch * 4);
+          const __half2* hr = reinterpret_cast<const __half2*>(&rr);
+          const float2 r0 = __half22float2(hr[0]), r1 = __half22float2(hr[1]);
+          uint2 o;
+          __half2* ho = reinterpret_cast<__half2*>(&o);
+          ho[0] = __floats2half2_rn(f[0] + r0.x, f[1] + r0.y);
+          ho[1] = __floats2half2_rn(f[2] + r1.x, f[3] + r1.y);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + dst_row * p.ldo + col + ch * 4) = o;
+        }
+      }
+      __syncwarp();
     }
   }
 };
@@ -239,24 +220,32 @@ struct EpiSoftmaxD2S {
 // ------------------------------------------------------------------------------------------------ launchers
 template <class Epi>
 static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g_in, int B,
-                     const typename Epi::Params& ep, const char* what, size_t epi_bytes = 0) {
+                     const typename Epi::Params& ep, const char* what, uint32_t epi_warp_bytes) {
   GemmGeom g = g_in;
-  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages, epi_bytes);
-  const size_t smem = gemm_smem_bytes(g.BN, g.stages, epi_bytes);
+  gemm_set_rows(g, g.M, B);
+  g.epi_warp_bytes = epi_warp_bytes;
+  // ring depth: keep the CTA near 110 KB so that two persistent CTAs (8 epilogue warps) share an SM when TMEM allows
+  const size_t stage = GEMM_TILE_A_BYTES + (size_t)g.BN * 128;
+  int st = (int)((110 * 1024 - 4 * (size_t)epi_warp_bytes) / stage);
+  g.stages = st < 2 ? 2 : (st > 4 ? 4 : st);
+  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages);
+  const size_t smem = gemm_smem_bytes(g.BN, g.stages, epi_warp_bytes);
   static size_t configured = 0;  // per-instantiation
   if (smem > configured) {
     HFB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  gemm_tc_kernel<Epi><<<gemm_grid(g, B), 128, smem, ctx->stream>>>(tmA, tmB, g, ep);
+  if (g.total_tiles <= 0) return HFB_OK;
+  const int grid = gemm_grid(g, ctx->n_sm, smem);
+  gemm_tc_kernel<Epi><<<grid, GEMM_THREADS, smem, ctx->stream>>>(tmA, tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, what);
   return HFB_OK;
 }
 
 int gemm_store(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, int B, void* out,
                int ldo, int col_off, const float* bias, const __half* residual, int ldr, int relu6, int f32) {
-  EpiStore::Params p{out, ldo, col_off, bias, residual, ldr, relu6, f32};
-  return launch_tc<EpiStore>(ctx, tmA, tmB, g, B, p, "gemm_store", EpiStore::stage_bytes(p, g.BN));
+  EpiStore::Params p{out, ldo, col_off, bias, residual, ldr, relu6, f32, 0};
+  return launch_tc<EpiStore>(ctx, tmA, tmB, g, B, p, "gemm_store", EPI_WARP_BYTES);
 }
 int gemm_l2norm(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* out,
                 const float* bias) {
@@ -264,8 +253,8 @@ int gemm_l2norm(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, co
     ctx->set_error("gemm_l2norm needs BN == N");
     return HFB_ERR_INVALID;
   }
-  EpiL2Norm::Params p{out, bias};
-  return launch_tc<EpiL2Norm>(ctx, tmA, tmB, g, 1, p, "gemm_l2norm");
+  EpiStore::Params p{out, g.N, 0, bias, nullptr, 0, 0, 1, 1};
+  return launch_tc<EpiStore>(ctx, tmA, tmB, g, 1, p, "gemm_l2norm", EPI_WARP_BYTES);
 }
 int gemm_softmax_d2s(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* scores,
                      float* logits, const float* bias, int Hc, int Wc) {
@@ -274,7 +263,7 @@ int gemm_softmax_d2s(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
     return HFB_ERR_INVALID;
   }
   EpiSoftmaxD2S::Params p{scores, logits, bias, Hc, Wc};
-  return launch_tc<EpiSoftmaxD2S>(ctx, tmA, tmB, g, 1, p, "gemm_softmax_d2s");
+  return launch_tc<EpiSoftmaxD2S>(ctx, tmA, tmB, g, 1, p, "gemm_softmax_d2s", 0);
 }
 
 // ------------------------------------------------------------------------------------------------ debug / parity

@@ -1,14 +1,17 @@
 // The one tensor-core main loop of this library (sm_100a): C[M][N] = A[M][K] * W[N][K]^T with fp16 operands staged by
 // TMA into 128B-swizzled shared-memory tiles, tcgen05.mma (UMMA 128 x BN x 16) accumulating fp32 in TMEM, and a
-// pluggable epilogue that reads the accumulator tile back with tcgen05.ld (thread t <-> tile row t).
+// pluggable epilogue that reads the accumulator tile back with tcgen05.ld (thread <-> tile row).
 //
-// A comes either from a 2-D map [rows][K] (1x1 convolutions, descriptor / database matrices) or, for the 3x3 SAME
-// stride-1 head convolutions, from a 4-D map (C, W, H, B) of an NHWC tensor: one tile row = one pixel of an 8 x 16
-// patch, one k-block = (tap, 64-channel slice), the tap shift is a TMA coordinate offset and TMA's out-of-bounds zero
-// fill is the SAME padding (hfnet/models/hf_net.py:63,70).
+// A comes either from a 2-D map [rows][K] (1x1 convolutions, descriptor matrices) or, for the 3x3 SAME stride-1 head
+// convolutions, from a 4-D map (C, W, H, B) of an NHWC tensor: one tile row = one pixel of an 8 x 16 patch, one
+// k-block = (tap, 64-channel slice), the tap shift is a TMA coordinate offset and TMA's out-of-bounds zero fill is the
+// SAME padding (hfnet/models/hf_net.py:63,70).
 //
-// CTA = 128 threads, one 128 x BN output tile.  Thread 0 is the TMA producer, thread 32 the UMMA issuer, then all four
-// warps run the epilogue (warp w owns TMEM lanes 32w..32w+31).
+// Persistent, warp-specialised CTA of 192 threads that walks tiles blockIdx.x, +gridDim.x, ...:
+//   warp 0      TMA producer (one elected lane) feeding a `stages`-deep smem ring that runs ahead across tiles
+//   warp 1      UMMA issuer (one lane) + TMEM owner; two accumulator stages of BN columns ping-pong, so the
+//               epilogue of tile i overlaps the loads and MMAs of tile i+1
+//   warps 2..5  epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (the hardware's lane-group rule) = 32 tile rows
 #pragma once
 #include "tc.cuh"
 
@@ -22,10 +25,12 @@ struct GemmGeom {
   int kb_per_row;     // k-blocks per tap (conv) / in total (plain) = ceil(K/64)
   int num_kb;         // plain: kb_per_row, conv: 9 * kb_per_row
   int stages;         // smem ring depth (<= 8)
+  int m_tiles, n_tiles, total_tiles;  // per problem (pair) m/n tiling; total over all pairs
   uint32_t idesc;
-  uint32_t tmem_cols; // power of two >= max(32, BN)
-  uint32_t ring_bytes; // operand ring size (>= stages * stage bytes); barriers live right behind it
-  // Batched independent problems (descriptor matching): blockIdx.z = pair, pair_tab = device int[4][n_pairs] holding
+  uint32_t tmem_cols;   // power of two >= max(32, 2*BN)
+  uint32_t ring_bytes;  // operand ring size (multiple of 1024)
+  uint32_t epi_warp_bytes;  // per-epilogue-warp staging bytes behind the ring
+  // Batched independent problems (descriptor matching): pair_tab = device int[4][n_pairs] holding
   // a_off | a_cnt | b_off | b_cnt (row ranges inside A's and W's maps).  null = one problem of M x N.
   const int* pair_tab;
   int n_pairs;
@@ -35,61 +40,80 @@ struct TileRow {
   bool valid;
   long long row;      // output row (pixel index / global A row) of this thread
   int n0;             // first output column of the tile (problem-local)
-  uint32_t taddr;     // TMEM address of (this warp's lane base, column 0)
+  uint32_t taddr;     // TMEM address of (this warp's lane base, accumulator column 0)
   int row_local;      // row inside the problem (== row when not batched)
   int n_cnt;          // columns of the problem (== N when not batched)
   int a_off, b_off;   // batched: first global row of the pair's A / B block
-  uint8_t* stage;     // operand ring (1024-aligned), free for epilogue staging once the accumulator is complete
+  uint8_t* stage;     // this warp's private staging area (epi_warp_bytes)
+  int ewarp;          // epilogue warp index 0..3 (== TMEM lane group)
 };
 
 #define GEMM_TILE_A_BYTES 16384  // 128 rows x 128 B
+#define GEMM_THREADS 192
+#define GEMM_EPI_BAR 1           // named barrier of the 128 epilogue threads
 
-// epi_bytes: shared memory the epilogue wants to reuse from the operand ring (the ring is grown if smaller)
-static inline size_t gemm_ring_bytes(int BN, int stages, size_t epi_bytes = 0) {
-  const size_t ring = (size_t)stages * (GEMM_TILE_A_BYTES + (size_t)BN * 128);
-  return (ring > epi_bytes ? ring : epi_bytes + 1023) & ~(size_t)1023;
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(GEMM_EPI_BAR), "n"(128) : "memory"); }
+
+struct TileCoord {
+  bool valid;
+  int m0, n0, img, y0, x0, a_off, a_cnt, b_off, b_cnt, mt;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int tile) {
+  TileCoord t;
+  const int per = g.m_tiles * g.n_tiles;
+  const int pr = tile / per;
+  const int rem = tile - pr * per;
+  t.mt = rem / g.n_tiles;
+  const int nt = rem - t.mt * g.n_tiles;
+  t.n0 = nt * g.BN;
+  t.a_off = 0; t.a_cnt = g.M; t.b_off = 0; t.b_cnt = g.N;
+  t.valid = true;
+  if (g.pair_tab) {
+    t.a_off = g.pair_tab[pr];
+    t.a_cnt = g.pair_tab[g.n_pairs + pr];
+    t.b_off = g.pair_tab[2 * g.n_pairs + pr];
+    t.b_cnt = g.pair_tab[3 * g.n_pairs + pr];
+    t.valid = (t.mt * 128 < t.a_cnt) && (t.n0 < t.b_cnt);
+  }
+  t.m0 = 0; t.img = 0; t.y0 = 0; t.x0 = 0;
+  if (g.conv) {
+    int q = t.mt;
+    const int tx = q % g.tiles_x;
+    q /= g.tiles_x;
+    const int ty = q % g.tiles_y;
+    t.img = q / g.tiles_y;
+    t.y0 = ty * 8;
+    t.x0 = tx * 16;
+  } else {
+    t.m0 = t.a_off + t.mt * 128;
+  }
+  return t;
 }
-static inline size_t gemm_smem_bytes(int BN, int stages, size_t epi_bytes = 0) {
-  return 1024 + gemm_ring_bytes(BN, stages, epi_bytes) + 256;
+
+static inline size_t gemm_ring_bytes(int BN, int stages) {
+  return (size_t)stages * (GEMM_TILE_A_BYTES + (size_t)BN * 128);
+}
+static inline size_t gemm_smem_bytes(int BN, int stages, size_t epi_warp_bytes) {
+  return 1024 + gemm_ring_bytes(BN, stages) + 4 * epi_warp_bytes + 256;
 }
 
 template <class Epi>
-__global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const GemmGeom g,
-                                                      const typename Epi::Params ep) {
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const GemmGeom g, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = GEMM_TILE_A_BYTES + (uint32_t)g.BN * 128u;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.ring_bytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 8;
-  uint64_t* acc_full = bars + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint8_t* epi_smem = smem + g.ring_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + 4 * (size_t)g.epi_warp_bytes);
+  uint64_t* full = bars;            // [8]
+  uint64_t* empty = bars + 8;       // [8]
+  uint64_t* acc_full = bars + 16;   // [2]
+  uint64_t* acc_empty = bars + 18;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int n0 = blockIdx.y * g.BN;
-  int a_off = 0, a_cnt = g.M, b_off = 0, b_cnt = g.N;
-  if (g.pair_tab) {
-    const int pr = blockIdx.z;
-    a_off = g.pair_tab[pr];
-    a_cnt = g.pair_tab[g.n_pairs + pr];
-    b_off = g.pair_tab[2 * g.n_pairs + pr];
-    b_cnt = g.pair_tab[3 * g.n_pairs + pr];
-    if ((int)blockIdx.x * 128 >= a_cnt || n0 >= b_cnt) return;  // uniform: whole CTA leaves before any setup
-  }
-  // tile origin
-  int m0 = 0, img = 0, y0 = 0, x0 = 0;
-  if (g.conv) {
-    int t = blockIdx.x;
-    int tx = t % g.tiles_x;
-    t /= g.tiles_x;
-    int ty = t % g.tiles_y;
-    img = t / g.tiles_y;
-    y0 = ty * 8;
-    x0 = tx * 16;
-  } else {
-    m0 = a_off + blockIdx.x * 128;
-  }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     tc::prefetch_tmap(&tmA);
@@ -98,7 +122,10 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ CU
       tc::mbar_init(&full[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
-    tc::mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&acc_full[s], 1);
+      tc::mbar_init(&acc_empty[s], 4);   // one arrival per epilogue warp
+    }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, g.tmem_cols);
@@ -107,70 +134,100 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ CU
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (tid == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    for (int kb = 0; kb < g.num_kb; ++kb) {
-      const int s = kb % g.stages;
-      const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-      tc::mbar_wait(&empty[s], ph ^ 1u);
-      uint8_t* sa = smem + (size_t)s * stage_bytes;
-      uint8_t* sb = sa + GEMM_TILE_A_BYTES;
-      tc::mbar_expect_tx(&full[s], stage_bytes);
-      if (g.conv) {
-        const int tap = kb / g.kb_per_row, cb = kb - tap * g.kb_per_row;
-        const int dy = tap / 3, dx = tap - dy * 3;
-        tc::tma_load_4d(sa, &tmA, &full[s], cb * 64, x0 + dx - 1, y0 + dy - 1, img);
-        tc::tma_load_2d(sb, &tmB, &full[s], tap * g.K + cb * 64, n0);
-      } else {
-        tc::tma_load_2d(sa, &tmA, &full[s], g.a_k_off + kb * 64, m0);
-        tc::tma_load_2d(sb, &tmB, &full[s], kb * 64, b_off + n0);
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(g, tile);
+        if (!t.valid) continue;
+        for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+          const int s = it % g.stages;
+          const uint32_t ph = (it / g.stages) & 1u;
+          tc::mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + GEMM_TILE_A_BYTES;
+          tc::mbar_expect_tx(&full[s], stage_bytes);
+          if (g.conv) {
+            const int tap = kb / g.kb_per_row, cb = kb - tap * g.kb_per_row;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            tc::tma_load_4d(sa, &tmA, &full[s], cb * 64, t.x0 + dx - 1, t.y0 + dy - 1, t.img);
+            tc::tma_load_2d(sb, &tmB, &full[s], tap * g.K + cb * 64, t.n0);
+          } else {
+            tc::tma_load_2d(sa, &tmA, &full[s], g.a_k_off + kb * 64, t.m0);
+            tc::tma_load_2d(sb, &tmB, &full[s], kb * 64, t.b_off + t.n0);
+          }
+        }
       }
     }
-  } else if (tid == 32) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------ UMMA issuer
-    for (int kb = 0; kb < g.num_kb; ++kb) {
-      const int s = kb % g.stages;
-      const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-      tc::mbar_wait(&full[s], ph);
-      tc::fence_after_sync();
-      const uint32_t sa = tc::smem_u32(smem + (size_t)s * stage_bytes);
-      const uint64_t da = tc::make_sdesc_sw128(sa);
-      const uint64_t db = tc::make_sdesc_sw128(sa + GEMM_TILE_A_BYTES);
-      const int cb = kb % g.kb_per_row;
-      const int krem = g.K - cb * 64;                       // valid K elements in this block
-      const int nk = krem >= 64 ? 4 : (krem + 15) >> 4;     // zero-filled tail needs no MMA
-      for (int k = 0; k < nk; ++k)
-        tc::umma_f16(tmem_base, tc::sdesc_advance_k16(da, k), tc::sdesc_advance_k16(db, k), g.idesc,
-                     (kb > 0 || k > 0) ? 1u : 0u);
-      tc::umma_commit(&empty[s]);                            // frees the smem slot when these MMAs retire
+    if (lane == 0) {
+      uint32_t it = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(g, tile);
+        if (!t.valid) continue;
+        const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        tc::mbar_wait(&acc_empty[as], aph ^ 1u);       // epilogue has drained this accumulator stage
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)g.BN;
+        for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+          const int s = it % g.stages;
+          const uint32_t ph = (it / g.stages) & 1u;
+          tc::mbar_wait(&full[s], ph);
+          tc::fence_after_sync();
+          const uint32_t sa = tc::smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t da = tc::make_sdesc_sw128(sa);
+          const uint64_t db = tc::make_sdesc_sw128(sa + GEMM_TILE_A_BYTES);
+          const int cb = kb % g.kb_per_row;
+          const int krem = g.K - cb * 64;                       // valid K elements in this block
+          const int nk = krem >= 64 ? 4 : (krem + 15) >> 4;     // zero-filled tail needs no MMA
+          for (int k = 0; k < nk; ++k)
+            tc::umma_f16(d_tmem, tc::sdesc_advance_k16(da, k), tc::sdesc_advance_k16(db, k), g.idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+          tc::umma_commit(&empty[s]);                            // frees the smem slot when these MMAs retire
+        }
+        tc::umma_commit(&acc_full[as]);
+        ++acc_it;
+      }
     }
-    tc::umma_commit(acc_full);
-  }
-  __syncwarp();
-  // ------------------------------------------------------------------ epilogue (all 128 threads)
-  tc::mbar_wait(acc_full, 0);
-  __syncwarp();
-  tc::fence_after_sync();
-
-  TileRow tr;
-  tr.n0 = n0;
-  tr.taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-  if (g.conv) {
-    const int y = y0 + (tid >> 4), x = x0 + (tid & 15);
-    tr.valid = (y < g.H) && (x < g.W);
-    tr.row = ((long long)img * g.H + y) * g.W + x;
-    tr.row_local = (int)tr.row;
   } else {
-    tr.row_local = blockIdx.x * 128 + tid;
-    tr.row = (long long)m0 + tid;
-    tr.valid = tr.row_local < a_cnt;
+    // ------------------------------------------------------------------ epilogue warps (2..5)
+    const int ewarp = warp & 3;   // TMEM lane group this warp may access
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(g, tile);
+      if (!t.valid) continue;
+      const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+      tc::mbar_wait(&acc_full[as], aph);
+      __syncwarp();
+      tc::fence_after_sync();
+      TileRow tr;
+      tr.n0 = t.n0;
+      tr.taddr = tmem_base + ((uint32_t)(ewarp * 32) << 16) + as * (uint32_t)g.BN;
+      const int r = ewarp * 32 + lane;
+      if (g.conv) {
+        const int y = t.y0 + (r >> 4), x = t.x0 + (r & 15);
+        tr.valid = (y < g.H) && (x < g.W);
+        tr.row = ((long long)t.img * g.H + y) * g.W + x;
+        tr.row_local = (int)tr.row;
+      } else {
+        tr.row_local = t.mt * 128 + r;
+        tr.row = (long long)t.m0 + r;
+        tr.valid = tr.row_local < t.a_cnt;
+      }
+      tr.n_cnt = t.b_cnt;
+      tr.a_off = t.a_off;
+      tr.b_off = t.b_off;
+      tr.stage = epi_smem + (size_t)ewarp * g.epi_warp_bytes;
+      tr.ewarp = ewarp;
+      Epi::run(ep, g, tr);
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+      ++acc_it;
+    }
   }
-  tr.n_cnt = b_cnt;
-  tr.a_off = a_off;
-  tr.b_off = b_off;
-  tr.stage = smem;
-  Epi::run(ep, g, tr);
-
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, g.tmem_cols);
@@ -184,8 +241,17 @@ int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, 
 
 static inline uint32_t tmem_cols_for(int BN) {
   uint32_t c = 32;
-  while ((int)c < BN) c <<= 1;
+  while ((int)c < 2 * BN) c <<= 1;
   return c;
+}
+
+static inline void gemm_finish_geom(GemmGeom& g, int m_tiles) {
+  g.m_tiles = m_tiles;
+  g.n_tiles = (g.N + g.BN - 1) / g.BN;
+  g.total_tiles = g.m_tiles * g.n_tiles * (g.pair_tab ? g.n_pairs : 1);
+  g.idesc = tc::make_idesc_f16(g.BN);
+  g.tmem_cols = tmem_cols_for(g.BN);
+  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages);
 }
 
 static inline void gemm_fill_geom(GemmGeom& g, int M, int N, int K, int BN, int a_k_off) {
@@ -193,11 +259,10 @@ static inline void gemm_fill_geom(GemmGeom& g, int M, int N, int K, int BN, int 
   g.conv = 0; g.H = g.W = 0; g.tiles_x = g.tiles_y = 0;
   g.kb_per_row = (K + 63) / 64;
   g.num_kb = g.kb_per_row;
-  g.stages = g.num_kb < 4 ? g.num_kb : 4;
-  g.idesc = tc::make_idesc_f16(BN);
-  g.tmem_cols = tmem_cols_for(BN);
-  g.ring_bytes = (uint32_t)gemm_ring_bytes(BN, g.stages);
+  g.stages = 4;
+  g.epi_warp_bytes = 0;
   g.pair_tab = nullptr; g.n_pairs = 0;
+  gemm_finish_geom(g, (M + 127) / 128);
 }
 static inline void gemm_fill_geom_conv(GemmGeom& g, int B, int H, int W, int C, int N, int BN) {
   g.M = B * H * W; g.N = N; g.K = C; g.BN = BN; g.a_k_off = 0;
@@ -205,12 +270,22 @@ static inline void gemm_fill_geom_conv(GemmGeom& g, int B, int H, int W, int C, 
   g.kb_per_row = (C + 63) / 64;
   g.num_kb = 9 * g.kb_per_row;
   g.stages = 4;
-  g.idesc = tc::make_idesc_f16(BN);
-  g.tmem_cols = tmem_cols_for(BN);
-  g.ring_bytes = (uint32_t)gemm_ring_bytes(BN, g.stages);
+  g.epi_warp_bytes = 0;
   g.pair_tab = nullptr; g.n_pairs = 0;
+  gemm_finish_geom(g, g.tiles_x * g.tiles_y * B);
 }
-static inline dim3 gemm_grid(const GemmGeom& g, int B) {
-  int mt = g.conv ? g.tiles_x * g.tiles_y * B : (g.M + 127) / 128;
-  return dim3((unsigned)mt, (unsigned)((g.N + g.BN - 1) / g.BN), 1);
+// Re-derive the tile counts for the actual batch / row count of a launch (plans are built for max_batch).
+static inline void gemm_set_rows(GemmGeom& g, int M, int B) {
+  g.M = M;
+  gemm_finish_geom(g, g.conv ? g.tiles_x * g.tiles_y * B : (M + 127) / 128);
+}
+// Persistent grid: as many CTAs as fit per SM by shared memory and TMEM columns, never more than tiles.
+static inline int gemm_grid(const GemmGeom& g, int n_sm, size_t smem_bytes) {
+  int per_sm = (int)(227 * 1024 / (smem_bytes + 1024));
+  const int by_tmem = 512 / (int)g.tmem_cols;
+  if (per_sm > by_tmem) per_sm = by_tmem;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  const long long want = (long long)n_sm * per_sm;
+  return (int)(g.total_tiles < want ? g.total_tiles : want);
 }

@@ -63,10 +63,10 @@ struct EpiArgmax {
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
     __shared__ u64 s_col[4][MATCH_BN];   // per-warp column maxima (no shared-memory atomics)
     __shared__ float s_hnb[MATCH_BN];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = tr.ewarp, et = warp * 32 + lane;   // et: 0..127 among epilogue threads
     const int ncols = min(g.BN, tr.n_cnt - tr.n0);  // valid columns of this tile
-    if (tid < MATCH_BN) s_hnb[tid] = tid < ncols ? __ldg(p.hnb + tr.b_off + tr.n0 + tid) : 0.f;
-    __syncthreads();
+    s_hnb[et] = et < ncols ? __ldg(p.hnb + tr.b_off + tr.n0 + et) : 0.f;
+    epi_bar_sync();
     const float my_hna = tr.valid ? __ldg(p.hna + tr.row) : 0.f;
     const int warp_row0 = tr.row_local - lane;      // problem-local row of this warp's lane 0
     float best = -INFINITY;
@@ -96,14 +96,15 @@ struct EpiArgmax {
       }
     }
     if (tr.valid && best > -INFINITY) atomicMax(p.rowbest + tr.row, pack_best(best, best_j));
-    __syncthreads();
-    if (tid < ncols) {
-      u64 m = s_col[0][tid];
-      m = m > s_col[1][tid] ? m : s_col[1][tid];
-      m = m > s_col[2][tid] ? m : s_col[2][tid];
-      m = m > s_col[3][tid] ? m : s_col[3][tid];
-      if (m != 0ull) atomicMax(p.colbest + tr.b_off + tr.n0 + tid, m);
+    epi_bar_sync();
+    if (et < ncols) {
+      u64 m = s_col[0][et];
+      m = m > s_col[1][et] ? m : s_col[1][et];
+      m = m > s_col[2][et] ? m : s_col[2][et];
+      m = m > s_col[3][et] ? m : s_col[3][et];
+      if (m != 0ull) atomicMax(p.colbest + tr.b_off + tr.n0 + et, m);
     }
+    epi_bar_sync();   // s_col / s_hnb are reused by the next tile
   }
 };
 
@@ -204,9 +205,10 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
   gemm_fill_geom(g, max_a, max_b, MATCH_K, MATCH_BN, 0);
   g.pair_tab = d_pair_tab;
   g.n_pairs = n_pairs;
-  g.stages = 2;   // 64 KB of operand ring: three CTAs per SM overlap each other's main loop and epilogue
-  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages);
-  const size_t smem = gemm_smem_bytes(g.BN, g.stages);
+  g.stages = 3;   // 96 KB ring: two persistent CTAs per SM (256 TMEM columns each)
+  g.epi_warp_bytes = 0;
+  gemm_finish_geom(g, ceil_div(max_a, 128));
+  const size_t smem = gemm_smem_bytes(g.BN, g.stages, 0);
   static bool configured = false;
   if (!configured) {
     HFB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<EpiArgmax>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -214,8 +216,7 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
     configured = true;
   }
   EpiArgmax::Params ep{hna, hnb, rowbest, colbest};
-  dim3 grid(ceil_div(max_a, 128), ceil_div(max_b, MATCH_BN), n_pairs);
-  gemm_tc_kernel<EpiArgmax><<<grid, 128, smem, ctx->stream>>>(tmA, tmB, g, ep);
+  gemm_tc_kernel<EpiArgmax><<<gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS, smem, ctx->stream>>>(tmA, tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, "match_gemm_argmax");
 
   dim3 fgrid(ceil_div(max_a, 8), n_pairs);
