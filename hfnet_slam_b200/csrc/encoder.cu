@@ -315,9 +315,19 @@ struct GemmPlan {
   CUtensorMap tmA, tmB;
   GemmGeom g;
 };
+// fused_block.cu
+struct FusedPlan;
+FusedPlan* fused_block_new();
+void fused_block_delete(FusedPlan* p);
+int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half* in, int Bmax, int Hi, int Wi, int Ho,
+                     int Wo, int pad_t, int pad_l);
+int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const __half* in, __half* out, int B);
+double fused_block_bytes(const FusedPlan& fp, int B);
+double fused_block_flops(const FusedPlan& fp, int B);
 struct BlockPlan {
   GemmPlan expand, project;
   int Hi, Wi, Ho, Wo, pad_t, pad_l;
+  FusedPlan* fused = nullptr;   // non-null: the whole block runs as one fused kernel
 };
 struct LevelExec {
   int H1, W1, pad_t1, pad_l1;
@@ -332,7 +342,12 @@ static std::vector<LevelExec>& execs(hfb_ctx* ctx) {
   static std::map<hfb_ctx*, std::vector<LevelExec>> m;
   return m[ctx];
 }
-void encoder_forget(hfb_ctx* ctx) { execs(ctx).clear(); }
+void encoder_forget(hfb_ctx* ctx) {
+  for (LevelExec& le : execs(ctx))
+    for (BlockPlan& bp : le.blocks)
+      if (bp.fused) fused_block_delete(bp.fused);
+  execs(ctx).clear();
+}
 
 static int make_plain(hfb_ctx* ctx, GemmPlan& gp, const void* A, int lda, int a_k_off, long long Mmax, const GemmW& w,
                       int n_sm, int force_bn) {
@@ -385,6 +400,11 @@ int encoder_plan(hfb_ctx* ctx) {
       if (bw.has_expand)
         HFB_TRY(make_plain(ctx, bp.expand, lv.act[bw.layer - 1], bw.cin, 0, Min, bw.expand, ctx->n_sm, 0));
       HFB_TRY(make_plain(ctx, bp.project, lv.d_dw, bw.cexp, 0, Mout, bw.project, ctx->n_sm, 0));
+      if (ctx->fused_blocks) {
+        bp.fused = fused_block_new();
+        HFB_TRY(fused_block_plan(ctx, *bp.fused, bw, lv.act[bw.layer - 1], Bm, bp.Hi, bp.Wi, bp.Ho, bp.Wo, bp.pad_t,
+                                 bp.pad_l));
+      }
       le.blocks.push_back(bp);
     }
     // local head on layer_7
@@ -455,6 +475,11 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
     const __half* dw_in = in;
     const long long Min = (long long)B * bp.Hi * bp.Wi, Mout = (long long)B * bp.Ho * bp.Wo;
     const std::string ln = "l" + std::to_string(bw.layer);
+    if (bp.fused) {
+      ctx->note(ln + ".fused", fused_block_bytes(*bp.fused, B), fused_block_flops(*bp.fused, B));
+      HFB_TRY(fused_block_run(ctx, *bp.fused, bw, in, lv.act[bw.layer], B));
+      continue;
+    }
     if (bw.has_expand) {
       ctx->note(ln + ".expand", 2.0 * Min * (bw.cin + bw.cexp) + 2.0 * bw.cin * bw.cexp, 2.0 * Min * bw.cin * bw.cexp);
       HFB_TRY(run_plain(ctx, bp.expand, Min, lv.d_exp, bw.cexp, bw.expand.b, nullptr, 0, 1));

@@ -1,0 +1,371 @@
+// One MobileNetV2 inverted-residual block (hfnet/models/backbones/utils/conv_blocks.py:162-312) as ONE kernel:
+//   1x1 expand (+bias, ReLU6)  ->  3x3 depthwise stride 1|2, TF-SAME (+bias, ReLU6)  ->  1x1 project (+bias, +residual)
+// The 6x-expanded tensor never touches HBM: per 8 x 16 output tile the CTA
+//   (0) TMA-loads the input halo tile (IH x IW pixels, OOB zero fill) as the A operand of the expand GEMM,
+//   then per 64-wide (32 for stride 2) chunk of the expanded channels
+//   (1) tcgen05.mma  halo pixels x chunk  (fp32 in TMEM), read back with tcgen05.ld, +bias, ReLU6, zeroed outside the
+//       image (SAME padding applies to the EXPANDED activation), stored fp16 in shared memory,
+//   (2) depthwise 3x3 on CUDA cores out of shared memory, written as the 128B-swizzled K-major A tile of
+//   (3) tcgen05.mma  128 output pixels x Cout, accumulated over the chunks in a second TMEM region,
+//   and finally (4) +bias (+residual) -> fp16 NHWC.
+// HBM traffic per block = input (with halo) + output, instead of 2 x (expanded + depthwise) tensors on top.
+#include "common.cuh"
+#include "tc.cuh"
+
+struct FusedGeom {
+  int B, Hi, Wi, Ho, Wo;
+  int Cin, Cexp, Cout;
+  int stride, pad_t, pad_l;
+  int has_expand, residual;
+  int tiles_x, tiles_y;
+  int IH, IW, R, MT;      // input halo tile, R = IH*IW rows, MT = ceil(R/128) expand M-tiles
+  int CW;                 // chunk of expanded channels (multiple of 16, <= 64)
+  int n_chunks;
+  int kb_in;              // 64-channel k-blocks of Cin
+  int cout_pad;           // Cout rounded up to 16
+  int e_pitch;            // bytes per row of the expanded tile in smem
+  uint32_t tmem_cols;
+  uint32_t off_X, off_A2, off_WE, off_WP, off_E, off_wd, off_bars, smem_bytes;
+};
+
+#define FB_THREADS 256
+
+__global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                 const __grid_constant__ CUtensorMap tmWE,
+                                                                 const __grid_constant__ CUtensorMap tmWP,
+                                                                 const FusedGeom g, const __half* __restrict__ in,
+                                                                 const float* __restrict__ be,   // expand bias [Cexp]
+                                                                 const float* __restrict__ wd,   // dw weights [9][Cexp]
+                                                                 const float* __restrict__ bd,   // dw bias [Cexp]
+                                                                 const float* __restrict__ bp,   // project bias [Cout]
+                                                                 __half* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem + g.off_X;      // [kb_in][MT*128 rows][128 B] swizzled (TMA)
+  uint8_t* sA2 = smem + g.off_A2;    // [128 rows][128 B] swizzled (written by the depthwise phase)
+  uint8_t* sWE = smem + g.off_WE;    // [kb_in][64 rows][128 B] swizzled (TMA)
+  uint8_t* sWP = smem + g.off_WP;    // [cout_pad rows][128 B] swizzled (TMA)
+  uint8_t* sE = smem + g.off_E;      // [R][e_pitch] expanded activations, fp16
+  float* s_wd = reinterpret_cast<float*>(smem + g.off_wd);  // [9][64] dw weights | [64] dw bias | [64] expand bias
+  float* s_bd = s_wd + 9 * 64;
+  float* s_be = s_bd + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bars);
+  uint64_t* bar_x = bars;      // input tile landed
+  uint64_t* bar_w = bars + 1;  // chunk weights landed
+  uint64_t* bar_e = bars + 2;  // expand MMAs retired
+  uint64_t* bar_p = bars + 3;  // project MMAs retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int t = blockIdx.x;
+  const int tx = t % g.tiles_x;
+  t /= g.tiles_x;
+  const int ty = t % g.tiles_y;
+  const int img = t / g.tiles_y;
+  const int oy0 = ty * 8, ox0 = tx * 16;
+  const int iy0 = oy0 * g.stride - g.pad_t, ix0 = ox0 * g.stride - g.pad_l;
+
+  if (tid == 0) {
+    tc::prefetch_tmap(&tmX);
+    tc::prefetch_tmap(&tmWE);
+    tc::prefetch_tmap(&tmWP);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, g.tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d2 = tmem_base + (uint32_t)(g.MT * g.CW);
+
+  // (0) input halo tile
+  if (tid == 0) {
+    tc::mbar_expect_tx(bar_x, (uint32_t)(g.kb_in * g.R * 128));
+    for (int kb = 0; kb < g.kb_in; ++kb)
+      tc::tma_load_4d(sX + (size_t)kb * g.MT * 128 * 128, &tmX, bar_x, kb * 64, ix0, iy0, img);
+  }
+
+  for (int j = 0; j < g.n_chunks; ++j) {
+    const int c0 = j * g.CW;                                   // first expanded channel of the chunk
+    const int cvalid = min(g.CW, g.Cexp - c0);                 // real channels in the chunk (multiple of 8)
+    const int cw16 = (cvalid + 15) & ~15;                      // K of the project step / N of the expand step
+    // chunk constants -> smem; chunk weights -> smem (TMA).  Everything of chunk j-1 has been consumed (bar_p wait).
+    if (tid == 0) {
+      uint32_t bytes = (uint32_t)(g.cout_pad * 128);
+      if (g.has_expand) bytes += (uint32_t)(g.kb_in * g.CW * 128);
+      tc::mbar_expect_tx(bar_w, bytes);
+      if (g.has_expand)
+        for (int kb = 0; kb < g.kb_in; ++kb) tc::tma_load_2d(sWE + (size_t)kb * 64 * 128, &tmWE, bar_w, kb * 64, c0);
+      tc::tma_load_2d(sWP, &tmWP, bar_w, c0, 0);
+    }
+    for (int i = tid; i < 11 * 64; i += FB_THREADS) {
+      const int row = i >> 6, c = i & 63;
+      float v = 0.f;
+      if (c < cvalid) {
+        if (row < 9) v = __ldg(wd + (size_t)row * g.Cexp + c0 + c);
+        else if (row == 9) v = __ldg(bd + c0 + c);
+        else if (g.has_expand) v = __ldg(be + c0 + c);
+      }
+      s_wd[i] = v;
+    }
+    if (j == 0) tc::mbar_wait(bar_x, 0);
+    tc::mbar_wait(bar_w, j & 1);
+    __syncthreads();
+
+    if (g.has_expand) {
+      // (1) expand: D1[mt] = X[mt] * WE^T
+      if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::make_idesc_f16(cw16);
+        for (int mt = 0; mt < g.MT; ++mt) {
+          for (int kb = 0; kb < g.kb_in; ++kb) {
+            const uint64_t da = tc::make_sdesc_sw128(tc::smem_u32(sX + ((size_t)kb * g.MT + mt) * 128 * 128));
+            const uint64_t db = tc::make_sdesc_sw128(tc::smem_u32(sWE + (size_t)kb * 64 * 128));
+            const int krem = g.Cin - kb * 64;
+            const int nk = krem >= 64 ? 4 : (krem + 15) >> 4;
+            for (int k = 0; k < nk; ++k)
+              tc::umma_f16(tmem_base + (uint32_t)(mt * g.CW), tc::sdesc_advance_k16(da, k),
+                           tc::sdesc_advance_k16(db, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        tc::umma_commit(bar_e);
+      }
+      __syncwarp();
+      tc::mbar_wait(bar_e, j & 1);
+      __syncwarp();
+      tc::fence_after_sync();
+      // TMEM -> +bias, ReLU6, zero outside the image -> fp16 rows of sE.  warp w reads lane group w%4; the two warp
+      // quads alternate over the M-tiles.
+      for (int mt = warp >> 2; mt < g.MT; mt += 2) {
+        const int r = mt * 128 + (warp & 3) * 32 + lane;
+        const int iy = iy0 + r / g.IW, ix = ix0 + r % g.IW;
+        const bool in_img = r < g.R && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * g.CW);
+        for (int cc = 0; cc < cw16; cc += 16) {
+          uint32_t v[16];
+          tc::tmem_ld16(taddr + (uint32_t)cc, v);
+          tc::tmem_ld_wait();
+          if (r < g.R) {
+            uint4 q[2];
+            __half2* hq = reinterpret_cast<__half2*>(q);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a = __uint_as_float(v[2 * i]) + s_be[cc + 2 * i];
+              float b = __uint_as_float(v[2 * i + 1]) + s_be[cc + 2 * i + 1];
+              a = in_img ? fminf(fmaxf(a, 0.f), 6.f) : 0.f;
+              b = in_img ? fminf(fmaxf(b, 0.f), 6.f) : 0.f;
+              hq[i] = __floats2half2_rn(a, b);
+            }
+            uint4* d = reinterpret_cast<uint4*>(sE + (size_t)r * g.e_pitch + (size_t)cc * 2);
+            d[0] = q[0];
+            d[1] = q[1];
+          }
+        }
+      }
+      tc::fence_before_sync();
+    } else {
+      // no expand conv (layer_2): the "expanded" activation is the input tile itself (TMA zero fill = SAME padding)
+      const int units = cw16 >> 3;
+      for (int i = tid; i < g.R * units; i += FB_THREADS) {
+        const int r = i / units, u = i - r * units;
+        const int cu = (c0 >> 3) + u;   // 16-byte unit inside the 128-byte swizzled row
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (cu * 8 < g.Cin) q = *reinterpret_cast<const uint4*>(sX + (size_t)r * 128 + (size_t)((cu ^ (r & 7)) << 4));
+        *reinterpret_cast<uint4*>(sE + (size_t)r * g.e_pitch + (size_t)u * 16) = q;
+      }
+    }
+    __syncthreads();
+
+    // (2) depthwise 3x3 (+bias, ReLU6) -> swizzled A tile of the project GEMM
+    {
+      const int units = cw16 >> 3;
+      for (int i = tid; i < 128 * units; i += FB_THREADS) {
+        const int p = i & 127, u = i >> 7;
+        const int oy = p >> 4, ox = p & 15;
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = s_bd[u * 8 + c];
+        const uint8_t* e0 = sE + (size_t)((oy * g.stride) * g.IW + ox * g.stride) * g.e_pitch + (size_t)u * 16;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint4 q = *reinterpret_cast<const uint4*>(e0 + (size_t)(ky * g.IW + kx) * g.e_pitch);
+            const __half2* hq = reinterpret_cast<const __half2*>(&q);
+            const float* w = s_wd + (ky * 3 + kx) * 64 + u * 8;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float2 f = __half22float2(hq[c]);
+              acc[2 * c] = fmaf(f.x, w[2 * c], acc[2 * c]);
+              acc[2 * c + 1] = fmaf(f.y, w[2 * c + 1], acc[2 * c + 1]);
+            }
+          }
+        }
+        uint4 o;
+        __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // channels beyond Cexp (zero weights, zero bias) come out as exact zeros
+          ho[c] = __floats2half2_rn(fminf(fmaxf(acc[2 * c], 0.f), 6.f), fminf(fmaxf(acc[2 * c + 1], 0.f), 6.f));
+        }
+        *reinterpret_cast<uint4*>(sA2 + (size_t)p * 128 + (size_t)((u ^ (p & 7)) << 4)) = o;
+      }
+    }
+    tc::fence_proxy_async();
+    __syncthreads();
+
+    // (3) project: D2 (+)= A2 * WP^T over this chunk's channels
+    if (tid == 0) {
+      tc::fence_after_sync();
+      const uint32_t idesc = tc::make_idesc_f16(g.cout_pad);
+      const uint64_t da = tc::make_sdesc_sw128(tc::smem_u32(sA2));
+      const uint64_t db = tc::make_sdesc_sw128(tc::smem_u32(sWP));
+      for (int k = 0; k < (cw16 >> 4); ++k)
+        tc::umma_f16(tmem_d2, tc::sdesc_advance_k16(da, k), tc::sdesc_advance_k16(db, k), idesc,
+                     (j > 0 || k > 0) ? 1u : 0u);
+      tc::umma_commit(bar_p);
+    }
+    __syncwarp();
+    tc::mbar_wait(bar_p, j & 1);   // A2 / WP / WE / sE may be overwritten by the next chunk
+    __syncwarp();
+  }
+  tc::fence_after_sync();
+
+  // (4) epilogue: +bias (+residual) -> fp16 NHWC.  Warp quad 0 writes the lower half of the channels, quad 1 the upper.
+  {
+    const int p = (warp & 3) * 32 + lane;
+    const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
+    const bool valid = oy < g.Ho && ox < g.Wo;
+    const long long opix = ((long long)img * g.Ho + oy) * g.Wo + ox;
+    const int half_cols = ((g.cout_pad >> 1) + 15) & ~15;
+    const int cbeg = (warp >> 2) ? half_cols : 0;
+    const int cend = (warp >> 2) ? g.cout_pad : half_cols;
+    const uint32_t taddr = tmem_d2 + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int cc = cbeg; cc < cend; cc += 16) {
+      uint32_t v[16];
+      tc::tmem_ld16(taddr + (uint32_t)cc, v);
+      tc::tmem_ld_wait();
+      if (!valid) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = cc + 8 * h;
+        if (n >= g.Cout) break;
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]) + __ldg(bp + n + i);
+        if (g.residual) {
+          const uint4 q = *reinterpret_cast<const uint4*>(in + opix * g.Cin + n);
+          const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 r2 = __half22float2(hq[i]);
+            f[2 * i] += r2.x;
+            f[2 * i + 1] += r2.y;
+          }
+        }
+        uint4 o;
+        __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        *reinterpret_cast<uint4*>(out + opix * g.Cout + n) = o;
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled_fb)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int hfb_make_tmap_2d(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                     uint64_t row_stride_bytes, uint32_t box_outer);
+int hfb_make_tmap_nhwc_box(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B, int box_w,
+                           int box_h);
+
+struct FusedPlan {
+  CUtensorMap tmX, tmWE, tmWP;
+  FusedGeom g;
+};
+
+FusedPlan* fused_block_new() { return new FusedPlan(); }
+void fused_block_delete(FusedPlan* p) { delete p; }
+
+int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half* in, int Bmax, int Hi, int Wi, int Ho,
+                     int Wo, int pad_t, int pad_l) {
+  FusedGeom& g = fp.g;
+  g.B = Bmax; g.Hi = Hi; g.Wi = Wi; g.Ho = Ho; g.Wo = Wo;
+  g.Cin = bw.cin; g.Cexp = bw.cexp; g.Cout = bw.cout;
+  g.stride = bw.stride; g.pad_t = pad_t; g.pad_l = pad_l;
+  g.has_expand = bw.has_expand ? 1 : 0;
+  g.residual = bw.residual ? 1 : 0;
+  g.tiles_x = (Wo + 15) / 16;
+  g.tiles_y = (Ho + 7) / 8;
+  g.IH = 7 * bw.stride + 3;
+  g.IW = 15 * bw.stride + 3;
+  g.R = g.IH * g.IW;
+  g.MT = (g.R + 127) / 128;
+  g.CW = bw.stride == 1 ? 64 : 32;
+  if (g.CW > ((bw.cexp + 15) & ~15)) g.CW = (bw.cexp + 15) & ~15;
+  g.n_chunks = (bw.cexp + g.CW - 1) / g.CW;
+  g.kb_in = (bw.cin + 63) / 64;
+  g.cout_pad = (bw.cout + 15) & ~15;
+  g.e_pitch = g.CW * 2 + 16;
+  uint32_t cols = 32;
+  while ((int)cols < g.MT * g.CW + g.cout_pad) cols <<= 1;
+  if (cols > 512) {
+    ctx->set_error("fused block: TMEM budget exceeded");
+    return HFB_ERR_STATE;
+  }
+  g.tmem_cols = cols;
+  auto al = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  uint32_t off = 0;
+  g.off_X = off;  off += al((uint32_t)(g.kb_in * g.MT * 128 * 128));
+  g.off_A2 = off; off += 128 * 128;
+  g.off_WE = off; off += al((uint32_t)(g.kb_in * 64 * 128));
+  g.off_WP = off; off += al((uint32_t)(g.cout_pad * 128));
+  g.off_E = off;  off += al((uint32_t)(g.R * g.e_pitch));
+  g.off_wd = off; off += al(11 * 64 * 4);
+  g.off_bars = off; off += 64;
+  g.smem_bytes = off + 1024;
+  if (g.smem_bytes > 227 * 1024) {
+    ctx->set_error("fused block: shared memory budget exceeded");
+    return HFB_ERR_STATE;
+  }
+  HFB_TRY(hfb_make_tmap_nhwc_box(ctx, &fp.tmX, in, bw.cin, Wi, Hi, Bmax, g.IW, g.IH));
+  if (bw.has_expand)
+    HFB_TRY(hfb_make_tmap_2d(ctx, &fp.tmWE, bw.expand.w, (uint64_t)bw.expand.Kp, (uint64_t)bw.expand.N,
+                             (uint64_t)bw.expand.Kp * 2, (uint32_t)g.CW));
+  else
+    fp.tmWE = fp.tmX;
+  HFB_TRY(hfb_make_tmap_2d(ctx, &fp.tmWP, bw.project.w, (uint64_t)bw.project.Kp, (uint64_t)bw.project.N,
+                           (uint64_t)bw.project.Kp * 2, (uint32_t)g.cout_pad));
+  return HFB_OK;
+}
+
+int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const __half* in, __half* out, int B) {
+  static size_t configured = 0;
+  if (fp.g.smem_bytes > configured) {
+    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)fp.g.smem_bytes));
+    configured = fp.g.smem_bytes;
+  }
+  const int grid = fp.g.tiles_x * fp.g.tiles_y * B;
+  fused_block_kernel<<<grid, FB_THREADS, fp.g.smem_bytes, ctx->stream>>>(fp.tmX, fp.tmWE, fp.tmWP, fp.g, in,
+                                                                        bw.expand.b, bw.wd, bw.bd, bw.project.b, out);
+  HFB_CHECK_LAUNCH(ctx, "fused_block");
+  return HFB_OK;
+}
+
+double fused_block_bytes(const FusedPlan& fp, int B) {   // algorithmic: input once + output once + weights
+  const FusedGeom& g = fp.g;
+  return 2.0 * B * ((double)g.Hi * g.Wi * g.Cin + (double)g.Ho * g.Wo * g.Cout * (g.residual ? 2 : 1)) +
+         2.0 * ((double)g.Cin * g.Cexp * g.has_expand + (double)g.Cexp * g.Cout) + 4.0 * 10 * g.Cexp;
+}
+double fused_block_flops(const FusedPlan& fp, int B) {
+  const FusedGeom& g = fp.g;
+  return 2.0 * B * ((double)g.Hi * g.Wi * g.Cin * g.Cexp * g.has_expand + (double)g.Ho * g.Wo * g.Cexp * (9 + g.Cout));
+}

@@ -61,15 +61,36 @@ int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, 
   return HFB_OK;
 }
 
+// fp16 NHWC tensor viewed as (C, W, H, B); box = 64 channels x box_w x box_h x 1 (input halo tile of a fused block).
+int hfb_make_tmap_nhwc_box(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B, int box_w,
+                           int box_h) {
+  PFN_encodeTiled enc = get_encode(ctx);
+  if (!enc) return HFB_ERR_CUDA;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctx->set_error("cuTensorMapEncodeTiled(4d box) failed: code " + std::to_string((int)r) + " box " +
+                   std::to_string(box_w) + "x" + std::to_string(box_h));
+    return HFB_ERR_CUDA;
+  }
+  return HFB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ epilogues
 // bias (+ReLU6) (+residual) (+L2 normalisation of the whole row) -> fp16 or fp32 rows.  Each epilogue warp owns 32 tile
 // rows; it stages 64-column slabs in its private shared-memory area and writes them out with lanes running along the
 // output row, so global stores are full, contiguous 16-byte pieces instead of one piece per thread-row.
-#define EPI_SLAB 64
+#define EPI_SLAB 32
 #define EPI_PITCH (EPI_SLAB * 4 + 16)              // bytes per staged row: odd multiple of 16 -> conflict-free
 #define EPI_WARP_BYTES (32 * EPI_PITCH)
 
 struct EpiStore {
+  static constexpr int kWarps = 8;   // two warps per TMEM lane group alternate over the 32-column slabs
   struct Params {
     void* out;
     int ldo;        // elements per output row
@@ -81,12 +102,13 @@ struct EpiStore {
     int f32;
     int l2norm;     // tf.nn.l2_normalize over the N columns (needs BN == N): descriptor head, hf_net.py:78-80
   };
+  static __device__ __forceinline__ const float* bias(const Params& p) { return p.bias; }
 
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
     const int lane = threadIdx.x & 31;
     const int esz = (p.f32 || p.residual) ? 4 : 2;   // staging element size
     uint8_t* my = tr.stage + (size_t)lane * EPI_PITCH;
-    const long long orow = tr.valid ? tr.row : -1;
+    const int orow = tr.valid ? (int)tr.row : -1;     // rows < 2^31 (B*H*W pixels)
     float inv = 1.f;
     if (p.l2norm) {
       float ss = 0.f;
@@ -96,66 +118,73 @@ struct EpiStore {
         tc::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float v = __uint_as_float(r[j]) + __ldg(p.bias + c0 + j);
+          const float v = __uint_as_float(r[j]) + tr.s_bias[c0 + j];
           ss = fmaf(v, v, ss);
         }
       }
       inv = rsqrtf(fmaxf(ss, 1e-12f));
     }
     const int ncols = min(g.BN, g.N - tr.n0);                 // valid columns of this tile (multiple of 8)
-    for (int s0 = 0; s0 < ncols; s0 += EPI_SLAB) {
-      const int scols = min(EPI_SLAB, ncols - s0);
-      for (int c0 = 0; c0 < scols; c0 += 16) {
-        uint32_t r[16];
-        tc::tmem_ld16(tr.taddr + (uint32_t)(s0 + c0), r);
-        tc::tmem_ld_wait();
-        const int n = tr.n0 + s0 + c0;
-        float v[16];
+    for (int s0 = tr.sub * EPI_SLAB; s0 < ncols; s0 += 2 * EPI_SLAB) {
+      const int scols = min(EPI_SLAB, ncols - s0);             // 8, 16, 24 or 32
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float b = (n + j < g.N && p.bias) ? __ldg(p.bias + n + j) : 0.f;
-          v[j] = (__uint_as_float(r[j]) + b) * inv;
-          if (p.relu6) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
-        }
-        if (esz == 4) {
-          float4* d = reinterpret_cast<float4*>(my + (size_t)c0 * 4);
+      for (int c0 = 0; c0 < EPI_SLAB; c0 += 16) {
+        if (c0 < scols) {
+          uint32_t r[16];
+          tc::tmem_ld16(tr.taddr + (uint32_t)(s0 + c0), r);
+          tc::tmem_ld_wait();
+          const int n = tr.n0 + s0 + c0;
+          float v[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-          uint4* d = reinterpret_cast<uint4*>(my + (size_t)c0 * 2);
+          for (int j = 0; j < 16; ++j) {
+            const float b = (tr.s_bias && n + j < g.N) ? tr.s_bias[n + j] : 0.f;
+            v[j] = (__uint_as_float(r[j]) + b) * inv;
+            if (p.relu6) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
+          }
+          if (esz == 4) {
+            float4* d = reinterpret_cast<float4*>(my + (size_t)c0 * 4);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint4 q;
-            __half2* hq = reinterpret_cast<__half2*>(&q);
+            for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+            uint4* d = reinterpret_cast<uint4*>(my + (size_t)c0 * 2);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
-            d[h] = q;
+            for (int h = 0; h < 2; ++h) {
+              uint4 q;
+              __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) hq[j] = __floats2half2_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
+              d[h] = q;
+            }
           }
         }
       }
       __syncwarp();
-      const int cpr = scols * esz / 16;                        // 16-byte chunks per staged row
-      const int total = 32 * cpr;                              // multiple of 32: every lane iterates equally
-      for (int id = lane; id < total; id += 32) {
-        const int row = id / cpr, ch = id - row * cpr;
-        const long long dst_row = __shfl_sync(0xffffffffu, orow, row);
-        if (dst_row < 0) continue;
+      // write-out: lanes run along the row.  cpr 16-byte chunks per row, padded to a power of two so that row / chunk
+      // come from shifts (tail slabs leave a few lanes idle)
+      const int cpr = scols * esz >> 4;                        // 1 .. 8
+      const int sh = cpr > 4 ? 3 : (cpr > 2 ? 2 : (cpr > 1 ? 1 : 0));
+      const int ch = lane & ((1 << sh) - 1);
+      const int rstep = 32 >> sh;
+      const long long col = (long long)p.col_off + tr.n0 + s0;
+      for (int row = lane >> sh; row < 32; row += rstep) {
+        const int dst_row = __shfl_sync(0xffffffffu, orow, row);
+        if (dst_row < 0 || ch >= cpr) continue;
         const uint4 q = *reinterpret_cast<const uint4*>(tr.stage + (size_t)row * EPI_PITCH + (size_t)ch * 16);
-        const long long col = (long long)p.col_off + tr.n0 + s0;
         if (esz == 2) {
-          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + dst_row * p.ldo + col + ch * 8) = q;
+          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + (long long)dst_row * p.ldo + col + ch * 8) = q;
         } else if (p.f32) {
-          *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + dst_row * p.ldo + col + ch * 4) = q;
+          *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + (long long)dst_row * p.ldo + col + ch * 4) = q;
         } else {  // fp32 staging + fp16 residual -> fp16 (single rounding)
           const float* f = reinterpret_cast<const float*>(&q);
-          const uint2 rr = *reinterpret_cast<const uint2*>(p.residual + dst_row * p.ldr + tr.n0 + s0 + ch * 4);
+          const uint2 rr =
+              *reinterpret_cast<const uint2*>(p.residual + (long long)dst_row * p.ldr + tr.n0 + s0 + ch * 4);
           const __half2* hr = reinterpret_cast<const __half2*>(&rr);
           const float2 r0 = __half22float2(hr[0]), r1 = __half22float2(hr[1]);
           uint2 o;
           __half2* ho = reinterpret_cast<__half2*>(&o);
           ho[0] = __floats2half2_rn(f[0] + r0.x, f[1] + r0.y);
           ho[1] = __floats2half2_rn(f[2] + r1.x, f[3] + r1.y);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + dst_row * p.ldo + col + ch * 4) = o;
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + (long long)dst_row * p.ldo + col + ch * 4) = o;
         }
       }
       __syncwarp();
@@ -166,12 +195,14 @@ struct EpiStore {
 // Detector head tail (hfnet/models/hf_net.py:88-93): + bias, softmax over 65 logits, drop the dustbin channel,
 // depth_to_space(8): scores[8h+i][8w+j] = prob[h][w][8i+j].  Optionally keeps the raw logits (parity hook).
 struct EpiSoftmaxD2S {
+  static constexpr int kWarps = 4;
   struct Params {
     float* scores;   // [B][Hc*8][Wc*8]
     float* logits;   // [row][65] or null
     const float* bias;
     int Hc, Wc;
   };
+  static __device__ __forceinline__ const float* bias(const Params&) { return nullptr; }
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
     float v[80];
 #pragma unroll
@@ -220,16 +251,18 @@ struct EpiSoftmaxD2S {
 // ------------------------------------------------------------------------------------------------ launchers
 template <class Epi>
 static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g_in, int B,
-                     const typename Epi::Params& ep, const char* what, uint32_t epi_warp_bytes) {
+                     const typename Epi::Params& ep, const char* what, uint32_t epi_warp_bytes, bool stage_bias) {
   GemmGeom g = g_in;
   gemm_set_rows(g, g.M, B);
   g.epi_warp_bytes = epi_warp_bytes;
+  g.bias_bytes = stage_bias ? (uint32_t)((g.N * 4 + 15) & ~15) : 0u;
+  const size_t epi_bytes = (size_t)Epi::kWarps * epi_warp_bytes + g.bias_bytes;
   // ring depth: keep the CTA near 110 KB so that two persistent CTAs (8 epilogue warps) share an SM when TMEM allows
   const size_t stage = GEMM_TILE_A_BYTES + (size_t)g.BN * 128;
-  int st = (int)((110 * 1024 - 4 * (size_t)epi_warp_bytes) / stage);
+  int st = (int)((110 * 1024 - epi_bytes) / stage);
   g.stages = st < 2 ? 2 : (st > 4 ? 4 : st);
   g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages);
-  const size_t smem = gemm_smem_bytes(g.BN, g.stages, epi_warp_bytes);
+  const size_t smem = gemm_smem_bytes(g.BN, g.stages, epi_bytes);
   static size_t configured = 0;  // per-instantiation
   if (smem > configured) {
     HFB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -237,7 +270,7 @@ static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
   }
   if (g.total_tiles <= 0) return HFB_OK;
   const int grid = gemm_grid(g, ctx->n_sm, smem);
-  gemm_tc_kernel<Epi><<<grid, GEMM_THREADS, smem, ctx->stream>>>(tmA, tmB, g, ep);
+  gemm_tc_kernel<Epi><<<grid, GEMM_THREADS(Epi::kWarps), smem, ctx->stream>>>(tmA, tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, what);
   return HFB_OK;
 }
@@ -245,7 +278,7 @@ static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
 int gemm_store(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, int B, void* out,
                int ldo, int col_off, const float* bias, const __half* residual, int ldr, int relu6, int f32) {
   EpiStore::Params p{out, ldo, col_off, bias, residual, ldr, relu6, f32, 0};
-  return launch_tc<EpiStore>(ctx, tmA, tmB, g, B, p, "gemm_store", EPI_WARP_BYTES);
+  return launch_tc<EpiStore>(ctx, tmA, tmB, g, B, p, "gemm_store", EPI_WARP_BYTES, bias != nullptr);
 }
 int gemm_l2norm(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* out,
                 const float* bias) {
@@ -254,7 +287,7 @@ int gemm_l2norm(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, co
     return HFB_ERR_INVALID;
   }
   EpiStore::Params p{out, g.N, 0, bias, nullptr, 0, 0, 1, 1};
-  return launch_tc<EpiStore>(ctx, tmA, tmB, g, 1, p, "gemm_l2norm", EPI_WARP_BYTES);
+  return launch_tc<EpiStore>(ctx, tmA, tmB, g, 1, p, "gemm_l2norm", EPI_WARP_BYTES, true);
 }
 int gemm_softmax_d2s(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* scores,
                      float* logits, const float* bias, int Hc, int Wc) {
@@ -263,7 +296,7 @@ int gemm_softmax_d2s(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
     return HFB_ERR_INVALID;
   }
   EpiSoftmaxD2S::Params p{scores, logits, bias, Hc, Wc};
-  return launch_tc<EpiSoftmaxD2S>(ctx, tmA, tmB, g, 1, p, "gemm_softmax_d2s", 0);
+  return launch_tc<EpiSoftmaxD2S>(ctx, tmA, tmB, g, 1, p, "gemm_softmax_d2s", 0, false);
 }
 
 // ------------------------------------------------------------------------------------------------ debug / parity

@@ -30,6 +30,7 @@ struct GemmGeom {
   uint32_t tmem_cols;   // power of two >= max(32, 2*BN)
   uint32_t ring_bytes;  // operand ring size (multiple of 1024)
   uint32_t epi_warp_bytes;  // per-epilogue-warp staging bytes behind the ring
+  uint32_t bias_bytes;      // staged bias vector behind the warp staging areas (0 = none), multiple of 16
   // Batched independent problems (descriptor matching): pair_tab = device int[4][n_pairs] holding
   // a_off | a_cnt | b_off | b_cnt (row ranges inside A's and W's maps).  null = one problem of M x N.
   const int* pair_tab;
@@ -45,11 +46,13 @@ struct TileRow {
   int n_cnt;          // columns of the problem (== N when not batched)
   int a_off, b_off;   // batched: first global row of the pair's A / B block
   uint8_t* stage;     // this warp's private staging area (epi_warp_bytes)
-  int ewarp;          // epilogue warp index 0..3 (== TMEM lane group)
+  int ewarp;          // TMEM lane group 0..3 of this warp
+  int sub;            // 0 .. kWarps/4-1: which of the warps sharing the lane group (they split the columns)
+  const float* s_bias;  // bias vector staged in shared memory (indexed by problem column), or null
 };
 
 #define GEMM_TILE_A_BYTES 16384  // 128 rows x 128 B
-#define GEMM_THREADS 192
+#define GEMM_THREADS(EW) (64 + 32 * (EW))
 #define GEMM_EPI_BAR 1           // named barrier of the 128 epilogue threads
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(GEMM_EPI_BAR), "n"(128) : "memory"); }
@@ -94,19 +97,20 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int tile) {
 static inline size_t gemm_ring_bytes(int BN, int stages) {
   return (size_t)stages * (GEMM_TILE_A_BYTES + (size_t)BN * 128);
 }
-static inline size_t gemm_smem_bytes(int BN, int stages, size_t epi_warp_bytes) {
-  return 1024 + gemm_ring_bytes(BN, stages) + 4 * epi_warp_bytes + 256;
+static inline size_t gemm_smem_bytes(int BN, int stages, size_t epi_bytes) {
+  return 1024 + gemm_ring_bytes(BN, stages) + epi_bytes + 256;
 }
 
 template <class Epi>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(GEMM_THREADS(Epi::kWarps)) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const GemmGeom g, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = GEMM_TILE_A_BYTES + (uint32_t)g.BN * 128u;
   uint8_t* epi_smem = smem + g.ring_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + 4 * (size_t)g.epi_warp_bytes);
+  float* s_bias = reinterpret_cast<float*>(epi_smem + (size_t)Epi::kWarps * g.epi_warp_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_bias) + g.bias_bytes);
   uint64_t* full = bars;            // [8]
   uint64_t* empty = bars + 8;       // [8]
   uint64_t* acc_full = bars + 16;   // [2]
@@ -124,11 +128,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&acc_full[s], 1);
-      tc::mbar_init(&acc_empty[s], 4);   // one arrival per epilogue warp
+      tc::mbar_init(&acc_empty[s], Epi::kWarps);   // one arrival per epilogue warp
     }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, g.tmem_cols);
+  if (g.bias_bytes) {
+    const float* gb = Epi::bias(ep);
+    for (int i = tid; i < g.N; i += blockDim.x) s_bias[i] = __ldg(gb + i);
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -192,8 +200,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (2..5)
+    // ------------------------------------------------------------------ epilogue warps (2 ..)
     const int ewarp = warp & 3;   // TMEM lane group this warp may access
+    const int eidx = warp - 2;    // 0 .. kWarps-1
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(g, tile);
@@ -219,8 +228,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
       tr.n_cnt = t.b_cnt;
       tr.a_off = t.a_off;
       tr.b_off = t.b_off;
-      tr.stage = epi_smem + (size_t)ewarp * g.epi_warp_bytes;
+      tr.stage = epi_smem + (size_t)eidx * g.epi_warp_bytes;
       tr.ewarp = ewarp;
+      tr.sub = eidx >> 2;
+      tr.s_bias = g.bias_bytes ? s_bias : nullptr;
       Epi::run(ep, g, tr);
       tc::fence_before_sync();
       __syncwarp();
@@ -261,6 +272,7 @@ static inline void gemm_fill_geom(GemmGeom& g, int M, int N, int K, int BN, int 
   g.num_kb = g.kb_per_row;
   g.stages = 4;
   g.epi_warp_bytes = 0;
+  g.bias_bytes = 0;
   g.pair_tab = nullptr; g.n_pairs = 0;
   gemm_finish_geom(g, (M + 127) / 128);
 }
@@ -271,6 +283,7 @@ static inline void gemm_fill_geom_conv(GemmGeom& g, int B, int H, int W, int C, 
   g.num_kb = 9 * g.kb_per_row;
   g.stages = 4;
   g.epi_warp_bytes = 0;
+  g.bias_bytes = 0;
   g.pair_tab = nullptr; g.n_pairs = 0;
   gemm_finish_geom(g, g.tiles_x * g.tiles_y * B);
 }

@@ -54,12 +54,14 @@ __device__ __forceinline__ u64 pack_best(float key, int idx) {
 
 // ---- epilogue: per-row and per-column arg-max of key = s - 0.5*|other|^2 (L2 mode) or s (cosine mode) ------------
 struct EpiArgmax {
+  static constexpr int kWarps = 4;
   struct Params {
     const float* hna;  // [na_total] 0.5*|a|^2 (0 in cosine mode)
     const float* hnb;  // [nb_total]
     u64* rowbest;      // [na_total], zero-initialised
     u64* colbest;      // [nb_total], zero-initialised
   };
+  static __device__ __forceinline__ const float* bias(const Params&) { return nullptr; }
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
     __shared__ u64 s_col[4][MATCH_BN];   // per-warp column maxima (no shared-memory atomics)
     __shared__ float s_hnb[MATCH_BN];
@@ -207,6 +209,7 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
   g.n_pairs = n_pairs;
   g.stages = 3;   // 96 KB ring: two persistent CTAs per SM (256 TMEM columns each)
   g.epi_warp_bytes = 0;
+  g.bias_bytes = 0;
   gemm_finish_geom(g, ceil_div(max_a, 128));
   const size_t smem = gemm_smem_bytes(g.BN, g.stages, 0);
   static bool configured = false;
@@ -216,7 +219,7 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
     configured = true;
   }
   EpiArgmax::Params ep{hna, hnb, rowbest, colbest};
-  gemm_tc_kernel<EpiArgmax><<<gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS, smem, ctx->stream>>>(tmA, tmB, g, ep);
+  gemm_tc_kernel<EpiArgmax><<<gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(4), smem, ctx->stream>>>(tmA, tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, "match_gemm_argmax");
 
   dim3 fgrid(ceil_div(max_a, 8), n_pairs);
