@@ -402,8 +402,14 @@ int encoder_plan(hfb_ctx* ctx) {
       HFB_TRY(make_plain(ctx, bp.project, lv.d_dw, bw.cexp, 0, Mout, bw.project, ctx->n_sm, 0));
       if (ctx->fused_blocks) {
         bp.fused = fused_block_new();
-        HFB_TRY(fused_block_plan(ctx, *bp.fused, bw, lv.act[bw.layer - 1], Bm, bp.Hi, bp.Wi, bp.Ho, bp.Wo, bp.pad_t,
-                                 bp.pad_l));
+        const int rc = fused_block_plan(ctx, *bp.fused, bw, lv.act[bw.layer - 1], Bm, bp.Hi, bp.Wi, bp.Ho, bp.Wo,
+                                        bp.pad_t, bp.pad_l);
+        if (rc == HFB_ERR_CAPACITY) {   // does not fit on chip: this block keeps the three-kernel path
+          fused_block_delete(bp.fused);
+          bp.fused = nullptr;
+        } else if (rc != HFB_OK) {
+          return rc;
+        }
       }
       le.blocks.push_back(bp);
     }

@@ -18,6 +18,7 @@ struct FusedGeom {
   int stride, pad_t, pad_l;
   int has_expand, residual;
   int tiles_x, tiles_y;
+  int TH;                 // output tile = TH x 16 pixels (8, or 4 when the halo tile would not fit in shared memory)
   int IH, IW, R, MT;      // input halo tile, R = IH*IW rows, MT = ceil(R/128) expand M-tiles
   int CW;                 // chunk of expanded channels (multiple of 16, <= 64)
   int n_chunks;
@@ -30,8 +31,7 @@ struct FusedGeom {
 
 #define FB_THREADS 256
 
-__global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                                 const __grid_constant__ CUtensorMap tmWE,
+__global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_constant__ CUtensorMap tmWE,
                                                                  const __grid_constant__ CUtensorMap tmWP,
                                                                  const FusedGeom g, const __half* __restrict__ in,
                                                                  const float* __restrict__ be,   // expand bias [Cexp]
@@ -50,7 +50,6 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
   float* s_bd = s_wd + 9 * 64;
   float* s_be = s_bd + 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bars);
-  uint64_t* bar_x = bars;      // input tile landed
   uint64_t* bar_w = bars + 1;  // chunk weights landed
   uint64_t* bar_e = bars + 2;  // expand MMAs retired
   uint64_t* bar_p = bars + 3;  // project MMAs retired
@@ -62,11 +61,10 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
   t /= g.tiles_x;
   const int ty = t % g.tiles_y;
   const int img = t / g.tiles_y;
-  const int oy0 = ty * 8, ox0 = tx * 16;
+  const int oy0 = ty * g.TH, ox0 = tx * 16;
   const int iy0 = oy0 * g.stride - g.pad_t, ix0 = ox0 * g.stride - g.pad_l;
 
   if (tid == 0) {
-    tc::prefetch_tmap(&tmX);
     tc::prefetch_tmap(&tmWE);
     tc::prefetch_tmap(&tmWP);
     for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
@@ -79,11 +77,22 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base + (uint32_t)(g.MT * g.CW);
 
-  // (0) input halo tile
-  if (tid == 0) {
-    tc::mbar_expect_tx(bar_x, (uint32_t)(g.kb_in * g.R * 128));
-    for (int kb = 0; kb < g.kb_in; ++kb)
-      tc::tma_load_4d(sX + (size_t)kb * g.MT * 128 * 128, &tmX, bar_x, kb * 64, ix0, iy0, img);
+  // (0) input halo tile -> K-major 128B-swizzled rows (one row per halo pixel, 64 channels per k-block), zero outside
+  // the image and in the K padding up to the next multiple of 16 channels.  Plain 16-byte loads: pixels are only
+  // Cin*2 = 32..240 bytes, far below TMA's efficient row size.
+  {
+    const int units = ((g.Cin + 15) & ~15) >> 3;   // 16-byte units per pixel incl. K padding
+    const __half* src = in + (size_t)img * g.Hi * g.Wi * g.Cin;
+    for (int i = tid; i < g.R * units; i += FB_THREADS) {
+      const int r = i / units, u = i - r * units;
+      const int iy = iy0 + r / g.IW, ix = ix0 + r % g.IW;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (u * 8 < g.Cin && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
+        q = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)iy * g.Wi + ix) * g.Cin + u * 8));
+      const int kb = u >> 3, uu = u & 7;
+      *reinterpret_cast<uint4*>(sX + ((size_t)kb * g.MT * 128 + r) * 128 + (size_t)((uu ^ (r & 7)) << 4)) = q;
+    }
+    tc::fence_proxy_async();
   }
 
   for (int j = 0; j < g.n_chunks; ++j) {
@@ -109,7 +118,6 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
       }
       s_wd[i] = v;
     }
-    if (j == 0) tc::mbar_wait(bar_x, 0);
     tc::mbar_wait(bar_w, j & 1);
     __syncthreads();
 
@@ -183,6 +191,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
       for (int i = tid; i < 128 * units; i += FB_THREADS) {
         const int p = i & 127, u = i >> 7;
         const int oy = p >> 4, ox = p & 15;
+        if (oy >= g.TH) continue;   // rows of a 4 x 16 tile's unused half: their accumulator rows are never read
         float acc[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = s_bd[u * 8 + c];
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
   {
     const int p = (warp & 3) * 32 + lane;
     const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
-    const bool valid = oy < g.Ho && ox < g.Wo;
+    const bool valid = (p >> 4) < g.TH && oy < g.Ho && ox < g.Wo;
     const long long opix = ((long long)img * g.Ho + oy) * g.Wo + ox;
     const int half_cols = ((g.cout_pad >> 1) + 15) & ~15;
     const int cbeg = (warp >> 2) ? half_cols : 0;
@@ -287,7 +296,7 @@ int hfb_make_tmap_nhwc_box(hfb_ctx* ctx, CUtensorMap* out, const void* base, int
                            int box_h);
 
 struct FusedPlan {
-  CUtensorMap tmX, tmWE, tmWP;
+  CUtensorMap tmWE, tmWP;
   FusedGeom g;
 };
 
@@ -303,46 +312,41 @@ int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half
   g.has_expand = bw.has_expand ? 1 : 0;
   g.residual = bw.residual ? 1 : 0;
   g.tiles_x = (Wo + 15) / 16;
-  g.tiles_y = (Ho + 7) / 8;
-  g.IH = 7 * bw.stride + 3;
-  g.IW = 15 * bw.stride + 3;
-  g.R = g.IH * g.IW;
-  g.MT = (g.R + 127) / 128;
   g.CW = bw.stride == 1 ? 64 : 32;
   if (g.CW > ((bw.cexp + 15) & ~15)) g.CW = (bw.cexp + 15) & ~15;
   g.n_chunks = (bw.cexp + g.CW - 1) / g.CW;
   g.kb_in = (bw.cin + 63) / 64;
   g.cout_pad = (bw.cout + 15) & ~15;
   g.e_pitch = g.CW * 2 + 16;
+  auto al = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  for (g.TH = 8; g.TH >= 4; g.TH >>= 1) {
+    g.tiles_y = (Ho + g.TH - 1) / g.TH;
+    g.IH = (g.TH - 1) * bw.stride + 3;
+    g.IW = 15 * bw.stride + 3;
+    g.R = g.IH * g.IW;
+    g.MT = (g.R + 127) / 128;
+    uint32_t off = 0;
+    g.off_X = off;  off += al((uint32_t)(g.kb_in * g.MT * 128 * 128));
+    g.off_A2 = off; off += 128 * 128;
+    g.off_WE = off; off += al((uint32_t)(g.kb_in * 64 * 128));
+    g.off_WP = off; off += al((uint32_t)(g.cout_pad * 128));
+    g.off_E = off;  off += al((uint32_t)(g.R * g.e_pitch));
+    g.off_wd = off; off += al(11 * 64 * 4);
+    g.off_bars = off; off += 64;
+    g.smem_bytes = off + 1024;
+    if (g.smem_bytes <= 200 * 1024) break;
+  }
   uint32_t cols = 32;
   while ((int)cols < g.MT * g.CW + g.cout_pad) cols <<= 1;
-  if (cols > 512) {
-    ctx->set_error("fused block: TMEM budget exceeded");
-    return HFB_ERR_STATE;
-  }
+  if (g.TH < 4 || g.smem_bytes > 200 * 1024 || cols > 512) return HFB_ERR_CAPACITY;   // caller keeps the unfused path
   g.tmem_cols = cols;
-  auto al = [](uint32_t v) { return (v + 1023u) & ~1023u; };
-  uint32_t off = 0;
-  g.off_X = off;  off += al((uint32_t)(g.kb_in * g.MT * 128 * 128));
-  g.off_A2 = off; off += 128 * 128;
-  g.off_WE = off; off += al((uint32_t)(g.kb_in * 64 * 128));
-  g.off_WP = off; off += al((uint32_t)(g.cout_pad * 128));
-  g.off_E = off;  off += al((uint32_t)(g.R * g.e_pitch));
-  g.off_wd = off; off += al(11 * 64 * 4);
-  g.off_bars = off; off += 64;
-  g.smem_bytes = off + 1024;
-  if (g.smem_bytes > 227 * 1024) {
-    ctx->set_error("fused block: shared memory budget exceeded");
-    return HFB_ERR_STATE;
-  }
-  HFB_TRY(hfb_make_tmap_nhwc_box(ctx, &fp.tmX, in, bw.cin, Wi, Hi, Bmax, g.IW, g.IH));
+  (void)in;
   if (bw.has_expand)
     HFB_TRY(hfb_make_tmap_2d(ctx, &fp.tmWE, bw.expand.w, (uint64_t)bw.expand.Kp, (uint64_t)bw.expand.N,
                              (uint64_t)bw.expand.Kp * 2, (uint32_t)g.CW));
-  else
-    fp.tmWE = fp.tmX;
   HFB_TRY(hfb_make_tmap_2d(ctx, &fp.tmWP, bw.project.w, (uint64_t)bw.project.Kp, (uint64_t)bw.project.N,
                            (uint64_t)bw.project.Kp * 2, (uint32_t)g.cout_pad));
+  if (!bw.has_expand) fp.tmWE = fp.tmWP;   // never dereferenced by the kernel
   return HFB_OK;
 }
 
@@ -354,7 +358,7 @@ int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const _
     configured = fp.g.smem_bytes;
   }
   const int grid = fp.g.tiles_x * fp.g.tiles_y * B;
-  fused_block_kernel<<<grid, FB_THREADS, fp.g.smem_bytes, ctx->stream>>>(fp.tmX, fp.tmWE, fp.tmWP, fp.g, in,
+  fused_block_kernel<<<grid, FB_THREADS, fp.g.smem_bytes, ctx->stream>>>(fp.tmWE, fp.tmWP, fp.g, in,
                                                                         bw.expand.b, bw.wd, bw.bd, bw.project.b, out);
   HFB_CHECK_LAUNCH(ctx, "fused_block");
   return HFB_OK;
