@@ -136,7 +136,7 @@ struct hfb_ctx {
   size_t d_scratch_bytes = 0;
   void* d_io = nullptr;        // persistent device staging of the host-pointer matcher entry points
   size_t d_io_bytes = 0;
-  bool fused_blocks = false;   // HFB_FUSED=1: inverted-residual blocks run as one fused kernel each
+  bool fused_blocks = true;    // HFB_FUSED=0: inverted-residual blocks run as three kernels (expand, dw, project)
   bool trace = false;          // HFB_TRACE=1: host-side stage timings of the host-pointer calls on stderr
   std::vector<void*> allocs;
   bool use_graph = true;

@@ -96,7 +96,7 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   const char* dbg = getenv("HFB_DEBUG");
   ctx->debug = dbg && dbg[0] == '1';
   const char* fu = getenv("HFB_FUSED");
-  ctx->fused_blocks = fu && fu[0] == '1';
+  ctx->fused_blocks = !(fu && fu[0] == '0');   // default on; HFB_FUSED=0 keeps the three-kernel blocks
   const char* tr = getenv("HFB_TRACE");
   ctx->trace = tr && tr[0] == '1';
   const char* ng = getenv("HFB_NO_GRAPH");

@@ -322,6 +322,7 @@ void fused_block_delete(FusedPlan* p);
 int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half* in, int Bmax, int Hi, int Wi, int Ho,
                      int Wo, int pad_t, int pad_l);
 int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const __half* in, __half* out, int B);
+int fused_block_tiles(const FusedPlan& fp, int B);
 double fused_block_bytes(const FusedPlan& fp, int B);
 double fused_block_flops(const FusedPlan& fp, int B);
 struct BlockPlan {
@@ -481,7 +482,9 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
     const __half* dw_in = in;
     const long long Min = (long long)B * bp.Hi * bp.Wi, Mout = (long long)B * bp.Ho * bp.Wo;
     const std::string ln = "l" + std::to_string(bw.layer);
-    if (bp.fused) {
+    // one fused kernel per block when there are enough tiles to fill the machine; tiny late layers (15 x 24 pixels)
+    // run faster as three small launches
+    if (bp.fused && fused_block_tiles(*bp.fused, B) >= ctx->n_sm) {
       ctx->note(ln + ".fused", fused_block_bytes(*bp.fused, B), fused_block_flops(*bp.fused, B));
       HFB_TRY(fused_block_run(ctx, *bp.fused, bw, in, lv.act[bw.layer], B));
       continue;

@@ -1,14 +1,19 @@
 // One MobileNetV2 inverted-residual block (hfnet/models/backbones/utils/conv_blocks.py:162-312) as ONE kernel:
 //   1x1 expand (+bias, ReLU6)  ->  3x3 depthwise stride 1|2, TF-SAME (+bias, ReLU6)  ->  1x1 project (+bias, +residual)
-// The 6x-expanded tensor never touches HBM: per 8 x 16 output tile the CTA
-//   (0) TMA-loads the input halo tile (IH x IW pixels, OOB zero fill) as the A operand of the expand GEMM,
+// The 6x-expanded tensor never touches HBM.  Persistent CTAs keep ALL weights of the block resident in shared memory
+// (one TMA burst at start) and walk TH x 16 output tiles; per tile
+//   (0) the input halo tile (IH x IW pixels, zero outside the image) is loaded with plain 16-byte loads into K-major
+//       128B-swizzled rows: the A operand of the expand GEMM (pixels are only 32..240 bytes, too small for TMA rows),
 //   then per 64-wide (32 for stride 2) chunk of the expanded channels
 //   (1) tcgen05.mma  halo pixels x chunk  (fp32 in TMEM), read back with tcgen05.ld, +bias, ReLU6, zeroed outside the
 //       image (SAME padding applies to the EXPANDED activation), stored fp16 in shared memory,
 //   (2) depthwise 3x3 on CUDA cores out of shared memory, written as the 128B-swizzled K-major A tile of
 //   (3) tcgen05.mma  128 output pixels x Cout, accumulated over the chunks in a second TMEM region,
 //   and finally (4) +bias (+residual) -> fp16 NHWC.
-// HBM traffic per block = input (with halo) + output, instead of 2 x (expanded + depthwise) tensors on top.
+// The MMAs are software-pipelined against the CUDA-core phases: expand(j+1) runs under depthwise(j), project(j) under
+// the TMEM read-back of chunk j+1.  HBM traffic per block = input (with halo) + output.
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -17,15 +22,17 @@ struct FusedGeom {
   int Cin, Cexp, Cout;
   int stride, pad_t, pad_l;
   int has_expand, residual;
-  int tiles_x, tiles_y;
-  int TH;                 // output tile = TH x 16 pixels (8, or 4 when the halo tile would not fit in shared memory)
+  int tiles_x, tiles_y, total_tiles;
+  int TH;                 // output tile = TH x 16 pixels
   int IH, IW, R, MT;      // input halo tile, R = IH*IW rows, MT = ceil(R/128) expand M-tiles
   int CW;                 // chunk of expanded channels (multiple of 16, <= 64)
   int n_chunks;
+  int cexp_pad;           // n_chunks * CW
   int kb_in;              // 64-channel k-blocks of Cin
   int cout_pad;           // Cout rounded up to 16
   int e_pitch;            // bytes per row of the expanded tile in smem
   uint32_t tmem_cols;
+  uint32_t we_chunk_bytes, wp_chunk_bytes, w_total_bytes;
   uint32_t off_X, off_A2, off_WE, off_WP, off_E, off_wd, off_bars, smem_bytes;
 };
 
@@ -41,244 +48,271 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
                                                                  __half* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sX = smem + g.off_X;      // [kb_in][MT*128 rows][128 B] swizzled (TMA)
+  uint8_t* sX = smem + g.off_X;      // [kb_in][MT*128 rows][128 B] swizzled
   uint8_t* sA2 = smem + g.off_A2;    // [128 rows][128 B] swizzled (written by the depthwise phase)
-  uint8_t* sWE = smem + g.off_WE;    // [kb_in][64 rows][128 B] swizzled (TMA)
-  uint8_t* sWP = smem + g.off_WP;    // [cout_pad rows][128 B] swizzled (TMA)
-  uint8_t* sE = smem + g.off_E;      // [R][e_pitch] expanded activations, fp16
-  float* s_wd = reinterpret_cast<float*>(smem + g.off_wd);  // [9][64] dw weights | [64] dw bias | [64] expand bias
-  float* s_bd = s_wd + 9 * 64;
-  float* s_be = s_bd + 64;
+  uint8_t* sWE = smem + g.off_WE;    // [n_chunks][kb_in][CW rows][128 B] swizzled (TMA, resident)
+  uint8_t* sWP = smem + g.off_WP;    // [n_chunks][cout_pad rows][128 B] swizzled (TMA, resident)
+  uint8_t* sE = smem + g.off_E;      // [R][e_pitch] expanded activations of the current chunk, fp16
+  float* s_wd = reinterpret_cast<float*>(smem + g.off_wd);  // [9][cexp_pad] dw weights | [cexp_pad] dw bias | expand bias
+  float* s_bd = s_wd + 9 * g.cexp_pad;
+  float* s_be = s_bd + g.cexp_pad;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bars);
-  uint64_t* bar_w = bars + 1;  // chunk weights landed
-  uint64_t* bar_e = bars + 2;  // expand MMAs retired
-  uint64_t* bar_p = bars + 3;  // project MMAs retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bar_w = bars;      // all weights landed (once)
+  uint64_t* bar_e = bars + 1;  // [2] expand MMAs retired (alternating)
+  uint64_t* bar_p = bars + 3;  // [2] project MMAs retired (alternating)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int t = blockIdx.x;
-  const int tx = t % g.tiles_x;
-  t /= g.tiles_x;
-  const int ty = t % g.tiles_y;
-  const int img = t / g.tiles_y;
-  const int oy0 = ty * g.TH, ox0 = tx * 16;
-  const int iy0 = oy0 * g.stride - g.pad_t, ix0 = ox0 * g.stride - g.pad_l;
 
   if (tid == 0) {
     tc::prefetch_tmap(&tmWE);
     tc::prefetch_tmap(&tmWP);
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5; ++i) tc::mbar_init(&bars[i], 1);
     tc::fence_barrier_init();
+    // resident weights: one burst
+    tc::mbar_expect_tx(bar_w, g.w_total_bytes);
+    for (int j = 0; j < g.n_chunks; ++j) {
+      if (g.has_expand)
+        for (int kb = 0; kb < g.kb_in; ++kb)
+          tc::tma_load_2d(sWE + (size_t)j * g.we_chunk_bytes + (size_t)kb * g.CW * 128, &tmWE, bar_w, kb * 64, j * g.CW);
+      tc::tma_load_2d(sWP + (size_t)j * g.wp_chunk_bytes, &tmWP, bar_w, j * g.CW, 0);
+    }
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, g.tmem_cols);
+  for (int i = tid; i < 11 * g.cexp_pad; i += FB_THREADS) {
+    const int row = i / g.cexp_pad, c = i - row * g.cexp_pad;
+    float v = 0.f;
+    if (c < g.Cexp) {
+      if (row < 9) v = __ldg(wd + (size_t)row * g.Cexp + c);
+      else if (row == 9) v = __ldg(bd + c);
+      else if (g.has_expand) v = __ldg(be + c);
+    }
+    s_wd[i] = v;
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base + (uint32_t)(g.MT * g.CW);
+  const uint32_t idesc_p = tc::make_idesc_f16(g.cout_pad);
 
-  // (0) input halo tile -> K-major 128B-swizzled rows (one row per halo pixel, 64 channels per k-block), zero outside
-  // the image and in the K padding up to the next multiple of 16 channels.  Plain 16-byte loads: pixels are only
-  // Cin*2 = 32..240 bytes, far below TMA's efficient row size.
-  {
-    const int units = ((g.Cin + 15) & ~15) >> 3;   // 16-byte units per pixel incl. K padding
-    const __half* src = in + (size_t)img * g.Hi * g.Wi * g.Cin;
-    for (int i = tid; i < g.R * units; i += FB_THREADS) {
-      const int r = i / units, u = i - r * units;
-      const int iy = iy0 + r / g.IW, ix = ix0 + r % g.IW;
-      uint4 q = make_uint4(0, 0, 0, 0);
-      if (u * 8 < g.Cin && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
-        q = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)iy * g.Wi + ix) * g.Cin + u * 8));
-      const int kb = u >> 3, uu = u & 7;
-      *reinterpret_cast<uint4*>(sX + ((size_t)kb * g.MT * 128 + r) * 128 + (size_t)((uu ^ (r & 7)) << 4)) = q;
-    }
-    tc::fence_proxy_async();
-  }
+  uint32_t e_cnt = 0, p_cnt = 0;   // expand / project commits issued so far (tracked identically by every thread)
+  bool first = true;
 
-  for (int j = 0; j < g.n_chunks; ++j) {
-    const int c0 = j * g.CW;                                   // first expanded channel of the chunk
-    const int cvalid = min(g.CW, g.Cexp - c0);                 // real channels in the chunk (multiple of 8)
-    const int cw16 = (cvalid + 15) & ~15;                      // K of the project step / N of the expand step
-    // chunk constants -> smem; chunk weights -> smem (TMA).  Everything of chunk j-1 has been consumed (bar_p wait).
-    if (tid == 0) {
-      uint32_t bytes = (uint32_t)(g.cout_pad * 128);
-      if (g.has_expand) bytes += (uint32_t)(g.kb_in * g.CW * 128);
-      tc::mbar_expect_tx(bar_w, bytes);
-      if (g.has_expand)
-        for (int kb = 0; kb < g.kb_in; ++kb) tc::tma_load_2d(sWE + (size_t)kb * 64 * 128, &tmWE, bar_w, kb * 64, c0);
-      tc::tma_load_2d(sWP, &tmWP, bar_w, c0, 0);
-    }
-    for (int i = tid; i < 11 * 64; i += FB_THREADS) {
-      const int row = i >> 6, c = i & 63;
-      float v = 0.f;
-      if (c < cvalid) {
-        if (row < 9) v = __ldg(wd + (size_t)row * g.Cexp + c0 + c);
-        else if (row == 9) v = __ldg(bd + c0 + c);
-        else if (g.has_expand) v = __ldg(be + c0 + c);
+  auto issue_expand = [&](int j) {   // thread 0 only; uses commit slot e_cnt
+    const int cvalid = min(g.CW, g.Cexp - j * g.CW);
+    const uint32_t idesc = tc::make_idesc_f16((cvalid + 15) & ~15);
+    for (int mt = 0; mt < g.MT; ++mt) {
+      for (int kb = 0; kb < g.kb_in; ++kb) {
+        const uint64_t da = tc::make_sdesc_sw128(tc::smem_u32(sX + ((size_t)kb * g.MT + mt) * 128 * 128));
+        const uint64_t db =
+            tc::make_sdesc_sw128(tc::smem_u32(sWE + (size_t)j * g.we_chunk_bytes + (size_t)kb * g.CW * 128));
+        const int krem = g.Cin - kb * 64;
+        const int nk = krem >= 64 ? 4 : (krem + 15) >> 4;
+        for (int k = 0; k < nk; ++k)
+          tc::umma_f16(tmem_base + (uint32_t)(mt * g.CW), tc::sdesc_advance_k16(da, k), tc::sdesc_advance_k16(db, k),
+                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
       }
-      s_wd[i] = v;
     }
-    tc::mbar_wait(bar_w, j & 1);
-    __syncthreads();
+    tc::umma_commit(&bar_e[e_cnt & 1u]);
+  };
 
-    if (g.has_expand) {
-      // (1) expand: D1[mt] = X[mt] * WE^T
-      if (tid == 0) {
-        tc::fence_after_sync();
-        const uint32_t idesc = tc::make_idesc_f16(cw16);
-        for (int mt = 0; mt < g.MT; ++mt) {
-          for (int kb = 0; kb < g.kb_in; ++kb) {
-            const uint64_t da = tc::make_sdesc_sw128(tc::smem_u32(sX + ((size_t)kb * g.MT + mt) * 128 * 128));
-            const uint64_t db = tc::make_sdesc_sw128(tc::smem_u32(sWE + (size_t)kb * 64 * 128));
-            const int krem = g.Cin - kb * 64;
-            const int nk = krem >= 64 ? 4 : (krem + 15) >> 4;
-            for (int k = 0; k < nk; ++k)
-              tc::umma_f16(tmem_base + (uint32_t)(mt * g.CW), tc::sdesc_advance_k16(da, k),
-                           tc::sdesc_advance_k16(db, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-        }
-        tc::umma_commit(bar_e);
-      }
-      __syncwarp();
-      tc::mbar_wait(bar_e, j & 1);
-      __syncwarp();
-      tc::fence_after_sync();
-      // TMEM -> +bias, ReLU6, zero outside the image -> fp16 rows of sE.  warp w reads lane group w%4; the two warp
-      // quads alternate over the M-tiles.
-      for (int mt = warp >> 2; mt < g.MT; mt += 2) {
-        const int r = mt * 128 + (warp & 3) * 32 + lane;
-        const int iy = iy0 + r / g.IW, ix = ix0 + r % g.IW;
-        const bool in_img = r < g.R && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * g.CW);
-        for (int cc = 0; cc < cw16; cc += 16) {
-          uint32_t v[16];
-          tc::tmem_ld16(taddr + (uint32_t)cc, v);
-          tc::tmem_ld_wait();
-          if (r < g.R) {
-            uint4 q[2];
-            __half2* hq = reinterpret_cast<__half2*>(q);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float a = __uint_as_float(v[2 * i]) + s_be[cc + 2 * i];
-              float b = __uint_as_float(v[2 * i + 1]) + s_be[cc + 2 * i + 1];
-              a = in_img ? fminf(fmaxf(a, 0.f), 6.f) : 0.f;
-              b = in_img ? fminf(fmaxf(b, 0.f), 6.f) : 0.f;
-              hq[i] = __floats2half2_rn(a, b);
-            }
-            uint4* d = reinterpret_cast<uint4*>(sE + (size_t)r * g.e_pitch + (size_t)cc * 2);
-            d[0] = q[0];
-            d[1] = q[1];
-          }
-        }
-      }
-      tc::fence_before_sync();
-    } else {
-      // no expand conv (layer_2): the "expanded" activation is the input tile itself (TMA zero fill = SAME padding)
-      const int units = cw16 >> 3;
+  for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % g.tiles_x;
+    t /= g.tiles_x;
+    const int ty = t % g.tiles_y;
+    const int img = t / g.tiles_y;
+    const int oy0 = ty * g.TH, ox0 = tx * 16;
+    const int iy0 = oy0 * g.stride - g.pad_t, ix0 = ox0 * g.stride - g.pad_l;
+
+    // (0) input halo tile -> swizzled K-major rows, zero outside the image and in the K padding
+    {
+      const int units = ((g.Cin + 15) & ~15) >> 3;   // 16-byte units per pixel incl. K padding
+      const __half* src = in + (size_t)img * g.Hi * g.Wi * g.Cin;
       for (int i = tid; i < g.R * units; i += FB_THREADS) {
         const int r = i / units, u = i - r * units;
-        const int cu = (c0 >> 3) + u;   // 16-byte unit inside the 128-byte swizzled row
+        const int iy = iy0 + r / g.IW, ix = ix0 + r % g.IW;
         uint4 q = make_uint4(0, 0, 0, 0);
-        if (cu * 8 < g.Cin) q = *reinterpret_cast<const uint4*>(sX + (size_t)r * 128 + (size_t)((cu ^ (r & 7)) << 4));
-        *reinterpret_cast<uint4*>(sE + (size_t)r * g.e_pitch + (size_t)u * 16) = q;
+        if (u * 8 < g.Cin && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
+          q = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)iy * g.Wi + ix) * g.Cin + u * 8));
+        const int kb = u >> 3, uu = u & 7;
+        *reinterpret_cast<uint4*>(sX + ((size_t)kb * g.MT * 128 + r) * 128 + (size_t)((uu ^ (r & 7)) << 4)) = q;
       }
+      tc::fence_proxy_async();
     }
-    __syncthreads();
+    if (first) {
+      tc::mbar_wait(bar_w, 0);
+      first = false;
+    }
+    __syncthreads();   // S0
+    if (g.has_expand) {
+      if (tid == 0) {
+        tc::fence_after_sync();
+        issue_expand(0);
+      }
+      ++e_cnt;
+    }
 
-    // (2) depthwise 3x3 (+bias, ReLU6) -> swizzled A tile of the project GEMM
-    {
-      const int units = cw16 >> 3;
-      for (int i = tid; i < 128 * units; i += FB_THREADS) {
-        const int p = i & 127, u = i >> 7;
-        const int oy = p >> 4, ox = p & 15;
-        if (oy >= g.TH) continue;   // rows of a 4 x 16 tile's unused half: their accumulator rows are never read
-        float acc[8];
+    for (int j = 0; j < g.n_chunks; ++j) {
+      const int c0 = j * g.CW;                                   // first expanded channel of the chunk
+      const int cvalid = min(g.CW, g.Cexp - c0);                 // real channels in the chunk (multiple of 8)
+      const int cw16 = (cvalid + 15) & ~15;                      // K of the project step / N of the expand step
+      if (g.has_expand) {
+        // (1) wait for expand(j) (commit number e_cnt-1), TMEM -> +bias, ReLU6, zero outside the image -> fp16 rows
+        const uint32_t k = e_cnt - 1;
+        tc::mbar_wait(&bar_e[k & 1u], (k >> 1) & 1u);
+        __syncwarp();
+        tc::fence_after_sync();
+        for (int mt = warp >> 2; mt < g.MT; mt += 2) {
+          const int r = mt * 128 + (warp & 3) * 32 + lane;
+          const int iy = iy0 + r / g.IW, ix = ix0 + r % g.IW;
+          const bool in_img = r < g.R && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * g.CW);
+          for (int cc = 0; cc < cw16; cc += 16) {
+            uint32_t v[16];
+            tc::tmem_ld16(taddr + (uint32_t)cc, v);
+            tc::tmem_ld_wait();
+            if (r < g.R) {
+              uint4 q[2];
+              __half2* hq = reinterpret_cast<__half2*>(q);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = s_bd[u * 8 + c];
-        const uint8_t* e0 = sE + (size_t)((oy * g.stride) * g.IW + ox * g.stride) * g.e_pitch + (size_t)u * 16;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const uint4 q = *reinterpret_cast<const uint4*>(e0 + (size_t)(ky * g.IW + kx) * g.e_pitch);
-            const __half2* hq = reinterpret_cast<const __half2*>(&q);
-            const float* w = s_wd + (ky * 3 + kx) * 64 + u * 8;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float2 f = __half22float2(hq[c]);
-              acc[2 * c] = fmaf(f.x, w[2 * c], acc[2 * c]);
-              acc[2 * c + 1] = fmaf(f.y, w[2 * c + 1], acc[2 * c + 1]);
+              for (int i = 0; i < 8; ++i) {
+                float a = __uint_as_float(v[2 * i]) + s_be[c0 + cc + 2 * i];
+                float b = __uint_as_float(v[2 * i + 1]) + s_be[c0 + cc + 2 * i + 1];
+                a = in_img ? fminf(fmaxf(a, 0.f), 6.f) : 0.f;
+                b = in_img ? fminf(fmaxf(b, 0.f), 6.f) : 0.f;
+                hq[i] = __floats2half2_rn(a, b);
+              }
+              uint4* d = reinterpret_cast<uint4*>(sE + (size_t)r * g.e_pitch + (size_t)cc * 2);
+              d[0] = q[0];
+              d[1] = q[1];
             }
           }
         }
-        uint4 o;
-        __half2* ho = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          // channels beyond Cexp (zero weights, zero bias) come out as exact zeros
-          ho[c] = __floats2half2_rn(fminf(fmaxf(acc[2 * c], 0.f), 6.f), fminf(fmaxf(acc[2 * c + 1], 0.f), 6.f));
+        tc::fence_before_sync();
+      } else {
+        // no expand conv (layer_2): the "expanded" activation is the input tile itself
+        const int units = cw16 >> 3;
+        for (int i = tid; i < g.R * units; i += FB_THREADS) {
+          const int r = i / units, u = i - r * units;
+          const int cu = (c0 >> 3) + u;   // 16-byte unit inside the 128-byte swizzled row
+          uint4 q = make_uint4(0, 0, 0, 0);
+          if (cu * 8 < g.Cin) q = *reinterpret_cast<const uint4*>(sX + (size_t)r * 128 + (size_t)((cu ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(sE + (size_t)r * g.e_pitch + (size_t)u * 16) = q;
         }
-        *reinterpret_cast<uint4*>(sA2 + (size_t)p * 128 + (size_t)((u ^ (p & 7)) << 4)) = o;
       }
-    }
-    tc::fence_proxy_async();
-    __syncthreads();
+      __syncthreads();   // S1: sE complete, D1 drained
 
-    // (3) project: D2 (+)= A2 * WP^T over this chunk's channels
-    if (tid == 0) {
-      tc::fence_after_sync();
-      const uint32_t idesc = tc::make_idesc_f16(g.cout_pad);
-      const uint64_t da = tc::make_sdesc_sw128(tc::smem_u32(sA2));
-      const uint64_t db = tc::make_sdesc_sw128(tc::smem_u32(sWP));
-      for (int k = 0; k < (cw16 >> 4); ++k)
-        tc::umma_f16(tmem_d2, tc::sdesc_advance_k16(da, k), tc::sdesc_advance_k16(db, k), idesc,
-                     (j > 0 || k > 0) ? 1u : 0u);
-      tc::umma_commit(bar_p);
-    }
-    __syncwarp();
-    tc::mbar_wait(bar_p, j & 1);   // A2 / WP / WE / sE may be overwritten by the next chunk
-    __syncwarp();
-  }
-  tc::fence_after_sync();
+      // expand(j+1) runs on the tensor core while the CUDA cores do the depthwise of chunk j
+      if (g.has_expand && j + 1 < g.n_chunks) {
+        if (tid == 0) {
+          tc::fence_after_sync();
+          issue_expand(j + 1);
+        }
+        ++e_cnt;
+      }
+      // project(j-1) (or the previous tile's last one) must have retired before A2 is overwritten
+      if (p_cnt > 0) {
+        const uint32_t k = p_cnt - 1;
+        tc::mbar_wait(&bar_p[k & 1u], (k >> 1) & 1u);
+      }
 
-  // (4) epilogue: +bias (+residual) -> fp16 NHWC.  Warp quad 0 writes the lower half of the channels, quad 1 the upper.
-  {
-    const int p = (warp & 3) * 32 + lane;
-    const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
-    const bool valid = (p >> 4) < g.TH && oy < g.Ho && ox < g.Wo;
-    const long long opix = ((long long)img * g.Ho + oy) * g.Wo + ox;
-    const int half_cols = ((g.cout_pad >> 1) + 15) & ~15;
-    const int cbeg = (warp >> 2) ? half_cols : 0;
-    const int cend = (warp >> 2) ? g.cout_pad : half_cols;
-    const uint32_t taddr = tmem_d2 + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int cc = cbeg; cc < cend; cc += 16) {
-      uint32_t v[16];
-      tc::tmem_ld16(taddr + (uint32_t)cc, v);
-      tc::tmem_ld_wait();
-      if (!valid) continue;
+      // (2) depthwise 3x3 (+bias, ReLU6) -> swizzled A tile of the project GEMM
+      {
+        const int units = cw16 >> 3;
+        for (int i = tid; i < 128 * units; i += FB_THREADS) {
+          const int p = i & 127, u = i >> 7;
+          const int oy = p >> 4, ox = p & 15;
+          if (oy >= g.TH) continue;   // unused half of a 4 x 16 tile: its accumulator rows are never read
+          float acc[8];
+          const float* bdp = s_bd + c0 + u * 8;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int n = cc + 8 * h;
-        if (n >= g.Cout) break;
-        float f[8];
+          for (int c = 0; c < 8; ++c) acc[c] = bdp[c];
+          const uint8_t* e0 = sE + (size_t)((oy * g.stride) * g.IW + ox * g.stride) * g.e_pitch + (size_t)u * 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]) + __ldg(bp + n + i);
-        if (g.residual) {
-          const uint4 q = *reinterpret_cast<const uint4*>(in + opix * g.Cin + n);
-          const __half2* hq = reinterpret_cast<const __half2*>(&q);
+          for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 r2 = __half22float2(hq[i]);
-            f[2 * i] += r2.x;
-            f[2 * i + 1] += r2.y;
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint4 q = *reinterpret_cast<const uint4*>(e0 + (size_t)(ky * g.IW + kx) * g.e_pitch);
+              const __half2* hq = reinterpret_cast<const __half2*>(&q);
+              const float* w = s_wd + (ky * 3 + kx) * g.cexp_pad + c0 + u * 8;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float2 f = __half22float2(hq[c]);
+                acc[2 * c] = fmaf(f.x, w[2 * c], acc[2 * c]);
+                acc[2 * c + 1] = fmaf(f.y, w[2 * c + 1], acc[2 * c + 1]);
+              }
+            }
           }
-        }
-        uint4 o;
-        __half2* ho = reinterpret_cast<__half2*>(&o);
+          uint4 o;
+          __half2* ho = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-        *reinterpret_cast<uint4*>(out + opix * g.Cout + n) = o;
+          for (int c = 0; c < 4; ++c)   // channels beyond Cexp (zero weights, zero bias) come out as exact zeros
+            ho[c] = __floats2half2_rn(fminf(fmaxf(acc[2 * c], 0.f), 6.f), fminf(fmaxf(acc[2 * c + 1], 0.f), 6.f));
+          *reinterpret_cast<uint4*>(sA2 + (size_t)p * 128 + (size_t)((u ^ (p & 7)) << 4)) = o;
+        }
       }
+      tc::fence_proxy_async();
+      __syncthreads();   // S2: A2 complete, sE free
+
+      // (3) project: D2 (+)= A2 * WP_j^T, runs under the next chunk's read-back
+      if (tid == 0) {
+        tc::fence_after_sync();
+        const uint64_t da = tc::make_sdesc_sw128(tc::smem_u32(sA2));
+        const uint64_t db = tc::make_sdesc_sw128(tc::smem_u32(sWP + (size_t)j * g.wp_chunk_bytes));
+        for (int k = 0; k < (cw16 >> 4); ++k)
+          tc::umma_f16(tmem_d2, tc::sdesc_advance_k16(da, k), tc::sdesc_advance_k16(db, k), idesc_p,
+                       (j > 0 || k > 0) ? 1u : 0u);
+        tc::umma_commit(&bar_p[p_cnt & 1u]);
+      }
+      ++p_cnt;
+    }
+    // (4) epilogue: wait for the last project, +bias (+residual) -> fp16 NHWC.  Warp quad 0 writes the lower half of the
+    // channels, quad 1 the upper.
+    {
+      const uint32_t k = p_cnt - 1;
+      tc::mbar_wait(&bar_p[k & 1u], (k >> 1) & 1u);
+      __syncwarp();
+      tc::fence_after_sync();
+      const int p = (warp & 3) * 32 + lane;
+      const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
+      const bool valid = (p >> 4) < g.TH && oy < g.Ho && ox < g.Wo;
+      const long long opix = ((long long)img * g.Ho + oy) * g.Wo + ox;
+      const int half_cols = ((g.cout_pad >> 1) + 15) & ~15;
+      const int cbeg = (warp >> 2) ? half_cols : 0;
+      const int cend = (warp >> 2) ? g.cout_pad : half_cols;
+      const uint32_t taddr = tmem_d2 + ((uint32_t)((warp & 3) * 32) << 16);
+      for (int cc = cbeg; cc < cend; cc += 16) {
+        uint32_t v[16];
+        tc::tmem_ld16(taddr + (uint32_t)cc, v);
+        tc::tmem_ld_wait();
+        if (!valid) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int n = cc + 8 * h;
+          if (n >= g.Cout) break;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * h + i]) + __ldg(bp + n + i);
+          if (g.residual) {
+            const uint4 q = *reinterpret_cast<const uint4*>(in + opix * g.Cin + n);
+            const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 r2 = __half22float2(hq[i]);
+              f[2 * i] += r2.x;
+              f[2 * i + 1] += r2.y;
+            }
+          }
+          uint4 o;
+          __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+          *reinterpret_cast<uint4*>(out + opix * g.Cout + n) = o;
+        }
+      }
+      tc::fence_before_sync();   // D2 reads are ordered before the next tile's first project (issued after S0..S2)
     }
   }
   tc::fence_before_sync();
@@ -287,24 +321,22 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled_fb)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int hfb_make_tmap_2d(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                      uint64_t row_stride_bytes, uint32_t box_outer);
-int hfb_make_tmap_nhwc_box(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B, int box_w,
-                           int box_h);
 
 struct FusedPlan {
   CUtensorMap tmWE, tmWP;
   FusedGeom g;
+  int ctas_per_sm;
 };
 
 FusedPlan* fused_block_new() { return new FusedPlan(); }
 void fused_block_delete(FusedPlan* p) { delete p; }
 
+// Returns HFB_ERR_CAPACITY when the block does not fit on chip (the caller keeps the three-kernel path).
 int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half* in, int Bmax, int Hi, int Wi, int Ho,
                      int Wo, int pad_t, int pad_l) {
+  (void)in;
   FusedGeom& g = fp.g;
   g.B = Bmax; g.Hi = Hi; g.Wi = Wi; g.Ho = Ho; g.Wo = Wo;
   g.Cin = bw.cin; g.Cexp = bw.cexp; g.Cout = bw.cout;
@@ -315,10 +347,16 @@ int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half
   g.CW = bw.stride == 1 ? 64 : 32;
   if (g.CW > ((bw.cexp + 15) & ~15)) g.CW = (bw.cexp + 15) & ~15;
   g.n_chunks = (bw.cexp + g.CW - 1) / g.CW;
+  g.cexp_pad = g.n_chunks * g.CW;
   g.kb_in = (bw.cin + 63) / 64;
   g.cout_pad = (bw.cout + 15) & ~15;
   g.e_pitch = g.CW * 2 + 16;
+  g.we_chunk_bytes = g.has_expand ? (uint32_t)(g.kb_in * g.CW * 128) : 0u;
+  g.wp_chunk_bytes = (uint32_t)(g.cout_pad * 128);
+  g.w_total_bytes = (uint32_t)g.n_chunks * (g.we_chunk_bytes + g.wp_chunk_bytes);
+  if (g.w_total_bytes >= (1u << 20)) return HFB_ERR_CAPACITY;   // mbarrier tx-count limit
   auto al = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  const uint32_t budget = 200 * 1024;
   for (g.TH = 8; g.TH >= 4; g.TH >>= 1) {
     g.tiles_y = (Ho + g.TH - 1) / g.TH;
     g.IH = (g.TH - 1) * bw.stride + 3;
@@ -328,19 +366,22 @@ int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half
     uint32_t off = 0;
     g.off_X = off;  off += al((uint32_t)(g.kb_in * g.MT * 128 * 128));
     g.off_A2 = off; off += 128 * 128;
-    g.off_WE = off; off += al((uint32_t)(g.kb_in * 64 * 128));
-    g.off_WP = off; off += al((uint32_t)(g.cout_pad * 128));
+    g.off_WE = off; off += al((uint32_t)g.n_chunks * g.we_chunk_bytes);
+    g.off_WP = off; off += al((uint32_t)g.n_chunks * g.wp_chunk_bytes);
     g.off_E = off;  off += al((uint32_t)(g.R * g.e_pitch));
-    g.off_wd = off; off += al(11 * 64 * 4);
+    g.off_wd = off; off += al((uint32_t)(11 * g.cexp_pad * 4));
     g.off_bars = off; off += 64;
     g.smem_bytes = off + 1024;
-    if (g.smem_bytes <= 200 * 1024) break;
+    if (g.smem_bytes <= budget) break;
   }
   uint32_t cols = 32;
   while ((int)cols < g.MT * g.CW + g.cout_pad) cols <<= 1;
-  if (g.TH < 4 || g.smem_bytes > 200 * 1024 || cols > 512) return HFB_ERR_CAPACITY;   // caller keeps the unfused path
+  if (g.TH < 4 || g.smem_bytes > budget || cols > 512) return HFB_ERR_CAPACITY;
   g.tmem_cols = cols;
-  (void)in;
+  g.total_tiles = g.tiles_x * g.tiles_y * Bmax;
+  int per_sm = (int)(227 * 1024 / (g.smem_bytes + 1024));
+  per_sm = std::min(per_sm, (int)(512 / cols));
+  fp.ctas_per_sm = std::max(1, std::min(per_sm, 3));
   if (bw.has_expand)
     HFB_TRY(hfb_make_tmap_2d(ctx, &fp.tmWE, bw.expand.w, (uint64_t)bw.expand.Kp, (uint64_t)bw.expand.N,
                              (uint64_t)bw.expand.Kp * 2, (uint32_t)g.CW));
@@ -350,6 +391,8 @@ int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half
   return HFB_OK;
 }
 
+int fused_block_tiles(const FusedPlan& fp, int B) { return fp.g.tiles_x * fp.g.tiles_y * B; }
+
 int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const __half* in, __half* out, int B) {
   static size_t configured = 0;
   if (fp.g.smem_bytes > configured) {
@@ -357,9 +400,12 @@ int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const _
                                        (int)fp.g.smem_bytes));
     configured = fp.g.smem_bytes;
   }
-  const int grid = fp.g.tiles_x * fp.g.tiles_y * B;
-  fused_block_kernel<<<grid, FB_THREADS, fp.g.smem_bytes, ctx->stream>>>(fp.tmWE, fp.tmWP, fp.g, in,
-                                                                        bw.expand.b, bw.wd, bw.bd, bw.project.b, out);
+  FusedGeom g = fp.g;
+  g.B = B;
+  g.total_tiles = g.tiles_x * g.tiles_y * B;
+  const int grid = std::min(g.total_tiles, ctx->n_sm * fp.ctas_per_sm);
+  fused_block_kernel<<<grid, FB_THREADS, g.smem_bytes, ctx->stream>>>(fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
+                                                                     bw.bd, bw.project.b, out);
   HFB_CHECK_LAUNCH(ctx, "fused_block");
   return HFB_OK;
 }
