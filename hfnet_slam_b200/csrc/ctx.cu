@@ -248,6 +248,7 @@ extern "C" int hfb_load_weights(hfb_ctx* ctx, const void* blob, size_t nbytes) {
   NetW& net = ctx->net;
   net.c1 = make_divisible(32.0 * dm, 8, 8);
   net.n_clusters = (int)n_clusters;
+  HFB_REQUIRE(ctx, net.c1 % 8 == 0 && net.c1 <= 32, "depth multiplier gives an unsupported first-layer width");
   ArenaBuilder ab;
   struct Fix { const void** dst; size_t off; };
   std::vector<Fix> fixes;

@@ -27,42 +27,53 @@ static inline int same_pad_before(int n, int k, int s) {
 // ----------------------------------------------------------------------------------------------- conv1 (layer_1)
 // u8 image -> (x-128)/128 -> 3x3 stride-2 SAME conv to C1 channels + bias + ReLU6 (hf_net.py:185-190,30).
 // One thread = one output pixel x 8 channels.
-__global__ void conv1_kernel(const uint8_t* __restrict__ img, int img_h, int img_w, int H8, int W8,
-                             const float* __restrict__ w, const float* __restrict__ bias, int C1,
-                             __half* __restrict__ out, int Ho, int Wo, int pad_t, int pad_l, long long total) {
+// One thread = one output pixel x all C1 (<= 32) channels: the 9 input bytes are read once, weights come from shared
+// memory, the pixel's C1 fp16 outputs leave as contiguous 16-byte stores.
+#define CONV1_MAXC 32
+__global__ void __launch_bounds__(256) conv1_kernel(const uint8_t* __restrict__ img, int img_h, int img_w, int H8,
+                                                    int W8, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, int C1,
+                                                    __half* __restrict__ out, int Ho, int Wo, int pad_t, int pad_l,
+                                                    long long total) {
+  __shared__ float s_w[9 * CONV1_MAXC + CONV1_MAXC];
+  for (int i = threadIdx.x; i < 10 * C1; i += blockDim.x) s_w[i] = i < 9 * C1 ? __ldg(w + i) : __ldg(bias + i - 9 * C1);
+  __syncthreads();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int groups = C1 >> 3;
-  const int cg = (int)(gid % groups);
-  long long p = gid / groups;
+  long long p = gid;
   const int ox = (int)(p % Wo);
   p /= Wo;
   const int oy = (int)(p % Ho);
   const int b = (int)(p / Ho);
   const uint8_t* src = img + (size_t)b * img_h * img_w;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + cg * 8 + j);
+  float px[9];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = oy * 2 + ky - pad_t;
-    if (iy < 0 || iy >= H8) continue;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int ix = ox * 2 + kx - pad_l;
-      if (ix < 0 || ix >= W8) continue;
-      const float v = ((float)src[(size_t)iy * img_w + ix] - 128.f) * (1.f / 128.f);
-      const float* wp = w + (ky * 3 + kx) * C1 + cg * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, __ldg(wp + j), acc[j]);
+      const bool ok = iy >= 0 && iy < H8 && ix >= 0 && ix < W8;
+      px[ky * 3 + kx] = ok ? ((float)src[(size_t)iy * img_w + ix] - 128.f) * (1.f / 128.f) : 0.f;
     }
   }
-  uint4 q;
-  __half2* hq = reinterpret_cast<__half2*>(&q);
+  __half* o = out + (((size_t)b * Ho + oy) * Wo + ox) * C1;
+  for (int c0 = 0; c0 < C1; c0 += 8) {
+    float acc[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    hq[j] = __floats2half2_rn(fminf(fmaxf(acc[2 * j], 0.f), 6.f), fminf(fmaxf(acc[2 * j + 1], 0.f), 6.f));
-  *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C1 + cg * 8) = q;
+    for (int j = 0; j < 8; ++j) acc[j] = s_w[9 * C1 + c0 + j];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(px[t], s_w[t * C1 + c0 + j], acc[j]);
+    }
+    uint4 q;
+    __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      hq[j] = __floats2half2_rn(fminf(fmaxf(acc[2 * j], 0.f), 6.f), fminf(fmaxf(acc[2 * j + 1], 0.f), 6.f));
+    *reinterpret_cast<uint4*>(o + c0) = q;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------- depthwise 3x3
@@ -115,36 +126,55 @@ __global__ void dw3x3_kernel(const __half* __restrict__ in, int Hi, int Wi, int 
 }
 
 // ----------------------------------------------------------------------------------------------- NetVLAD
-// (1) memberships: 1x1 conv D -> C + folded BN, softmax over clusters (layers.py:66-71).  Warp = 4 pixels, lane = cluster.
-__global__ void vlad_memberships_kernel(const __half* __restrict__ x, int P, int D, int C, const float* __restrict__ w,
-                                        const float* __restrict__ bias, float* __restrict__ memb) {
+// (1) memberships: 1x1 conv D -> C + folded BN, softmax over clusters (layers.py:66-71).  One CTA = 32 pixels staged in
+//     shared memory; warp = 4 pixels, lane = cluster (C <= 64: two passes of 32).
+#define VLAD_PIX 32
+__global__ void __launch_bounds__(256) vlad_memberships_kernel(const __half* __restrict__ x, int P, int D, int C,
+                                                               const float* __restrict__ w,
+                                                               const float* __restrict__ bias,
+                                                               float* __restrict__ memb) {
+  extern __shared__ __half s_x[];   // [VLAD_PIX][D]
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 4;
-  if (p0 >= P) return;
+  const int pix0 = blockIdx.x * VLAD_PIX;
+  const int npix = min(VLAD_PIX, P - pix0);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * P + pix0) * D);
+    uint4* dst = reinterpret_cast<uint4*>(s_x);
+    const int n16 = npix * D / 8;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int p0 = warp * 4;
+  if (p0 >= npix) return;
+  float logit[2][4];
   for (int cb = 0; cb < C; cb += 32) {
     const int c = cb + lane;
     float acc[4];
     const float bb = c < C ? __ldg(bias + c) : 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[q] = bb;
-    const __half* xp = x + ((size_t)b * P + p0) * D;
-    for (int d = 0; d < D; ++d) {
-      const float wv = c < C ? __ldg(w + (size_t)d * C + c) : 0.f;
+    const __half* xp = s_x + (size_t)p0 * D;
+#pragma unroll 4
+    for (int d = 0; d < D; d += 2) {
+      const float w0 = c < C ? __ldg(w + (size_t)d * C + c) : 0.f;
+      const float w1 = c < C ? __ldg(w + (size_t)(d + 1) * C + c) : 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (p0 + q < P) acc[q] = fmaf(__half2float(xp[(size_t)q * D + d]), wv, acc[q]);
+      for (int q = 0; q < 4; ++q) {
+        if (p0 + q < npix) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(xp + (size_t)q * D + d));
+          acc[q] = fmaf(f.x, w0, acc[q]);
+          acc[q] = fmaf(f.y, w1, acc[q]);
+        }
+      }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (p0 + q < P && c < C) memb[((size_t)b * P + p0 + q) * C + c] = acc[q];
+    for (int q = 0; q < 4; ++q) logit[cb >> 5][q] = c < C ? acc[q] : -INFINITY;
   }
-  __syncwarp();
-  // softmax over the C logits of each pixel (C <= 64: each lane holds up to 2)
+  // softmax over the C logits of each pixel (each lane holds up to 2)
   for (int q = 0; q < 4; ++q) {
-    if (p0 + q >= P) break;
-    float* m = memb + ((size_t)b * P + p0 + q) * C;
-    float v0 = lane < C ? m[lane] : -INFINITY, v1 = lane + 32 < C ? m[lane + 32] : -INFINITY;
+    if (p0 + q >= npix) break;
+    float v0 = logit[0][q], v1 = C > 32 ? logit[1][q] : -INFINITY;
     float mx = fmaxf(v0, v1);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
@@ -154,23 +184,39 @@ __global__ void vlad_memberships_kernel(const __half* __restrict__ x, int P, int
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
     const float inv = 1.f / sum;
+    float* m = memb + ((size_t)b * P + pix0 + p0 + q) * C;
     if (lane < C) m[lane] = v0 * inv;
     if (lane + 32 < C) m[lane + 32] = v1 * inv;
   }
 }
 
 // (2) V[c][d] = (sum_p m[p][c]) * centroid[c][d] - sum_p m[p][c] * x[p][d]   (layers.py:81-86: clusters - x)
-__global__ void vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ memb, int P, int D, int C,
-                                      const float* __restrict__ clusters, float* __restrict__ vlad) {
+//     One CTA per (cluster, frame); the cluster's membership column is staged in shared memory.
+__global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ memb,
+                                                             int P, int D, int C, const float* __restrict__ clusters,
+                                                             float* __restrict__ vlad) {
+  extern __shared__ float s_m[];   // [P]
   const int c = blockIdx.x, b = blockIdx.y;
   const float* m = memb + (size_t)b * P * C + c;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) s_m[p] = __ldg(m + (size_t)p * C);
+  __syncthreads();
   const __half* xb = x + (size_t)b * P * D;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float acc = 0.f, msum = 0.f;
-    for (int p = 0; p < P; ++p) {
-      const float mv = __ldg(m + (size_t)p * C);
-      msum += mv;
-      acc = fmaf(mv, __half2float(xb[(size_t)p * D + d]), acc);
+    int p = 0;
+    for (; p + 8 <= P; p += 8) {
+      float xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xv[u] = __half2float(xb[(size_t)(p + u) * D + d]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        msum += s_m[p + u];
+        acc = fmaf(s_m[p + u], xv[u], acc);
+      }
+    }
+    for (; p < P; ++p) {
+      msum += s_m[p];
+      acc = fmaf(s_m[p], __half2float(xb[(size_t)p * D + d]), acc);
     }
     vlad[((size_t)b * C + c) * D + d] = msum * __ldg(clusters + (size_t)c * D + d) - acc;
   }
@@ -244,7 +290,7 @@ __global__ void __launch_bounds__(256) fc_partial_kernel(const float* __restrict
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[bb][j] = 0.f;
       const __half* wp = w + (size_t)k0 * N + n;
-#pragma unroll 4
+#pragma unroll 8
       for (int kk = 0; kk < kn; ++kk) {
         const uint4 q = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)kk * N));
         const __half2* hq = reinterpret_cast<const __half2*>(&q);
@@ -444,7 +490,7 @@ int encoder_plan(hfb_ctx* ctx) {
       HFB_TRY(ctx->dalloc(&lv.d_memb, (size_t)Bm * le.P * C));
       HFB_TRY(ctx->dalloc(&lv.d_vlad, (size_t)Bm * K));
       HFB_TRY(ctx->dalloc(&lv.d_vladn, (size_t)Bm * K));
-      le.fc_split = std::max(1, ctx->n_sm / 2);
+      le.fc_split = std::max(1, ctx->n_sm);
       le.fc_kps = (K + le.fc_split - 1) / le.fc_split;
       le.fc_split = (K + le.fc_kps - 1) / le.fc_kps;
       HFB_TRY(ctx->dalloc(&lv.d_fc_partial, (size_t)Bm * le.fc_split * HFB_GLOBAL_DIM + (size_t)Bm * 64));
@@ -467,8 +513,8 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
   LevelPlan& lv = ctx->lv[level];
   LevelExec& le = execs(ctx)[level];
   {
-    const long long total = (long long)B * le.H1 * le.W1 * (net.c1 / 8);
-    ctx->note("conv1", (double)B * lv.H8 * lv.W8 + (double)total * 16, 2.0 * 9 * total * 8);
+    const long long total = (long long)B * le.H1 * le.W1;
+    ctx->note("conv1", (double)B * lv.H8 * lv.W8 + (double)total * net.c1 * 2, 2.0 * 9 * total * net.c1);
     conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
         lv.d_img, lv.H, lv.W, lv.H8, lv.W8, net.conv1_w, net.conv1_b, net.c1, lv.act[1], le.H1, le.W1, le.pad_t1,
         le.pad_l1, total);
@@ -524,11 +570,13 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
   HFB_TRY(launch_nms(ctx, lv.d_scores, lv.d_nms, lv.H8, lv.W8, B));
   if (lv.global) {
     const int C = net.n_clusters, K = C * le.D;
-    dim3 g1(ceil_div(le.P, 8 * 4), B);
-    vlad_memberships_kernel<<<g1, 256, 0, ctx->stream>>>(lv.act[18], le.P, le.D, C, net.vlad_w, net.vlad_b, lv.d_memb);
+    dim3 g1(ceil_div(le.P, VLAD_PIX), B);
+    vlad_memberships_kernel<<<g1, 256, (size_t)VLAD_PIX * le.D * 2, ctx->stream>>>(lv.act[18], le.P, le.D, C, net.vlad_w,
+                                                                                 net.vlad_b, lv.d_memb);
     HFB_CHECK_LAUNCH(ctx, "vlad_memberships");
     dim3 g2(C, B);
-    vlad_aggregate_kernel<<<g2, 256, 0, ctx->stream>>>(lv.act[18], lv.d_memb, le.P, le.D, C, net.vlad_c, lv.d_vlad);
+    vlad_aggregate_kernel<<<g2, 256, (size_t)le.P * 4, ctx->stream>>>(lv.act[18], lv.d_memb, le.P, le.D, C, net.vlad_c,
+                                                                     lv.d_vlad);
     HFB_CHECK_LAUNCH(ctx, "vlad_aggregate");
     vlad_normalize_kernel<<<B, 256, 0, ctx->stream>>>(lv.d_vlad, C, le.D, lv.d_vladn);
     HFB_CHECK_LAUNCH(ctx, "vlad_normalize");

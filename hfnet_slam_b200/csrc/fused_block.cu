@@ -36,7 +36,7 @@ struct FusedGeom {
   uint32_t off_X, off_A2, off_WE, off_WP, off_E, off_wd, off_bars, smem_bytes;
 };
 
-#define FB_THREADS 256
+#define FB_THREADS 512
 
 __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_constant__ CUtensorMap tmWE,
                                                                  const __grid_constant__ CUtensorMap tmWP,
@@ -117,6 +117,29 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
     tc::umma_commit(&bar_e[e_cnt & 1u]);
   };
 
+  // input halo tile -> swizzled K-major rows via cp.async (zero fill outside the image and in the K padding)
+  auto load_x = [&](int tile_idx) {
+    int q = tile_idx;
+    const int ltx = q % g.tiles_x;
+    q /= g.tiles_x;
+    const int lty = q % g.tiles_y;
+    const int limg = q / g.tiles_y;
+    const int liy0 = lty * g.TH * g.stride - g.pad_t, lix0 = ltx * 16 * g.stride - g.pad_l;
+    const int units = ((g.Cin + 15) & ~15) >> 3;   // 16-byte units per pixel incl. K padding
+    const __half* src = in + (size_t)limg * g.Hi * g.Wi * g.Cin;
+    for (int i = tid; i < g.R * units; i += FB_THREADS) {
+      const int r = i / units, u = i - r * units;
+      const int iy = liy0 + r / g.IW, ix = lix0 + r % g.IW;
+      const bool ok = u * 8 < g.Cin && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+      const __half* gp = ok ? src + ((size_t)iy * g.Wi + ix) * g.Cin + u * 8 : in;
+      const int kb = u >> 3, uu = u & 7;
+      const uint32_t dst = tc::smem_u32(sX + ((size_t)kb * g.MT * 128 + r) * 128 + (size_t)((uu ^ (r & 7)) << 4));
+      const int nbytes = ok ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(nbytes) : "memory");
+    }
+  };
+  if ((int)blockIdx.x < g.total_tiles) load_x(blockIdx.x);
+
   for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
     int t = tile;
     const int tx = t % g.tiles_x;
@@ -126,21 +149,9 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
     const int oy0 = ty * g.TH, ox0 = tx * 16;
     const int iy0 = oy0 * g.stride - g.pad_t, ix0 = ox0 * g.stride - g.pad_l;
 
-    // (0) input halo tile -> swizzled K-major rows, zero outside the image and in the K padding
-    {
-      const int units = ((g.Cin + 15) & ~15) >> 3;   // 16-byte units per pixel incl. K padding
-      const __half* src = in + (size_t)img * g.Hi * g.Wi * g.Cin;
-      for (int i = tid; i < g.R * units; i += FB_THREADS) {
-        const int r = i / units, u = i - r * units;
-        const int iy = iy0 + r / g.IW, ix = ix0 + r % g.IW;
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (u * 8 < g.Cin && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
-          q = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)iy * g.Wi + ix) * g.Cin + u * 8));
-        const int kb = u >> 3, uu = u & 7;
-        *reinterpret_cast<uint4*>(sX + ((size_t)kb * g.MT * 128 + r) * 128 + (size_t)((uu ^ (r & 7)) << 4)) = q;
-      }
-      tc::fence_proxy_async();
-    }
+    // (0) input halo tile: already in flight (cp.async issued during the previous tile, or just above for the first)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    tc::fence_proxy_async();
     if (first) {
       tc::mbar_wait(bar_w, 0);
       first = false;
@@ -164,12 +175,16 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
         tc::mbar_wait(&bar_e[k & 1u], (k >> 1) & 1u);
         __syncwarp();
         tc::fence_after_sync();
-        for (int mt = warp >> 2; mt < g.MT; mt += 2) {
+        // work units = (M-tile, column half) spread over the four warp quads; warp w reads TMEM lane group w % 4
+        const int nch = cw16 >> 4, ch_half = (nch + 1) >> 1;
+        for (int wu = warp >> 2; wu < g.MT * 2; wu += 4) {
+          const int mt = wu >> 1, half = wu & 1;
+          const int cbeg = half ? ch_half * 16 : 0, cend = half ? cw16 : ch_half * 16;
           const int r = mt * 128 + (warp & 3) * 32 + lane;
           const int iy = iy0 + r / g.IW, ix = ix0 + r % g.IW;
           const bool in_img = r < g.R && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
           const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * g.CW);
-          for (int cc = 0; cc < cw16; cc += 16) {
+          for (int cc = cbeg; cc < cend; cc += 16) {
             uint32_t v[16];
             tc::tmem_ld16(taddr + (uint32_t)cc, v);
             tc::tmem_ld_wait();
@@ -203,6 +218,9 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
         }
       }
       __syncthreads();   // S1: sE complete, D1 drained
+      // every expand of this tile has retired and (layer_2) the copy out of sX is done: sX is free, so the next
+      // tile's halo load flies under the remaining depthwise / project / store work
+      if (j + 1 == g.n_chunks && tile + (int)gridDim.x < g.total_tiles) load_x(tile + gridDim.x);
 
       // expand(j+1) runs on the tensor core while the CUDA cores do the depthwise of chunk j
       if (g.has_expand && j + 1 < g.n_chunks) {
@@ -268,8 +286,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
       }
       ++p_cnt;
     }
-    // (4) epilogue: wait for the last project, +bias (+residual) -> fp16 NHWC.  Warp quad 0 writes the lower half of the
-    // channels, quad 1 the upper.
+    // (4) epilogue: wait for the last project, +bias (+residual) -> fp16 NHWC; the four warp quads split the channels
     {
       const uint32_t k = p_cnt - 1;
       tc::mbar_wait(&bar_p[k & 1u], (k >> 1) & 1u);
@@ -279,11 +296,8 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
       const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
       const bool valid = (p >> 4) < g.TH && oy < g.Ho && ox < g.Wo;
       const long long opix = ((long long)img * g.Ho + oy) * g.Wo + ox;
-      const int half_cols = ((g.cout_pad >> 1) + 15) & ~15;
-      const int cbeg = (warp >> 2) ? half_cols : 0;
-      const int cend = (warp >> 2) ? g.cout_pad : half_cols;
       const uint32_t taddr = tmem_d2 + ((uint32_t)((warp & 3) * 32) << 16);
-      for (int cc = cbeg; cc < cend; cc += 16) {
+      for (int cc = (warp >> 2) * 16; cc < g.cout_pad; cc += 64) {   // 16-column pieces round-robin over the quads
         uint32_t v[16];
         tc::tmem_ld16(taddr + (uint32_t)cc, v);
         tc::tmem_ld_wait();
