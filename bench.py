@@ -222,8 +222,8 @@ def main_gpu(args):
     with ClockSampler(local) as cs:
         ms_dev, wall_dev, launches = timed(step_dev, args.steps, warm)
     clocks = cs.summary()
-    ms_host, wall_host, _ = timed(step_host, max(3, args.steps // 4), 2)
-    n_host = max(3, args.steps // 4)
+    n_host = max(5, args.steps)
+    ms_host, wall_host, _ = timed(step_host, n_host, 3)
     # sanity inside the bench: the device chain produced real keypoints and matches
     f0 = ctx.fetch_features(0)
     ctx.match_consecutive_dev(B, 0, 0.6)

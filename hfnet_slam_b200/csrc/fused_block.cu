@@ -24,7 +24,7 @@ struct FusedGeom {
   int has_expand, residual;
   int tiles_x, tiles_y, total_tiles;
   int TH;                 // output tile = TH x 16 pixels
-  int IH, IW, R, MT;      // input halo tile, R = IH*IW rows, MT = ceil(R/128) expand M-tiles
+  int IH, IW_, R, MT;     // input halo tile, R = IH*IW rows, MT = ceil(R/128) expand M-tiles
   int CW;                 // chunk of expanded channels (multiple of 16, <= 64)
   int n_chunks;
   int cexp_pad;           // n_chunks * CW
@@ -38,6 +38,7 @@ struct FusedGeom {
 
 #define FB_THREADS 512
 
+template <int S>
 __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_constant__ CUtensorMap tmWE,
                                                                  const __grid_constant__ CUtensorMap tmWP,
                                                                  const FusedGeom g, const __half* __restrict__ in,
@@ -47,7 +48,10 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
                                                                  const float* __restrict__ bp,   // project bias [Cout]
                                                                  __half* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic (keeps the shared-memory address space visible to the compiler: LDS/STS
+  // instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int IW = 15 * S + 3;   // halo tile width
   uint8_t* sX = smem + g.off_X;      // [kb_in][MT*128 rows][128 B] swizzled
   uint8_t* sA2 = smem + g.off_A2;    // [128 rows][128 B] swizzled (written by the depthwise phase)
   uint8_t* sWE = smem + g.off_WE;    // [n_chunks][kb_in][CW rows][128 B] swizzled (TMA, resident)
@@ -124,18 +128,23 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
     q /= g.tiles_x;
     const int lty = q % g.tiles_y;
     const int limg = q / g.tiles_y;
-    const int liy0 = lty * g.TH * g.stride - g.pad_t, lix0 = ltx * 16 * g.stride - g.pad_l;
+    const int liy0 = lty * g.TH * S - g.pad_t, lix0 = ltx * 16 * S - g.pad_l;
     const int units = ((g.Cin + 15) & ~15) >> 3;   // 16-byte units per pixel incl. K padding
+    const int vunits = g.Cin >> 3;                 // units holding real channels
     const __half* src = in + (size_t)limg * g.Hi * g.Wi * g.Cin;
-    for (int i = tid; i < g.R * units; i += FB_THREADS) {
-      const int r = i / units, u = i - r * units;
-      const int iy = liy0 + r / g.IW, ix = lix0 + r % g.IW;
-      const bool ok = u * 8 < g.Cin && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
-      const __half* gp = ok ? src + ((size_t)iy * g.Wi + ix) * g.Cin + u * 8 : in;
-      const int kb = u >> 3, uu = u & 7;
-      const uint32_t dst = tc::smem_u32(sX + ((size_t)kb * g.MT * 128 + r) * 128 + (size_t)((uu ^ (r & 7)) << 4));
-      const int nbytes = ok ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(nbytes) : "memory");
+    for (int r = tid; r < g.R; r += FB_THREADS) {
+      const int ry = r / IW, rx = r - ry * IW;
+      const int iy = liy0 + ry, ix = lix0 + rx;
+      const bool inb = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+      const __half* gp = inb ? src + ((size_t)iy * g.Wi + ix) * g.Cin : in;
+      const uint32_t row_dst = tc::smem_u32(sX) + (uint32_t)r * 128u;
+      for (int u = 0; u < units; ++u) {
+        const bool ok = inb && u < vunits;
+        const uint32_t dst = row_dst + (uint32_t)(u >> 3) * (uint32_t)(g.MT * 128 * 128) + (uint32_t)(((u & 7) ^ (r & 7)) << 4);
+        const int nbytes = ok ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? gp + u * 8 : in), "r"(nbytes)
+                     : "memory");
+      }
     }
   };
   if ((int)blockIdx.x < g.total_tiles) load_x(blockIdx.x);
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
     const int ty = t % g.tiles_y;
     const int img = t / g.tiles_y;
     const int oy0 = ty * g.TH, ox0 = tx * 16;
-    const int iy0 = oy0 * g.stride - g.pad_t, ix0 = ox0 * g.stride - g.pad_l;
+    const int iy0 = oy0 * S - g.pad_t, ix0 = ox0 * S - g.pad_l;
 
     // (0) input halo tile: already in flight (cp.async issued during the previous tile, or just above for the first)
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
           const int mt = wu >> 1, half = wu & 1;
           const int cbeg = half ? ch_half * 16 : 0, cend = half ? cw16 : ch_half * 16;
           const int r = mt * 128 + (warp & 3) * 32 + lane;
-          const int iy = iy0 + r / g.IW, ix = ix0 + r % g.IW;
+          const int iy = iy0 + r / IW, ix = ix0 + r % IW;
           const bool in_img = r < g.R && iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
           const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * g.CW);
           for (int cc = cbeg; cc < cend; cc += 16) {
@@ -236,39 +245,54 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
         tc::mbar_wait(&bar_p[k & 1u], (k >> 1) & 1u);
       }
 
-      // (2) depthwise 3x3 (+bias, ReLU6) -> swizzled A tile of the project GEMM
+      // (2) depthwise 3x3 (+bias, ReLU6) -> swizzled A tile of the project GEMM.  Thread = (8-channel unit, pixel
+      // pair p, p+64): the unit's 72 weights + 8 biases sit in registers for both pixels.
       {
         const int units = cw16 >> 3;
-        for (int i = tid; i < 128 * units; i += FB_THREADS) {
-          const int p = i & 127, u = i >> 7;
-          const int oy = p >> 4, ox = p & 15;
-          if (oy >= g.TH) continue;   // unused half of a 4 x 16 tile: its accumulator rows are never read
-          float acc[8];
-          const float* bdp = s_bd + c0 + u * 8;
+        if (tid < 64 * units) {
+          const int u = tid >> 6, pb = tid & 63;
+          float w[72], bias8[8];
+          {
+            const float4* bq = reinterpret_cast<const float4*>(s_bd + c0 + u * 8);
+            const float4 b0 = bq[0], b1 = bq[1];
+            bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+            bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[c] = bdp[c];
-          const uint8_t* e0 = sE + (size_t)((oy * g.stride) * g.IW + ox * g.stride) * g.e_pitch + (size_t)u * 16;
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const uint4 q = *reinterpret_cast<const uint4*>(e0 + (size_t)(ky * g.IW + kx) * g.e_pitch);
-              const __half2* hq = reinterpret_cast<const __half2*>(&q);
-              const float* w = s_wd + (ky * 3 + kx) * g.cexp_pad + c0 + u * 8;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float2 f = __half22float2(hq[c]);
-                acc[2 * c] = fmaf(f.x, w[2 * c], acc[2 * c]);
-                acc[2 * c + 1] = fmaf(f.y, w[2 * c + 1], acc[2 * c + 1]);
-              }
+            for (int tp = 0; tp < 9; ++tp) {
+              const float4* wq = reinterpret_cast<const float4*>(s_wd + tp * g.cexp_pad + c0 + u * 8);
+              const float4 w0 = wq[0], w1 = wq[1];
+              w[tp * 8 + 0] = w0.x; w[tp * 8 + 1] = w0.y; w[tp * 8 + 2] = w0.z; w[tp * 8 + 3] = w0.w;
+              w[tp * 8 + 4] = w1.x; w[tp * 8 + 5] = w1.y; w[tp * 8 + 6] = w1.z; w[tp * 8 + 7] = w1.w;
             }
           }
-          uint4 o;
-          __half2* ho = reinterpret_cast<__half2*>(&o);
+          const int npix = g.TH * 16;
+          for (int p = pb; p < npix; p += 64) {
+            const int oy = p >> 4, ox = p & 15;
+            float acc[8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c)   // channels beyond Cexp (zero weights, zero bias) come out as exact zeros
-            ho[c] = __floats2half2_rn(fminf(fmaxf(acc[2 * c], 0.f), 6.f), fminf(fmaxf(acc[2 * c + 1], 0.f), 6.f));
-          *reinterpret_cast<uint4*>(sA2 + (size_t)p * 128 + (size_t)((u ^ (p & 7)) << 4)) = o;
+            for (int c = 0; c < 8; ++c) acc[c] = bias8[c];
+            const uint8_t* e0 = sE + (size_t)((oy * S) * IW + ox * S) * g.e_pitch + (size_t)u * 16;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const uint4 q = *reinterpret_cast<const uint4*>(e0 + (size_t)(ky * IW + kx) * g.e_pitch);
+                const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float2 f = __half22float2(hq[c]);
+                  acc[2 * c] = fmaf(f.x, w[(ky * 3 + kx) * 8 + 2 * c], acc[2 * c]);
+                  acc[2 * c + 1] = fmaf(f.y, w[(ky * 3 + kx) * 8 + 2 * c + 1], acc[2 * c + 1]);
+                }
+              }
+            }
+            uint4 o;
+            __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)   // channels beyond Cexp (zero weights, zero bias) come out as exact zeros
+              ho[c] = __floats2half2_rn(fminf(fmaxf(acc[2 * c], 0.f), 6.f), fminf(fmaxf(acc[2 * c + 1], 0.f), 6.f));
+            *reinterpret_cast<uint4*>(sA2 + (size_t)p * 128 + (size_t)((u ^ (p & 7)) << 4)) = o;
+          }
         }
       }
       tc::fence_proxy_async();
@@ -374,8 +398,8 @@ int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half
   for (g.TH = 8; g.TH >= 4; g.TH >>= 1) {
     g.tiles_y = (Ho + g.TH - 1) / g.TH;
     g.IH = (g.TH - 1) * bw.stride + 3;
-    g.IW = 15 * bw.stride + 3;
-    g.R = g.IH * g.IW;
+    g.IW_ = 15 * bw.stride + 3;
+    g.R = g.IH * g.IW_;
     g.MT = (g.R + 127) / 128;
     uint32_t off = 0;
     g.off_X = off;  off += al((uint32_t)(g.kb_in * g.MT * 128 * 128));
@@ -410,7 +434,9 @@ int fused_block_tiles(const FusedPlan& fp, int B) { return fp.g.tiles_x * fp.g.t
 int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const __half* in, __half* out, int B) {
   static size_t configured = 0;
   if (fp.g.smem_bytes > configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)fp.g.smem_bytes));
+    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)fp.g.smem_bytes));
     configured = fp.g.smem_bytes;
   }
@@ -418,8 +444,12 @@ int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const _
   g.B = B;
   g.total_tiles = g.tiles_x * g.tiles_y * B;
   const int grid = std::min(g.total_tiles, ctx->n_sm * fp.ctas_per_sm);
-  fused_block_kernel<<<grid, FB_THREADS, g.smem_bytes, ctx->stream>>>(fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
-                                                                     bw.bd, bw.project.b, out);
+  if (g.stride == 1)
+    fused_block_kernel<1><<<grid, FB_THREADS, g.smem_bytes, ctx->stream>>>(fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
+                                                                          bw.bd, bw.project.b, out);
+  else
+    fused_block_kernel<2><<<grid, FB_THREADS, g.smem_bytes, ctx->stream>>>(fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
+                                                                          bw.bd, bw.project.b, out);
   HFB_CHECK_LAUNCH(ctx, "fused_block");
   return HFB_OK;
 }

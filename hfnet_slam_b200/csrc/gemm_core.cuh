@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(GEMM_THREADS(Epi::kWarps)) gemm_tc_kernel(cons
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const GemmGeom g, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic: keeps the shared address space visible to the compiler (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t stage_bytes = GEMM_TILE_A_BYTES + (uint32_t)g.BN * 128u;
   uint8_t* epi_smem = smem + g.ring_bytes;
   float* s_bias = reinterpret_cast<float*>(epi_smem + (size_t)Epi::kWarps * g.epi_warp_bytes);
