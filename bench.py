@@ -175,8 +175,14 @@ def main_gpu(args):
 
     ctx = Context(height=H, width=W, n_levels=1, max_keypoints=NKP, max_batch=B, with_global=True, device=local)
     ctx.load_weights(weights.synthetic_blob(seed=0))
+    from hfnet_slam_b200.lib import pinned_empty
     frames = synthetic_frames(B, 1000 * rank)
     d_frames = torch.from_numpy(np.stack(frames)).to(dev)            # resident in HBM before the timed region
+    pinned_frames = []                                               # e2e arm: frames arrive in page-locked host memory
+    for f in frames:
+        pf = pinned_empty(f.shape, np.uint8)
+        pf[...] = f
+        pinned_frames.append(pf)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     budgets = [NKP]
@@ -192,7 +198,7 @@ def main_gpu(args):
         ctx.match_consecutive_dev(B, 0, 0.6)
 
     def step_host():
-        feats, block = ctx.extract_batch(frames, budgets, THR, return_block=True)
+        feats, block = ctx.extract_batch(pinned_frames, budgets, THR, return_block=True, pinned=True)
         cnt = np.array([len(f["x"]) for f in feats], np.int32)
         descs = block["descriptors"].reshape(-1, 256)                 # frame b's rows start at b * kp_cap
         off = (np.arange(B) * ctx.kp_cap).astype(np.int32)

@@ -184,6 +184,23 @@ extern "C" void hfb_destroy(hfb_ctx* ctx) {
   delete ctx;
 }
 
+extern "C" void* hfb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes > 0 ? bytes : 16) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void hfb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int hfb_sync(hfb_ctx* ctx) {
   if (!ctx) return HFB_ERR_INVALID;
   HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -492,30 +509,42 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
   const size_t per_frame_out = (size_t)ctx->kp_cap * (4 * 4 + HFB_DESC_DIM * 4) + HFB_GLOBAL_DIM * 4 + 64;
   HFB_TRY(ctx->ensure_stage((size_t)n_images * (img_bytes + per_frame_out)));
   uint8_t* hs = reinterpret_cast<uint8_t*>(ctx->h_stage);
+  // inputs: page-locked, densely packed frames are DMA'd in place; anything else goes through the pinned stage
   for (int b = 0; b < n_images; ++b) {
     HFB_REQUIRE(ctx, images[b] != nullptr, "null image");
-    for (int y = 0; y < l0.H; ++y) memcpy(hs + (size_t)b * img_bytes + (size_t)y * l0.W, images[b] + (size_t)y * stride, l0.W);
+    if (stride == l0.W && is_pinned(images[b])) {
+      HFB_CUDA(ctx, cudaMemcpyAsync(l0.d_img + (size_t)b * img_bytes, images[b], img_bytes, cudaMemcpyHostToDevice,
+                                    ctx->stream));
+    } else {
+      uint8_t* dst = hs + (size_t)b * img_bytes;
+      for (int y = 0; y < l0.H; ++y) memcpy(dst + (size_t)y * l0.W, images[b] + (size_t)y * stride, l0.W);
+      HFB_CUDA(ctx, cudaMemcpyAsync(l0.d_img + (size_t)b * img_bytes, dst, img_bytes, cudaMemcpyHostToDevice,
+                                    ctx->stream));
+    }
   }
   tm.mark("stage_in");
-  HFB_CUDA(ctx, cudaMemcpyAsync(l0.d_img, hs, (size_t)n_images * img_bytes, cudaMemcpyHostToDevice, ctx->stream));
   HFB_TRY(run_extract(ctx, n_images, n_per_level, threshold));
   tm.mark("enqueue");
-  // one D2H burst of budget-sized slices into pinned memory, one synchronisation
+  // outputs: one D2H burst of budget-sized slices, one synchronisation.  Page-locked caller arrays receive the DMA
+  // directly; pageable ones are filled from the pinned stage after the sync.
   int budget = 0;
   for (int l = 0; l < ctx->n_levels; ++l) budget += n_per_level[l];
   uint8_t* ho = hs + (size_t)n_images * img_bytes;
-  struct Slot { int* counts; float *x, *y, *r; int* o; float *d, *g; };
+  struct Slot { int* counts; float *x, *y, *r; int* o; float *d, *g; bool direct; };
   std::vector<Slot> slots(n_images);
   for (int b = 0; b < n_images; ++b) {
     uint8_t* q = ho + (size_t)b * per_frame_out;
     Slot& s = slots[b];
+    hfb_features& f = outs[b];
+    s.direct = is_pinned(f.descriptors) && is_pinned(f.x) && is_pinned(f.y) && is_pinned(f.response) &&
+               is_pinned(f.octave) && (!f.global_descriptor || is_pinned(f.global_descriptor));
     s.counts = reinterpret_cast<int*>(q); q += 64;
-    s.x = reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
-    s.y = reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
-    s.r = reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
-    s.o = reinterpret_cast<int*>(q); q += (size_t)ctx->kp_cap * 4;
-    s.d = reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * HFB_DESC_DIM * 4;
-    s.g = reinterpret_cast<float*>(q);
+    s.x = s.direct ? f.x : reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
+    s.y = s.direct ? f.y : reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
+    s.r = s.direct ? f.response : reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
+    s.o = s.direct ? f.octave : reinterpret_cast<int*>(q); q += (size_t)ctx->kp_cap * 4;
+    s.d = s.direct ? f.descriptors : reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * HFB_DESC_DIM * 4;
+    s.g = (s.direct && f.global_descriptor) ? f.global_descriptor : reinterpret_cast<float*>(q);
     const size_t o = (size_t)b * ctx->kp_cap;
     HFB_CUDA(ctx, cudaMemcpyAsync(s.counts, ctx->d_kcount + (size_t)b * HFB_MAX_LEVELS, HFB_MAX_LEVELS * 4,
                                   cudaMemcpyDeviceToHost, ctx->stream));
@@ -527,7 +556,7 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
       HFB_CUDA(ctx, cudaMemcpyAsync(s.d, ctx->d_kdesc + o * HFB_DESC_DIM, (size_t)budget * HFB_DESC_DIM * 4,
                                     cudaMemcpyDeviceToHost, ctx->stream));
     }
-    if (ctx->cfg.with_global)
+    if (ctx->cfg.with_global && (f.global_descriptor || !s.direct))
       HFB_CUDA(ctx, cudaMemcpyAsync(s.g, ctx->d_global + (size_t)b * HFB_GLOBAL_DIM, HFB_GLOBAL_DIM * 4,
                                     cudaMemcpyDeviceToHost, ctx->stream));
   }
@@ -543,6 +572,7 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
       total += f.n_per_level[l];
     }
     f.n_total = total;
+    if (s.direct) continue;
     if (total > 0) {
       memcpy(f.x, s.x, (size_t)total * 4);
       memcpy(f.y, s.y, (size_t)total * 4);

@@ -172,20 +172,39 @@ __global__ void __launch_bounds__(1024) select_topk_kernel(const u64* __restrict
       if (tid < 256) s_hist[tid] = 0;
       __syncthreads();
       const u64 prefix = s_prefix;
+      const int rem = s_remaining;   // stable until this pass's winner bin rewrites it after the scan
       const u64 himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
       for (int i = tid; i < n; i += 1024) {
         const u64 key = c[i];
         if ((key & himask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 0xFF)], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int rem = s_remaining, bin = 255;
-        for (; bin > 0; --bin) {
-          if (s_hist[bin] >= rem) break;
-          rem -= s_hist[bin];
+      // find the bin where the count from the top reaches `remaining`: parallel suffix sums over the 256 bins
+      // (8 warps x 32 bins) instead of a serial walk
+      {
+        __shared__ int s_wtot[8];
+        int h = 0, incl = 0;
+        if (tid < 256) {
+          h = s_hist[tid];
+          incl = h;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_down_sync(0xffffffffu, incl, d);
+            if ((tid & 31) + d < 32) incl += v;
+          }
+          if ((tid & 31) == 0) s_wtot[tid >> 5] = incl;   // total of this warp's 32 bins
         }
-        s_prefix = prefix | ((u64)bin << shift);
-        s_remaining = rem;
+        __syncthreads();
+        if (tid < 256) {
+          int above = 0;
+          for (int w = (tid >> 5) + 1; w < 8; ++w) above += s_wtot[w];
+          const int suffix_incl = incl + above;            // elements in bins >= tid
+          const int suffix_excl = suffix_incl - h;         // elements in bins >  tid
+          if (suffix_incl >= rem && suffix_excl < rem) {    // exactly one bin qualifies
+            s_prefix = prefix | ((u64)tid << shift);
+            s_remaining = rem - suffix_excl;
+          }
+        }
       }
       __syncthreads();
     }

@@ -62,6 +62,8 @@ SIGNATURES = {
     "hfb_sync": (C.c_int, [C.c_void_p]),
     "hfb_stream": (C.c_void_p, [C.c_void_p]),
     "hfb_launch_count": (C.c_uint64, [C.c_void_p]),
+    "hfb_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "hfb_host_free": (None, [C.c_void_p]),
     "hfb_load_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "hfb_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, C.c_float,
                               C.POINTER(hfb_features)]),
@@ -122,6 +124,46 @@ def load(path: Optional[Path] = None) -> C.CDLL:
     if path is None:
         _lib = lib
     return lib
+
+
+class PinnedBuffer:
+    """Page-locked host memory (hfb_host_alloc) exposed as numpy arrays: DMA source / target without staging copies."""
+
+    def __init__(self, nbytes: int):
+        self.lib = load()
+        self.nbytes = int(nbytes)
+        self.ptr = self.lib.hfb_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise HfbError(2, "hfb_host_alloc failed")
+        self._buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+
+    def array(self, offset: int, shape, dtype) -> np.ndarray:
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return np.frombuffer(self._buf, dtype=dtype, count=int(np.prod(shape)), offset=offset).reshape(shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self._buf = None
+            self.lib.hfb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked memory; the buffer lives as long as the array (kept on ``arr.base`` chain)."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    buf = PinnedBuffer(max(nbytes, 16))
+    arr = buf.array(0, shape, dtype)
+    _PINNED_KEEPALIVE[arr.ctypes.data] = buf
+    return arr
+
+
+_PINNED_KEEPALIVE = {}
 
 
 def as_f32(a) -> np.ndarray:
@@ -189,13 +231,23 @@ class Context:
         self.check(self.lib.hfb_load_weights(self.handle, C.cast(buf, C.c_void_p), len(blob)))
 
     # ------------------------------------------------------------------------------------------ extraction
-    def _alloc_features(self, n: int = 1):
-        """One contiguous host block per field for n frames (frame b's rows start at b * kp_cap)."""
+    def _alloc_features(self, n: int = 1, pinned: bool = False):
+        """One contiguous host block per field for n frames (frame b's rows start at b * kp_cap).  pinned=True reuses a
+        page-locked block owned by the context (results are valid until the next pinned call)."""
         cap = self.kp_cap
-        arrs = dict(x=np.empty((n, cap), np.float32), y=np.empty((n, cap), np.float32),
-                    response=np.empty((n, cap), np.float32), octave=np.empty((n, cap), np.int32),
-                    descriptors=np.empty((n, cap, HFB_DESC_DIM), np.float32),
-                    global_descriptor=np.empty((n, HFB_GLOBAL_DIM), np.float32))
+        if pinned:
+            cache = self.__dict__.setdefault("_pinned_out", {})
+            if n not in cache:
+                cache[n] = dict(x=pinned_empty((n, cap), np.float32), y=pinned_empty((n, cap), np.float32),
+                                response=pinned_empty((n, cap), np.float32), octave=pinned_empty((n, cap), np.int32),
+                                descriptors=pinned_empty((n, cap, HFB_DESC_DIM), np.float32),
+                                global_descriptor=pinned_empty((n, HFB_GLOBAL_DIM), np.float32))
+            arrs = cache[n]
+        else:
+            arrs = dict(x=np.empty((n, cap), np.float32), y=np.empty((n, cap), np.float32),
+                        response=np.empty((n, cap), np.float32), octave=np.empty((n, cap), np.int32),
+                        descriptors=np.empty((n, cap, HFB_DESC_DIM), np.float32),
+                        global_descriptor=np.empty((n, HFB_GLOBAL_DIM), np.float32))
         feats = (hfb_features * n)()
         for b in range(n):
             f = feats[b]
@@ -216,7 +268,7 @@ class Context:
     def _budgets(self, n_per_level):
         return (C.c_int32 * HFB_MAX_LEVELS)(*([int(v) for v in n_per_level] + [0] * (HFB_MAX_LEVELS - len(n_per_level))))
 
-    def extract_batch(self, images, n_per_level, threshold: float, return_block: bool = False):
+    def extract_batch(self, images, n_per_level, threshold: float, return_block: bool = False, pinned: bool = False):
         """HFextractor::operator() for n frames.  Returns one dict per frame (views into one contiguous host block;
         with return_block=True also the block itself: frame b's descriptors are block['descriptors'][b, :n_b])."""
         imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
@@ -225,7 +277,7 @@ class Context:
                 raise HfbError(1, f"image shape {im.shape} differs from the context's {(self.height, self.width)}")
         n = len(imgs)
         ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
-        feats, arrs = self._alloc_features(n)
+        feats, arrs = self._alloc_features(n, pinned)
         self.check(self.lib.hfb_extract_batch(self.handle, ptrs, n, self.width, self._budgets(n_per_level), threshold,
                                               feats))
         out = [self._view(feats[i], arrs, i, self.with_global) for i in range(n)]

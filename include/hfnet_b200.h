@@ -68,6 +68,11 @@ void* hfb_stream(hfb_ctx* ctx);
 /* Number of kernels this library has launched on ctx since creation (graph replays count their kernel nodes). */
 uint64_t hfb_launch_count(const hfb_ctx* ctx);
 
+/* Page-locked host memory for zero-copy staging: images / output arrays that live in memory obtained here are DMA'd
+ * directly (no intermediate copy).  Ordinary (pageable) pointers are accepted everywhere and are staged internally. */
+void* hfb_host_alloc(size_t bytes);
+void hfb_host_free(void* p);
+
 /* Weights: flat 'HFB2WTS1' blob (hfnet_slam_b200/weights.py), BatchNorm folded.  Replaces the ONNX parse + TensorRT
  * engine build of HFNetRTModel::LoadHFNetTRModel (src/Extractors/HFNetRTModel.cc:208-254). */
 int hfb_load_weights(hfb_ctx* ctx, const void* blob, size_t nbytes);

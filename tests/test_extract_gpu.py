@@ -144,3 +144,21 @@ def test_errors_are_loud(native_lib, weights_blob):
             ctx.load_weights(b"garbage" * 10)
         out = ctx.extract(np.zeros((64, 64), np.uint8), [0], 0.01)         # zero budget is legal
         assert out["x"].size == 0
+
+
+def test_pinned_zero_copy_path_equals_staged_path(ctx_euroc, oracle_euroc):
+    """Frames / outputs in page-locked memory (hfb_host_alloc) are DMA'd in place; results must be identical."""
+    from hfnet_slam_b200.lib import pinned_empty
+    img, _ = oracle_euroc
+    img2 = weights.synthetic_image(480, 752, seed=9)
+    staged = ctx_euroc.extract_batch([img, img2], [1000], 0.01)
+    pin = []
+    for im in (img, img2):
+        p = pinned_empty(im.shape, np.uint8)
+        p[...] = im
+        pin.append(p)
+    direct, block = ctx_euroc.extract_batch(pin, [1000], 0.01, return_block=True, pinned=True)
+    for a, b in zip(staged, direct):
+        for k in ("x", "y", "response", "octave", "descriptors", "global_descriptor"):
+            assert np.array_equal(a[k], b[k]), k
+    assert block["descriptors"].shape == (2, 1000, 256)
