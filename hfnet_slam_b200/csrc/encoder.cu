@@ -125,6 +125,82 @@ __global__ void dw3x3_kernel(const __half* __restrict__ in, int Hi, int Wi, int 
   *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + cg * 8) = q;
 }
 
+// ----------------------------------------------------------------------------------------------- layer_2
+// Block without an expand convolution (layer_2: depthwise 3x3 on 24 channels -> 1x1 project to 16, hf_net.py:32-34):
+// far too little contraction work for a tensor-core tile, so one thread does one output pixel end to end on the CUDA
+// cores: depthwise (+bias, ReLU6) for all C channels in registers, then the C x Cout projection (+bias) out of
+// shared-memory weights, one contiguous Cout*2-byte store.  HBM traffic = input + output only.
+template <int C, int COUT>
+__global__ void __launch_bounds__(128) dw_project_small_kernel(const __half* __restrict__ in, int H, int W,
+                                                               const float* __restrict__ wd,
+                                                               const float* __restrict__ bd,
+                                                               const __half* __restrict__ wp,   // [COUT][C] fp16
+                                                               const float* __restrict__ bp, __half* __restrict__ out,
+                                                               long long total) {
+  __shared__ float s_wd[9 * C + C];
+  __shared__ float s_wp[C * COUT + COUT];   // [c][o] for conflict-free broadcast reads
+  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) s_wd[i] = i < 9 * C ? __ldg(wd + i) : __ldg(bd + i - 9 * C);
+  for (int i = threadIdx.x; i < C * COUT; i += blockDim.x) {
+    const int c = i / COUT, o = i - c * COUT;
+    s_wp[i] = __half2float(wp[(size_t)o * C + c]);
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_wp[C * COUT + i] = __ldg(bp + i);
+  __syncthreads();
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  long long p = gid;
+  const int x = (int)(p % W);
+  p /= W;
+  const int y = (int)(p % H);
+  const int b = (int)(p / H);
+  const __half* src = in + (size_t)b * H * W * C;
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = s_wd[9 * C + c];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = y + ky - 1;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = x + kx - 1;
+      if (ix < 0 || ix >= W) continue;
+      const uint4* q = reinterpret_cast<const uint4*>(src + ((size_t)iy * W + ix) * C);
+#pragma unroll
+      for (int u = 0; u < C / 8; ++u) {
+        const uint4 v = __ldg(q + u);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(hv[k]);
+          acc[u * 8 + 2 * k] = fmaf(f.x, s_wd[(ky * 3 + kx) * C + u * 8 + 2 * k], acc[u * 8 + 2 * k]);
+          acc[u * 8 + 2 * k + 1] = fmaf(f.y, s_wd[(ky * 3 + kx) * C + u * 8 + 2 * k + 1], acc[u * 8 + 2 * k + 1]);
+        }
+      }
+    }
+  }
+  // the depthwise output is rounded to fp16 like the stored activation of the three-kernel path
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = __half2float(__float2half_rn(fminf(fmaxf(acc[c], 0.f), 6.f)));
+  float o[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) o[j] = s_wp[C * COUT + j];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) o[j] = fmaf(acc[c], s_wp[c * COUT + j], o[j]);
+  }
+  __half* dst = out + (size_t)gid * COUT;
+#pragma unroll
+  for (int u = 0; u < COUT / 8; ++u) {
+    uint4 q;
+    __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hq[k] = __floats2half2_rn(o[u * 8 + 2 * k], o[u * 8 + 2 * k + 1]);
+    *reinterpret_cast<uint4*>(dst + u * 8) = q;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------- NetVLAD
 // (1) memberships: 1x1 conv D -> C + folded BN, softmax over clusters (layers.py:66-71).  One CTA = 32 pixels staged in
 //     shared memory; warp = 4 pixels, lane = cluster (C <= 64: two passes of 32).
@@ -528,6 +604,13 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
     const __half* dw_in = in;
     const long long Min = (long long)B * bp.Hi * bp.Wi, Mout = (long long)B * bp.Ho * bp.Wo;
     const std::string ln = "l" + std::to_string(bw.layer);
+    if (!bw.has_expand && bw.stride == 1 && !bw.residual && bw.cexp == 24 && bw.cout == 16) {
+      ctx->note(ln + ".dw+project", 2.0 * Min * bw.cin + 2.0 * Mout * bw.cout, 2.0 * Mout * bw.cexp * (9 + bw.cout));
+      dw_project_small_kernel<24, 16><<<(unsigned)((Mout + 127) / 128), 128, 0, ctx->stream>>>(
+          in, bp.Hi, bp.Wi, bw.wd, bw.bd, bw.project.w, bw.project.b, lv.act[bw.layer], Mout);
+      HFB_CHECK_LAUNCH(ctx, "dw_project_small");
+      continue;
+    }
     // one fused kernel per block when there are enough tiles to fill the machine; tiny late layers (15 x 24 pixels)
     // run faster as three small launches
     if (bp.fused && fused_block_tiles(*bp.fused, B) >= ctx->n_sm) {
