@@ -267,12 +267,16 @@ def main_gpu(args):
         roof = {"bound": "tensor", "achieved": fl / t_s / 1e12, "peak": pk["tf"], "unit": "TFLOP/s", "frac": frac_t}
     else:
         roof = {"bound": "hbm", "achieved": by / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": frac_h}
-    roof.update({"traffic": None, "kernel": name, "ms_per_launch": a["ms"] / a["n"], "share_of_step": a["ms"] / total_ms,
+    traffic = None
+    tp = ROOT / "profiles" / "ncu_traffic.json"      # dram__bytes_read+write per launch from the committed ncu --set full capture
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get(name, {}).get("dram_bytes_per_launch")
+    roof.update({"traffic": traffic, "kernel": name, "ms_per_launch": a["ms"] / a["n"], "share_of_step": a["ms"] / total_ms,
                  "peak_source": pk["src"], "algorithmic_bytes": by, "algorithmic_flops": fl})
     kernels = sorted(({"name": k, "ms": v["ms"], "share": v["ms"] / total_ms,
                        "hbm_frac": (v["bytes"] / (v["ms"] / 1e3) / 1e9 / pk["hbm"]) if v["ms"] > 0 else 0,
                        "tensor_frac": (v["flops"] / (v["ms"] / 1e3) / 1e12 / pk["tf"]) if v["ms"] > 0 else 0}
-                      for k, v in agg.items()), key=lambda r: -r["ms"])[:12]
+                      for k, v in agg.items()), key=lambda r: -r["ms"])
 
     extra = {"keypoints_frame0": int(len(f0["x"])), "matches_frame0": int((midx >= 0).sum()),
              "host_matches_frame0": int((hidx[:cnt[0]] >= 0).sum()), "ungraphed_step_ms": total_ms, "kernels": kernels}

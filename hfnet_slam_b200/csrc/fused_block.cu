@@ -395,7 +395,10 @@ int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half
   if (g.w_total_bytes >= (1u << 20)) return HFB_ERR_CAPACITY;   // mbarrier tx-count limit
   auto al = [](uint32_t v) { return (v + 1023u) & ~1023u; };
   const uint32_t budget = 200 * 1024;
-  for (g.TH = 8; g.TH >= 4; g.TH >>= 1) {
+  // 8 x 16 tiles, or 4 x 16 when the halo tile would not fit in shared memory or when the taller tiles cannot give
+  // every SM at least two tiles (small late layers)
+  const int th0 = (g.tiles_x * ((Ho + 7) / 8) * Bmax < 2 * ctx->n_sm) ? 4 : 8;
+  for (g.TH = th0; g.TH >= 4; g.TH >>= 1) {
     g.tiles_y = (Ho + g.TH - 1) / g.TH;
     g.IH = (g.TH - 1) * bw.stride + 3;
     g.IW_ = 15 * bw.stride + 3;
