@@ -47,6 +47,9 @@
     if (_s != HFB_OK) return _s;                                                                 \
   } while (0)
 
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
 
@@ -136,6 +139,7 @@ struct hfb_ctx {
   size_t d_scratch_bytes = 0;
   void* d_io = nullptr;        // persistent device staging of the host-pointer matcher entry points
   size_t d_io_bytes = 0;
+  bool pdl = true;             // HFB_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
   bool fused_blocks = true;    // HFB_FUSED=0: inverted-residual blocks run as three kernels (expand, dw, project)
   bool trace = false;          // HFB_TRACE=1: host-side stage timings of the host-pointer calls on stderr
   std::vector<void*> allocs;
@@ -187,20 +191,41 @@ struct hfb_ctx {
   }
 };
 
+// Kernel launch with the programmatic-dependent-launch attribute (see tc.cuh).  Every kernel launched through this
+// helper calls pdl_wait() before touching data of earlier kernels.
+template <typename K, typename... Args>
+static inline void hfb_launch(hfb_ctx* ctx, K kernel, dim3 grid, dim3 block, size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = (ctx->pdl && !ctx->prof_on) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ---- launchers implemented in the individual .cu files ------------------------------------------------------
 // postproc.cu
-int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, int B);
+int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, int B, float threshold, u64* d_cand,
+               int* d_cand_count, int cand_cap);
 int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const float* d_descmap, int Hd, int Wd,
                          u64* d_cand, int* d_cand_count, int cand_cap, u64* d_sel, int* d_nsel, int n_keypoints,
                          float threshold, float level_scale, int level, int B, int kp_cap, float* d_x, float* d_y,
-                         float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow);
+                         float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow,
+                         bool candidates_ready);
 int launch_resize(hfb_ctx* ctx, const uint8_t* d_src, int sh, int sw, uint8_t* d_dst, int dh, int dw, const int* d_xi,
                   const short* d_xa, const int* d_yi, const short* d_ya, int B);
 void build_resize_tables(int sn, int dn, std::vector<int>& idx, std::vector<short>& coef);
 // encoder.cu
 int encoder_plan(hfb_ctx* ctx);
 void encoder_forget(hfb_ctx* ctx);
-int encoder_forward(hfb_ctx* ctx, int level, int B);
+int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold);
 // match.cu: pair_tab = device int[4][n_pairs] (a_off | a_cnt | b_off | b_cnt)
 int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB, int n_pairs, const int* d_pair_tab,
                        int max_a, int max_b, float thr, int* d_match_idx, float* d_match_val, int na_total,

@@ -97,6 +97,8 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   ctx->debug = dbg && dbg[0] == '1';
   const char* fu = getenv("HFB_FUSED");
   ctx->fused_blocks = !(fu && fu[0] == '0');   // default on; HFB_FUSED=0 keeps the three-kernel blocks
+  const char* pd = getenv("HFB_PDL");
+  ctx->pdl = !(pd && pd[0] == '0');
   const char* tr = getenv("HFB_TRACE");
   ctx->trace = tr && tr[0] == '1';
   const char* ng = getenv("HFB_NO_GRAPH");
@@ -394,11 +396,11 @@ static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, floa
       LevelPlan& pv = ctx->lv[l - 1];
       HFB_TRY(launch_resize(ctx, pv.d_img, pv.H, pv.W, lv.d_img, lv.H, lv.W, lv.d_xi, lv.d_xa, lv.d_yi, lv.d_ya, B));
     }
-    HFB_TRY(encoder_forward(ctx, l, B));
+    HFB_TRY(encoder_forward(ctx, l, B, threshold));
     HFB_TRY(launch_select_sample(ctx, lv.d_nms, lv.H8, lv.W8, lv.d_descmap, lv.H8 / 8, lv.W8 / 8, lv.d_cand,
                                  lv.d_cand_count, ctx->cand_cap, ctx->d_sel, ctx->d_nsel, n_per_level[l], threshold,
                                  lv.scale, l, B, ctx->kp_cap, ctx->d_kx, ctx->d_ky, ctx->d_kresp, ctx->d_koct,
-                                 ctx->d_kdesc, ctx->d_kcount, ctx->d_overflow));
+                                 ctx->d_kdesc, ctx->d_kcount, ctx->d_overflow, true));
   }
   return HFB_OK;
 }
@@ -642,7 +644,7 @@ extern "C" int hfb_nms(hfb_ctx* ctx, const float* scores, int32_t height, int32_
   float* d_in = reinterpret_cast<float*>(ctx->d_scratch);
   float* d_out = d_in + n;
   HFB_CUDA(ctx, cudaMemcpyAsync(d_in, scores, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-  HFB_TRY(launch_nms(ctx, d_in, d_out, height, width, 1));
+  HFB_TRY(launch_nms(ctx, d_in, d_out, height, width, 1, 0.f, nullptr, nullptr, 0));
   HFB_CUDA(ctx, cudaMemcpyAsync(scores_nms, d_out, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HFB_OK;
@@ -678,7 +680,7 @@ extern "C" int hfb_select_sample(hfb_ctx* ctx, const float* scores_nms, int32_t 
   HFB_CUDA(ctx, cudaMemsetAsync(d_k, 0, HFB_MAX_LEVELS * 4, ctx->stream));
   HFB_TRY(launch_select_sample(ctx, d_nms, height, width, d_dm, desc_h, desc_w, d_cand, d_cnt, cap, ctx->d_sel,
                                ctx->d_nsel, n_keypoints, threshold, 1.0f, 0, 1, 8192, d_x, d_y, d_r, d_o, d_d, d_k,
-                               ctx->d_overflow));
+                               ctx->d_overflow, false));
   int cnt = 0;
   HFB_CUDA(ctx, cudaMemcpyAsync(&cnt, d_k, 4, cudaMemcpyDeviceToHost, ctx->stream));
   HFB_TRY(check_overflow(ctx));

@@ -36,8 +36,10 @@ __global__ void __launch_bounds__(256) conv1_kernel(const uint8_t* __restrict__ 
                                                     __half* __restrict__ out, int Ho, int Wo, int pad_t, int pad_l,
                                                     long long total) {
   __shared__ float s_w[9 * CONV1_MAXC + CONV1_MAXC];
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < 10 * C1; i += blockDim.x) s_w[i] = i < 9 * C1 ? __ldg(w + i) : __ldg(bias + i - 9 * C1);
   __syncthreads();
+  pdl_wait();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   long long p = gid;
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(256) conv1_kernel(const uint8_t* __restrict__ 
 __global__ void dw3x3_kernel(const __half* __restrict__ in, int Hi, int Wi, int C, const float* __restrict__ w,
                              const float* __restrict__ bias, __half* __restrict__ out, int Ho, int Wo, int stride,
                              int pad_t, int pad_l, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const int groups = C >> 3;
@@ -139,6 +143,7 @@ __global__ void __launch_bounds__(128) dw_project_small_kernel(const __half* __r
                                                                long long total) {
   __shared__ float s_wd[9 * C + C];
   __shared__ float s_wp[C * COUT + COUT];   // [c][o] for conflict-free broadcast reads
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) s_wd[i] = i < 9 * C ? __ldg(wd + i) : __ldg(bd + i - 9 * C);
   for (int i = threadIdx.x; i < C * COUT; i += blockDim.x) {
     const int c = i / COUT, o = i - c * COUT;
@@ -146,6 +151,7 @@ __global__ void __launch_bounds__(128) dw_project_small_kernel(const __half* __r
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_wp[C * COUT + i] = __ldg(bp + i);
   __syncthreads();
+  pdl_wait();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   long long p = gid;
@@ -210,6 +216,8 @@ __global__ void __launch_bounds__(256) vlad_memberships_kernel(const __half* __r
                                                                const float* __restrict__ bias,
                                                                float* __restrict__ memb) {
   extern __shared__ __half s_x[];   // [VLAD_PIX][D]
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pix0 = blockIdx.x * VLAD_PIX;
@@ -272,6 +280,8 @@ __global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __res
                                                              int P, int D, int C, const float* __restrict__ clusters,
                                                              float* __restrict__ vlad) {
   extern __shared__ float s_m[];   // [P]
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x, b = blockIdx.y;
   const float* m = memb + (size_t)b * P * C + c;
   for (int p = threadIdx.x; p < P; p += blockDim.x) s_m[p] = __ldg(m + (size_t)p * C);
@@ -314,6 +324,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 //     (layers.py:89-90) and the L2-normalise at the top of the dimensionality reduction (layers.py:97).
 __global__ void vlad_normalize_kernel(const float* __restrict__ vlad, int C, int D, float* __restrict__ out) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const float* v = vlad + (size_t)b * C * D;
   float* o = out + (size_t)b * C * D;
@@ -347,6 +359,8 @@ __global__ void __launch_bounds__(256) fc_partial_kernel(const float* __restrict
                                                          const __half* __restrict__ w, int N, int k_per_split,
                                                          float* __restrict__ partial) {
   extern __shared__ float s_v[];  // [FC_BCH][k_per_split]
+  pdl_launch_dependents();
+  pdl_wait();
   const int ks = blockIdx.y;
   const int k0 = ks * k_per_split;
   const int kn = min(k_per_split, K - k0);
@@ -398,6 +412,8 @@ __global__ void __launch_bounds__(256) fc_finish_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, float* __restrict__ out,
                                                         float* __restrict__ ss_part) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
   float y = 0.f;
   if (n < N) {
@@ -412,6 +428,8 @@ __global__ void __launch_bounds__(256) fc_finish_kernel(const float* __restrict_
 
 // final tf.nn.l2_normalize of the 4096-d global descriptor (layers.py:108)
 __global__ void fc_norm_kernel(float* __restrict__ out, int N, const float* __restrict__ ss_part, int n_part) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   float tot = 0.f;
   for (int i = 0; i < n_part; ++i) tot += ss_part[b * n_part + i];
@@ -583,15 +601,15 @@ static int run_plain(hfb_ctx* ctx, const GemmPlan& gp, long long M, void* out, i
 }
 
 // Forward of one pyramid level for `B` frames whose u8 images are in lv.d_img.  Produces d_scores, d_nms (no
-// selection), d_descmap and (level 0) the global descriptors.
-int encoder_forward(hfb_ctx* ctx, int level, int B) {
+// selection beyond the threshold scan), d_descmap and (level 0) the global descriptors.
+int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
   const NetW& net = ctx->net;
   LevelPlan& lv = ctx->lv[level];
   LevelExec& le = execs(ctx)[level];
   {
     const long long total = (long long)B * le.H1 * le.W1;
     ctx->note("conv1", (double)B * lv.H8 * lv.W8 + (double)total * net.c1 * 2, 2.0 * 9 * total * net.c1);
-    conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+    hfb_launch(ctx, conv1_kernel, (unsigned)((total + 255) / 256), 256, 0, 
         lv.d_img, lv.H, lv.W, lv.H8, lv.W8, net.conv1_w, net.conv1_b, net.c1, lv.act[1], le.H1, le.W1, le.pad_t1,
         le.pad_l1, total);
     HFB_CHECK_LAUNCH(ctx, "conv1");
@@ -606,7 +624,7 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
     const std::string ln = "l" + std::to_string(bw.layer);
     if (!bw.has_expand && bw.stride == 1 && !bw.residual && bw.cexp == 24 && bw.cout == 16) {
       ctx->note(ln + ".dw+project", 2.0 * Min * bw.cin + 2.0 * Mout * bw.cout, 2.0 * Mout * bw.cexp * (9 + bw.cout));
-      dw_project_small_kernel<24, 16><<<(unsigned)((Mout + 127) / 128), 128, 0, ctx->stream>>>(
+      hfb_launch(ctx, dw_project_small_kernel<24, 16>, (unsigned)((Mout + 127) / 128), 128, 0, 
           in, bp.Hi, bp.Wi, bw.wd, bw.bd, bw.project.w, bw.project.b, lv.act[bw.layer], Mout);
       HFB_CHECK_LAUNCH(ctx, "dw_project_small");
       continue;
@@ -625,7 +643,7 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
     }
     const long long total = Mout * (bw.cexp / 8);
     ctx->note(ln + ".dw", 2.0 * (Min + Mout) * bw.cexp, 2.0 * 9 * Mout * bw.cexp);
-    dw3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+    hfb_launch(ctx, dw3x3_kernel, (unsigned)((total + 255) / 256), 256, 0, 
         dw_in, bp.Hi, bp.Wi, bw.cexp, bw.wd, bw.bd, lv.d_dw, bp.Ho, bp.Wo, bw.stride, bp.pad_t, bp.pad_l, total);
     HFB_CHECK_LAUNCH(ctx, "dw3x3");
     ctx->note(ln + ".project", 2.0 * Mout * (bw.cexp + bw.cout * (bw.residual ? 2 : 1)) + 2.0 * bw.cexp * bw.cout,
@@ -650,31 +668,31 @@ int encoder_forward(hfb_ctx* ctx, int level, int B) {
     HFB_TRY(gemm_softmax_d2s(ctx, le.det2.tmA, le.det2.tmB, gt, lv.d_scores, lv.d_logits, net.det2.b, le.Hd, le.Wd));
   }
   ctx->note("nms", 8.0 * B * lv.H8 * lv.W8, 0);
-  HFB_TRY(launch_nms(ctx, lv.d_scores, lv.d_nms, lv.H8, lv.W8, B));
+  HFB_TRY(launch_nms(ctx, lv.d_scores, lv.d_nms, lv.H8, lv.W8, B, threshold, lv.d_cand, lv.d_cand_count, ctx->cand_cap));
   if (lv.global) {
     const int C = net.n_clusters, K = C * le.D;
     dim3 g1(ceil_div(le.P, VLAD_PIX), B);
-    vlad_memberships_kernel<<<g1, 256, (size_t)VLAD_PIX * le.D * 2, ctx->stream>>>(lv.act[18], le.P, le.D, C, net.vlad_w,
+    hfb_launch(ctx, vlad_memberships_kernel, g1, 256, (size_t)VLAD_PIX * le.D * 2, lv.act[18], le.P, le.D, C, net.vlad_w,
                                                                                  net.vlad_b, lv.d_memb);
     HFB_CHECK_LAUNCH(ctx, "vlad_memberships");
     dim3 g2(C, B);
-    vlad_aggregate_kernel<<<g2, 256, (size_t)le.P * 4, ctx->stream>>>(lv.act[18], lv.d_memb, le.P, le.D, C, net.vlad_c,
+    hfb_launch(ctx, vlad_aggregate_kernel, g2, 256, (size_t)le.P * 4, lv.act[18], lv.d_memb, le.P, le.D, C, net.vlad_c,
                                                                      lv.d_vlad);
     HFB_CHECK_LAUNCH(ctx, "vlad_aggregate");
-    vlad_normalize_kernel<<<B, 256, 0, ctx->stream>>>(lv.d_vlad, C, le.D, lv.d_vladn);
+    hfb_launch(ctx, vlad_normalize_kernel, B, 256, 0, lv.d_vlad, C, le.D, lv.d_vladn);
     HFB_CHECK_LAUNCH(ctx, "vlad_normalize");
     dim3 g3(ceil_div(HFB_GLOBAL_DIM, 256 * 8), le.fc_split);
     const size_t smem = (size_t)FC_BCH * le.fc_kps * sizeof(float);
     ctx->note("global.fc", 2.0 * K * HFB_GLOBAL_DIM + 4.0 * B * K, 2.0 * B * K * HFB_GLOBAL_DIM);
-    fc_partial_kernel<<<g3, 256, smem, ctx->stream>>>(lv.d_vladn, K, B, net.fc_w, HFB_GLOBAL_DIM, le.fc_kps,
+    hfb_launch(ctx, fc_partial_kernel, g3, 256, smem, lv.d_vladn, K, B, net.fc_w, HFB_GLOBAL_DIM, le.fc_kps,
                                                       lv.d_fc_partial);
     HFB_CHECK_LAUNCH(ctx, "fc_partial");
     const int n_part = ceil_div(HFB_GLOBAL_DIM, 256);
     float* ss_part = lv.d_fc_partial + (size_t)ctx->cfg.max_batch * le.fc_split * HFB_GLOBAL_DIM;
-    fc_finish_kernel<<<dim3(n_part, B), 256, 0, ctx->stream>>>(lv.d_fc_partial, le.fc_split, HFB_GLOBAL_DIM, net.fc_b,
+    hfb_launch(ctx, fc_finish_kernel, dim3(n_part, B), 256, 0, lv.d_fc_partial, le.fc_split, HFB_GLOBAL_DIM, net.fc_b,
                                                                ctx->d_global, ss_part);
     HFB_CHECK_LAUNCH(ctx, "fc_finish");
-    fc_norm_kernel<<<dim3(n_part, B), 256, 0, ctx->stream>>>(ctx->d_global, HFB_GLOBAL_DIM, ss_part, n_part);
+    hfb_launch(ctx, fc_norm_kernel, dim3(n_part, B), 256, 0, ctx->d_global, HFB_GLOBAL_DIM, ss_part, n_part);
     HFB_CHECK_LAUNCH(ctx, "fc_norm");
   }
   return HFB_OK;

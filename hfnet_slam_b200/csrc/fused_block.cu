@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  tc::pdl_launch_dependents();
 
   if (tid == 0) {
     tc::prefetch_tmap(&tmWE);
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  tc::pdl_wait();   // everything above touched only weights / on-chip state; the input tensor is the predecessor's output
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base + (uint32_t)(g.MT * g.CW);
   const uint32_t idesc_p = tc::make_idesc_f16(g.cout_pad);
@@ -448,10 +450,10 @@ int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const _
   g.total_tiles = g.tiles_x * g.tiles_y * B;
   const int grid = std::min(g.total_tiles, ctx->n_sm * fp.ctas_per_sm);
   if (g.stride == 1)
-    fused_block_kernel<1><<<grid, FB_THREADS, g.smem_bytes, ctx->stream>>>(fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
+    hfb_launch(ctx, fused_block_kernel<1>, grid, FB_THREADS, g.smem_bytes, fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
                                                                           bw.bd, bw.project.b, out);
   else
-    fused_block_kernel<2><<<grid, FB_THREADS, g.smem_bytes, ctx->stream>>>(fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
+    hfb_launch(ctx, fused_block_kernel<2>, grid, FB_THREADS, g.smem_bytes, fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
                                                                           bw.bd, bw.project.b, out);
   HFB_CHECK_LAUNCH(ctx, "fused_block");
   return HFB_OK;

@@ -270,7 +270,7 @@ static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
   }
   if (g.total_tiles <= 0) return HFB_OK;
   const int grid = gemm_grid(g, ctx->n_sm, smem);
-  gemm_tc_kernel<Epi><<<grid, GEMM_THREADS(Epi::kWarps), smem, ctx->stream>>>(tmA, tmB, g, ep);
+  hfb_launch(ctx, gemm_tc_kernel<Epi>, grid, GEMM_THREADS(Epi::kWarps), smem, tmA, tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, what);
   return HFB_OK;
 }

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(Epi::kWarps)) gemm_tc_kernel(cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  tc::pdl_launch_dependents();
 
   if (tid == 0) {
     tc::prefetch_tmap(&tmA);
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(GEMM_THREADS(Epi::kWarps)) gemm_tc_kernel(cons
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  tc::pdl_wait();   // prologue done (barriers, TMEM, bias = weights only); operands / residuals come from predecessors
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {

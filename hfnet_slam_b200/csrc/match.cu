@@ -21,6 +21,8 @@
 // ---- prep: fp32 [n][256] -> fp16 [n][768] (A: hi|hi|lo, B: hi|lo|hi) and half squared norms -------------------
 __global__ void match_prep_kernel(const float* __restrict__ X, int n, __half* __restrict__ out, float* __restrict__ hn,
                                   int is_b, int l2_mode) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -116,6 +118,8 @@ __global__ void match_finalize_kernel(const float* __restrict__ A, const float* 
                                       const int* __restrict__ pair_tab, int n_pairs, int mode, float thr,
                                       int* __restrict__ match_idx, float* __restrict__ match_val,
                                       int* __restrict__ n_matches) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int pr = blockIdx.y;
   const int a_off = pair_tab[pr], a_cnt = pair_tab[n_pairs + pr], b_off = pair_tab[2 * n_pairs + pr];
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -195,9 +199,9 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
   HFB_CUDA(ctx, cudaMemsetAsync(rowbest, 0, szrb + szcb + sznm, ctx->stream));
 
   const int l2 = (mode == 0);
-  match_prep_kernel<<<ceil_div(na_total, 8), 256, 0, ctx->stream>>>(dA, na_total, A2, hna, 0, l2);
+  hfb_launch(ctx, match_prep_kernel, ceil_div(na_total, 8), 256, 0, dA, na_total, A2, hna, 0, l2);
   HFB_CHECK_LAUNCH(ctx, "match_prep(A)");
-  match_prep_kernel<<<ceil_div(nb_total, 8), 256, 0, ctx->stream>>>(dB, nb_total, B2, hnb, 1, l2);
+  hfb_launch(ctx, match_prep_kernel, ceil_div(nb_total, 8), 256, 0, dB, nb_total, B2, hnb, 1, l2);
   HFB_CHECK_LAUNCH(ctx, "match_prep(B)");
 
   CUtensorMap tmA, tmB;
@@ -219,11 +223,11 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
     configured = true;
   }
   EpiArgmax::Params ep{hna, hnb, rowbest, colbest};
-  gemm_tc_kernel<EpiArgmax><<<gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(4), smem, ctx->stream>>>(tmA, tmB, g, ep);
+  hfb_launch(ctx, gemm_tc_kernel<EpiArgmax>, gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(4), smem, tmA, tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, "match_gemm_argmax");
 
   dim3 fgrid(ceil_div(max_a, 8), n_pairs);
-  match_finalize_kernel<<<fgrid, 256, 0, ctx->stream>>>(dA, dB, rowbest, colbest, d_pair_tab, n_pairs, mode, thr,
+  hfb_launch(ctx, match_finalize_kernel, fgrid, 256, 0, dA, dB, rowbest, colbest, d_pair_tab, n_pairs, mode, thr,
                                                         d_match_idx, d_match_val, nm);
   HFB_CHECK_LAUNCH(ctx, "match_finalize");
   if (d_n_matches_out) *d_n_matches_out = nm;

@@ -63,13 +63,18 @@ __device__ __forceinline__ void colmax_pass(const float (*src)[NMS_P], int r0, i
   }
 }
 
+// With cand != null the kernel also performs the reference's threshold scan (HFNetRTModel.cc:150-168) on its own
+// output: every surviving pixel with score >= threshold is appended as a (score, scan index) key.
 __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H,
-                                                  int W) {
+                                                  int W, float threshold, u64* __restrict__ cand,
+                                                  int* __restrict__ cand_count, int cand_cap) {
   __shared__ float sS[NMS_AH][NMS_P];   // scores, -inf outside the image
   __shared__ float sT[NMS_AH][NMS_P];   // row-pass scratch
   __shared__ float sM[NMS_AH][NMS_P];   // max_mask (1/0) on region B, later s' on region C
   __shared__ unsigned char sSupp[NMS_AH][NMS_AW];
   __shared__ unsigned char sKeep[NMS_TH][NMS_TW];   // max_mask of the tile pixels
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
   const float* src = scores + (size_t)blockIdx.z * H * W;
@@ -111,13 +116,22 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
     if (y >= H || x >= W) return;
     const bool is_new = (sM[r][c] == m);
     const bool mx = sKeep[r - 12][c - 12] || (is_new && !sSupp[r][c]);
-    dst[(size_t)y * W + x] = mx ? sS[r][c] : 0.f;
+    const float v = mx ? sS[r][c] : 0.f;
+    dst[(size_t)y * W + x] = v;
+    if (cand && v >= threshold) {
+      const int pos = atomicAdd(cand_count + blockIdx.z, 1);
+      if (pos < cand_cap)
+        cand[(size_t)blockIdx.z * cand_cap + pos] =
+            ((u64)f2ord(v) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(x * H + y));
+    }
   });
 }
 
-int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, int B) {
+int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, int B, float threshold, u64* d_cand,
+               int* d_cand_count, int cand_cap) {
+  if (d_cand) HFB_CUDA(ctx, cudaMemsetAsync(d_cand_count, 0, sizeof(int) * B, ctx->stream));
   dim3 grid(ceil_div(W, NMS_TW), ceil_div(H, NMS_TH), B);
-  nms_kernel<<<grid, 256, 0, ctx->stream>>>(d_scores, d_out, H, W);
+  hfb_launch(ctx, nms_kernel, grid, 256, 0, d_scores, d_out, H, W, threshold, d_cand, d_cand_count, cand_cap);
   HFB_CHECK_LAUNCH(ctx, "nms");
   return HFB_OK;
 }
@@ -151,6 +165,8 @@ __global__ void __launch_bounds__(1024) select_topk_kernel(const u64* __restrict
   __shared__ int s_hist[256];
   __shared__ u64 s_prefix;
   __shared__ int s_remaining, s_fill;
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   int n = count[b];
   if (n > cap) {
@@ -251,6 +267,8 @@ __global__ void sample_kernel(const u64* __restrict__ sel, const int* __restrict
                               int level, const int* __restrict__ kcount_prev, int kp_cap, float* __restrict__ ox,
                               float* __restrict__ oy, float* __restrict__ oresp, int* __restrict__ ooct,
                               float* __restrict__ odesc, int* __restrict__ kcount_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int kp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -323,12 +341,15 @@ __global__ void sample_kernel(const u64* __restrict__ sel, const int* __restrict
 int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const float* d_descmap, int Hd, int Wd,
                          u64* d_cand, int* d_cand_count, int cand_cap, u64* d_sel, int* d_nsel, int n_keypoints,
                          float threshold, float level_scale, int level, int B, int kp_cap, float* d_x, float* d_y,
-                         float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow) {
+                         float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow,
+                         bool candidates_ready) {
   HFB_REQUIRE(ctx, n_keypoints >= 0 && n_keypoints <= SELECT_KMAX, "keypoint budget exceeds SELECT_KMAX (8192)");
-  HFB_CUDA(ctx, cudaMemsetAsync(d_cand_count, 0, sizeof(int) * B, ctx->stream));
-  dim3 g1(ceil_div(H * W, 256), B);
-  select_compact_kernel<<<g1, 256, 0, ctx->stream>>>(d_nms, H, W, threshold, d_cand, d_cand_count, cand_cap);
-  HFB_CHECK_LAUNCH(ctx, "select_compact");
+  if (!candidates_ready) {   // the in-graph NMS kernel already scanned its own output otherwise
+    HFB_CUDA(ctx, cudaMemsetAsync(d_cand_count, 0, sizeof(int) * B, ctx->stream));
+    dim3 g1(ceil_div(H * W, 256), B);
+    select_compact_kernel<<<g1, 256, 0, ctx->stream>>>(d_nms, H, W, threshold, d_cand, d_cand_count, cand_cap);
+    HFB_CHECK_LAUNCH(ctx, "select_compact");
+  }
   int P = 1;
   while (P < n_keypoints) P <<= 1;
   const size_t smem = (size_t)P * 8;
@@ -337,18 +358,18 @@ int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const f
     HFB_CUDA(ctx, cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  select_topk_kernel<<<B, 1024, smem, ctx->stream>>>(d_cand, d_cand_count, cand_cap, n_keypoints, d_sel, d_nsel,
+  hfb_launch(ctx, select_topk_kernel, B, 1024, smem, d_cand, d_cand_count, cand_cap, n_keypoints, d_sel, d_nsel,
                                                      SELECT_KMAX, d_overflow);
   HFB_CHECK_LAUNCH(ctx, "select_topk");
   if (n_keypoints > 0) {
     dim3 g2(ceil_div(n_keypoints, 8), B);
-    sample_kernel<<<g2, 256, 0, ctx->stream>>>(d_sel, d_nsel, SELECT_KMAX, d_descmap, H, W, Hd, Wd, level_scale, level,
+    hfb_launch(ctx, sample_kernel, g2, 256, 0, d_sel, d_nsel, SELECT_KMAX, d_descmap, H, W, Hd, Wd, level_scale, level,
                                                d_kcount, kp_cap, d_x, d_y, d_resp, d_oct, d_desc, d_kcount);
     HFB_CHECK_LAUNCH(ctx, "sample");
   } else {
     // budget 0: still publish the count
     dim3 g2(1, B);
-    sample_kernel<<<g2, 32, 0, ctx->stream>>>(d_sel, d_nsel, SELECT_KMAX, d_descmap, H, W, Hd, Wd, level_scale, level,
+    hfb_launch(ctx, sample_kernel, g2, 32, 0, d_sel, d_nsel, SELECT_KMAX, d_descmap, H, W, Hd, Wd, level_scale, level,
                                               d_kcount, kp_cap, d_x, d_y, d_resp, d_oct, d_desc, d_kcount);
     HFB_CHECK_LAUNCH(ctx, "sample");
   }
@@ -361,6 +382,8 @@ int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const f
 __global__ void resize_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh,
                               int dw, const int* __restrict__ xi, const short* __restrict__ xa,
                               const int* __restrict__ yi, const short* __restrict__ ya) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= dw) return;
   const uint8_t* s = src + (size_t)blockIdx.z * sh * sw;
@@ -394,7 +417,7 @@ void build_resize_tables(int sn, int dn, std::vector<int>& idx, std::vector<shor
 int launch_resize(hfb_ctx* ctx, const uint8_t* d_src, int sh, int sw, uint8_t* d_dst, int dh, int dw, const int* d_xi,
                   const short* d_xa, const int* d_yi, const short* d_ya, int B) {
   dim3 grid(ceil_div(dw, 128), dh, B);
-  resize_kernel<<<grid, 128, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, d_xi, d_xa, d_yi, d_ya);
+  hfb_launch(ctx, resize_kernel, grid, 128, 0, d_src, sh, sw, d_dst, dh, dw, d_xi, d_xa, d_yi, d_ya);
   HFB_CHECK_LAUNCH(ctx, "resize");
   return HFB_OK;
 }
