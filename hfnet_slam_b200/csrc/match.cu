@@ -233,3 +233,247 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
   if (d_n_matches_out) *d_n_matches_out = nm;
   return HFB_OK;
 }
+
+
+// =====================================================================================================================
+// Windowed matching = the descriptor stage of Matcher::SearchByProjection (src/Matcher.cc:40-210, 1574-1721) and
+// Frame::GetFeaturesInArea (src/Frame.cc:659-725): for every projected map point, the K best frame features inside
+// its search window |x - u| < r, |y - v| < r with octave in [minLevel, maxLevel].  The full nq x nf contraction runs on
+// the tensor cores; the window is a predicate in the epilogue (no grid cells: the reference's cells only accelerate the
+// same predicate).  K = 4 sorted candidates per query let the caller replay the reference's sequential bookkeeping
+// (features claimed by earlier map points are skipped, best / second-best + level-aware ratio test) without any
+// descriptor arithmetic on the host.
+#define PROJ_K 4
+
+struct ProjRec {
+  float d[PROJ_K];   // half squared distance proxy (tile-local ranking key), ascending
+  int j[PROJ_K];     // feature index or -1
+};
+
+__device__ __forceinline__ void proj_insert(ProjRec& r, float d, int j) {
+  if (!(d < r.d[PROJ_K - 1])) return;   // strict '<' keeps the earlier feature on ties (Matcher.cc:98,109)
+  int pos = PROJ_K - 1;
+#pragma unroll
+  for (int k = PROJ_K - 1; k > 0; --k) {
+    if (d < r.d[k - 1]) {
+      r.d[k] = r.d[k - 1];
+      r.j[k] = r.j[k - 1];
+      pos = k - 1;
+    }
+  }
+  r.d[pos] = d;
+  r.j[pos] = j;
+}
+
+struct EpiProjTopK {
+  static constexpr int kWarps = 4;
+  struct Params {
+    const float* hnq;      // [nq] 0.5*|q|^2
+    const float* hnf;      // [nf]
+    const float4* qwin;    // [nq] (u, v, r, unused)
+    const int2* qlev;      // [nq] (minLevel, maxLevel)
+    const float2* fxy;     // [nf]
+    const int* flevel;     // [nf]
+    const unsigned char* fskip;  // [nf] or null
+    ProjRec* rec;          // [n_tiles][nq]
+    int nq;
+  };
+  static __device__ __forceinline__ const float* bias(const Params&) { return nullptr; }
+  static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
+    __shared__ float s_fx[MATCH_BN], s_fy[MATCH_BN], s_hn[MATCH_BN];
+    __shared__ int s_lv[MATCH_BN];
+    const int lane = threadIdx.x & 31, et = tr.ewarp * 32 + lane;
+    const int ncols = min(g.BN, tr.n_cnt - tr.n0);
+    if (et < ncols) {
+      const int j = tr.n0 + et;
+      const float2 xy = __ldg(p.fxy + j);
+      s_fx[et] = xy.x;
+      s_fy[et] = xy.y;
+      s_hn[et] = __ldg(p.hnf + j);
+      s_lv[et] = (p.fskip && p.fskip[j]) ? -1000000 : __ldg(p.flevel + j);   // skipped features fail every level test
+    }
+    epi_bar_sync();
+    ProjRec best;
+#pragma unroll
+    for (int k = 0; k < PROJ_K; ++k) {
+      best.d[k] = 3.0e38f;
+      best.j[k] = -1;
+    }
+    float4 win = make_float4(0.f, 0.f, -1.f, 0.f);
+    int2 lev = make_int2(0, -1);
+    float hq = 0.f;
+    if (tr.valid) {
+      win = __ldg(p.qwin + tr.row);
+      lev = __ldg(p.qlev + tr.row);
+      hq = __ldg(p.hnq + tr.row);
+    }
+    for (int c0 = 0; c0 < g.BN; c0 += 16) {
+      uint32_t r[16];
+      tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
+      tc::tmem_ld_wait();
+      if (c0 >= ncols || !tr.valid) continue;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const int c = c0 + jj;
+        if (c >= ncols) break;
+        const int lv = s_lv[c];
+        const bool in_win = fabsf(s_fx[c] - win.x) < win.z && fabsf(s_fy[c] - win.y) < win.z && lv >= lev.x &&
+                            (lev.y < 0 || lv <= lev.y) && lv > -1000000;
+        if (in_win) proj_insert(best, hq + s_hn[c] - __uint_as_float(r[jj]), tr.n0 + c);
+      }
+    }
+    if (tr.valid) p.rec[(size_t)(tr.n0 / g.BN) * p.nq + tr.row] = best;
+    epi_bar_sync();
+  }
+};
+
+// merge the per-tile lists (ascending tile = ascending feature index), then exact fp32 distances of the K survivors
+__global__ void proj_finalize_kernel(const float* __restrict__ Q, const float* __restrict__ F, const ProjRec* __restrict__ rec,
+                                     int n_tiles, int nq, const int* __restrict__ flevel, int* __restrict__ cand_idx,
+                                     float* __restrict__ cand_dist, int* __restrict__ cand_level) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= nq) return;
+  ProjRec best;
+#pragma unroll
+  for (int k = 0; k < PROJ_K; ++k) {
+    best.d[k] = 3.0e38f;
+    best.j[k] = -1;
+  }
+  for (int t = 0; t < n_tiles; ++t) {
+    const ProjRec r = rec[(size_t)t * nq + i];
+#pragma unroll
+    for (int k = 0; k < PROJ_K; ++k)
+      if (r.j[k] >= 0) proj_insert(best, r.d[k], r.j[k]);
+  }
+  const float4* q = reinterpret_cast<const float4*>(Q + (size_t)i * 256) + lane * 2;
+  const float4 q0 = __ldg(q), q1 = __ldg(q + 1);
+  float dist[PROJ_K];
+#pragma unroll
+  for (int k = 0; k < PROJ_K; ++k) {
+    float acc = 0.f;
+    if (best.j[k] >= 0) {
+      const float4* f = reinterpret_cast<const float4*>(F + (size_t)best.j[k] * 256) + lane * 2;
+      const float4 f0 = __ldg(f), f1 = __ldg(f + 1);
+      float d;
+      d = q0.x - f0.x; acc = d * d;
+      d = q0.y - f0.y; acc = fmaf(d, d, acc);
+      d = q0.z - f0.z; acc = fmaf(d, d, acc);
+      d = q0.w - f0.w; acc = fmaf(d, d, acc);
+      d = q1.x - f1.x; acc = fmaf(d, d, acc);
+      d = q1.y - f1.y; acc = fmaf(d, d, acc);
+      d = q1.z - f1.z; acc = fmaf(d, d, acc);
+      d = q1.w - f1.w; acc = fmaf(d, d, acc);
+    }
+#pragma unroll
+    for (int s2 = 16; s2 > 0; s2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s2);
+    dist[k] = sqrtf(acc);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < PROJ_K; ++k) {
+      const int j = best.j[k];
+      cand_idx[(size_t)i * PROJ_K + k] = j;
+      cand_dist[(size_t)i * PROJ_K + k] = j >= 0 ? dist[k] : 3.402823466e38f;
+      cand_level[(size_t)i * PROJ_K + k] = j >= 0 ? __ldg(flevel + j) : -1;
+    }
+  }
+}
+
+__global__ void proj_pack_kernel(const float* __restrict__ uv, const float* __restrict__ radius, const int* __restrict__ minl,
+                                 const int* __restrict__ maxl, int nq, float4* __restrict__ qwin, int2* __restrict__ qlev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  qwin[i] = make_float4(uv[2 * i], uv[2 * i + 1], radius[i], 0.f);
+  qlev[i] = make_int2(minl[i], maxl[i]);
+}
+
+extern "C" int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, const float* q_uv, const float* q_radius,
+                                    const int32_t* q_min_level, const int32_t* q_max_level, const float* F, int32_t nf,
+                                    const float* f_xy, const int32_t* f_level, const uint8_t* f_skip, int32_t* cand_idx,
+                                    float* cand_dist, int32_t* cand_level) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, nq >= 0 && nf >= 0, "negative size");
+  HFB_REQUIRE(ctx, cand_idx && cand_dist && cand_level, "null output");
+  for (long long i = 0; i < (long long)nq * PROJ_K; ++i) {
+    cand_idx[i] = -1;
+    cand_dist[i] = 3.402823466e38f;
+    cand_level[i] = -1;
+  }
+  if (nq == 0 || nf == 0) return HFB_OK;
+  HFB_REQUIRE(ctx, Q && q_uv && q_radius && q_min_level && q_max_level && F && f_xy && f_level, "null input");
+  auto al = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
+  const int n_tiles = ceil_div(nf, MATCH_BN);
+  // io block: Q | F | uv | r | minl | maxl | fxy | flevel | fskip | cand_idx | cand_dist | cand_level
+  const size_t oQ = 0, oF = oQ + al((size_t)nq * 1024), o_uv = oF + al((size_t)nf * 1024), o_r = o_uv + al((size_t)nq * 8),
+               o_mn = o_r + al((size_t)nq * 4), o_mx = o_mn + al((size_t)nq * 4), o_fxy = o_mx + al((size_t)nq * 4),
+               o_fl = o_fxy + al((size_t)nf * 8), o_fs = o_fl + al((size_t)nf * 4), o_ci = o_fs + al((size_t)nf),
+               o_cd = o_ci + al((size_t)nq * PROJ_K * 4), o_cl = o_cd + al((size_t)nq * PROJ_K * 4),
+               io_total = o_cl + al((size_t)nq * PROJ_K * 4);
+  HFB_TRY(ctx->ensure_io(io_total));
+  uint8_t* io = reinterpret_cast<uint8_t*>(ctx->d_io);
+  cudaStream_t st = ctx->stream;
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + oQ, Q, (size_t)nq * 1024, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + oF, F, (size_t)nf * 1024, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_uv, q_uv, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_r, q_radius, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_mn, q_min_level, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_mx, q_max_level, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fxy, f_xy, (size_t)nf * 8, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fl, f_level, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  if (f_skip) HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fs, f_skip, (size_t)nf, cudaMemcpyHostToDevice, st));
+  // scratch: Q' | F' | hnq | hnf | qwin | qlev | records
+  const size_t sQ = 0, sF = sQ + al((size_t)nq * MATCH_K * 2), s_hq = sF + al((size_t)nf * MATCH_K * 2),
+               s_hf = s_hq + al((size_t)nq * 4), s_qw = s_hf + al((size_t)nf * 4), s_ql = s_qw + al((size_t)nq * 16),
+               s_rec = s_ql + al((size_t)nq * 8), s_total = s_rec + al((size_t)n_tiles * nq * sizeof(ProjRec));
+  HFB_TRY(ctx->ensure_scratch(s_total));
+  uint8_t* sc = reinterpret_cast<uint8_t*>(ctx->d_scratch);
+  const float* dQ = reinterpret_cast<const float*>(io + oQ);
+  const float* dF = reinterpret_cast<const float*>(io + oF);
+  __half* Q2 = reinterpret_cast<__half*>(sc + sQ);
+  __half* F2 = reinterpret_cast<__half*>(sc + sF);
+  float* hnq = reinterpret_cast<float*>(sc + s_hq);
+  float* hnf = reinterpret_cast<float*>(sc + s_hf);
+  float4* qwin = reinterpret_cast<float4*>(sc + s_qw);
+  int2* qlev = reinterpret_cast<int2*>(sc + s_ql);
+  ProjRec* rec = reinterpret_cast<ProjRec*>(sc + s_rec);
+  hfb_launch(ctx, match_prep_kernel, ceil_div(nq, 8), 256, 0, dQ, nq, Q2, hnq, 0, 1);
+  HFB_CHECK_LAUNCH(ctx, "match_prep(Q)");
+  hfb_launch(ctx, match_prep_kernel, ceil_div(nf, 8), 256, 0, dF, nf, F2, hnf, 1, 1);
+  HFB_CHECK_LAUNCH(ctx, "match_prep(F)");
+  proj_pack_kernel<<<ceil_div(nq, 256), 256, 0, st>>>(reinterpret_cast<const float*>(io + o_uv),
+                                                    reinterpret_cast<const float*>(io + o_r),
+                                                    reinterpret_cast<const int*>(io + o_mn),
+                                                    reinterpret_cast<const int*>(io + o_mx), nq, qwin, qlev);
+  HFB_CHECK_LAUNCH(ctx, "proj_pack");
+  CUtensorMap tmA, tmB;
+  HFB_TRY(hfb_make_tmap_2d(ctx, &tmA, Q2, MATCH_K, (uint64_t)nq, MATCH_K * 2, 128));
+  HFB_TRY(hfb_make_tmap_2d(ctx, &tmB, F2, MATCH_K, (uint64_t)nf, MATCH_K * 2, MATCH_BN));
+  GemmGeom g;
+  gemm_fill_geom(g, nq, nf, MATCH_K, MATCH_BN, 0);
+  g.stages = 3;
+  g.epi_warp_bytes = 0;
+  g.bias_bytes = 0;
+  gemm_finish_geom(g, ceil_div(nq, 128));
+  const size_t smem = gemm_smem_bytes(g.BN, g.stages, 0);
+  static bool configured = false;
+  if (!configured) {
+    HFB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<EpiProjTopK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  EpiProjTopK::Params ep{hnq, hnf, qwin, qlev, reinterpret_cast<const float2*>(io + o_fxy),
+                         reinterpret_cast<const int*>(io + o_fl), f_skip ? io + o_fs : nullptr, rec, nq};
+  gemm_tc_kernel<EpiProjTopK><<<gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(4), smem, st>>>(tmA, tmB, g, ep);
+  HFB_CHECK_LAUNCH(ctx, "proj_gemm_topk");
+  hfb_launch(ctx, proj_finalize_kernel, ceil_div(nq, 8), 256, 0, dQ, dF, rec, n_tiles, nq,
+             reinterpret_cast<const int*>(io + o_fl), reinterpret_cast<int*>(io + o_ci),
+             reinterpret_cast<float*>(io + o_cd), reinterpret_cast<int*>(io + o_cl));
+  HFB_CHECK_LAUNCH(ctx, "proj_finalize");
+  HFB_CUDA(ctx, cudaMemcpyAsync(cand_idx, io + o_ci, (size_t)nq * PROJ_K * 4, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(cand_dist, io + o_cd, (size_t)nq * PROJ_K * 4, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(cand_level, io + o_cl, (size_t)nq * PROJ_K * 4, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaStreamSynchronize(st));
+  return HFB_OK;
+}

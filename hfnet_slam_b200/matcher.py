@@ -58,3 +58,31 @@ class Matcher:
             i = np.flatnonzero(idx[sl] >= 0)
             out.append((i.astype(np.int32), idx[sl][i], val[sl][i]))
         return out
+
+
+    def search_by_projection(self, mp_desc: np.ndarray, proj_uv: np.ndarray, radius: np.ndarray, min_level: np.ndarray,
+                             max_level: np.ndarray, frame_desc: np.ndarray, frame_xy: np.ndarray,
+                             frame_octave: np.ndarray, occupied=None, ratio: float = 0.8, th_high: float = TH_HIGH):
+        """Matcher::SearchByProjection(F, vpMapPoints, ratio, th) (src/Matcher.cc:40-210), descriptor + bookkeeping part:
+        map point i (descriptor, projection (u, v), window radius, octave range) is matched to the nearest unclaimed
+        frame feature in its window if best <= TH_HIGH and not (same octave as the second best and best > ratio *
+        second).  Map points are processed in order and claim their feature, exactly like the reference's loop; the
+        distances come from the GPU (top-4 candidates per map point), the claiming runs here.
+        Returns match[i] = feature index or -1."""
+        idx, dist, lvl = self.ctx.match_projection(mp_desc, proj_uv, radius, min_level, max_level, frame_desc, frame_xy,
+                                                   frame_octave, occupied)
+        taken = set()
+        out = np.full(idx.shape[0], -1, np.int32)
+        fmax = np.finfo(np.float32).max
+        for i in range(idx.shape[0]):
+            free = [(dist[i, k], lvl[i, k], idx[i, k]) for k in range(idx.shape[1]) if idx[i, k] >= 0 and int(idx[i, k]) not in taken]
+            if not free:
+                continue
+            bd, bl, bi = free[0]
+            sd, sl = (free[1][0], free[1][1]) if len(free) > 1 else (np.float32(fmax), -1)
+            if bd <= np.float32(th_high):
+                if bl == sl and bd > np.float32(ratio) * sd:
+                    continue
+                out[i] = bi
+                taken.add(int(bi))
+        return out

@@ -166,6 +166,19 @@ int hfb_match_batch_dev(hfb_ctx* ctx, int32_t mode, const float* dA_all, int32_t
                         int32_t nb_total, int32_t n_pairs, const int32_t* d_pair_tab, int32_t max_a_cnt,
                         int32_t max_b_cnt, float thr, int32_t* d_match_idx, float* d_match_val);
 
+/* Windowed matching: the descriptor stage of Matcher::SearchByProjection (src/Matcher.cc:40-210, 1574-1721) +
+ * Frame::GetFeaturesInArea (src/Frame.cc:659-725).  For every query (projected map point: descriptor, (u, v), window
+ * radius r, octave range [min_level, max_level], max_level < 0 = unbounded) the HFB_PROJ_TOPK = 4 nearest frame
+ * features with |x-u| < r, |y-v| < r, octave in range and f_skip[j] == 0, sorted by L2 distance (ties: lower index).
+ * Outputs are [nq][4]: feature index or -1, distance or FLT_MAX, octave or -1.  The caller replays the reference's
+ * sequential bookkeeping (skip features claimed by earlier map points, best / second + level-aware ratio test) on
+ * these lists; see hfnet_slam_b200/matcher.py. */
+#define HFB_PROJ_TOPK 4
+int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, const float* q_uv, const float* q_radius,
+                         const int32_t* q_min_level, const int32_t* q_max_level, const float* F, int32_t nf,
+                         const float* f_xy, const int32_t* f_level, const uint8_t* f_skip, int32_t* cand_idx,
+                         float* cand_dist, int32_t* cand_level);
+
 /* Tracking's frame-to-previous-frame descriptor association (the brute-force stage behind
  * Matcher::SearchByBoW / SearchForInitialization call sites, src/Tracking.cc:2030,1796) with the descriptors of the last
  * hfb_extract_batch* still resident in HBM: frame b is matched against frame (b-1) mod n_images.  No sync. */

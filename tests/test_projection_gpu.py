@@ -1,0 +1,98 @@
+"""Windowed matching: hfb_match_projection + Matcher.search_by_projection against a restatement of
+Matcher::SearchByProjection(F, MPs) (src/Matcher.cc:40-210) and Frame::GetFeaturesInArea (src/Frame.cc:659-725).
+Indices exact, distances within 2e-6."""
+import numpy as np
+import pytest
+
+from hfnet_slam_b200.matcher import Matcher
+from oracle import match_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(nq, nf, seed, W=752, H=480):
+    rng = np.random.default_rng(seed)
+    F = rng.normal(size=(nf, 256)).astype(np.float32)
+    F /= np.linalg.norm(F, axis=1, keepdims=True)
+    fxy = np.stack([rng.uniform(0, W, nf), rng.uniform(0, H, nf)], 1).astype(np.float32)
+    flev = rng.integers(0, 4, nf).astype(np.int32)
+    src = rng.integers(0, nf, nq)
+    Q = F[src] + 0.04 * rng.normal(size=(nq, 256)).astype(np.float32)
+    Q[nq // 2:] = rng.normal(size=(nq - nq // 2, 256))            # half the map points have no true partner
+    Q = (Q / np.linalg.norm(Q, axis=1, keepdims=True)).astype(np.float32)
+    uv = (fxy[src] + rng.normal(0, 3.0, (nq, 2))).astype(np.float32)
+    pred = flev[src].copy()
+    rad = (rng.uniform(4.0, 40.0, nq) * (1.2 ** pred)).astype(np.float32)
+    return Q, uv, rad, (pred - 1).astype(np.int32), pred.astype(np.int32), F, fxy, flev
+
+
+def _window(u, v, r, mn, mx, fxy, flev, skip=None):
+    """Frame::GetFeaturesInArea predicate (the grid cells only pre-filter it), ascending feature index."""
+    ok = (np.abs(fxy[:, 0] - u) < r) & (np.abs(fxy[:, 1] - v) < r) & (flev >= mn)
+    if mx >= 0:
+        ok &= flev <= mx
+    if skip is not None:
+        ok &= ~skip
+    return np.flatnonzero(ok)
+
+
+@pytest.mark.parametrize("nq,nf,seed", [(900, 1200, 0), (1, 1, 1), (300, 4000, 2), (130, 129, 3)])
+def test_top2_in_window_matches_oracle(small_ctx, nq, nf, seed):
+    Q, uv, rad, mn, mx, F, fxy, flev = _scene(nq, nf, seed)
+    idx, dist, lvl = small_ctx.match_projection(Q, uv, rad, mn, mx, F, fxy, flev)
+    ptr, cand = [0], []
+    for i in range(nq):
+        c = _window(uv[i, 0], uv[i, 1], rad[i], mn[i], mx[i], fxy, flev)
+        cand.extend(c.tolist())
+        ptr.append(len(cand))
+    bi, bd, bl, sd, sl = match_ref.best2_masked(Q, F, np.array(ptr), np.array(cand, np.int64), flev)
+    assert np.array_equal(idx[:, 0], bi), f"best index differs for rows {np.flatnonzero(idx[:, 0] != bi)[:8]}"
+    has = bi >= 0
+    assert np.abs(dist[has, 0] - bd[has]).max(initial=0) <= 2e-6 and np.array_equal(lvl[has, 0], bl[has])
+    has2 = sl >= 0
+    assert np.abs(dist[has2, 1] - sd[has2]).max(initial=0) <= 2e-6 and np.array_equal(lvl[has2, 1], sl[has2])
+    assert (idx[~has2, 1] == -1).all()
+    # lists are sorted and duplicate-free
+    d = np.where(idx >= 0, dist, np.inf)
+    assert (np.diff(d, axis=1) >= 0).all()
+    assert has.sum() > 0 or nq == 1
+
+
+def test_search_by_projection_sequential_claims(small_ctx):
+    Q, uv, rad, mn, mx, F, fxy, flev = _scene(700, 900, 5)
+    Q[10] = Q[3]; uv[10] = uv[3]; rad[10] = rad[3]; mn[10] = mn[3]; mx[10] = mx[3]      # two map points want one feature
+    occupied = np.zeros(900, bool); occupied[::17] = True                               # features that already have a map point
+    got = Matcher(small_ctx).search_by_projection(Q, uv, rad, mn, mx, F, fxy, flev, occupied=occupied, ratio=0.8)
+    # restatement of src/Matcher.cc:78-125 with the occupancy test of :84-86
+    taken = occupied.copy()
+    exp = np.full(700, -1, np.int32)
+    fmax = np.finfo(np.float32).max
+    for i in range(700):
+        bd, bl, bi, sd, sl = fmax, -1, -1, fmax, -1
+        for j in _window(uv[i, 0], uv[i, 1], rad[i], mn[i], mx[i], fxy, flev, skip=taken):
+            d = np.float32(np.sqrt(((Q[i].astype(np.float64) - F[j].astype(np.float64)) ** 2).sum()))
+            if d < bd:
+                sd, sl = bd, bl
+                bd, bl, bi = d, flev[j], j
+            elif d < sd:
+                sd, sl = d, flev[j]
+        if bd <= np.float32(0.75) and not (bl == sl and bd > np.float32(0.8) * sd):
+            exp[i] = bi
+            taken[bi] = True
+    assert np.array_equal(got, exp), f"rows {np.flatnonzero(got != exp)[:10]}"
+    assert got[3] >= 0 and got[10] != got[3]
+    assert (got >= 0).sum() > 100
+
+
+def test_projection_empty_and_no_window(small_ctx):
+    Q, uv, rad, mn, mx, F, fxy, flev = _scene(50, 60, 7)
+    idx, dist, lvl = small_ctx.match_projection(Q, uv, np.zeros(50, np.float32), mn, mx, F, fxy, flev)
+    assert (idx == -1).all()
+    idx, dist, lvl = small_ctx.match_projection(Q[:0], uv[:0], rad[:0], mn[:0], mx[:0], F, fxy, flev)
+    assert idx.shape == (0, 4)
+    idx, dist, lvl = small_ctx.match_projection(Q, uv, rad, mn, mx, F[:0], fxy[:0], flev[:0])
+    assert (idx == -1).all()
+    # unbounded max level (-1) and min level 0 == no level check
+    idx2, _, _ = small_ctx.match_projection(Q, uv, rad * 100, np.zeros(50, np.int32), -np.ones(50, np.int32), F, fxy, flev)
+    D = np.sqrt(((Q[:, None, :].astype(np.float64) - F[None].astype(np.float64)) ** 2).sum(-1))
+    assert np.array_equal(idx2[:, 0], D.argmin(1))
