@@ -202,13 +202,22 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
             if (r < g.R) {
               uint4 q[2];
               __half2* hq = reinterpret_cast<__half2*>(q);
+              if (in_img) {
+                // bias add in fp32, one rounding to fp16, then the ReLU6 clamp on packed halves (0 and 6 are exact in
+                // fp16 and rounding is monotonic, so clamp-after-round == round-after-clamp bit for bit)
+                const float4* bq = reinterpret_cast<const float4*>(s_be + c0 + cc);
+                const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float a = __uint_as_float(v[2 * i]) + s_be[c0 + cc + 2 * i];
-                float b = __uint_as_float(v[2 * i + 1]) + s_be[c0 + cc + 2 * i + 1];
-                a = in_img ? fminf(fmaxf(a, 0.f), 6.f) : 0.f;
-                b = in_img ? fminf(fmaxf(b, 0.f), 6.f) : 0.f;
-                hq[i] = __floats2half2_rn(a, b);
+                for (int i = 0; i < 4; ++i) {
+                  const float4 b4 = bq[i];
+                  __half2 h0 = __floats2half2_rn(__uint_as_float(v[4 * i]) + b4.x, __uint_as_float(v[4 * i + 1]) + b4.y);
+                  __half2 h1 = __floats2half2_rn(__uint_as_float(v[4 * i + 2]) + b4.z, __uint_as_float(v[4 * i + 3]) + b4.w);
+                  hq[2 * i] = __hmin2(__hmax2(h0, zero2), six2);
+                  hq[2 * i + 1] = __hmin2(__hmax2(h1, zero2), six2);
+                }
+              } else {
+                q[0] = make_uint4(0, 0, 0, 0);
+                q[1] = make_uint4(0, 0, 0, 0);
               }
               uint4* d = reinterpret_cast<uint4*>(sE + (size_t)r * g.e_pitch + (size_t)cc * 2);
               d[0] = q[0];
@@ -251,8 +260,11 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
       // pair p, p+64): the unit's 72 weights + 8 biases sit in registers for both pixels.
       {
         const int units = cw16 >> 3;
-        if (tid < 64 * units) {
-          const int u = tid >> 6, pb = tid & 63;
+        // 8 units: 64 pixel-pairs per unit; <= 4 units: one pixel per thread so that all 512 threads stay busy
+        const int shift = units > 4 ? 6 : 7;
+        const int pstep = 1 << shift;
+        if ((tid >> shift) < units) {
+          const int u = tid >> shift, pb = tid & (pstep - 1);
           float w[72], bias8[8];
           {
             const float4* bq = reinterpret_cast<const float4*>(s_bd + c0 + u * 8);
@@ -268,7 +280,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
             }
           }
           const int npix = g.TH * 16;
-          for (int p = pb; p < npix; p += 64) {
+          for (int p = pb; p < npix; p += pstep) {
             const int oy = p >> 4, ox = p & 15;
             float acc[8];
 #pragma unroll

@@ -53,7 +53,7 @@ def test_top2_in_window_matches_oracle(small_ctx, nq, nf, seed):
     assert np.abs(dist[has2, 1] - sd[has2]).max(initial=0) <= 2e-6 and np.array_equal(lvl[has2, 1], sl[has2])
     assert (idx[~has2, 1] == -1).all()
     # lists are sorted and duplicate-free
-    d = np.where(idx >= 0, dist, np.inf)
+    d = np.where(idx >= 0, dist.astype(np.float64), 1e30)
     assert (np.diff(d, axis=1) >= 0).all()
     assert has.sum() > 0 or nq == 1
 
