@@ -685,3 +685,361 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   }
   return HFB_OK;
 }
+
+
+// =====================================================================================================================
+// Optimizer::PoseOptimization (src/Optimizer.cc:814-1114), monocular branch, as ONE persistent single-CTA kernel: the
+// whole schedule -- 4 rounds x optimize(10) of Levenberg-Marquardt on one SE3 vertex with unary
+// EdgeSE3ProjectXYZOnlyPose edges (src/OptimizableTypes.cpp:49-64), Huber kernel dropped after the third round,
+// inlier re-classification with chi2 > 5.991 after every round -- runs on the device without a host round trip.
+// The problem is a few hundred edges: latency, not bandwidth, so everything (6x6 Cholesky, exp map) stays on chip.
+#define PO_THREADS 256
+#define PO_NV 28   // 21 upper-triangular H entries + 6 b entries + 1 robust chi2
+
+__device__ __forceinline__ void po_edge(const double* R, const double* t, const double* K, const double* Xw,
+                                        const double* obs, double is2, double& e0, double& e1, double& chi2, double& x,
+                                        double& y, double& z) {
+  x = R[0] * Xw[0] + R[1] * Xw[1] + R[2] * Xw[2] + t[0];
+  y = R[3] * Xw[0] + R[4] * Xw[1] + R[5] * Xw[2] + t[1];
+  z = R[6] * Xw[0] + R[7] * Xw[1] + R[8] * Xw[2] + t[2];
+  e0 = obs[0] - (K[0] * x / z + K[2]);
+  e1 = obs[1] - (K[1] * y / z + K[3]);
+  chi2 = is2 * (e0 * e0 + e1 * e1);
+}
+
+// fixed-order block reduction of NV doubles per thread; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void po_reduce(double (&v)[NV], double (*sh)[NV]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], s);
+  }
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[warp][i] = v[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double t = 0;
+      for (int w = 0; w < PO_THREADS / 32; ++w) t += sh[w][i];
+      v[i] = t;
+    }
+  }
+}
+
+__device__ void po_pose_oplus(const double* pose, const double* u, double* out) {
+  const double w0 = u[0], w1 = u[1], w2 = u[2];
+  const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+  const double Om[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+  double Om2[9], R[9], V[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Om2[3 * i + j] = Om[3 * i] * Om[j] + Om[3 * i + 1] * Om[3 + j] + Om[3 * i + 2] * Om[6 + j];
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; ++i) R[i] = I[i] + Om[i] + Om2[i];
+    for (int i = 0; i < 9; ++i) V[i] = R[i];
+  } else {
+    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta);
+    const double c = (theta - sin(theta)) / (theta * theta * theta);
+    for (int i = 0; i < 9; ++i) {
+      R[i] = I[i] + a * Om[i] + b * Om2[i];
+      V[i] = I[i] + b * Om[i] + c * Om2[i];
+    }
+  }
+  // Eigen Quaternion(Matrix3)
+  double qe[4];
+  double tr = R[0] + R[4] + R[8];
+  if (tr > 0) {
+    double t = sqrt(tr + 1.0);
+    qe[3] = 0.5 * t;
+    t = 0.5 / t;
+    qe[0] = (R[7] - R[5]) * t;
+    qe[1] = (R[2] - R[6]) * t;
+    qe[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    qe[i] = 0.5 * t;
+    t = 0.5 / t;
+    qe[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+    qe[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+    qe[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+  {
+    if (qe[3] < 0) for (int i = 0; i < 4; ++i) qe[i] = -qe[i];
+    const double nn = sqrt(qe[0] * qe[0] + qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3]);
+    for (int i = 0; i < 4; ++i) qe[i] /= nn;
+  }
+  const double te[3] = {V[0] * u[3] + V[1] * u[4] + V[2] * u[5], V[3] * u[3] + V[4] * u[4] + V[5] * u[5],
+                        V[6] * u[3] + V[7] * u[4] + V[8] * u[5]};
+  const double ax = qe[0], ay = qe[1], az = qe[2], aw = qe[3];
+  const double bx = pose[0], by = pose[1], bz = pose[2], bw = pose[3];
+  double q[4] = {aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                 aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz};
+  double Re[9];
+  quat_to_R(qe, Re);
+  const double* t = pose + 4;
+  out[4] = te[0] + Re[0] * t[0] + Re[1] * t[1] + Re[2] * t[2];
+  out[5] = te[1] + Re[3] * t[0] + Re[4] * t[1] + Re[5] * t[2];
+  out[6] = te[2] + Re[6] * t[0] + Re[7] * t[1] + Re[8] * t[2];
+  if (q[3] < 0) for (int i = 0; i < 4; ++i) q[i] = -q[i];
+  const double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) out[i] = q[i] / nn;
+}
+
+__device__ bool po_chol6(const double* Hu, double lambda, const double* b, double* x) {   // Hu: 21 upper-tri entries
+  double A[36];
+  int k = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) {
+      A[6 * i + j] = A[6 * j + i] = Hu[k++];
+    }
+  for (int i = 0; i < 6; ++i) A[7 * i] += lambda;
+  for (int j = 0; j < 6; ++j) {
+    double s = A[7 * j];
+    for (int q = 0; q < j; ++q) s -= A[6 * j + q] * A[6 * j + q];
+    if (!(s > 0.0) || !isfinite(s)) return false;
+    const double l = sqrt(s);
+    A[7 * j] = l;
+    for (int i = j + 1; i < 6; ++i) {
+      double t = A[6 * i + j];
+      for (int q = 0; q < j; ++q) t -= A[6 * i + q] * A[6 * j + q];
+      A[6 * i + j] = t / l;
+    }
+  }
+  for (int i = 0; i < 6; ++i) {
+    double t = b[i];
+    for (int q = 0; q < i; ++q) t -= A[6 * i + q] * x[q];
+    x[i] = t / A[7 * i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double t = x[i];
+    for (int q = i + 1; q < 6; ++q) t -= A[6 * q + i] * x[q];
+    x[i] = t / A[7 * i];
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const double* __restrict__ Xw,
+                                                              const double* __restrict__ obs,
+                                                              const double* __restrict__ invs2, const double* __restrict__ Kd,
+                                                              double delta, const double* __restrict__ pose0,
+                                                              double* __restrict__ cached, unsigned char* __restrict__ outlier,
+                                                              double* __restrict__ pose_out, int* __restrict__ stats) {
+  __shared__ double sh[PO_THREADS / 32][PO_NV];
+  __shared__ double s_pose[7], s_trial[7], s_x[6], s_b[6], s_Hu[21];
+  __shared__ double s_lambda, s_ni, s_cur, s_ini, s_rho;
+  __shared__ int s_ok, s_cont, s_stop, s_nbad_lm, s_qmax, s_trials, s_iters, s_nactive;
+  const int tid = threadIdx.x;
+  const double K[4] = {Kd[0], Kd[1], Kd[2], Kd[3]};
+  const double dsqr = delta * delta;
+  if (tid == 0) {
+    s_trials = 0;
+    s_iters = 0;
+  }
+  for (int e = tid; e < n; e += PO_THREADS) outlier[e] = 0;
+  __syncthreads();
+  int n_bad = 0;
+  for (int rnd = 0; rnd < 4; ++rnd) {
+    const bool robust = rnd < 3;
+    if (tid < 7) s_pose[tid] = pose0[tid];
+    if (tid == 0) {
+      s_lambda = 0;
+      s_ni = 2;
+      s_nbad_lm = 0;
+      s_stop = 0;
+    }
+    __syncthreads();
+    for (int it = 0; it < 10; ++it) {
+      // ---- computeActiveErrors + buildSystem at s_pose
+      double R[9];
+      quat_to_R(s_pose, R);
+      const double t3[3] = {s_pose[4], s_pose[5], s_pose[6]};
+      double v[PO_NV];
+#pragma unroll
+      for (int i = 0; i < PO_NV; ++i) v[i] = 0;
+      int nact = 0;
+      for (int e = tid; e < n; e += PO_THREADS) {
+        if (outlier[e]) continue;
+        ++nact;
+        double e0, e1, chi2, x, y, z;
+        po_edge(R, t3, K, Xw + 3 * e, obs + 2 * e, invs2[e], e0, e1, chi2, x, y, z);
+        cached[e] = chi2;
+        const bool inl = !robust || chi2 <= dsqr;
+        const double sq = sqrt(fmax(chi2, 1e-300));
+        v[27] += inl ? chi2 : 2 * sq * delta - dsqr;
+        const double wo = (inl ? 1.0 : delta / sq) * invs2[e];
+        const double iz = 1.0 / z, iz2 = 1.0 / (z * z);
+        const double a00 = -K[0] * iz, a02 = K[0] * x * iz2, a11 = -K[1] * iz, a12 = K[1] * y * iz2;
+        const double J0[6] = {a02 * y, a00 * z - a02 * x, -a00 * y, a00, 0, a02};
+        const double J1[6] = {-a11 * z + a12 * y, -a12 * x, a11 * x, 0, a11, a12};
+        const double r0 = -wo * e0, r1 = -wo * e1;
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+          for (int j = i; j < 6; ++j) v[k++] += wo * (J0[i] * J0[j] + J1[i] * J1[j]);
+          v[21 + i] += J0[i] * r0 + J1[i] * r1;
+        }
+      }
+      double cnt[1] = {(double)nact};
+      po_reduce<PO_NV>(v, sh);
+      __shared__ double sh1[PO_THREADS / 32][1];
+      po_reduce<1>(cnt, sh1);
+      if (tid == 0) {
+        s_nactive = (int)cnt[0];
+        for (int i = 0; i < 21; ++i) s_Hu[i] = v[i];
+        for (int i = 0; i < 6; ++i) s_b[i] = v[21 + i];
+        s_cur = v[27];
+        s_ini = v[27];
+        if (it == 0) {
+          double md = 0;
+          int k = 0;
+          for (int i = 0; i < 6; ++i) {
+            md = fmax(md, fabs(v[k]));
+            k += 6 - i;
+          }
+          s_lambda = 1e-5 * md;
+          s_ni = 2;
+          s_nbad_lm = 0;
+        }
+        s_qmax = 0;
+        s_rho = 0;
+      }
+      __syncthreads();
+      if (s_nactive == 0) break;
+      // ---- Levenberg trials
+      while (true) {
+        if (tid == 0) {
+          double x[6];
+          s_ok = po_chol6(s_Hu, s_lambda, s_b, x) ? 1 : 0;
+          if (!s_ok)
+            for (int i = 0; i < 6; ++i) x[i] = 0;
+          for (int i = 0; i < 6; ++i) s_x[i] = x[i];
+          po_pose_oplus(s_pose, x, s_trial);
+        }
+        __syncthreads();
+        double Rt[9];
+        quat_to_R(s_trial, Rt);
+        const double tt[3] = {s_trial[4], s_trial[5], s_trial[6]};
+        double c[1] = {0};
+        for (int e = tid; e < n; e += PO_THREADS) {
+          if (outlier[e]) continue;
+          double e0, e1, chi2, x, y, z;
+          po_edge(Rt, tt, K, Xw + 3 * e, obs + 2 * e, invs2[e], e0, e1, chi2, x, y, z);
+          cached[e] = chi2;
+          const bool inl = !robust || chi2 <= dsqr;
+          c[0] += inl ? chi2 : 2 * sqrt(fmax(chi2, 1e-300)) * delta - dsqr;
+        }
+        po_reduce<1>(c, sh1);
+        if (tid == 0) {
+          const double temp = s_ok ? c[0] : 1.7976931348623157e308;
+          double scale = 1e-3;
+          for (int i = 0; i < 6; ++i) scale += s_x[i] * (s_lambda * s_x[i] + s_b[i]);
+          const double rho = (s_cur - temp) / scale;
+          s_rho = rho;
+          ++s_trials;
+          if (rho > 0 && isfinite(temp)) {
+            double alpha = 1.0 - (2 * rho - 1) * (2 * rho - 1) * (2 * rho - 1);
+            alpha = fmin(alpha, 2.0 / 3.0);
+            s_lambda *= fmax(1.0 / 3.0, alpha);
+            s_ni = 2;
+            s_cur = temp;
+            for (int i = 0; i < 7; ++i) s_pose[i] = s_trial[i];
+          } else {
+            s_lambda *= s_ni;
+            s_ni *= 2;
+          }
+          ++s_qmax;
+          s_cont = (rho < 0 && s_qmax < 10) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_cont) break;
+      }
+      if (tid == 0) {
+        ++s_iters;
+        if (s_qmax == 10 || s_rho == 0) s_stop = 1;
+        else {
+          if ((s_ini - s_cur) * 1e3 < s_ini) ++s_nbad_lm;
+          else s_nbad_lm = 0;
+          if (s_nbad_lm >= 3) s_stop = 1;
+        }
+      }
+      __syncthreads();
+      if (s_stop) break;
+    }
+    // ---- classification: outliers are re-evaluated at the round's final pose, inliers keep the cached chi2
+    double R[9];
+    quat_to_R(s_pose, R);
+    const double t3[3] = {s_pose[4], s_pose[5], s_pose[6]};
+    double bad[1] = {0};
+    for (int e = tid; e < n; e += PO_THREADS) {
+      double chi2 = cached[e];
+      if (outlier[e]) {
+        double e0, e1, x, y, z;
+        po_edge(R, t3, K, Xw + 3 * e, obs + 2 * e, invs2[e], e0, e1, chi2, x, y, z);
+      }
+      const bool o = (float)chi2 > 5.991f;
+      outlier[e] = o ? 1 : 0;
+      bad[0] += o ? 1.0 : 0.0;
+    }
+    __shared__ double sh2[PO_THREADS / 32][1];
+    po_reduce<1>(bad, sh2);
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = (int)bad[0];
+    __syncthreads();
+    n_bad = s_bad;
+    if (n < 10) break;
+  }
+  if (tid < 7) pose_out[tid] = s_pose[tid];
+  if (tid == 0) {
+    stats[0] = n - n_bad;
+    stats[1] = s_trials;
+    stats[2] = s_iters;
+  }
+}
+
+extern "C" int hfb_pose_optimize(hfb_ctx* ctx, const float* K, const double* pose_in, int32_t n, const double* Xw,
+                                 const double* obs, const double* inv_sigma2, double* pose_out, uint8_t* outlier_out,
+                                 int32_t* n_inliers, int32_t* n_trials) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, K && pose_in && pose_out && n >= 0 && (n == 0 || (Xw && obs && inv_sigma2)), "bad argument");
+  if (n == 0) {
+    memcpy(pose_out, pose_in, 56);
+    if (n_inliers) *n_inliers = 0;
+    if (n_trials) *n_trials = 0;
+    return HFB_OK;
+  }
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t oX = 0, oO = oX + al((size_t)n * 24), oS = oO + al((size_t)n * 16), oK = oS + al((size_t)n * 8),
+               oP = oK + 256, oC = oP + 256, oF = oC + al((size_t)n * 8), oPo = oF + al((size_t)n), oSt = oPo + 256,
+               total = oSt + 256;
+  HFB_TRY(ctx->ensure_scratch(total));
+  uint8_t* a = reinterpret_cast<uint8_t*>(ctx->d_scratch);
+  cudaStream_t st = ctx->stream;
+  const double Kd[4] = {(double)K[0], (double)K[1], (double)K[2], (double)K[3]};
+  HFB_CUDA(ctx, cudaMemcpyAsync(a + oX, Xw, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(a + oO, obs, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(a + oS, inv_sigma2, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(a + oK, Kd, 32, cudaMemcpyHostToDevice, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(a + oP, pose_in, 56, cudaMemcpyHostToDevice, st));
+  pose_opt_kernel<<<1, PO_THREADS, 0, st>>>(n, (const double*)(a + oX), (const double*)(a + oO), (const double*)(a + oS),
+                                           (const double*)(a + oK), sqrt(5.991), (const double*)(a + oP),
+                                           (double*)(a + oC), a + oF, (double*)(a + oPo), (int*)(a + oSt));
+  HFB_CHECK_LAUNCH(ctx, "pose_opt");
+  int stats[3] = {0, 0, 0};
+  HFB_CUDA(ctx, cudaMemcpyAsync(pose_out, a + oPo, 56, cudaMemcpyDeviceToHost, st));
+  if (outlier_out) HFB_CUDA(ctx, cudaMemcpyAsync(outlier_out, a + oF, (size_t)n, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(stats, a + oSt, 12, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaStreamSynchronize(st));   // Kd / stats are stack variables: must not outlive this frame
+  if (n_inliers) *n_inliers = stats[0];
+  if (n_trials) *n_trials = stats[1];
+  return HFB_OK;
+}

@@ -103,6 +103,7 @@ SIGNATURES = {
     "hfb_kfdb_query_shard": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
     "hfb_lba_optimize": (C.c_int, [C.c_void_p, C.POINTER(hfb_lba_problem), C.c_int32, C.c_double, _u8p, _f64p, _f64p,
                                    _f64p, _u8p, C.POINTER(hfb_lba_stats)]),
+    "hfb_pose_optimize": (C.c_int, [C.c_void_p, _f32p, _f64p, C.c_int32, _f64p, _f64p, _f64p, _f64p, _u8p, _i32p, _i32p]),
     "hfb_lba_build_schur": (C.c_int, [C.c_void_p, C.POINTER(hfb_lba_problem), C.c_double, _f64p, _f64p, _f64p, _i32p]),
 }
 

@@ -63,3 +63,20 @@ def build_schur(ctx: Context, problem: Dict[str, np.ndarray], lam: float, huber_
     ctx.check(ctx.lib.hfb_lba_build_schur(ctx.handle, C.byref(p), lam, ptr(Hs, _f64p), ptr(bs, _f64p), C.byref(chi),
                                           C.byref(n)))
     return Hs, bs, float(chi.value), int(n.value)
+
+
+def pose_optimization(ctx: Context, K, pose, Xw, obs, inv_sigma2) -> dict:
+    """Optimizer::PoseOptimization (src/Optimizer.cc:814-1114), monocular: returns dict(pose, outlier, n_inliers, trials)."""
+    from .lib import _f32p
+    k = np.ascontiguousarray(K, np.float32)
+    p0 = np.ascontiguousarray(pose, np.float64).reshape(7)
+    X = np.ascontiguousarray(Xw, np.float64).reshape(-1, 3)
+    o = np.ascontiguousarray(obs, np.float64).reshape(-1, 2)
+    s2 = np.ascontiguousarray(inv_sigma2, np.float64).reshape(-1)
+    n = X.shape[0]
+    out = np.zeros(7, np.float64)
+    flags = np.zeros(max(n, 1), np.uint8)
+    ninl, ntr = C.c_int32(), C.c_int32()
+    ctx.check(ctx.lib.hfb_pose_optimize(ctx.handle, ptr(k, _f32p), ptr(p0, _f64p), n, ptr(X, _f64p), ptr(o, _f64p),
+                                        ptr(s2, _f64p), ptr(out, _f64p), ptr(flags, _u8p), C.byref(ninl), C.byref(ntr)))
+    return dict(pose=out, outlier=flags[:n].astype(bool), n_inliers=int(ninl.value), trials=int(ntr.value))

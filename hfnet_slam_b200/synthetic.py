@@ -123,3 +123,27 @@ def lba_problem(n_opt: int = 20, n_fixed: int = 40, n_points: int = 3000, seed: 
     return dict(poses=poses, fixed=fixed, points=pts_init, cam_idx=cam_idx[order], pt_idx=pt_idx[order],
                 obs=obs[order], inv_sigma2=inv_s2[order], K=np.asarray(K, np.float32),
                 true_points=pts)
+
+
+def pose_problem(n: int = 400, seed: int = 11, pixel_noise: float = 1.0, outlier_frac: float = 0.12,
+                 pose_noise: float = 0.02, width: int = 752, height: int = 480, K: np.ndarray = EUROC_K):
+    """Tracking-shaped motion-only BA (Optimizer::PoseOptimization, src/Optimizer.cc:814): one frame observing n fixed
+    map points; observations = true projection + octave-scaled pixel noise, a fraction replaced by gross mismatches;
+    the initial pose is the truth perturbed (the motion-model prediction)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = [float(v) for v in K]
+    Rcw = _rot(np.array([0.05, -0.1, 0.02]))
+    tcw = np.array([0.3, -0.1, 0.2])
+    u = rng.uniform(5, width - 5, n); v = rng.uniform(5, height - 5, n); z = rng.uniform(1.5, 12.0, n)
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    Xw = (Xc - tcw) @ Rcw                    # Rcw^T (Xc - t)
+    octave = rng.integers(0, 4, n)
+    sig = 1.2 ** octave
+    obs = np.stack([u, v], 1) + rng.normal(0, pixel_noise, (n, 2)) * sig[:, None]
+    bad = rng.random(n) < outlier_frac
+    obs[bad] += rng.uniform(-60, 60, (int(bad.sum()), 2))
+    R0 = _rot(rng.normal(0, pose_noise, 3)) @ Rcw
+    t0 = tcw + rng.normal(0, pose_noise, 3)
+    pose0 = np.concatenate([_rot_to_quat(R0), t0])
+    return dict(K=np.asarray(K, np.float32), pose0=pose0, Xw=Xw, obs=obs, inv_sigma2=1.0 / (sig * sig),
+                true_pose=np.concatenate([_rot_to_quat(Rcw), tcw]), planted_outlier=bad)

@@ -256,6 +256,15 @@ int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, int32_t itera
                      const volatile uint8_t* stop_flag, double* poses_out, double* points_out, double* chi2_out,
                      uint8_t* depth_positive_out, hfb_lba_stats* stats);
 
+/* Optimizer::PoseOptimization (src/Optimizer.cc:814-1114), monocular branch: motion-only BA of one frame against fixed
+ * map points.  4 rounds x optimize(10) (Levenberg, Huber sqrt(5.991) dropped after the third round), inlier
+ * re-classification with chi2 > 5.991 after every round, every round restarted from pose_in -- the whole schedule
+ * runs in one device kernel.  pose: qx qy qz qw tx ty tz (Tcw).  outlier_out = Frame::mvbOutlier of the used edges,
+ * *n_inliers = nInitialCorrespondences - nBad. */
+int hfb_pose_optimize(hfb_ctx* ctx, const float* K, const double* pose_in, int32_t n, const double* Xw,
+                      const double* obs, const double* inv_sigma2, double* pose_out, uint8_t* outlier_out,
+                      int32_t* n_inliers, int32_t* n_trials);
+
 /* One linearisation + Schur reduction at the given estimate and damping (parity hook for the two kernels):
  * Hschur [6n_opt x 6n_opt] row-major (full symmetric), bschur [6n_opt], robust chi2 (sum of rho(chi2_e)).
  * Optimisable cameras take slots in array order. */

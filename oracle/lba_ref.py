@@ -351,3 +351,114 @@ def optimize(pr: Problem, iterations: int = 10, user_lambda_init: float = 0.0,
     res.outlier = (last_chi2 > CHI2_MONO) | ~res.depth_positive
     res.iterations = it_done
     return res
+
+
+# ====================================================================================================================
+# Optimizer::PoseOptimization (src/Optimizer.cc:814-1114), monocular branch: one VertexSE3Expmap, unary
+# EdgeSE3ProjectXYZOnlyPose edges (include/OptimizableTypes.h:30-56, src/OptimizableTypes.cpp:49-64) with fixed Xw.
+# Four rounds of optimize(10); every round restarts from the frame's pose (:1007-1008), uses only the current inliers
+# (level 0, :1010), re-classifies all edges with chi2 > 5.991 (:1024-1036, `float` compare) and after the third round
+# drops the Huber kernel (:1038-1039).  Returns the last round's pose.
+def _pose_edges(K, pose, Xw, obs, inv_sigma2):
+    R = quat_to_rot(pose[:4])
+    Xc = Xw @ R.T + pose[4:]
+    fx, fy, cx, cy = [float(v) for v in K]
+    proj = np.stack([fx * Xc[:, 0] / Xc[:, 2] + cx, fy * Xc[:, 1] / Xc[:, 2] + cy], axis=1)
+    err = obs - proj
+    chi2 = inv_sigma2 * (err * err).sum(axis=1)
+    return err, chi2, Xc
+
+
+def _pose_jac(K, Xc):
+    fx, fy = float(K[0]), float(K[1])
+    x, y, z = Xc[:, 0], Xc[:, 1], Xc[:, 2]
+    n = Xc.shape[0]
+    Jp = np.zeros((n, 2, 3))
+    Jp[:, 0, 0] = -fx / z
+    Jp[:, 0, 2] = fx * x / (z * z)
+    Jp[:, 1, 1] = -fy / z
+    Jp[:, 1, 2] = fy * y / (z * z)
+    D = np.zeros((n, 3, 6))
+    D[:, 0, 1] = z; D[:, 0, 2] = -y; D[:, 0, 3] = 1
+    D[:, 1, 0] = -z; D[:, 1, 2] = x; D[:, 1, 4] = 1
+    D[:, 2, 0] = y; D[:, 2, 1] = -x; D[:, 2, 5] = 1
+    return np.einsum("nij,njk->nik", Jp, D)
+
+
+def pose_optimization(K, pose0, Xw, obs, inv_sigma2, huber_delta: float = float(HUBER_MONO)):
+    """Returns (pose [7], outlier [n] bool, n_inliers, stats dict)."""
+    pose0 = np.asarray(pose0, np.float64)
+    n = Xw.shape[0]
+    outlier = np.zeros(n, bool)
+    chi2_mono = np.float32(5.991)
+    tau, good_lo, good_hi, max_trials = 1e-5, 1.0 / 3.0, 2.0 / 3.0, 10
+    dsqr = huber_delta * huber_delta
+    pose = pose0.copy()
+    trials_total, iters_total = 0, 0
+    n_bad = 0
+
+    def rho_sum(chi2, robust):
+        if not robust:
+            return float(chi2.sum())
+        return float(np.where(chi2 <= dsqr, chi2, 2 * np.sqrt(np.maximum(chi2, 1e-300)) * huber_delta - dsqr).sum())
+
+    for rnd in range(4):
+        robust = rnd < 3
+        act = ~outlier
+        pose = pose0.copy()
+        cached = np.zeros(n)                       # chi2 as cached by the last computeActiveErrors (active edges)
+        lam, ni, nbad_lm = 0.0, 2.0, 0
+        for it in range(10):
+            if act.sum() == 0:
+                break
+            err, chi2, Xc = _pose_edges(K, pose, Xw[act], obs[act], inv_sigma2[act])
+            cached[act] = chi2
+            current_chi = rho_sum(chi2, robust)
+            ini_chi = current_chi
+            J = _pose_jac(K, Xc)
+            w = np.where(chi2 <= dsqr, 1.0, huber_delta / np.sqrt(np.maximum(chi2, 1e-300))) if robust else np.ones_like(chi2)
+            wo = w * inv_sigma2[act]
+            H = np.einsum("n,nki,nkj->ij", wo, J, J)
+            b = np.einsum("nki,nk->i", J, -(wo[:, None] * err))
+            if it == 0:
+                lam = tau * float(np.abs(np.diag(H)).max())
+                ni, nbad_lm = 2.0, 0
+            rho, qmax = 0.0, 0
+            while True:
+                ok2, x = solve_reduced(H + lam * np.eye(6), b)
+                new_pose = pose_oplus(pose, x)
+                _, chi2_t, _ = _pose_edges(K, new_pose, Xw[act], obs[act], inv_sigma2[act])
+                cached[act] = chi2_t
+                temp_chi = rho_sum(chi2_t, robust) if ok2 else np.finfo(np.float64).max
+                scale = float(np.sum(x * (lam * x + b))) + 1e-3
+                rho = (current_chi - temp_chi) / scale
+                trials_total += 1
+                if rho > 0 and np.isfinite(temp_chi):
+                    alpha = min(1.0 - (2 * rho - 1) ** 3, good_hi)
+                    lam *= max(good_lo, alpha)
+                    ni = 2.0
+                    current_chi = temp_chi
+                    pose = new_pose
+                else:
+                    lam *= ni
+                    ni *= 2
+                qmax += 1
+                if not (rho < 0 and qmax < max_trials):
+                    break
+            iters_total += 1
+            if qmax == max_trials or rho == 0:
+                break
+            if (ini_chi - current_chi) * 1e3 < ini_chi:
+                nbad_lm += 1
+            else:
+                nbad_lm = 0
+            if nbad_lm >= 3:
+                break
+        # classification (:1016-1040): outlier edges are re-evaluated at the round's final pose, inliers keep the cache
+        _, chi2_all, _ = _pose_edges(K, pose, Xw, obs, inv_sigma2)
+        chi2_used = np.where(outlier, chi2_all, cached)
+        outlier = chi2_used.astype(np.float32) > chi2_mono
+        n_bad = int(outlier.sum())
+        if n < 10:
+            break
+    return pose, outlier, n - n_bad, dict(trials=trials_total, iterations=iters_total)
