@@ -308,7 +308,11 @@ extern "C" int hfb_load_weights(hfb_ctx* ctx, const void* blob, size_t nbytes) {
     {
       TAKE(w, (size_t)9 * bw.cexp);
       TAKE(b, (size_t)bw.cexp);
-      fix((const void**)&bw.wd, ab.add(w, (size_t)9 * bw.cexp * 4));
+      // depthwise weights are fp16 operands like every other conv weight (kept as fp32 words holding fp16-exact values:
+      // the fused kernel narrows them losslessly for its mixed-precision FMA, the plain kernels use them as they are)
+      std::vector<float> w16((size_t)9 * bw.cexp);
+      for (size_t i = 0; i < w16.size(); ++i) w16[i] = __half2float(__float2half_rn(w[i]));
+      fix((const void**)&bw.wd, ab.add(w16.data(), (size_t)9 * bw.cexp * 4));
       fix((const void**)&bw.bd, ab.add(b, (size_t)bw.cexp * 4));
     }
     {

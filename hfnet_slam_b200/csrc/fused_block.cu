@@ -31,15 +31,34 @@ struct FusedGeom {
   int kb_in;              // 64-channel k-blocks of Cin
   int cout_pad;           // Cout rounded up to 16
   int e_pitch;            // bytes per row of the expanded tile in smem
+  int xrb;                // bytes per row of the input tile: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B, Cin <= 32)
   uint32_t tmem_cols;
   uint32_t we_chunk_bytes, wp_chunk_bytes, w_total_bytes;
   uint32_t off_X, off_A2, off_WE, off_WP, off_E, off_wd, off_bars, smem_bytes;
 };
 
-#define FB_THREADS 512
+// packed (lo, hi) fp16 pair x fp16 pair -> two fp32 accumulators: one FHFMA each (sm_100 mixed-precision FMA; the
+// fp16 x fp16 product is exact in fp32, so this is bit-identical to fmaf(float(x), float(w), acc))
+__device__ __forceinline__ void fma2_f16(float& a0, float& a1, uint32_t x, uint32_t w) {
+  asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\tmov.b32 {xl, xh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+      "fma.rn.f32.f16 %0, xl, wl, %0;\n\tfma.rn.f32.f16 %1, xh, wh, %1;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "r"(x), "r"(w));
+}
+// round two fp32 to a packed fp16 pair (lo, hi) with max(., 0) folded into the conversion, then min(., 6): ReLU6.
+// Rounding is monotonic and 0 / 6 are exact in fp16, so this equals rounding the fp32 clamp.
+__device__ __forceinline__ uint32_t relu6_pack(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  const __half2 six2 = __float2half2_rn(6.f);
+  __half2 h = __hmin2(*reinterpret_cast<__half2*>(&r), six2);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
-template <int S>
-__global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_constant__ CUtensorMap tmWE,
+// NT = threads per CTA: 256 (two CTAs per SM hide each other's barrier / MMA round-trip stalls) or 512 (one CTA per SM
+// for the blocks whose resident weights leave no room for a second CTA).
+template <int S, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) fused_block_kernel(const __grid_constant__ CUtensorMap tmWE,
                                                                  const __grid_constant__ CUtensorMap tmWP,
                                                                  const FusedGeom g, const __half* __restrict__ in,
                                                                  const float* __restrict__ be,   // expand bias [Cexp]
@@ -52,14 +71,14 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
   // instead of generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int IW = 15 * S + 3;   // halo tile width
-  uint8_t* sX = smem + g.off_X;      // [kb_in][MT*128 rows][128 B] swizzled
+  uint8_t* sX = smem + g.off_X;      // [kb_in][MT*128 rows][xrb B] swizzled
   uint8_t* sA2 = smem + g.off_A2;    // [128 rows][128 B] swizzled (written by the depthwise phase)
   uint8_t* sWE = smem + g.off_WE;    // [n_chunks][kb_in][CW rows][128 B] swizzled (TMA, resident)
   uint8_t* sWP = smem + g.off_WP;    // [n_chunks][cout_pad rows][128 B] swizzled (TMA, resident)
   uint8_t* sE = smem + g.off_E;      // [R][e_pitch] expanded activations of the current chunk, fp16
-  float* s_wd = reinterpret_cast<float*>(smem + g.off_wd);  // [9][cexp_pad] dw weights | [cexp_pad] dw bias | expand bias
-  float* s_bd = s_wd + 9 * g.cexp_pad;
-  float* s_be = s_bd + g.cexp_pad;
+  __half* s_wd = reinterpret_cast<__half*>(smem + g.off_wd);  // [9][cexp_pad] dw weights (fp16-exact values)
+  float* s_bd = reinterpret_cast<float*>(smem + g.off_wd + 18 * g.cexp_pad);   // [cexp_pad] dw bias
+  float* s_be = s_bd + g.cexp_pad;                                             // [cexp_pad] expand bias
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bars);
   uint64_t* bar_w = bars;      // all weights landed (once)
   uint64_t* bar_e = bars + 1;  // [2] expand MMAs retired (alternating)
@@ -84,7 +103,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
     }
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, g.tmem_cols);
-  for (int i = tid; i < 11 * g.cexp_pad; i += FB_THREADS) {
+  for (int i = tid; i < 11 * g.cexp_pad; i += NT) {
     const int row = i / g.cexp_pad, c = i - row * g.cexp_pad;
     float v = 0.f;
     if (c < g.Cexp) {
@@ -92,7 +111,8 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
       else if (row == 9) v = __ldg(bd + c);
       else if (g.has_expand) v = __ldg(be + c);
     }
-    s_wd[i] = v;
+    if (row < 9) s_wd[i] = __float2half_rn(v);   // exact: the loader stores fp16-representable depthwise weights
+    else s_bd[i - 9 * g.cexp_pad] = v;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -110,7 +130,8 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
     const uint32_t idesc = tc::make_idesc_f16((cvalid + 15) & ~15);
     for (int mt = 0; mt < g.MT; ++mt) {
       for (int kb = 0; kb < g.kb_in; ++kb) {
-        const uint64_t da = tc::make_sdesc_sw128(tc::smem_u32(sX + ((size_t)kb * g.MT + mt) * 128 * 128));
+        const uint64_t da = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(sX + ((size_t)kb * g.MT + mt) * 128 * 128))
+                                         : tc::make_sdesc_sw64(tc::smem_u32(sX + (size_t)mt * 128 * 64));
         const uint64_t db =
             tc::make_sdesc_sw128(tc::smem_u32(sWE + (size_t)j * g.we_chunk_bytes + (size_t)kb * g.CW * 128));
         const int krem = g.Cin - kb * 64;
@@ -134,15 +155,19 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
     const int units = ((g.Cin + 15) & ~15) >> 3;   // 16-byte units per pixel incl. K padding
     const int vunits = g.Cin >> 3;                 // units holding real channels
     const __half* src = in + (size_t)limg * g.Hi * g.Wi * g.Cin;
-    for (int r = tid; r < g.R; r += FB_THREADS) {
+    for (int r = tid; r < g.R; r += NT) {
       const int ry = r / IW, rx = r - ry * IW;
       const int iy = liy0 + ry, ix = lix0 + rx;
       const bool inb = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
       const __half* gp = inb ? src + ((size_t)iy * g.Wi + ix) * g.Cin : in;
-      const uint32_t row_dst = tc::smem_u32(sX) + (uint32_t)r * 128u;
+      const uint32_t row_dst = tc::smem_u32(sX) + (uint32_t)r * (uint32_t)g.xrb;
       for (int u = 0; u < units; ++u) {
         const bool ok = inb && u < vunits;
-        const uint32_t dst = row_dst + (uint32_t)(u >> 3) * (uint32_t)(g.MT * 128 * 128) + (uint32_t)(((u & 7) ^ (r & 7)) << 4);
+        // 16-byte chunk u of row r under the operand swizzle: SWIZZLE_128B = chunk ^ (row & 7) in 128-byte rows,
+        // SWIZZLE_64B = chunk ^ ((row >> 1) & 3) in 64-byte rows (address bits [4,6) ^= bits [7,9))
+        const uint32_t dst = g.xrb == 128 ? row_dst + (uint32_t)(u >> 3) * (uint32_t)(g.MT * 128 * 128) +
+                                                (uint32_t)(((u & 7) ^ (r & 7)) << 4)
+                                          : row_dst + (uint32_t)((u ^ ((r >> 1) & 3)) << 4);
         const int nbytes = ok ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? gp + u * 8 : in), "r"(nbytes)
                      : "memory");
@@ -188,7 +213,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
         tc::fence_after_sync();
         // work units = (M-tile, column half) spread over the four warp quads; warp w reads TMEM lane group w % 4
         const int nch = cw16 >> 4, ch_half = (nch + 1) >> 1;
-        for (int wu = warp >> 2; wu < g.MT * 2; wu += 4) {
+        for (int wu = warp >> 2; wu < g.MT * 2; wu += NT / 128) {
           const int mt = wu >> 1, half = wu & 1;
           const int cbeg = half ? ch_half * 16 : 0, cend = half ? cw16 : ch_half * 16;
           const int r = mt * 128 + (warp & 3) * 32 + lane;
@@ -201,19 +226,15 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
             tc::tmem_ld_wait();
             if (r < g.R) {
               uint4 q[2];
-              __half2* hq = reinterpret_cast<__half2*>(q);
+              uint32_t* hq = reinterpret_cast<uint32_t*>(q);
               if (in_img) {
-                // bias add in fp32, one rounding to fp16, then the ReLU6 clamp on packed halves (0 and 6 are exact in
-                // fp16 and rounding is monotonic, so clamp-after-round == round-after-clamp bit for bit)
+                // bias add in fp32, one rounding to fp16 with the ReLU6 clamp folded into the conversion
                 const float4* bq = reinterpret_cast<const float4*>(s_be + c0 + cc);
-                const __half2 zero2 = __float2half2_rn(0.f), six2 = __float2half2_rn(6.f);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float4 b4 = bq[i];
-                  __half2 h0 = __floats2half2_rn(__uint_as_float(v[4 * i]) + b4.x, __uint_as_float(v[4 * i + 1]) + b4.y);
-                  __half2 h1 = __floats2half2_rn(__uint_as_float(v[4 * i + 2]) + b4.z, __uint_as_float(v[4 * i + 3]) + b4.w);
-                  hq[2 * i] = __hmin2(__hmax2(h0, zero2), six2);
-                  hq[2 * i + 1] = __hmin2(__hmax2(h1, zero2), six2);
+                  hq[2 * i] = relu6_pack(__uint_as_float(v[4 * i]) + b4.x, __uint_as_float(v[4 * i + 1]) + b4.y);
+                  hq[2 * i + 1] = relu6_pack(__uint_as_float(v[4 * i + 2]) + b4.z, __uint_as_float(v[4 * i + 3]) + b4.w);
                 }
               } else {
                 q[0] = make_uint4(0, 0, 0, 0);
@@ -229,7 +250,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
       } else {
         // no expand conv (layer_2): the "expanded" activation is the input tile itself
         const int units = cw16 >> 3;
-        for (int i = tid; i < g.R * units; i += FB_THREADS) {
+        for (int i = tid; i < g.R * units; i += NT) {
           const int r = i / units, u = i - r * units;
           const int cu = (c0 >> 3) + u;   // 16-byte unit inside the 128-byte swizzled row
           uint4 q = make_uint4(0, 0, 0, 0);
@@ -260,24 +281,21 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
       // pair p, p+64): the unit's 72 weights + 8 biases sit in registers for both pixels.
       {
         const int units = cw16 >> 3;
-        // 8 units: 64 pixel-pairs per unit; <= 4 units: one pixel per thread so that all 512 threads stay busy
-        const int shift = units > 4 ? 6 : 7;
-        const int pstep = 1 << shift;
-        if ((tid >> shift) < units) {
-          const int u = tid >> shift, pb = tid & (pstep - 1);
-          float w[72], bias8[8];
+        // threads of one unit (8 channels) = NT / (units rounded up to 2, 4 or 8); each walks the tile's pixels with the
+        // unit's 72 weights (36 packed registers) + 8 biases resident
+        const int upow = units > 4 ? 8 : (units > 2 ? 4 : 2);
+        const int pstep = NT / upow;
+        const int u = tid / pstep, pb = tid - u * pstep;
+        if (u < units) {
+          uint4 w[9];
+          float bias8[8];
           {
             const float4* bq = reinterpret_cast<const float4*>(s_bd + c0 + u * 8);
             const float4 b0 = bq[0], b1 = bq[1];
             bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
             bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
 #pragma unroll
-            for (int tp = 0; tp < 9; ++tp) {
-              const float4* wq = reinterpret_cast<const float4*>(s_wd + tp * g.cexp_pad + c0 + u * 8);
-              const float4 w0 = wq[0], w1 = wq[1];
-              w[tp * 8 + 0] = w0.x; w[tp * 8 + 1] = w0.y; w[tp * 8 + 2] = w0.z; w[tp * 8 + 3] = w0.w;
-              w[tp * 8 + 4] = w1.x; w[tp * 8 + 5] = w1.y; w[tp * 8 + 6] = w1.z; w[tp * 8 + 7] = w1.w;
-            }
+            for (int tp = 0; tp < 9; ++tp) w[tp] = *reinterpret_cast<const uint4*>(s_wd + tp * g.cexp_pad + c0 + u * 8);
           }
           const int npix = g.TH * 16;
           for (int p = pb; p < npix; p += pstep) {
@@ -291,20 +309,18 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
                 const uint4 q = *reinterpret_cast<const uint4*>(e0 + (size_t)(ky * IW + kx) * g.e_pitch);
-                const __half2* hq = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const float2 f = __half22float2(hq[c]);
-                  acc[2 * c] = fmaf(f.x, w[(ky * 3 + kx) * 8 + 2 * c], acc[2 * c]);
-                  acc[2 * c + 1] = fmaf(f.y, w[(ky * 3 + kx) * 8 + 2 * c + 1], acc[2 * c + 1]);
-                }
+                const uint4 wq = w[ky * 3 + kx];
+                fma2_f16(acc[0], acc[1], q.x, wq.x);
+                fma2_f16(acc[2], acc[3], q.y, wq.y);
+                fma2_f16(acc[4], acc[5], q.z, wq.z);
+                fma2_f16(acc[6], acc[7], q.w, wq.w);
               }
             }
-            uint4 o;
-            __half2* ho = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)   // channels beyond Cexp (zero weights, zero bias) come out as exact zeros
-              ho[c] = __floats2half2_rn(fminf(fmaxf(acc[2 * c], 0.f), 6.f), fminf(fmaxf(acc[2 * c + 1], 0.f), 6.f));
+            uint4 o;   // channels beyond Cexp (zero weights, zero bias) come out as exact zeros
+            o.x = relu6_pack(acc[0], acc[1]);
+            o.y = relu6_pack(acc[2], acc[3]);
+            o.z = relu6_pack(acc[4], acc[5]);
+            o.w = relu6_pack(acc[6], acc[7]);
             *reinterpret_cast<uint4*>(sA2 + (size_t)p * 128 + (size_t)((u ^ (p & 7)) << 4)) = o;
           }
         }
@@ -335,7 +351,7 @@ __global__ void __launch_bounds__(FB_THREADS) fused_block_kernel(const __grid_co
       const bool valid = (p >> 4) < g.TH && oy < g.Ho && ox < g.Wo;
       const long long opix = ((long long)img * g.Ho + oy) * g.Wo + ox;
       const uint32_t taddr = tmem_d2 + ((uint32_t)((warp & 3) * 32) << 16);
-      for (int cc = (warp >> 2) * 16; cc < g.cout_pad; cc += 64) {   // 16-column pieces round-robin over the quads
+      for (int cc = (warp >> 2) * 16; cc < g.cout_pad; cc += NT / 8) {   // 16-column pieces round-robin over the quads
         uint32_t v[16];
         tc::tmem_ld16(taddr + (uint32_t)cc, v);
         tc::tmem_ld_wait();
@@ -380,12 +396,17 @@ struct FusedPlan {
   CUtensorMap tmWE, tmWP;
   FusedGeom g;
   int ctas_per_sm;
+  int nt;   // threads per CTA (256 or 512)
 };
 
 FusedPlan* fused_block_new() { return new FusedPlan(); }
 void fused_block_delete(FusedPlan* p) { delete p; }
 
 // Returns HFB_ERR_CAPACITY when the block does not fit on chip (the caller keeps the three-kernel path).
+// Configuration search, in order of preference: 256-thread CTAs, two per SM (shared memory <= 112 KB and <= 256 TMEM
+// columns each), then one 512-thread CTA per SM; 8 x 16 output tiles unless the halo tile does not fit or the taller
+// tiles cannot give every resident CTA two tiles (small late layers), then 4 x 16.
+// HFB_FUSED_NT / HFB_FUSED_TH (environment) pin the choice for experiments.
 int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half* in, int Bmax, int Hi, int Wi, int Ho,
                      int Wo, int pad_t, int pad_l) {
   (void)in;
@@ -401,6 +422,7 @@ int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half
   g.n_chunks = (bw.cexp + g.CW - 1) / g.CW;
   g.cexp_pad = g.n_chunks * g.CW;
   g.kb_in = (bw.cin + 63) / 64;
+  g.xrb = (bw.has_expand && bw.cin <= 32) ? 64 : 128;
   g.cout_pad = (bw.cout + 15) & ~15;
   g.e_pitch = g.CW * 2 + 16;
   g.we_chunk_bytes = g.has_expand ? (uint32_t)(g.kb_in * g.CW * 128) : 0u;
@@ -408,67 +430,87 @@ int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half
   g.w_total_bytes = (uint32_t)g.n_chunks * (g.we_chunk_bytes + g.wp_chunk_bytes);
   if (g.w_total_bytes >= (1u << 20)) return HFB_ERR_CAPACITY;   // mbarrier tx-count limit
   auto al = [](uint32_t v) { return (v + 1023u) & ~1023u; };
-  const uint32_t budget = 200 * 1024;
-  // 8 x 16 tiles, or 4 x 16 when the halo tile would not fit in shared memory or when the taller tiles cannot give
-  // every SM at least two tiles (small late layers)
-  const int th0 = (g.tiles_x * ((Ho + 7) / 8) * Bmax < 2 * ctx->n_sm) ? 4 : 8;
-  for (g.TH = th0; g.TH >= 4; g.TH >>= 1) {
+  auto layout = [&](int th) {
+    g.TH = th;
     g.tiles_y = (Ho + g.TH - 1) / g.TH;
     g.IH = (g.TH - 1) * bw.stride + 3;
     g.IW_ = 15 * bw.stride + 3;
     g.R = g.IH * g.IW_;
     g.MT = (g.R + 127) / 128;
     uint32_t off = 0;
-    g.off_X = off;  off += al((uint32_t)(g.kb_in * g.MT * 128 * 128));
+    g.off_X = off;  off += al((uint32_t)(g.kb_in * g.MT * 128 * g.xrb));
     g.off_A2 = off; off += 128 * 128;
     g.off_WE = off; off += al((uint32_t)g.n_chunks * g.we_chunk_bytes);
     g.off_WP = off; off += al((uint32_t)g.n_chunks * g.wp_chunk_bytes);
     g.off_E = off;  off += al((uint32_t)(g.R * g.e_pitch));
-    g.off_wd = off; off += al((uint32_t)(11 * g.cexp_pad * 4));
+    g.off_wd = off; off += al((uint32_t)(26 * g.cexp_pad));
     g.off_bars = off; off += 64;
     g.smem_bytes = off + 1024;
-    if (g.smem_bytes <= budget) break;
+    uint32_t cols = 32;
+    while ((int)cols < g.MT * g.CW + g.cout_pad) cols <<= 1;
+    g.tmem_cols = cols;
+  };
+  const char* e_nt = getenv("HFB_FUSED_NT");
+  const char* e_th = getenv("HFB_FUSED_TH");
+  const int pin_nt = e_nt ? atoi(e_nt) : 0, pin_th = e_th ? atoi(e_th) : 0;
+  bool found = false;
+  for (int nt : {256, 512}) {
+    if (pin_nt && nt != pin_nt) continue;
+    const int ctas = nt == 256 ? 2 : 1;
+    const uint32_t budget = nt == 256 ? 112u * 1024u : 200u * 1024u;
+    const uint32_t max_cols = nt == 256 ? 256u : 512u;
+    const int th0 = pin_th ? pin_th : ((g.tiles_x * ((Ho + 7) / 8) * Bmax < 2 * ctas * ctx->n_sm) ? 4 : 8);
+    for (int th = th0; th >= 4 && !found; th >>= 1) {
+      layout(th);
+      if (g.smem_bytes <= budget && g.tmem_cols <= max_cols) {
+        found = true;
+        fp.nt = nt;
+        fp.ctas_per_sm = ctas;
+      }
+      if (pin_th) break;
+    }
+    if (found) break;
   }
-  uint32_t cols = 32;
-  while ((int)cols < g.MT * g.CW + g.cout_pad) cols <<= 1;
-  if (g.TH < 4 || g.smem_bytes > budget || cols > 512) return HFB_ERR_CAPACITY;
-  g.tmem_cols = cols;
+  if (!found) return HFB_ERR_CAPACITY;
   g.total_tiles = g.tiles_x * g.tiles_y * Bmax;
-  int per_sm = (int)(227 * 1024 / (g.smem_bytes + 1024));
-  per_sm = std::min(per_sm, (int)(512 / cols));
-  fp.ctas_per_sm = std::max(1, std::min(per_sm, 3));
   if (bw.has_expand)
     HFB_TRY(hfb_make_tmap_2d(ctx, &fp.tmWE, bw.expand.w, (uint64_t)bw.expand.Kp, (uint64_t)bw.expand.N,
                              (uint64_t)bw.expand.Kp * 2, (uint32_t)g.CW));
   HFB_TRY(hfb_make_tmap_2d(ctx, &fp.tmWP, bw.project.w, (uint64_t)bw.project.Kp, (uint64_t)bw.project.N,
                            (uint64_t)bw.project.Kp * 2, (uint32_t)g.cout_pad));
   if (!bw.has_expand) fp.tmWE = fp.tmWP;   // never dereferenced by the kernel
+  if (ctx->trace)
+    fprintf(stderr, "hfnet_b200: fused layer_%d: NT=%d x%d TH=%d MT=%d CW=%d xrb=%d smem=%u tmem=%u tiles=%d\n", bw.layer,
+            fp.nt, fp.ctas_per_sm, g.TH, g.MT, g.CW, g.xrb, g.smem_bytes, g.tmem_cols, g.total_tiles);
   return HFB_OK;
 }
 
 int fused_block_tiles(const FusedPlan& fp, int B) { return fp.g.tiles_x * fp.g.tiles_y * B; }
 
-int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const __half* in, __half* out, int B) {
-  static size_t configured = 0;
-  if (fp.g.smem_bytes > configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)fp.g.smem_bytes));
-    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)fp.g.smem_bytes));
-    configured = fp.g.smem_bytes;
+template <int S, int NT>
+static int fused_launch(hfb_ctx* ctx, const FusedPlan& fp, const FusedGeom& g, const BlockW& bw, const __half* in,
+                        __half* out, int grid) {
+  static size_t configured = 0;   // per instantiation
+  if (g.smem_bytes > configured) {
+    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_kernel<S, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)g.smem_bytes));
+    configured = g.smem_bytes;
   }
+  hfb_launch(ctx, fused_block_kernel<S, NT>, grid, NT, g.smem_bytes, fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd, bw.bd,
+             bw.project.b, out);
+  HFB_CHECK_LAUNCH(ctx, "fused_block");
+  return HFB_OK;
+}
+
+int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const __half* in, __half* out, int B) {
   FusedGeom g = fp.g;
   g.B = B;
   g.total_tiles = g.tiles_x * g.tiles_y * B;
   const int grid = std::min(g.total_tiles, ctx->n_sm * fp.ctas_per_sm);
-  if (g.stride == 1)
-    hfb_launch(ctx, fused_block_kernel<1>, grid, FB_THREADS, g.smem_bytes, fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
-                                                                          bw.bd, bw.project.b, out);
-  else
-    hfb_launch(ctx, fused_block_kernel<2>, grid, FB_THREADS, g.smem_bytes, fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
-                                                                          bw.bd, bw.project.b, out);
-  HFB_CHECK_LAUNCH(ctx, "fused_block");
-  return HFB_OK;
+  if (g.stride == 1) return fp.nt == 256 ? fused_launch<1, 256>(ctx, fp, g, bw, in, out, grid)
+                                         : fused_launch<1, 512>(ctx, fp, g, bw, in, out, grid);
+  return fp.nt == 256 ? fused_launch<2, 256>(ctx, fp, g, bw, in, out, grid)
+                      : fused_launch<2, 512>(ctx, fp, g, bw, in, out, grid);
 }
 
 double fused_block_bytes(const FusedPlan& fp, int B) {   // algorithmic: input once + output once + weights

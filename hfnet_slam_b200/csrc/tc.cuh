@@ -130,6 +130,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// Same for rows of 64 bytes (32 fp16 along K) under the 64-byte swizzle (address bits [4,6) ^= bits [7,9)): 8-row groups
+// are 512 bytes apart, layout type 4 = SWIZZLE_64B.  Used when K <= 32 so that the operand tile is half the size.
+__device__ __forceinline__ uint64_t make_sdesc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
 // Advancing by UMMA_K = 16 fp16 (32 bytes) inside the swizzle atom == +2 in the start-address field.
 __device__ __forceinline__ uint64_t sdesc_advance_k16(uint64_t desc, int k) { return desc + (uint64_t)(2 * k); }
 
