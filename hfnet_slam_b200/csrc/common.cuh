@@ -140,6 +140,7 @@ struct hfb_ctx {
   void* d_io = nullptr;        // persistent device staging of the host-pointer matcher entry points
   size_t d_io_bytes = 0;
   bool pdl = true;             // HFB_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
+  int fused_min_tiles = 37;    // HFB_FUSED_MIN_TILES: fewer tiles than this -> three-kernel path
   bool fused_blocks = true;    // HFB_FUSED=0: inverted-residual blocks run as three kernels (expand, dw, project)
   bool trace = false;          // HFB_TRACE=1: host-side stage timings of the host-pointer calls on stderr
   std::vector<void*> allocs;

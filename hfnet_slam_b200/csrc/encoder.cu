@@ -629,9 +629,9 @@ int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
       HFB_CHECK_LAUNCH(ctx, "dw_project_small");
       continue;
     }
-    // one fused kernel per block when there are enough tiles to fill the machine; tiny late layers (15 x 24 pixels)
-    // run faster as three small launches
-    if (bp.fused && fused_block_tiles(*bp.fused, B) >= ctx->n_sm) {
+    // one fused kernel per block unless the batch leaves it only a handful of tiles (single frames at 15 x 24 pixels
+    // run faster as three small launches that spread over the output channels)
+    if (bp.fused && fused_block_tiles(*bp.fused, B) >= ctx->fused_min_tiles) {
       ctx->note(ln + ".fused", fused_block_bytes(*bp.fused, B), fused_block_flops(*bp.fused, B));
       HFB_TRY(fused_block_run(ctx, *bp.fused, bw, in, lv.act[bw.layer], B));
       continue;
