@@ -41,13 +41,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trap (CUDA error at the next sync), never as a hung GPU box.
+// try_wait suspends the thread in hardware (up to a system time limit) and wakes it when the phase completes, so the
+// loop normally runs once or twice.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("hfnet_b200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 22)) __trap();
   }
 }
 
