@@ -1,0 +1,709 @@
+// One MobileNetV2 inverted-residual block (hfnet/models/backbones/utils/conv_blocks.py:162-312) as ONE kernel,
+// "channel per lane" formulation:
+//   1x1 expand (+bias, ReLU6)  ->  3x3 depthwise stride 1|2, TF-SAME (+bias, ReLU6)  ->  1x1 project (+bias, +residual)
+// The expand GEMM is issued TRANSPOSED: A = 128 expanded channels x K (weights, K-major), B = halo pixels x K (input
+// tile, K-major), so the fp32 accumulator in tensor memory holds one expanded CHANNEL per TMEM lane and one halo PIXEL
+// per column.  A thread (= one channel) then pulls whole pixel rows of its channel into registers with tcgen05.ld and
+// runs the depthwise 3x3 as a register sliding window: no shared-memory round trip for the 6x-expanded tensor, scalar
+// per-thread depthwise weights, 9 FMAs per output and nothing else.  The depthwise output goes to shared memory as the
+// MN-major (pixel-contiguous) A operand of the project GEMM (32 contiguous bytes per thread and row), which accumulates
+// over the 128-channel chunks in a second TMEM accumulator with pixels in lanes, ready for a row-per-thread epilogue.
+//   * expand bias and SAME zero padding cost nothing: the input tile carries two extra "ones" channels (1 inside the
+//     image, 0 outside) and the weight image carries the bias in those K columns (fp16 high part + fp16 residual, i.e.
+//     fp32-accurate), so out-of-image pixels expand to exactly 0 = the zero padding the depthwise conv must see
+//     (padding applies to the EXPANDED activation).
+//   * 16 compute warps (4 TMEM lane groups x 4 row groups) never meet at a CTA barrier: mbarriers pair them with one
+//     issuing thread that keeps expand(c+1) and project(c-1) in flight while chunk c is in the CUDA cores.
+//   * weights arrive as pre-swizzled per-chunk images (one cp.async.bulk each) that stay resident when they fit and
+//     stream through a ring otherwise; input halo tiles are prefetched NX-1 tiles ahead with cp.async.
+// HBM traffic per block = input (with halo) + output.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace {
+
+struct CplGeom {
+  int B, Hi, Wi, Ho, Wo;
+  int Cin, Cexp, Cout;
+  int pad_t, pad_l, residual;
+  int tiles_x, tiles_y, total_tiles;
+  int n_chunks;      // ceil(Cexp / 128)
+  int units;         // 16-byte units per input-tile row: Cin/8 data units, one "ones" unit, zero units up to K % 16 == 0
+  int ones_unit;     // = Cin / 8
+  int xrb;           // bytes per operand row of a k-block: 64 (K = 32, SWIZZLE_64B) or 128 (SWIZZLE_128B)
+  int kb_in;         // k-blocks of 64 channels (1 when xrb == 64)
+  int nk16;          // K steps of the expand MMA
+  int cout_pad;      // Cout rounded up to 16 (project N)
+  int NS, NX;        // weight ring slots (== n_chunks: resident), input tile buffers
+  uint32_t we_bytes, wp_bytes, blob_bytes;
+  uint32_t x_buf_bytes, a2_buf_bytes;
+  uint32_t off_X, off_A2, off_W, off_bars, smem_bytes;
+  uint32_t tmem_cols;
+  float* dbg;        // HFB_CPL_DBG=<layer>: CTA 0 dumps the raw expand accumulators of its first chunk ([rg][lane 0..127][row][18])
+};
+
+constexpr int CPL_NT = 512;          // compute threads
+constexpr int CPL_DW_BYTES = 6 * 128 * 4;   // per chunk: 5 words of packed fp16 taps + fp32 bias per lane
+
+__device__ __forceinline__ uint32_t relu6_pack(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  const __half2 six2 = __float2half2_rn(6.f);
+  __half2 h = __hmin2(*reinterpret_cast<__half2*>(&r), six2);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// acc + x.half[XH] * w.half[WH] with an fp32 accumulator (sm_100 mixed-precision FMA; the fp16 x fp16 product is exact
+// in fp32, i.e. bit-identical to fmaf(float(x), float(w), acc))
+template <int XH, int WH>
+__device__ __forceinline__ float fmah(uint32_t x, uint32_t w, float acc) {
+  float d;
+  if constexpr (XH == 0 && WH == 0)
+    asm("{\n\t.reg .b16 a, b, c, d;\n\tmov.b32 {a, b}, %1;\n\tmov.b32 {c, d}, %2;\n\tfma.rn.f32.f16 %0, a, c, %3;\n\t}"
+        : "=f"(d) : "r"(x), "r"(w), "f"(acc));
+  else if constexpr (XH == 0 && WH == 1)
+    asm("{\n\t.reg .b16 a, b, c, d;\n\tmov.b32 {a, b}, %1;\n\tmov.b32 {c, d}, %2;\n\tfma.rn.f32.f16 %0, a, d, %3;\n\t}"
+        : "=f"(d) : "r"(x), "r"(w), "f"(acc));
+  else if constexpr (XH == 1 && WH == 0)
+    asm("{\n\t.reg .b16 a, b, c, d;\n\tmov.b32 {a, b}, %1;\n\tmov.b32 {c, d}, %2;\n\tfma.rn.f32.f16 %0, b, c, %3;\n\t}"
+        : "=f"(d) : "r"(x), "r"(w), "f"(acc));
+  else
+    asm("{\n\t.reg .b16 a, b, c, d;\n\tmov.b32 {a, b}, %1;\n\tmov.b32 {c, d}, %2;\n\tfma.rn.f32.f16 %0, b, d, %3;\n\t}"
+        : "=f"(d) : "r"(x), "r"(w), "f"(acc));
+  return d;
+}
+
+// selectors are compile-time constants after unrolling
+__device__ __forceinline__ float fmah_sel(uint32_t x, int xh, uint32_t w, int wh, float acc) {
+  if (xh) return wh ? fmah<1, 1>(x, w, acc) : fmah<1, 0>(x, w, acc);
+  return wh ? fmah<0, 1>(x, w, acc) : fmah<0, 0>(x, w, acc);
+}
+
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& a) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(a) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tc::smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+// MN-major operand (64 MN-contiguous elements per 128-byte line, 8 K lines per 1024-byte swizzle atom), 128B swizzle:
+// LBO = byte distance between 64-element MN groups, SBO = byte distance between groups of 8 K
+// (cute::UMMA::make_umma_desc<Major::MN>: LayoutType::B128 ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)))
+__device__ __forceinline__ uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+// S = stride, TH x TW = output tile (TW = 16 for stride 1, 8 for stride 2); each of the 16 compute warps owns TMEM lane
+// group (warp & 3) = 32 channels of the chunk and row group (warp >> 2) = TH / 4 output rows of the tile.
+template <int S, int TH, bool KM>
+__global__ void __launch_bounds__(CPL_NT + 32, 1)
+fused_block_cpl_kernel(const CplGeom g, const __half* __restrict__ in, const uint8_t* __restrict__ wblob,
+                       const float* __restrict__ bp, const __half* __restrict__ ones, __half* __restrict__ out) {
+  constexpr int TW = S == 1 ? 16 : 8;
+  constexpr int IW = (TW - 1) * S + 3;
+  constexpr int IH = (TH - 1) * S + 3;
+  constexpr int R = IH * IW;               // halo pixels = N of the expand MMA = TMEM columns per accumulator
+  constexpr int RP = (R + 15) & ~15;
+  constexpr int NPIX = TH * TW;
+  constexpr int MG = NPIX > 64 ? 2 : 1;    // 64-pixel groups of the project A operand
+  constexpr int NRO = TH / 4;              // output rows per warp
+  constexpr int NRI = (NRO - 1) * S + 3;   // input rows per warp
+  constexpr int NPK = (IW + 1) / 2;        // packed fp16 pairs per input row
+  static_assert(RP <= 256 && NPIX <= 128 && TH % 4 == 0, "tile shape");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sX = smem + g.off_X;     // [NX][kb_in][RP rows][xrb B] swizzled K-major (B operand of expand)
+  uint8_t* sA2 = smem + g.off_A2;   // [2][16 k-groups][MG][1024 B] swizzled MN-major (A operand of project)
+  uint8_t* sW = smem + g.off_W;     // [NS] chunk images: WE | WP | depthwise taps + bias
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bars);
+  uint64_t* bar_e = bars;            // [2] expand(c) retired              -> D1[c & 1] full
+  uint64_t* bar_p = bars + 2;        // [2] project(c) retired             -> A2[c & 1] + weight slot free, D2 progress
+  uint64_t* bar_d1 = bars + 4;       // [2] D1[c & 1] drained by the compute warps (16 arrivals)
+  uint64_t* bar_a2 = bars + 6;       // [2] A2[c & 1] written (16 arrivals)
+  uint64_t* bar_d2 = bars + 8;       // [1] D2 drained by the epilogue (16 arrivals)
+  uint64_t* bar_x = bars + 9;        // [3] input tile landed (16 arrivals)
+  uint64_t* bar_w = bars + 12;       // [8] weight chunk image landed (tx)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_issuer = warp == CPL_NT / 32;
+  const int n_chunks = g.n_chunks, NS = g.NS, NX = g.NX;
+  const int my_tiles = (g.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int Ctot = my_tiles * n_chunks;
+  const bool streaming = NS < n_chunks;
+  tc::pdl_launch_dependents();
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+    for (int i = 4; i < 12; ++i) tc::mbar_init(&bars[i], CPL_NT / 32);
+    for (int i = 12; i < 20; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, g.tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d2 = tmem_base + 2u * RP;
+
+  auto tile_pos = [&](int t, int& tx, int& ty, int& img) {
+    int k = (int)blockIdx.x + t * (int)gridDim.x;
+    tx = k % g.tiles_x;
+    k /= g.tiles_x;
+    ty = k % g.tiles_y;
+    img = k / g.tiles_y;
+  };
+
+  if (is_issuer) {
+    // =========================================================================================== issuing thread
+    if (lane == 0) {
+      const int pre = streaming ? min(NS, Ctot) : n_chunks;
+      for (int c = 0; c < pre; ++c) {   // weights do not depend on the predecessor kernel: before pdl_wait
+        tc::mbar_expect_tx(&bar_w[c], g.blob_bytes);
+        bulk_load(sW + (size_t)c * g.blob_bytes, wblob + (size_t)(c % n_chunks) * g.blob_bytes, g.blob_bytes, &bar_w[c]);
+      }
+      const uint32_t idesc_e = tc::make_idesc_f16(RP);
+      const uint32_t idesc_p = tc::make_idesc_f16(g.cout_pad) | (KM ? 0u : (1u << 15));   // A operand MN-major
+      int t = 0, j = 0;      // tile / chunk-in-tile of chunk c
+      int pt = 0, pj = 0;    // ... of chunk c - 1
+      for (int c = 0; c <= Ctot; ++c) {
+        if (streaming && c >= 2 && c - 2 + NS < Ctot) {   // the slot of chunk c-2 is free once project(c-2) has retired
+          const int k = c - 2, slot = k % NS;
+          tc::mbar_wait(&bar_p[k & 1], (uint32_t)((k >> 1) & 1));
+          tc::mbar_expect_tx(&bar_w[slot], g.blob_bytes);
+          bulk_load(sW + (size_t)slot * g.blob_bytes, wblob + (size_t)((k + NS) % n_chunks) * g.blob_bytes, g.blob_bytes,
+                    &bar_w[slot]);
+        }
+        if (c < Ctot) {
+          const int slot = streaming ? c % NS : j;
+          tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
+          if (j == 0) tc::mbar_wait(&bar_x[t % NX], (uint32_t)((t / NX) & 1));
+          if (c >= 2) tc::mbar_wait(&bar_d1[c & 1], (uint32_t)(((c >> 1) - 1) & 1));
+          tc::fence_after_sync();
+          const uint8_t* we = sW + (size_t)slot * g.blob_bytes;
+          const uint8_t* xb = sX + (size_t)(t % NX) * g.x_buf_bytes;
+          const uint32_t d1 = tmem_base + (uint32_t)((c & 1) * RP);
+          int k16 = 0;
+          for (int kb = 0; kb < g.kb_in; ++kb) {
+            const uint64_t da = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(we + (size_t)kb * 128 * 128))
+                                             : tc::make_sdesc_sw64(tc::smem_u32(we));
+            const uint64_t db = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(xb + (size_t)kb * RP * 128))
+                                             : tc::make_sdesc_sw64(tc::smem_u32(xb));
+            const int nk = min(g.xrb == 128 ? 4 : 2, g.nk16 - k16);
+            for (int k = 0; k < nk; ++k, ++k16)
+              tc::umma_f16(d1, tc::sdesc_advance_k16(da, k), tc::sdesc_advance_k16(db, k), idesc_e, k16 > 0 ? 1u : 0u);
+          }
+          tc::umma_commit(&bar_e[c & 1]);
+        }
+        if (c >= 1) {
+          const int pc = c - 1;
+          tc::mbar_wait(&bar_a2[pc & 1], (uint32_t)((pc >> 1) & 1));
+          if (pj == 0 && pt >= 1) tc::mbar_wait(&bar_d2[0], (uint32_t)((pt - 1) & 1));
+          tc::fence_after_sync();
+          const int slot = streaming ? pc % NS : pj;
+          const uint8_t* wp = sW + (size_t)slot * g.blob_bytes + g.we_bytes;
+          const uint8_t* a2 = sA2 + (size_t)(pc & 1) * g.a2_buf_bytes;
+          const int valid = min(128, g.Cexp - pj * 128);
+          const int nk = (valid + 15) >> 4;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t da = KM ? tc::make_sdesc_sw128(tc::smem_u32(a2 + (size_t)(k >> 2) * 16384 + (k & 3) * 32))
+                                   : make_sdesc_mn_sw128(tc::smem_u32(a2 + (size_t)k * 2 * MG * 1024), 1024u, MG * 1024u);
+            const uint64_t db = tc::make_sdesc_sw128(tc::smem_u32(wp + (size_t)(k >> 2) * g.cout_pad * 128 + (k & 3) * 32));
+            tc::umma_f16(tmem_d2, da, db, idesc_p, (pj > 0 || k > 0) ? 1u : 0u);
+          }
+          tc::umma_commit(&bar_p[pc & 1]);
+        }
+        pt = t;
+        pj = j;
+        if (++j == n_chunks) { j = 0; ++t; }
+      }
+    }
+  } else {
+    // =========================================================================================== compute warps
+    const int lg = warp & 3, rg = warp >> 2;
+    const uint32_t tm_lane = (uint32_t)(lg * 32) << 16;
+
+    // input halo tile -> swizzled K-major rows (zero outside the image and in the K padding, ones unit inside)
+    auto load_x = [&](int t, int xbuf) {
+      int tx, ty, img;
+      tile_pos(t, tx, ty, img);
+      const int iy0 = ty * TH * S - g.pad_t, ix0 = tx * TW * S - g.pad_l;
+      const __half* src = in + (size_t)img * g.Hi * g.Wi * g.Cin;
+      const uint32_t xbase = tc::smem_u32(sX) + (uint32_t)xbuf * g.x_buf_bytes;
+      const int half_units = (g.units + 1) >> 1;
+      for (int r = tid >> 1; r < R; r += CPL_NT / 2) {   // two threads per pixel row
+        const int ry = r / IW, rx = r - ry * IW;
+        const int iy = iy0 + ry, ix = ix0 + rx;
+        const bool inb = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+        const __half* gp = src + ((size_t)iy * g.Wi + ix) * g.Cin;
+        const int u0 = (tid & 1) * half_units, u1 = min(g.units, u0 + half_units);
+        for (int u = u0; u < u1; ++u) {
+          const __half* sp = u < g.ones_unit ? gp + u * 8 : ones;
+          const int nbytes = (inb && u <= g.ones_unit) ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+          const uint32_t dst = g.xrb == 128 ? xbase + (uint32_t)(u >> 3) * (uint32_t)(RP * 128) + (uint32_t)r * 128u +
+                                                  (uint32_t)(((u & 7) ^ (r & 7)) << 4)
+                                            : xbase + (uint32_t)r * 64u + (uint32_t)((u ^ ((r >> 1) & 3)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(nbytes ? sp : ones), "r"(nbytes)
+                       : "memory");
+        }
+      }
+    };
+    auto x_landed = [&](int xbuf) {   // this thread's copies have landed and are visible to the tensor core
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_x[xbuf]);
+    };
+
+    // D2 + bias (+residual) -> fp16 NHWC for the tile at (tx, ty, img) whose last chunk was lc
+    auto epilogue = [&](int tx, int ty, int img, int lc) {
+      tc::mbar_wait(&bar_p[lc & 1], (uint32_t)((lc >> 1) & 1));
+      tc::fence_after_sync();
+      if (lg * 32 < NPIX) {
+        const int p = lg * 32 + lane;
+        const int oy = ty * TH + p / TW, ox = tx * TW + p % TW;
+        const bool valid = p < NPIX && oy < g.Ho && ox < g.Wo;
+        const long long opix = ((long long)img * g.Ho + oy) * g.Wo + ox;
+        for (int cc = rg * 16; cc < g.cout_pad; cc += 64) {
+          uint32_t v[16];
+          tc::tmem_ld16(tmem_d2 + tm_lane + (uint32_t)cc, v);
+          tc::tmem_ld_wait();
+          if (!valid) continue;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n = cc + 8 * h;
+            if (n >= g.Cout) break;
+            const float4 bb0 = __ldg(reinterpret_cast<const float4*>(bp + n)), bb1 = __ldg(reinterpret_cast<const float4*>(bp + n) + 1);
+            float f[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += __uint_as_float(v[8 * h + i]);
+            if (g.residual) {
+              const uint4 rq = *reinterpret_cast<const uint4*>(in + opix * g.Cin + n);
+              const __half2* hq = reinterpret_cast<const __half2*>(&rq);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 r2 = __half22float2(hq[i]);
+                f[2 * i] += r2.x;
+                f[2 * i + 1] += r2.y;
+              }
+            }
+            uint4 o;
+            __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            *reinterpret_cast<uint4*>(out + opix * g.Cout + n) = o;
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_d2[0]);
+    };
+
+    tc::pdl_wait();   // the input tensor is the predecessor's output
+    for (int i = 0; i < NX - 1 && i < my_tiles; ++i) {
+      load_x(i, i);
+      x_landed(i);
+    }
+
+    int c = 0;
+    int ptx = 0, pty = 0, pimg = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      int tx, ty, img;
+      tile_pos(t, tx, ty, img);
+      for (int j = 0; j < n_chunks; ++j, ++c) {
+        const bool prefetch = j == 0 && t + NX - 1 < my_tiles;
+        if (prefetch) {
+          load_x(t + NX - 1, (t + NX - 1) % NX);
+          if (NX == 1) x_landed(0);   // no look-ahead: this tile's own expand waits for it
+        }
+        const int slot = streaming ? c % NS : j;
+        tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
+        const uint32_t* dwp = reinterpret_cast<const uint32_t*>(sW + (size_t)slot * g.blob_bytes + g.we_bytes + g.wp_bytes) +
+                              lg * 32 + lane;
+        uint32_t wv[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) wv[i] = dwp[i * 128];
+        const float bias = __uint_as_float(dwp[5 * 128]);
+        const bool active = j * 128 + lg * 32 < g.Cexp;   // warp-uniform: this lane group holds real channels
+        tc::mbar_wait(&bar_e[c & 1], (uint32_t)((c >> 1) & 1));
+        tc::fence_after_sync();
+        uint32_t hrow[NRI][NPK];
+        if (active) {
+          uint32_t v[NRI][IW + 1];
+          const uint32_t tbase = tmem_base + tm_lane + (uint32_t)((c & 1) * RP) + (uint32_t)(rg * NRO * S * IW);
+#pragma unroll
+          for (int i = 0; i < NRI; ++i) {
+            uint32_t(&vr)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[i][0]);
+            tc::tmem_ld16(tbase + (uint32_t)(i * IW), vr);
+            if constexpr (S == 1) tmem_ld2(tbase + (uint32_t)(i * IW + 16), v[i][16], v[i][17]);
+            else tmem_ld1(tbase + (uint32_t)(i * IW + 16), v[i][16]);
+          }
+          tc::tmem_ld_wait();
+          if (g.dbg && blockIdx.x == 0 && c == 0) {
+#pragma unroll
+            for (int i = 0; i < NRI; ++i)
+#pragma unroll
+              for (int k = 0; k < 18; ++k)
+                g.dbg[((size_t)(rg * 128 + lg * 32 + lane) * NRI + i) * 18 + k] = k < IW ? __uint_as_float(v[i][k]) : 0.f;
+          }
+          if constexpr (S == 2) {
+#pragma unroll
+            for (int i = 0; i < NRI; ++i) v[i][17] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < NRI; ++i)
+#pragma unroll
+            for (int k = 0; k < NPK; ++k)
+              hrow[i][k] = relu6_pack(__uint_as_float(v[i][2 * k]), __uint_as_float(v[i][2 * k + 1]));
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_d1[c & 1]);
+        if (c >= 2) tc::mbar_wait(&bar_p[c & 1], (uint32_t)(((c - 2) >> 1) & 1));   // project(c-2) has read A2[c & 1]
+        if (active) {
+          const int kg = lg * 4 + (lane >> 3), jj = lane & 7;
+          uint8_t* a2 = sA2 + (size_t)(c & 1) * g.a2_buf_bytes + (size_t)kg * (MG * 1024) + jj * 128;
+#pragma unroll
+          for (int ro = 0; ro < NRO; ++ro) {
+            float acc[TW];
+#pragma unroll
+            for (int x = 0; x < TW; ++x) acc[x] = bias;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint32_t* hr = hrow[ro * S + ky];
+#pragma unroll
+              for (int x = 0; x < TW; ++x) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {   // tap (ky, kx) reads input column x * S + kx
+                  const int ix = x * S + kx, tap = ky * 3 + kx;
+                  acc[x] = fmah_sel(hr[ix >> 1], ix & 1, wv[tap >> 1], tap & 1, acc[x]);
+                }
+              }
+            }
+            // output row r = rg * NRO + ro of the tile: pixels p = r * TW + x, 16-byte chunk (p % 64) / 8 of atom p / 64
+            const int r = rg * NRO + ro;
+            const int p0 = r * TW;
+            if constexpr (KM) {   // K-major A2 (debug / fallback): [2 k-blocks][128 pixel rows][128 B], 2-byte stores
+              const int chl = lg * 32 + lane;
+              uint8_t* kbase = sA2 + (size_t)(c & 1) * g.a2_buf_bytes + (size_t)(chl >> 6) * 16384 + (chl & 7) * 2;
+              const int kc = (chl & 63) >> 3;
+#pragma unroll
+              for (int x = 0; x < TW; x += 2) {
+                const uint32_t pk = relu6_pack(acc[x], acc[x + 1]);
+                const int p = p0 + x;
+                *reinterpret_cast<uint16_t*>(kbase + (size_t)p * 128 + ((kc ^ (p & 7)) << 4)) = (uint16_t)(pk & 0xffffu);
+                *reinterpret_cast<uint16_t*>(kbase + (size_t)(p + 1) * 128 + ((kc ^ ((p + 1) & 7)) << 4)) = (uint16_t)(pk >> 16);
+              }
+              continue;
+            }
+            uint8_t* arow = a2 + (size_t)(p0 >> 6) * 1024;
+#pragma unroll
+            for (int h = 0; h < TW / 8; ++h) {
+              uint4 o;
+              o.x = relu6_pack(acc[8 * h + 0], acc[8 * h + 1]);
+              o.y = relu6_pack(acc[8 * h + 2], acc[8 * h + 3]);
+              o.z = relu6_pack(acc[8 * h + 4], acc[8 * h + 5]);
+              o.w = relu6_pack(acc[8 * h + 6], acc[8 * h + 7]);
+              const int chunk = ((p0 & 63) >> 3) + h;
+              *reinterpret_cast<uint4*>(arow + ((chunk ^ jj) << 4)) = o;
+            }
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_a2[c & 1]);
+        if (prefetch && NX > 1) x_landed((t + NX - 1) % NX);
+        if (j == 0 && t >= 1) epilogue(ptx, pty, pimg, c - 1);   // previous tile, hidden behind project(c)
+      }
+      ptx = tx; pty = ty; pimg = img;
+    }
+    if (my_tiles > 0) epilogue(ptx, pty, pimg, Ctot - 1);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+// Builds the per-chunk weight images: WE (A operand of expand: 128 channel rows x K, K-major, swizzled, bias in the
+// "ones" column), WP (B operand of project: cout_pad rows x 128 channels as two 64-channel k-blocks, K-major, 128B
+// swizzle), depthwise taps (5 words of packed fp16 pairs per lane) + depthwise bias.
+__global__ void cpl_pack_kernel(CplGeom g, const __half* __restrict__ we, int we_ld, const float* __restrict__ be,
+                                const __half* __restrict__ wp, int wp_ld, const float* __restrict__ wd,
+                                const float* __restrict__ bd, uint8_t* __restrict__ blob) {
+  const int K = g.units * 8;
+  const long long per_chunk = 128LL * K + (long long)g.cout_pad * 128 + 6 * 128;
+  const long long total = per_chunk * g.n_chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i / per_chunk);
+    long long e = i - (long long)j * per_chunk;
+    uint8_t* base = blob + (size_t)j * g.blob_bytes;
+    if (e < 128LL * K) {
+      const int r = (int)(e / K), k = (int)(e % K);
+      const int ch = j * 128 + r;
+      __half v = __float2half_rn(0.f);
+      if (ch < g.Cexp) {
+        if (k < g.Cin) v = we[(size_t)ch * we_ld + k];
+        else if (k == g.Cin) v = __float2half_rn(be[ch]);                                      // bias, high part
+        else if (k == g.Cin + 1) v = __float2half_rn(be[ch] - __half2float(__float2half_rn(be[ch])));   // low part
+      }
+      size_t off;
+      if (g.xrb == 128) {
+        const int kb = k >> 6, kk = k & 63;
+        off = (size_t)kb * 128 * 128 + (size_t)r * 128 + (size_t)(((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2;
+      } else {
+        off = (size_t)r * 64 + (size_t)(((k >> 3) ^ ((r >> 1) & 3)) << 4) + (k & 7) * 2;
+      }
+      *reinterpret_cast<__half*>(base + off) = v;
+      continue;
+    }
+    e -= 128LL * K;
+    if (e < (long long)g.cout_pad * 128) {
+      const int n = (int)(e / 128), k = (int)(e % 128);
+      const int ch = j * 128 + k;
+      __half v = __float2half_rn(0.f);
+      if (n < g.Cout && ch < g.Cexp) v = wp[(size_t)n * wp_ld + ch];
+      const int kb = k >> 6, kk = k & 63;
+      const size_t off = (size_t)kb * g.cout_pad * 128 + (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
+      *reinterpret_cast<__half*>(base + g.we_bytes + off) = v;
+      continue;
+    }
+    e -= (long long)g.cout_pad * 128;
+    const int word = (int)(e / 128), l = (int)(e % 128);
+    const int ch = j * 128 + l;
+    uint32_t v = 0;
+    if (ch < g.Cexp) {
+      if (word < 5) {
+        const __half lo = __float2half_rn(wd[(size_t)(2 * word) * g.Cexp + ch]);
+        const __half hi = 2 * word + 1 < 9 ? __float2half_rn(wd[(size_t)(2 * word + 1) * g.Cexp + ch]) : __float2half_rn(0.f);
+        v = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+      } else {
+        v = __float_as_uint(bd[ch]);
+      }
+    }
+    reinterpret_cast<uint32_t*>(base + g.we_bytes + g.wp_bytes)[word * 128 + l] = v;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host side
+struct CplPlan {
+  CplGeom g;          // everything that does not depend on the tile shape / batch
+  uint8_t* d_blob = nullptr;
+  const __half* d_ones = nullptr;
+  int pin_th = 0, pin_ns = 0, pin_nx = 0;
+};
+
+CplPlan* cpl_new() { return new CplPlan(); }
+void cpl_delete(CplPlan* p) { delete p; }
+
+static __half* cpl_ones(hfb_ctx* ctx) {   // 16 bytes {1, 1, 0, 0, 0, 0, 0, 0}: the "ones" unit of in-image pixels
+  __half* d = nullptr;
+  if (ctx->dalloc(&d, 8) != HFB_OK) return nullptr;
+  const __half h[8] = {__float2half(1.f), __float2half(1.f), __float2half(0.f), __float2half(0.f),
+                       __float2half(0.f), __float2half(0.f), __float2half(0.f), __float2half(0.f)};
+  if (cudaMemcpy(d, h, 16, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  return d;
+}
+
+static bool cpl_layout(CplGeom& g, int S, int TH, int NS, int NX) {
+  const int TW = S == 1 ? 16 : 8;
+  const int IW = (TW - 1) * S + 3, IH = (TH - 1) * S + 3;
+  const int R = IH * IW, RP = (R + 15) & ~15;
+  const int NPIX = TH * TW, MG = NPIX > 64 ? 2 : 1;
+  if (RP > 256 || 2 * RP + g.cout_pad > 512) return false;
+  auto al = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  g.NS = NS;
+  g.NX = NX;
+  g.x_buf_bytes = al((uint32_t)(g.kb_in * RP * g.xrb));
+  g.a2_buf_bytes = (uint32_t)(16 * (getenv("HFB_CPL_KM") ? 2 : MG) * 1024);
+  uint32_t off = 0;
+  g.off_X = off;  off += (uint32_t)NX * g.x_buf_bytes;
+  g.off_A2 = off; off += 2 * g.a2_buf_bytes;
+  g.off_W = off;  off += al((uint32_t)NS * g.blob_bytes);
+  g.off_bars = off; off += 256;
+  g.smem_bytes = off + 1024;
+  uint32_t cols = 32;
+  while ((int)cols < 2 * RP + g.cout_pad) cols <<= 1;
+  g.tmem_cols = cols;
+  return g.smem_bytes <= 227u * 1024u;
+}
+
+// Returns HFB_ERR_CAPACITY when the block cannot run in this formulation (the caller keeps another path).
+int cpl_plan(hfb_ctx* ctx, CplPlan& cp, const BlockW& bw, int Hi, int Wi, int Ho, int Wo, int pad_t, int pad_l) {
+  if (!bw.has_expand || bw.cin % 8 != 0 || bw.cout % 8 != 0) return HFB_ERR_CAPACITY;
+  CplGeom& g = cp.g;
+  memset(&g, 0, sizeof(g));
+  g.Hi = Hi; g.Wi = Wi; g.Ho = Ho; g.Wo = Wo;
+  g.Cin = bw.cin; g.Cexp = bw.cexp; g.Cout = bw.cout;
+  g.pad_t = pad_t; g.pad_l = pad_l;
+  g.residual = bw.residual ? 1 : 0;
+  g.n_chunks = (bw.cexp + 127) / 128;
+  g.ones_unit = bw.cin / 8;
+  g.units = (g.ones_unit + 1 + 1) & ~1;        // K = units * 8, multiple of 16
+  if (g.units * 8 > 128) return HFB_ERR_CAPACITY;
+  g.xrb = g.units <= 4 ? 64 : 128;
+  g.kb_in = g.xrb == 64 ? 1 : (g.units + 7) / 8;
+  g.nk16 = g.units / 2;
+  g.cout_pad = (bw.cout + 15) & ~15;
+  if (g.cout_pad > 256) return HFB_ERR_CAPACITY;
+  g.we_bytes = (uint32_t)(g.kb_in * 128 * g.xrb);
+  g.wp_bytes = (uint32_t)(2 * g.cout_pad * 128);
+  g.blob_bytes = g.we_bytes + g.wp_bytes + CPL_DW_BYTES;
+  auto env_int = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
+  cp.pin_th = env_int("HFB_CPL_TH");
+  cp.pin_ns = env_int("HFB_CPL_NS");
+  cp.pin_nx = env_int("HFB_CPL_NX");
+  // at least one configuration must fit
+  bool ok = false;
+  for (int th : {8, 4})
+    for (int ns : {g.n_chunks, 2})
+      if (cpl_layout(g, bw.stride, bw.stride == 2 ? 4 : th, std::min(ns, g.n_chunks), 1)) ok = true;
+  if (!ok) return HFB_ERR_CAPACITY;
+  cp.d_ones = cpl_ones(ctx);
+  if (!cp.d_ones) return HFB_ERR_CUDA;
+  HFB_TRY(ctx->dalloc(&cp.d_blob, (size_t)g.n_chunks * g.blob_bytes));
+  HFB_CUDA(ctx, cudaMemsetAsync(cp.d_blob, 0, (size_t)g.n_chunks * g.blob_bytes, ctx->stream));
+  cpl_pack_kernel<<<64, 256, 0, ctx->stream>>>(g, bw.expand.w, bw.expand.Kp, bw.expand.b, bw.project.w, bw.project.Kp,
+                                               bw.wd, bw.bd, cp.d_blob);
+  HFB_CHECK_LAUNCH(ctx, "cpl_pack");
+  return HFB_OK;
+}
+
+// Tile shape / ring depth for a batch: stride 2 -> 4 x 8 tiles; stride 1 -> 8 x 16 when that still gives most SMs a
+// tile (or the weights would not stay resident otherwise), else 4 x 16.  Weights resident when they fit, else the
+// deepest ring that fits; NX = 3 for single-chunk layers (the next expand must not wait for its input tile), else 2,
+// 1 when every CTA has a single tile.
+static bool cpl_configure(const hfb_ctx* ctx, const CplPlan& cp, int stride, int B, CplGeom& g, int& TH) {
+  g = cp.g;
+  g.B = B;
+  const int TW = stride == 1 ? 16 : 8;
+  g.tiles_x = (g.Wo + TW - 1) / TW;
+  auto try_cfg = [&](int th, bool need_resident) -> bool {
+    g.tiles_y = (g.Ho + th - 1) / th;
+    g.total_tiles = g.tiles_x * g.tiles_y * B;
+    const int per_cta = (g.total_tiles + ctx->n_sm - 1) / ctx->n_sm;
+    int nx_want = per_cta <= 1 ? 1 : (g.n_chunks == 1 ? 3 : 2);
+    if (cp.pin_nx) nx_want = cp.pin_nx;
+    for (int nx = nx_want; nx >= (per_cta <= 1 ? 1 : 2); --nx) {
+      for (int ns : {g.n_chunks, 4, 3, 2}) {
+        if (ns > g.n_chunks || ns > 8) continue;
+        if (cp.pin_ns && ns != std::min(cp.pin_ns, g.n_chunks)) continue;
+        if (need_resident && ns < g.n_chunks) continue;
+        if (cpl_layout(g, stride, th, ns, nx)) return true;
+      }
+    }
+    return false;
+  };
+  if (stride == 2) {
+    TH = 4;
+    return try_cfg(4, false);
+  }
+  if (cp.pin_th) {
+    TH = cp.pin_th;
+    return try_cfg(TH, false);
+  }
+  const int tiles8 = g.tiles_x * ((g.Ho + 7) / 8) * B;
+  const bool prefer8 = tiles8 * 10 >= ctx->n_sm * 6;
+  for (bool need_res : {true, false}) {
+    for (int th : {prefer8 ? 8 : 4, prefer8 ? 4 : 8}) {
+      if (try_cfg(th, need_res)) {
+        TH = th;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+int cpl_tiles(const hfb_ctx* ctx, const CplPlan& cp, int stride, int B) {
+  CplGeom g;
+  int th;
+  if (!cpl_configure(ctx, cp, stride, B, g, th)) return 0;
+  return g.total_tiles;
+}
+
+template <int S, int TH, bool KM>
+static int cpl_launch(hfb_ctx* ctx, const CplPlan& cp, const CplGeom& g, const BlockW& bw, const __half* in, __half* out) {
+  static size_t configured = 0;   // per instantiation
+  if (g.smem_bytes > configured) {
+    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_cpl_kernel<S, TH, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)g.smem_bytes));
+    configured = g.smem_bytes;
+  }
+  const int grid = std::min(g.total_tiles, ctx->n_sm);
+  hfb_launch(ctx, fused_block_cpl_kernel<S, TH, KM>, grid, CPL_NT + 32, g.smem_bytes, g, in, (const uint8_t*)cp.d_blob,
+             bw.project.b, cp.d_ones, out);
+  HFB_CHECK_LAUNCH(ctx, "fused_block_cpl");
+  return HFB_OK;
+}
+
+int cpl_run(hfb_ctx* ctx, const CplPlan& cp, const BlockW& bw, const __half* in, __half* out, int B) {
+  CplGeom g;
+  int TH = 0;
+  if (!cpl_configure(ctx, cp, bw.stride, B, g, TH)) {
+    ctx->set_error("internal: fused block (cpl) has no configuration for this batch");
+    return HFB_ERR_STATE;
+  }
+  static bool traced[32] = {false};
+  if (ctx->trace && bw.layer < 32 && !traced[bw.layer]) {
+    traced[bw.layer] = true;
+    fprintf(stderr, "hfnet_b200: cpl layer_%d: S=%d TH=%d chunks=%d units=%d xrb=%d NS=%d NX=%d smem=%u tmem=%u tiles=%d\n",
+            bw.layer, bw.stride, TH, g.n_chunks, g.units, g.xrb, g.NS, g.NX, g.smem_bytes, g.tmem_cols, g.total_tiles);
+  }
+  static const bool km = getenv("HFB_CPL_KM") != nullptr;   // K-major project operand (debug / fallback)
+  if (km) {
+    if (bw.stride == 1 && TH == 8) return cpl_launch<1, 8, true>(ctx, cp, g, bw, in, out);
+    if (bw.stride == 1 && TH == 4) return cpl_launch<1, 4, true>(ctx, cp, g, bw, in, out);
+    if (bw.stride == 2 && TH == 4) return cpl_launch<2, 4, true>(ctx, cp, g, bw, in, out);
+  }
+  static const int dbg_layer = getenv("HFB_CPL_DBG") ? atoi(getenv("HFB_CPL_DBG")) : 0;
+  static int dbg_done = 0;
+  if (dbg_layer == bw.layer && !dbg_done) {   // needs HFB_NO_GRAPH=1
+    dbg_done = 1;
+    const size_t n = 4 * 128 * 4 * 18;
+    float* d = nullptr;
+    HFB_CUDA(ctx, cudaMalloc(&d, n * 4));
+    HFB_CUDA(ctx, cudaMemset(d, 0, n * 4));
+    g.dbg = d;
+    int rc = HFB_ERR_STATE;
+    if (bw.stride == 1 && TH == 8) rc = cpl_launch<1, 8, false>(ctx, cp, g, bw, in, out);
+    if (bw.stride == 1 && TH == 4) rc = cpl_launch<1, 4, false>(ctx, cp, g, bw, in, out);
+    if (bw.stride == 2 && TH == 4) rc = cpl_launch<2, 4, false>(ctx, cp, g, bw, in, out);
+    HFB_TRY(rc);
+    HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<float> h(n);
+    HFB_CUDA(ctx, cudaMemcpy(h.data(), d, n * 4, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen("gpurun_out/cpl_dbg.bin", "wb")) {
+      fwrite(h.data(), 4, n, f);
+      fclose(f);
+    }
+    cudaFree(d);
+    return HFB_OK;
+  }
+  if (bw.stride == 1 && TH == 8) return cpl_launch<1, 8, false>(ctx, cp, g, bw, in, out);
+  if (bw.stride == 1 && TH == 4) return cpl_launch<1, 4, false>(ctx, cp, g, bw, in, out);
+  if (bw.stride == 2 && TH == 4) return cpl_launch<2, 4, false>(ctx, cp, g, bw, in, out);
+  ctx->set_error("internal: no fused block (cpl) kernel for this tile shape");
+  return HFB_ERR_STATE;
+}
+
+double cpl_bytes(const CplPlan& cp, int B) {   // algorithmic: input once + output once (+ residual re-read) + weights
+  const CplGeom& g = cp.g;
+  return 2.0 * B * ((double)g.Hi * g.Wi * g.Cin + (double)g.Ho * g.Wo * g.Cout * (g.residual ? 2 : 1)) +
+         2.0 * ((double)g.Cin * g.Cexp + (double)g.Cexp * g.Cout) + 4.0 * 10 * g.Cexp;
+}
+double cpl_flops(const CplPlan& cp, int B) {
+  const CplGeom& g = cp.g;
+  return 2.0 * B * ((double)g.Hi * g.Wi * g.Cin * g.Cexp + (double)g.Ho * g.Wo * g.Cexp * (9 + g.Cout));
+}
