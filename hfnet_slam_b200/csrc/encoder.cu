@@ -469,7 +469,8 @@ double fused_block_flops(const FusedPlan& fp, int B);
 struct CplPlan;
 CplPlan* cpl_new();
 void cpl_delete(CplPlan* p);
-int cpl_plan(hfb_ctx* ctx, CplPlan& cp, const BlockW& bw, int Hi, int Wi, int Ho, int Wo, int pad_t, int pad_l);
+int cpl_plan(hfb_ctx* ctx, CplPlan& cp, const BlockW& bw, const __half* in, int Bmax, int Hi, int Wi, int Ho, int Wo,
+             int pad_t, int pad_l);
 int cpl_run(hfb_ctx* ctx, const CplPlan& cp, const BlockW& bw, const __half* in, __half* out, int B);
 int cpl_tiles(const hfb_ctx* ctx, const CplPlan& cp, int stride, int B);
 double cpl_bytes(const CplPlan& cp, int B);
@@ -558,7 +559,8 @@ int encoder_plan(hfb_ctx* ctx) {
       static const long cpl_mask = getenv("HFB_CPL_LAYERS") ? strtol(getenv("HFB_CPL_LAYERS"), nullptr, 0) : -1L;
       if (ctx->fused_blocks && ctx->fused_impl != 1 && ((cpl_mask >> bw.layer) & 1)) {
         bp.cpl = cpl_new();
-        const int rc = cpl_plan(ctx, *bp.cpl, bw, bp.Hi, bp.Wi, bp.Ho, bp.Wo, bp.pad_t, bp.pad_l);
+        const int rc = cpl_plan(ctx, *bp.cpl, bw, lv.act[bw.layer - 1], Bm, bp.Hi, bp.Wi, bp.Ho, bp.Wo, bp.pad_t,
+                                bp.pad_l);
         if (rc == HFB_ERR_CAPACITY) {
           cpl_delete(bp.cpl);
           bp.cpl = nullptr;

@@ -37,15 +37,17 @@ struct CplGeom {
   int kb_in;         // k-blocks of 64 channels (1 when xrb == 64)
   int nk16;          // K steps of the expand MMA
   int cout_pad;      // Cout rounded up to 16 (project N)
-  int NS, NX;        // weight ring slots (== n_chunks: resident), input tile buffers
+  int NS, NX, ND2;   // weight ring slots (== n_chunks: resident), input tile buffers, project accumulators
   uint32_t we_bytes, wp_bytes, blob_bytes;
   uint32_t x_buf_bytes, a2_buf_bytes;
   uint32_t off_X, off_A2, off_W, off_bars, smem_bytes;
   uint32_t tmem_cols;
-  float* dbg;        // HFB_CPL_DBG=<layer>: CTA 0 dumps the raw expand accumulators of its first chunk ([rg][lane 0..127][row][18])
+  long long* dbg;    // HFB_CPL_DBG=<layer>: clock stamps of CTA 0, [role 0..4][chunk or tile 0..63][8]
 };
 
 constexpr int CPL_NT = 512;          // compute threads
+constexpr int CPL_LOADERS = 64;      // input-tile loader threads (two warps)
+constexpr int CPL_THREADS = 768;     // 16 depthwise warps + 2 issuer warps + 2 loader warps + 4 epilogue warps
 constexpr int CPL_DW_BYTES = 6 * 128 * 4;   // per chunk: 5 words of packed fp16 taps + fp32 bias per lane
 
 __device__ __forceinline__ uint32_t relu6_pack(float lo, float hi) {
@@ -101,12 +103,20 @@ __device__ __forceinline__ uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint
          (1ull << 46) | (2ull << 61);
 }
 
-// S = stride, TH x TW = output tile (TW = 16 for stride 1, 8 for stride 2); each of the 16 compute warps owns TMEM lane
-// group (warp & 3) = 32 channels of the chunk and row group (warp >> 2) = TH / 4 output rows of the tile.
-template <int S, int TH, bool KM>
-__global__ void __launch_bounds__(CPL_NT + 32, 1)
-fused_block_cpl_kernel(const CplGeom g, const __half* __restrict__ in, const uint8_t* __restrict__ wblob,
-                       const float* __restrict__ bp, const __half* __restrict__ ones, __half* __restrict__ out) {
+#define CPL_STAMP(role, idx, k)                                                             \
+  if (g.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 64) g.dbg[(((role) * 64 + (idx)) * 8) + (k)] = clock64()
+
+// S = stride, TH x TW = output tile (TW = 16 for stride 1, 8 for stride 2).  Warp roles (24 warps):
+//   0..15  depthwise: TMEM lane group (warp & 3) = 32 channels of the chunk, row group (warp >> 2) = TH / 4 output rows
+//   16     expand issuer (lane 0): expand(c) goes out as soon as its accumulator buffer has been drained
+//   17     project issuer (lane 0) + weight ring refills
+//   18,19  input-tile loaders (cp.async with asynchronous mbarrier arrival)
+//   20..23 epilogue: one TMEM lane group each, D2 + bias (+residual) -> fp16 NHWC; the only warps that touch global
+//          memory besides the loaders, so the proxy fences of the depthwise warps never wait on global traffic
+template <int S, int TH>
+__global__ void __launch_bounds__(CPL_THREADS, 1)
+fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g, const __half* __restrict__ in,
+                       const uint8_t* __restrict__ wblob, const float* __restrict__ bp, __half* __restrict__ out) {
   constexpr int TW = S == 1 ? 16 : 8;
   constexpr int IW = (TW - 1) * S + 3;
   constexpr int IH = (TH - 1) * S + 3;
@@ -126,17 +136,19 @@ fused_block_cpl_kernel(const CplGeom g, const __half* __restrict__ in, const uin
   uint8_t* sW = smem + g.off_W;     // [NS] chunk images: WE | WP | depthwise taps + bias
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bars);
   uint64_t* bar_e = bars;            // [2] expand(c) retired              -> D1[c & 1] full
-  uint64_t* bar_p = bars + 2;        // [2] project(c) retired             -> A2[c & 1] + weight slot free, D2 progress
-  uint64_t* bar_d1 = bars + 4;       // [2] D1[c & 1] drained by the compute warps (16 arrivals)
+  uint64_t* bar_p = bars + 2;        // [2] project(c) retired             -> A2[c & 1] and the chunk's weight slot free
+  uint64_t* bar_d1 = bars + 4;       // [2] D1[c & 1] drained by the depthwise warps (16 arrivals)
   uint64_t* bar_a2 = bars + 6;       // [2] A2[c & 1] written (16 arrivals)
-  uint64_t* bar_d2 = bars + 8;       // [1] D2 drained by the epilogue (16 arrivals)
-  uint64_t* bar_x = bars + 9;        // [3] input tile landed (16 arrivals)
-  uint64_t* bar_w = bars + 12;       // [8] weight chunk image landed (tx)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* bar_d2 = bars + 8;       // [2] D2[t % ND2] drained by the epilogue warps (4 arrivals)
+  uint64_t* bar_x = bars + 10;       // [3] input tile landed (cp.async arrivals of the loader threads)
+  uint64_t* bar_w = bars + 13;       // [8] weight chunk image landed (tx)
+  uint64_t* bar_xf = bars + 21;      // [3] every expand reading the input tile has retired -> buffer free
+  uint64_t* bar_f = bars + 24;       // [2] last project of the tile retired -> D2[t % ND2] full
+  uint64_t* bar_t = bars + 26;       // [3] TMA of the input tile landed (tx) -> the loaders patch the ones unit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_issuer = warp == CPL_NT / 32;
-  const int n_chunks = g.n_chunks, NS = g.NS, NX = g.NX;
+  const int n_chunks = g.n_chunks, NS = g.NS, NX = g.NX, ND2 = g.ND2;
   const int my_tiles = (g.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int Ctot = my_tiles * n_chunks;
   const bool streaming = NS < n_chunks;
@@ -144,138 +156,199 @@ fused_block_cpl_kernel(const CplGeom g, const __half* __restrict__ in, const uin
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
-    for (int i = 4; i < 12; ++i) tc::mbar_init(&bars[i], CPL_NT / 32);
-    for (int i = 12; i < 20; ++i) tc::mbar_init(&bars[i], 1);
+    for (int i = 4; i < 8; ++i) tc::mbar_init(&bars[i], CPL_NT / 32);
+    for (int i = 8; i < 10; ++i) tc::mbar_init(&bars[i], 4);
+    for (int i = 10; i < 13; ++i) tc::mbar_init(&bars[i], CPL_LOADERS);
+    for (int i = 13; i < 29; ++i) tc::mbar_init(&bars[i], 1);
     tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmX);
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, g.tmem_cols);
+  if (warp == 16) tc::tmem_alloc(tmem_slot, g.tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d2 = tmem_base + 2u * RP;
+  const uint32_t tmem_d2 = tmem_base + 2u * RP;   // D2[b] at + b * cout_pad
 
-  auto tile_pos = [&](int t, int& tx, int& ty, int& img) {
-    int k = (int)blockIdx.x + t * (int)gridDim.x;
-    tx = k % g.tiles_x;
+  // Tile cursors advance by gridDim.x tiles without divisions: (tx, ty, img) += (dx, dy, dimg) with carries.
+  struct TilePos { int tx, ty, img; };
+  TilePos pos0;
+  int step_x, step_y, step_img;
+  {
+    int k = (int)blockIdx.x;
+    pos0.tx = k % g.tiles_x;
     k /= g.tiles_x;
-    ty = k % g.tiles_y;
-    img = k / g.tiles_y;
+    pos0.ty = k % g.tiles_y;
+    pos0.img = k / g.tiles_y;
+    k = (int)gridDim.x;
+    step_x = k % g.tiles_x;
+    k /= g.tiles_x;
+    step_y = k % g.tiles_y;
+    step_img = k / g.tiles_y;
+  }
+  auto advance = [&](TilePos& p) {
+    p.tx += step_x;
+    int carry = 0;
+    if (p.tx >= g.tiles_x) { p.tx -= g.tiles_x; carry = 1; }
+    p.ty += step_y + carry;
+    carry = 0;
+    if (p.ty >= g.tiles_y) { p.ty -= g.tiles_y; carry = 1; }
+    p.img += step_img + carry;
   };
 
-  if (is_issuer) {
-    // =========================================================================================== issuing thread
+  // Register re-balancing between warpgroups: the 8 service warps give registers back, the depthwise warps take them.
+  if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+  if (warp == 16) {
+    // =========================================================================================== expand issuer
+    if (lane == 0) {
+      const uint32_t idesc_e = tc::make_idesc_f16(RP);
+      const uint64_t desc_w0 = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(sW)) : tc::make_sdesc_sw64(tc::smem_u32(sW));
+      const uint64_t desc_x0 = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(sX)) : tc::make_sdesc_sw64(tc::smem_u32(sX));
+      int t = 0, j = 0;
+      for (int c = 0; c < Ctot; ++c) {
+        const int slot = streaming ? c % NS : j;
+        CPL_STAMP(1, c, 0);
+        tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
+        CPL_STAMP(1, c, 1);
+        if (j == 0) tc::mbar_wait(&bar_x[t % NX], (uint32_t)((t / NX) & 1));
+        CPL_STAMP(1, c, 2);
+        if (c >= 2) tc::mbar_wait(&bar_d1[c & 1], (uint32_t)(((c >> 1) - 1) & 1));
+        CPL_STAMP(1, c, 3);
+        tc::fence_after_sync();
+        // descriptors: start-address field += bytes >> 4 (k-blocks of 64 channels are 128 rows x 128 B (weights) and
+        // RP rows x 128 B (input tile) apart; a K step of 16 is 32 bytes inside the swizzled row)
+        const uint64_t da = desc_w0 + (uint64_t)((slot * g.blob_bytes) >> 4);
+        const uint64_t db = desc_x0 + (uint64_t)(((t % NX) * g.x_buf_bytes) >> 4);
+        const uint32_t d1 = tmem_base + (uint32_t)((c & 1) * RP);
+        for (int k16 = 0; k16 < g.nk16; ++k16) {
+          const int kb = k16 >> 2, k = g.xrb == 128 ? (k16 & 3) : k16;
+          tc::umma_f16(d1, da + (uint64_t)(kb * (128 * 128 >> 4) + 2 * k), db + (uint64_t)(kb * (RP * 128 >> 4) + 2 * k),
+                       idesc_e, k16 > 0 ? 1u : 0u);
+        }
+        tc::umma_commit(&bar_e[c & 1]);
+        if (j == n_chunks - 1) tc::umma_commit(&bar_xf[t % NX]);   // the tile's input buffer may be refilled
+        CPL_STAMP(1, c, 4);
+        if (++j == n_chunks) { j = 0; ++t; }
+      }
+    }
+  } else if (warp == 17) {
+    // =========================================================================================== project issuer
     if (lane == 0) {
       const int pre = streaming ? min(NS, Ctot) : n_chunks;
-      for (int c = 0; c < pre; ++c) {   // weights do not depend on the predecessor kernel: before pdl_wait
+      for (int c = 0; c < pre; ++c) {   // weights do not depend on the predecessor kernel
         tc::mbar_expect_tx(&bar_w[c], g.blob_bytes);
         bulk_load(sW + (size_t)c * g.blob_bytes, wblob + (size_t)(c % n_chunks) * g.blob_bytes, g.blob_bytes, &bar_w[c]);
       }
-      const uint32_t idesc_e = tc::make_idesc_f16(RP);
-      const uint32_t idesc_p = tc::make_idesc_f16(g.cout_pad) | (KM ? 0u : (1u << 15));   // A operand MN-major
-      int t = 0, j = 0;      // tile / chunk-in-tile of chunk c
-      int pt = 0, pj = 0;    // ... of chunk c - 1
-      for (int c = 0; c <= Ctot; ++c) {
-        if (streaming && c >= 2 && c - 2 + NS < Ctot) {   // the slot of chunk c-2 is free once project(c-2) has retired
-          const int k = c - 2, slot = k % NS;
+      const uint32_t idesc_p = tc::make_idesc_f16(g.cout_pad) | (1u << 15);   // A operand MN-major
+      const uint64_t desc_a0 = make_sdesc_mn_sw128(tc::smem_u32(sA2), 1024u, MG * 1024u);
+      const uint64_t desc_p0 = tc::make_sdesc_sw128(tc::smem_u32(sW + g.we_bytes));
+      int t = 0, j = 0;
+      for (int c = 0; c < Ctot; ++c) {
+        if (streaming && c >= 1 && c - 1 + NS < Ctot) {   // the slot of chunk c-1 is free once project(c-1) has retired
+          const int k = c - 1, slot = k % NS;
           tc::mbar_wait(&bar_p[k & 1], (uint32_t)((k >> 1) & 1));
           tc::mbar_expect_tx(&bar_w[slot], g.blob_bytes);
           bulk_load(sW + (size_t)slot * g.blob_bytes, wblob + (size_t)((k + NS) % n_chunks) * g.blob_bytes, g.blob_bytes,
                     &bar_w[slot]);
         }
-        if (c < Ctot) {
-          const int slot = streaming ? c % NS : j;
-          tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
-          if (j == 0) tc::mbar_wait(&bar_x[t % NX], (uint32_t)((t / NX) & 1));
-          if (c >= 2) tc::mbar_wait(&bar_d1[c & 1], (uint32_t)(((c >> 1) - 1) & 1));
-          tc::fence_after_sync();
-          const uint8_t* we = sW + (size_t)slot * g.blob_bytes;
-          const uint8_t* xb = sX + (size_t)(t % NX) * g.x_buf_bytes;
-          const uint32_t d1 = tmem_base + (uint32_t)((c & 1) * RP);
-          int k16 = 0;
-          for (int kb = 0; kb < g.kb_in; ++kb) {
-            const uint64_t da = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(we + (size_t)kb * 128 * 128))
-                                             : tc::make_sdesc_sw64(tc::smem_u32(we));
-            const uint64_t db = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(xb + (size_t)kb * RP * 128))
-                                             : tc::make_sdesc_sw64(tc::smem_u32(xb));
-            const int nk = min(g.xrb == 128 ? 4 : 2, g.nk16 - k16);
-            for (int k = 0; k < nk; ++k, ++k16)
-              tc::umma_f16(d1, tc::sdesc_advance_k16(da, k), tc::sdesc_advance_k16(db, k), idesc_e, k16 > 0 ? 1u : 0u);
-          }
-          tc::umma_commit(&bar_e[c & 1]);
-        }
-        if (c >= 1) {
-          const int pc = c - 1;
-          tc::mbar_wait(&bar_a2[pc & 1], (uint32_t)((pc >> 1) & 1));
-          if (pj == 0 && pt >= 1) tc::mbar_wait(&bar_d2[0], (uint32_t)((pt - 1) & 1));
-          tc::fence_after_sync();
-          const int slot = streaming ? pc % NS : pj;
-          const uint8_t* wp = sW + (size_t)slot * g.blob_bytes + g.we_bytes;
-          const uint8_t* a2 = sA2 + (size_t)(pc & 1) * g.a2_buf_bytes;
-          const int valid = min(128, g.Cexp - pj * 128);
-          const int nk = (valid + 15) >> 4;
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t da = KM ? tc::make_sdesc_sw128(tc::smem_u32(a2 + (size_t)(k >> 2) * 16384 + (k & 3) * 32))
-                                   : make_sdesc_mn_sw128(tc::smem_u32(a2 + (size_t)k * 2 * MG * 1024), 1024u, MG * 1024u);
-            const uint64_t db = tc::make_sdesc_sw128(tc::smem_u32(wp + (size_t)(k >> 2) * g.cout_pad * 128 + (k & 3) * 32));
-            tc::umma_f16(tmem_d2, da, db, idesc_p, (pj > 0 || k > 0) ? 1u : 0u);
-          }
-          tc::umma_commit(&bar_p[pc & 1]);
-        }
-        pt = t;
-        pj = j;
+        CPL_STAMP(2, c, 0);
+        tc::mbar_wait(&bar_a2[c & 1], (uint32_t)((c >> 1) & 1));
+        CPL_STAMP(2, c, 1);
+        const int b2 = t % ND2;
+        if (j == 0 && t >= ND2) tc::mbar_wait(&bar_d2[b2], (uint32_t)(((t / ND2) - 1) & 1));
+        CPL_STAMP(2, c, 2);
+        tc::fence_after_sync();
+        const int slot = streaming ? c % NS : j;
+        const uint64_t da = desc_a0 + (uint64_t)(((c & 1) * g.a2_buf_bytes) >> 4);
+        const uint64_t db = desc_p0 + (uint64_t)((slot * g.blob_bytes) >> 4);
+        const int valid = min(128, g.Cexp - j * 128);
+        const int nk = (valid + 15) >> 4;
+        const uint32_t d2 = tmem_d2 + (uint32_t)(b2 * g.cout_pad);
+        for (int k = 0; k < nk; ++k)   // A: 2 k-groups of MG KB per K step; B: k-blocks of 64 channels cout_pad rows apart
+          tc::umma_f16(d2, da + (uint64_t)(k * (2 * MG * 1024 >> 4)), db + (uint64_t)((k >> 2) * ((g.cout_pad * 128) >> 4) + 2 * (k & 3)),
+                       idesc_p, (j > 0 || k > 0) ? 1u : 0u);
+        tc::umma_commit(&bar_p[c & 1]);
+        if (j == n_chunks - 1) tc::umma_commit(&bar_f[b2]);
+        CPL_STAMP(2, c, 3);
         if (++j == n_chunks) { j = 0; ++t; }
       }
     }
-  } else {
-    // =========================================================================================== compute warps
-    const int lg = warp & 3, rg = warp >> 2;
-    const uint32_t tm_lane = (uint32_t)(lg * 32) << 16;
-
-    // input halo tile -> swizzled K-major rows (zero outside the image and in the K padding, ones unit inside)
-    auto load_x = [&](int t, int xbuf) {
-      int tx, ty, img;
-      tile_pos(t, tx, ty, img);
-      const int iy0 = ty * TH * S - g.pad_t, ix0 = tx * TW * S - g.pad_l;
-      const __half* src = in + (size_t)img * g.Hi * g.Wi * g.Cin;
-      const uint32_t xbase = tc::smem_u32(sX) + (uint32_t)xbuf * g.x_buf_bytes;
-      const int half_units = (g.units + 1) >> 1;
-      for (int r = tid >> 1; r < R; r += CPL_NT / 2) {   // two threads per pixel row
+  } else if (warp == 18 || warp == 19) {
+    // =========================================================================================== input-tile loaders
+    // One thread issues the TMA loads of the halo tile (NHWC box, zero fill outside the image and beyond Cin) NX-1 tiles
+    // ahead; once a tile has landed, the 64 loader threads patch the "ones" unit of its in-image pixels and hand it to
+    // the expand issuer.
+    const int ltid = tid - 18 * 32;
+    tc::pdl_wait();   // the input tensor is the predecessor's output
+    TilePos lp = pos0, tp = pos0;
+    const uint32_t tx_bytes = (uint32_t)(g.kb_in * R * g.xrb);
+    auto issue = [&](int t, const TilePos& q) {
+      const int xbuf = t % NX;
+      if (t >= NX) tc::mbar_wait(&bar_xf[xbuf], (uint32_t)(((t / NX) - 1) & 1));
+      tc::mbar_expect_tx(&bar_t[xbuf], tx_bytes);
+      for (int kb = 0; kb < g.kb_in; ++kb)
+        tc::tma_load_4d(sX + (size_t)xbuf * g.x_buf_bytes + (size_t)kb * RP * 128, &tmX, &bar_t[xbuf], kb * 64,
+                        q.tx * TW * S - g.pad_l, q.ty * TH * S - g.pad_t, q.img);
+    };
+    if (ltid == 0) {
+      for (int t = 0; t < NX - 1 && t < my_tiles; ++t) {
+        issue(t, tp);
+        advance(tp);
+      }
+    }
+    const uint32_t unit_off = g.xrb == 128 ? (uint32_t)(g.ones_unit >> 3) * (uint32_t)(RP * 128) : 0u;
+    for (int t = 0; t < my_tiles; ++t) {
+      if (warp == 18) { CPL_STAMP(3, t, 0); }
+      if (NX == 1 && ltid == 0) {   // no look-ahead buffer: the tile's own load goes out here
+        issue(t, tp);
+        advance(tp);
+      }
+      const int xbuf = t % NX;
+      if (warp == 18) { CPL_STAMP(3, t, 1); }
+      tc::mbar_wait(&bar_t[xbuf], (uint32_t)((t / NX) & 1));
+      if (warp == 18) { CPL_STAMP(3, t, 2); }
+      const int iy0 = lp.ty * TH * S - g.pad_t, ix0 = lp.tx * TW * S - g.pad_l;
+      const uint32_t xbase = tc::smem_u32(sX) + (uint32_t)xbuf * g.x_buf_bytes + unit_off;
+      for (int r = ltid; r < R; r += CPL_LOADERS) {
         const int ry = r / IW, rx = r - ry * IW;
         const int iy = iy0 + ry, ix = ix0 + rx;
         const bool inb = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
-        const __half* gp = src + ((size_t)iy * g.Wi + ix) * g.Cin;
-        const int u0 = (tid & 1) * half_units, u1 = min(g.units, u0 + half_units);
-        for (int u = u0; u < u1; ++u) {
-          const __half* sp = u < g.ones_unit ? gp + u * 8 : ones;
-          const int nbytes = (inb && u <= g.ones_unit) ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
-          const uint32_t dst = g.xrb == 128 ? xbase + (uint32_t)(u >> 3) * (uint32_t)(RP * 128) + (uint32_t)r * 128u +
-                                                  (uint32_t)(((u & 7) ^ (r & 7)) << 4)
-                                            : xbase + (uint32_t)r * 64u + (uint32_t)((u ^ ((r >> 1) & 3)) << 4);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(nbytes ? sp : ones), "r"(nbytes)
-                       : "memory");
-        }
+        const uint32_t dst = g.xrb == 128 ? xbase + (uint32_t)r * 128u + (uint32_t)(((g.ones_unit & 7) ^ (r & 7)) << 4)
+                                          : xbase + (uint32_t)r * 64u + (uint32_t)((g.ones_unit ^ ((r >> 1) & 3)) << 4);
+        const uint32_t one2 = inb ? 0x3C003C00u : 0u;   // {1, 1, 0, 0, 0, 0, 0, 0} in fp16
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(dst), "r"(one2), "r"(0u) : "memory");
       }
-    };
-    auto x_landed = [&](int xbuf) {   // this thread's copies have landed and are visible to the tensor core
-      asm volatile("cp.async.wait_all;" ::: "memory");
       tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bar_x[xbuf]);
-    };
-
-    // D2 + bias (+residual) -> fp16 NHWC for the tile at (tx, ty, img) whose last chunk was lc
-    auto epilogue = [&](int tx, int ty, int img, int lc) {
-      tc::mbar_wait(&bar_p[lc & 1], (uint32_t)((lc >> 1) & 1));
+      tc::mbar_arrive(&bar_x[xbuf]);
+      if (warp == 18) { CPL_STAMP(3, t, 3); }
+      advance(lp);
+      if (NX > 1 && ltid == 0 && t + NX - 1 < my_tiles) {   // refill the buffer tile t-1 has just left
+        issue(t + NX - 1, tp);
+        advance(tp);
+      }
+    }
+  } else if (warp >= 20) {
+    // =========================================================================================== epilogue warps
+    const int lg = warp - 20;
+    const uint32_t tm_lane = (uint32_t)(lg * 32) << 16;
+    tc::pdl_wait();   // residual reads / output writes order after the predecessor
+    TilePos ep = pos0;
+    const int p = lg * 32 + lane;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int b2 = t % ND2;
+      if (warp == 20) { CPL_STAMP(4, t, 0); }
+      tc::mbar_wait(&bar_f[b2], (uint32_t)((t / ND2) & 1));
+      if (warp == 20) { CPL_STAMP(4, t, 1); }
       tc::fence_after_sync();
       if (lg * 32 < NPIX) {
-        const int p = lg * 32 + lane;
-        const int oy = ty * TH + p / TW, ox = tx * TW + p % TW;
+        const int oy = ep.ty * TH + p / TW, ox = ep.tx * TW + p % TW;
         const bool valid = p < NPIX && oy < g.Ho && ox < g.Wo;
-        const long long opix = ((long long)img * g.Ho + oy) * g.Wo + ox;
-        for (int cc = rg * 16; cc < g.cout_pad; cc += 64) {
+        const long long opix = ((long long)ep.img * g.Ho + oy) * g.Wo + ox;
+        const uint32_t taddr = tmem_d2 + tm_lane + (uint32_t)(b2 * g.cout_pad);
+        for (int cc = 0; cc < g.cout_pad; cc += 16) {
           uint32_t v[16];
-          tc::tmem_ld16(tmem_d2 + tm_lane + (uint32_t)cc, v);
+          tc::tmem_ld16(taddr + (uint32_t)cc, v);
           tc::tmem_ld_wait();
           if (!valid) continue;
 #pragma unroll
@@ -306,27 +379,19 @@ fused_block_cpl_kernel(const CplGeom g, const __half* __restrict__ in, const uin
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bar_d2[0]);
-    };
-
-    tc::pdl_wait();   // the input tensor is the predecessor's output
-    for (int i = 0; i < NX - 1 && i < my_tiles; ++i) {
-      load_x(i, i);
-      x_landed(i);
+      if (lane == 0) tc::mbar_arrive(&bar_d2[b2]);
+      if (warp == 20) { CPL_STAMP(4, t, 2); }
+      advance(ep);
     }
-
+  } else {
+    // =========================================================================================== depthwise warps
+    const int lg = warp & 3, rg = warp >> 2;
+    const uint32_t tm_lane = (uint32_t)(lg * 32) << 16;
     int c = 0;
-    int ptx = 0, pty = 0, pimg = 0;
     for (int t = 0; t < my_tiles; ++t) {
-      int tx, ty, img;
-      tile_pos(t, tx, ty, img);
       for (int j = 0; j < n_chunks; ++j, ++c) {
-        const bool prefetch = j == 0 && t + NX - 1 < my_tiles;
-        if (prefetch) {
-          load_x(t + NX - 1, (t + NX - 1) % NX);
-          if (NX == 1) x_landed(0);   // no look-ahead: this tile's own expand waits for it
-        }
         const int slot = streaming ? c % NS : j;
+        if (warp == 0) { CPL_STAMP(0, c, 0); }
         tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
         const uint32_t* dwp = reinterpret_cast<const uint32_t*>(sW + (size_t)slot * g.blob_bytes + g.we_bytes + g.wp_bytes) +
                               lg * 32 + lane;
@@ -336,40 +401,43 @@ fused_block_cpl_kernel(const CplGeom g, const __half* __restrict__ in, const uin
         const float bias = __uint_as_float(dwp[5 * 128]);
         const bool active = j * 128 + lg * 32 < g.Cexp;   // warp-uniform: this lane group holds real channels
         tc::mbar_wait(&bar_e[c & 1], (uint32_t)((c >> 1) & 1));
+        if (warp == 0) { CPL_STAMP(0, c, 1); }
         tc::fence_after_sync();
         uint32_t hrow[NRI][NPK];
         if (active) {
-          uint32_t v[NRI][IW + 1];
+          // rows come out of TMEM in groups of at most 3 (register pressure: 19 fp32 words per row before packing)
           const uint32_t tbase = tmem_base + tm_lane + (uint32_t)((c & 1) * RP) + (uint32_t)(rg * NRO * S * IW);
+          constexpr int GRP = NRI <= 3 ? NRI : 2;
 #pragma unroll
-          for (int i = 0; i < NRI; ++i) {
-            uint32_t(&vr)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[i][0]);
-            tc::tmem_ld16(tbase + (uint32_t)(i * IW), vr);
-            if constexpr (S == 1) tmem_ld2(tbase + (uint32_t)(i * IW + 16), v[i][16], v[i][17]);
-            else tmem_ld1(tbase + (uint32_t)(i * IW + 16), v[i][16]);
+          for (int i0 = 0; i0 < NRI; i0 += GRP) {
+            uint32_t v[GRP][IW + 1];
+#pragma unroll
+            for (int i = 0; i < GRP; ++i) {
+              if (i0 + i < NRI) {
+                uint32_t(&vr)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[i][0]);
+                tc::tmem_ld16(tbase + (uint32_t)((i0 + i) * IW), vr);
+                if constexpr (S == 1) tmem_ld2(tbase + (uint32_t)((i0 + i) * IW + 16), v[i][16], v[i][17]);
+                else tmem_ld1(tbase + (uint32_t)((i0 + i) * IW + 16), v[i][16]);
+              }
+            }
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < GRP; ++i) {
+              if (i0 + i < NRI) {
+                if constexpr (S == 2) v[i][17] = 0u;
+#pragma unroll
+                for (int k = 0; k < NPK; ++k)
+                  hrow[i0 + i][k] = relu6_pack(__uint_as_float(v[i][2 * k]), __uint_as_float(v[i][2 * k + 1]));
+              }
+            }
           }
-          tc::tmem_ld_wait();
-          if (g.dbg && blockIdx.x == 0 && c == 0) {
-#pragma unroll
-            for (int i = 0; i < NRI; ++i)
-#pragma unroll
-              for (int k = 0; k < 18; ++k)
-                g.dbg[((size_t)(rg * 128 + lg * 32 + lane) * NRI + i) * 18 + k] = k < IW ? __uint_as_float(v[i][k]) : 0.f;
-          }
-          if constexpr (S == 2) {
-#pragma unroll
-            for (int i = 0; i < NRI; ++i) v[i][17] = 0u;
-          }
-#pragma unroll
-          for (int i = 0; i < NRI; ++i)
-#pragma unroll
-            for (int k = 0; k < NPK; ++k)
-              hrow[i][k] = relu6_pack(__uint_as_float(v[i][2 * k]), __uint_as_float(v[i][2 * k + 1]));
         }
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bar_d1[c & 1]);
+        if (warp == 0) { CPL_STAMP(0, c, 2); }
         if (c >= 2) tc::mbar_wait(&bar_p[c & 1], (uint32_t)(((c - 2) >> 1) & 1));   // project(c-2) has read A2[c & 1]
+        if (warp == 0) { CPL_STAMP(0, c, 3); }
         if (active) {
           const int kg = lg * 4 + (lane >> 3), jj = lane & 7;
           uint8_t* a2 = sA2 + (size_t)(c & 1) * g.a2_buf_bytes + (size_t)kg * (MG * 1024) + jj * 128;
@@ -393,19 +461,6 @@ fused_block_cpl_kernel(const CplGeom g, const __half* __restrict__ in, const uin
             // output row r = rg * NRO + ro of the tile: pixels p = r * TW + x, 16-byte chunk (p % 64) / 8 of atom p / 64
             const int r = rg * NRO + ro;
             const int p0 = r * TW;
-            if constexpr (KM) {   // K-major A2 (debug / fallback): [2 k-blocks][128 pixel rows][128 B], 2-byte stores
-              const int chl = lg * 32 + lane;
-              uint8_t* kbase = sA2 + (size_t)(c & 1) * g.a2_buf_bytes + (size_t)(chl >> 6) * 16384 + (chl & 7) * 2;
-              const int kc = (chl & 63) >> 3;
-#pragma unroll
-              for (int x = 0; x < TW; x += 2) {
-                const uint32_t pk = relu6_pack(acc[x], acc[x + 1]);
-                const int p = p0 + x;
-                *reinterpret_cast<uint16_t*>(kbase + (size_t)p * 128 + ((kc ^ (p & 7)) << 4)) = (uint16_t)(pk & 0xffffu);
-                *reinterpret_cast<uint16_t*>(kbase + (size_t)(p + 1) * 128 + ((kc ^ ((p + 1) & 7)) << 4)) = (uint16_t)(pk >> 16);
-              }
-              continue;
-            }
             uint8_t* arow = a2 + (size_t)(p0 >> 6) * 1024;
 #pragma unroll
             for (int h = 0; h < TW / 8; ++h) {
@@ -419,19 +474,17 @@ fused_block_cpl_kernel(const CplGeom g, const __half* __restrict__ in, const uin
             }
           }
         }
+        if (warp == 0) { CPL_STAMP(0, c, 4); }
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bar_a2[c & 1]);
-        if (prefetch && NX > 1) x_landed((t + NX - 1) % NX);
-        if (j == 0 && t >= 1) epilogue(ptx, pty, pimg, c - 1);   // previous tile, hidden behind project(c)
+        if (warp == 0) { CPL_STAMP(0, c, 5); }
       }
-      ptx = tx; pty = ty; pimg = img;
     }
-    if (my_tiles > 0) epilogue(ptx, pty, pimg, Ctot - 1);
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, g.tmem_cols);
+  if (warp == 16) tc::tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
 // Builds the per-chunk weight images: WE (A operand of expand: 128 channel rows x K, K-major, swizzled, bias in the
@@ -500,21 +553,15 @@ __global__ void cpl_pack_kernel(CplGeom g, const __half* __restrict__ we, int we
 struct CplPlan {
   CplGeom g;          // everything that does not depend on the tile shape / batch
   uint8_t* d_blob = nullptr;
-  const __half* d_ones = nullptr;
+  CUtensorMap tmX[2]; // input halo tile boxes: [0] tall tile (TH = 8), [1] TH = 4
   int pin_th = 0, pin_ns = 0, pin_nx = 0;
 };
 
+int hfb_make_tmap_nhwc_box(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B, int box_w,
+                           int box_h, int box_c);
+
 CplPlan* cpl_new() { return new CplPlan(); }
 void cpl_delete(CplPlan* p) { delete p; }
-
-static __half* cpl_ones(hfb_ctx* ctx) {   // 16 bytes {1, 1, 0, 0, 0, 0, 0, 0}: the "ones" unit of in-image pixels
-  __half* d = nullptr;
-  if (ctx->dalloc(&d, 8) != HFB_OK) return nullptr;
-  const __half h[8] = {__float2half(1.f), __float2half(1.f), __float2half(0.f), __float2half(0.f),
-                       __float2half(0.f), __float2half(0.f), __float2half(0.f), __float2half(0.f)};
-  if (cudaMemcpy(d, h, 16, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
-  return d;
-}
 
 static bool cpl_layout(CplGeom& g, int S, int TH, int NS, int NX) {
   const int TW = S == 1 ? 16 : 8;
@@ -526,21 +573,23 @@ static bool cpl_layout(CplGeom& g, int S, int TH, int NS, int NX) {
   g.NS = NS;
   g.NX = NX;
   g.x_buf_bytes = al((uint32_t)(g.kb_in * RP * g.xrb));
-  g.a2_buf_bytes = (uint32_t)(16 * (getenv("HFB_CPL_KM") ? 2 : MG) * 1024);
+  g.a2_buf_bytes = (uint32_t)(16 * MG * 1024);
   uint32_t off = 0;
   g.off_X = off;  off += (uint32_t)NX * g.x_buf_bytes;
   g.off_A2 = off; off += 2 * g.a2_buf_bytes;
   g.off_W = off;  off += al((uint32_t)NS * g.blob_bytes);
   g.off_bars = off; off += 256;
   g.smem_bytes = off + 1024;
+  g.ND2 = 2 * RP + 2 * g.cout_pad <= 512 ? 2 : 1;
   uint32_t cols = 32;
-  while ((int)cols < 2 * RP + g.cout_pad) cols <<= 1;
+  while ((int)cols < 2 * RP + g.ND2 * g.cout_pad) cols <<= 1;
   g.tmem_cols = cols;
   return g.smem_bytes <= 227u * 1024u;
 }
 
 // Returns HFB_ERR_CAPACITY when the block cannot run in this formulation (the caller keeps another path).
-int cpl_plan(hfb_ctx* ctx, CplPlan& cp, const BlockW& bw, int Hi, int Wi, int Ho, int Wo, int pad_t, int pad_l) {
+int cpl_plan(hfb_ctx* ctx, CplPlan& cp, const BlockW& bw, const __half* in, int Bmax, int Hi, int Wi, int Ho, int Wo,
+             int pad_t, int pad_l) {
   if (!bw.has_expand || bw.cin % 8 != 0 || bw.cout % 8 != 0) return HFB_ERR_CAPACITY;
   CplGeom& g = cp.g;
   memset(&g, 0, sizeof(g));
@@ -570,8 +619,12 @@ int cpl_plan(hfb_ctx* ctx, CplPlan& cp, const BlockW& bw, int Hi, int Wi, int Ho
     for (int ns : {g.n_chunks, 2})
       if (cpl_layout(g, bw.stride, bw.stride == 2 ? 4 : th, std::min(ns, g.n_chunks), 1)) ok = true;
   if (!ok) return HFB_ERR_CAPACITY;
-  cp.d_ones = cpl_ones(ctx);
-  if (!cp.d_ones) return HFB_ERR_CUDA;
+  {
+    const int S = bw.stride, TW = S == 1 ? 16 : 8, IW = (TW - 1) * S + 3;
+    const int box_c = g.xrb == 128 ? 64 : 32;
+    if (S == 1) HFB_TRY(hfb_make_tmap_nhwc_box(ctx, &cp.tmX[0], in, bw.cin, Wi, Hi, Bmax, IW, 7 * S + 3, box_c));
+    HFB_TRY(hfb_make_tmap_nhwc_box(ctx, &cp.tmX[1], in, bw.cin, Wi, Hi, Bmax, IW, 3 * S + 3, box_c));
+  }
   HFB_TRY(ctx->dalloc(&cp.d_blob, (size_t)g.n_chunks * g.blob_bytes));
   HFB_CUDA(ctx, cudaMemsetAsync(cp.d_blob, 0, (size_t)g.n_chunks * g.blob_bytes, ctx->stream));
   cpl_pack_kernel<<<64, 256, 0, ctx->stream>>>(g, bw.expand.w, bw.expand.Kp, bw.expand.b, bw.project.w, bw.project.Kp,
@@ -633,17 +686,17 @@ int cpl_tiles(const hfb_ctx* ctx, const CplPlan& cp, int stride, int B) {
   return g.total_tiles;
 }
 
-template <int S, int TH, bool KM>
+template <int S, int TH>
 static int cpl_launch(hfb_ctx* ctx, const CplPlan& cp, const CplGeom& g, const BlockW& bw, const __half* in, __half* out) {
   static size_t configured = 0;   // per instantiation
   if (g.smem_bytes > configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_cpl_kernel<S, TH, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_cpl_kernel<S, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)g.smem_bytes));
     configured = g.smem_bytes;
   }
   const int grid = std::min(g.total_tiles, ctx->n_sm);
-  hfb_launch(ctx, fused_block_cpl_kernel<S, TH, KM>, grid, CPL_NT + 32, g.smem_bytes, g, in, (const uint8_t*)cp.d_blob,
-             bw.project.b, cp.d_ones, out);
+  hfb_launch(ctx, fused_block_cpl_kernel<S, TH>, grid, CPL_THREADS, g.smem_bytes, cp.tmX[TH == 8 ? 0 : 1], g, in,
+             (const uint8_t*)cp.d_blob, bw.project.b, out);
   HFB_CHECK_LAUNCH(ctx, "fused_block_cpl");
   return HFB_OK;
 }
@@ -661,41 +714,47 @@ int cpl_run(hfb_ctx* ctx, const CplPlan& cp, const BlockW& bw, const __half* in,
     fprintf(stderr, "hfnet_b200: cpl layer_%d: S=%d TH=%d chunks=%d units=%d xrb=%d NS=%d NX=%d smem=%u tmem=%u tiles=%d\n",
             bw.layer, bw.stride, TH, g.n_chunks, g.units, g.xrb, g.NS, g.NX, g.smem_bytes, g.tmem_cols, g.total_tiles);
   }
-  static const bool km = getenv("HFB_CPL_KM") != nullptr;   // K-major project operand (debug / fallback)
-  if (km) {
-    if (bw.stride == 1 && TH == 8) return cpl_launch<1, 8, true>(ctx, cp, g, bw, in, out);
-    if (bw.stride == 1 && TH == 4) return cpl_launch<1, 4, true>(ctx, cp, g, bw, in, out);
-    if (bw.stride == 2 && TH == 4) return cpl_launch<2, 4, true>(ctx, cp, g, bw, in, out);
+  g.dbg = nullptr;
+  static const int dbg_layer = getenv("HFB_CPL_DBG") ? atoi(getenv("HFB_CPL_DBG")) : 0;   // needs HFB_NO_GRAPH=1
+  static int dbg_runs = 0;
+  static long long* d_dbg = nullptr;
+  const bool dbg = dbg_layer == bw.layer && dbg_runs < 2;
+  if (dbg) {
+    ++dbg_runs;
+    if (!d_dbg) HFB_CUDA(ctx, cudaMalloc(&d_dbg, 5 * 64 * 8 * 8));
+    HFB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, 5 * 64 * 8 * 8, ctx->stream));
+    g.dbg = d_dbg;
   }
-  static const int dbg_layer = getenv("HFB_CPL_DBG") ? atoi(getenv("HFB_CPL_DBG")) : 0;
-  static int dbg_done = 0;
-  if (dbg_layer == bw.layer && !dbg_done) {   // needs HFB_NO_GRAPH=1
-    dbg_done = 1;
-    const size_t n = 4 * 128 * 4 * 18;
-    float* d = nullptr;
-    HFB_CUDA(ctx, cudaMalloc(&d, n * 4));
-    HFB_CUDA(ctx, cudaMemset(d, 0, n * 4));
-    g.dbg = d;
-    int rc = HFB_ERR_STATE;
-    if (bw.stride == 1 && TH == 8) rc = cpl_launch<1, 8, false>(ctx, cp, g, bw, in, out);
-    if (bw.stride == 1 && TH == 4) rc = cpl_launch<1, 4, false>(ctx, cp, g, bw, in, out);
-    if (bw.stride == 2 && TH == 4) rc = cpl_launch<2, 4, false>(ctx, cp, g, bw, in, out);
-    HFB_TRY(rc);
+  int rc = HFB_ERR_STATE;
+  if (bw.stride == 1 && TH == 8) rc = cpl_launch<1, 8>(ctx, cp, g, bw, in, out);
+  else if (bw.stride == 1 && TH == 4) rc = cpl_launch<1, 4>(ctx, cp, g, bw, in, out);
+  else if (bw.stride == 2 && TH == 4) rc = cpl_launch<2, 4>(ctx, cp, g, bw, in, out);
+  else ctx->set_error("internal: no fused block (cpl) kernel for this tile shape");
+  if (rc == HFB_OK && dbg) {
+    std::vector<long long> h(5 * 64 * 8);
     HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<float> h(n);
-    HFB_CUDA(ctx, cudaMemcpy(h.data(), d, n * 4, cudaMemcpyDeviceToHost));
-    if (FILE* f = fopen("gpurun_out/cpl_dbg.bin", "wb")) {
-      fwrite(h.data(), 4, n, f);
-      fclose(f);
+    HFB_CUDA(ctx, cudaMemcpy(h.data(), d_dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+    const char* roles[5] = {"depthwise", "expand", "project", "loader", "epilogue"};
+    long long t0 = 0;
+    for (int r = 0; r < 5; ++r)
+      for (int i = 0; i < 64; ++i)
+        for (int k = 0; k < 8; ++k) {
+          const long long v = h[(r * 64 + i) * 8 + k];
+          if (v && (!t0 || v < t0)) t0 = v;
+        }
+    for (int r = 0; r < 5; ++r) {
+      fprintf(stderr, "hfnet_b200: cpl layer_%d %s stamps (cycles since first):\n", bw.layer, roles[r]);
+      for (int i = 0; i < 14; ++i) {
+        fprintf(stderr, "   [%2d]", i);
+        for (int k = 0; k < 6; ++k) {
+          const long long v = h[(r * 64 + i) * 8 + k];
+          fprintf(stderr, " %8lld", v ? v - t0 : -1LL);
+        }
+        fprintf(stderr, "\n");
+      }
     }
-    cudaFree(d);
-    return HFB_OK;
   }
-  if (bw.stride == 1 && TH == 8) return cpl_launch<1, 8, false>(ctx, cp, g, bw, in, out);
-  if (bw.stride == 1 && TH == 4) return cpl_launch<1, 4, false>(ctx, cp, g, bw, in, out);
-  if (bw.stride == 2 && TH == 4) return cpl_launch<2, 4, false>(ctx, cp, g, bw, in, out);
-  ctx->set_error("internal: no fused block (cpl) kernel for this tile shape");
-  return HFB_ERR_STATE;
+  return rc;
 }
 
 double cpl_bytes(const CplPlan& cp, int B) {   // algorithmic: input once + output once (+ residual re-read) + weights

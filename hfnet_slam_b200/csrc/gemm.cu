@@ -61,18 +61,19 @@ int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, 
   return HFB_OK;
 }
 
-// fp16 NHWC tensor viewed as (C, W, H, B); box = 64 channels x box_w x box_h x 1 (input halo tile of a fused block).
+// fp16 NHWC tensor viewed as (C, W, H, B); box = box_c channels (64: 128B swizzle, 32: 64B swizzle) x box_w x box_h x 1
+// (input halo tile of a fused block; out-of-range coordinates, negative ones included, are zero-filled).
 int hfb_make_tmap_nhwc_box(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B, int box_w,
-                           int box_h) {
+                           int box_h, int box_c) {
   PFN_encodeTiled enc = get_encode(ctx);
   if (!enc) return HFB_ERR_CUDA;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     ctx->set_error("cuTensorMapEncodeTiled(4d box) failed: code " + std::to_string((int)r) + " box " +
                    std::to_string(box_w) + "x" + std::to_string(box_h));
