@@ -109,6 +109,9 @@ struct hfb_ctx {
   int device = 0;
   int n_sm = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;   // global branch of the encoder (forked off after layer_7)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool fork_branches = true;            // HFB_FORK=0: everything on one stream
   std::string err;
   uint64_t launches = 0;
   // weights

@@ -113,6 +113,16 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
     return HFB_ERR_CUDA;
   }
   HFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  {
+    // the side stream carries the small late-layer grids: highest priority, so that their CTAs are placed first and the
+    // wide kernels of the local branch fill the SMs they leave free
+    int lo = 0, hi = 0;
+    HFB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    HFB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+  }
+  HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  if (const char* fk = getenv("HFB_FORK")) ctx->fork_branches = !(fk[0] == '0');
   // level shapes: mvScaleFactor[l] = scaleFactor^l accumulated in float (HFextractor.cc:92-103); image size of
   // level l = cvRound(size * 1/scale) (HFextractor.cc:159-173, BaseModel.cc:35-65)
   float sf = 1.f;
@@ -185,6 +195,9 @@ extern "C" void hfb_destroy(hfb_ctx* ctx) {
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_io) cudaFree(ctx->d_io);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -852,6 +865,20 @@ extern "C" int hfb_fetch_matches(hfb_ctx* ctx, int32_t image_index, int32_t* mat
   const size_t o = (size_t)image_index * ctx->kp_cap;
   HFB_CUDA(ctx, cudaMemcpyAsync(match_idx, ctx->d_cm_idx + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   HFB_CUDA(ctx, cudaMemcpyAsync(match_val, ctx->d_cm_val + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
+}
+
+// Host-result form of hfb_match_consecutive_dev: the descriptors of the last extraction never leave HBM, only the
+// match rows ([n_images][kp_cap] indices + values) come back, in one transfer each.
+extern "C" int hfb_match_consecutive(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr, int32_t* match_idx,
+                                     float* match_val) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, match_idx && match_val, "null output");
+  HFB_TRY(hfb_match_consecutive_dev(ctx, n_images, mode, thr));
+  const size_t n = (size_t)n_images * ctx->kp_cap;
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_idx, ctx->d_cm_idx, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_val, ctx->d_cm_val, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HFB_OK;
 }

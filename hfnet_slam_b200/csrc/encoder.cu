@@ -627,6 +627,36 @@ static int run_plain(hfb_ctx* ctx, const GemmPlan& gp, long long M, void* out, i
   return gemm_store(ctx, gp.tmA, gp.tmB, g, 1, out, ldo, 0, bias, residual, ldr, relu6, 0);
 }
 
+// NetVLAD + dimensionality reduction (layers.py:57-109) on layer_18.
+static int global_head(hfb_ctx* ctx, LevelPlan& lv, LevelExec& le, int B) {
+  const NetW& net = ctx->net;
+  const int C = net.n_clusters, K = C * le.D;
+  dim3 g1(ceil_div(le.P, VLAD_PIX), B);
+  hfb_launch(ctx, vlad_memberships_kernel, g1, 256, (size_t)VLAD_PIX * le.D * 2, lv.act[18], le.P, le.D, C, net.vlad_w,
+                                                                               net.vlad_b, lv.d_memb);
+  HFB_CHECK_LAUNCH(ctx, "vlad_memberships");
+  dim3 g2(C, B);
+  hfb_launch(ctx, vlad_aggregate_kernel, g2, 256, (size_t)le.P * 4, lv.act[18], lv.d_memb, le.P, le.D, C, net.vlad_c,
+                                                                   lv.d_vlad);
+  HFB_CHECK_LAUNCH(ctx, "vlad_aggregate");
+  hfb_launch(ctx, vlad_normalize_kernel, B, 256, 0, lv.d_vlad, C, le.D, lv.d_vladn);
+  HFB_CHECK_LAUNCH(ctx, "vlad_normalize");
+  dim3 g3(ceil_div(HFB_GLOBAL_DIM, 256 * 8), le.fc_split);
+  const size_t smem = (size_t)FC_BCH * le.fc_kps * sizeof(float);
+  ctx->note("global.fc", 2.0 * K * HFB_GLOBAL_DIM + 4.0 * B * K, 2.0 * B * K * HFB_GLOBAL_DIM);
+  hfb_launch(ctx, fc_partial_kernel, g3, 256, smem, lv.d_vladn, K, B, net.fc_w, HFB_GLOBAL_DIM, le.fc_kps,
+                                                    lv.d_fc_partial);
+  HFB_CHECK_LAUNCH(ctx, "fc_partial");
+  const int n_part = ceil_div(HFB_GLOBAL_DIM, 256);
+  float* ss_part = lv.d_fc_partial + (size_t)ctx->cfg.max_batch * le.fc_split * HFB_GLOBAL_DIM;
+  hfb_launch(ctx, fc_finish_kernel, dim3(n_part, B), 256, 0, lv.d_fc_partial, le.fc_split, HFB_GLOBAL_DIM, net.fc_b,
+                                                             ctx->d_global, ss_part);
+  HFB_CHECK_LAUNCH(ctx, "fc_finish");
+  hfb_launch(ctx, fc_norm_kernel, dim3(n_part, B), 256, 0, ctx->d_global, HFB_GLOBAL_DIM, ss_part, n_part);
+  HFB_CHECK_LAUNCH(ctx, "fc_norm");
+  return HFB_OK;
+}
+
 // Forward of one pyramid level for `B` frames whose u8 images are in lv.d_img.  Produces d_scores, d_nms (no
 // selection beyond the threshold scan), d_descmap and (level 0) the global descriptors.
 int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
@@ -641,9 +671,24 @@ int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
         le.pad_l1, total);
     HFB_CHECK_LAUNCH(ctx, "conv1");
   }
+  // The global branch (layer_8 .. layer_18, NetVLAD, FC) and the local branch (heads, NMS) only share layer_7: they
+  // run on two streams (fork / join with events, captured into the same graph), so that the small late-layer grids
+  // and the local head fill each other's idle SMs.  Profiling runs (one event per launch) stay on one stream.
+  cudaStream_t main_stream = ctx->stream;
+  struct StreamGuard {   // error returns must not leave the context on the side stream
+    hfb_ctx* c;
+    cudaStream_t s;
+    ~StreamGuard() { c->stream = s; }
+  } guard{ctx, main_stream};
+  const bool fork = lv.global && ctx->side_stream && ctx->fork_branches && !ctx->prof_on;
   size_t bi = 0;
   for (const BlockW& bw : net.blocks) {
     if (bw.layer > lv.n_act) break;
+    if (fork && bw.layer == 8) {
+      HFB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+      HFB_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+      ctx->stream = ctx->side_stream;   // every launcher enqueues on ctx->stream
+    }
     const BlockPlan& bp = le.blocks[bi++];
     const __half* in = lv.act[bw.layer - 1];
     const __half* dw_in = in;
@@ -683,6 +728,12 @@ int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
     HFB_TRY(run_plain(ctx, bp.project, Mout, lv.act[bw.layer], bw.cout, bw.project.b,
                       bw.residual ? in : nullptr, bw.cin, 0));
   }
+  if (fork) {   // global head on the side stream, then back to the main stream for the local branch
+    const int rc = global_head(ctx, lv, le, B);
+    ctx->stream = main_stream;
+    HFB_TRY(rc);
+    HFB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  }
   // local head (hf_net.py:74-93)
   {
     GemmGeom g = le.head1.g;
@@ -701,31 +752,7 @@ int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
   }
   ctx->note("nms", 8.0 * B * lv.H8 * lv.W8, 0);
   HFB_TRY(launch_nms(ctx, lv.d_scores, lv.d_nms, lv.H8, lv.W8, B, threshold, lv.d_cand, lv.d_cand_count, ctx->cand_cap));
-  if (lv.global) {
-    const int C = net.n_clusters, K = C * le.D;
-    dim3 g1(ceil_div(le.P, VLAD_PIX), B);
-    hfb_launch(ctx, vlad_memberships_kernel, g1, 256, (size_t)VLAD_PIX * le.D * 2, lv.act[18], le.P, le.D, C, net.vlad_w,
-                                                                                 net.vlad_b, lv.d_memb);
-    HFB_CHECK_LAUNCH(ctx, "vlad_memberships");
-    dim3 g2(C, B);
-    hfb_launch(ctx, vlad_aggregate_kernel, g2, 256, (size_t)le.P * 4, lv.act[18], lv.d_memb, le.P, le.D, C, net.vlad_c,
-                                                                     lv.d_vlad);
-    HFB_CHECK_LAUNCH(ctx, "vlad_aggregate");
-    hfb_launch(ctx, vlad_normalize_kernel, B, 256, 0, lv.d_vlad, C, le.D, lv.d_vladn);
-    HFB_CHECK_LAUNCH(ctx, "vlad_normalize");
-    dim3 g3(ceil_div(HFB_GLOBAL_DIM, 256 * 8), le.fc_split);
-    const size_t smem = (size_t)FC_BCH * le.fc_kps * sizeof(float);
-    ctx->note("global.fc", 2.0 * K * HFB_GLOBAL_DIM + 4.0 * B * K, 2.0 * B * K * HFB_GLOBAL_DIM);
-    hfb_launch(ctx, fc_partial_kernel, g3, 256, smem, lv.d_vladn, K, B, net.fc_w, HFB_GLOBAL_DIM, le.fc_kps,
-                                                      lv.d_fc_partial);
-    HFB_CHECK_LAUNCH(ctx, "fc_partial");
-    const int n_part = ceil_div(HFB_GLOBAL_DIM, 256);
-    float* ss_part = lv.d_fc_partial + (size_t)ctx->cfg.max_batch * le.fc_split * HFB_GLOBAL_DIM;
-    hfb_launch(ctx, fc_finish_kernel, dim3(n_part, B), 256, 0, lv.d_fc_partial, le.fc_split, HFB_GLOBAL_DIM, net.fc_b,
-                                                               ctx->d_global, ss_part);
-    HFB_CHECK_LAUNCH(ctx, "fc_finish");
-    hfb_launch(ctx, fc_norm_kernel, dim3(n_part, B), 256, 0, ctx->d_global, HFB_GLOBAL_DIM, ss_part, n_part);
-    HFB_CHECK_LAUNCH(ctx, "fc_norm");
-  }
+  if (fork) HFB_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+  else if (lv.global) HFB_TRY(global_head(ctx, lv, le, B));
   return HFB_OK;
 }

@@ -209,7 +209,7 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
       for (int c = 0; c < Ctot; ++c) {
         const int slot = streaming ? c % NS : j;
         CPL_STAMP(1, c, 0);
-        tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
+        if (streaming || c < n_chunks) tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
         CPL_STAMP(1, c, 1);
         if (j == 0) tc::mbar_wait(&bar_x[t % NX], (uint32_t)((t / NX) & 1));
         CPL_STAMP(1, c, 2);
@@ -392,7 +392,7 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
       for (int j = 0; j < n_chunks; ++j, ++c) {
         const int slot = streaming ? c % NS : j;
         if (warp == 0) { CPL_STAMP(0, c, 0); }
-        tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
+        if (streaming || c < n_chunks) tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
         const uint32_t* dwp = reinterpret_cast<const uint32_t*>(sW + (size_t)slot * g.blob_bytes + g.we_bytes + g.wp_bytes) +
                               lg * 32 + lane;
         uint32_t wv[5];
@@ -616,7 +616,7 @@ int cpl_plan(hfb_ctx* ctx, CplPlan& cp, const BlockW& bw, const __half* in, int 
   // at least one configuration must fit
   bool ok = false;
   for (int th : {8, 4})
-    for (int ns : {g.n_chunks, 2})
+    for (int ns : {g.n_chunks, 2, 1})
       if (cpl_layout(g, bw.stride, bw.stride == 2 ? 4 : th, std::min(ns, g.n_chunks), 1)) ok = true;
   if (!ok) return HFB_ERR_CAPACITY;
   {
@@ -649,7 +649,7 @@ static bool cpl_configure(const hfb_ctx* ctx, const CplPlan& cp, int stride, int
     int nx_want = per_cta <= 1 ? 1 : (g.n_chunks == 1 ? 3 : 2);
     if (cp.pin_nx) nx_want = cp.pin_nx;
     for (int nx = nx_want; nx >= (per_cta <= 1 ? 1 : 2); --nx) {
-      for (int ns : {g.n_chunks, 4, 3, 2}) {
+      for (int ns : {g.n_chunks, 4, 3, 2, 1}) {
         if (ns > g.n_chunks || ns > 8) continue;
         if (cp.pin_ns && ns != std::min(cp.pin_ns, g.n_chunks)) continue;
         if (need_resident && ns < g.n_chunks) continue;

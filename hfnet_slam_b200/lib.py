@@ -89,6 +89,7 @@ SIGNATURES = {
                                        _i32p, _u8p, _i32p, _f32p, _i32p]),
     "hfb_match_consecutive_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float]),
     "hfb_fetch_matches": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _f32p, C.c_int32]),
+    "hfb_match_consecutive": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, _i32p, _f32p]),
     "hfb_profile_extract": (C.c_int, [C.c_void_p, C.c_int32, _i32p, C.c_float, C.c_char_p, C.c_size_t]),
     "hfb_kfdb_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "hfb_kfdb_destroy": (None, [C.c_void_p]),
@@ -319,6 +320,15 @@ class Context:
 
     def match_consecutive_dev(self, n_images: int, mode: int, thr: float):
         self.check(self.lib.hfb_match_consecutive_dev(self.handle, n_images, mode, thr))
+
+    def match_consecutive(self, n_images: int, mode: int, thr: float, out=None):
+        """Frame b of the last extraction against frame b-1 (descriptors resident in HBM); returns [n_images][kp_cap]
+        match indices / values on the host.  ``out`` = (idx, val) arrays to reuse (e.g. page-locked)."""
+        if out is None:
+            out = (np.empty((n_images, self.kp_cap), np.int32), np.empty((n_images, self.kp_cap), np.float32))
+        idx, val = out
+        self.check(self.lib.hfb_match_consecutive(self.handle, n_images, mode, thr, ptr(idx, _i32p), ptr(val, _f32p)))
+        return idx, val
 
     def fetch_matches(self, image_index: int, n: int):
         idx = np.full(n, -1, np.int32)

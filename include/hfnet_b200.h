@@ -183,6 +183,12 @@ int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, const float* 
  * Matcher::SearchByBoW / SearchForInitialization call sites, src/Tracking.cc:2030,1796) with the descriptors of the last
  * hfb_extract_batch* still resident in HBM: frame b is matched against frame (b-1) mod n_images.  No sync. */
 int hfb_match_consecutive_dev(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr);
+/* Same, synchronous, results to host: match_idx / match_val are [n_images][kp_cap] rows (kp_cap = n_levels *
+ * max_keypoints; row b holds frame b's matches into frame (b-1) mod n_images, -1 = unmatched).  This is the call
+ * Tracking makes right after Frame construction: the previous frame's descriptors are still resident, so nothing is
+ * uploaded (Matcher::SearchByBoW with host cv::Mat descriptors re-reads both sets, src/Matcher.cc:220-263). */
+int hfb_match_consecutive(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr, int32_t* match_idx,
+                          float* match_val);
 /* match_idx / match_val of frame `image_index` (indices into the previous frame's keypoints), first n rows. */
 int hfb_fetch_matches(hfb_ctx* ctx, int32_t image_index, int32_t* match_idx, float* match_val, int32_t n);
 

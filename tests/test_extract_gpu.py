@@ -162,3 +162,23 @@ def test_pinned_zero_copy_path_equals_staged_path(ctx_euroc, oracle_euroc):
         for k in ("x", "y", "response", "octave", "descriptors", "global_descriptor"):
             assert np.array_equal(a[k], b[k]), k
     assert block["descriptors"].shape == (2, 1000, 256)
+
+
+def test_consecutive_match_on_resident_descriptors(ctx_euroc):
+    """hfb_match_consecutive: frame b vs frame b-1 on the descriptors the extraction left in HBM == the oracle's
+    cv::BFMatcher(NORM_L2, crossCheck) + dist < 0.6 (src/Matcher.cc:220-263) on the descriptors returned to the host."""
+    from oracle import match_ref
+    base = weights.synthetic_image(480, 752, seed=7)
+    imgs = [base, np.roll(base, (3, 5), axis=(0, 1))]
+    feats = ctx_euroc.extract_batch(imgs, [1000], 0.01)
+    idx, val = ctx_euroc.match_consecutive(2, 0, 0.6)
+    assert idx.shape == (2, ctx_euroc.kp_cap)
+    for b in range(2):
+        A, Bd = feats[b]["descriptors"], feats[(b - 1) % 2]["descriptors"]
+        ia, ib, dist = match_ref.search_by_bow(A, Bd, 0.6)
+        got = {(int(i), int(idx[b, i])) for i in np.flatnonzero(idx[b, :len(A)] >= 0)}
+        assert got == set(zip(ia.tolist(), ib.tolist())), f"frame {b}"
+        assert len(got) > 50, "shifted copies of one frame should share many keypoints"
+        one_idx, one_val = ctx_euroc.fetch_matches(b, len(A))
+        assert np.array_equal(one_idx, idx[b, :len(A)]) and np.array_equal(one_val, val[b, :len(A)])
+        assert (idx[b, len(A):] < 0).all()
