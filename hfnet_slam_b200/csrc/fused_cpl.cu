@@ -46,7 +46,6 @@ struct CplGeom {
 };
 
 constexpr int CPL_NT = 512;          // compute threads
-constexpr int CPL_LOADERS = 64;      // input-tile loader threads (two warps)
 constexpr int CPL_THREADS = 768;     // 16 depthwise warps + 2 issuer warps + 2 loader warps + 4 epilogue warps
 constexpr int CPL_DW_BYTES = 6 * 128 * 4;   // per chunk: 5 words of packed fp16 taps + fp32 bias per lane
 
@@ -110,7 +109,8 @@ __device__ __forceinline__ uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint
 //   0..15  depthwise: TMEM lane group (warp & 3) = 32 channels of the chunk, row group (warp >> 2) = TH / 4 output rows
 //   16     expand issuer (lane 0): expand(c) goes out as soon as its accumulator buffer has been drained
 //   17     project issuer (lane 0) + weight ring refills
-//   18,19  input-tile loaders (cp.async with asynchronous mbarrier arrival)
+//   18     input-tile TMA issuer (lane 0)
+//   19     patches the ones unit of landed tiles and hands them to the expand issuer
 //   20..23 epilogue: one TMEM lane group each, D2 + bias (+residual) -> fp16 NHWC; the only warps that touch global
 //          memory besides the loaders, so the proxy fences of the depthwise warps never wait on global traffic
 template <int S, int TH>
@@ -140,12 +140,12 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
   uint64_t* bar_d1 = bars + 4;       // [2] D1[c & 1] drained by the depthwise warps (16 arrivals)
   uint64_t* bar_a2 = bars + 6;       // [2] A2[c & 1] written (16 arrivals)
   uint64_t* bar_d2 = bars + 8;       // [2] D2[t % ND2] drained by the epilogue warps (4 arrivals)
-  uint64_t* bar_x = bars + 10;       // [3] input tile landed (cp.async arrivals of the loader threads)
-  uint64_t* bar_w = bars + 13;       // [8] weight chunk image landed (tx)
-  uint64_t* bar_xf = bars + 21;      // [3] every expand reading the input tile has retired -> buffer free
-  uint64_t* bar_f = bars + 24;       // [2] last project of the tile retired -> D2[t % ND2] full
-  uint64_t* bar_t = bars + 26;       // [3] TMA of the input tile landed (tx) -> the loaders patch the ones unit
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint64_t* bar_f = bars + 10;       // [2] last project of the tile retired -> D2[t % ND2] full
+  uint64_t* bar_w = bars + 12;       // [8] weight chunk image landed (tx)
+  uint64_t* bar_x = bars + 20;       // [8] input tile patched (32 arrivals of warp 19) -> expand may read it
+  uint64_t* bar_xf = bars + 28;      // [8] every expand reading the input tile has retired -> buffer free
+  uint64_t* bar_t = bars + 36;       // [8] TMA of the input tile landed (tx) -> the loaders patch the ones unit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_chunks = g.n_chunks, NS = g.NS, NX = g.NX, ND2 = g.ND2;
@@ -155,11 +155,8 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
   tc::pdl_launch_dependents();
 
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
-    for (int i = 4; i < 8; ++i) tc::mbar_init(&bars[i], CPL_NT / 32);
-    for (int i = 8; i < 10; ++i) tc::mbar_init(&bars[i], 4);
-    for (int i = 10; i < 13; ++i) tc::mbar_init(&bars[i], CPL_LOADERS);
-    for (int i = 13; i < 29; ++i) tc::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 44; ++i)
+      tc::mbar_init(&bars[i], (i >= 4 && i < 8) ? CPL_NT / 32 : (i >= 8 && i < 10) ? 4 : (i >= 20 && i < 28) ? 32 : 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmX);
   }
@@ -274,59 +271,62 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
         if (++j == n_chunks) { j = 0; ++t; }
       }
     }
-  } else if (warp == 18 || warp == 19) {
-    // =========================================================================================== input-tile loaders
-    // One thread issues the TMA loads of the halo tile (NHWC box, zero fill outside the image and beyond Cin) NX-1 tiles
-    // ahead; once a tile has landed, the 64 loader threads patch the "ones" unit of its in-image pixels and hand it to
-    // the expand issuer.
-    const int ltid = tid - 18 * 32;
-    tc::pdl_wait();   // the input tensor is the predecessor's output
-    TilePos lp = pos0, tp = pos0;
-    const uint32_t tx_bytes = (uint32_t)(g.kb_in * R * g.xrb);
-    auto issue = [&](int t, const TilePos& q) {
-      const int xbuf = t % NX;
-      if (t >= NX) tc::mbar_wait(&bar_xf[xbuf], (uint32_t)(((t / NX) - 1) & 1));
-      tc::mbar_expect_tx(&bar_t[xbuf], tx_bytes);
-      for (int kb = 0; kb < g.kb_in; ++kb)
-        tc::tma_load_4d(sX + (size_t)xbuf * g.x_buf_bytes + (size_t)kb * RP * 128, &tmX, &bar_t[xbuf], kb * 64,
-                        q.tx * TW * S - g.pad_l, q.ty * TH * S - g.pad_t, q.img);
-    };
-    if (ltid == 0) {
-      for (int t = 0; t < NX - 1 && t < my_tiles; ++t) {
-        issue(t, tp);
+  } else if (warp == 18) {
+    // =========================================================================================== input-tile TMA issuer
+    // One thread issues the TMA loads of the halo tiles (NHWC box, zero fill outside the image and beyond Cin), NX tiles
+    // ahead, as soon as the ring slot has been released by the last expand that read it.
+    if (lane == 0) {
+      tc::pdl_wait();   // the input tensor is the predecessor's output
+      TilePos tp = pos0;
+      const uint32_t tx_bytes = (uint32_t)(g.kb_in * R * g.xrb);
+      for (int t = 0; t < my_tiles; ++t) {
+        const int xbuf = t % NX;
+        CPL_STAMP(3, t, 0);
+        if (t >= NX) tc::mbar_wait(&bar_xf[xbuf], (uint32_t)(((t / NX) - 1) & 1));
+        CPL_STAMP(3, t, 1);
+        tc::mbar_expect_tx(&bar_t[xbuf], tx_bytes);
+        for (int kb = 0; kb < g.kb_in; ++kb)
+          tc::tma_load_4d(sX + (size_t)xbuf * g.x_buf_bytes + (size_t)kb * RP * 128, &tmX, &bar_t[xbuf], kb * 64,
+                          tp.tx * TW * S - g.pad_l, tp.ty * TH * S - g.pad_t, tp.img);
+        CPL_STAMP(3, t, 2);
         advance(tp);
       }
     }
-    const uint32_t unit_off = g.xrb == 128 ? (uint32_t)(g.ones_unit >> 3) * (uint32_t)(RP * 128) : 0u;
+  } else if (warp == 19) {
+    // =========================================================================================== ones-unit patcher
+    // Once a tile has landed, this warp writes the "ones" unit of its in-image pixels (TMA zero-filled it) and hands the
+    // tile to the expand issuer.  Each lane owns rows lane, lane + 32, ... of every tile: their (row, column) inside the
+    // halo and their shared-memory offsets are computed once.
+    constexpr int NROWS = (R + 31) / 32;
+    int ry[NROWS], rx[NROWS];
+    uint32_t roff[NROWS];
+#pragma unroll
+    for (int i = 0; i < NROWS; ++i) {
+      const int r = lane + 32 * i;
+      ry[i] = r / IW;
+      rx[i] = r - ry[i] * IW;
+      roff[i] = g.xrb == 128 ? (uint32_t)(g.ones_unit >> 3) * (uint32_t)(RP * 128) + (uint32_t)r * 128u +
+                                   (uint32_t)(((g.ones_unit & 7) ^ (r & 7)) << 4)
+                             : (uint32_t)r * 64u + (uint32_t)((g.ones_unit ^ ((r >> 1) & 3)) << 4);
+    }
+    TilePos lp = pos0;
     for (int t = 0; t < my_tiles; ++t) {
-      if (warp == 18) { CPL_STAMP(3, t, 0); }
-      if (NX == 1 && ltid == 0) {   // no look-ahead buffer: the tile's own load goes out here
-        issue(t, tp);
-        advance(tp);
-      }
       const int xbuf = t % NX;
-      if (warp == 18) { CPL_STAMP(3, t, 1); }
-      tc::mbar_wait(&bar_t[xbuf], (uint32_t)((t / NX) & 1));
-      if (warp == 18) { CPL_STAMP(3, t, 2); }
       const int iy0 = lp.ty * TH * S - g.pad_t, ix0 = lp.tx * TW * S - g.pad_l;
-      const uint32_t xbase = tc::smem_u32(sX) + (uint32_t)xbuf * g.x_buf_bytes + unit_off;
-      for (int r = ltid; r < R; r += CPL_LOADERS) {
-        const int ry = r / IW, rx = r - ry * IW;
-        const int iy = iy0 + ry, ix = ix0 + rx;
-        const bool inb = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
-        const uint32_t dst = g.xrb == 128 ? xbase + (uint32_t)r * 128u + (uint32_t)(((g.ones_unit & 7) ^ (r & 7)) << 4)
-                                          : xbase + (uint32_t)r * 64u + (uint32_t)((g.ones_unit ^ ((r >> 1) & 3)) << 4);
-        const uint32_t one2 = inb ? 0x3C003C00u : 0u;   // {1, 1, 0, 0, 0, 0, 0, 0} in fp16
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(dst), "r"(one2), "r"(0u) : "memory");
+      const uint32_t xbase = tc::smem_u32(sX) + (uint32_t)xbuf * g.x_buf_bytes;
+      tc::mbar_wait(&bar_t[xbuf], (uint32_t)((t / NX) & 1));
+#pragma unroll
+      for (int i = 0; i < NROWS; ++i) {
+        if (lane + 32 * i < R) {
+          const int iy = iy0 + ry[i], ix = ix0 + rx[i];
+          const bool inb = iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi;
+          const uint32_t one2 = inb ? 0x3C003C00u : 0u;   // {1, 1, 0, 0, 0, 0, 0, 0} in fp16
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(xbase + roff[i]), "r"(one2), "r"(0u) : "memory");
+        }
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(&bar_x[xbuf]);
-      if (warp == 18) { CPL_STAMP(3, t, 3); }
       advance(lp);
-      if (NX > 1 && ltid == 0 && t + NX - 1 < my_tiles) {   // refill the buffer tile t-1 has just left
-        issue(t + NX - 1, tp);
-        advance(tp);
-      }
     }
   } else if (warp >= 20) {
     // =========================================================================================== epilogue warps
@@ -578,7 +578,7 @@ static bool cpl_layout(CplGeom& g, int S, int TH, int NS, int NX) {
   g.off_X = off;  off += (uint32_t)NX * g.x_buf_bytes;
   g.off_A2 = off; off += 2 * g.a2_buf_bytes;
   g.off_W = off;  off += al((uint32_t)NS * g.blob_bytes);
-  g.off_bars = off; off += 256;
+  g.off_bars = off; off += 512;
   g.smem_bytes = off + 1024;
   g.ND2 = 2 * RP + 2 * g.cout_pad <= 512 ? 2 : 1;
   uint32_t cols = 32;
@@ -646,15 +646,16 @@ static bool cpl_configure(const hfb_ctx* ctx, const CplPlan& cp, int stride, int
     g.tiles_y = (g.Ho + th - 1) / th;
     g.total_tiles = g.tiles_x * g.tiles_y * B;
     const int per_cta = (g.total_tiles + ctx->n_sm - 1) / ctx->n_sm;
-    int nx_want = per_cta <= 1 ? 1 : (g.n_chunks == 1 ? 3 : 2);
+    // input tiles in flight: a halo tile is many short rows (32..240 B per pixel), which TMA moves slowly (thousands
+    // of cycles per tile), so tiles with few chunks need a deep ring to cover it
+    int nx_want = std::min(std::min(per_cta, 8), std::max(2, 6 / g.n_chunks + 1));
     if (cp.pin_nx) nx_want = cp.pin_nx;
-    for (int nx = nx_want; nx >= (per_cta <= 1 ? 1 : 2); --nx) {
-      for (int ns : {g.n_chunks, 4, 3, 2, 1}) {
-        if (ns > g.n_chunks || ns > 8) continue;
-        if (cp.pin_ns && ns != std::min(cp.pin_ns, g.n_chunks)) continue;
-        if (need_resident && ns < g.n_chunks) continue;
+    for (int ns : {g.n_chunks, 4, 3, 2, 1}) {   // resident weights first, then the deepest input ring that fits
+      if (ns > g.n_chunks || ns > 8) continue;
+      if (cp.pin_ns && ns != std::min(cp.pin_ns, g.n_chunks)) continue;
+      if (need_resident && ns < g.n_chunks) continue;
+      for (int nx = nx_want; nx >= std::min(per_cta, 2); --nx)
         if (cpl_layout(g, stride, th, ns, nx)) return true;
-      }
     }
     return false;
   };
