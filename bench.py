@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="frames per step and GPU")
     ap.add_argument("--db-rows", type=int, default=50000)
-    ap.add_argument("--cpu-frames", type=int, default=12)
+    ap.add_argument("--cpu-frames", type=int, default=80)
     ap.add_argument("--skip-extra", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

@@ -11,12 +11,12 @@
 #include "common.cuh"
 
 // =============================================================================================== simple_nms
-// One CTA produces a 64 x 16 tile.  Dependency radius is 12 (three chained 9x9 max-pools), so the tile is computed
-// from an 88 x 40 halo region held in shared memory; every pool is separable (row pass, column pass).  Each thread
+// One CTA produces a 64 x 32 tile.  Dependency radius is 12 (three chained 9x9 max-pools), so the tile is computed
+// from an 88 x 56 halo region held in (dynamic) shared memory: 2.4 halo pixels per output pixel; every pool is separable (row pass, column pass).  Each thread
 // produces a run of 8 outputs from 16 inputs with a suffix-max / prefix-max split (22 max ops, 2 smem loads per
 // output instead of 9).  Row pitch 89 (odd) keeps the row pass, whose lanes walk down rows, bank-conflict free.
 #define NMS_TW 64
-#define NMS_TH 16
+#define NMS_TH 32
 #define NMS_AW (NMS_TW + 24)
 #define NMS_AH (NMS_TH + 24)
 #define NMS_P 89
@@ -68,11 +68,12 @@ __device__ __forceinline__ void colmax_pass(const float (*src)[NMS_P], int r0, i
 __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H,
                                                   int W, float threshold, u64* __restrict__ cand,
                                                   int* __restrict__ cand_count, int cand_cap) {
-  __shared__ float sS[NMS_AH][NMS_P];   // scores, -inf outside the image
-  __shared__ float sT[NMS_AH][NMS_P];   // row-pass scratch
-  __shared__ float sM[NMS_AH][NMS_P];   // max_mask (1/0) on region B, later s' on region C
-  __shared__ unsigned char sSupp[NMS_AH][NMS_AW];
-  __shared__ unsigned char sKeep[NMS_TH][NMS_TW];   // max_mask of the tile pixels
+  extern __shared__ __align__(16) unsigned char nms_smem[];
+  float (*sS)[NMS_P] = reinterpret_cast<float (*)[NMS_P]>(nms_smem);                        // scores, -inf outside the image
+  float (*sT)[NMS_P] = sS + NMS_AH;                                                          // row-pass scratch
+  float (*sM)[NMS_P] = sT + NMS_AH;                                                          // max_mask (1/0) on region B, later s' on region C
+  unsigned char (*sSupp)[NMS_AW] = reinterpret_cast<unsigned char (*)[NMS_AW]>(sM + NMS_AH);
+  unsigned char (*sKeep)[NMS_TW] = reinterpret_cast<unsigned char (*)[NMS_TW]>(sSupp + NMS_AH);   // max_mask of the tile pixels
   pdl_launch_dependents();
   pdl_wait();
   const int tid = threadIdx.x;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
     sS[r][c] = inside(r, c) ? src[(size_t)(ay0 + r) * W + (ax0 + c)] : NEG;
   }
   __syncthreads();
-  // max_mask = (s == mp(s)) on B = rows [4,36) x cols [4,84)
+  // max_mask = (s == mp(s)) on B = rows [4,AH-4) x cols [4,84)
   rowmax_pass(sS, sT, 0, NMS_AH, 4, NMS_AW - 8);
   __syncthreads();
   colmax_pass(sT, 4, NMS_AH - 8, 4, NMS_AW - 8, [&](int r, int c, float m) {
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
     if (r >= 12 && r < 12 + NMS_TH && c >= 12 && c < 12 + NMS_TW) sKeep[r - 12][c - 12] = mk ? 1 : 0;
   });
   __syncthreads();
-  // supp = mp(max_mask) > 0 on C = rows [8,32) x cols [8,80);  s' = supp ? 0 : s  (-inf outside the image)
+  // supp = mp(max_mask) > 0 on C = rows [8,AH-8) x cols [8,80);  s' = supp ? 0 : s  (-inf outside the image)
   rowmax_pass(sM, sT, 4, NMS_AH - 8, 8, NMS_AW - 16);
   __syncthreads();
   colmax_pass(sT, 8, NMS_AH - 16, 8, NMS_AW - 16, [&](int r, int c, float m) {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
     sM[r][c] = inside(r, c) ? (supp ? 0.f : sS[r][c]) : NEG;
   });
   __syncthreads();
-  // new = (s' == mp(s')) on the tile D = rows [12,28) x cols [12,76);  out = (max_mask | (new & !supp)) ? s : 0
+  // new = (s' == mp(s')) on the tile D = rows [12,AH-12) x cols [12,76);  out = (max_mask | (new & !supp)) ? s : 0
   rowmax_pass(sM, sT, 8, NMS_AH - 16, 12, NMS_TW);
   __syncthreads();
   colmax_pass(sT, 12, NMS_TH, 12, NMS_TW, [&](int r, int c, float m) {
@@ -131,7 +132,13 @@ int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, 
                int* d_cand_count, int cand_cap) {
   if (d_cand) HFB_CUDA(ctx, cudaMemsetAsync(d_cand_count, 0, sizeof(int) * B, ctx->stream));
   dim3 grid(ceil_div(W, NMS_TW), ceil_div(H, NMS_TH), B);
-  hfb_launch(ctx, nms_kernel, grid, 256, 0, d_scores, d_out, H, W, threshold, d_cand, d_cand_count, cand_cap);
+  constexpr size_t smem = 3 * sizeof(float) * NMS_AH * NMS_P + NMS_AH * NMS_AW + NMS_TH * NMS_TW;
+  static bool configured = false;
+  if (!configured) {
+    HFB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  hfb_launch(ctx, nms_kernel, grid, 256, smem, d_scores, d_out, H, W, threshold, d_cand, d_cand_count, cand_cap);
   HFB_CHECK_LAUNCH(ctx, "nms");
   return HFB_OK;
 }
