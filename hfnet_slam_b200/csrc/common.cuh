@@ -112,6 +112,7 @@ struct hfb_ctx {
   cudaStream_t side_stream = nullptr;   // global branch of the encoder (forked off after layer_7)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fork_branches = true;            // HFB_FORK=0: everything on one stream
+  bool fused_stem = true;               // HFB_STEM=0: layer_1 and layer_2 as two kernels
   std::string err;
   uint64_t launches = 0;
   // weights

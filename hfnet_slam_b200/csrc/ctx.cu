@@ -123,6 +123,7 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   if (const char* fk = getenv("HFB_FORK")) ctx->fork_branches = !(fk[0] == '0');
+  if (const char* sk = getenv("HFB_STEM")) ctx->fused_stem = !(sk[0] == '0');
   // level shapes: mvScaleFactor[l] = scaleFactor^l accumulated in float (HFextractor.cc:92-103); image size of
   // level l = cvRound(size * 1/scale) (HFextractor.cc:159-173, BaseModel.cc:35-65)
   float sf = 1.f;

@@ -657,13 +657,26 @@ static int global_head(hfb_ctx* ctx, LevelPlan& lv, LevelExec& le, int B) {
   return HFB_OK;
 }
 
+// stem.cu: layer_1 + layer_2 in one kernel
+bool stem_applies(int c1, const BlockW& bw);
+int stem_run(hfb_ctx* ctx, const uint8_t* d_img, int img_h, int img_w, int H8, int W8, int H1, int W1, int pad_t,
+             int pad_l, const float* w1, const float* b1, const BlockW& bw, __half* l1_out, __half* out, int B);
+
 // Forward of one pyramid level for `B` frames whose u8 images are in lv.d_img.  Produces d_scores, d_nms (no
 // selection beyond the threshold scan), d_descmap and (level 0) the global descriptors.
 int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
   const NetW& net = ctx->net;
   LevelPlan& lv = ctx->lv[level];
   LevelExec& le = execs(ctx)[level];
-  {
+  // HFB_STEM=0 keeps layer_1 and layer_2 as two kernels (comparison / debugging)
+  const bool stem = ctx->fused_stem && !net.blocks.empty() && stem_applies(net.c1, net.blocks[0]);
+  if (stem) {
+    const BlockW& b2 = net.blocks[0];
+    const double M1 = (double)B * le.H1 * le.W1;
+    ctx->note("stem.conv1+l2", (double)B * lv.H8 * lv.W8 + 2.0 * M1 * b2.cout, 2.0 * M1 * (9 * net.c1 + b2.cexp * (9 + b2.cout)));
+    HFB_TRY(stem_run(ctx, lv.d_img, lv.H, lv.W, lv.H8, lv.W8, le.H1, le.W1, le.pad_t1, le.pad_l1, net.conv1_w, net.conv1_b,
+                     b2, ctx->debug ? lv.act[1] : nullptr, lv.act[2], B));
+  } else {
     const long long total = (long long)B * le.H1 * le.W1;
     ctx->note("conv1", (double)B * lv.H8 * lv.W8 + (double)total * net.c1 * 2, 2.0 * 9 * total * net.c1);
     hfb_launch(ctx, conv1_kernel, (unsigned)((total + 255) / 256), 256, 0, 
@@ -694,6 +707,7 @@ int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
     const __half* dw_in = in;
     const long long Min = (long long)B * bp.Hi * bp.Wi, Mout = (long long)B * bp.Ho * bp.Wo;
     const std::string ln = "l" + std::to_string(bw.layer);
+    if (stem && bw.layer == 2) continue;   // done by the stem kernel
     if (!bw.has_expand && bw.stride == 1 && !bw.residual && bw.cexp == 24 && bw.cout == 16) {
       ctx->note(ln + ".dw+project", 2.0 * Min * bw.cin + 2.0 * Mout * bw.cout, 2.0 * Mout * bw.cexp * (9 + bw.cout));
       hfb_launch(ctx, dw_project_small_kernel<24, 16>, (unsigned)((Mout + 127) / 128), 128, 0, 

@@ -34,7 +34,7 @@ def run(env):
     return out
 
 
-ref = run({"HFB_FUSED": "0"})
+ref = run({"HFB_FUSED": "0", "HFB_STEM": "0"})
 new = run({"HFB_TRACE": "1"})
 bad = 0
 for L in range(2, 19):
