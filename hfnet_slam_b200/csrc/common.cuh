@@ -113,6 +113,14 @@ struct hfb_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool fork_branches = true;            // HFB_FORK=0: everything on one stream
   bool fused_stem = true;               // HFB_STEM=0: layer_1 and layer_2 as two kernels
+  bool join_pending = false;            // the global branch is still running on side_stream (joined by enqueue_extract)
+  // Host destinations of the extraction results when they can be written by the extraction graph itself (page-locked,
+  // contiguous over the batch): the local features leave on the main stream while the global branch is still computing.
+  struct D2HPlan {
+    bool on = false;
+    float *x = nullptr, *y = nullptr, *r = nullptr, *d = nullptr, *g = nullptr;
+    int *o = nullptr, *counts = nullptr, *overflow = nullptr;
+  } d2h;
   std::string err;
   uint64_t launches = 0;
   // weights

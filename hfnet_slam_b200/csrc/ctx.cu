@@ -423,6 +423,24 @@ static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, floa
                                  lv.scale, l, B, ctx->kp_cap, ctx->d_kx, ctx->d_ky, ctx->d_kresp, ctx->d_koct,
                                  ctx->d_kdesc, ctx->d_kcount, ctx->d_overflow, true));
   }
+  // results that do not depend on the global branch leave now (main stream), overlapping the side stream
+  const hfb_ctx::D2HPlan& d = ctx->d2h;
+  const size_t rows = (size_t)B * ctx->kp_cap;
+  if (d.on) {
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.counts, ctx->d_kcount, (size_t)B * HFB_MAX_LEVELS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.overflow, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.x, ctx->d_kx, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.y, ctx->d_ky, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.r, ctx->d_kresp, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.o, ctx->d_koct, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.d, ctx->d_kdesc, rows * HFB_DESC_DIM * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (ctx->join_pending) {
+    ctx->join_pending = false;
+    HFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  }
+  if (d.on && d.g)
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.g, ctx->d_global, (size_t)B * HFB_GLOBAL_DIM * 4, cudaMemcpyDeviceToHost, ctx->stream));
   return HFB_OK;
 }
 
@@ -442,6 +460,14 @@ static int run_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float th
   int tb;
   memcpy(&tb, &threshold, 4);
   key.push_back(tb);
+  if (ctx->d2h.on) {   // the captured copies target these host addresses
+    const void* ps[8] = {ctx->d2h.x, ctx->d2h.y, ctx->d2h.r, ctx->d2h.d, ctx->d2h.g, ctx->d2h.o, ctx->d2h.counts, ctx->d2h.overflow};
+    for (const void* q : ps) {
+      const uint64_t v = (uint64_t)(uintptr_t)q;
+      key.push_back((int)(v & 0xffffffffu));
+      key.push_back((int)(v >> 32));
+    }
+  }
   for (auto& g : ctx->graphs)
     if (g.key == key) {
       HFB_CUDA(ctx, cudaGraphLaunch(g.exec, ctx->stream));
@@ -546,6 +572,53 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
     }
   }
   tm.mark("stage_in");
+  // Fast path: page-locked outputs that are contiguous over the batch (frame b's rows start at b * kp_cap of one array
+  // per field) are written by the extraction graph itself, the local features ahead of the global branch's join.
+  {
+    bool fast = true;
+    const hfb_features& f0 = outs[0];
+    for (int b = 0; b < n_images && fast; ++b) {
+      const hfb_features& f = outs[b];
+      const size_t o = (size_t)b * ctx->kp_cap;
+      fast = f.x == f0.x + o && f.y == f0.y + o && f.response == f0.response + o && f.octave == f0.octave + o &&
+             f.descriptors == f0.descriptors + o * HFB_DESC_DIM &&
+             (!ctx->cfg.with_global ? true
+                                    : (f0.global_descriptor ? f.global_descriptor == f0.global_descriptor + (size_t)b * HFB_GLOBAL_DIM
+                                                            : f.global_descriptor == nullptr));
+    }
+    fast = fast && is_pinned(f0.x) && is_pinned(f0.y) && is_pinned(f0.response) && is_pinned(f0.octave) &&
+           is_pinned(f0.descriptors) && (!f0.global_descriptor || is_pinned(f0.global_descriptor));
+    if (fast) {
+      int* hc = reinterpret_cast<int*>(hs + (size_t)n_images * img_bytes);   // counts + overflow flag in the pinned stage
+      ctx->d2h.on = true;
+      ctx->d2h.x = f0.x; ctx->d2h.y = f0.y; ctx->d2h.r = f0.response; ctx->d2h.o = f0.octave;
+      ctx->d2h.d = f0.descriptors;
+      ctx->d2h.g = ctx->cfg.with_global ? f0.global_descriptor : nullptr;
+      ctx->d2h.counts = hc;
+      ctx->d2h.overflow = hc + (size_t)n_images * HFB_MAX_LEVELS;
+      const int rc = run_extract(ctx, n_images, n_per_level, threshold);
+      ctx->d2h.on = false;
+      HFB_TRY(rc);
+      tm.mark("enqueue");
+      HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      tm.mark("gpu_wait");
+      if (*ctx->d2h.overflow) {
+        cudaMemsetAsync(ctx->d_overflow, 0, sizeof(int), ctx->stream);
+        ctx->set_error("more threshold-scan candidates than the context's candidate capacity (threshold too low)");
+        return HFB_ERR_CAPACITY;
+      }
+      for (int b = 0; b < n_images; ++b) {
+        hfb_features& f = outs[b];
+        int total = 0;
+        for (int l = 0; l < HFB_MAX_LEVELS; ++l) {
+          f.n_per_level[l] = l < ctx->n_levels ? hc[(size_t)b * HFB_MAX_LEVELS + l] : 0;
+          total += f.n_per_level[l];
+        }
+        f.n_total = total;
+      }
+      return HFB_OK;
+    }
+  }
   HFB_TRY(run_extract(ctx, n_images, n_per_level, threshold));
   tm.mark("enqueue");
   // outputs: one D2H burst of budget-sized slices, one synchronisation.  Page-locked caller arrays receive the DMA

@@ -766,7 +766,7 @@ int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
   }
   ctx->note("nms", 8.0 * B * lv.H8 * lv.W8, 0);
   HFB_TRY(launch_nms(ctx, lv.d_scores, lv.d_nms, lv.H8, lv.W8, B, threshold, lv.d_cand, lv.d_cand_count, ctx->cand_cap));
-  if (fork) HFB_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+  if (fork) ctx->join_pending = true;   // joined by the caller once the local branch has been enqueued completely
   else if (lv.global) HFB_TRY(global_head(ctx, lv, le, B));
   return HFB_OK;
 }
