@@ -194,18 +194,18 @@ def main_gpu(args):
         torch.cuda.synchronize(dev)
 
     def step_dev():
-        ctx.extract_batch_dev(d_frames.data_ptr(), B, budgets, THR)
-        ctx.match_consecutive_dev(B, 0, 0.6)
+        # extraction + frame-to-previous-frame association as one enqueue: the matching runs on the main stream while
+        # the global branch (layer_8 .. FC) finishes on the side stream
+        ctx.extract_match_batch_dev(d_frames.data_ptr(), B, budgets, THR, 0, 0.6)
 
     match_out = (pinned_empty((B, ctx.kp_cap), np.int32), pinned_empty((B, ctx.kp_cap), np.float32))
 
     def step_host():
         # HFextractor::operator() on host frames (H2D of the u8 frames, D2H of keypoints / descriptors / global
-        # descriptors), then the frame-to-previous-frame association on the descriptors still resident in HBM (D2H of
-        # the match rows only)
-        feats = ctx.extract_batch(pinned_frames, budgets, THR, pinned=True)
+        # descriptors) and the frame-to-previous-frame association on the descriptors still resident in HBM (D2H of
+        # the match rows only) through hfb_extract_match_batch
+        feats, idx, val = ctx.extract_match_batch(pinned_frames, budgets, THR, 0, 0.6, pinned=True, out=match_out)
         cnt = np.array([len(f["x"]) for f in feats], np.int32)
-        idx, val = ctx.match_consecutive(B, 0, 0.6, out=match_out)
         return feats, cnt, idx
 
     def timed(fn, steps, warm):

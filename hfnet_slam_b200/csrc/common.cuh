@@ -111,6 +111,8 @@ struct hfb_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t side_stream = nullptr;   // global branch of the encoder (forked off after layer_7)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t copy_stream = nullptr;   // in-graph D2H of the local features, concurrent with the matching kernels
+  cudaEvent_t ev_local = nullptr, ev_copied = nullptr;
   bool fork_branches = true;            // HFB_FORK=0: everything on one stream
   bool fused_stem = true;               // HFB_STEM=0: layer_1 and layer_2 as two kernels
   bool join_pending = false;            // the global branch is still running on side_stream (joined by enqueue_extract)
@@ -120,7 +122,16 @@ struct hfb_ctx {
     bool on = false;
     float *x = nullptr, *y = nullptr, *r = nullptr, *d = nullptr, *g = nullptr;
     int *o = nullptr, *counts = nullptr, *overflow = nullptr;
+    int* match_idx = nullptr;      // with fused matching: [B][kp_cap] rows
+    float* match_val = nullptr;
   } d2h;
+  // Frame-to-previous-frame association enqueued inside the extraction (hfb_extract_match_batch*): it only needs the
+  // local features, so it runs on the main stream while the global branch is still computing.
+  struct FusedMatch {
+    bool on = false;
+    int mode = 0;
+    float thr = 0.f;
+  } fmatch;
   std::string err;
   uint64_t launches = 0;
   // weights

@@ -120,6 +120,9 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
     HFB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
     HFB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
   }
+  HFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_local, cudaEventDisableTiming));
+  HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   if (const char* fk = getenv("HFB_FORK")) ctx->fork_branches = !(fk[0] == '0');
@@ -196,6 +199,9 @@ extern "C" void hfb_destroy(hfb_ctx* ctx) {
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_io) cudaFree(ctx->d_io);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->ev_local) cudaEventDestroy(ctx->ev_local);
+  if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
@@ -409,6 +415,8 @@ static int check_overflow(hfb_ctx* ctx) {
   return HFB_OK;
 }
 
+static int enqueue_match_consecutive(hfb_ctx* ctx, int n_images, int mode, float thr);
+
 // Enqueues pyramid + encoder + selection of every level for frames already in lv[0].d_img.
 static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float threshold) {
   for (int l = 0; l < ctx->n_levels; ++l) {
@@ -423,18 +431,29 @@ static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, floa
                                  lv.scale, l, B, ctx->kp_cap, ctx->d_kx, ctx->d_ky, ctx->d_kresp, ctx->d_koct,
                                  ctx->d_kdesc, ctx->d_kcount, ctx->d_overflow, true));
   }
-  // results that do not depend on the global branch leave now (main stream), overlapping the side stream
+  // everything that does not depend on the global branch happens now (main stream), overlapping the side stream:
+  // the optional frame-to-previous-frame association and the transfer of the local features
   const hfb_ctx::D2HPlan& d = ctx->d2h;
   const size_t rows = (size_t)B * ctx->kp_cap;
-  if (d.on) {
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.counts, ctx->d_kcount, (size_t)B * HFB_MAX_LEVELS * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.overflow, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.x, ctx->d_kx, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.y, ctx->d_ky, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.r, ctx->d_kresp, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.o, ctx->d_koct, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.d, ctx->d_kdesc, rows * HFB_DESC_DIM * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (d.on) {   // feature transfer on its own stream: the copy engine works while the matching kernels run
+    cudaStream_t cs = ctx->copy_stream;
+    HFB_CUDA(ctx, cudaEventRecord(ctx->ev_local, ctx->stream));
+    HFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_local, 0));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.counts, ctx->d_kcount, (size_t)B * HFB_MAX_LEVELS * 4, cudaMemcpyDeviceToHost, cs));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.overflow, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, cs));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.x, ctx->d_kx, rows * 4, cudaMemcpyDeviceToHost, cs));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.y, ctx->d_ky, rows * 4, cudaMemcpyDeviceToHost, cs));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.r, ctx->d_kresp, rows * 4, cudaMemcpyDeviceToHost, cs));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.o, ctx->d_koct, rows * 4, cudaMemcpyDeviceToHost, cs));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.d, ctx->d_kdesc, rows * HFB_DESC_DIM * 4, cudaMemcpyDeviceToHost, cs));
+    HFB_CUDA(ctx, cudaEventRecord(ctx->ev_copied, cs));
   }
+  if (ctx->fmatch.on) HFB_TRY(enqueue_match_consecutive(ctx, B, ctx->fmatch.mode, ctx->fmatch.thr));
+  if (d.on && d.match_idx) {
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.match_idx, ctx->d_cm_idx, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.match_val, ctx->d_cm_val, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (d.on) HFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
   if (ctx->join_pending) {
     ctx->join_pending = false;
     HFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
@@ -460,8 +479,15 @@ static int run_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float th
   int tb;
   memcpy(&tb, &threshold, 4);
   key.push_back(tb);
+  if (ctx->fmatch.on) {
+    int tt;
+    memcpy(&tt, &ctx->fmatch.thr, 4);
+    key.push_back(0x4d415443 + ctx->fmatch.mode);
+    key.push_back(tt);
+  }
   if (ctx->d2h.on) {   // the captured copies target these host addresses
-    const void* ps[8] = {ctx->d2h.x, ctx->d2h.y, ctx->d2h.r, ctx->d2h.d, ctx->d2h.g, ctx->d2h.o, ctx->d2h.counts, ctx->d2h.overflow};
+    const void* ps[10] = {ctx->d2h.x, ctx->d2h.y, ctx->d2h.r, ctx->d2h.d, ctx->d2h.g, ctx->d2h.o, ctx->d2h.counts, ctx->d2h.overflow,
+                          ctx->d2h.match_idx, ctx->d2h.match_val};
     for (const void* q : ps) {
       const uint64_t v = (uint64_t)(uintptr_t)q;
       key.push_back((int)(v & 0xffffffffu));
@@ -547,8 +573,19 @@ extern "C" int hfb_fetch_features(hfb_ctx* ctx, int32_t image_index, hfb_feature
 
 extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int32_t n_images, int32_t stride,
                                  const int32_t* n_per_level, float threshold, hfb_features* outs) {
+  return hfb_extract_match_batch(ctx, images, n_images, stride, n_per_level, threshold, outs, -1, 0.f, nullptr, nullptr);
+}
+
+// hfb_extract_batch + hfb_match_consecutive in one call (match_mode < 0: extraction only).  The association is enqueued
+// inside the extraction, ahead of the global branch's join.
+extern "C" int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* images, int32_t n_images, int32_t stride,
+                                       const int32_t* n_per_level, float threshold, hfb_features* outs,
+                                       int32_t match_mode, float match_thr, int32_t* match_idx, float* match_val) {
   if (!ctx) return HFB_ERR_INVALID;
   HFB_REQUIRE(ctx, images && n_per_level && outs, "null argument");
+  const bool want_match = match_mode >= 0;
+  HFB_REQUIRE(ctx, !want_match || ((match_mode == 0 || match_mode == 1) && match_idx && match_val),
+              "match mode must be 0 (l2) or 1 (cos) with non-null outputs");
   HFB_REQUIRE(ctx, n_images >= 1 && n_images <= ctx->cfg.max_batch, "batch size outside [1, max_batch]");
   LevelPlan& l0 = ctx->lv[0];
   HFB_REQUIRE(ctx, stride >= l0.W, "stride smaller than the image width");
@@ -587,7 +624,8 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
                                                             : f.global_descriptor == nullptr));
     }
     fast = fast && is_pinned(f0.x) && is_pinned(f0.y) && is_pinned(f0.response) && is_pinned(f0.octave) &&
-           is_pinned(f0.descriptors) && (!f0.global_descriptor || is_pinned(f0.global_descriptor));
+           is_pinned(f0.descriptors) && (!f0.global_descriptor || is_pinned(f0.global_descriptor)) &&
+           (!want_match || (is_pinned(match_idx) && is_pinned(match_val)));
     if (fast) {
       int* hc = reinterpret_cast<int*>(hs + (size_t)n_images * img_bytes);   // counts + overflow flag in the pinned stage
       ctx->d2h.on = true;
@@ -596,8 +634,14 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
       ctx->d2h.g = ctx->cfg.with_global ? f0.global_descriptor : nullptr;
       ctx->d2h.counts = hc;
       ctx->d2h.overflow = hc + (size_t)n_images * HFB_MAX_LEVELS;
+      ctx->d2h.match_idx = want_match ? match_idx : nullptr;
+      ctx->d2h.match_val = want_match ? match_val : nullptr;
+      ctx->fmatch.on = want_match;
+      ctx->fmatch.mode = match_mode;
+      ctx->fmatch.thr = match_thr;
       const int rc = run_extract(ctx, n_images, n_per_level, threshold);
       ctx->d2h.on = false;
+      ctx->fmatch.on = false;
       HFB_TRY(rc);
       tm.mark("enqueue");
       HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -679,6 +723,7 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
     if (f.global_descriptor && ctx->cfg.with_global) memcpy(f.global_descriptor, s.g, HFB_GLOBAL_DIM * 4);
   }
   tm.mark("copy_out");
+  if (want_match) HFB_TRY(hfb_match_consecutive(ctx, n_images, match_mode, match_thr, match_idx, match_val));
   return HFB_OK;
 }
 
@@ -922,6 +967,24 @@ __global__ void consecutive_tab_kernel(const int* __restrict__ kcount, int n_lev
 // hfb_extract_batch*(n_images) never leave HBM.  Frame b is matched against frame (b-1) mod n_images.
 extern "C" int hfb_match_consecutive_dev(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr) {
   if (!ctx) return HFB_ERR_INVALID;
+  return enqueue_match_consecutive(ctx, n_images, mode, thr);
+}
+
+// Device-resident extraction + association in one enqueue (see hfb_extract_match_batch).  No sync.
+extern "C" int hfb_extract_match_batch_dev(hfb_ctx* ctx, const uint8_t* d_images, int32_t n_images,
+                                           const int32_t* n_per_level, float threshold, int32_t match_mode,
+                                           float match_thr) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, match_mode == 0 || match_mode == 1, "mode must be 0 (l2) or 1 (cos)");
+  ctx->fmatch.on = true;
+  ctx->fmatch.mode = match_mode;
+  ctx->fmatch.thr = match_thr;
+  const int rc = hfb_extract_batch_dev(ctx, d_images, n_images, n_per_level, threshold);
+  ctx->fmatch.on = false;
+  return rc;
+}
+
+static int enqueue_match_consecutive(hfb_ctx* ctx, int n_images, int mode, float thr) {
   HFB_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (l2) or 1 (cos)");
   HFB_REQUIRE(ctx, n_images >= 1 && n_images <= ctx->last_batch, "n_images exceeds the last extracted batch");
   consecutive_tab_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_kcount, ctx->n_levels, n_images, ctx->kp_cap, ctx->d_cm_tab);

@@ -354,7 +354,7 @@ __global__ void vlad_normalize_kernel(const float* __restrict__ vlad, int C, int
 }
 
 // (4) FC K -> 4096 (layers.py:99-107): split-K GEMV over the fp16 weight [K][4096]; each thread owns 8 columns.
-#define FC_BCH 4
+#define FC_BCH 8
 __global__ void __launch_bounds__(256) fc_partial_kernel(const float* __restrict__ v, int K, int B,
                                                          const __half* __restrict__ w, int N, int k_per_split,
                                                          float* __restrict__ partial) {

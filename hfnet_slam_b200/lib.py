@@ -70,6 +70,9 @@ SIGNATURES = {
     "hfb_extract_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _i32p, C.c_float,
                                     C.POINTER(hfb_features)]),
     "hfb_extract_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _i32p, C.c_float]),
+    "hfb_extract_match_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _i32p, C.c_float,
+                                          C.POINTER(hfb_features), C.c_int32, C.c_float, _i32p, _f32p]),
+    "hfb_extract_match_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _i32p, C.c_float, C.c_int32, C.c_float]),
     "hfb_fetch_features": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(hfb_features)]),
     "hfb_nms": (C.c_int, [C.c_void_p, _f32p, C.c_int32, C.c_int32, _f32p]),
     "hfb_select_sample": (C.c_int, [C.c_void_p, _f32p, C.c_int32, C.c_int32, _f32p, C.c_int32, C.c_int32, C.c_int32,
@@ -286,6 +289,30 @@ class Context:
                                               feats))
         out = [self._view(feats[i], arrs, i, self.with_global) for i in range(n)]
         return (out, arrs) if return_block else out
+
+    def extract_match_batch(self, images, n_per_level, threshold: float, mode: int, thr: float, pinned: bool = False,
+                            out=None):
+        """extract_batch + match_consecutive as one call (hfb_extract_match_batch): returns (features, idx, val) with
+        idx / val [n][kp_cap] (row b: frame b -> frame b-1).  pinned=True: page-locked outputs written by the graph."""
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        for im in imgs:
+            if im.ndim != 2 or im.shape != (self.height, self.width):
+                raise HfbError(1, f"image shape {im.shape} differs from the context's {(self.height, self.width)}")
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        feats, arrs = self._alloc_features(n, pinned)
+        if out is None:
+            mk = pinned_empty if pinned else np.empty
+            out = (mk((n, self.kp_cap), np.int32), mk((n, self.kp_cap), np.float32))
+        idx, val = out
+        self.check(self.lib.hfb_extract_match_batch(self.handle, ptrs, n, self.width, self._budgets(n_per_level),
+                                                    threshold, feats, mode, thr, ptr(idx, _i32p), ptr(val, _f32p)))
+        return [self._view(feats[i], arrs, i, self.with_global) for i in range(n)], idx, val
+
+    def extract_match_batch_dev(self, d_images_ptr: int, n_images: int, n_per_level, threshold: float, mode: int,
+                                thr: float):
+        self.check(self.lib.hfb_extract_match_batch_dev(self.handle, C.c_void_p(d_images_ptr), n_images,
+                                                        self._budgets(n_per_level), threshold, mode, thr))
 
     def extract(self, image, n_per_level, threshold: float) -> dict:
         return self.extract_batch([image], n_per_level, threshold)[0]

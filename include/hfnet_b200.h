@@ -183,6 +183,15 @@ int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, const float* 
  * Matcher::SearchByBoW / SearchForInitialization call sites, src/Tracking.cc:2030,1796) with the descriptors of the last
  * hfb_extract_batch* still resident in HBM: frame b is matched against frame (b-1) mod n_images.  No sync. */
 int hfb_match_consecutive_dev(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr);
+/* Extraction and the association above as ONE call: the matching kernels only need the local features, so they (and,
+ * for page-locked batch-contiguous outputs, the transfer of keypoints / descriptors / match rows) are enqueued on the
+ * main stream while the global branch (layer_8 .. FC) is still computing on the side stream.  match_mode < 0 skips the
+ * association (== hfb_extract_batch).  match_idx / match_val: [n_images][kp_cap] as for hfb_match_consecutive. */
+int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* images, int32_t n_images, int32_t stride,
+                            const int32_t* n_per_level, float threshold, hfb_features* outs, int32_t match_mode,
+                            float match_thr, int32_t* match_idx, float* match_val);
+int hfb_extract_match_batch_dev(hfb_ctx* ctx, const uint8_t* d_images, int32_t n_images, const int32_t* n_per_level,
+                                float threshold, int32_t match_mode, float match_thr);
 /* Same, synchronous, results to host: match_idx / match_val are [n_images][kp_cap] rows (kp_cap = n_levels *
  * max_keypoints; row b holds frame b's matches into frame (b-1) mod n_images, -1 = unmatched).  This is the call
  * Tracking makes right after Frame construction: the previous frame's descriptors are still resident, so nothing is

@@ -182,3 +182,11 @@ def test_consecutive_match_on_resident_descriptors(ctx_euroc):
         one_idx, one_val = ctx_euroc.fetch_matches(b, len(A))
         assert np.array_equal(one_idx, idx[b, :len(A)]) and np.array_equal(one_val, val[b, :len(A)])
         assert (idx[b, len(A):] < 0).all()
+    # the one-call form (association enqueued inside the extraction, ahead of the global branch) gives the same rows,
+    # through pageable and through page-locked outputs
+    for pinned in (False, True):
+        feats2, idx2, val2 = ctx_euroc.extract_match_batch(imgs, [1000], 0.01, 0, 0.6, pinned=pinned)
+        assert np.array_equal(idx2, idx) and np.array_equal(val2, val), f"pinned={pinned}"
+        for b in range(2):
+            for k in ("x", "y", "response", "descriptors", "global_descriptor"):
+                assert np.array_equal(feats2[b][k], feats[b][k]), (pinned, b, k)
