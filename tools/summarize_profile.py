@@ -42,8 +42,10 @@ def main():
           f"({bench['e2e'].get('ms_per_step', 0):.3f} ms/step), launches/timed region {bench['gpu_launches']}")
     print(f"* clocks {bench['clocks']}")
     r = bench["roofline"]
+    tr = r.get("traffic")
     print(f"* roofline: `{r['kernel']}` {r['bound']}-bound, {r['achieved']:.1f} {r['unit']} of {r['peak']} "
-          f"({100 * r['frac']:.1f}%), {r['ms_per_launch'] * 1e3:.1f} us/launch, share of step {100 * r['share_of_step']:.1f}%")
+          f"({100 * r['frac']:.1f}%), {r['ms_per_launch'] * 1e3:.1f} us/launch, share of step {100 * r['share_of_step']:.1f}%, "
+          f"algorithmic {r['algorithmic_bytes'] / 1e6:.1f} MB, DRAM traffic (ncu) {('%.1f MB' % (tr / 1e6)) if tr else 'n/a'}")
     print("\n| kernel (event-timed, un-graphed step) | ms | share | HBM frac | tensor frac |\n|---|---:|---:|---:|---:|")
     for k in bench["extra"]["kernels"]:
         print(f"| {k['name']} | {k['ms']:.4f} | {100 * k['share']:.1f}% | {100 * k['hbm_frac']:.1f}% | {100 * k['tensor_frac']:.1f}% |")
