@@ -283,6 +283,20 @@ def main_gpu(args):
     extra = {"keypoints_frame0": int(len(f0["x"])), "matches_frame0": int((midx >= 0).sum()),
              "host_matches_frame0": int((hidx[0, :cnt[0]] >= 0).sum()), "ungraphed_step_ms": total_ms, "kernels": kernels}
 
+    # ---- single-frame latency (what the reference's per-frame TrackMonocular loop sees), device-resident and host API
+    def one_dev():
+        ctx.extract_match_batch_dev(d_frames.data_ptr(), 1, budgets, THR, 0, 0.6)
+
+    match_out1 = (pinned_empty((1, ctx.kp_cap), np.int32), pinned_empty((1, ctx.kp_cap), np.float32))
+
+    def one_host():
+        ctx.extract_match_batch(pinned_frames[:1], budgets, THR, 0, 0.6, pinned=True, out=match_out1)
+
+    ms1_dev, _, _ = timed(one_dev, 20, 3)
+    ms1_host, _, _ = timed(one_host, 20, 3)
+    extra["single_frame"] = {"device_ms": ms1_dev / 20, "host_api_ms": ms1_host / 20,
+                             "note": "batch of 1 (self-association), same graph path as the batched step"}
+
     # ---- the other two parts of the metric ------------------------------------------------------------------
     if not args.skip_extra:
         # loop-DB: 50 k x 4096 fp32 rows sharded by id % world, one all-gather of fixed-size shard records

@@ -257,6 +257,9 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
                        int max_a, int max_b, float thr, int* d_match_idx, float* d_match_val, int na_total,
                        int nb_total, int** d_n_matches_out);
 
+int launch_distinctive(hfb_ctx* ctx, const float* d_desc, const int* d_offsets, int n_points, int max_n, int* d_best_idx,
+                       float* d_best_med);
+
 // order-preserving float <-> uint32 map (larger float -> larger uint)
 __host__ __device__ static inline unsigned int f2ord(float f) {
 #ifdef __CUDA_ARCH__

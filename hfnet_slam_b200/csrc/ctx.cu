@@ -1020,6 +1020,40 @@ extern "C" int hfb_match_consecutive(hfb_ctx* ctx, int32_t n_images, int32_t mod
   return HFB_OK;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors for a ragged batch of map points (src/MapPoint.cc:331-400).
+extern "C" int hfb_distinctive_descriptors(hfb_ctx* ctx, const float* descriptors, const int32_t* offsets,
+                                           int32_t n_points, int32_t* best_index, float* best_median) {
+  if (!ctx) return HFB_ERR_INVALID;
+  HFB_REQUIRE(ctx, n_points >= 0 && offsets && best_index && best_median, "bad argument");
+  if (n_points == 0) return HFB_OK;
+  int max_n = 0;
+  HFB_REQUIRE(ctx, offsets[0] == 0, "offsets must start at 0");
+  for (int p = 0; p < n_points; ++p) {
+    HFB_REQUIRE(ctx, offsets[p + 1] >= offsets[p], "offsets must be non-decreasing");
+    max_n = std::max(max_n, offsets[p + 1] - offsets[p]);
+  }
+  HFB_REQUIRE(ctx, max_n <= 128, "more than 128 observations for one map point");
+  const int total = offsets[n_points];
+  HFB_REQUIRE(ctx, total == 0 || descriptors, "null descriptors");
+  const size_t szD = ((size_t)total * HFB_DESC_DIM * 4 + 255) & ~(size_t)255;
+  const size_t szO = ((size_t)(n_points + 1) * 4 + 255) & ~(size_t)255;
+  const size_t szR = ((size_t)n_points * 4 + 255) & ~(size_t)255;
+  HFB_TRY(ctx->ensure_io(szD + szO + 2 * szR));
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->d_io);
+  float* dD = reinterpret_cast<float*>(base);
+  int* dO = reinterpret_cast<int*>(base + szD);
+  int* dI = reinterpret_cast<int*>(base + szD + szO);
+  float* dM = reinterpret_cast<float*>(base + szD + szO + szR);
+  if (total > 0)
+    HFB_CUDA(ctx, cudaMemcpyAsync(dD, descriptors, (size_t)total * HFB_DESC_DIM * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(dO, offsets, (size_t)(n_points + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_TRY(launch_distinctive(ctx, dD, dO, n_points, max_n, dI, dM));
+  HFB_CUDA(ctx, cudaMemcpyAsync(best_index, dI, (size_t)n_points * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(best_median, dM, (size_t)n_points * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
+}
+
 static int match_host(hfb_ctx* ctx, int mode, const float* A_all, int na_total, const float* B_all, int nb_total,
                       int n_pairs, const int32_t* a_off, const int32_t* a_cnt, const int32_t* b_off,
                       const int32_t* b_cnt, float thr, int32_t* match_idx, float* match_val, int32_t* n_matches) {

@@ -477,3 +477,97 @@ extern "C" int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, co
   HFB_CUDA(ctx, cudaStreamSynchronize(st));
   return HFB_OK;
 }
+
+// =============================================================================================== distinctive descriptors
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:331-400) for a ragged batch of map points: all-pairs
+// Matcher::DescriptorDistance over a point's N observed descriptors, per-row median (sorted[int(0.5 * (N-1))]), first row
+// with the smallest median.  One CTA per map point: a warp evaluates one pair at a time in the literal difference form
+// (lane = 8 of the 256 components, butterfly sum), the N x N table lives in shared memory, thread i then finds row i's
+// median by rank counting (no sort: rank(j) = #{k : d[k] < d[j]} + #{k < j : d[k] == d[j]}) and the CTA takes the first
+// minimum.  N <= DD_MAXN per point (more observations than any keyframe window holds); larger points report -2.
+#define DD_MAXN 128
+__global__ void __launch_bounds__(256) distinctive_kernel(const float* __restrict__ desc, const int* __restrict__ offsets,
+                                                          int* __restrict__ best_idx, float* __restrict__ best_med) {
+  extern __shared__ float s_d[];   // [N][N]
+  __shared__ float s_med[DD_MAXN];
+  const int p = blockIdx.x;
+  const int r0 = offsets[p], N = offsets[p + 1] - r0;
+  if (N <= 0 || N > DD_MAXN) {
+    if (threadIdx.x == 0) {
+      best_idx[p] = N <= 0 ? -1 : -2;
+      best_med[p] = 3.402823466e+38f;
+    }
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* D = desc + (size_t)r0 * HFB_DESC_DIM;
+  const int n_pairs = N * (N - 1) / 2;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_d[i * N + i] = 0.f;
+  for (int q = warp; q < n_pairs; q += nw) {
+    // pair index -> (i, j), i < j, rows enumerated i-major
+    int i = 0, rem = q;
+    while (rem >= N - 1 - i) {
+      rem -= N - 1 - i;
+      ++i;
+    }
+    const int j = i + 1 + rem;
+    const float4* a = reinterpret_cast<const float4*>(D + (size_t)i * HFB_DESC_DIM) + lane * 2;
+    const float4* b = reinterpret_cast<const float4*>(D + (size_t)j * HFB_DESC_DIM) + lane * 2;
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 x = __ldg(a + h), y = __ldg(b + h);
+      float t = x.x - y.x; s = fmaf(t, t, s);
+      t = x.y - y.y; s = fmaf(t, t, s);
+      t = x.z - y.z; s = fmaf(t, t, s);
+      t = x.w - y.w; s = fmaf(t, t, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      const float d = sqrtf(s);
+      s_d[i * N + j] = d;
+      s_d[j * N + i] = d;
+    }
+  }
+  __syncthreads();
+  const int target = (int)(0.5 * (N - 1));
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float* row = s_d + i * N;
+    float med = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float v = row[j];
+      int rank = 0;
+      for (int k = 0; k < N; ++k) rank += (row[k] < v) || (row[k] == v && k < j);
+      if (rank == target) med = v;
+    }
+    s_med[i] = med;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bm = 3.402823466e+38f;
+    int bi = 0;
+    for (int i = 0; i < N; ++i)
+      if (s_med[i] < bm) {
+        bm = s_med[i];
+        bi = i;
+      }
+    best_idx[p] = bi;
+    best_med[p] = bm;
+  }
+}
+
+int launch_distinctive(hfb_ctx* ctx, const float* d_desc, const int* d_offsets, int n_points, int max_n, int* d_best_idx,
+                       float* d_best_med) {
+  if (n_points <= 0) return HFB_OK;
+  const int n = std::min(std::max(max_n, 1), DD_MAXN);
+  const size_t smem = (size_t)n * n * sizeof(float);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    HFB_CUDA(ctx, cudaFuncSetAttribute(distinctive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  distinctive_kernel<<<n_points, 256, smem, ctx->stream>>>(d_desc, d_offsets, d_best_idx, d_best_med);
+  HFB_CHECK_LAUNCH(ctx, "distinctive");
+  return HFB_OK;
+}

@@ -92,6 +92,7 @@ SIGNATURES = {
                                        _i32p, _u8p, _i32p, _f32p, _i32p]),
     "hfb_match_consecutive_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float]),
     "hfb_fetch_matches": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _f32p, C.c_int32]),
+    "hfb_distinctive_descriptors": (C.c_int, [C.c_void_p, _f32p, _i32p, C.c_int32, _i32p, _f32p]),
     "hfb_match_consecutive": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, _i32p, _f32p]),
     "hfb_profile_extract": (C.c_int, [C.c_void_p, C.c_int32, _i32p, C.c_float, C.c_char_p, C.c_size_t]),
     "hfb_kfdb_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
@@ -347,6 +348,17 @@ class Context:
 
     def match_consecutive_dev(self, n_images: int, mode: int, thr: float):
         self.check(self.lib.hfb_match_consecutive_dev(self.handle, n_images, mode, thr))
+
+    def distinctive_descriptors(self, descriptors, offsets):
+        """MapPoint::ComputeDistinctiveDescriptors for a ragged batch: returns (best_index int32[n], best_median f32[n])."""
+        d = as_f32(descriptors).reshape(-1, HFB_DESC_DIM)
+        off = np.ascontiguousarray(offsets, dtype=np.int32)
+        n = len(off) - 1
+        idx = np.full(n, -1, np.int32)
+        med = np.zeros(n, np.float32)
+        self.check(self.lib.hfb_distinctive_descriptors(self.handle, ptr(d, _f32p), ptr(off, _i32p), n, ptr(idx, _i32p),
+                                                        ptr(med, _f32p)))
+        return idx, med
 
     def match_consecutive(self, n_images: int, mode: int, thr: float, out=None):
         """Frame b of the last extraction against frame b-1 (descriptors resident in HBM); returns [n_images][kp_cap]

@@ -86,3 +86,14 @@ class Matcher:
                 out[i] = bi
                 taken.add(int(bi))
         return out
+
+    def compute_distinctive_descriptors(self, observations):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:331-400) for a batch of map points: ``observations``
+        is a list of [N_i][256] arrays (the descriptors of each point's observations).  Returns (index, median): the row
+        of each point with the least median L2 distance to the rest (-1 for a point without observations)."""
+        sizes = [int(np.asarray(o).shape[0]) for o in observations]
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        rows = [np.asarray(o, np.float32).reshape(-1, 256) for o in observations if np.asarray(o).shape[0]]
+        desc = np.concatenate(rows) if rows else np.zeros((0, 256), np.float32)
+        return self.ctx.distinctive_descriptors(desc, off)
+

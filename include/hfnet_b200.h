@@ -201,6 +201,13 @@ int hfb_match_consecutive(hfb_ctx* ctx, int32_t n_images, int32_t mode, float th
 /* match_idx / match_val of frame `image_index` (indices into the previous frame's keypoints), first n rows. */
 int hfb_fetch_matches(hfb_ctx* ctx, int32_t image_index, int32_t* match_idx, float* match_val, int32_t n);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:331-400) for a ragged batch of map points: point p owns the
+ * descriptor rows offsets[p] .. offsets[p+1]-1 (its observations, <= 128); best_index[p] is the row (relative to the
+ * point's first) whose median L2 distance to the point's other descriptors is smallest (first such row, the
+ * reference's strict '<' scan), best_median[p] that median (sorted[int(0.5 * (N - 1))]); -1 for a point without rows. */
+int hfb_distinctive_descriptors(hfb_ctx* ctx, const float* descriptors, const int32_t* offsets, int32_t n_points,
+                                int32_t* best_index, float* best_median);
+
 /* ------------------------------------------------------------------------------------------------------ keyframe DB
  * Replaces KeyFrameDatabase's linear scan (src/KeyFrameDatabase.cc:75-256).  Rows live in HBM as fp32 [capacity][dim].
  * The covisibility accumulation stays with the caller (it walks the KeyFrame graph); see include/HFNetB200Model.h. */

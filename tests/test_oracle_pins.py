@@ -157,3 +157,18 @@ def test_kfdb_candidate_rule():
     sel, best = kfdb_ref.candidate_set(sc, 0.8)
     assert sc.argmax() in sel and all(sc[i] > np.float32(0.8) * np.float32(best) for i in sel)
     assert int(qi[0]) in sel
+
+
+def test_distinctive_descriptor_oracle_matches_literal_loops():
+    """oracle/mappoint_ref.distinctive_index (vectorised) == the reference's loops transcribed one to one
+    (src/MapPoint.cc:368-394), including the int(0.5 * (N - 1)) median index and the strict '<' first-minimum scan."""
+    from oracle import mappoint_ref
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 4, 7, 12, 25):
+        D = rng.standard_normal((n, 256)).astype(np.float32)
+        D /= np.linalg.norm(D, axis=1, keepdims=True)
+        if n >= 4:
+            D[3] = D[1]            # duplicated observation: exact ties
+        a, am = mappoint_ref.distinctive_index(D)
+        b, bm = mappoint_ref.distinctive_index_literal(D)
+        assert a == b and abs(float(am) - float(bm)) < 1e-6, n
