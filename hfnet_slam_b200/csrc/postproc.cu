@@ -11,15 +11,21 @@
 #include "common.cuh"
 
 // =============================================================================================== simple_nms
-// One CTA produces a 64 x 32 tile.  Dependency radius is 12 (three chained 9x9 max-pools), so the tile is computed
-// from an 88 x 56 halo region held in (dynamic) shared memory: 2.4 halo pixels per output pixel; every pool is separable (row pass, column pass).  Each thread
-// produces a run of 8 outputs from 16 inputs with a suffix-max / prefix-max split (22 max ops, 2 smem loads per
-// output instead of 9).  Row pitch 89 (odd) keeps the row pass, whose lanes walk down rows, bank-conflict free.
+// simple_nms(radius 4, iterations 2):  M1 = (s == mp(s));  supp = mp(M1) > 0;  s' = supp ? 0 : s;
+// out = (M1 | ((s' == mp(s')) & !supp)) ? s : 0, mp = 9x9 max-pool, -inf outside the image.
+// One CTA produces a 64 x 32 tile.  The dependency radius is 12 (three chained pools), so the tile is computed from an
+// 88 x 56 halo region in shared memory (2.4 halo pixels per output pixel).  The two float pools are separable (row
+// pass, column pass); each thread produces a run of 8 outputs from 16 inputs with a suffix-max / prefix-max split
+// (22 max ops, 2 smem loads per output instead of 9).  Row pitch 89 (odd) keeps the row pass, whose lanes walk down
+// rows, bank-conflict free.  The middle pool runs on a 0/1 mask, so it is done on bit words: the column pass of the
+// first pool ballots M1 into 32-pixel words, the 9x9 dilation is shifts + ORs on 3 words per row, and s' is rebuilt on
+// the fly from the scores and the supp bits (two float planes instead of three: five CTAs per SM).
 #define NMS_TW 64
 #define NMS_TH 32
 #define NMS_AW (NMS_TW + 24)
 #define NMS_AH (NMS_TH + 24)
 #define NMS_P 89
+#define NMS_WORDS 3   // bit b of word g of a row = region column 4 + 32 g + b
 
 __device__ __forceinline__ void run9(const float (&v)[16], float (&o)[8]) {
   float L[8], R[8];
@@ -33,50 +39,20 @@ __device__ __forceinline__ void run9(const float (&v)[16], float (&o)[8]) {
   for (int j = 0; j < 8; ++j) o[j] = fmaxf(L[j], R[j]);
 }
 
-// dst[r][c] = max(src[r][c-4..c+4]) for r in [r0, r0+nrows), c in [c0, c0+ncols), ncols % 8 == 0
-__device__ __forceinline__ void rowmax_pass(const float (*src)[NMS_P], float (*dst)[NMS_P], int r0, int nrows, int c0,
-                                            int ncols) {
-  const int total = nrows * (ncols >> 3);
-  for (int i = threadIdx.x; i < total; i += 256) {
-    const int r = r0 + i % nrows, c = c0 + (i / nrows) * 8;
-    float v[16], o[8];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = src[r][c - 4 + j];
-    run9(v, o);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dst[r][c + j] = o[j];
-  }
-}
-
-// f(r, c, max(src[r-4..r+4][c])) for r in [r0, r0+nrows), c in [c0, c0+ncols), nrows % 8 == 0
-template <class F>
-__device__ __forceinline__ void colmax_pass(const float (*src)[NMS_P], int r0, int nrows, int c0, int ncols, F f) {
-  const int total = (nrows >> 3) * ncols;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    const int c = c0 + i % ncols, r = r0 + (i / ncols) * 8;
-    float v[16], o[8];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = src[r - 4 + j][c];
-    run9(v, o);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f(r + j, c, o[j]);
-  }
-}
-
 // With cand != null the kernel also performs the reference's threshold scan (HFNetRTModel.cc:150-168) on its own
 // output: every surviving pixel with score >= threshold is appended as a (score, scan index) key.
 __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H,
                                                   int W, float threshold, u64* __restrict__ cand,
                                                   int* __restrict__ cand_count, int cand_cap) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
-  float (*sS)[NMS_P] = reinterpret_cast<float (*)[NMS_P]>(nms_smem);                        // scores, -inf outside the image
-  float (*sT)[NMS_P] = sS + NMS_AH;                                                          // row-pass scratch
-  float (*sM)[NMS_P] = sT + NMS_AH;                                                          // max_mask (1/0) on region B, later s' on region C
-  unsigned char (*sSupp)[NMS_AW] = reinterpret_cast<unsigned char (*)[NMS_AW]>(sM + NMS_AH);
-  unsigned char (*sKeep)[NMS_TW] = reinterpret_cast<unsigned char (*)[NMS_TW]>(sSupp + NMS_AH);   // max_mask of the tile pixels
+  float (*sS)[NMS_P] = reinterpret_cast<float (*)[NMS_P]>(nms_smem);   // scores, -inf outside the image
+  float (*sT)[NMS_P] = sS + NMS_AH;                                     // row-pass scratch
+  uint32_t (*sM1)[NMS_WORDS] = reinterpret_cast<uint32_t (*)[NMS_WORDS]>(sT + NMS_AH);   // M1 bits, rows [4, AH-4)
+  uint32_t (*sRow)[NMS_WORDS] = sM1 + NMS_AH;                                               // M1 dilated along the row
+  uint32_t (*sSupp)[NMS_WORDS] = sRow + NMS_AH;                                             // supp bits, rows [8, AH-8)
   pdl_launch_dependents();
   pdl_wait();
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
   const float* src = scores + (size_t)blockIdx.z * H * W;
   float* dst = out + (size_t)blockIdx.z * H * W;
@@ -86,53 +62,124 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
     const int y = ay0 + r, x = ax0 + c;
     return y >= 0 && y < H && x >= 0 && x < W;
   };
-  for (int i = tid; i < NMS_AH * NMS_AW; i += 256) {
-    const int r = i / NMS_AW, c = i % NMS_AW;
-    sS[r][c] = inside(r, c) ? src[(size_t)(ay0 + r) * W + (ax0 + c)] : NEG;
+  if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // 16-byte loads: ax0 is a multiple of 4 and so is W, so a quad is entirely inside or outside the image
+    for (int i = tid; i < NMS_AH * (NMS_AW / 4); i += 256) {
+      const int r = i / (NMS_AW / 4), c = (i - r * (NMS_AW / 4)) * 4;
+      float4 v = make_float4(NEG, NEG, NEG, NEG);
+      if (inside(r, c)) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(ay0 + r) * W + (ax0 + c)));
+      sS[r][c] = v.x; sS[r][c + 1] = v.y; sS[r][c + 2] = v.z; sS[r][c + 3] = v.w;
+    }
+  } else {
+    for (int i = tid; i < NMS_AH * NMS_AW; i += 256) {
+      const int r = i / NMS_AW, c = i % NMS_AW;
+      sS[r][c] = inside(r, c) ? src[(size_t)(ay0 + r) * W + (ax0 + c)] : NEG;
+    }
   }
   __syncthreads();
-  // max_mask = (s == mp(s)) on B = rows [4,AH-4) x cols [4,84)
-  rowmax_pass(sS, sT, 0, NMS_AH, 4, NMS_AW - 8);
+  // ---- pool 1, row pass: sT[r][c] = max(sS[r][c-4..c+4]) on rows [0, AH) x cols [4, 84)
+  for (int i = tid; i < NMS_AH * 10; i += 256) {
+    const int r = i % NMS_AH, c = 4 + (i / NMS_AH) * 8;
+    float v[16], o[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = sS[r][c - 4 + j];
+    run9(v, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sT[r][c + j] = o[j];
+  }
   __syncthreads();
-  colmax_pass(sT, 4, NMS_AH - 8, 4, NMS_AW - 8, [&](int r, int c, float m) {
-    const bool mk = inside(r, c) && sS[r][c] == m;
-    sM[r][c] = mk ? 1.f : 0.f;
-    if (r >= 12 && r < 12 + NMS_TH && c >= 12 && c < 12 + NMS_TW) sKeep[r - 12][c - 12] = mk ? 1 : 0;
-  });
-  __syncthreads();
-  // supp = mp(max_mask) > 0 on C = rows [8,AH-8) x cols [8,80);  s' = supp ? 0 : s  (-inf outside the image)
-  rowmax_pass(sM, sT, 4, NMS_AH - 8, 8, NMS_AW - 16);
-  __syncthreads();
-  colmax_pass(sT, 8, NMS_AH - 16, 8, NMS_AW - 16, [&](int r, int c, float m) {
-    const bool supp = m > 0.f;
-    sSupp[r][c] = supp ? 1 : 0;
-    sM[r][c] = inside(r, c) ? (supp ? 0.f : sS[r][c]) : NEG;
-  });
-  __syncthreads();
-  // new = (s' == mp(s')) on the tile D = rows [12,AH-12) x cols [12,76);  out = (max_mask | (new & !supp)) ? s : 0
-  rowmax_pass(sM, sT, 8, NMS_AH - 16, 12, NMS_TW);
-  __syncthreads();
-  colmax_pass(sT, 12, NMS_TH, 12, NMS_TW, [&](int r, int c, float m) {
-    const int y = ay0 + r, x = ax0 + c;
-    if (y >= H || x >= W) return;
-    const bool is_new = (sM[r][c] == m);
-    const bool mx = sKeep[r - 12][c - 12] || (is_new && !sSupp[r][c]);
-    const float v = mx ? sS[r][c] : 0.f;
-    dst[(size_t)y * W + x] = v;
-    if (cand && v >= threshold) {
-      const int pos = atomicAdd(cand_count + blockIdx.z, 1);
-      if (pos < cand_cap)
-        cand[(size_t)blockIdx.z * cand_cap + pos] =
-            ((u64)f2ord(v) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(x * H + y));
+  // ---- pool 1, column pass + M1 = (s == mp(s)) as ballots: warp task = (8-row block, 32-column group)
+  for (int t = warp; t < ((NMS_AH - 8) / 8) * NMS_WORDS; t += 8) {
+    const int rb = t / NMS_WORDS, g = t - rb * NMS_WORDS;
+    const int r = 4 + rb * 8, c = 4 + 32 * g + lane;
+    const bool col_ok = c < NMS_AW - 4;
+    float o[8];
+    if (col_ok) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = sT[r - 4 + j][c];
+      run9(v, o);
     }
-  });
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool mk = col_ok && inside(r + j, c) && sS[r + j][c] == o[j];
+      const uint32_t word = __ballot_sync(0xffffffffu, mk);
+      if (lane == 0) sM1[r + j][g] = word;
+    }
+  }
+  __syncthreads();
+  // ---- pool 2 on bits: supp = 9x9 dilation of M1.  Row dilation of rows [4, AH-4), then column OR on rows [8, AH-8)
+  for (int i = tid; i < (NMS_AH - 8) * NMS_WORDS; i += 256) {
+    const int r = 4 + i / NMS_WORDS, g = i % NMS_WORDS;
+    const uint32_t x = sM1[r][g], l = g > 0 ? sM1[r][g - 1] : 0u, rr = g < NMS_WORDS - 1 ? sM1[r][g + 1] : 0u;
+    uint32_t d = x;
+#pragma unroll
+    for (int k = 1; k <= 4; ++k) d |= (x << k) | (l >> (32 - k)) | (x >> k) | (rr << (32 - k));
+    sRow[r][g] = d;
+  }
+  __syncthreads();
+  for (int i = tid; i < (NMS_AH - 16) * NMS_WORDS; i += 256) {
+    const int r = 8 + i / NMS_WORDS, g = i % NMS_WORDS;
+    uint32_t d = 0u;
+#pragma unroll
+    for (int dr = -4; dr <= 4; ++dr) d |= sRow[r + dr][g];
+    sSupp[r][g] = d;
+  }
+  __syncthreads();
+  // ---- pool 3, row pass on s' = supp ? 0 : s (-inf outside the image): rows [8, AH-8) x cols [12, 76)
+  for (int i = tid; i < (NMS_AH - 16) * 8; i += 256) {
+    const int r = 8 + i % (NMS_AH - 16), c = 12 + (i / (NMS_AH - 16)) * 8;
+    // supp bits of columns c-4 .. c+11 = bit positions (c - 8) .. (c + 7) of the row's 96-bit string
+    const int b0 = c - 8, g = b0 >> 5;
+    const uint64_t two = (uint64_t)sSupp[r][g] | ((uint64_t)(g + 1 < NMS_WORDS ? sSupp[r][g + 1] : 0u) << 32);
+    const uint32_t sb = (uint32_t)(two >> (b0 & 31));
+    float v[16], o[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float sv = sS[r][c - 4 + j];   // -inf outside the image already
+      v[j] = ((sb >> j) & 1u) ? (inside(r, c - 4 + j) ? 0.f : NEG) : sv;
+    }
+    run9(v, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sT[r][c + j] = o[j];
+  }
+  __syncthreads();
+  // ---- pool 3, column pass + output: warp task = (8-row block of the tile, 32-column half)
+  {
+    const int rb = warp >> 1, h = warp & 1;
+    const int r = 12 + rb * 8, c = 12 + 32 * h + lane;
+    float v[16], o[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = sT[r - 4 + j][c];
+    run9(v, o);
+    const int bit = c - 4, g = bit >> 5, sh = bit & 31;
+    const int x = ax0 + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int y = ay0 + r + j;
+      if (y >= H || x >= W) continue;
+      const float sv = sS[r + j][c];
+      const bool supp = (sSupp[r + j][g] >> sh) & 1u;
+      const bool m1 = (sM1[r + j][g] >> sh) & 1u;
+      const float s2 = supp ? 0.f : sv;
+      const bool mx = m1 || (!supp && s2 == o[j]);
+      const float val = mx ? sv : 0.f;
+      dst[(size_t)y * W + x] = val;
+      if (cand && val >= threshold) {
+        const int pos = atomicAdd(cand_count + blockIdx.z, 1);
+        if (pos < cand_cap)
+          cand[(size_t)blockIdx.z * cand_cap + pos] =
+              ((u64)f2ord(val) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(x * H + y));
+      }
+    }
+  }
 }
 
 int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, int B, float threshold, u64* d_cand,
                int* d_cand_count, int cand_cap) {
   if (d_cand) HFB_CUDA(ctx, cudaMemsetAsync(d_cand_count, 0, sizeof(int) * B, ctx->stream));
   dim3 grid(ceil_div(W, NMS_TW), ceil_div(H, NMS_TH), B);
-  constexpr size_t smem = 3 * sizeof(float) * NMS_AH * NMS_P + NMS_AH * NMS_AW + NMS_TH * NMS_TW;
+  constexpr size_t smem = 2 * sizeof(float) * NMS_AH * NMS_P + 3 * sizeof(uint32_t) * NMS_AH * NMS_WORDS;
   static bool configured = false;
   if (!configured) {
     HFB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
