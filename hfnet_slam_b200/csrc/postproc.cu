@@ -41,7 +41,7 @@ __device__ __forceinline__ void run9(const float (&v)[16], float (&o)[8]) {
 
 // With cand != null the kernel also performs the reference's threshold scan (HFNetRTModel.cc:150-168) on its own
 // output: every surviving pixel with score >= threshold is appended as a (score, scan index) key.
-__global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H,
+__global__ void __launch_bounds__(256, 5) nms_kernel(const float* __restrict__ scores, float* __restrict__ out, int H,
                                                   int W, float threshold, u64* __restrict__ cand,
                                                   int* __restrict__ cand_count, int cand_cap) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
   }
   __syncthreads();
   // ---- pool 1, row pass: sT[r][c] = max(sS[r][c-4..c+4]) on rows [0, AH) x cols [4, 84)
+#pragma unroll 2
   for (int i = tid; i < NMS_AH * 10; i += 256) {
     const int r = i % NMS_AH, c = 4 + (i / NMS_AH) * 8;
     float v[16], o[8];
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ scor
   }
   __syncthreads();
   // ---- pool 3, row pass on s' = supp ? 0 : s (-inf outside the image): rows [8, AH-8) x cols [12, 76)
+#pragma unroll 2
   for (int i = tid; i < (NMS_AH - 16) * 8; i += 256) {
     const int r = 8 + i % (NMS_AH - 16), c = 12 + (i / (NMS_AH - 16)) * 8;
     // supp bits of columns c-4 .. c+11 = bit positions (c - 8) .. (c + 7) of the row's 96-bit string
