@@ -18,6 +18,7 @@
 //     stream through a ring otherwise; input halo tiles are prefetched NX-1 tiles ahead with cp.async.
 // HBM traffic per block = input (with halo) + output.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -38,6 +39,7 @@ struct CplGeom {
   int nk16;          // K steps of the expand MMA
   int cout_pad;      // Cout rounded up to 16 (project N)
   int NS, NX, ND2;   // weight ring slots (== n_chunks: resident), input tile buffers, project accumulators
+  int rem_vp;        // last chunk holds <= 64 channels: they are replicated every rem_vp (32 | 64) lanes, 0 = no
   uint32_t we_bytes, wp_bytes, blob_bytes;
   uint32_t x_buf_bytes, a2_buf_bytes;
   uint32_t off_X, off_A2, off_W, off_bars, smem_bytes;
@@ -83,6 +85,12 @@ __device__ __forceinline__ float fmah_sel(uint32_t x, int xh, uint32_t w, int wh
   return wh ? fmah<0, 1>(x, w, acc) : fmah<0, 0>(x, w, acc);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
 }
@@ -126,7 +134,6 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
   constexpr int MG = NPIX > 64 ? 2 : 1;    // 64-pixel groups of the project A operand
   constexpr int NRO = TH / 4;              // output rows per warp
   constexpr int NRI = (NRO - 1) * S + 3;   // input rows per warp
-  constexpr int NPK = (IW + 1) / 2;        // packed fp16 pairs per input row
   static_assert(RP <= 256 && NPIX <= 128 && TH % 4 == 0, "tile shape");
 
   extern __shared__ uint8_t smem_raw[];
@@ -399,80 +406,120 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
 #pragma unroll
         for (int i = 0; i < 5; ++i) wv[i] = dwp[i * 128];
         const float bias = __uint_as_float(dwp[5 * 128]);
-        const bool active = j * 128 + lg * 32 < g.Cexp;   // warp-uniform: this lane group holds real channels
+        // A short last chunk (<= 64 channels) is replicated across the lane groups by the weight image: every replica
+        // sees the same channels and takes a column slice of the tile, so the chunk costs 1/4 or 1/2 of a full one.
+        const bool rem = g.rem_vp != 0 && j == n_chunks - 1;
+        const bool active = rem || j * 128 + lg * 32 < g.Cexp;   // warp-uniform: this lane group holds real channels
         tc::mbar_wait(&bar_e[c & 1], (uint32_t)((c >> 1) & 1));
         if (warp == 0) { CPL_STAMP(0, c, 1); }
         tc::fence_after_sync();
-        uint32_t hrow[NRI][NPK];
-        if (active) {
-          // rows come out of TMEM in groups of at most 3 (register pressure: 19 fp32 words per row before packing)
-          const uint32_t tbase = tmem_base + tm_lane + (uint32_t)((c & 1) * RP) + (uint32_t)(rg * NRO * S * IW);
+        const uint32_t tbase = tmem_base + tm_lane + (uint32_t)((c & 1) * RP) + (uint32_t)(rg * NRO * S * IW);
+        uint8_t* a2buf = sA2 + (size_t)(c & 1) * g.a2_buf_bytes;
+
+        // NOUT output columns starting at x0 of this warp's NRO rows, channel chl of the chunk (A2 position)
+        auto dw_cols = [&](auto nout_c, int x0, int chl) {
+          constexpr int NOUT = decltype(nout_c)::value;
+          constexpr int NIN = (NOUT - 1) * S + 3;          // input columns, starting at x0 * S
+          constexpr int NPKN = (NIN + 1) / 2;
+          constexpr int NV = NIN >= 16 ? NIN + 1 : 16;      // staging words per row (loads come in x16 / x8 pieces)
+          uint32_t hrow[NRI][NPKN];
+          const uint32_t tcol = tbase + (uint32_t)(x0 * S);
+          // rows come out of TMEM in groups of at most 3 (register pressure: fp32 words before packing)
           constexpr int GRP = NRI <= 3 ? NRI : 2;
 #pragma unroll
           for (int i0 = 0; i0 < NRI; i0 += GRP) {
-            uint32_t v[GRP][IW + 1];
+            uint32_t v[GRP][NV];
 #pragma unroll
             for (int i = 0; i < GRP; ++i) {
               if (i0 + i < NRI) {
-                uint32_t(&vr)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[i][0]);
-                tc::tmem_ld16(tbase + (uint32_t)((i0 + i) * IW), vr);
-                if constexpr (S == 1) tmem_ld2(tbase + (uint32_t)((i0 + i) * IW + 16), v[i][16], v[i][17]);
-                else tmem_ld1(tbase + (uint32_t)((i0 + i) * IW + 16), v[i][16]);
+                const uint32_t ta = tcol + (uint32_t)((i0 + i) * IW);
+                if constexpr (NIN >= 16) {
+                  uint32_t(&vr)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[i][0]);
+                  tc::tmem_ld16(ta, vr);
+                  if constexpr (NIN == 18) tmem_ld2(ta + 16, v[i][16], v[i][17]);
+                  else tmem_ld1(ta + 16, v[i][16]);
+                } else {
+                  uint32_t(&vr)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[i][0]);
+                  tmem_ld8(ta, vr);
+                  if constexpr (NIN == 10) tmem_ld2(ta + 8, v[i][8], v[i][9]);
+                  else if constexpr (NIN == 9) tmem_ld1(ta + 8, v[i][8]);
+                }
               }
             }
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < GRP; ++i) {
               if (i0 + i < NRI) {
-                if constexpr (S == 2) v[i][17] = 0u;
 #pragma unroll
-                for (int k = 0; k < NPK; ++k)
-                  hrow[i0 + i][k] = relu6_pack(__uint_as_float(v[i][2 * k]), __uint_as_float(v[i][2 * k + 1]));
+                for (int k = 0; k < NPKN; ++k) {
+                  const float lo = __uint_as_float(v[i][2 * k]);
+                  const float hi = 2 * k + 1 < NIN ? __uint_as_float(v[i][2 * k + 1]) : 0.f;
+                  hrow[i0 + i][k] = relu6_pack(lo, hi);
+                }
               }
             }
           }
-        }
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&bar_d1[c & 1]);
-        if (warp == 0) { CPL_STAMP(0, c, 2); }
-        if (c >= 2) tc::mbar_wait(&bar_p[c & 1], (uint32_t)(((c - 2) >> 1) & 1));   // project(c-2) has read A2[c & 1]
-        if (warp == 0) { CPL_STAMP(0, c, 3); }
-        if (active) {
-          const int kg = lg * 4 + (lane >> 3), jj = lane & 7;
-          uint8_t* a2 = sA2 + (size_t)(c & 1) * g.a2_buf_bytes + (size_t)kg * (MG * 1024) + jj * 128;
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bar_d1[c & 1]);
+          if (warp == 0) { CPL_STAMP(0, c, 2); }
+          if (c >= 2) tc::mbar_wait(&bar_p[c & 1], (uint32_t)(((c - 2) >> 1) & 1));   // project(c-2) has read A2[c & 1]
+          if (warp == 0) { CPL_STAMP(0, c, 3); }
+          const int kg = chl >> 3, jj = chl & 7;
+          uint8_t* a2 = a2buf + (size_t)kg * (MG * 1024) + jj * 128;
 #pragma unroll
           for (int ro = 0; ro < NRO; ++ro) {
-            float acc[TW];
+            float acc[NOUT];
 #pragma unroll
-            for (int x = 0; x < TW; ++x) acc[x] = bias;
+            for (int x = 0; x < NOUT; ++x) acc[x] = bias;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
               const uint32_t* hr = hrow[ro * S + ky];
 #pragma unroll
-              for (int x = 0; x < TW; ++x) {
+              for (int x = 0; x < NOUT; ++x) {
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {   // tap (ky, kx) reads input column x * S + kx
+                for (int kx = 0; kx < 3; ++kx) {   // tap (ky, kx) reads input column x * S + kx (relative to x0 * S)
                   const int ix = x * S + kx, tap = ky * 3 + kx;
                   acc[x] = fmah_sel(hr[ix >> 1], ix & 1, wv[tap >> 1], tap & 1, acc[x]);
                 }
               }
             }
-            // output row r = rg * NRO + ro of the tile: pixels p = r * TW + x, 16-byte chunk (p % 64) / 8 of atom p / 64
-            const int r = rg * NRO + ro;
-            const int p0 = r * TW;
+            // output row r = rg * NRO + ro of the tile: pixels p = r * TW + x0 + x live in atom p / 64, 16-byte chunk
+            // (p % 64) / 8 (swizzled with the channel's line), 2 bytes per pixel
+            const int p0 = (rg * NRO + ro) * TW + x0;
             uint8_t* arow = a2 + (size_t)(p0 >> 6) * 1024;
+            const int pb = (p0 & 63) * 2;
+            if constexpr (NOUT >= 8) {
 #pragma unroll
-            for (int h = 0; h < TW / 8; ++h) {
-              uint4 o;
-              o.x = relu6_pack(acc[8 * h + 0], acc[8 * h + 1]);
-              o.y = relu6_pack(acc[8 * h + 2], acc[8 * h + 3]);
-              o.z = relu6_pack(acc[8 * h + 4], acc[8 * h + 5]);
-              o.w = relu6_pack(acc[8 * h + 6], acc[8 * h + 7]);
-              const int chunk = ((p0 & 63) >> 3) + h;
-              *reinterpret_cast<uint4*>(arow + ((chunk ^ jj) << 4)) = o;
+              for (int h = 0; h < NOUT / 8; ++h) {
+                uint4 o;
+                o.x = relu6_pack(acc[8 * h + 0], acc[8 * h + 1]);
+                o.y = relu6_pack(acc[8 * h + 2], acc[8 * h + 3]);
+                o.z = relu6_pack(acc[8 * h + 4], acc[8 * h + 5]);
+                o.w = relu6_pack(acc[8 * h + 6], acc[8 * h + 7]);
+                *reinterpret_cast<uint4*>(arow + ((((pb >> 4) + h) ^ jj) << 4)) = o;
+              }
+            } else if constexpr (NOUT == 4) {
+              uint2 o;
+              o.x = relu6_pack(acc[0], acc[1]);
+              o.y = relu6_pack(acc[2], acc[3]);
+              *reinterpret_cast<uint2*>(arow + (((pb >> 4) ^ jj) << 4) + (pb & 15)) = o;
+            } else {
+              *reinterpret_cast<uint32_t*>(arow + (((pb >> 4) ^ jj) << 4) + (pb & 15)) = relu6_pack(acc[0], acc[1]);
             }
           }
+        };
+        if (!active) {
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bar_d1[c & 1]);
+          if (c >= 2) tc::mbar_wait(&bar_p[c & 1], (uint32_t)(((c - 2) >> 1) & 1));
+        } else if (!rem) {
+          dw_cols(std::integral_constant<int, TW>{}, 0, lg * 32 + lane);
+        } else if (g.rem_vp == 32) {
+          dw_cols(std::integral_constant<int, TW / 4>{}, lg * (TW / 4), lane);
+        } else {
+          dw_cols(std::integral_constant<int, TW / 2>{}, (lg >> 1) * (TW / 2), (lg & 1) * 32 + lane);
         }
         if (warp == 0) { CPL_STAMP(0, c, 4); }
         tc::fence_proxy_async();
@@ -500,9 +547,10 @@ __global__ void cpl_pack_kernel(CplGeom g, const __half* __restrict__ we, int we
     const int j = (int)(i / per_chunk);
     long long e = i - (long long)j * per_chunk;
     uint8_t* base = blob + (size_t)j * g.blob_bytes;
+    const bool repl = g.rem_vp != 0 && j == g.n_chunks - 1;   // lane l of the short last chunk holds channel l % rem_vp
     if (e < 128LL * K) {
       const int r = (int)(e / K), k = (int)(e % K);
-      const int ch = j * 128 + r;
+      const int ch = repl ? j * 128 + (r % g.rem_vp) : j * 128 + r;
       __half v = __float2half_rn(0.f);
       if (ch < g.Cexp) {
         if (k < g.Cin) v = we[(size_t)ch * we_ld + k];
@@ -532,7 +580,7 @@ __global__ void cpl_pack_kernel(CplGeom g, const __half* __restrict__ we, int we
     }
     e -= (long long)g.cout_pad * 128;
     const int word = (int)(e / 128), l = (int)(e % 128);
-    const int ch = j * 128 + l;
+    const int ch = repl ? j * 128 + (l % g.rem_vp) : j * 128 + l;
     uint32_t v = 0;
     if (ch < g.Cexp) {
       if (word < 5) {
@@ -598,6 +646,11 @@ int cpl_plan(hfb_ctx* ctx, CplPlan& cp, const BlockW& bw, const __half* in, int 
   g.pad_t = pad_t; g.pad_l = pad_l;
   g.residual = bw.residual ? 1 : 0;
   g.n_chunks = (bw.cexp + 127) / 128;
+  {
+    const int valid = bw.cexp - 128 * (g.n_chunks - 1);
+    static const bool no_rep = getenv("HFB_CPL_NOREP") != nullptr;   // experiments: plain (unreplicated) last chunk
+    g.rem_vp = no_rep ? 0 : (valid <= 32 ? 32 : (valid <= 64 ? 64 : 0));
+  }
   g.ones_unit = bw.cin / 8;
   g.units = (g.ones_unit + 1 + 1) & ~1;        // K = units * 8, multiple of 16
   if (g.units * 8 > 128) return HFB_ERR_CAPACITY;
