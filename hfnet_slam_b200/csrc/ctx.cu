@@ -595,7 +595,21 @@ extern "C" int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* image
   const size_t per_frame_out = (size_t)ctx->kp_cap * (4 * 4 + HFB_DESC_DIM * 4) + HFB_GLOBAL_DIM * 4 + 64;
   HFB_TRY(ctx->ensure_stage((size_t)n_images * (img_bytes + per_frame_out)));
   uint8_t* hs = reinterpret_cast<uint8_t*>(ctx->h_stage);
-  // inputs: page-locked, densely packed frames are DMA'd in place; anything else goes through the pinned stage
+  // inputs: page-locked, densely packed frames are DMA'd in place (one transfer when the frames are also contiguous
+  // over the batch, e.g. slots of one capture ring); anything else goes through the pinned stage
+  bool one_block = stride == l0.W && images[0] != nullptr;
+  for (int b = 1; b < n_images && one_block; ++b) one_block = images[b] == images[0] + (size_t)b * img_bytes;
+  if (one_block && n_images > 1 && is_pinned(images[0]) && is_pinned(images[0] + (size_t)n_images * img_bytes - 1)) {
+    // adjacent addresses can still belong to separate page-locked allocations: the runtime then rejects the copy
+    // (synchronously, nothing enqueued) and the frames go one by one
+    if (cudaMemcpyAsync(l0.d_img, images[0], (size_t)n_images * img_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+      cudaGetLastError();
+      one_block = false;
+    }
+  } else {
+    one_block = false;
+  }
+  if (!one_block) {
   for (int b = 0; b < n_images; ++b) {
     HFB_REQUIRE(ctx, images[b] != nullptr, "null image");
     if (stride == l0.W && is_pinned(images[b])) {
@@ -607,6 +621,7 @@ extern "C" int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* image
       HFB_CUDA(ctx, cudaMemcpyAsync(l0.d_img + (size_t)b * img_bytes, dst, img_bytes, cudaMemcpyHostToDevice,
                                     ctx->stream));
     }
+  }
   }
   tm.mark("stage_in");
   // Fast path: page-locked outputs that are contiguous over the batch (frame b's rows start at b * kp_cap of one array

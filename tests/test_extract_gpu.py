@@ -105,21 +105,26 @@ def test_batch_equals_single(ctx_euroc, oracle_euroc):
     assert not np.array_equal(two[0]["global_descriptor"], two[1]["global_descriptor"])
 
 
-def test_multilevel_pyramid(native_lib, weights_blob, weights_dict):
-    """4-level EuRoC configuration (Examples/Monocular/EuRoC.yaml:67-80 -> 675 features, 1.2, 4 levels) on a smaller frame."""
-    H, W = 240, 376
+@pytest.mark.parametrize("H,W,n_feat,thr", [(240, 376, 675, 0.01), (512, 512, 850, 0.02)],
+                         ids=["euroc-4level-small", "tumvi-512x512-4level"])
+def test_multilevel_pyramid(native_lib, weights_blob, weights_dict, H, W, n_feat, thr):
+    """4-level configurations: EuRoC (Examples/Monocular/EuRoC.yaml:67-80 -> 675 features, 1.2, 4 levels; smaller frame)
+    and the TUM-VI shape of BASELINE.json configs[4] (Examples/Monocular/TUM-VI.yaml:66-67 -> 850 features -> 274 / 228 /
+    190 / 158 per level, threshold 0.02, 512 x 512)."""
     img = weights.synthetic_image(H, W, seed=2, n_corners=80)
-    budgets = select_ref.features_per_level(675, 4, 1.2)
+    budgets = select_ref.features_per_level(n_feat, 4, 1.2)
+    if n_feat == 850:
+        assert budgets == [274, 228, 190, 158]
     with Context(height=H, width=W, n_levels=4, scale_factor=1.2, max_keypoints=1000, max_batch=1) as ctx:
         ctx.load_weights(weights_blob)
-        out = ctx.extract(img, budgets, 0.01)
+        out = ctx.extract(img, budgets, thr)
         pyr = select_ref.compute_pyramid(img, 4, 1.2)
         per_level = []
         for l, im in enumerate(pyr):
             nms = ctx.debug_tensor("scores_dense_nms", level=l)[0, :, :, 0]
             dm = ctx.debug_tensor("local_descriptor_map", level=l)[0]
             assert nms.shape == (im.shape[0] // 8 * 8, im.shape[1] // 8 * 8)
-            per_level.append(select_ref.local_features(nms, dm, budgets[l], 0.01))
+            per_level.append(select_ref.local_features(nms, dm, budgets[l], thr))
             # dense maps of every level track the fp32 oracle run on the cv2 pyramid
             r = hfnet_ref.forward(im, weights_dict, want_global=False)
             sc = ctx.debug_tensor("scores_dense", level=l)[0, :, :, 0]
