@@ -43,7 +43,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms DURING the timed regions (device loop + host-API loop)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -53,7 +53,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -225,11 +225,12 @@ def main_gpu(args):
         return ms, wall, ctx.launch_count - lc0
 
     warm = max(args.warmup, 3)
-    with ClockSampler(local) as cs:
-        ms_dev, wall_dev, launches = timed(step_dev, args.steps, warm)
-    clocks = cs.summary()
     n_host = max(5, args.steps)
-    ms_host, wall_host, _ = timed(step_host, n_host, 3)
+    with ClockSampler(local) as cs:
+        time.sleep(0.05)                                             # let the sampler start before the first timed step
+        ms_dev, wall_dev, launches = timed(step_dev, args.steps, warm)
+        ms_host, wall_host, _ = timed(step_host, n_host, 3)
+    clocks = cs.summary()
     # sanity inside the bench: the device chain produced real keypoints and matches
     f0 = ctx.fetch_features(0)
     ctx.match_consecutive_dev(B, 0, 0.6)
