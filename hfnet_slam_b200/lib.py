@@ -256,6 +256,8 @@ class Context:
                         response=np.empty((n, cap), np.float32), octave=np.empty((n, cap), np.int32),
                         descriptors=np.empty((n, cap, HFB_DESC_DIM), np.float32),
                         global_descriptor=np.empty((n, HFB_GLOBAL_DIM), np.float32))
+        if pinned and "_feats" in arrs:
+            return arrs["_feats"], arrs          # same page-locked arrays, same struct array: nothing to rebuild
         feats = (hfb_features * n)()
         for b in range(n):
             f = feats[b]
@@ -263,6 +265,8 @@ class Context:
             f.response, f.octave = ptr(arrs["response"][b], _f32p), ptr(arrs["octave"][b], _i32p)
             f.descriptors = ptr(arrs["descriptors"][b], _f32p)
             f.global_descriptor = ptr(arrs["global_descriptor"][b], _f32p) if self.with_global else None
+        if pinned:
+            arrs["_feats"] = feats
         return feats, arrs
 
     @staticmethod
