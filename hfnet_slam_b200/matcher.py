@@ -97,3 +97,53 @@ class Matcher:
         desc = np.concatenate(rows) if rows else np.zeros((0, 256), np.float32)
         return self.ctx.distinctive_descriptors(desc, off)
 
+    def search_for_initialization(self, d1, xy1, oct1, d2, xy2, oct2, prev_matched, nnratio: float = 0.9,
+                                  window: float = 100.0):
+        """Matcher::SearchForInitialization (src/Matcher.cc:486-559): the distances come from the windowed kernel (top-4
+        level-0 candidates of every level-0 keypoint of frame 1 around its previously matched position), the sequential
+        claiming / take-over bookkeeping of the reference's loop is replayed here.  A keypoint whose four nearest
+        candidates are all already claimed by better matches is re-scanned exactly over its whole window (rare).
+        Returns (matches12, n_matches, updated prev_matched)."""
+        d1, d2 = np.asarray(d1, np.float32), np.asarray(d2, np.float32)
+        xy1, xy2 = np.asarray(xy1, np.float32), np.asarray(xy2, np.float32)
+        oct1, oct2 = np.asarray(oct1, np.int32), np.asarray(oct2, np.int32)
+        prev = np.asarray(prev_matched, np.float32)
+        n1, n2 = d1.shape[0], d2.shape[0]
+        fmax = np.finfo(np.float32).max
+        m12 = np.full(n1, -1, np.int32)
+        m21 = np.full(n2, -1, np.int32)
+        matched = np.full(n2, fmax, np.float32)
+        q = np.flatnonzero(oct1 == 0)
+        n = 0
+        if len(q) and n2:
+            zeros = np.zeros(len(q), np.int32)
+            idx, dist, _ = self.ctx.match_projection(d1[q], prev[q], np.full(len(q), window, np.float32), zeros, zeros,
+                                                     d2, xy2, oct2)
+            r = np.float32(window)
+            for row, i1 in enumerate(q):
+                cand = [(dist[row, k], int(idx[row, k])) for k in range(idx.shape[1]) if idx[row, k] >= 0]
+                free = [(dd, i2) for dd, i2 in cand if not matched[i2] <= dd]
+                if len(free) < 2 and len(cand) == idx.shape[1]:
+                    # the list may be truncated: exact scan of the whole window for this keypoint
+                    u, v = prev[i1]
+                    ok = (np.abs(xy2[:, 0] - u) < r) & (np.abs(xy2[:, 1] - v) < r) & (oct2 == 0)
+                    ii = np.flatnonzero(ok)
+                    dd = np.sqrt(((d2[ii] - d1[i1]) ** 2).sum(1, dtype=np.float32)).astype(np.float32)
+                    free = sorted((float(x), int(i)) for x, i in zip(dd, ii) if not matched[i] <= x)
+                if not free:
+                    continue
+                best, bidx = free[0]
+                best2 = free[1][0] if len(free) > 1 else fmax
+                if best <= np.float32(TH_LOW) and best < np.float32(best2) * np.float32(nnratio):
+                    if m21[bidx] >= 0:
+                        m12[m21[bidx]] = -1
+                        n -= 1
+                    m12[i1] = bidx
+                    m21[bidx] = i1
+                    matched[bidx] = best
+                    n += 1
+        pm = prev.copy()
+        hit = m12 >= 0
+        pm[hit] = xy2[m12[hit]]
+        return m12, n, pm
+

@@ -119,3 +119,46 @@ def accept_projection(bd, bl, sd, sl, ratio: float, th_high: float = float(TH_HI
     ok = bd <= np.float32(th_high)
     reject = (bl == sl) & (bd > np.float32(ratio) * sd)
     return ok & ~reject
+
+
+def search_for_initialization(d1: np.ndarray, xy1: np.ndarray, oct1: np.ndarray, d2: np.ndarray, xy2: np.ndarray,
+                              oct2: np.ndarray, prev_matched: np.ndarray, nnratio: float = 0.9, window: float = 100.0):
+    """Matcher::SearchForInitialization (src/Matcher.cc:486-559), literal: level-0 keypoints of frame 1 in order, window
+    search around ``prev_matched`` (Frame::GetFeaturesInArea with minLevel = maxLevel = 0, src/Frame.cc:659-725: the grid
+    only pre-filters ``|dx| < r and |dy| < r``), candidates whose recorded match distance is <= the new distance are
+    skipped, best <= TH_LOW and best < nnratio * second, a claimed feature is taken over by the better match.
+    Returns (matches12 int32[N1], n_matches, updated prev_matched).  Candidates are visited in ascending index here, by
+    grid cell in the reference: only exact fp32 distance ties could tell the difference."""
+    n1, n2 = d1.shape[0], d2.shape[0]
+    fmax = np.finfo(np.float32).max
+    m12 = np.full(n1, -1, np.int32)
+    m21 = np.full(n2, -1, np.int32)
+    matched_dist = np.full(n2, fmax, np.float32)
+    n = 0
+    r = np.float32(window)
+    for i1 in range(n1):
+        if oct1[i1] > 0:
+            continue
+        u, v = prev_matched[i1]
+        ok = (np.abs(xy2[:, 0] - u) < r) & (np.abs(xy2[:, 1] - v) < r) & (oct2 == 0)
+        best, best2, bidx = fmax, fmax, -1
+        for i2 in np.flatnonzero(ok):
+            dist = descriptor_distance(d1[i1], d2[i2])
+            if matched_dist[i2] <= dist:
+                continue
+            if dist < best:
+                best2, best, bidx = best, dist, int(i2)
+            elif dist < best2:
+                best2 = dist
+        if best <= TH_LOW and best < np.float32(best2) * np.float32(nnratio):
+            if m21[bidx] >= 0:
+                m12[m21[bidx]] = -1
+                n -= 1
+            m12[i1] = bidx
+            m21[bidx] = i1
+            matched_dist[bidx] = best
+            n += 1
+    pm = np.array(prev_matched, np.float32, copy=True)
+    hit = m12 >= 0
+    pm[hit] = xy2[m12[hit]]
+    return m12, n, pm

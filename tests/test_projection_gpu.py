@@ -96,3 +96,36 @@ def test_projection_empty_and_no_window(small_ctx):
     idx2, _, _ = small_ctx.match_projection(Q, uv, rad * 100, np.zeros(50, np.int32), -np.ones(50, np.int32), F, fxy, flev)
     D = np.sqrt(((Q[:, None, :].astype(np.float64) - F[None].astype(np.float64)) ** 2).sum(-1))
     assert np.array_equal(idx2[:, 0], D.argmin(1))
+
+
+@pytest.mark.parametrize("seed,shift", [(0, 6.0), (1, 25.0)])
+def test_search_for_initialization_matches_oracle(small_ctx, seed, shift):
+    """Matcher::SearchForInitialization (src/Matcher.cc:486-559): two frames of the same scene, the second shifted and
+    jittered; level-0 keypoints only, window 100, nnratio 0.9; matches12, count and updated vbPrevMatched identical."""
+    rng = np.random.default_rng(seed)
+    n1 = 700
+    d1 = rng.normal(size=(n1, 256)).astype(np.float32)
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    xy1 = np.stack([rng.uniform(0, 752, n1), rng.uniform(0, 480, n1)], 1).astype(np.float32)
+    oct1 = (rng.uniform(size=n1) < 0.25).astype(np.int32) * rng.integers(1, 4, n1).astype(np.int32)
+    keep = rng.uniform(size=n1) < 0.8                     # 80 % of the keypoints reappear in frame 2 ...
+    d2 = d1[keep] + 0.02 * rng.normal(size=(keep.sum(), 256)).astype(np.float32)
+    xy2 = xy1[keep] + np.float32(shift) + rng.normal(0, 1.5, (keep.sum(), 2)).astype(np.float32)
+    oct2 = oct1[keep]
+    extra = 250                                           # ... next to unrelated ones, some of them near-duplicates
+    de = rng.normal(size=(extra, 256)).astype(np.float32)
+    de[:60] = d2[:60] + 0.025 * rng.normal(size=(60, 256)).astype(np.float32)
+    d2 = np.concatenate([d2, de]).astype(np.float32)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    xe = np.stack([rng.uniform(0, 752, extra), rng.uniform(0, 480, extra)], 1).astype(np.float32)
+    xe[:60] = xy2[:60] + rng.normal(0, 8.0, (60, 2)).astype(np.float32)
+    xy2 = np.concatenate([xy2, xe]).astype(np.float32)
+    oct2 = np.concatenate([oct2, np.zeros(extra, np.int32)])
+    prev = xy1.copy()
+    m = Matcher(small_ctx)
+    got, n_got, pm_got = m.search_for_initialization(d1, xy1, oct1, d2, xy2, oct2, prev, 0.9, 100.0)
+    ref, n_ref, pm_ref = match_ref.search_for_initialization(d1, xy1, oct1, d2, xy2, oct2, prev, 0.9, 100.0)
+    assert n_ref > 200, "the scene should produce a few hundred initial matches"
+    assert np.array_equal(got, ref) and n_got == n_ref
+    assert np.array_equal(pm_got, pm_ref)
+    assert (got[oct1 > 0] == -1).all()
