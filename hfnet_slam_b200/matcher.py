@@ -147,3 +147,53 @@ class Matcher:
         pm[hit] = xy2[m12[hit]]
         return m12, n, pm
 
+    def search_by_projection_last_frame(self, Tcw, K, bounds, scale_factors, last_points_w, last_valid, last_octave,
+                                        last_desc, cur_desc, cur_xy, cur_octave, cur_occupied, th: float,
+                                        th_high: float = TH_HIGH):
+        """Matcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=true) (src/Matcher.cc:1574-1650): projection of
+        the last frame's map points with the current pose estimate on the host (a few thousand 3x4 products), windowed
+        distances on the device (top-4 per map point over octaves [oct-1, oct+1]), the reference's sequential claiming
+        replayed here (exact re-scan when all four candidates are already taken).
+        Returns (assigned: last-frame map-point index per current feature or -1, n_matches)."""
+        Tcw = np.asarray(Tcw, np.float32)
+        fx, fy, cx, cy = [np.float32(v) for v in K]
+        mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+        P = np.asarray(last_points_w, np.float32)
+        xc = (P @ Tcw[:, :3].T + Tcw[:, 3]).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            invz = np.float32(1.0) / xc[:, 2]
+            u = fx * xc[:, 0] / xc[:, 2] + cx
+            v = fy * xc[:, 1] / xc[:, 2] + cy
+        lo = np.asarray(last_octave, np.int32)
+        ok = np.asarray(last_valid, bool) & ~(invz < 0) & ~((u < mnx) | (u > mxx) | (v < mny) | (v > mxy))
+        q = np.flatnonzero(ok)
+        cur_desc = np.asarray(cur_desc, np.float32)
+        cur_xy = np.asarray(cur_xy, np.float32)
+        cur_octave = np.asarray(cur_octave, np.int32)
+        occ = np.array(cur_occupied, bool, copy=True)
+        assigned = np.full(cur_desc.shape[0], -1, np.int32)
+        n = 0
+        if len(q) == 0 or cur_desc.shape[0] == 0:
+            return assigned, n
+        rad = (np.float32(th) * np.asarray(scale_factors, np.float32)[lo[q]]).astype(np.float32)
+        uv = np.stack([u[q], v[q]], 1).astype(np.float32)
+        ld = np.asarray(last_desc, np.float32)
+        idx, dist, _ = self.ctx.match_projection(ld[q], uv, rad, lo[q] - 1, lo[q] + 1, cur_desc, cur_xy, cur_octave,
+                                                 occ.astype(np.uint8))
+        for row, i in enumerate(q):
+            cand = [(dist[row, k], int(idx[row, k])) for k in range(idx.shape[1]) if idx[row, k] >= 0]
+            free = [(d, i2) for d, i2 in cand if not occ[i2]]
+            if not free and len(cand) == idx.shape[1]:   # list possibly truncated: exact scan of this window
+                r = rad[row]
+                w = (np.abs(cur_xy[:, 0] - uv[row, 0]) < r) & (np.abs(cur_xy[:, 1] - uv[row, 1]) < r) & \
+                    (cur_octave >= lo[i] - 1) & (cur_octave <= lo[i] + 1) & ~occ
+                ii = np.flatnonzero(w)
+                dd = np.sqrt(((cur_desc[ii] - ld[i]) ** 2).sum(1, dtype=np.float32)).astype(np.float32)
+                free = sorted((float(x), int(j)) for x, j in zip(dd, ii))
+            if free and free[0][0] <= np.float32(th_high):
+                b = free[0][1]
+                assigned[b] = i
+                occ[b] = True
+                n += 1
+        return assigned, n
+

@@ -162,3 +162,48 @@ def search_for_initialization(d1: np.ndarray, xy1: np.ndarray, oct1: np.ndarray,
     hit = m12 >= 0
     pm[hit] = xy2[m12[hit]]
     return m12, n, pm
+
+
+def search_by_projection_last_frame(Tcw: np.ndarray, K, bounds, scale_factors, last_points_w: np.ndarray,
+                                    last_valid: np.ndarray, last_octave: np.ndarray, last_desc: np.ndarray,
+                                    cur_desc: np.ndarray, cur_xy: np.ndarray, cur_octave: np.ndarray,
+                                    cur_occupied: np.ndarray, th: float, th_high: float = float(TH_HIGH)):
+    """Matcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=true) (src/Matcher.cc:1574-1650), literal, monocular:
+    every map point of the last frame (in order, skipping outliers / empty slots = ``last_valid`` False) is projected
+    with the current pose estimate (Pinhole::project, src/CameraModels/Pinhole.cpp:35-41), searched in the window
+    ``th * scale[octave]`` over octaves [oct-1, oct+1] (Frame::GetFeaturesInArea), skipping features that already carry
+    a map point with observations (``cur_occupied``, extended as this loop assigns), best distance only, accepted iff
+    ``best <= TH_HIGH``.  Tcw: 3x4 [R|t]; K = (fx, fy, cx, cy); bounds = (minX, maxX, minY, maxY).
+    Returns (assigned int32[N_cur]: index of the last-frame map point or -1, n_matches)."""
+    fx, fy, cx, cy = [np.float32(v) for v in K]
+    mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+    R, t = Tcw[:, :3].astype(np.float32), Tcw[:, 3].astype(np.float32)
+    occ = np.array(cur_occupied, bool, copy=True)
+    assigned = np.full(cur_desc.shape[0], -1, np.int32)
+    n = 0
+    for i in range(last_points_w.shape[0]):
+        if not last_valid[i]:
+            continue
+        xc = (R @ last_points_w[i].astype(np.float32) + t).astype(np.float32)
+        invz = np.float32(1.0) / xc[2]
+        if invz < 0:
+            continue
+        u = fx * xc[0] / xc[2] + cx
+        v = fy * xc[1] / xc[2] + cy
+        if u < mnx or u > mxx or v < mny or v > mxy:
+            continue
+        o = int(last_octave[i])
+        r = np.float32(th) * np.float32(scale_factors[o])
+        ok = (np.abs(cur_xy[:, 0] - u) < r) & (np.abs(cur_xy[:, 1] - v) < r) & (cur_octave >= o - 1) & (cur_octave <= o + 1)
+        best, bidx = np.finfo(np.float32).max, -1
+        for i2 in np.flatnonzero(ok):
+            if occ[i2]:
+                continue
+            d = descriptor_distance(last_desc[i], cur_desc[i2])
+            if d < best:
+                best, bidx = d, int(i2)
+        if best <= np.float32(th_high):
+            assigned[bidx] = i
+            occ[bidx] = True          # the assigned map point has observations: later points skip this feature
+            n += 1
+    return assigned, n

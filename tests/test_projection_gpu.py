@@ -129,3 +129,42 @@ def test_search_for_initialization_matches_oracle(small_ctx, seed, shift):
     assert np.array_equal(got, ref) and n_got == n_ref
     assert np.array_equal(pm_got, pm_ref)
     assert (got[oct1 > 0] == -1).all()
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_by_projection_last_frame_matches_oracle(small_ctx, seed):
+    """Matcher::SearchByProjection(CurrentFrame, LastFrame, th, mono) (src/Matcher.cc:1574-1650): synthetic scene, small
+    inter-frame motion, EuRoC intrinsics; the assignment of last-frame map points to current features is identical."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = 458.654, 457.296, 367.215, 248.375
+    W, H = 752, 480
+    n_last = 600
+    Pw = np.stack([rng.uniform(-4, 4, n_last), rng.uniform(-3, 3, n_last), rng.uniform(3, 12, n_last)], 1).astype(np.float32)
+    Pw[:15, 2] = -2.0                                              # behind the camera
+    ang = 0.02
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32)
+    Tcw = np.concatenate([R, np.array([[0.05], [-0.02], [0.1]], np.float32)], 1)
+    last_valid = rng.uniform(size=n_last) < 0.9
+    last_oct = rng.integers(0, 4, n_last).astype(np.int32)
+    ld = rng.normal(size=(n_last, 256)).astype(np.float32)
+    ld /= np.linalg.norm(ld, axis=1, keepdims=True)
+    xc = Pw @ Tcw[:, :3].T + Tcw[:, 3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        uv = np.stack([fx * xc[:, 0] / xc[:, 2] + cx, fy * xc[:, 1] / xc[:, 2] + cy], 1).astype(np.float32)
+    vis = rng.uniform(size=n_last) < 0.85
+    cd = ld[vis] + 0.02 * rng.normal(size=(vis.sum(), 256)).astype(np.float32)
+    cxy = uv[vis] + rng.normal(0, 2.0, (vis.sum(), 2)).astype(np.float32)
+    coct = np.clip(last_oct[vis] + rng.integers(-1, 2, vis.sum()), 0, 3).astype(np.int32)
+    extra = 300
+    cd = np.concatenate([cd, rng.normal(size=(extra, 256))]).astype(np.float32)
+    cd /= np.linalg.norm(cd, axis=1, keepdims=True)
+    cxy = np.concatenate([cxy, np.stack([rng.uniform(0, W, extra), rng.uniform(0, H, extra)], 1)]).astype(np.float32)
+    coct = np.concatenate([coct, rng.integers(0, 4, extra)]).astype(np.int32)
+    occupied = rng.uniform(size=cd.shape[0]) < 0.05
+    scale = (1.2 ** np.arange(4)).astype(np.float32)
+    args = (Tcw, (fx, fy, cx, cy), (0.0, float(W), 0.0, float(H)), scale, Pw, last_valid, last_oct, ld, cd, cxy, coct,
+            occupied, 15.0)
+    got, n_got = Matcher(small_ctx).search_by_projection_last_frame(*args)
+    ref, n_ref = match_ref.search_by_projection_last_frame(*args)
+    assert n_ref > 250, "most visible map points should be re-found"
+    assert n_got == n_ref and np.array_equal(got, ref)
