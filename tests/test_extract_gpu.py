@@ -182,7 +182,16 @@ def test_consecutive_match_on_resident_descriptors(ctx_euroc):
         A, Bd = feats[b]["descriptors"], feats[(b - 1) % 2]["descriptors"]
         ia, ib, dist = match_ref.search_by_bow(A, Bd, 0.6)
         got = {(int(i), int(idx[b, i])) for i in np.flatnonzero(idx[b, :len(A)] >= 0)}
-        assert got == set(zip(ia.tolist(), ib.tolist())), f"frame {b}"
+        want = set(zip(ia.tolist(), ib.tolist()))
+        # identical sets, except pairs sitting on the decision boundaries within the fp32 noise of the two distance
+        # evaluations (|dist - TH_LOW| or the gap to the runner-up below 5e-6)
+        for i, j in got ^ want:
+            dm = match_ref.l2_distance_matrix(A[i:i + 1], Bd)[0]
+            dcol = match_ref.l2_distance_matrix(A, Bd[j:j + 1])[:, 0]
+            gap_row = np.partition(dm, 1)[1] - np.partition(dm, 1)[0]
+            gap_col = np.partition(dcol, 1)[1] - np.partition(dcol, 1)[0]
+            assert abs(dm[j] - 0.6) < 5e-6 or gap_row < 5e-6 or gap_col < 5e-6, f"frame {b}: pair {(i, j)} differs"
+        assert len(got ^ want) <= 2, f"frame {b}"
         assert len(got) > 50, "shifted copies of one frame should share many keypoints"
         one_idx, one_val = ctx_euroc.fetch_matches(b, len(A))
         assert np.array_equal(one_idx, idx[b, :len(A)]) and np.array_equal(one_val, val[b, :len(A)])
