@@ -125,3 +125,88 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+class _FakeProjectionCtx:
+    """numpy stand-in for Context.match_projection (top-k in-window candidates, ascending distance): lets the host-side
+    claiming loops of hfnet_slam_b200/matcher.py run without a GPU.  ``k`` smaller than the device's 4 forces the
+    'list exhausted -> exact re-scan' branch."""
+
+    def __init__(self, k=4):
+        self.k = k
+
+    def match_projection(self, Q, q_uv, q_radius, q_min_level, q_max_level, F, f_xy, f_level, f_skip=None):
+        Q, F = np.asarray(Q, np.float32), np.asarray(F, np.float32)
+        nq = Q.shape[0]
+        idx = np.full((nq, self.k), -1, np.int32)
+        dist = np.full((nq, self.k), np.finfo(np.float32).max, np.float32)
+        lvl = np.full((nq, self.k), -1, np.int32)
+        for i in range(nq):
+            ok = (np.abs(f_xy[:, 0] - q_uv[i, 0]) < q_radius[i]) & (np.abs(f_xy[:, 1] - q_uv[i, 1]) < q_radius[i]) & \
+                 (f_level >= q_min_level[i])
+            if q_max_level[i] >= 0:
+                ok &= f_level <= q_max_level[i]
+            if f_skip is not None:
+                ok &= ~np.asarray(f_skip, bool)
+            ii = np.flatnonzero(ok)
+            d = np.sqrt(((F[ii] - Q[i]) ** 2).sum(1, dtype=np.float32)).astype(np.float32)
+            o = np.argsort(d, kind="stable")[:self.k]
+            idx[i, :len(o)], dist[i, :len(o)], lvl[i, :len(o)] = ii[o], d[o], f_level[ii[o]]
+        return idx, dist, lvl
+
+
+def _two_frames(seed):
+    rng = np.random.default_rng(seed)
+    n1 = 300
+    d1 = rng.normal(size=(n1, 256)).astype(np.float32)
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    xy1 = np.stack([rng.uniform(0, 752, n1), rng.uniform(0, 480, n1)], 1).astype(np.float32)
+    oct1 = (rng.uniform(size=n1) < 0.25).astype(np.int32)
+    # every keypoint reappears three times with decreasing similarity: claimed candidates and take-overs are frequent
+    d2 = np.concatenate([d1 + s * rng.normal(size=d1.shape).astype(np.float32) for s in (0.015, 0.02, 0.03)])
+    d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32)
+    xy2 = np.concatenate([xy1 + rng.normal(0, 3.0, xy1.shape).astype(np.float32) for _ in range(3)]).astype(np.float32)
+    oct2 = np.concatenate([oct1] * 3)
+    return d1, xy1, oct1, d2, xy2, oct2
+
+
+@pytest.mark.parametrize("k", [4, 1])
+def test_search_for_initialization_replay_equals_oracle(k):
+    """Host replay of Matcher::SearchForInitialization (src/Matcher.cc:486-559) over top-k candidate lists == the literal
+    restatement, including the exact re-scan when a list is exhausted (k = 1 exercises it constantly)."""
+    from hfnet_slam_b200.matcher import Matcher
+    from oracle import match_ref
+    d1, xy1, oct1, d2, xy2, oct2 = _two_frames(0)
+    got, n_got, pm_got = Matcher(_FakeProjectionCtx(k)).search_for_initialization(d1, xy1, oct1, d2, xy2, oct2, xy1.copy(),
+                                                                                  0.9, 100.0)
+    ref, n_ref, pm_ref = match_ref.search_for_initialization(d1, xy1, oct1, d2, xy2, oct2, xy1.copy(), 0.9, 100.0)
+    assert n_ref > 100
+    assert n_got == n_ref and np.array_equal(got, ref) and np.array_equal(pm_got, pm_ref)
+
+
+@pytest.mark.parametrize("k", [4, 1])
+def test_search_by_projection_last_frame_replay_equals_oracle(k):
+    """Host replay of Matcher::SearchByProjection(CurrentFrame, LastFrame) (src/Matcher.cc:1574-1650) == the restatement."""
+    from hfnet_slam_b200.matcher import Matcher
+    from oracle import match_ref
+    rng = np.random.default_rng(3)
+    fx, fy, cx, cy = 458.654, 457.296, 367.215, 248.375
+    n_last = 250
+    Pw = np.stack([rng.uniform(-4, 4, n_last), rng.uniform(-3, 3, n_last), rng.uniform(3, 12, n_last)], 1).astype(np.float32)
+    Tcw = np.concatenate([np.eye(3, dtype=np.float32), np.array([[0.05], [-0.02], [0.1]], np.float32)], 1)
+    last_valid = rng.uniform(size=n_last) < 0.9
+    last_oct = rng.integers(0, 4, n_last).astype(np.int32)
+    ld = rng.normal(size=(n_last, 256)).astype(np.float32)
+    ld /= np.linalg.norm(ld, axis=1, keepdims=True)
+    xc = Pw @ Tcw[:, :3].T + Tcw[:, 3]
+    uv = np.stack([fx * xc[:, 0] / xc[:, 2] + cx, fy * xc[:, 1] / xc[:, 2] + cy], 1).astype(np.float32)
+    cd = np.concatenate([ld + s * rng.normal(size=ld.shape).astype(np.float32) for s in (0.02, 0.03)])
+    cd = (cd / np.linalg.norm(cd, axis=1, keepdims=True)).astype(np.float32)
+    cxy = np.concatenate([uv + rng.normal(0, 2.0, uv.shape).astype(np.float32) for _ in range(2)]).astype(np.float32)
+    coct = np.concatenate([last_oct, last_oct])
+    occupied = rng.uniform(size=cd.shape[0]) < 0.1
+    scale = (1.2 ** np.arange(4)).astype(np.float32)
+    args = (Tcw, (fx, fy, cx, cy), (0.0, 752.0, 0.0, 480.0), scale, Pw, last_valid, last_oct, ld, cd, cxy, coct, occupied, 15.0)
+    got, n_got = Matcher(_FakeProjectionCtx(k)).search_by_projection_last_frame(*args)
+    ref, n_ref = match_ref.search_by_projection_last_frame(*args)
+    assert n_ref > 100 and n_got == n_ref and np.array_equal(got, ref)
