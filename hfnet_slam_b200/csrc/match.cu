@@ -275,12 +275,14 @@ struct EpiProjTopK {
     const float2* fxy;     // [nf]
     const int* flevel;     // [nf]
     const unsigned char* fskip;  // [nf] or null
+    const float* finv;     // [nf] inverse level sigma^2 of every feature, or null: chi^2 gate (dx^2+dy^2)*finv <= chi2_max
+    float chi2_max;
     ProjRec* rec;          // [n_tiles][nq]
     int nq;
   };
   static __device__ __forceinline__ const float* bias(const Params&) { return nullptr; }
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
-    __shared__ float s_fx[MATCH_BN], s_fy[MATCH_BN], s_hn[MATCH_BN];
+    __shared__ float s_fx[MATCH_BN], s_fy[MATCH_BN], s_hn[MATCH_BN], s_inv[MATCH_BN];
     __shared__ int s_lv[MATCH_BN];
     const int lane = threadIdx.x & 31, et = tr.ewarp * 32 + lane;
     const int ncols = min(g.BN, tr.n_cnt - tr.n0);
@@ -290,6 +292,7 @@ struct EpiProjTopK {
       s_fx[et] = xy.x;
       s_fy[et] = xy.y;
       s_hn[et] = __ldg(p.hnf + j);
+      s_inv[et] = p.finv ? __ldg(p.finv + j) : 0.f;   // 0: the gate below never rejects
       s_lv[et] = (p.fskip && p.fskip[j]) ? -1000000 : __ldg(p.flevel + j);   // skipped features fail every level test
     }
     epi_bar_sync();
@@ -317,8 +320,11 @@ struct EpiProjTopK {
         const int c = c0 + jj;
         if (c >= ncols) break;
         const int lv = s_lv[c];
+        const float ex = win.x - s_fx[c], ey = win.y - s_fy[c];
+        // Matcher::Fuse's reprojection gate (Matcher.cc:1180-1188): skip iff e2 * invSigma2 > chi2_max, same expression order
+        const bool gate_ok = !(__fmul_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), s_inv[c]) > p.chi2_max);
         const bool in_win = fabsf(s_fx[c] - win.x) < win.z && fabsf(s_fy[c] - win.y) < win.z && lv >= lev.x &&
-                            (lev.y < 0 || lv <= lev.y) && lv > -1000000;
+                            (lev.y < 0 || lv <= lev.y) && lv > -1000000 && gate_ok;
         if (in_win) proj_insert(best, hq + s_hn[c] - __uint_as_float(r[jj]), tr.n0 + c);
       }
     }
@@ -394,6 +400,15 @@ extern "C" int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, co
                                     const int32_t* q_min_level, const int32_t* q_max_level, const float* F, int32_t nf,
                                     const float* f_xy, const int32_t* f_level, const uint8_t* f_skip, int32_t* cand_idx,
                                     float* cand_dist, int32_t* cand_level) {
+  return hfb_match_projection_gated(ctx, Q, nq, q_uv, q_radius, q_min_level, q_max_level, F, nf, f_xy, f_level, f_skip,
+                                    nullptr, 0.f, cand_idx, cand_dist, cand_level);
+}
+
+extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t nq, const float* q_uv,
+                                          const float* q_radius, const int32_t* q_min_level, const int32_t* q_max_level,
+                                          const float* F, int32_t nf, const float* f_xy, const int32_t* f_level,
+                                          const uint8_t* f_skip, const float* f_inv_sigma2, float chi2_max,
+                                          int32_t* cand_idx, float* cand_dist, int32_t* cand_level) {
   if (!ctx) return HFB_ERR_INVALID;
   HFB_REQUIRE(ctx, nq >= 0 && nf >= 0, "negative size");
   HFB_REQUIRE(ctx, cand_idx && cand_dist && cand_level, "null output");
@@ -409,7 +424,8 @@ extern "C" int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, co
   // io block: Q | F | uv | r | minl | maxl | fxy | flevel | fskip | cand_idx | cand_dist | cand_level
   const size_t oQ = 0, oF = oQ + al((size_t)nq * 1024), o_uv = oF + al((size_t)nf * 1024), o_r = o_uv + al((size_t)nq * 8),
                o_mn = o_r + al((size_t)nq * 4), o_mx = o_mn + al((size_t)nq * 4), o_fxy = o_mx + al((size_t)nq * 4),
-               o_fl = o_fxy + al((size_t)nf * 8), o_fs = o_fl + al((size_t)nf * 4), o_ci = o_fs + al((size_t)nf),
+               o_fl = o_fxy + al((size_t)nf * 8), o_fs = o_fl + al((size_t)nf * 4), o_fi = o_fs + al((size_t)nf),
+               o_ci = o_fi + al((size_t)nf * 4),
                o_cd = o_ci + al((size_t)nq * PROJ_K * 4), o_cl = o_cd + al((size_t)nq * PROJ_K * 4),
                io_total = o_cl + al((size_t)nq * PROJ_K * 4);
   HFB_TRY(ctx->ensure_io(io_total));
@@ -424,6 +440,7 @@ extern "C" int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, co
   HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fxy, f_xy, (size_t)nf * 8, cudaMemcpyHostToDevice, st));
   HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fl, f_level, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
   if (f_skip) HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fs, f_skip, (size_t)nf, cudaMemcpyHostToDevice, st));
+  if (f_inv_sigma2) HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fi, f_inv_sigma2, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
   // scratch: Q' | F' | hnq | hnf | qwin | qlev | records
   const size_t sQ = 0, sF = sQ + al((size_t)nq * MATCH_K * 2), s_hq = sF + al((size_t)nf * MATCH_K * 2),
                s_hf = s_hq + al((size_t)nq * 4), s_qw = s_hf + al((size_t)nf * 4), s_ql = s_qw + al((size_t)nq * 16),
@@ -464,7 +481,9 @@ extern "C" int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, co
     configured = true;
   }
   EpiProjTopK::Params ep{hnq, hnf, qwin, qlev, reinterpret_cast<const float2*>(io + o_fxy),
-                         reinterpret_cast<const int*>(io + o_fl), f_skip ? io + o_fs : nullptr, rec, nq};
+                         reinterpret_cast<const int*>(io + o_fl), f_skip ? io + o_fs : nullptr,
+                         f_inv_sigma2 ? reinterpret_cast<const float*>(io + o_fi) : nullptr,
+                         f_inv_sigma2 ? chi2_max : 3.402823466e38f, rec, nq};
   gemm_tc_kernel<EpiProjTopK><<<gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(4), smem, st>>>(tmA, tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, "proj_gemm_topk");
   hfb_launch(ctx, proj_finalize_kernel, ceil_div(nq, 8), 256, 0, dQ, dF, rec, n_tiles, nq,

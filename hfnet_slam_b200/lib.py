@@ -90,6 +90,8 @@ SIGNATURES = {
                                       C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "hfb_match_projection": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p, _i32p, _i32p, _f32p, C.c_int32, _f32p,
                                        _i32p, _u8p, _i32p, _f32p, _i32p]),
+    "hfb_match_projection_gated": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p, _i32p, _i32p, _f32p, C.c_int32,
+                                             _f32p, _i32p, _u8p, _f32p, C.c_float, _i32p, _f32p, _i32p]),
     "hfb_match_consecutive_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float]),
     "hfb_fetch_matches": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _f32p, C.c_int32]),
     "hfb_distinctive_descriptors": (C.c_int, [C.c_void_p, _f32p, _i32p, C.c_int32, _i32p, _f32p]),
@@ -331,8 +333,10 @@ class Context:
         self.check(self.lib.hfb_fetch_features(self.handle, image_index, C.byref(feats[0])))
         return self._view(feats[0], arrs, 0, self.with_global)
 
-    def match_projection(self, Q, q_uv, q_radius, q_min_level, q_max_level, F, f_xy, f_level, f_skip=None):
-        """Top-4 in-window candidates per query: (idx [nq,4], dist [nq,4], level [nq,4])."""
+    def match_projection(self, Q, q_uv, q_radius, q_min_level, q_max_level, F, f_xy, f_level, f_skip=None,
+                         f_inv_sigma2=None, chi2_max: float = 0.0):
+        """Top-4 in-window candidates per query: (idx [nq,4], dist [nq,4], level [nq,4]).  With f_inv_sigma2 the
+        candidates also pass Matcher::Fuse's reprojection gate ((du^2 + dv^2) * f_inv_sigma2 <= chi2_max)."""
         q, f = as_f32(Q).reshape(-1, HFB_DESC_DIM), as_f32(F).reshape(-1, HFB_DESC_DIM)
         nq, nf = q.shape[0], f.shape[0]
         uv, rad = as_f32(q_uv).reshape(-1, 2), as_f32(q_radius).reshape(-1)
@@ -344,10 +348,12 @@ class Context:
         idx = np.full((nq, 4), -1, np.int32)
         dist = np.full((nq, 4), np.finfo(np.float32).max, np.float32)
         lvl = np.full((nq, 4), -1, np.int32)
-        self.check(self.lib.hfb_match_projection(self.handle, ptr(q, _f32p), nq, ptr(uv, _f32p), ptr(rad, _f32p),
-                                                 ptr(mn, _i32p), ptr(mx, _i32p), ptr(f, _f32p), nf, ptr(fxy, _f32p),
-                                                 ptr(fl, _i32p), ptr(fs, _u8p) if fs is not None else None,
-                                                 ptr(idx, _i32p), ptr(dist, _f32p), ptr(lvl, _i32p)))
+        fi = as_f32(f_inv_sigma2).reshape(-1) if f_inv_sigma2 is not None else None
+        self.check(self.lib.hfb_match_projection_gated(self.handle, ptr(q, _f32p), nq, ptr(uv, _f32p), ptr(rad, _f32p),
+                                                       ptr(mn, _i32p), ptr(mx, _i32p), ptr(f, _f32p), nf, ptr(fxy, _f32p),
+                                                       ptr(fl, _i32p), ptr(fs, _u8p) if fs is not None else None,
+                                                       ptr(fi, _f32p) if fi is not None else None, float(chi2_max),
+                                                       ptr(idx, _i32p), ptr(dist, _f32p), ptr(lvl, _i32p)))
         return idx, dist, lvl
 
     def match_consecutive_dev(self, n_images: int, mode: int, thr: float):

@@ -197,3 +197,43 @@ class Matcher:
                 n += 1
         return assigned, n
 
+
+
+    def fuse(self, Tcw, Ow, K, bounds, scale_factors, log_scale_factor, mp_pos, mp_normal, mp_min_dist, mp_max_dist,
+             mp_desc, mp_skip, kf_desc, kf_xy, kf_octave, th: float = 3.0, th_low: float = TH_LOW, chi2: float = 5.99):
+        """Matcher::Fuse(pKF, vpMapPoints, th) (src/Matcher.cc:1046-1250), monocular, up to the map bookkeeping: geometry
+        (projection, distance range, viewing angle, PredictScale) on the host, the gated window search on the device (every
+        map point is independent here, so the best in-window candidate is the answer).  Returns (best_idx, best_dist):
+        the keyframe feature each map point would be fused into, or -1."""
+        Tcw = np.asarray(Tcw, np.float32)
+        fx, fy, cx, cy = [np.float32(v) for v in K]
+        mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+        P = np.asarray(mp_pos, np.float32)
+        sf = np.asarray(scale_factors, np.float32)
+        pc = (P @ Tcw[:, :3].T + Tcw[:, 3]).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = fx * pc[:, 0] / pc[:, 2] + cx
+            v = fy * pc[:, 1] / pc[:, 2] + cy
+            PO = (P - np.asarray(Ow, np.float32)).astype(np.float32)
+            d3 = np.sqrt(np.sum(PO * PO, axis=1, dtype=np.float32)).astype(np.float32)
+            ratio = (np.asarray(mp_max_dist, np.float32) / d3).astype(np.float32)
+            lvl = np.ceil(np.log(ratio) / np.float32(log_scale_factor))
+        ok = ~np.asarray(mp_skip, bool) & ~(pc[:, 2] < 0) & (u >= mnx) & (u < mxx) & (v >= mny) & (v < mxy)
+        ok &= ~((d3 < np.asarray(mp_min_dist, np.float32)) | (d3 > np.asarray(mp_max_dist, np.float32)))
+        ok &= ~(np.sum(PO * np.asarray(mp_normal, np.float32), axis=1, dtype=np.float32) < np.float32(0.5) * d3)
+        M = P.shape[0]
+        best_idx = np.full(M, -1, np.int32)
+        best_dist = np.full(M, np.finfo(np.float32).max, np.float32)
+        q = np.flatnonzero(ok)
+        if len(q) == 0 or np.asarray(kf_desc).shape[0] == 0:
+            return best_idx, best_dist
+        lv = np.clip(np.nan_to_num(lvl[q], nan=0.0, posinf=len(sf) - 1, neginf=0.0), 0, len(sf) - 1).astype(np.int32)
+        rad = (np.float32(th) * sf[lv]).astype(np.float32)
+        ko = np.asarray(kf_octave, np.int32)
+        inv_sigma2 = (np.float32(1.0) / (sf * sf)).astype(np.float32)[ko]
+        idx, dist, _ = self.ctx.match_projection(np.asarray(mp_desc, np.float32)[q], np.stack([u[q], v[q]], 1), rad,
+                                                 lv - 1, lv, kf_desc, kf_xy, ko, None, inv_sigma2, chi2)
+        hit = (idx[:, 0] >= 0) & (dist[:, 0] <= np.float32(th_low))
+        best_dist[q] = np.where(idx[:, 0] >= 0, dist[:, 0], best_dist[q])
+        best_idx[q[hit]] = idx[hit, 0]
+        return best_idx, best_dist

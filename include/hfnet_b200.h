@@ -178,6 +178,14 @@ int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, const float* 
                          const int32_t* q_min_level, const int32_t* q_max_level, const float* F, int32_t nf,
                          const float* f_xy, const int32_t* f_level, const uint8_t* f_skip, int32_t* cand_idx,
                          float* cand_dist, int32_t* cand_level);
+/* Same with Matcher::Fuse's reprojection gate (src/Matcher.cc:1160-1190): a candidate is skipped iff
+ * ((u - x)^2 + (v - y)^2) * f_inv_sigma2[candidate] > chi2_max (f_inv_sigma2 = mvInvLevelSigma2 of the feature's octave,
+ * chi2_max = 5.99 mono).  f_inv_sigma2 == NULL: no gate (== hfb_match_projection). */
+int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t nq, const float* q_uv, const float* q_radius,
+                               const int32_t* q_min_level, const int32_t* q_max_level, const float* F, int32_t nf,
+                               const float* f_xy, const int32_t* f_level, const uint8_t* f_skip,
+                               const float* f_inv_sigma2, float chi2_max, int32_t* cand_idx, float* cand_dist,
+                               int32_t* cand_level);
 
 /* Tracking's frame-to-previous-frame descriptor association (the brute-force stage behind
  * Matcher::SearchByBoW / SearchForInitialization call sites, src/Tracking.cc:2030,1796) with the descriptors of the last

@@ -207,3 +207,62 @@ def search_by_projection_last_frame(Tcw: np.ndarray, K, bounds, scale_factors, l
             occ[bidx] = True          # the assigned map point has observations: later points skip this feature
             n += 1
     return assigned, n
+
+
+def fuse(Tcw: np.ndarray, Ow: np.ndarray, K, bounds, scale_factors, log_scale_factor: float, mp_pos: np.ndarray,
+         mp_normal: np.ndarray, mp_min_dist: np.ndarray, mp_max_dist: np.ndarray, mp_desc: np.ndarray,
+         mp_skip: np.ndarray, kf_desc: np.ndarray, kf_xy: np.ndarray, kf_octave: np.ndarray, th: float = 3.0,
+         th_low: float = float(TH_LOW), chi2: float = 5.99):
+    """Matcher::Fuse(pKF, vpMapPoints, th) (src/Matcher.cc:1046-1250), monocular, up to the map bookkeeping: for every map
+    point (``mp_skip`` = null / bad / already in the keyframe) -- positive depth, inside the image, distance within the
+    scale-invariance range, viewing angle below 60 degrees (PO . Pn >= 0.5 dist), predicted level
+    (MapPoint::PredictScale, src/MapPoint.cc:497-514: ceil(log(maxDistance / dist) / logScaleFactor), clamped), window
+    th * scale[level], keyframe features of level [pred-1, pred] that pass the reprojection gate
+    e2 * invLevelSigma2 <= chi2, least descriptor distance, accepted iff <= TH_LOW.
+    Returns (best_idx int32[M] or -1, best_dist f32[M]): the feature each map point would be fused into (the reference
+    then Replace()s or AddObservation()s, which is map data-model code outside the path)."""
+    fx, fy, cx, cy = [np.float32(v) for v in K]
+    mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+    R, t = Tcw[:, :3].astype(np.float32), Tcw[:, 3].astype(np.float32)
+    sf = np.asarray(scale_factors, np.float32)
+    inv_sigma2 = (np.float32(1.0) / (sf * sf)).astype(np.float32)
+    n_levels = len(sf)
+    M = mp_pos.shape[0]
+    best_idx = np.full(M, -1, np.int32)
+    best_dist = np.full(M, np.finfo(np.float32).max, np.float32)
+    for i in range(M):
+        if mp_skip[i]:
+            continue
+        pw = mp_pos[i].astype(np.float32)
+        pc = (R @ pw + t).astype(np.float32)
+        if pc[2] < 0:
+            continue
+        u = fx * pc[0] / pc[2] + cx
+        v = fy * pc[1] / pc[2] + cy
+        if not (mnx <= u < mxx and mny <= v < mxy):           # KeyFrame::IsInImage (src/KeyFrame.cc:812-815)
+            continue
+        PO = (pw - Ow.astype(np.float32)).astype(np.float32)
+        dist3d = np.float32(np.sqrt(np.sum(PO * PO, dtype=np.float32)))
+        if dist3d < mp_min_dist[i] or dist3d > mp_max_dist[i]:
+            continue
+        if np.float32(PO @ mp_normal[i].astype(np.float32)) < np.float32(0.5) * dist3d:
+            continue
+        ratio = np.float32(mp_max_dist[i]) / dist3d
+        lvl = int(np.ceil(np.log(ratio) / np.float32(log_scale_factor)))
+        lvl = min(max(lvl, 0), n_levels - 1)
+        r = np.float32(th) * sf[lvl]
+        ok = (np.abs(kf_xy[:, 0] - u) < r) & (np.abs(kf_xy[:, 1] - v) < r)
+        for j in np.flatnonzero(ok):
+            kl = int(kf_octave[j])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            ex, ey = u - kf_xy[j, 0], v - kf_xy[j, 1]
+            e2 = np.float32(ex * ex + ey * ey)
+            if e2 * inv_sigma2[kl] > np.float32(chi2):
+                continue
+            d = descriptor_distance(mp_desc[i], kf_desc[j])
+            if d < best_dist[i]:
+                best_dist[i], best_idx[i] = d, int(j)
+        if not best_dist[i] <= np.float32(th_low):
+            best_idx[i] = -1
+    return best_idx, best_dist

@@ -210,3 +210,36 @@ def test_search_by_projection_last_frame_replay_equals_oracle(k):
     got, n_got = Matcher(_FakeProjectionCtx(k)).search_by_projection_last_frame(*args)
     ref, n_ref = match_ref.search_by_projection_last_frame(*args)
     assert n_ref > 100 and n_got == n_ref and np.array_equal(got, ref)
+
+
+def test_fuse_host_geometry_equals_oracle():
+    """Host side of Matcher::Fuse (projection, distance range, viewing angle, PredictScale, gate parameters) over the numpy
+    stand-in for the device search == the literal restatement (src/Matcher.cc:1046-1250)."""
+    from hfnet_slam_b200.matcher import Matcher
+    from oracle import match_ref
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from test_projection_gpu import _fuse_scene
+
+    class Ctx(_FakeProjectionCtx):
+        def match_projection(self, Q, q_uv, q_radius, q_min_level, q_max_level, F, f_xy, f_level, f_skip=None,
+                             f_inv_sigma2=None, chi2_max=0.0):
+            Q, F = np.asarray(Q, np.float32), np.asarray(F, np.float32)
+            nq = Q.shape[0]
+            idx = np.full((nq, 4), -1, np.int32)
+            dist = np.full((nq, 4), np.finfo(np.float32).max, np.float32)
+            lvl = np.full((nq, 4), -1, np.int32)
+            for i in range(nq):
+                ex, ey = q_uv[i, 0] - f_xy[:, 0], q_uv[i, 1] - f_xy[:, 1]
+                ok = (np.abs(ex) < q_radius[i]) & (np.abs(ey) < q_radius[i]) & (f_level >= q_min_level[i]) & \
+                     (f_level <= q_max_level[i]) & ~((ex * ex + ey * ey).astype(np.float32) * f_inv_sigma2 > np.float32(chi2_max))
+                ii = np.flatnonzero(ok)
+                d = np.sqrt(((F[ii] - Q[i]) ** 2).sum(1, dtype=np.float32)).astype(np.float32)
+                o = np.argsort(d, kind="stable")[:4]
+                idx[i, :len(o)], dist[i, :len(o)], lvl[i, :len(o)] = ii[o], d[o], f_level[ii[o]]
+            return idx, dist, lvl
+
+    sc = _fuse_scene(0)
+    got_i, _ = Matcher(Ctx()).fuse(**sc)
+    ref_i, _ = match_ref.fuse(**sc)
+    assert (ref_i >= 0).sum() > 40
+    assert np.array_equal(got_i, ref_i)

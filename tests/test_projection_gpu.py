@@ -168,3 +168,52 @@ def test_search_by_projection_last_frame_matches_oracle(small_ctx, seed):
     ref, n_ref = match_ref.search_by_projection_last_frame(*args)
     assert n_ref > 250, "most visible map points should be re-found"
     assert n_got == n_ref and np.array_equal(got, ref)
+
+
+def _fuse_scene(seed):
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = 458.654, 457.296, 367.215, 248.375
+    W, H = 752, 480
+    M = 500
+    Pw = np.stack([rng.uniform(-5, 5, M), rng.uniform(-4, 4, M), rng.uniform(-1, 12, M)], 1).astype(np.float32)
+    ang = -0.03
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32)
+    t = np.array([0.1, 0.05, 0.2], np.float32)
+    Tcw = np.concatenate([R, t[:, None]], 1)
+    Ow = (-R.T @ t).astype(np.float32)
+    scale = (1.2 ** np.arange(4)).astype(np.float32)
+    PO = Pw - Ow
+    d3 = np.linalg.norm(PO, axis=1).astype(np.float32)
+    normal = (PO / d3[:, None] + 0.5 * rng.normal(size=(M, 3))).astype(np.float32)      # some fail the 60 degree test
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    ref_level = rng.integers(0, 4, M)
+    max_d = (d3 * rng.uniform(0.9, 1.2 ** 3, M)).astype(np.float32)                      # some are out of range
+    min_d = (max_d / 1.2 ** 4 * rng.uniform(0.8, 1.3, M)).astype(np.float32)
+    md = rng.normal(size=(M, 256)).astype(np.float32)
+    md /= np.linalg.norm(md, axis=1, keepdims=True)
+    pc = Pw @ R.T + t
+    with np.errstate(divide="ignore", invalid="ignore"):
+        uv = np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], 1).astype(np.float32)
+    uv = np.nan_to_num(uv, nan=-1e4, posinf=1e4, neginf=-1e4)
+    # keyframe features: noisy re-observations (some several pixels off: they meet the chi^2 gate) + clutter
+    kd = np.concatenate([md + 0.02 * rng.normal(size=md.shape), rng.normal(size=(400, 256))]).astype(np.float32)
+    kd /= np.linalg.norm(kd, axis=1, keepdims=True)
+    kxy = np.concatenate([uv + rng.normal(0, 1.6, uv.shape), np.stack([rng.uniform(0, W, 400), rng.uniform(0, H, 400)], 1)])
+    koct = rng.integers(0, 4, len(kd)).astype(np.int32)
+    skip = rng.uniform(size=M) < 0.1
+    return dict(Tcw=Tcw, Ow=Ow, K=(fx, fy, cx, cy), bounds=(0.0, float(W), 0.0, float(H)), scale_factors=scale,
+                log_scale_factor=float(np.log(1.2)), mp_pos=Pw, mp_normal=normal, mp_min_dist=min_d, mp_max_dist=max_d,
+                mp_desc=md, mp_skip=skip, kf_desc=kd, kf_xy=kxy.astype(np.float32), kf_octave=koct)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_fuse_matches_oracle(small_ctx, seed):
+    """Matcher::Fuse(pKF, vpMapPoints, th = 3) (src/Matcher.cc:1046-1250) up to the map bookkeeping: the keyframe feature
+    every map point would be fused into is identical; distances within 2e-6."""
+    sc = _fuse_scene(seed)
+    got_i, got_d = Matcher(small_ctx).fuse(**sc)
+    ref_i, ref_d = match_ref.fuse(**sc)
+    assert (ref_i >= 0).sum() > 40, "the scene should fuse a fair number of points"
+    assert np.array_equal(got_i, ref_i)
+    hit = ref_i >= 0
+    assert np.abs(got_d[hit] - ref_d[hit]).max() <= 2e-6
