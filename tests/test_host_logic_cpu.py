@@ -243,3 +243,36 @@ def test_fuse_host_geometry_equals_oracle():
     ref_i, _ = match_ref.fuse(**sc)
     assert (ref_i >= 0).sum() > 40
     assert np.array_equal(got_i, ref_i)
+
+
+def test_onnx_initialiser_import_round_trip(tmp_path):
+    """hfnet_slam_b200/onnx_import.py: the seeded weights written as a minimal ONNX graph (Conv nodes with OIHW weights +
+    biases in a SHUFFLED-between-branches but topologically valid order, centroids, MatMul weight) come back as exactly the
+    blob tensors they started from; a wrong shape fails loudly."""
+    from hfnet_slam_b200 import onnx_import as oi
+    wd = weights.synthetic(seed=3)
+    exp = oi.expected_convs()
+    c1, blocks = weights.architecture(0.75)
+    convs = []
+    for base, shape, dw in exp:
+        w = wd[base + ".w"]
+        if base == "vlad.memberships":
+            w = w.reshape(1 * shape[1], shape[0])               # [c_global][C] == HWIO-flattened 1x1
+        convs.append((base, oi.to_oihw(w, shape[2], shape[1], dw), wd[base + ".b"]))
+    # heads interleaved with the late backbone layers, as a topological sort of the forked graph may emit them
+    head = [c for c in convs if c[0].startswith(("desc.", "det."))]
+    rest = [c for c in convs if not c[0].startswith(("desc.", "det."))]
+    k = next(i for i, c in enumerate(rest) if c[0] == "l9.dw")
+    order = rest[:k] + head[:2] + rest[k:k + 5] + head[2:] + rest[k + 5:]
+    extra = {"vlad/clusters": wd["vlad.clusters"].reshape(1, 1, 1, *wd["vlad.clusters"].shape),
+             "dimensionality_reduction/weights": wd["fc.w"], "dimensionality_reduction/biases": wd["fc.b"]}
+    path = tmp_path / "synthetic_hfnet.onnx"
+    oi.write_model(path, order, extra)
+    got = oi.convert(path)
+    for name, _ in weights.tensor_specs():
+        assert np.array_equal(got[name], wd[name]), name
+    assert weights.pack(got) == weights.pack(wd)
+    # a truncated graph (one Conv missing) is an error, not a silent mis-assignment
+    oi.write_model(path, [c for c in order if c[0] != "l10.project"], extra)
+    with pytest.raises(ValueError):
+        oi.convert(path)
