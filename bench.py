@@ -301,6 +301,37 @@ def main_gpu(args):
     extra["single_frame"] = {"device_ms": ms1_dev / 20, "host_api_ms": ms1_host / 20,
                              "note": "batch of 1 (self-association), same graph path as the batched step"}
 
+    # ---- BASELINE.json configs[0]: 1000 x 1000 brute-force 256-d match through the host-pointer calls (H2D of both sets
+    # and D2H of the match rows inside the timing), single pair and one CreateNewMapPoints-sized batch of 30 pairs
+    if not args.skip_extra:
+        A, Bd = synthetic.descriptor_pair(1000, 1000, n_true=300, seed=0)
+        for _ in range(3):
+            ctx.match_mutual_l2(A, Bd, 0.6)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ctx.match_mutual_l2(A, Bd, 0.6)
+        t_single = (time.perf_counter() - t0) / 20
+        npair = 30
+        A30, B30 = np.concatenate([A] * npair), np.concatenate([Bd] * npair)
+        off = (np.arange(npair) * 1000).astype(np.int32)
+        cnt = np.full(npair, 1000, np.int32)
+        for _ in range(2):
+            ctx.match_batch(0, A30, B30, off, cnt, off, cnt, 0.6)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctx.match_batch(0, A30, B30, off, cnt, off, cnt, 0.6)
+        t_batch = (time.perf_counter() - t0) / 5
+        extra["match_c1"] = {"single_pair_host_ms": 1e3 * t_single, "pairs_per_s_batch30_host": npair / t_batch,
+                             "note": "hfb_match_mutual_l2 / hfb_match_batch with pageable host descriptors (2 MB per pair up)"}
+        if rank == 0 and not args.skip_cpu:
+            import cv2
+            bf = cv2.BFMatcher(cv2.NORM_L2, crossCheck=True)
+            bf.match(A, Bd)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                bf.match(A, Bd)
+            extra["match_c1"]["cpu_bfmatcher_ms"] = 1e3 * (time.perf_counter() - t0) / 3
+
     # ---- the other two parts of the metric ------------------------------------------------------------------
     if not args.skip_extra:
         # loop-DB: 50 k x 4096 fp32 rows sharded by id % world, one all-gather of fixed-size shard records
