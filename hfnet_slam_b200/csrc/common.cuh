@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -102,6 +103,23 @@ struct LevelPlan {
   float *d_memb = nullptr, *d_vlad = nullptr, *d_vladn = nullptr, *d_fc_partial = nullptr;
   int *d_xi = nullptr, *d_yi = nullptr;      // resize tables (from previous level)
   short *d_xa = nullptr, *d_ya = nullptr;
+};
+
+// Opt-in to more than 48 KB of dynamic shared memory, per kernel instantiation (one static object each) and per device
+// (cudaFuncSetAttribute acts on the current device's copy of the function).  Serialised: contexts live on different host
+// threads, and a second thread must not launch before the attribute is in place.
+struct SmemOptIn {
+  std::mutex mu;
+  size_t have[64] = {};
+  template <class Kernel>
+  cudaError_t ensure(Kernel kernel, int device, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& h = have[device & 63];
+    if (bytes <= h) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) h = bytes;
+    return e;
+  }
 };
 
 struct hfb_ctx {

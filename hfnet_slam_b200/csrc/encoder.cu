@@ -490,8 +490,12 @@ struct LevelExec {
   int fc_split, fc_kps;
 };
 
+// Per-context execution plans.  The table is shared by every context of the process and contexts live on different host
+// threads, so look-ups are serialised; std::map nodes do not move, the returned reference stays valid.
 static std::vector<LevelExec>& execs(hfb_ctx* ctx) {
+  static std::mutex mu;
   static std::map<hfb_ctx*, std::vector<LevelExec>> m;
+  std::lock_guard<std::mutex> lk(mu);
   return m[ctx];
 }
 void encoder_forget(hfb_ctx* ctx) {

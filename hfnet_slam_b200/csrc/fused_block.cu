@@ -637,12 +637,8 @@ int fused_block_tiles(const FusedPlan& fp, int B) { return fp.g.tiles_x * fp.g.t
 template <int S, int TH>
 static int fused_launch(hfb_ctx* ctx, const FusedPlan& fp, const FusedGeom& g, const BlockW& bw, const __half* in,
                         __half* out, int grid) {
-  static size_t configured = 0;   // per instantiation
-  if (g.smem_bytes > configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_kernel<S, 512, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)g.smem_bytes));
-    configured = g.smem_bytes;
-  }
+  static SmemOptIn optin;   // per instantiation
+  HFB_CUDA(ctx, optin.ensure(fused_block_kernel<S, 512, TH>, ctx->device, g.smem_bytes));
   hfb_launch(ctx, fused_block_kernel<S, 512, TH>, grid, 512 + 32, g.smem_bytes, fp.tmWE, fp.tmWP, g, in, bw.expand.b, bw.wd,
              bw.bd, bw.project.b, out);
   HFB_CHECK_LAUNCH(ctx, "fused_block");

@@ -742,12 +742,8 @@ int cpl_tiles(const hfb_ctx* ctx, const CplPlan& cp, int stride, int B) {
 
 template <int S, int TH>
 static int cpl_launch(hfb_ctx* ctx, const CplPlan& cp, const CplGeom& g, const BlockW& bw, const __half* in, __half* out) {
-  static size_t configured = 0;   // per instantiation
-  if (g.smem_bytes > configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(fused_block_cpl_kernel<S, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)g.smem_bytes));
-    configured = g.smem_bytes;
-  }
+  static SmemOptIn optin;   // per instantiation
+  HFB_CUDA(ctx, optin.ensure(fused_block_cpl_kernel<S, TH>, ctx->device, g.smem_bytes));
   const int grid = std::min(g.total_tiles, ctx->n_sm);
   hfb_launch(ctx, fused_block_cpl_kernel<S, TH>, grid, CPL_THREADS, g.smem_bytes, cp.tmX[TH == 8 ? 0 : 1], g, in,
              (const uint8_t*)cp.d_blob, bw.project.b, out);

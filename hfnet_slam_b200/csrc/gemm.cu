@@ -1,5 +1,6 @@
 // Tensor-map construction, the store / L2-normalise / softmax+depth_to_space epilogues of the HF-Net encoder GEMMs
 // and their launchers (kernel template in gemm_core.cuh).
+#include <atomic>
 #include "common.cuh"
 #include "gemm_core.cuh"
 
@@ -9,8 +10,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_encodeTiled get_encode(hfb_ctx* ctx) {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn) return fn;
+  static std::atomic<PFN_encodeTiled> cached{nullptr};   // same value from every thread; atomic so the publication is defined
+  if (PFN_encodeTiled fn = cached.load(std::memory_order_acquire)) return fn;
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
@@ -18,8 +19,8 @@ static PFN_encodeTiled get_encode(hfb_ctx* ctx) {
     ctx->set_error("cuTensorMapEncodeTiled entry point not available");
     return nullptr;
   }
-  fn = reinterpret_cast<PFN_encodeTiled>(p);
-  return fn;
+  cached.store(reinterpret_cast<PFN_encodeTiled>(p), std::memory_order_release);
+  return reinterpret_cast<PFN_encodeTiled>(p);
 }
 
 // fp16 [outer][inner] matrix, rows `row_stride_bytes` apart; box = 64 (inner) x box_outer, 128B swizzle, OOB -> 0.
@@ -264,11 +265,8 @@ static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
   g.stages = st < 2 ? 2 : (st > 4 ? 4 : st);
   g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages);
   const size_t smem = gemm_smem_bytes(g.BN, g.stages, epi_bytes);
-  static size_t configured = 0;  // per-instantiation
-  if (smem > configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemOptIn optin;  // per instantiation
+  HFB_CUDA(ctx, optin.ensure(gemm_tc_kernel<Epi>, ctx->device, smem));
   if (g.total_tiles <= 0) return HFB_OK;
   const int grid = gemm_grid(g, ctx->n_sm, smem);
   hfb_launch(ctx, gemm_tc_kernel<Epi>, grid, GEMM_THREADS(Epi::kWarps), smem, tmA, tmB, g, ep);

@@ -106,12 +106,9 @@ static int kfdb_scan(hfb_kfdb* db, const float* d_query, int nq, float* d_scores
   HFB_CUDA(ctx, cudaMemsetAsync(d_best, 0, sizeof(unsigned int) * nq, ctx->stream));
   if (db->size == 0) return HFB_OK;
   const size_t smem = (size_t)KFDB_QB * db->dim * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(kfdb_scan_kernel<KFDB_QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    HFB_CUDA(ctx, cudaFuncSetAttribute(kfdb_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  static SmemOptIn optin_batch, optin_one;
+  HFB_CUDA(ctx, optin_batch.ensure(kfdb_scan_kernel<KFDB_QB>, ctx->device, 200 * 1024));
+  HFB_CUDA(ctx, optin_one.ensure(kfdb_scan_kernel<1>, ctx->device, 200 * 1024));
   for (int q0 = 0; q0 < nq; q0 += KFDB_QB) {
     const int nb = std::min(KFDB_QB, nq - q0);
     // grid: a multiple of the SM count, 8 warps per CTA, at most one warp per row

@@ -216,12 +216,8 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
   g.bias_bytes = 0;
   gemm_finish_geom(g, ceil_div(max_a, 128));
   const size_t smem = gemm_smem_bytes(g.BN, g.stages, 0);
-  static bool configured = false;
-  if (!configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<EpiArgmax>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  HFB_CUDA(ctx, optin.ensure(gemm_tc_kernel<EpiArgmax>, ctx->device, smem));
   EpiArgmax::Params ep{hna, hnb, rowbest, colbest};
   hfb_launch(ctx, gemm_tc_kernel<EpiArgmax>, gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(4), smem, tmA, tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, "match_gemm_argmax");
@@ -475,11 +471,8 @@ extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t 
   g.bias_bytes = 0;
   gemm_finish_geom(g, ceil_div(nq, 128));
   const size_t smem = gemm_smem_bytes(g.BN, g.stages, 0);
-  static bool configured = false;
-  if (!configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<EpiProjTopK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  HFB_CUDA(ctx, optin.ensure(gemm_tc_kernel<EpiProjTopK>, ctx->device, smem));
   EpiProjTopK::Params ep{hnq, hnf, qwin, qlev, reinterpret_cast<const float2*>(io + o_fxy),
                          reinterpret_cast<const int*>(io + o_fl), f_skip ? io + o_fs : nullptr,
                          f_inv_sigma2 ? reinterpret_cast<const float*>(io + o_fi) : nullptr,
@@ -581,11 +574,8 @@ int launch_distinctive(hfb_ctx* ctx, const float* d_desc, const int* d_offsets, 
   if (n_points <= 0) return HFB_OK;
   const int n = std::min(std::max(max_n, 1), DD_MAXN);
   const size_t smem = (size_t)n * n * sizeof(float);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(distinctive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (smem > 48 * 1024) HFB_CUDA(ctx, optin.ensure(distinctive_kernel, ctx->device, smem));
   distinctive_kernel<<<n_points, 256, smem, ctx->stream>>>(d_desc, d_offsets, d_best_idx, d_best_med);
   HFB_CHECK_LAUNCH(ctx, "distinctive");
   return HFB_OK;

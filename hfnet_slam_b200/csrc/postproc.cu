@@ -182,11 +182,8 @@ int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, 
   if (d_cand) HFB_CUDA(ctx, cudaMemsetAsync(d_cand_count, 0, sizeof(int) * B, ctx->stream));
   dim3 grid(ceil_div(W, NMS_TW), ceil_div(H, NMS_TH), B);
   constexpr size_t smem = 2 * sizeof(float) * NMS_AH * NMS_P + 3 * sizeof(uint32_t) * NMS_AH * NMS_WORDS;
-  static bool configured = false;
-  if (!configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  HFB_CUDA(ctx, optin.ensure(nms_kernel, ctx->device, smem));
   hfb_launch(ctx, nms_kernel, grid, 256, smem, d_scores, d_out, H, W, threshold, d_cand, d_cand_count, cand_cap);
   HFB_CHECK_LAUNCH(ctx, "nms");
   return HFB_OK;
@@ -409,11 +406,8 @@ int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const f
   int P = 1;
   while (P < n_keypoints) P <<= 1;
   const size_t smem = (size_t)P * 8;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    HFB_CUDA(ctx, cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (smem > 48 * 1024) HFB_CUDA(ctx, optin.ensure(select_topk_kernel, ctx->device, smem));
   hfb_launch(ctx, select_topk_kernel, B, 1024, smem, d_cand, d_cand_count, cand_cap, n_keypoints, d_sel, d_nsel,
                                                      SELECT_KMAX, d_overflow);
   HFB_CHECK_LAUNCH(ctx, "select_topk");

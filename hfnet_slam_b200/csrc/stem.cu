@@ -340,24 +340,21 @@ int stem_run(hfb_ctx* ctx, const uint8_t* d_img, int img_h, int img_w, int H8, i
   g.total_tiles = g.tiles_x * g.tiles_y * B;
   constexpr size_t smem = sizeof(float) * (ST_PH * ST_PW + 3) + 16 + sizeof(__half) * ST_C1 * (ST_CH * ST_CW + ST_TH * ST_TW);
   // HFB_STEM_MMA (bit 0: projection, bit 1: layer_1 on warp tensor-core tiles; default both; 7: the same at 80 registers,
-  // three CTAs per SM).  The layer_1 debug output is
-  // only written by the scalar phase A.
-  static int mode_env = -1;
-  if (mode_env < 0) {
+  // three CTAs per SM).  The layer_1 debug output is only written by the scalar phase A.
+  static const int mode_env = [] {
     const char* e = getenv("HFB_STEM_MMA");
-    mode_env = e ? (atoi(e) & 7) : 3;
-    if (mode_env & 4) mode_env = 7;   // three CTAs per SM exists for the all-tensor-core variant only
-    HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HFB_CUDA(ctx, cudaFuncSetAttribute(stem_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+    const int m = e ? (atoi(e) & 7) : 3;
+    return (m & 4) ? 7 : m;   // three CTAs per SM exists for the all-tensor-core variant only
+  }();
+  static SmemOptIn optin[8];
   const int mode = l1_out ? (mode_env & 1) : mode_env;
   const int grid = std::min(g.total_tiles, ctx->n_sm * ((mode & 4) ? 3 : 2));
-#define STEM_LAUNCH(M)                                                                                              \
-  hfb_launch(ctx, stem_kernel<M>, grid, ST_THREADS, smem, g, d_img, w1, b1, bw.wd, bw.bd, bw.project.w, bw.project.Kp, \
-             bw.project.b, l1_out, out)
+#define STEM_LAUNCH(M)                                                                                           \
+  do {                                                                                                           \
+    HFB_CUDA(ctx, optin[M].ensure(stem_kernel<M>, ctx->device, smem));                                           \
+    hfb_launch(ctx, stem_kernel<M>, grid, ST_THREADS, smem, g, d_img, w1, b1, bw.wd, bw.bd, bw.project.w,        \
+               bw.project.Kp, bw.project.b, l1_out, out);                                                        \
+  } while (0)
   switch (mode) {
     case 0: STEM_LAUNCH(0); break;
     case 1: STEM_LAUNCH(1); break;
