@@ -48,6 +48,25 @@
     if (_s != HFB_OK) return _s;                                                                 \
   } while (0)
 
+// Every extern "C" entry point runs on its context's device whatever the calling thread's current device is (the
+// reference calls Detect from cv::parallel_for_ workers and three SLAM threads, src/Extractors/HFextractor.cc:228-243):
+// kernel launches, cudaMalloc and cudaFuncSetAttribute all act on the thread's current device.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int device) : dev(device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define HFB_ENTER(ctx)                      \
+  if (!(ctx)) return HFB_ERR_INVALID;       \
+  DeviceGuard _device_guard((ctx)->device)
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -196,6 +215,15 @@ struct hfb_ctx {
   int* d_cm_tab = nullptr;     // [4][max_batch]
   int* d_cm_idx = nullptr;     // [max_batch][kp_cap]
   float* d_cm_val = nullptr;
+  void* d_cm_ws = nullptr;     // fixed matcher workspace of the association (its addresses are baked into the graphs)
+  size_t d_cm_ws_bytes = 0;
+  // Streaming state of the frame-to-previous-frame association (src/Tracking.cc:2030,2167: every frame is matched
+  // against the previous frame of its stream, also across calls).  d_kdesc holds 2 * max_batch frame slots: slots
+  // [0, max_batch) = the frames of the current call, slots [max_batch, 2 * max_batch) = carried descriptors of the
+  // previous call (stream_mode 0: slot max_batch = its last frame; stream_mode 1: slot max_batch + b = its frame b).
+  int cm_shift = 1;            // carried slots below frame 0 in the last association's row window
+  int stream_mode = 0;         // 0: a batch is B consecutive frames of ONE stream; 1: one frame of each of B streams
+  int* d_stream_state = nullptr;  // [0] = frames of the previous extraction (0 = none yet), [1 + s] = rows of carry slot s
   // per-launch profiling (hfb_profile_extract): one CUDA event after every launch, with the launch's algorithmic
   // bytes / flops as stated by the launcher
   bool prof_on = false;
@@ -273,7 +301,8 @@ int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold);
 // match.cu: pair_tab = device int[4][n_pairs] (a_off | a_cnt | b_off | b_cnt)
 int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB, int n_pairs, const int* d_pair_tab,
                        int max_a, int max_b, float thr, int* d_match_idx, float* d_match_val, int na_total,
-                       int nb_total, int** d_n_matches_out);
+                       int nb_total, int** d_n_matches_out, void* ws = nullptr, size_t ws_bytes = 0, int pad_rows = 0);
+size_t match_workspace_bytes(int na_total, int nb_total, int n_pairs, bool same);
 
 int launch_distinctive(hfb_ctx* ctx, const float* d_desc, const int* d_offsets, int n_points, int max_n, int* d_best_idx,
                        float* d_best_med);

@@ -6,8 +6,13 @@
 #include "common.cuh"
 
 // ================================================================================================ context
+static void drop_graphs(hfb_ctx* ctx);
+
 int hfb_ctx::ensure_scratch(size_t bytes) {
   if (bytes <= d_scratch_bytes) return HFB_OK;
+  // No captured graph refers to the scratch block (the in-graph association owns a fixed workspace, d_cm_ws); dropping
+  // the graphs before the block moves keeps that true by construction should a later graph ever use it.
+  drop_graphs(this);
   if (d_scratch) cudaFree(d_scratch);
   d_scratch = nullptr;
   d_scratch_bytes = 0;
@@ -85,7 +90,7 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
     return HFB_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return HFB_ERR_CUDA;
-  if (cudaSetDevice(cfg->device) != cudaSuccess) return HFB_ERR_CUDA;
+  DeviceGuard _device_guard(cfg->device);   // the caller's current device is restored on return
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return HFB_ERR_CUDA;
   hfb_ctx* ctx = new hfb_ctx();
@@ -167,7 +172,12 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   HFB_TRY(ctx->dalloc(&ctx->d_ky, nb * ctx->kp_cap));
   HFB_TRY(ctx->dalloc(&ctx->d_kresp, nb * ctx->kp_cap));
   HFB_TRY(ctx->dalloc(&ctx->d_koct, nb * ctx->kp_cap));
-  HFB_TRY(ctx->dalloc(&ctx->d_kdesc, nb * ctx->kp_cap * HFB_DESC_DIM));
+  {
+    // 2 * max_batch frame slots: the carried descriptors of the previous call sit right below the current frames
+    float* slots = nullptr;
+    HFB_TRY(ctx->dalloc(&slots, 2 * nb * ctx->kp_cap * HFB_DESC_DIM));
+    ctx->d_kdesc = slots + nb * ctx->kp_cap * HFB_DESC_DIM;
+  }
   HFB_TRY(ctx->dalloc(&ctx->d_global, nb * HFB_GLOBAL_DIM));
   HFB_TRY(ctx->dalloc(&ctx->d_kcount, nb * HFB_MAX_LEVELS));
   HFB_TRY(ctx->dalloc(&ctx->d_sel, nb * 8192));
@@ -175,14 +185,24 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   HFB_TRY(ctx->dalloc(&ctx->d_overflow, 1));
   HFB_TRY(ctx->dalloc(&ctx->d_pair_tab, 4));
   HFB_TRY(ctx->dalloc(&ctx->d_cm_tab, 4 * nb));
-  HFB_TRY(ctx->dalloc(&ctx->d_cm_idx, nb * ctx->kp_cap));
-  HFB_TRY(ctx->dalloc(&ctx->d_cm_val, nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_cm_idx, 2 * nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_cm_val, 2 * nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_stream_state, 1 + nb));
+  HFB_CUDA(ctx, cudaMemset(ctx->d_stream_state, 0, (1 + nb) * sizeof(int)));
+  {
+    const int rows = (int)(2 * nb * ctx->kp_cap);
+    ctx->d_cm_ws_bytes = match_workspace_bytes(rows, rows, (int)nb, true);
+    uint8_t* w = nullptr;
+    HFB_TRY(ctx->dalloc(&w, ctx->d_cm_ws_bytes));
+    ctx->d_cm_ws = w;
+  }
   HFB_CUDA(ctx, cudaMemset(ctx->d_overflow, 0, sizeof(int)));
   HFB_CUDA(ctx, cudaMemset(ctx->d_kcount, 0, nb * HFB_MAX_LEVELS * sizeof(int)));
   return HFB_OK;
 }
 
 static void drop_graphs(hfb_ctx* ctx) {
+  if (ctx->stream && !ctx->graphs.empty()) cudaStreamSynchronize(ctx->stream);
   for (auto& g : ctx->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   ctx->graphs.clear();
@@ -190,7 +210,7 @@ static void drop_graphs(hfb_ctx* ctx) {
 
 extern "C" void hfb_destroy(hfb_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard _device_guard(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   drop_graphs(ctx);
   encoder_forget(ctx);
@@ -227,7 +247,7 @@ static bool is_pinned(const void* p) {
 }
 
 extern "C" int hfb_sync(hfb_ctx* ctx) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HFB_OK;
 }
@@ -262,7 +282,7 @@ static size_t add_gemm_w(ArenaBuilder& ab, const float* w, int K, int N, int Kp)
 }
 
 extern "C" int hfb_load_weights(hfb_ctx* ctx, const void* blob, size_t nbytes) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, !ctx->weights_loaded, "weights already loaded (create a new context)");
   const uint8_t* p = reinterpret_cast<const uint8_t*>(blob);
   HFB_REQUIRE(ctx, blob && nbytes >= 32 && memcmp(p, "HFB2WTS1", 8) == 0, "bad weight blob magic");
@@ -417,8 +437,43 @@ static int check_overflow(hfb_ctx* ctx) {
 
 static int enqueue_match_consecutive(hfb_ctx* ctx, int n_images, int mode, float thr);
 
+// Streaming association: before a new extraction overwrites the frame slots, the descriptors the NEXT association needs
+// from the previous call are carried into the slots right below d_kdesc (src/Tracking.cc:2030,2167 match every frame
+// against mLastFrame, whichever call delivered it).  stream_mode 0 (B consecutive frames of one stream): the previous
+// call's last frame -> slot -1.  stream_mode 1 (one frame of each of B streams): previous frame b -> slot b - B (only
+// when the previous call had the same batch size).  state[0] = frames of the previous extraction, state[1 + s] = rows
+// carried for pair s.
+__global__ void carry_prev_kernel(float* __restrict__ kdesc, const int* __restrict__ kcount, int* __restrict__ state,
+                                  int n_levels, int kp_cap, int mode, int B) {
+  const int s = blockIdx.y;                       // carried slot: 0 (mode 0) or stream b (mode 1)
+  const int last_b = state[0];
+  int src = -1;
+  if (mode == 0) src = last_b - 1;
+  else if (last_b == B) src = s;
+  int cnt = 0;
+  if (src >= 0)
+    for (int l = 0; l < n_levels; ++l) cnt += kcount[src * HFB_MAX_LEVELS + l];
+  if (cnt > kp_cap) cnt = kp_cap;
+  const int shift = mode == 0 ? 1 : B;
+  const float4* from = reinterpret_cast<const float4*>(kdesc + (size_t)(src < 0 ? 0 : src) * kp_cap * HFB_DESC_DIM);
+  float4* to = reinterpret_cast<float4*>(kdesc + ((long long)s - shift) * kp_cap * HFB_DESC_DIM);
+  const int n4 = cnt * (HFB_DESC_DIM / 4);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) to[i] = from[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) state[1 + s] = cnt;
+}
+
+static int enqueue_carry(hfb_ctx* ctx, int B) {
+  const int slots = ctx->stream_mode == 0 ? 1 : B;
+  dim3 grid(std::max(1, std::min(32, ctx->kp_cap / 32)), slots);
+  carry_prev_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_kdesc, ctx->d_kcount, ctx->d_stream_state, ctx->n_levels,
+                                                  ctx->kp_cap, ctx->stream_mode, B);
+  HFB_CHECK_LAUNCH(ctx, "carry_prev");
+  return HFB_OK;
+}
+
 // Enqueues pyramid + encoder + selection of every level for frames already in lv[0].d_img.
 static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float threshold) {
+  HFB_TRY(enqueue_carry(ctx, B));
   for (int l = 0; l < ctx->n_levels; ++l) {
     LevelPlan& lv = ctx->lv[l];
     if (l > 0) {
@@ -434,24 +489,34 @@ static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, floa
   // everything that does not depend on the global branch happens now (main stream), overlapping the side stream:
   // the optional frame-to-previous-frame association and the transfer of the local features
   const hfb_ctx::D2HPlan& d = ctx->d2h;
-  const size_t rows = (size_t)B * ctx->kp_cap;
+  // Only the `budget` = sum(n_per_level) rows a frame can hold are transferred (the caller's arrays are sized for that,
+  // include/hfnet_b200.h): one strided copy per field, frame b's rows at b * kp_cap on both sides.
+  size_t budget = 0;
+  for (int l = 0; l < ctx->n_levels; ++l) budget += (size_t)n_per_level[l];
+  auto rows_d2h = [&](void* dst, const void* src, size_t elem_bytes, cudaStream_t st) -> cudaError_t {
+    if (budget == 0) return cudaSuccess;
+    const size_t pb = (size_t)ctx->kp_cap * elem_bytes, wb = budget * elem_bytes;
+    if (B == 1 || wb == pb) return cudaMemcpyAsync(dst, src, B == 1 ? wb : pb * B, cudaMemcpyDeviceToHost, st);
+    return cudaMemcpy2DAsync(dst, pb, src, pb, wb, (size_t)B, cudaMemcpyDeviceToHost, st);
+  };
   if (d.on) {   // feature transfer on its own stream: the copy engine works while the matching kernels run
     cudaStream_t cs = ctx->copy_stream;
     HFB_CUDA(ctx, cudaEventRecord(ctx->ev_local, ctx->stream));
     HFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_local, 0));
     HFB_CUDA(ctx, cudaMemcpyAsync(d.counts, ctx->d_kcount, (size_t)B * HFB_MAX_LEVELS * 4, cudaMemcpyDeviceToHost, cs));
     HFB_CUDA(ctx, cudaMemcpyAsync(d.overflow, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, cs));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.x, ctx->d_kx, rows * 4, cudaMemcpyDeviceToHost, cs));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.y, ctx->d_ky, rows * 4, cudaMemcpyDeviceToHost, cs));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.r, ctx->d_kresp, rows * 4, cudaMemcpyDeviceToHost, cs));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.o, ctx->d_koct, rows * 4, cudaMemcpyDeviceToHost, cs));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.d, ctx->d_kdesc, rows * HFB_DESC_DIM * 4, cudaMemcpyDeviceToHost, cs));
+    HFB_CUDA(ctx, rows_d2h(d.x, ctx->d_kx, 4, cs));
+    HFB_CUDA(ctx, rows_d2h(d.y, ctx->d_ky, 4, cs));
+    HFB_CUDA(ctx, rows_d2h(d.r, ctx->d_kresp, 4, cs));
+    HFB_CUDA(ctx, rows_d2h(d.o, ctx->d_koct, 4, cs));
+    HFB_CUDA(ctx, rows_d2h(d.d, ctx->d_kdesc, (size_t)HFB_DESC_DIM * 4, cs));
     HFB_CUDA(ctx, cudaEventRecord(ctx->ev_copied, cs));
   }
   if (ctx->fmatch.on) HFB_TRY(enqueue_match_consecutive(ctx, B, ctx->fmatch.mode, ctx->fmatch.thr));
   if (d.on && d.match_idx) {
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.match_idx, ctx->d_cm_idx, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaMemcpyAsync(d.match_val, ctx->d_cm_val, rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t o = (size_t)ctx->cm_shift * ctx->kp_cap;
+    HFB_CUDA(ctx, rows_d2h(d.match_idx, ctx->d_cm_idx + o, 4, ctx->stream));
+    HFB_CUDA(ctx, rows_d2h(d.match_val, ctx->d_cm_val + o, 4, ctx->stream));
   }
   if (d.on) HFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
   if (ctx->join_pending) {
@@ -460,6 +525,8 @@ static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, floa
   }
   if (d.on && d.g)
     HFB_CUDA(ctx, cudaMemcpyAsync(d.g, ctx->d_global, (size_t)B * HFB_GLOBAL_DIM * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // state[0] = B for the next call's carry (B <= 64 fits the low byte; the upper bytes stay zero)
+  HFB_CUDA(ctx, cudaMemsetAsync(ctx->d_stream_state, B, 1, ctx->stream));
   return HFB_OK;
 }
 
@@ -475,6 +542,7 @@ static int run_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float th
   if (!ctx->use_graph) return enqueue_extract(ctx, B, n_per_level, threshold);
   std::vector<int> key;
   key.push_back(B);
+  key.push_back(ctx->stream_mode);
   for (int l = 0; l < ctx->n_levels; ++l) key.push_back(n_per_level[l]);
   int tb;
   memcpy(&tb, &threshold, 4);
@@ -532,7 +600,7 @@ static int run_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float th
 
 extern "C" int hfb_extract_batch_dev(hfb_ctx* ctx, const uint8_t* d_images, int32_t n_images,
                                      const int32_t* n_per_level, float threshold) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, d_images && n_per_level, "null argument");
   HFB_REQUIRE(ctx, n_images >= 1 && n_images <= ctx->cfg.max_batch, "batch size outside [1, max_batch]");
   LevelPlan& l0 = ctx->lv[0];
@@ -543,7 +611,7 @@ extern "C" int hfb_extract_batch_dev(hfb_ctx* ctx, const uint8_t* d_images, int3
 }
 
 extern "C" int hfb_fetch_features(hfb_ctx* ctx, int32_t image_index, hfb_features* out) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, out && image_index >= 0 && image_index < ctx->last_batch, "bad image index");
   int counts[HFB_MAX_LEVELS];
   HFB_CUDA(ctx, cudaMemcpyAsync(counts, ctx->d_kcount + (size_t)image_index * HFB_MAX_LEVELS, sizeof(counts),
@@ -581,7 +649,7 @@ extern "C" int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int
 extern "C" int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* images, int32_t n_images, int32_t stride,
                                        const int32_t* n_per_level, float threshold, hfb_features* outs,
                                        int32_t match_mode, float match_thr, int32_t* match_idx, float* match_val) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, images && n_per_level && outs, "null argument");
   const bool want_match = match_mode >= 0;
   HFB_REQUIRE(ctx, !want_match || ((match_mode == 0 || match_mode == 1) && match_idx && match_val),
@@ -744,7 +812,7 @@ extern "C" int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* image
 
 extern "C" int hfb_extract(hfb_ctx* ctx, const uint8_t* image, int32_t height, int32_t width, int32_t stride,
                            const int32_t* n_per_level, float threshold, hfb_features* out) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, height == ctx->cfg.height && width == ctx->cfg.width,
               "image size differs from the context's (the reference builds one engine per fixed shape too, "
               "BaseModel.cc:35-65)");
@@ -756,7 +824,7 @@ extern "C" int hfb_extract(hfb_ctx* ctx, const uint8_t* image, int32_t height, i
 // {"name", "ms", "bytes", "flops"} with the launcher-stated algorithmic bytes / flops (bench.py's roofline source).
 extern "C" int hfb_profile_extract(hfb_ctx* ctx, int32_t n_images, const int32_t* n_per_level, float threshold,
                                    char* json_out, size_t cap) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, ctx->weights_loaded && n_per_level && json_out && cap > 2, "bad argument");
   HFB_REQUIRE(ctx, n_images >= 1 && n_images <= ctx->cfg.max_batch, "batch size outside [1, max_batch]");
   HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -791,7 +859,7 @@ extern "C" int hfb_profile_extract(hfb_ctx* ctx, int32_t n_images, const int32_t
 
 // ------------------------------------------------------------------------------------------------ parity hooks
 extern "C" int hfb_nms(hfb_ctx* ctx, const float* scores, int32_t height, int32_t width, float* scores_nms) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, scores && scores_nms && height > 0 && width > 0, "bad argument");
   const size_t n = (size_t)height * width;
   HFB_TRY(ctx->ensure_scratch(2 * n * 4));
@@ -808,7 +876,7 @@ extern "C" int hfb_select_sample(hfb_ctx* ctx, const float* scores_nms, int32_t 
                                  const float* desc_map, int32_t desc_h, int32_t desc_w, int32_t n_keypoints,
                                  float threshold, float* x, float* y, float* response, float* descriptors,
                                  int32_t* n_out) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, scores_nms && desc_map && n_out && height > 0 && width > 0 && desc_h > 0 && desc_w > 0,
               "bad argument");
   HFB_REQUIRE(ctx, n_keypoints >= 0 && n_keypoints <= 8192, "n_keypoints outside [0, 8192]");
@@ -851,7 +919,7 @@ extern "C" int hfb_select_sample(hfb_ctx* ctx, const float* scores_nms, int32_t 
 
 extern "C" int hfb_resize_linear_u8(hfb_ctx* ctx, const uint8_t* src, int32_t sh, int32_t sw, uint8_t* dst, int32_t dh,
                                     int32_t dw) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, src && dst && sh > 0 && sw > 0 && dh > 0 && dw > 0, "bad argument");
   std::vector<int> xi, yi;
   std::vector<short> xa, ya;
@@ -886,7 +954,7 @@ __global__ void h2f_kernel(const __half* __restrict__ in, int ld, int col0, int 
 
 extern "C" int hfb_debug_tensor(hfb_ctx* ctx, const char* name, int32_t image_index, int32_t level, float* out,
                                 size_t cap, size_t* n, int32_t* dims4) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, name && n && dims4, "null argument");
   HFB_REQUIRE(ctx, ctx->weights_loaded && ctx->last_batch > 0, "no extraction has run yet");
   HFB_REQUIRE(ctx, level >= 0 && level < ctx->n_levels && image_index >= 0 && image_index < ctx->last_batch,
@@ -953,7 +1021,7 @@ extern "C" int hfb_match_batch_dev(hfb_ctx* ctx, int32_t mode, const float* dA_a
                                    const float* dB_all, int32_t nb_total, int32_t n_pairs, const int32_t* d_pair_tab,
                                    int32_t max_a_cnt, int32_t max_b_cnt, float thr, int32_t* d_match_idx,
                                    float* d_match_val) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (l2) or 1 (cos)");
   HFB_REQUIRE(ctx, dA_all && dB_all && d_pair_tab && d_match_idx && d_match_val, "null argument");
   HFB_REQUIRE(ctx, na_total >= 0 && nb_total >= 0 && n_pairs >= 0 && max_a_cnt >= 0 && max_b_cnt >= 0, "negative size");
@@ -961,27 +1029,32 @@ extern "C" int hfb_match_batch_dev(hfb_ctx* ctx, int32_t mode, const float* dA_a
                             d_match_val, na_total, nb_total, nullptr);
 }
 
-// Pair table for "frame b against frame b-1" (cyclic) from the per-level keypoint counts of the last extraction.
-__global__ void consecutive_tab_kernel(const int* __restrict__ kcount, int n_levels, int B, int kp_cap,
-                                       int* __restrict__ tab) {
+// Pair table of the streaming association, rows relative to the window base d_kdesc - shift * kp_cap * 256
+// (shift = 1 carried slot in stream_mode 0, B in stream_mode 1): A = frame b, B = the frame before it in its stream --
+// frame b-1 of this call or the descriptors carried over from the previous call (no rows on the first call / after
+// hfb_reset_stream: the frame then has no matches, like the first frame of a sequence).
+__global__ void consecutive_tab_kernel(const int* __restrict__ kcount, const int* __restrict__ state, int n_levels, int B,
+                                       int kp_cap, int mode, int* __restrict__ tab) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const int pb = (b + B - 1) % B;
+  const int shift = mode == 0 ? 1 : B;
   int na = 0, nb = 0;
-  for (int l = 0; l < n_levels; ++l) {
-    na += kcount[b * HFB_MAX_LEVELS + l];
-    nb += kcount[pb * HFB_MAX_LEVELS + l];
+  for (int l = 0; l < n_levels; ++l) na += kcount[b * HFB_MAX_LEVELS + l];
+  if (mode == 0 && b > 0) {
+    for (int l = 0; l < n_levels; ++l) nb += kcount[(b - 1) * HFB_MAX_LEVELS + l];
+  } else {
+    nb = state[1 + (mode == 0 ? 0 : b)];
   }
-  tab[b] = b * kp_cap;
+  tab[b] = (shift + b) * kp_cap;
   tab[B + b] = na;
-  tab[2 * B + b] = pb * kp_cap;
+  tab[2 * B + b] = b * kp_cap;
   tab[3 * B + b] = nb;
 }
 
 // Tracking's per-frame descriptor association with the previous frame, device-resident: the descriptors of the last
 // hfb_extract_batch*(n_images) never leave HBM.  Frame b is matched against frame (b-1) mod n_images.
 extern "C" int hfb_match_consecutive_dev(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   return enqueue_match_consecutive(ctx, n_images, mode, thr);
 }
 
@@ -989,7 +1062,7 @@ extern "C" int hfb_match_consecutive_dev(hfb_ctx* ctx, int32_t n_images, int32_t
 extern "C" int hfb_extract_match_batch_dev(hfb_ctx* ctx, const uint8_t* d_images, int32_t n_images,
                                            const int32_t* n_per_level, float threshold, int32_t match_mode,
                                            float match_thr) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, match_mode == 0 || match_mode == 1, "mode must be 0 (l2) or 1 (cos)");
   ctx->fmatch.on = true;
   ctx->fmatch.mode = match_mode;
@@ -1002,19 +1075,44 @@ extern "C" int hfb_extract_match_batch_dev(hfb_ctx* ctx, const uint8_t* d_images
 static int enqueue_match_consecutive(hfb_ctx* ctx, int n_images, int mode, float thr) {
   HFB_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (l2) or 1 (cos)");
   HFB_REQUIRE(ctx, n_images >= 1 && n_images <= ctx->last_batch, "n_images exceeds the last extracted batch");
-  consecutive_tab_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_kcount, ctx->n_levels, n_images, ctx->kp_cap, ctx->d_cm_tab);
+  HFB_REQUIRE(ctx, ctx->stream_mode == 0 || n_images == ctx->last_batch,
+              "stream_mode 1 associates every frame of the batch with its own stream's previous frame");
+  consecutive_tab_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_kcount, ctx->d_stream_state, ctx->n_levels, n_images,
+                                                   ctx->kp_cap, ctx->stream_mode, ctx->d_cm_tab);
   HFB_CHECK_LAUNCH(ctx, "consecutive_tab");
   int budget = 0;
   for (int l = 0; l < ctx->n_levels; ++l) budget += ctx->last_budget[l];
-  return launch_match_batch(ctx, mode, ctx->d_kdesc, ctx->d_kdesc, n_images, ctx->d_cm_tab, budget, budget, thr,
-                            ctx->d_cm_idx, ctx->d_cm_val, n_images * ctx->kp_cap, n_images * ctx->kp_cap, nullptr);
+  const int shift = ctx->stream_mode == 0 ? 1 : n_images;
+  ctx->cm_shift = shift;
+  const float* base = ctx->d_kdesc - (size_t)shift * ctx->kp_cap * HFB_DESC_DIM;
+  const int rows = (shift + n_images) * ctx->kp_cap;
+  return launch_match_batch(ctx, mode, base, base, n_images, ctx->d_cm_tab, budget, budget, thr, ctx->d_cm_idx,
+                            ctx->d_cm_val, rows, rows, nullptr, ctx->d_cm_ws, ctx->d_cm_ws_bytes, ctx->kp_cap);
+}
+
+// Stream layout of a batch and the reset of the association's history (Tracking::Reset / a new map start from an empty
+// mLastFrame, src/Tracking.cc:3256-3330).
+extern "C" int hfb_set_stream_mode(hfb_ctx* ctx, int32_t mode) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, mode == 0 || mode == 1, "stream mode must be 0 (one stream per batch) or 1 (one stream per batch slot)");
+  if (mode != ctx->stream_mode) {
+    ctx->stream_mode = mode;
+    return hfb_reset_stream(ctx);
+  }
+  return HFB_OK;
+}
+
+extern "C" int hfb_reset_stream(hfb_ctx* ctx) {
+  HFB_ENTER(ctx);
+  HFB_CUDA(ctx, cudaMemsetAsync(ctx->d_stream_state, 0, (size_t)(1 + ctx->cfg.max_batch) * sizeof(int), ctx->stream));
+  return HFB_OK;
 }
 
 extern "C" int hfb_fetch_matches(hfb_ctx* ctx, int32_t image_index, int32_t* match_idx, float* match_val, int32_t n) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, match_idx && match_val && image_index >= 0 && image_index < ctx->last_batch && n >= 0 &&
                        n <= ctx->kp_cap, "bad argument");
-  const size_t o = (size_t)image_index * ctx->kp_cap;
+  const size_t o = (size_t)(ctx->cm_shift + image_index) * ctx->kp_cap;
   HFB_CUDA(ctx, cudaMemcpyAsync(match_idx, ctx->d_cm_idx + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   HFB_CUDA(ctx, cudaMemcpyAsync(match_val, ctx->d_cm_val + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1025,12 +1123,12 @@ extern "C" int hfb_fetch_matches(hfb_ctx* ctx, int32_t image_index, int32_t* mat
 // match rows ([n_images][kp_cap] indices + values) come back, in one transfer each.
 extern "C" int hfb_match_consecutive(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr, int32_t* match_idx,
                                      float* match_val) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, match_idx && match_val, "null output");
   HFB_TRY(hfb_match_consecutive_dev(ctx, n_images, mode, thr));
-  const size_t n = (size_t)n_images * ctx->kp_cap;
-  HFB_CUDA(ctx, cudaMemcpyAsync(match_idx, ctx->d_cm_idx, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  HFB_CUDA(ctx, cudaMemcpyAsync(match_val, ctx->d_cm_val, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t n = (size_t)n_images * ctx->kp_cap, o = (size_t)ctx->cm_shift * ctx->kp_cap;
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_idx, ctx->d_cm_idx + o, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_val, ctx->d_cm_val + o, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HFB_OK;
 }
@@ -1038,7 +1136,7 @@ extern "C" int hfb_match_consecutive(hfb_ctx* ctx, int32_t n_images, int32_t mod
 // MapPoint::ComputeDistinctiveDescriptors for a ragged batch of map points (src/MapPoint.cc:331-400).
 extern "C" int hfb_distinctive_descriptors(hfb_ctx* ctx, const float* descriptors, const int32_t* offsets,
                                            int32_t n_points, int32_t* best_index, float* best_median) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, n_points >= 0 && offsets && best_index && best_median, "bad argument");
   if (n_points == 0) return HFB_OK;
   int max_n = 0;
@@ -1130,7 +1228,7 @@ extern "C" int hfb_match_batch(hfb_ctx* ctx, int32_t mode, const float* A_all, i
                                int32_t nb_total, int32_t n_pairs, const int32_t* a_off, const int32_t* a_cnt,
                                const int32_t* b_off, const int32_t* b_cnt, float thr, int32_t* match_idx,
                                float* match_val) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   return match_host(ctx, mode, A_all, na_total, B_all, nb_total, n_pairs, a_off, a_cnt, b_off, b_cnt, thr, match_idx,
                     match_val, nullptr);
 }
@@ -1145,11 +1243,11 @@ static int match_single(hfb_ctx* ctx, int mode, const float* A, int na, const fl
 }
 extern "C" int hfb_match_mutual_l2(hfb_ctx* ctx, const float* A, int32_t na, const float* B, int32_t nb,
                                    float max_dist, int32_t* match_idx, float* match_val, int32_t* n_matches) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   return match_single(ctx, 0, A, na, B, nb, max_dist, match_idx, match_val, n_matches);
 }
 extern "C" int hfb_match_mutual_cos(hfb_ctx* ctx, const float* A, int32_t na, const float* B, int32_t nb, float min_cos,
                                     int32_t* match_idx, float* match_val, int32_t* n_matches) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   return match_single(ctx, 1, A, na, B, nb, min_cos, match_idx, match_val, n_matches);
 }

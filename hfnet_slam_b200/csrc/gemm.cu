@@ -336,7 +336,7 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restri
 extern "C" int hfb_debug_gemm(hfb_ctx* ctx, const float* A, int B, int H, int W, int K, const float* Wt, int N,
                               const float* bias, int relu6, int conv3x3, int use_tc, int BN, float* out) {
   // A: [B*H*W][K] (NHWC when conv3x3), Wt: [N][Kw] with Kw = conv3x3 ? 9*K : K.  out: [B*H*W][N] fp32.
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, K % 8 == 0 && N % 8 == 0, "hfb_debug_gemm: K and N must be multiples of 8");
   const long long M = (long long)B * H * W;
   const int Kw = conv3x3 ? 9 * K : K;

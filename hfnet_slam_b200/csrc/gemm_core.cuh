@@ -35,6 +35,9 @@ struct GemmGeom {
   // a_off | a_cnt | b_off | b_cnt (row ranges inside A's and W's maps).  null = one problem of M x N.
   const int* pair_tab;
   int n_pairs;
+  // Split-precision contraction (descriptor matching): operand rows are stored once as [hi(256) | lo(256)] fp16 and the
+  // K' = 768 loop reads A's k-blocks as hi|hi|lo and B's as hi|lo|hi, i.e. ah.bh + ah.bl + al.bh.
+  int split3;
 };
 
 struct TileRow {
@@ -56,6 +59,8 @@ struct TileRow {
 #define GEMM_EPI_BAR 1           // named barrier of the 128 epilogue threads
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(GEMM_EPI_BAR), "n"(128) : "memory"); }
+template <int kThreads>
+__device__ __forceinline__ void epi_bar_sync_n() { asm volatile("bar.sync %0, %1;" ::"n"(GEMM_EPI_BAR), "n"(kThreads) : "memory"); }
 
 struct TileCoord {
   bool valid;
@@ -165,8 +170,13 @@ __global__ void __launch_bounds__(GEMM_THREADS(Epi::kWarps)) gemm_tc_kernel(cons
             tc::tma_load_4d(sa, &tmA, &full[s], cb * 64, t.x0 + dx - 1, t.y0 + dy - 1, t.img);
             tc::tma_load_2d(sb, &tmB, &full[s], tap * g.K + cb * 64, t.n0);
           } else {
-            tc::tma_load_2d(sa, &tmA, &full[s], g.a_k_off + kb * 64, t.m0);
-            tc::tma_load_2d(sb, &tmB, &full[s], kb * 64, t.b_off + t.n0);
+            int ka = kb, kbb = kb;
+            if (g.split3) {
+              ka = kb < 8 ? (kb & 3) : 4 + (kb & 3);
+              kbb = kb < 8 ? kb : kb - 8;
+            }
+            tc::tma_load_2d(sa, &tmA, &full[s], g.a_k_off + ka * 64, t.m0);
+            tc::tma_load_2d(sb, &tmB, &full[s], kbb * 64, t.b_off + t.n0);
           }
         }
       }
@@ -277,6 +287,7 @@ static inline void gemm_fill_geom(GemmGeom& g, int M, int N, int K, int BN, int 
   g.epi_warp_bytes = 0;
   g.bias_bytes = 0;
   g.pair_tab = nullptr; g.n_pairs = 0;
+  g.split3 = 0;
   gemm_finish_geom(g, (M + 127) / 128);
 }
 static inline void gemm_fill_geom_conv(GemmGeom& g, int B, int H, int W, int C, int N, int BN) {
@@ -288,6 +299,7 @@ static inline void gemm_fill_geom_conv(GemmGeom& g, int B, int H, int W, int C, 
   g.epi_warp_bytes = 0;
   g.bias_bytes = 0;
   g.pair_tab = nullptr; g.n_pairs = 0;
+  g.split3 = 0;
   gemm_finish_geom(g, g.tiles_x * g.tiles_y * B);
 }
 // Re-derive the tile counts for the actual batch / row count of a launch (plans are built for max_batch).

@@ -4,6 +4,7 @@
 // cv::Mat objects).  The scan is a pure HBM stream: dim*4 bytes per keyframe per query batch, the literal
 // difference form (q - d).norm() of the reference in fp32, one warp per row, 8 x 16-byte loads in flight per lane.
 #include <algorithm>
+#include <unordered_set>
 
 #include "common.cuh"
 
@@ -129,6 +130,7 @@ static int kfdb_scan(hfb_kfdb* db, const float* d_query, int nq, float* d_scores
 
 extern "C" int hfb_kfdb_create(hfb_ctx* ctx, int32_t dim, int32_t capacity, hfb_kfdb** out) {
   if (!ctx || !out) return HFB_ERR_INVALID;
+  DeviceGuard _device_guard(ctx->device);
   *out = nullptr;
   HFB_REQUIRE(ctx, dim >= 4 && dim % 4 == 0 && dim <= 8192, "dim must be a multiple of 4 in [4, 8192]");
   HFB_REQUIRE(ctx, capacity >= 1, "capacity must be positive");
@@ -157,6 +159,7 @@ extern "C" int hfb_kfdb_create(hfb_ctx* ctx, int32_t dim, int32_t capacity, hfb_
 
 extern "C" void hfb_kfdb_destroy(hfb_kfdb* db) {
   if (!db) return;
+  DeviceGuard _device_guard(db->ctx->device);
   cudaStreamSynchronize(db->ctx->stream);
   cudaFree(db->d_rows); cudaFree(db->d_scores); cudaFree(db->d_query); cudaFree(db->d_best);
   cudaFree(db->d_ncand); cudaFree(db->d_cand_slot); cudaFree(db->d_cand_score);
@@ -170,16 +173,19 @@ static int kfdb_add_common(hfb_kfdb* db, const int64_t* ids, const float* src, i
     ctx->set_error("keyframe database capacity exceeded");
     return HFB_ERR_CAPACITY;
   }
-  for (int i = 0; i < n; ++i) {
-    if (db->slot_of.count(ids[i])) {
-      ctx->set_error("keyframe id already in the database: " + std::to_string(ids[i]));
-      return HFB_ERR_INVALID;
-    }
-    for (int j = 0; j < i; ++j)
-      if (ids[j] == ids[i]) {
+  {
+    std::unordered_set<int64_t> seen;
+    seen.reserve((size_t)n * 2);
+    for (int i = 0; i < n; ++i) {
+      if (db->slot_of.count(ids[i])) {
+        ctx->set_error("keyframe id already in the database: " + std::to_string(ids[i]));
+        return HFB_ERR_INVALID;
+      }
+      if (!seen.insert(ids[i]).second) {
         ctx->set_error("duplicate keyframe id in one add call");
         return HFB_ERR_INVALID;
       }
+    }
   }
   if (n == 0) return HFB_OK;
   HFB_CUDA(ctx, cudaMemcpyAsync(db->d_rows + (size_t)db->size * db->dim, src, (size_t)n * db->dim * 4, kind, ctx->stream));
@@ -195,16 +201,19 @@ static int kfdb_add_common(hfb_kfdb* db, const int64_t* ids, const float* src, i
 
 extern "C" int hfb_kfdb_add(hfb_kfdb* db, const int64_t* ids, const float* descriptors, int32_t n) {
   if (!db) return HFB_ERR_INVALID;
+  DeviceGuard _device_guard(db->ctx->device);
   return kfdb_add_common(db, ids, descriptors, n, cudaMemcpyHostToDevice);
 }
 extern "C" int hfb_kfdb_add_dev(hfb_kfdb* db, const int64_t* ids, const float* d_descriptors, int32_t n) {
   if (!db) return HFB_ERR_INVALID;
+  DeviceGuard _device_guard(db->ctx->device);
   return kfdb_add_common(db, ids, d_descriptors, n, cudaMemcpyDeviceToDevice);
 }
 
 // KeyFrameDatabase::erase (src/KeyFrameDatabase.cc:38-43): the last row moves into the freed slot.
 extern "C" int hfb_kfdb_erase(hfb_kfdb* db, int64_t id) {
   if (!db) return HFB_ERR_INVALID;
+  DeviceGuard _device_guard(db->ctx->device);
   hfb_ctx* ctx = db->ctx;
   auto it = db->slot_of.find(id);
   if (it == db->slot_of.end()) return HFB_OK;  // std::set::erase of a missing key is a no-op
@@ -224,6 +233,7 @@ extern "C" int hfb_kfdb_erase(hfb_kfdb* db, int64_t id) {
 
 extern "C" int hfb_kfdb_clear(hfb_kfdb* db) {
   if (!db) return HFB_ERR_INVALID;
+  DeviceGuard _device_guard(db->ctx->device);
   db->ids.clear();
   db->slot_of.clear();
   db->size = 0;
@@ -277,6 +287,7 @@ static int kfdb_query_common(hfb_kfdb* db, const float* query, float rel, float 
 extern "C" int hfb_kfdb_query(hfb_kfdb* db, const float* query, float rel, float floor_, int64_t* cand_ids,
                               float* cand_scores, int32_t cap, int32_t* n_cand, float* best_score) {
   if (!db) return HFB_ERR_INVALID;
+  DeviceGuard _device_guard(db->ctx->device);
   hfb_ctx* ctx = db->ctx;
   HFB_REQUIRE(ctx, n_cand && best_score && cap >= 0, "bad argument");
   std::vector<int64_t> cid;
@@ -297,6 +308,7 @@ extern "C" int hfb_kfdb_query(hfb_kfdb* db, const float* query, float rel, float
 
 extern "C" int hfb_kfdb_scores_of(hfb_kfdb* db, const int64_t* ids, int32_t n, float* scores) {
   if (!db) return HFB_ERR_INVALID;
+  DeviceGuard _device_guard(db->ctx->device);
   hfb_ctx* ctx = db->ctx;
   HFB_REQUIRE(ctx, ids && scores && n >= 0, "bad argument");
   if (!db->h_scores_valid) {
@@ -322,6 +334,7 @@ __global__ void kfdb_best_to_float_kernel(const unsigned int* __restrict__ b, fl
 
 extern "C" int hfb_kfdb_scan_dev(hfb_kfdb* db, const float* d_query, int32_t n_queries, float* d_scores, float* d_best) {
   if (!db) return HFB_ERR_INVALID;
+  DeviceGuard _device_guard(db->ctx->device);
   hfb_ctx* ctx = db->ctx;
   HFB_REQUIRE(ctx, d_query && d_scores && d_best && n_queries >= 1, "bad argument");
   // d_best doubles as the ordered-uint accumulator (scores >= 0, so the bit patterns are already floats)
@@ -333,6 +346,7 @@ extern "C" int hfb_kfdb_scan_dev(hfb_kfdb* db, const float* d_query, int32_t n_q
 // Fixed-size shard record for ONE all-gather; layout documented in include/hfnet_b200.h.
 extern "C" int hfb_kfdb_query_shard(hfb_kfdb* db, const float* query, float rel, float floor_, int32_t k, void* record) {
   if (!db) return HFB_ERR_INVALID;
+  DeviceGuard _device_guard(db->ctx->device);
   hfb_ctx* ctx = db->ctx;
   HFB_REQUIRE(ctx, record && k >= 1, "bad argument");
   std::vector<int64_t> cid;

@@ -544,7 +544,7 @@ static int lba_schur(hfb_ctx* ctx, LbaDev& d, double lambda) {
 
 extern "C" int hfb_lba_build_schur(hfb_ctx* ctx, const hfb_lba_problem* problem, double lambda, double* Hschur,
                                    double* bschur, double* robust_chi2, int32_t* n_opt_cams) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   LbaDev d;
   LbaHost h;
   uint8_t* arena = nullptr;
@@ -564,7 +564,7 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
                                 double user_lambda_init, const volatile uint8_t* stop_flag, double* poses_out,
                                 double* points_out, double* chi2_out, uint8_t* depth_positive_out,
                                 hfb_lba_stats* stats) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   LbaDev d;
   LbaHost h;
   uint8_t* arena = nullptr;
@@ -1009,7 +1009,7 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
 extern "C" int hfb_pose_optimize(hfb_ctx* ctx, const float* K, const double* pose_in, int32_t n, const double* Xw,
                                  const double* obs, const double* inv_sigma2, double* pose_out, uint8_t* outlier_out,
                                  int32_t* n_inliers, int32_t* n_trials) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, K && pose_in && pose_out && n >= 0 && (n == 0 || (Xw && obs && inv_sigma2)), "bad argument");
   if (n == 0) {
     memcpy(pose_out, pose_in, 56);

@@ -5,22 +5,26 @@
 //                                                     cross-check, strict '>' (lowest index wins ties)
 //   SearchByBoW             (src/Matcher.cc:220-263, :561-621)  cv::BFMatcher(NORM_L2, crossCheck).match, dist < TH_LOW
 //
-// fp32 descriptors are split into fp16 hi + lo parts (a = ah + al, |al| <= 2^-11 |a|) and the contraction runs over
-// K' = 768 = [ah|ah|al] . [bh|bl|bh], i.e. ah.bh + ah.bl + al.bh: the dropped al.bl term is ~1e-8, so the scores
-// that drive the arg-max carry fp32-level accuracy while using kind::f16 UMMA.  The epilogue reduces every 128 x 128
-// accumulator tile to per-row and per-column (key, index) maxima straight out of TMEM (row: thread-local scan;
-// column: redux.sync max + ballot inside each warp) and merges them with packed 64-bit atomicMax.  The accepted
-// value (cosine or L2 distance) is recomputed in plain fp32 from the original descriptors before thresholding,
-// like Matcher::DescriptorDistance (src/Matcher.cc:1893-1900).
+// fp32 descriptors are split into fp16 hi + lo parts (a = ah + al, |al| <= 2^-11 |a|), stored once per row as
+// [hi(256) | lo(256)], and the contraction runs over K' = 768: the TMA producer reads A's k-blocks as hi|hi|lo and B's as
+// hi|lo|hi (GemmGeom::split3), i.e. ah.bh + ah.bl + al.bh: the dropped al.bl term is ~1e-8, so the scores that drive the
+// arg-max carry fp32-level accuracy while using kind::f16 UMMA.  The epilogue (8 warps: two per TMEM lane group, each
+// taking 64 of the tile's 128 columns) reduces every 128 x 128 accumulator tile to per-row and per-column (key, index)
+// maxima straight out of TMEM: the row scan is thread-local; the column maxima of a warp's 32 rows come from a
+// register butterfly (transpose-reduce over 32 columns: 31 shuffles instead of 32 warp reductions), the winning row of
+// each column from one ballot.  Both are merged with packed 64-bit atomicMax.  The accepted value (cosine or L2
+// distance) is recomputed in plain fp32 from the original descriptors before thresholding, like
+// Matcher::DescriptorDistance (src/Matcher.cc:1893-1900).
 #include "common.cuh"
 #include "gemm_core.cuh"
 
-#define MATCH_K 768
+#define MATCH_K 768      // contraction length of the split product
+#define MATCH_LD 512     // stored row: hi(256) | lo(256) fp16
 #define MATCH_BN 128
 
-// ---- prep: fp32 [n][256] -> fp16 [n][768] (A: hi|hi|lo, B: hi|lo|hi) and half squared norms -------------------
+// ---- prep: fp32 [n][256] -> fp16 [n][512] (hi | lo) and half squared norms ------------------------------------------
 __global__ void match_prep_kernel(const float* __restrict__ X, int n, __half* __restrict__ out, float* __restrict__ hn,
-                                  int is_b, int l2_mode) {
+                                  int l2_mode) {
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -41,10 +45,9 @@ __global__ void match_prep_kernel(const float* __restrict__ X, int n, __half* __
     ss = fmaf(v[2 * j], v[2 * j], ss);
     ss = fmaf(v[2 * j + 1], v[2 * j + 1], ss);
   }
-  uint4* o = reinterpret_cast<uint4*>(out + (size_t)row * MATCH_K) + lane;
-  o[0] = hi;                     // k in [0,256)
-  o[32] = is_b ? lo : hi;        // k in [256,512)
-  o[64] = is_b ? hi : lo;        // k in [512,768)
+  uint4* o = reinterpret_cast<uint4*>(out + (size_t)row * MATCH_LD) + lane;
+  o[0] = hi;      // k in [0,256)
+  o[32] = lo;     // k in [256,512)
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
   if (lane == 0) hn[row] = l2_mode ? 0.5f * ss : 0.f;
@@ -54,9 +57,27 @@ __device__ __forceinline__ u64 pack_best(float key, int idx) {
   return ((u64)f2ord(key) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)idx);
 }
 
+// Column maxima of a warp's 32 rows for 32 columns at once: lane L enters with its row's keys k[0..31] (0 = invalid)
+// and leaves with the maximum of column L over the 32 lanes in k[0] (recursive halving: at offset o a lane keeps the
+// half of its columns whose bit o matches its own lane bit and trades the other half with lane ^ o).
+__device__ __forceinline__ uint32_t warp_colmax32(uint32_t (&k)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const uint32_t send = up ? k[i] : k[i + o];
+      const uint32_t keep = up ? k[i + o] : k[i];
+      const uint32_t got = __shfl_xor_sync(0xffffffffu, send, o);
+      k[i] = keep > got ? keep : got;
+    }
+  }
+  return k[0];
+}
+
 // ---- epilogue: per-row and per-column arg-max of key = s - 0.5*|other|^2 (L2 mode) or s (cosine mode) ------------
 struct EpiArgmax {
-  static constexpr int kWarps = 4;
+  static constexpr int kWarps = 8;
   struct Params {
     const float* hna;  // [na_total] 0.5*|a|^2 (0 in cosine mode)
     const float* hnb;  // [nb_total]
@@ -65,50 +86,54 @@ struct EpiArgmax {
   };
   static __device__ __forceinline__ const float* bias(const Params&) { return nullptr; }
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
-    __shared__ u64 s_col[4][MATCH_BN];   // per-warp column maxima (no shared-memory atomics)
     __shared__ float s_hnb[MATCH_BN];
-    const int lane = threadIdx.x & 31, warp = tr.ewarp, et = warp * 32 + lane;   // et: 0..127 among epilogue threads
+    const int lane = threadIdx.x & 31;
+    const int et = (int)threadIdx.x - 64;           // 0..255 among the epilogue threads
     const int ncols = min(g.BN, tr.n_cnt - tr.n0);  // valid columns of this tile
-    s_hnb[et] = et < ncols ? __ldg(p.hnb + tr.b_off + tr.n0 + et) : 0.f;
-    epi_bar_sync();
+    if (et < MATCH_BN) s_hnb[et] = et < ncols ? __ldg(p.hnb + tr.b_off + tr.n0 + et) : 0.f;
+    epi_bar_sync_n<32 * kWarps>();
     const float my_hna = tr.valid ? __ldg(p.hna + tr.row) : 0.f;
     const int warp_row0 = tr.row_local - lane;      // problem-local row of this warp's lane 0
     float best = -INFINITY;
     int best_j = 0;
-    for (int c0 = 0; c0 < g.BN; c0 += 16) {
-      uint32_t r[16];
-      tc::tmem_ld16(tr.taddr + (uint32_t)c0, r);
+    const int cbeg = tr.sub * (MATCH_BN / 2);       // this warp's half of the tile's columns
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + MATCH_BN / 2; c0 += 32) {
+      if (c0 >= ncols) break;  // warp-uniform
+      uint32_t r[32];
+      tc::tmem_ld32(tr.taddr + (uint32_t)c0, r);
       tc::tmem_ld_wait();
-      if (c0 >= ncols) continue;  // warp-uniform
+      uint32_t k[32];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 32; ++j) {
         const float s = __uint_as_float(r[j]);
-        const bool cv = (c0 + j) < ncols;
+        const bool cv = (c0 + j) < ncols && tr.valid;
         // row pass (this thread's row, ascending j: strict '>' keeps the lowest index on ties)
         const float kr = s - s_hnb[c0 + j];
-        if (cv && tr.valid && kr > best) {
+        if (cv && kr > best) {
           best = kr;
           best_j = tr.n0 + c0 + j;
         }
-        // column pass: max over the warp's 32 rows, lowest lane among equals
-        const uint32_t kc = (cv && tr.valid) ? f2ord(s - my_hna) : 0u;
-        const uint32_t mx = __reduce_max_sync(0xffffffffu, kc);
-        const uint32_t who = __ballot_sync(0xffffffffu, kc == mx);
-        if (lane == 0)
-          s_col[warp][c0 + j] =
-              mx != 0u ? (((u64)mx << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(warp_row0 + __ffs(who) - 1))) : 0ull;
+        k[j] = cv ? f2ord(s - my_hna) : 0u;
       }
+      // column pass: maximum over the warp's 32 rows (lane c ends up with column c0 + c), then the lowest row among
+      // the lanes that hold it
+      const uint32_t mx = warp_colmax32(k, lane);
+      int win = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t m = __shfl_sync(0xffffffffu, mx, j);
+        const bool cv = (c0 + j) < ncols && tr.valid;
+        const uint32_t mine = cv ? f2ord(__uint_as_float(r[j]) - my_hna) : 0u;
+        const uint32_t who = __ballot_sync(0xffffffffu, mine == m);
+        if (lane == j) win = __ffs(who) - 1;
+      }
+      if (mx != 0u && c0 + lane < ncols)
+        atomicMax(p.colbest + tr.b_off + tr.n0 + c0 + lane,
+                  ((u64)mx << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(warp_row0 + win)));
     }
     if (tr.valid && best > -INFINITY) atomicMax(p.rowbest + tr.row, pack_best(best, best_j));
-    epi_bar_sync();
-    if (et < ncols) {
-      u64 m = s_col[0][et];
-      m = m > s_col[1][et] ? m : s_col[1][et];
-      m = m > s_col[2][et] ? m : s_col[2][et];
-      m = m > s_col[3][et] ? m : s_col[3][et];
-      if (m != 0ull) atomicMax(p.colbest + tr.b_off + tr.n0 + et, m);
-    }
-    epi_bar_sync();   // s_col / s_hnb are reused by the next tile
+    epi_bar_sync_n<32 * kWarps>();   // s_hnb is reused by the next tile
   }
 };
 
@@ -117,14 +142,20 @@ __global__ void match_finalize_kernel(const float* __restrict__ A, const float* 
                                       const u64* __restrict__ rowbest, const u64* __restrict__ colbest,
                                       const int* __restrict__ pair_tab, int n_pairs, int mode, float thr,
                                       int* __restrict__ match_idx, float* __restrict__ match_val,
-                                      int* __restrict__ n_matches) {
+                                      int* __restrict__ n_matches, int pad_rows) {
   pdl_launch_dependents();
   pdl_wait();
   const int pr = blockIdx.y;
   const int a_off = pair_tab[pr], a_cnt = pair_tab[n_pairs + pr], b_off = pair_tab[2 * n_pairs + pr];
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (i >= a_cnt) return;
+  if (i >= a_cnt) {
+    if (i < pad_rows && lane == 0) {   // fixed-pitch rows (frame association): unmatched beyond the frame's keypoints
+      match_idx[a_off + i] = -1;
+      match_val[a_off + i] = 0.f;
+    }
+    return;
+  }
   const u64 rb = rowbest[a_off + i];
   int j = -1;
   float val = 0.f;
@@ -171,10 +202,20 @@ __global__ void match_finalize_kernel(const float* __restrict__ A, const float* 
   }
 }
 
-// Scratch layout (ctx->d_scratch): A' | B' | hna | hnb | rowbest | colbest | n_matches[n_pairs]
+// Workspace layout: X' (A rows) | X' (B rows, absent when A and B are the same array) | hna | hnb | rowbest | colbest |
+// n_matches[n_pairs].  ws == nullptr: the context's grow-on-demand scratch; the in-graph association passes its own
+// fixed block (captured graphs bake these addresses).
+size_t match_workspace_bytes(int na_total, int nb_total, int n_pairs, bool same) {
+  auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  const int nmax = same ? (na_total > nb_total ? na_total : nb_total) : na_total;
+  return al((size_t)nmax * MATCH_LD * 2) + (same ? 0 : al((size_t)nb_total * MATCH_LD * 2)) + al((size_t)nmax * 4) +
+         (same ? 0 : al((size_t)nb_total * 4)) + al((size_t)na_total * 8) + al((size_t)nb_total * 8) +
+         al((size_t)n_pairs * 4);
+}
+
 int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB, int n_pairs, const int* d_pair_tab,
                        int max_a, int max_b, float thr, int* d_match_idx, float* d_match_val, int na_total,
-                       int nb_total, int** d_n_matches_out) {
+                       int nb_total, int** d_n_matches_out, void* ws, size_t ws_bytes, int pad_rows) {
   if (na_total <= 0 || nb_total <= 0 || n_pairs <= 0 || max_a <= 0 || max_b <= 0) {
     if (na_total > 0) {
       HFB_CUDA(ctx, cudaMemsetAsync(d_match_idx, 0xFF, (size_t)na_total * 4, ctx->stream));
@@ -184,33 +225,45 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
     return HFB_OK;
   }
   auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
-  const size_t szA = al((size_t)na_total * MATCH_K * 2), szB = al((size_t)nb_total * MATCH_K * 2);
-  const size_t szna = al((size_t)na_total * 4), sznb = al((size_t)nb_total * 4);
+  const bool same = dA == dB;
+  const int nmax = same ? std::max(na_total, nb_total) : na_total;
+  const size_t szA = al((size_t)nmax * MATCH_LD * 2), szB = same ? 0 : al((size_t)nb_total * MATCH_LD * 2);
+  const size_t szna = al((size_t)nmax * 4), sznb = same ? 0 : al((size_t)nb_total * 4);
   const size_t szrb = al((size_t)na_total * 8), szcb = al((size_t)nb_total * 8), sznm = al((size_t)n_pairs * 4);
-  HFB_TRY(ctx->ensure_scratch(szA + szB + szna + sznb + szrb + szcb + sznm));
-  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->d_scratch);
+  const size_t need = szA + szB + szna + sznb + szrb + szcb + sznm;
+  uint8_t* base;
+  if (ws) {
+    HFB_REQUIRE(ctx, need <= ws_bytes, "matcher workspace too small");
+    base = reinterpret_cast<uint8_t*>(ws);
+  } else {
+    HFB_TRY(ctx->ensure_scratch(need));
+    base = reinterpret_cast<uint8_t*>(ctx->d_scratch);
+  }
   __half* A2 = reinterpret_cast<__half*>(base);
-  __half* B2 = reinterpret_cast<__half*>(base + szA);
+  __half* B2 = same ? A2 : reinterpret_cast<__half*>(base + szA);
   float* hna = reinterpret_cast<float*>(base + szA + szB);
-  float* hnb = reinterpret_cast<float*>(base + szA + szB + szna);
+  float* hnb = same ? hna : reinterpret_cast<float*>(base + szA + szB + szna);
   u64* rowbest = reinterpret_cast<u64*>(base + szA + szB + szna + sznb);
   u64* colbest = reinterpret_cast<u64*>(base + szA + szB + szna + sznb + szrb);
   int* nm = reinterpret_cast<int*>(base + szA + szB + szna + sznb + szrb + szcb);
   HFB_CUDA(ctx, cudaMemsetAsync(rowbest, 0, szrb + szcb + sznm, ctx->stream));
 
   const int l2 = (mode == 0);
-  hfb_launch(ctx, match_prep_kernel, ceil_div(na_total, 8), 256, 0, dA, na_total, A2, hna, 0, l2);
+  hfb_launch(ctx, match_prep_kernel, ceil_div(nmax, 8), 256, 0, dA, nmax, A2, hna, l2);
   HFB_CHECK_LAUNCH(ctx, "match_prep(A)");
-  hfb_launch(ctx, match_prep_kernel, ceil_div(nb_total, 8), 256, 0, dB, nb_total, B2, hnb, 1, l2);
-  HFB_CHECK_LAUNCH(ctx, "match_prep(B)");
+  if (!same) {
+    hfb_launch(ctx, match_prep_kernel, ceil_div(nb_total, 8), 256, 0, dB, nb_total, B2, hnb, l2);
+    HFB_CHECK_LAUNCH(ctx, "match_prep(B)");
+  }
 
   CUtensorMap tmA, tmB;
-  HFB_TRY(hfb_make_tmap_2d(ctx, &tmA, A2, MATCH_K, (uint64_t)na_total, MATCH_K * 2, 128));
-  HFB_TRY(hfb_make_tmap_2d(ctx, &tmB, B2, MATCH_K, (uint64_t)nb_total, MATCH_K * 2, MATCH_BN));
+  HFB_TRY(hfb_make_tmap_2d(ctx, &tmA, A2, MATCH_LD, (uint64_t)nmax, MATCH_LD * 2, 128));
+  HFB_TRY(hfb_make_tmap_2d(ctx, &tmB, B2, MATCH_LD, (uint64_t)(same ? nmax : nb_total), MATCH_LD * 2, MATCH_BN));
   GemmGeom g;
   gemm_fill_geom(g, max_a, max_b, MATCH_K, MATCH_BN, 0);
   g.pair_tab = d_pair_tab;
   g.n_pairs = n_pairs;
+  g.split3 = 1;
   g.stages = 3;   // 96 KB ring: two persistent CTAs per SM (256 TMEM columns each)
   g.epi_warp_bytes = 0;
   g.bias_bytes = 0;
@@ -219,12 +272,14 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
   static SmemOptIn optin;
   HFB_CUDA(ctx, optin.ensure(gemm_tc_kernel<EpiArgmax>, ctx->device, smem));
   EpiArgmax::Params ep{hna, hnb, rowbest, colbest};
-  hfb_launch(ctx, gemm_tc_kernel<EpiArgmax>, gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(4), smem, tmA, tmB, g, ep);
+  ctx->note("match_gemm_argmax", (double)(na_total + nb_total) * 1024.0, 2.0 * n_pairs * (double)max_a * max_b * 256.0);
+  hfb_launch(ctx, gemm_tc_kernel<EpiArgmax>, gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(EpiArgmax::kWarps), smem, tmA,
+             tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, "match_gemm_argmax");
 
-  dim3 fgrid(ceil_div(max_a, 8), n_pairs);
+  dim3 fgrid(ceil_div(std::max(max_a, pad_rows), 8), n_pairs);
   hfb_launch(ctx, match_finalize_kernel, fgrid, 256, 0, dA, dB, rowbest, colbest, d_pair_tab, n_pairs, mode, thr,
-                                                        d_match_idx, d_match_val, nm);
+                                                        d_match_idx, d_match_val, nm, pad_rows);
   HFB_CHECK_LAUNCH(ctx, "match_finalize");
   if (d_n_matches_out) *d_n_matches_out = nm;
   return HFB_OK;
@@ -405,7 +460,7 @@ extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t 
                                           const float* F, int32_t nf, const float* f_xy, const int32_t* f_level,
                                           const uint8_t* f_skip, const float* f_inv_sigma2, float chi2_max,
                                           int32_t* cand_idx, float* cand_dist, int32_t* cand_level) {
-  if (!ctx) return HFB_ERR_INVALID;
+  HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, nq >= 0 && nf >= 0, "negative size");
   HFB_REQUIRE(ctx, cand_idx && cand_dist && cand_level, "null output");
   for (long long i = 0; i < (long long)nq * PROJ_K; ++i) {
@@ -438,7 +493,7 @@ extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t 
   if (f_skip) HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fs, f_skip, (size_t)nf, cudaMemcpyHostToDevice, st));
   if (f_inv_sigma2) HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fi, f_inv_sigma2, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
   // scratch: Q' | F' | hnq | hnf | qwin | qlev | records
-  const size_t sQ = 0, sF = sQ + al((size_t)nq * MATCH_K * 2), s_hq = sF + al((size_t)nf * MATCH_K * 2),
+  const size_t sQ = 0, sF = sQ + al((size_t)nq * MATCH_LD * 2), s_hq = sF + al((size_t)nf * MATCH_LD * 2),
                s_hf = s_hq + al((size_t)nq * 4), s_qw = s_hf + al((size_t)nf * 4), s_ql = s_qw + al((size_t)nq * 16),
                s_rec = s_ql + al((size_t)nq * 8), s_total = s_rec + al((size_t)n_tiles * nq * sizeof(ProjRec));
   HFB_TRY(ctx->ensure_scratch(s_total));
@@ -452,9 +507,9 @@ extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t 
   float4* qwin = reinterpret_cast<float4*>(sc + s_qw);
   int2* qlev = reinterpret_cast<int2*>(sc + s_ql);
   ProjRec* rec = reinterpret_cast<ProjRec*>(sc + s_rec);
-  hfb_launch(ctx, match_prep_kernel, ceil_div(nq, 8), 256, 0, dQ, nq, Q2, hnq, 0, 1);
+  hfb_launch(ctx, match_prep_kernel, ceil_div(nq, 8), 256, 0, dQ, nq, Q2, hnq, 1);
   HFB_CHECK_LAUNCH(ctx, "match_prep(Q)");
-  hfb_launch(ctx, match_prep_kernel, ceil_div(nf, 8), 256, 0, dF, nf, F2, hnf, 1, 1);
+  hfb_launch(ctx, match_prep_kernel, ceil_div(nf, 8), 256, 0, dF, nf, F2, hnf, 1);
   HFB_CHECK_LAUNCH(ctx, "match_prep(F)");
   proj_pack_kernel<<<ceil_div(nq, 256), 256, 0, st>>>(reinterpret_cast<const float*>(io + o_uv),
                                                     reinterpret_cast<const float*>(io + o_r),
@@ -462,10 +517,11 @@ extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t 
                                                     reinterpret_cast<const int*>(io + o_mx), nq, qwin, qlev);
   HFB_CHECK_LAUNCH(ctx, "proj_pack");
   CUtensorMap tmA, tmB;
-  HFB_TRY(hfb_make_tmap_2d(ctx, &tmA, Q2, MATCH_K, (uint64_t)nq, MATCH_K * 2, 128));
-  HFB_TRY(hfb_make_tmap_2d(ctx, &tmB, F2, MATCH_K, (uint64_t)nf, MATCH_K * 2, MATCH_BN));
+  HFB_TRY(hfb_make_tmap_2d(ctx, &tmA, Q2, MATCH_LD, (uint64_t)nq, MATCH_LD * 2, 128));
+  HFB_TRY(hfb_make_tmap_2d(ctx, &tmB, F2, MATCH_LD, (uint64_t)nf, MATCH_LD * 2, MATCH_BN));
   GemmGeom g;
   gemm_fill_geom(g, nq, nf, MATCH_K, MATCH_BN, 0);
+  g.split3 = 1;
   g.stages = 3;
   g.epi_warp_bytes = 0;
   g.bias_bytes = 0;

@@ -94,6 +94,8 @@ SIGNATURES = {
                                              _f32p, _i32p, _u8p, _f32p, C.c_float, _i32p, _f32p, _i32p]),
     "hfb_match_consecutive_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float]),
     "hfb_fetch_matches": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _f32p, C.c_int32]),
+    "hfb_set_stream_mode": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hfb_reset_stream": (C.c_int, [C.c_void_p]),
     "hfb_distinctive_descriptors": (C.c_int, [C.c_void_p, _f32p, _i32p, C.c_int32, _i32p, _f32p]),
     "hfb_match_consecutive": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, _i32p, _f32p]),
     "hfb_profile_extract": (C.c_int, [C.c_void_p, C.c_int32, _i32p, C.c_float, C.c_char_p, C.c_size_t]),
@@ -355,6 +357,14 @@ class Context:
                                                        ptr(fi, _f32p) if fi is not None else None, float(chi2_max),
                                                        ptr(idx, _i32p), ptr(dist, _f32p), ptr(lvl, _i32p)))
         return idx, dist, lvl
+
+    def set_stream_mode(self, mode: int):
+        """0: a batch is B consecutive frames of one stream; 1: one frame of each of B streams (see hfnet_b200.h)."""
+        self.check(self.lib.hfb_set_stream_mode(self.handle, mode))
+
+    def reset_stream(self):
+        """Forget the previous frame of the streaming association (Tracking::Reset)."""
+        self.check(self.lib.hfb_reset_stream(self.handle))
 
     def match_consecutive_dev(self, n_images: int, mode: int, thr: float):
         self.check(self.lib.hfb_match_consecutive_dev(self.handle, n_images, mode, thr))

@@ -75,7 +75,13 @@ class Matcher:
         out = np.full(idx.shape[0], -1, np.int32)
         fmax = np.finfo(np.float32).max
         for i in range(idx.shape[0]):
-            free = [(dist[i, k], lvl[i, k], idx[i, k]) for k in range(idx.shape[1]) if idx[i, k] >= 0 and int(idx[i, k]) not in taken]
+            cand = [(dist[i, k], lvl[i, k], idx[i, k]) for k in range(idx.shape[1]) if idx[i, k] >= 0]
+            free = [c for c in cand if int(c[2]) not in taken]
+            if len(free) < 2 and len(cand) == idx.shape[1]:
+                # the device list may be truncated (features claimed by earlier map points took its slots): the
+                # reference would go on to the 5th, 6th ... nearest feature, so this window is re-scanned exactly
+                free = self._rescan_window(np.asarray(mp_desc, np.float32)[i], proj_uv[i], radius[i], min_level[i],
+                                           max_level[i], frame_desc, frame_xy, frame_octave, occupied, taken)
             if not free:
                 continue
             bd, bl, bi = free[0]
@@ -86,6 +92,26 @@ class Matcher:
                 out[i] = bi
                 taken.add(int(bi))
         return out
+
+    @staticmethod
+    def _rescan_window(q, uv, r, min_level, max_level, frame_desc, frame_xy, frame_octave, occupied, taken):
+        """Exact host scan of one search window (Frame::GetFeaturesInArea + Matcher::DescriptorDistance): the unclaimed
+        in-window features as (distance, octave, index), nearest first (ties: lower index)."""
+        fd = np.asarray(frame_desc, np.float32)
+        xy = np.asarray(frame_xy, np.float32)
+        octv = np.asarray(frame_octave, np.int32)
+        ok = (np.abs(xy[:, 0] - np.float32(uv[0])) < np.float32(r)) & (np.abs(xy[:, 1] - np.float32(uv[1])) < np.float32(r))
+        ok &= octv >= int(min_level)
+        if int(max_level) >= 0:
+            ok &= octv <= int(max_level)
+        if occupied is not None:
+            ok &= ~np.asarray(occupied, bool)
+        ii = [int(j) for j in np.flatnonzero(ok) if int(j) not in taken]
+        if not ii:
+            return []
+        dd = np.sqrt(((fd[ii] - np.asarray(q, np.float32)) ** 2).sum(1, dtype=np.float32)).astype(np.float32)
+        order = np.lexsort((np.asarray(ii), dd))
+        return [(dd[o], int(octv[ii[o]]), ii[o]) for o in order]
 
     def compute_distinctive_descriptors(self, observations):
         """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:331-400) for a batch of map points: ``observations``
@@ -203,8 +229,10 @@ class Matcher:
              mp_desc, mp_skip, kf_desc, kf_xy, kf_octave, th: float = 3.0, th_low: float = TH_LOW, chi2: float = 5.99):
         """Matcher::Fuse(pKF, vpMapPoints, th) (src/Matcher.cc:1046-1250), monocular, up to the map bookkeeping: geometry
         (projection, distance range, viewing angle, PredictScale) on the host, the gated window search on the device (every
-        map point is independent here, so the best in-window candidate is the answer).  Returns (best_idx, best_dist):
-        the keyframe feature each map point would be fused into, or -1."""
+        map point is independent here, so the best in-window candidate is the answer).  ``mp_min_dist`` / ``mp_max_dist``
+        are the raw mfMinDistance / mfMaxDistance: the range gate uses the invariance distances min / 1.2f and 1.2f * max
+        (MapPoint::GetMin/MaxDistanceInvariance, src/MapPoint.cc:504-516), PredictScale the raw maximum (:518-534).
+        Returns (best_idx, best_dist): the keyframe feature each map point would be fused into, or -1."""
         Tcw = np.asarray(Tcw, np.float32)
         fx, fy, cx, cy = [np.float32(v) for v in K]
         mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
@@ -218,8 +246,14 @@ class Matcher:
             d3 = np.sqrt(np.sum(PO * PO, axis=1, dtype=np.float32)).astype(np.float32)
             ratio = (np.asarray(mp_max_dist, np.float32) / d3).astype(np.float32)
             lvl = np.ceil(np.log(ratio) / np.float32(log_scale_factor))
+        if len(sf) <= 1:
+            lvl = np.zeros_like(d3)
+            min_inv, max_inv = np.zeros_like(d3), np.full_like(d3, 10000.0)
+        else:
+            min_inv = (np.asarray(mp_min_dist, np.float32) / np.float32(1.2)).astype(np.float32)
+            max_inv = (np.float32(1.2) * np.asarray(mp_max_dist, np.float32)).astype(np.float32)
         ok = ~np.asarray(mp_skip, bool) & ~(pc[:, 2] < 0) & (u >= mnx) & (u < mxx) & (v >= mny) & (v < mxy)
-        ok &= ~((d3 < np.asarray(mp_min_dist, np.float32)) | (d3 > np.asarray(mp_max_dist, np.float32)))
+        ok &= ~((d3 < min_inv) | (d3 > max_inv))
         ok &= ~(np.sum(PO * np.asarray(mp_normal, np.float32), axis=1, dtype=np.float32) < np.float32(0.5) * d3)
         M = P.shape[0]
         best_idx = np.full(M, -1, np.int32)

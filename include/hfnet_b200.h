@@ -188,9 +188,20 @@ int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t nq, const f
                                int32_t* cand_level);
 
 /* Tracking's frame-to-previous-frame descriptor association (the brute-force stage behind
- * Matcher::SearchByBoW / SearchForInitialization call sites, src/Tracking.cc:2030,1796) with the descriptors of the last
- * hfb_extract_batch* still resident in HBM: frame b is matched against frame (b-1) mod n_images.  No sync. */
+ * Matcher::SearchByBoW / SearchForInitialization call sites, src/Tracking.cc:2030,1796, which match the current frame
+ * against mLastFrame / the reference keyframe) with the descriptors of the last hfb_extract_batch* still resident in
+ * HBM.  The association is STREAMING: every frame is matched against the previous frame of its stream, also across
+ * calls -- the context keeps the descriptors it needs from the previous extraction.
+ *   stream mode 0 (default): a batch holds B consecutive frames of ONE stream; frame b is matched against frame b-1,
+ *                            frame 0 against the last frame of the previous call (a batch of 1 == the reference's loop).
+ *   stream mode 1:           a batch holds one frame of each of B independent streams (cameras); frame b is matched
+ *                            against frame b of the previous call (same batch size).
+ * A frame without a predecessor (first call, after hfb_reset_stream, after a mode change) has no matches.  No sync. */
 int hfb_match_consecutive_dev(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr);
+int hfb_set_stream_mode(hfb_ctx* ctx, int32_t mode);
+/* Forget the previous frame(s): Tracking::Reset / ResetActiveMap start again from an empty mLastFrame
+ * (src/Tracking.cc:3256-3330). */
+int hfb_reset_stream(hfb_ctx* ctx);
 /* Extraction and the association above as ONE call: the matching kernels only need the local features, so they (and,
  * for page-locked batch-contiguous outputs, the transfer of keypoints / descriptors / match rows) are enqueued on the
  * main stream while the global branch (layer_8 .. FC) is still computing on the side stream.  match_mode < 0 skips the
@@ -201,7 +212,7 @@ int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* images, int32_t 
 int hfb_extract_match_batch_dev(hfb_ctx* ctx, const uint8_t* d_images, int32_t n_images, const int32_t* n_per_level,
                                 float threshold, int32_t match_mode, float match_thr);
 /* Same, synchronous, results to host: match_idx / match_val are [n_images][kp_cap] rows (kp_cap = n_levels *
- * max_keypoints; row b holds frame b's matches into frame (b-1) mod n_images, -1 = unmatched).  This is the call
+ * max_keypoints; row b holds frame b's matches into the keypoints of its stream's previous frame, -1 = unmatched).  This is the call
  * Tracking makes right after Frame construction: the previous frame's descriptors are still resident, so nothing is
  * uploaded (Matcher::SearchByBoW with host cv::Mat descriptors re-reads both sets, src/Matcher.cc:220-263). */
 int hfb_match_consecutive(hfb_ctx* ctx, int32_t n_images, int32_t mode, float thr, int32_t* match_idx,

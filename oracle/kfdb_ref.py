@@ -24,8 +24,11 @@ import numpy as np
 
 def scores(q: np.ndarray, db: np.ndarray) -> np.ndarray:
     """max(0, 1 - ||q - d_i||) for every row of db.  q [4096], db [N,4096] -> f32[N]."""
-    diff = db.astype(np.float64) - q.astype(np.float64)[None, :]
-    nrm = np.sqrt((diff * diff).sum(axis=1)).astype(np.float32)
+    q64 = q.astype(np.float64)[None, :]
+    nrm = np.empty(db.shape[0], np.float32)
+    for r0 in range(0, db.shape[0], 4096):          # chunked: a 50 k-row database would need 1.6 GB in one piece
+        diff = db[r0:r0 + 4096].astype(np.float64) - q64
+        nrm[r0:r0 + 4096] = np.sqrt((diff * diff).sum(axis=1)).astype(np.float32)
     return np.maximum(np.float32(0), np.float32(1) - nrm).astype(np.float32)
 
 

@@ -121,6 +121,43 @@ def accept_projection(bd, bl, sd, sl, ratio: float, th_high: float = float(TH_HI
     return ok & ~reject
 
 
+def search_by_projection_map_points(Q: np.ndarray, uv: np.ndarray, radius: np.ndarray, min_level: np.ndarray,
+                                    max_level: np.ndarray, F: np.ndarray, f_xy: np.ndarray, f_level: np.ndarray,
+                                    occupied=None, ratio: float = 0.8, th_high: float = float(TH_HIGH)) -> np.ndarray:
+    """Matcher::SearchByProjection(F, vpMapPoints, th, ...) (src/Matcher.cc:40-210), the descriptor + bookkeeping part:
+    map points in order; window of Frame::GetFeaturesInArea (|x-u| < r, |y-v| < r, octave in [min, max], max < 0 =
+    unbounded, src/Frame.cc:659-725); features that already carry a map point with observations are skipped (:84-86) --
+    which includes every feature claimed by an earlier map point of this call (:137); best / second best with their
+    levels (:88-117); accepted iff best <= TH_HIGH and not (bestLevel == bestLevel2 and best > ratio * second) (:119-125).
+    Returns match[i] = feature index or -1."""
+    M, N = Q.shape[0], F.shape[0]
+    taken = np.zeros(N, bool) if occupied is None else np.array(occupied, bool, copy=True)
+    out = np.full(M, -1, np.int32)
+    fmax = np.finfo(np.float32).max
+    for i in range(M):
+        r = np.float32(radius[i])
+        ok = (np.abs(f_xy[:, 0] - np.float32(uv[i, 0])) < r) & (np.abs(f_xy[:, 1] - np.float32(uv[i, 1])) < r)
+        ok &= f_level >= min_level[i]
+        if max_level[i] >= 0:
+            ok &= f_level <= max_level[i]
+        bd, bl, bi, sd, sl = fmax, -1, -1, fmax, -1
+        for j in np.flatnonzero(ok):
+            if taken[j]:
+                continue
+            d = descriptor_distance(Q[i], F[j])
+            if d < bd:
+                sd, sl = bd, bl
+                bd, bl, bi = d, int(f_level[j]), int(j)
+            elif d < sd:
+                sd, sl = d, int(f_level[j])
+        if bd <= np.float32(th_high):
+            if bl == sl and bd > np.float32(ratio) * np.float32(sd):
+                continue
+            out[i] = bi
+            taken[bi] = True
+    return out
+
+
 def search_for_initialization(d1: np.ndarray, xy1: np.ndarray, oct1: np.ndarray, d2: np.ndarray, xy2: np.ndarray,
                               oct2: np.ndarray, prev_matched: np.ndarray, nnratio: float = 0.9, window: float = 100.0):
     """Matcher::SearchForInitialization (src/Matcher.cc:486-559), literal: level-0 keypoints of frame 1 in order, window
@@ -215,10 +252,13 @@ def fuse(Tcw: np.ndarray, Ow: np.ndarray, K, bounds, scale_factors, log_scale_fa
          th_low: float = float(TH_LOW), chi2: float = 5.99):
     """Matcher::Fuse(pKF, vpMapPoints, th) (src/Matcher.cc:1046-1250), monocular, up to the map bookkeeping: for every map
     point (``mp_skip`` = null / bad / already in the keyframe) -- positive depth, inside the image, distance within the
-    scale-invariance range, viewing angle below 60 degrees (PO . Pn >= 0.5 dist), predicted level
-    (MapPoint::PredictScale, src/MapPoint.cc:497-514: ceil(log(maxDistance / dist) / logScaleFactor), clamped), window
+    scale-invariance range [GetMinDistanceInvariance, GetMaxDistanceInvariance] = [mfMinDistance / 1.2f, 1.2f *
+    mfMaxDistance] (src/MapPoint.cc:504-516; [0, 10000] for a single-level pyramid), viewing angle below 60 degrees
+    (PO . Pn >= 0.5 dist), predicted level (MapPoint::PredictScale, src/MapPoint.cc:518-534:
+    ceil(log(mfMaxDistance / dist) / logScaleFactor) on the RAW mfMaxDistance, clamped; 0 for a single level), window
     th * scale[level], keyframe features of level [pred-1, pred] that pass the reprojection gate
     e2 * invLevelSigma2 <= chi2, least descriptor distance, accepted iff <= TH_LOW.
+    ``mp_min_dist`` / ``mp_max_dist`` are the map points' raw mfMinDistance / mfMaxDistance.
     Returns (best_idx int32[M] or -1, best_dist f32[M]): the feature each map point would be fused into (the reference
     then Replace()s or AddObservation()s, which is map data-model code outside the path)."""
     fx, fy, cx, cy = [np.float32(v) for v in K]
@@ -243,13 +283,21 @@ def fuse(Tcw: np.ndarray, Ow: np.ndarray, K, bounds, scale_factors, log_scale_fa
             continue
         PO = (pw - Ow.astype(np.float32)).astype(np.float32)
         dist3d = np.float32(np.sqrt(np.sum(PO * PO, dtype=np.float32)))
-        if dist3d < mp_min_dist[i] or dist3d > mp_max_dist[i]:
+        if n_levels <= 1:
+            min_inv, max_inv = np.float32(0), np.float32(10000)
+        else:
+            min_inv = np.float32(mp_min_dist[i]) / np.float32(1.2)
+            max_inv = np.float32(1.2) * np.float32(mp_max_dist[i])
+        if dist3d < min_inv or dist3d > max_inv:
             continue
         if np.float32(PO @ mp_normal[i].astype(np.float32)) < np.float32(0.5) * dist3d:
             continue
-        ratio = np.float32(mp_max_dist[i]) / dist3d
-        lvl = int(np.ceil(np.log(ratio) / np.float32(log_scale_factor)))
-        lvl = min(max(lvl, 0), n_levels - 1)
+        if n_levels <= 1:
+            lvl = 0
+        else:
+            ratio = np.float32(mp_max_dist[i]) / dist3d
+            lvl = int(np.ceil(np.log(ratio) / np.float32(log_scale_factor)))
+            lvl = min(max(lvl, 0), n_levels - 1)
         r = np.float32(th) * sf[lvl]
         ok = (np.abs(kf_xy[:, 0] - u) < r) & (np.abs(kf_xy[:, 1] - v) < r)
         for j in np.flatnonzero(ok):

@@ -105,8 +105,8 @@ def test_batch_equals_single(ctx_euroc, oracle_euroc):
     assert not np.array_equal(two[0]["global_descriptor"], two[1]["global_descriptor"])
 
 
-@pytest.mark.parametrize("H,W,n_feat,thr", [(240, 376, 675, 0.01), (512, 512, 850, 0.02)],
-                         ids=["euroc-4level-small", "tumvi-512x512-4level"])
+@pytest.mark.parametrize("H,W,n_feat,thr", [(240, 376, 675, 0.01), (512, 512, 850, 0.02), (480, 752, 675, 0.01)],
+                         ids=["euroc-4level-small", "tumvi-512x512-4level", "euroc-752x480-4level-675"])
 def test_multilevel_pyramid(native_lib, weights_blob, weights_dict, H, W, n_feat, thr):
     """4-level configurations: EuRoC (Examples/Monocular/EuRoC.yaml:67-80 -> 675 features, 1.2, 4 levels; smaller frame)
     and the TUM-VI shape of BASELINE.json configs[4] (Examples/Monocular/TUM-VI.yaml:66-67 -> 850 features -> 274 / 228 /
@@ -115,6 +115,9 @@ def test_multilevel_pyramid(native_lib, weights_blob, weights_dict, H, W, n_feat
     budgets = select_ref.features_per_level(n_feat, 4, 1.2)
     if n_feat == 850:
         assert budgets == [274, 228, 190, 158]
+    if (H, W, n_feat) == (480, 752, 675):       # BASELINE.json configs[2]'s extraction shape (EuRoC.yaml:67-80)
+        assert budgets == [217, 181, 151, 126]
+        assert [im.shape for im in select_ref.compute_pyramid(img, 4, 1.2)] == [(480, 752), (400, 627), (333, 522), (278, 435)]
     with Context(height=H, width=W, n_levels=4, scale_factor=1.2, max_keypoints=1000, max_batch=1) as ctx:
         ctx.load_weights(weights_blob)
         out = ctx.extract(img, budgets, thr)
@@ -169,38 +172,122 @@ def test_pinned_zero_copy_path_equals_staged_path(ctx_euroc, oracle_euroc):
     assert block["descriptors"].shape == (2, 1000, 256)
 
 
-def test_consecutive_match_on_resident_descriptors(ctx_euroc):
-    """hfb_match_consecutive: frame b vs frame b-1 on the descriptors the extraction left in HBM == the oracle's
-    cv::BFMatcher(NORM_L2, crossCheck) + dist < 0.6 (src/Matcher.cc:220-263) on the descriptors returned to the host."""
+def _check_association(A, Bd, idx_row, tag):
+    """Device association row == the oracle's cv::BFMatcher(NORM_L2, crossCheck) + dist < 0.6 (src/Matcher.cc:220-263) on the
+    descriptors returned to the host: identical sets, except pairs sitting on the decision boundaries within the fp32
+    noise of the two distance evaluations (|dist - TH_LOW| or the gap to the runner-up below 5e-6)."""
     from oracle import match_ref
+    ia, ib, dist = match_ref.search_by_bow(A, Bd, 0.6)
+    got = {(int(i), int(idx_row[i])) for i in np.flatnonzero(idx_row[:len(A)] >= 0)}
+    want = set(zip(ia.tolist(), ib.tolist()))
+    for i, j in got ^ want:
+        dm = match_ref.l2_distance_matrix(A[i:i + 1], Bd)[0]
+        dcol = match_ref.l2_distance_matrix(A, Bd[j:j + 1])[:, 0]
+        gap_row = np.partition(dm, 1)[1] - np.partition(dm, 1)[0]
+        gap_col = np.partition(dcol, 1)[1] - np.partition(dcol, 1)[0]
+        assert abs(dm[j] - 0.6) < 5e-6 or gap_row < 5e-6 or gap_col < 5e-6, f"{tag}: pair {(i, j)} differs"
+    assert len(got ^ want) <= 2, tag
+    assert (idx_row[len(A):] < 0).all(), tag
+    return got
+
+
+def test_streaming_association_on_resident_descriptors(ctx_euroc):
+    """hfb_match_consecutive / hfb_extract_match_batch: every frame is matched against the previous frame of the stream
+    (src/Tracking.cc:2030,2167 match against mLastFrame) on the descriptors the extraction left in HBM -- frame b-1 of
+    the same call, or the last frame of the PREVIOUS call for frame 0; the first frame of a stream has no matches."""
     base = weights.synthetic_image(480, 752, seed=7)
-    imgs = [base, np.roll(base, (3, 5), axis=(0, 1))]
-    feats = ctx_euroc.extract_batch(imgs, [1000], 0.01)
+    imgs = [np.roll(base, (3 * i, 5 * i), axis=(0, 1)) for i in range(5)]
+    ctx_euroc.reset_stream()
+    feats = ctx_euroc.extract_batch(imgs[:2], [1000], 0.01)
     idx, val = ctx_euroc.match_consecutive(2, 0, 0.6)
     assert idx.shape == (2, ctx_euroc.kp_cap)
+    assert (idx[0] < 0).all(), "the first frame of a stream has no previous frame"
+    got = _check_association(feats[1]["descriptors"], feats[0]["descriptors"], idx[1], "call 1 frame 1")
+    assert len(got) > 50, "shifted copies of one frame should share many keypoints"
     for b in range(2):
-        A, Bd = feats[b]["descriptors"], feats[(b - 1) % 2]["descriptors"]
-        ia, ib, dist = match_ref.search_by_bow(A, Bd, 0.6)
-        got = {(int(i), int(idx[b, i])) for i in np.flatnonzero(idx[b, :len(A)] >= 0)}
-        want = set(zip(ia.tolist(), ib.tolist()))
-        # identical sets, except pairs sitting on the decision boundaries within the fp32 noise of the two distance
-        # evaluations (|dist - TH_LOW| or the gap to the runner-up below 5e-6)
-        for i, j in got ^ want:
-            dm = match_ref.l2_distance_matrix(A[i:i + 1], Bd)[0]
-            dcol = match_ref.l2_distance_matrix(A, Bd[j:j + 1])[:, 0]
-            gap_row = np.partition(dm, 1)[1] - np.partition(dm, 1)[0]
-            gap_col = np.partition(dcol, 1)[1] - np.partition(dcol, 1)[0]
-            assert abs(dm[j] - 0.6) < 5e-6 or gap_row < 5e-6 or gap_col < 5e-6, f"frame {b}: pair {(i, j)} differs"
-        assert len(got ^ want) <= 2, f"frame {b}"
-        assert len(got) > 50, "shifted copies of one frame should share many keypoints"
-        one_idx, one_val = ctx_euroc.fetch_matches(b, len(A))
-        assert np.array_equal(one_idx, idx[b, :len(A)]) and np.array_equal(one_val, val[b, :len(A)])
-        assert (idx[b, len(A):] < 0).all()
-    # the one-call form (association enqueued inside the extraction, ahead of the global branch) gives the same rows,
-    # through pageable and through page-locked outputs
-    for pinned in (False, True):
-        feats2, idx2, val2 = ctx_euroc.extract_match_batch(imgs, [1000], 0.01, 0, 0.6, pinned=pinned)
-        assert np.array_equal(idx2, idx) and np.array_equal(val2, val), f"pinned={pinned}"
-        for b in range(2):
-            for k in ("x", "y", "response", "descriptors", "global_descriptor"):
-                assert np.array_equal(feats2[b][k], feats[b][k]), (pinned, b, k)
+        n = len(feats[b]["x"])
+        one_idx, one_val = ctx_euroc.fetch_matches(b, n)
+        assert np.array_equal(one_idx, idx[b, :n]) and np.array_equal(one_val, val[b, :n])
+    # second call, one-call form (association enqueued inside the extraction, ahead of the global branch), through
+    # pageable and through page-locked outputs: frame 0 continues from the previous call's last frame
+    prev_last = feats[1]["descriptors"].copy()
+    for pinned, pair in ((False, imgs[2:4]), (True, imgs[3:5])):
+        feats2, idx2, val2 = ctx_euroc.extract_match_batch(pair, [1000], 0.01, 0, 0.6, pinned=pinned)
+        g0 = _check_association(feats2[0]["descriptors"], prev_last, idx2[0], f"pinned={pinned} frame 0 vs previous call")
+        g1 = _check_association(feats2[1]["descriptors"], feats2[0]["descriptors"], idx2[1], f"pinned={pinned} frame 1")
+        assert len(g0) > 50 and len(g1) > 50
+        prev_last = feats2[1]["descriptors"].copy()
+    # after a reset the history is gone
+    ctx_euroc.reset_stream()
+    _, idx3, _ = ctx_euroc.extract_match_batch(imgs[:2], [1000], 0.01, 0, 0.6)
+    assert (idx3[0] < 0).all() and (idx3[1] >= 0).sum() > 50
+
+
+def test_streaming_association_batch_of_one_and_per_slot_streams(native_lib, weights_blob):
+    """A batch of one is the reference's per-frame loop (frame t vs frame t-1 of the previous call); stream mode 1 keeps
+    one history per batch slot (BASELINE.json configs[4]: independent camera streams)."""
+    H, W = 240, 376
+    base = [weights.synthetic_image(H, W, seed=s, n_corners=120) for s in (3, 4)]
+    seq = [[np.roll(b, (2 * i, 3 * i), axis=(0, 1)) for i in range(3)] for b in base]
+    with Context(height=H, width=W, n_levels=1, max_keypoints=600, max_batch=2, with_global=True) as ctx:
+        ctx.load_weights(weights_blob)
+        prev = None
+        for t in range(3):
+            f, idx, _ = ctx.extract_match_batch([seq[0][t]], [600], 0.01, 0, 0.6)
+            if prev is None:
+                assert (idx[0] < 0).all()
+            else:
+                assert len(_check_association(f[0]["descriptors"], prev, idx[0], f"B=1 frame {t}")) > 20
+            prev = f[0]["descriptors"].copy()
+        ctx.set_stream_mode(1)
+        prev = None
+        for t in range(3):
+            f, idx, _ = ctx.extract_match_batch([seq[0][t], seq[1][t]], [600], 0.01, 0, 0.6, pinned=(t == 2))
+            for b in range(2):
+                if prev is None:
+                    assert (idx[b] < 0).all()
+                else:
+                    assert len(_check_association(f[b]["descriptors"], prev[b], idx[b], f"stream {b} frame {t}")) > 20
+            prev = [f[b]["descriptors"].copy() for b in range(2)]
+
+
+def test_c5_tumvi_stream_masked_best2(native_lib, weights_blob):
+    """BASELINE.json configs[4] per stream: 512 x 512, 4 levels, 850 keypoints, threshold 0.02; frame t against frame t-1
+    as the masked best-2 search of SearchByProjection (windows 15 * 1.2^octave around the previous keypoints, octaves
+    [o-1, o+1], src/Matcher.cc:1574-1650) on the extracted descriptors == the oracle's best / second best over the same
+    windows (src/Matcher.cc:78-117)."""
+    from oracle import match_ref
+    H = W = 512
+    base = weights.synthetic_image(H, W, seed=12, n_corners=250)
+    frames = [base, np.roll(base, (2, 3), axis=(0, 1))]
+    budgets = select_ref.features_per_level(850, 4, 1.2)
+    with Context(height=H, width=W, n_levels=4, scale_factor=1.2, max_keypoints=850, max_batch=1) as ctx:
+        ctx.load_weights(weights_blob)
+        prev = {k: np.array(v, copy=True) for k, v in ctx.extract(frames[0], budgets, 0.02).items() if k != "n_per_level"}
+        cur = ctx.extract(frames[1], budgets, 0.02)
+        assert len(prev["x"]) > 300 and len(cur["x"]) > 300
+        uv = np.stack([prev["x"] + 3.0, prev["y"] + 2.0], 1).astype(np.float32)       # predicted positions in frame t
+        sf = (np.float32(1.2) ** prev["octave"]).astype(np.float32)
+        rad = (np.float32(15.0) * sf).astype(np.float32)
+        mn, mx = prev["octave"] - 1, prev["octave"] + 1
+        fxy = np.stack([cur["x"], cur["y"]], 1).astype(np.float32)
+        idx, dist, lvl = ctx.match_projection(prev["descriptors"], uv, rad, mn, mx, cur["descriptors"], fxy, cur["octave"])
+        ptr, cand = [0], []
+        for i in range(len(uv)):
+            ok = (np.abs(fxy[:, 0] - uv[i, 0]) < rad[i]) & (np.abs(fxy[:, 1] - uv[i, 1]) < rad[i]) & \
+                 (cur["octave"] >= mn[i]) & (cur["octave"] <= mx[i])
+            cand.extend(np.flatnonzero(ok).tolist())
+            ptr.append(len(cand))
+        bi, bd, bl, sd, sl = match_ref.best2_masked(prev["descriptors"], cur["descriptors"], np.array(ptr),
+                                                    np.array(cand, np.int64), cur["octave"])
+        has = bi >= 0
+        assert has.sum() > 200, "most keypoints of a shifted frame should have candidates in their windows"
+        tie = np.abs(bd - sd) < 2e-6
+        assert np.array_equal(idx[has & ~tie, 0], bi[has & ~tie])
+        assert np.abs(dist[has, 0] - bd[has]).max() <= 2e-6
+        two = has & (sd < np.finfo(np.float32).max)
+        assert np.abs(dist[two, 1] - sd[two]).max() <= 2e-6
+        assert np.array_equal(lvl[has & ~tie, 0], bl[has & ~tie])
+        assert (idx[~has] == -1).all()
+        # the shifted copy re-finds its keypoints: the best candidate is a close descriptor for most of them
+        assert (bd[has] < 0.6).mean() > 0.5

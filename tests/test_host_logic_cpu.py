@@ -212,6 +212,37 @@ def test_search_by_projection_last_frame_replay_equals_oracle(k):
     assert n_ref > 100 and n_got == n_ref and np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("k", [4, 2])
+def test_search_by_projection_contended_window_rescans_exactly(k):
+    """More map points than the device's top-k contend for ONE window: once the candidate list of a point is
+    eaten by earlier claims the host mirror must re-scan the window exactly -- the reference simply walks on to the 5th,
+    6th ... nearest feature (src/Matcher.cc:78-125) -- instead of dropping the point or passing the ratio test against
+    FLT_MAX."""
+    from hfnet_slam_b200.matcher import Matcher
+    from oracle import match_ref
+    rng = np.random.default_rng(11)
+    nq, nf = 10, 14
+    proto = rng.normal(size=256).astype(np.float32)
+    Q = (proto + 0.05 * rng.normal(size=(nq, 256))).astype(np.float32)
+    F = (proto + 0.05 * rng.normal(size=(nf, 256))).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    F /= np.linalg.norm(F, axis=1, keepdims=True)
+    uv = np.full((nq, 2), 100.0, np.float32)
+    fxy = (100.0 + rng.uniform(-5, 5, (nf, 2))).astype(np.float32)
+    rad = np.full(nq, 15.0, np.float32)
+    flev = rng.integers(0, 2, nf).astype(np.int32)
+    mn, mx = np.zeros(nq, np.int32), np.full(nq, -1, np.int32)
+    occupied = np.zeros(nf, bool)
+    occupied[3] = True
+    for ratio, least in ((0.9, 4), (1.0, 9)):
+        got = Matcher(_FakeProjectionCtx(k)).search_by_projection(Q, uv, rad, mn, mx, F, fxy, flev, occupied=occupied,
+                                                                  ratio=ratio)
+        ref = match_ref.search_by_projection_map_points(Q, uv, rad, mn, mx, F, fxy, flev, occupied=occupied, ratio=ratio)
+        assert np.array_equal(got, ref), ratio
+        assert (ref >= 0).sum() >= least, "the contending points should still find free features"
+        assert len(set(ref[ref >= 0].tolist())) == (ref >= 0).sum()
+
+
 def test_fuse_host_geometry_equals_oracle():
     """Host side of Matcher::Fuse (projection, distance range, viewing angle, PredictScale, gate parameters) over the numpy
     stand-in for the device search == the literal restatement (src/Matcher.cc:1046-1250)."""
@@ -243,6 +274,40 @@ def test_fuse_host_geometry_equals_oracle():
     ref_i, _ = match_ref.fuse(**sc)
     assert (ref_i >= 0).sum() > 40
     assert np.array_equal(got_i, ref_i)
+    # single-level pyramid: PredictScale returns 0 and the invariance range is [0, 10000] (src/MapPoint.cc:504-534)
+    one = dict(sc, scale_factors=sc["scale_factors"][:1], kf_octave=np.zeros_like(sc["kf_octave"]))
+    g1, _ = Matcher(Ctx()).fuse(**one)
+    r1, _ = match_ref.fuse(**one)
+    assert np.array_equal(g1, r1) and (r1 >= 0).sum() > 40
+
+
+def test_fuse_distance_gate_and_predicted_level_pins():
+    """Pins of the oracle's Fuse geometry against hand-evaluated reference expressions: the range gate uses
+    GetMin/MaxDistanceInvariance = mfMinDistance / 1.2f and 1.2f * mfMaxDistance, PredictScale the RAW mfMaxDistance
+    (src/MapPoint.cc:504-534) -- with scaleFactor 1.2 the two choices differ by exactly one level."""
+    from oracle import match_ref
+    sf = (1.2 ** np.arange(4)).astype(np.float32)
+    Tcw = np.concatenate([np.eye(3, dtype=np.float32), np.zeros((3, 1), np.float32)], 1)
+    Ow = np.zeros(3, np.float32)
+    K, bounds = (400.0, 400.0, 320.0, 240.0), (0.0, 640.0, 0.0, 480.0)
+    desc = np.zeros((1, 256), np.float32); desc[0, 0] = 1
+
+    def run(dist3d, min_d, max_d, kf_level):
+        pos = np.array([[0.0, 0.0, dist3d]], np.float32)
+        return match_ref.fuse(Tcw, Ow, K, bounds, sf, float(np.log(1.2)), pos, np.array([[0, 0, 1.0]], np.float32),
+                              np.array([min_d], np.float32), np.array([max_d], np.float32), desc, np.zeros(1, bool), desc,
+                              np.array([[320.0, 240.0]], np.float32), np.array([kf_level], np.int32))[0][0]
+
+    # dist 11 > mfMaxDistance 10 but < 1.2 * 10: inside the invariance range; ratio < 1 -> level clamps to 0
+    assert run(11.0, 4.0, 10.0, 0) == 0
+    assert run(12.5, 4.0, 10.0, 0) == -1                   # beyond 1.2 * mfMaxDistance
+    assert run(3.5, 4.0, 10.0, 3) == 0                     # >= mfMinDistance / 1.2 = 3.33; ratio 2.857 -> ceil(5.76) -> clamp 3
+    assert run(3.2, 4.0, 10.0, 3) == -1                    # below mfMinDistance / 1.2
+    # dist 9: ratio 10/9 -> ceil(log(1.111)/log(1.2)) = ceil(0.578) = 1 -> octaves [0, 1] pass, 2 does not
+    assert run(9.0, 4.0, 10.0, 1) == 0 and run(9.0, 4.0, 10.0, 0) == 0 and run(9.0, 4.0, 10.0, 2) == -1
+    # with the invariance maximum (12) in PredictScale the level would be ceil(log(12/9)/log 1.2) = 2: octave 2 would pass
+
+
 
 
 def test_onnx_initialiser_import_round_trip(tmp_path):

@@ -97,3 +97,58 @@ def test_shard_records_merge_to_global_set(small_ctx):
     assert not overflow and m_best == best
     assert list(m_ids) == list(cand)
     assert np.array_equal(m_scores, scores)
+
+
+@pytest.fixture(scope="module")
+def c4_db():
+    """BASELINE.json configs[3] / SURVEY.md 8(d)-C4: 50 000 x 4096 fp32 unit rows, 200 planted near-duplicates, queries =
+    planted rows + noise."""
+    return synthetic.keyframe_db(50000, 4096, n_planted=200, seed=2, n_queries=64)
+
+
+def _check_candidates(cand, best, sc_ref, ids):
+    sel, best_ref = kfdb_ref.candidate_set(sc_ref, 0.8)
+    assert abs(best - best_ref) <= TOL
+    thr = 0.8 * best_ref
+    sure = {int(ids[i]) for i in sel if sc_ref[i] > thr + 5e-6}
+    maybe = {int(ids[i]) for i in np.flatnonzero(np.abs(sc_ref - thr) <= 5e-6)}
+    got = set(int(c) for c in cand)
+    assert sure <= got <= (sure | maybe), f"{len(got)} vs {len(sure)}"
+
+
+def test_c4_50k_rows_single_query(small_ctx, c4_db):
+    db, q, qi = c4_db
+    n = db.shape[0]
+    ids = np.arange(n, dtype=np.int64)
+    kf = KeyFrameDatabase(small_ctx, capacity=n)
+    kf.add_many(ids, db)
+    for k in (0, 17):
+        cand, scores, best = kf.query(q[k])
+        sc_ref = kfdb_ref.scores(q[k], db)
+        _check_candidates(cand, best, sc_ref, ids)
+        assert int(qi[k]) in set(int(c) for c in cand), "the planted source row is a candidate"
+        assert np.abs(kf.scores_of(ids[::97]) - sc_ref[::97]).max() <= TOL
+    kf.close()
+
+
+def test_c4_50k_rows_eight_way_shard_merge(small_ctx, c4_db):
+    """Row-shard by id % 8, one fixed-size record per shard, merged == the unsharded candidate set at the full C4 size."""
+    from hfnet_slam_b200.keyframe_database import merge_shard_records
+    db, q, _ = c4_db
+    n, world = db.shape[0], 8
+    ids = np.arange(n, dtype=np.int64)
+    shards = []
+    for r in range(world):
+        sh = KeyFrameDatabase(small_ctx, capacity=n // world + 1)
+        m = ids % world == r
+        sh.add_many(ids[m], db[m])
+        shards.append(sh)
+    for k in (0, 33):
+        sc_ref = kfdb_ref.scores(q[k], db)
+        recs = [sh.query_shard(q[k], k=64) for sh in shards]
+        m_ids, m_scores, m_best, overflow = merge_shard_records(recs, rel=0.8, floor=0.0)
+        assert not overflow
+        _check_candidates(m_ids, m_best, sc_ref, ids)
+        assert np.abs(m_scores - sc_ref[m_ids]).max() <= TOL
+    for sh in shards:
+        sh.close()

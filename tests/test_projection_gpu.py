@@ -64,21 +64,7 @@ def test_search_by_projection_sequential_claims(small_ctx):
     occupied = np.zeros(900, bool); occupied[::17] = True                               # features that already have a map point
     got = Matcher(small_ctx).search_by_projection(Q, uv, rad, mn, mx, F, fxy, flev, occupied=occupied, ratio=0.8)
     # restatement of src/Matcher.cc:78-125 with the occupancy test of :84-86
-    taken = occupied.copy()
-    exp = np.full(700, -1, np.int32)
-    fmax = np.finfo(np.float32).max
-    for i in range(700):
-        bd, bl, bi, sd, sl = fmax, -1, -1, fmax, -1
-        for j in _window(uv[i, 0], uv[i, 1], rad[i], mn[i], mx[i], fxy, flev, skip=taken):
-            d = np.float32(np.sqrt(((Q[i].astype(np.float64) - F[j].astype(np.float64)) ** 2).sum()))
-            if d < bd:
-                sd, sl = bd, bl
-                bd, bl, bi = d, flev[j], j
-            elif d < sd:
-                sd, sl = d, flev[j]
-        if bd <= np.float32(0.75) and not (bl == sl and bd > np.float32(0.8) * sd):
-            exp[i] = bi
-            taken[bi] = True
+    exp = match_ref.search_by_projection_map_points(Q, uv, rad, mn, mx, F, fxy, flev, occupied=occupied, ratio=0.8)
     assert np.array_equal(got, exp), f"rows {np.flatnonzero(got != exp)[:10]}"
     assert got[3] >= 0 and got[10] != got[3]
     assert (got >= 0).sum() > 100
