@@ -57,85 +57,288 @@ __device__ __forceinline__ u64 pack_best(float key, int idx) {
   return ((u64)f2ord(key) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)idx);
 }
 
-// Column maxima of a warp's 32 rows for 32 columns at once: lane L enters with its row's keys k[0..31] (0 = invalid)
-// and leaves with the maximum of column L over the 32 lanes in k[0] (recursive halving: at offset o a lane keeps the
-// half of its columns whose bit o matches its own lane bit and trades the other half with lane ^ o).
-__device__ __forceinline__ uint32_t warp_colmax32(uint32_t (&k)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const uint32_t send = up ? k[i] : k[i + o];
-      const uint32_t keep = up ? k[i + o] : k[i];
-      const uint32_t got = __shfl_xor_sync(0xffffffffu, send, o);
-      k[i] = keep > got ? keep : got;
-    }
-  }
-  return k[0];
+// ---- the matcher's own tensor-core kernel -------------------------------------------------------------------------------
+// One CTA per SM walks work units (pair, 128-row block of A, chunk of B's 128-column tiles).  The A block lives in shared
+// memory for the whole unit (8 swizzled k-blocks: hi 0..3 | lo 0..3 = 128 KB) and only B streams through a 5-slot ring,
+// so a 128 x 128 tile costs 128 KB of L2 traffic instead of the 384 KB of a both-operands-streamed split product (which
+// pins the kernel to the L2 -> SM path, not the tensor pipe).  Per B k-block pair the issuer runs
+//     hi_k: D += A_hi[k] . B_hi[k],  D += A_lo[k] . B_hi[k]          lo_k: D += A_hi[k] . B_lo[k]
+// (12 k-block products from 8 loads).  Roles: warp 0 TMA producer, warp 1 UMMA issuer + TMEM owner (two accumulator
+// stages), warps 2..9 epilogue: warp (lane group g, half h) owns rows 32 g .. 32 g + 31 and columns 64 h .. 64 h + 63 of
+// the tile.  Row arg-max: thread-local scan.  Column arg-max: every warp transposes 32 x 8 key blocks through a private
+// padded shared-memory patch (2 x 16-byte stores per thread, conflict-free), then lane (c, h) scans rows 8 h .. 8 h + 7
+// of column c and two shuffles join the four row groups -- no warp reductions.  Both land in packed 64-bit atomicMax
+// (key << 32 | ~index: lowest index wins ties).  The patches are small on purpose: what bounds the kernel is the bytes
+// of B in flight per SM (ring capacity / TMA latency), so shared memory goes to the ring first.
+#define MAR_THREADS 320
+#define MAR_A_BYTES (8 * 16384)
+#define MAR_B_SLOTS 5
+#define MAR_PATCH_WORDS (32 * 12 + 24)
+#define MAR_SMEM (1024 + MAR_A_BYTES + MAR_B_SLOTS * 16384 + 8 * MAR_PATCH_WORDS * 4 + 2 * MATCH_BN * 4 + 256)
+
+struct MatchGeom {
+  int n_pairs, m_tiles, n_tiles, chunk_tiles, n_chunks, total_units;
+  const int* pair_tab;   // device int[4][n_pairs]: a_off | a_cnt | b_off | b_cnt
+  uint32_t idesc;
+};
+
+struct MatchUnit {
+  bool valid;
+  int a_off, a_cnt, b_off, b_cnt, m0, nt0, nt1;   // rows of A: a_off + m0 .. ; B tiles nt0 .. nt1-1
+};
+
+__device__ __forceinline__ MatchUnit match_decode(const MatchGeom& g, int unit) {
+  MatchUnit u;
+  const int per = g.m_tiles * g.n_chunks;
+  const int pr = unit / per;
+  const int rem = unit - pr * per;
+  const int mt = rem / g.n_chunks, ch = rem - mt * g.n_chunks;
+  u.a_off = g.pair_tab[pr];
+  u.a_cnt = g.pair_tab[g.n_pairs + pr];
+  u.b_off = g.pair_tab[2 * g.n_pairs + pr];
+  u.b_cnt = g.pair_tab[3 * g.n_pairs + pr];
+  u.m0 = mt * 128;
+  u.nt0 = ch * g.chunk_tiles;
+  const int nt_valid = (u.b_cnt + MATCH_BN - 1) / MATCH_BN;
+  u.nt1 = min(min(u.nt0 + g.chunk_tiles, g.n_tiles), nt_valid);
+  u.valid = u.m0 < u.a_cnt && u.nt0 < u.nt1;
+  return u;
 }
 
-// ---- epilogue: per-row and per-column arg-max of key = s - 0.5*|other|^2 (L2 mode) or s (cosine mode) ------------
-struct EpiArgmax {
-  static constexpr int kWarps = 8;
-  struct Params {
-    const float* hna;  // [na_total] 0.5*|a|^2 (0 in cosine mode)
-    const float* hnb;  // [nb_total]
-    u64* rowbest;      // [na_total], zero-initialised
-    u64* colbest;      // [nb_total], zero-initialised
-  };
-  static __device__ __forceinline__ const float* bias(const Params&) { return nullptr; }
-  static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
-    __shared__ float s_hnb[MATCH_BN];
-    const int lane = threadIdx.x & 31;
-    const int et = (int)threadIdx.x - 64;           // 0..255 among the epilogue threads
-    const int ncols = min(g.BN, tr.n_cnt - tr.n0);  // valid columns of this tile
-    if (et < MATCH_BN) s_hnb[et] = et < ncols ? __ldg(p.hnb + tr.b_off + tr.n0 + et) : 0.f;
-    epi_bar_sync_n<32 * kWarps>();
-    const float my_hna = tr.valid ? __ldg(p.hna + tr.row) : 0.f;
-    const int warp_row0 = tr.row_local - lane;      // problem-local row of this warp's lane 0
-    float best = -INFINITY;
-    int best_j = 0;
-    const int cbeg = tr.sub * (MATCH_BN / 2);       // this warp's half of the tile's columns
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + MATCH_BN / 2; c0 += 32) {
-      if (c0 >= ncols) break;  // warp-uniform
-      uint32_t r[32];
-      tc::tmem_ld32(tr.taddr + (uint32_t)c0, r);
-      tc::tmem_ld_wait();
-      uint32_t k[32];
+// Epilogue work of one warp on a 32-row x 32-column block of the accumulator (r = this thread's row): one common key
+// k = s - 0.5|b_j|^2 - 0.5|a_i|^2 (= -0.5 dist^2; the norm terms are 0 in cosine mode) serves both arg-maxes -- the
+// per-row term does not change a row's ordering, the per-column term not a column's.  Rows / columns outside the pair
+// carry +inf in their norm term, so their keys are -inf (or NaN) and never win a strict '>' -- no masks in the loops.
+// Row pass: thread-local, ascending columns, strict '>' (lowest index on ties).  Column pass: 8 columns at a time through
+// the warp's shared-memory patch (32 x 8 transposition), lane (c, h) scans rows 8 h .. 8 h + 7 of column c, two shuffles
+// join the four row groups.
+__device__ __forceinline__ void match_epi_block(const uint32_t (&r)[32], const float* hb, float my_hna, int ncols,
+                                                int col0, float& best, int& best_j, uint32_t* my_patch, int lane,
+                                                u64* colbest, int row0) {
+  float k[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float s = __uint_as_float(r[j]);
-        const bool cv = (c0 + j) < ncols && tr.valid;
-        // row pass (this thread's row, ascending j: strict '>' keeps the lowest index on ties)
-        const float kr = s - s_hnb[c0 + j];
-        if (cv && kr > best) {
-          best = kr;
-          best_j = tr.n0 + c0 + j;
-        }
-        k[j] = cv ? f2ord(s - my_hna) : 0u;
-      }
-      // column pass: maximum over the warp's 32 rows (lane c ends up with column c0 + c), then the lowest row among
-      // the lanes that hold it
-      const uint32_t mx = warp_colmax32(k, lane);
-      int win = 0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const uint32_t m = __shfl_sync(0xffffffffu, mx, j);
-        const bool cv = (c0 + j) < ncols && tr.valid;
-        const uint32_t mine = cv ? f2ord(__uint_as_float(r[j]) - my_hna) : 0u;
-        const uint32_t who = __ballot_sync(0xffffffffu, mine == m);
-        if (lane == j) win = __ffs(who) - 1;
-      }
-      if (mx != 0u && c0 + lane < ncols)
-        atomicMax(p.colbest + tr.b_off + tr.n0 + c0 + lane,
-                  ((u64)mx << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(warp_row0 + win)));
-    }
-    if (tr.valid && best > -INFINITY) atomicMax(p.rowbest + tr.row, pack_best(best, best_j));
-    epi_bar_sync_n<32 * kWarps>();   // s_hnb is reused by the next tile
+  for (int q = 0; q < 8; ++q) {
+    const float4 h4 = *reinterpret_cast<const float4*>(hb + 4 * q);
+    k[4 * q + 0] = (__uint_as_float(r[4 * q + 0]) - h4.x) - my_hna;
+    k[4 * q + 1] = (__uint_as_float(r[4 * q + 1]) - h4.y) - my_hna;
+    k[4 * q + 2] = (__uint_as_float(r[4 * q + 2]) - h4.z) - my_hna;
+    k[4 * q + 3] = (__uint_as_float(r[4 * q + 3]) - h4.w) - my_hna;
   }
-};
+  // four independent compare chains of eight columns (instruction-level parallelism), joined in ascending order with
+  // strict '>' so that the lowest column still wins ties
+  float cb[4];
+  int cj[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cb[q] = k[8 * q];
+    cj[q] = 8 * q;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      const bool p = k[8 * q + j] > cb[q];
+      cb[q] = p ? k[8 * q + j] : cb[q];
+      cj[q] = p ? 8 * q + j : cj[q];
+    }
+  }
+  float lb = cb[0];
+  int lj = cj[0];
+#pragma unroll
+  for (int q = 1; q < 4; ++q) {
+    const bool p = cb[q] > lb;
+    lb = p ? cb[q] : lb;
+    lj = p ? cj[q] : lj;
+  }
+  if (lb > best) {
+    best = lb;
+    best_j = col0 + lj;
+  }
+  const int c = lane & 7, h = lane >> 3;
+  // patch row of tile row `lane`: 12 words apart, every group of 8 rows shifted by 8 more words (the 16-byte stores of
+  // 8 lanes and the column reads each hit 32 distinct banks)
+  float4* prow = reinterpret_cast<float4*>(my_patch + lane * 12 + (lane & 24));
+  const float* pcol = reinterpret_cast<const float*>(my_patch) + (8 * h) * 12 + 8 * h + c;
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    if (8 * g8 >= ncols) break;   // warp-uniform
+    prow[0] = make_float4(k[8 * g8 + 0], k[8 * g8 + 1], k[8 * g8 + 2], k[8 * g8 + 3]);
+    prow[1] = make_float4(k[8 * g8 + 4], k[8 * g8 + 5], k[8 * g8 + 6], k[8 * g8 + 7]);
+    __syncwarp();
+    float m = -INFINITY;
+    int mi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {       // column c over rows 8 h + i, ascending: lowest row on ties
+      const float v = pcol[i * 12];
+      const bool p = v > m;
+      m = p ? v : m;
+      mi = p ? i : mi;
+    }
+    mi += 8 * h;
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {  // join the four row groups: a higher group wins only when strictly greater
+      const float m2 = __shfl_down_sync(0xffffffffu, m, o);
+      const int mi2 = __shfl_down_sync(0xffffffffu, mi, o);
+      const bool p = m2 > m;
+      m = p ? m2 : m;
+      mi = p ? mi2 : mi;
+    }
+    __syncwarp();
+    if (h == 0 && m > -INFINITY)
+      atomicMax(colbest + 8 * g8 + c, ((u64)f2ord(m) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)(row0 + mi)));
+  }
+}
+
+__global__ void __launch_bounds__(MAR_THREADS, 1)
+match_ar_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const MatchGeom g,
+                const float* __restrict__ hna, const float* __restrict__ hnb, u64* __restrict__ rowbest,
+                u64* __restrict__ colbest) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                  // 8 k-blocks x 16 KB
+  uint8_t* sB = smem + MAR_A_BYTES;                    // ring
+  uint32_t* patch = reinterpret_cast<uint32_t*>(sB + MAR_B_SLOTS * 16384);   // [8 warps][32][36]
+  float* s_hnb = reinterpret_cast<float*>(patch + 8 * MAR_PATCH_WORDS);      // [2 acc stages][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_hnb + 2 * MATCH_BN);
+  uint64_t* a_full = bars;            // [1]
+  uint64_t* a_empty = bars + 1;       // [1]
+  uint64_t* b_full = bars + 2;        // [MAR_B_SLOTS]
+  uint64_t* b_empty = bars + 2 + MAR_B_SLOTS;
+  uint64_t* acc_full = bars + 2 + 2 * MAR_B_SLOTS;   // [2]
+  uint64_t* acc_empty = acc_full + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  tc::pdl_launch_dependents();
+  if (tid == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    tc::mbar_init(a_full, 1);
+    tc::mbar_init(a_empty, 1);
+    for (int s = 0; s < MAR_B_SLOTS; ++s) {
+      tc::mbar_init(&b_full[s], 1);
+      tc::mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&acc_full[s], 1);
+      tc::mbar_init(&acc_empty[s], 8);   // one arrival per epilogue warp
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  tc::pdl_wait();   // descriptor images / norms / zeroed best arrays come from the predecessors
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t ua = 0, bi = 0;
+      for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
+        const MatchUnit u = match_decode(g, unit);
+        if (!u.valid) continue;
+        tc::mbar_wait(a_empty, (ua & 1u) ^ 1u);          // the previous unit's products have retired
+        tc::mbar_expect_tx(a_full, MAR_A_BYTES);
+        for (int kb = 0; kb < 8; ++kb) tc::tma_load_2d(sA + kb * 16384, &tmA, a_full, kb * 64, u.a_off + u.m0);
+        ++ua;
+        for (int nt = u.nt0; nt < u.nt1; ++nt)
+          for (int j = 0; j < 8; ++j, ++bi) {            // hi0 lo0 hi1 lo1 ...
+            const int s = bi % MAR_B_SLOTS;
+            tc::mbar_wait(&b_empty[s], ((bi / MAR_B_SLOTS) & 1u) ^ 1u);
+            tc::mbar_expect_tx(&b_full[s], 16384);
+            const int kq = j >> 1, lo = j & 1;
+            tc::tma_load_2d(sB + s * 16384, &tmB, &b_full[s], (lo * 4 + kq) * 64, u.b_off + nt * MATCH_BN);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      uint32_t ua = 0, bi = 0, acc_it = 0;
+      const uint32_t sa0 = tc::smem_u32(sA), sb0 = tc::smem_u32(sB);
+      for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
+        const MatchUnit u = match_decode(g, unit);
+        if (!u.valid) continue;
+        tc::mbar_wait(a_full, ua & 1u);
+        ++ua;
+        for (int nt = u.nt0; nt < u.nt1; ++nt) {
+          const uint32_t as = acc_it & 1u;
+          tc::mbar_wait(&acc_empty[as], ((acc_it >> 1) & 1u) ^ 1u);
+          tc::fence_after_sync();
+          const uint32_t d_tmem = tmem_base + as * MATCH_BN;
+          for (int j = 0; j < 8; ++j, ++bi) {
+            const int s = bi % MAR_B_SLOTS;
+            tc::mbar_wait(&b_full[s], (bi / MAR_B_SLOTS) & 1u);
+            tc::fence_after_sync();
+            const int kq = j >> 1, lo = j & 1;
+            const uint64_t db = tc::make_sdesc_sw128(sb0 + s * 16384);
+            const uint64_t da_hi = tc::make_sdesc_sw128(sa0 + kq * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::umma_f16(d_tmem, tc::sdesc_advance_k16(da_hi, k), tc::sdesc_advance_k16(db, k), g.idesc,
+                           (j > 0 || k > 0) ? 1u : 0u);
+            if (!lo) {
+              const uint64_t da_lo = tc::make_sdesc_sw128(sa0 + (4 + kq) * 16384);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc::umma_f16(d_tmem, tc::sdesc_advance_k16(da_lo, k), tc::sdesc_advance_k16(db, k), g.idesc, 1u);
+            }
+            tc::umma_commit(&b_empty[s]);
+          }
+          tc::umma_commit(&acc_full[as]);
+          ++acc_it;
+        }
+        tc::umma_commit(a_empty);     // the A block may be replaced once every product of this unit has retired
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 2..9
+    const int lg = warp & 3;          // TMEM lane group this warp may access
+    const int half = (warp - 2) >> 2; // which 64 of the tile's 128 columns
+    uint32_t* my_patch = patch + (warp - 2) * MAR_PATCH_WORDS;
+    const int et = tid - 64;
+    uint32_t acc_it = 0;
+    for (int unit = blockIdx.x; unit < g.total_units; unit += gridDim.x) {
+      const MatchUnit u = match_decode(g, unit);
+      if (!u.valid) continue;
+      const int row_local = u.m0 + lg * 32 + lane;
+      const bool rvalid = row_local < u.a_cnt;
+      const float my_hna = rvalid ? __ldg(hna + u.a_off + row_local) : INFINITY;   // rows outside the pair never win
+      float best = -INFINITY;
+      int best_j = 0;
+      for (int nt = u.nt0; nt < u.nt1; ++nt) {
+        const uint32_t as = acc_it & 1u;
+        const int n0 = nt * MATCH_BN;
+        const int ncols = min(MATCH_BN, u.b_cnt - n0);
+        float* hb = s_hnb + as * MATCH_BN;
+        // all eight warps left the tile that used this stage two tiles ago before the issuer let this one start
+        if (et < MATCH_BN) hb[et] = et < ncols ? __ldg(hnb + u.b_off + n0 + et) : INFINITY;   // nor do such columns
+        tc::mbar_wait(&acc_full[as], (acc_it >> 1) & 1u);
+        __syncwarp();
+        tc::fence_after_sync();
+        epi_bar_sync_n<256>();
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + as * MATCH_BN;
+#pragma unroll 1
+        for (int gi = 0; gi < 2; ++gi) {
+          const int c0 = half * 64 + gi * 32;
+          if (c0 >= ncols) break;   // warp-uniform
+          uint32_t r[32];
+          tc::tmem_ld32(taddr + (uint32_t)c0, r);
+          tc::tmem_ld_wait();
+          match_epi_block(r, hb + c0, my_hna, ncols - c0, n0 + c0, best, best_j, my_patch, lane,
+                          colbest + u.b_off + n0 + c0, u.m0 + lg * 32);
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+        ++acc_it;
+      }
+      if (rvalid && best > -INFINITY) atomicMax(rowbest + u.a_off + row_local, pack_best(best, best_j));
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+}
 
 // ---- finalize: mutual check + exact fp32 value + threshold ----------------------------------------------------------
 __global__ void match_finalize_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
@@ -259,22 +462,35 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
   CUtensorMap tmA, tmB;
   HFB_TRY(hfb_make_tmap_2d(ctx, &tmA, A2, MATCH_LD, (uint64_t)nmax, MATCH_LD * 2, 128));
   HFB_TRY(hfb_make_tmap_2d(ctx, &tmB, B2, MATCH_LD, (uint64_t)(same ? nmax : nb_total), MATCH_LD * 2, MATCH_BN));
-  GemmGeom g;
-  gemm_fill_geom(g, max_a, max_b, MATCH_K, MATCH_BN, 0);
-  g.pair_tab = d_pair_tab;
+  MatchGeom g;
   g.n_pairs = n_pairs;
-  g.split3 = 1;
-  g.stages = 3;   // 96 KB ring: two persistent CTAs per SM (256 TMEM columns each)
-  g.epi_warp_bytes = 0;
-  g.bias_bytes = 0;
-  gemm_finish_geom(g, ceil_div(max_a, 128));
-  const size_t smem = gemm_smem_bytes(g.BN, g.stages, 0);
+  g.m_tiles = ceil_div(max_a, 128);
+  g.n_tiles = ceil_div(max_b, MATCH_BN);
+  // B tiles per unit: the split that minimises the makespan of the static unit walk, counting the reload of the A block
+  // (128 KB, about one tile's worth of L2 traffic) once per unit
+  {
+    const int base_units = n_pairs * g.m_tiles;
+    long long best_cost = -1;
+    g.chunk_tiles = g.n_tiles;
+    g.n_chunks = 1;
+    for (int chunks = 1; chunks <= g.n_tiles; ++chunks) {
+      const int ct = ceil_div(g.n_tiles, chunks), nc = ceil_div(g.n_tiles, ct);
+      const long long cost = (long long)ceil_div(base_units * nc, ctx->n_sm) * (ct + 1);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        g.chunk_tiles = ct;
+        g.n_chunks = nc;
+      }
+    }
+  }
+  g.total_units = n_pairs * g.m_tiles * g.n_chunks;
+  g.pair_tab = d_pair_tab;
+  g.idesc = tc::make_idesc_f16(MATCH_BN);
   static SmemOptIn optin;
-  HFB_CUDA(ctx, optin.ensure(gemm_tc_kernel<EpiArgmax>, ctx->device, smem));
-  EpiArgmax::Params ep{hna, hnb, rowbest, colbest};
+  HFB_CUDA(ctx, optin.ensure(match_ar_kernel, ctx->device, MAR_SMEM));
   ctx->note("match_gemm_argmax", (double)(na_total + nb_total) * 1024.0, 2.0 * n_pairs * (double)max_a * max_b * 256.0);
-  hfb_launch(ctx, gemm_tc_kernel<EpiArgmax>, gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(EpiArgmax::kWarps), smem, tmA,
-             tmB, g, ep);
+  hfb_launch(ctx, match_ar_kernel, std::min(ctx->n_sm, g.total_units), MAR_THREADS, MAR_SMEM, tmA, tmB, g, hna, hnb,
+             rowbest, colbest);
   HFB_CHECK_LAUNCH(ctx, "match_gemm_argmax");
 
   dim3 fgrid(ceil_div(std::max(max_a, pad_rows), 8), n_pairs);
