@@ -172,3 +172,63 @@ def test_distinctive_descriptor_oracle_matches_literal_loops():
         a, am = mappoint_ref.distinctive_index(D)
         b, bm = mappoint_ref.distinctive_index_literal(D)
         assert a == b and abs(float(am) - float(bm)) < 1e-6, n
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# native oracle pieces (oracle/c/*.c, oracle/_ref): the C restatements agree with the numpy oracle, and the numpy
+# Resampler restatement is bit-exact against the REFERENCE'S OWN Resampler compiled from /root/reference
+def test_resample_bilinear_equals_reference_resampler_bit_exact():
+    """select_ref.resample_bilinear vs the reference's Resampler (src/Extractors/BaseModel.cc:489-562) built from the source
+    where it lies (oracle/build_c.build_ref): identical bits, including points on / outside the border."""
+    from oracle import c_ref, select_ref
+    rng = np.random.default_rng(3)
+    Hd, Wd, C = 60, 94, 256
+    data = rng.standard_normal((Hd, Wd, C)).astype(np.float32)
+    warp = np.stack([rng.uniform(-2.0, Wd + 1.0, 3000), rng.uniform(-2.0, Hd + 1.0, 3000)], 1).astype(np.float32)
+    warp[:50] = np.round(warp[:50])                       # integer coordinates (dx = 1)
+    warp[50:60] = [[-1.0, 5.0], [5.0, -1.0], [Wd - 1.0, Hd - 1.0], [Wd - 0.5, 3.0], [3.0, Hd - 0.5],
+                   [-0.5, -0.5], [float(Wd), 1.0], [1.0, float(Hd)], [0.0, 0.0], [-0.999, 10.25]]
+    ref = c_ref.resample_reference(data, warp)
+    if ref is None:
+        pytest.skip("oracle/_ref was not built (no /root/reference on this box)")
+    got = select_ref.resample_bilinear(data, warp)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_c_matcher_restatements_equal_numpy_oracle_and_cv2():
+    from hfnet_slam_b200 import synthetic
+    from oracle import c_ref, match_ref
+    A, B = synthetic.descriptor_pair(700, 650, n_true=250, seed=9)
+    idx, val = c_ref.match_bf_l2(A, B, 0.6)
+    ia, ib, dist = match_ref.search_by_bow(A, B, 0.6)
+    assert {(int(i), int(idx[i])) for i in np.flatnonzero(idx >= 0)} == set(zip(ia.tolist(), ib.tolist()))
+    assert np.abs(val[ia] - dist).max() < 2e-6
+    ms = cv2.BFMatcher(cv2.NORM_L2, crossCheck=True).match(A, B)
+    assert {(m.queryIdx, m.trainIdx) for m in ms if m.distance < 0.6} == set(zip(ia.tolist(), ib.tolist()))
+    idx, val = c_ref.match_cos_mutual(A, B, float(match_ref.COS_FLOOR))
+    i1, i2, cs = match_ref.search_for_triangulation_core(A, B)
+    assert {(int(i), int(idx[i])) for i in np.flatnonzero(idx >= 0)} == set(zip(i1.tolist(), i2.tolist()))
+    assert np.abs(val[i1] - cs).max() < 2e-6
+
+
+def test_c_kfdb_scan_equals_numpy_oracle():
+    from hfnet_slam_b200 import synthetic
+    from oracle import c_ref, kfdb_ref
+    db, q, _ = synthetic.keyframe_db(3000, 4096, n_planted=60, seed=4, n_queries=2)
+    for k in range(2):
+        assert np.abs(c_ref.kfdb_scores(q[k], db) - kfdb_ref.scores(q[k], db)).max() <= 2e-6
+
+
+def test_c_lba_restatement_equals_numpy_oracle():
+    """oracle/c/lba_ref.c mirrors oracle/lba_ref.py: same LM path (iterations, trials), poses / points / chi2 to 1e-9."""
+    from hfnet_slam_b200 import synthetic
+    from oracle import c_ref, lba_ref
+    for seed, kw in ((5, dict(n_opt=3, n_fixed=2, n_points=60)), (7, dict(n_opt=6, n_fixed=5, n_points=400))):
+        d = synthetic.lba_problem(seed=seed, **kw)
+        r = lba_ref.optimize(lba_ref.Problem(d["poses"], d["fixed"], d["points"], d["cam_idx"], d["pt_idx"], d["obs"],
+                                             d["inv_sigma2"], d["K"]), 10)
+        c = c_ref.lba_optimize(d, 10)
+        assert c["iterations"] == r.iterations and c["trials"] == r.trials
+        assert np.abs(c["poses"] - r.poses).max() < 1e-9 and np.abs(c["points"] - r.points).max() < 1e-9
+        assert np.abs(c["chi2"] - r.chi2).max() < 1e-6 * max(1.0, float(np.abs(r.chi2).max()))
+        assert np.array_equal(c["depth_positive"], r.depth_positive)
