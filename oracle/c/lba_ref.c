@@ -425,3 +425,133 @@ int ref_lba_optimize(int n_cam, int n_pt, int n_edge, const double* poses0, cons
   free(Hs); free(bs); free(xp); free(Dinv); free(xl); free(cl); free(chi2_t); free(last_chi2);
   return 0;
 }
+
+/* ===================================================================================================================
+ * Optimizer::PoseOptimization (src/Optimizer.cc:814-1114), monocular branch, mirroring oracle/lba_ref.py:
+ * pose_optimization: one VertexSE3Expmap, unary EdgeSE3ProjectXYZOnlyPose edges (include/OptimizableTypes.h:30-56,
+ * src/OptimizableTypes.cpp:49-64); four rounds of optimize(10), each restarted from the frame's pose, inliers only,
+ * re-classification with chi2 > 5.991 (float compare) after every round, Huber dropped after the third. */
+static double pose_edges(const double* K, const double* pose, int n, const double* Xw, const double* obs,
+                         const double* is2, const uint8_t* skip, double* err, double* chi2, double* Xc, int robust,
+                         double delta) {
+  double R[9];
+  quat_to_rot(pose, R);
+  const double dsqr = delta * delta;
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    if (skip && skip[i]) continue;
+    const double* X = Xw + 3 * i;
+    const double x = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + pose[4];
+    const double y = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + pose[5];
+    const double z = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + pose[6];
+    const double ex = obs[2 * i] - (K[0] * x / z + K[2]), ey = obs[2 * i + 1] - (K[1] * y / z + K[3]);
+    const double c2 = is2[i] * (ex * ex + ey * ey);
+    if (err) { err[2 * i] = ex; err[2 * i + 1] = ey; }
+    if (Xc) { Xc[3 * i] = x; Xc[3 * i + 1] = y; Xc[3 * i + 2] = z; }
+    chi2[i] = c2;
+    sum += (!robust || c2 <= dsqr) ? c2 : 2 * sqrt(c2) * delta - dsqr;
+  }
+  return sum;
+}
+
+int ref_pose_optimize(const float* Kf, const double* pose0, int n, const double* Xw, const double* obs, const double* is2,
+                      double huber_delta, double* pose_out, uint8_t* outlier_out, int* n_inliers, int* n_trials) {
+  const double K[4] = {Kf[0], Kf[1], Kf[2], Kf[3]};
+  const double tau = 1e-5, good_lo = 1.0 / 3.0, good_hi = 2.0 / 3.0, dsqr = huber_delta * huber_delta;
+  const int max_trials = 10;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  uint8_t* outlier = (uint8_t*)calloc(nn, 1);
+  double* err = (double*)calloc(2 * nn, sizeof(double));
+  double* chi2 = (double*)calloc(nn, sizeof(double));
+  double* chi2_t = (double*)calloc(nn, sizeof(double));
+  double* cached = (double*)calloc(nn, sizeof(double));
+  double* Xc = (double*)calloc(3 * nn, sizeof(double));
+  double pose[7], new_pose[7];
+  int trials = 0, n_bad = 0;
+  memcpy(pose, pose0, sizeof(pose));
+  for (int rnd = 0; rnd < 4; ++rnd) {
+    const int robust = rnd < 3;
+    memcpy(pose, pose0, sizeof(pose));
+    memset(cached, 0, sizeof(double) * nn);
+    int n_act = 0;
+    for (int i = 0; i < n; ++i) n_act += !outlier[i];
+    double lam = 0.0, ni = 2.0;
+    int nbad_lm = 0;
+    for (int it = 0; it < 10 && n_act > 0; ++it) {
+      double current_chi = pose_edges(K, pose, n, Xw, obs, is2, outlier, err, chi2, Xc, robust, huber_delta);
+      const double ini_chi = current_chi;
+      double H[36] = {0}, b[6] = {0};
+      for (int i = 0; i < n; ++i) {
+        if (outlier[i]) continue;
+        cached[i] = chi2[i];
+        const double x = Xc[3 * i], y = Xc[3 * i + 1], z = Xc[3 * i + 2];
+        const double P[6] = {-K[0] / z, 0, K[0] * x / (z * z), 0, -K[1] / z, K[1] * y / (z * z)};
+        const double D[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
+        double J[12];
+        for (int r = 0; r < 2; ++r)
+          for (int c = 0; c < 6; ++c) J[r * 6 + c] = P[r * 3] * D[c] + P[r * 3 + 1] * D[6 + c] + P[r * 3 + 2] * D[12 + c];
+        const double w = (!robust || chi2[i] <= dsqr) ? 1.0 : huber_delta / sqrt(chi2[i]);
+        const double wo = w * is2[i];
+        const double r0 = -(wo * err[2 * i]), r1 = -(wo * err[2 * i + 1]);
+        for (int r = 0; r < 6; ++r) {
+          for (int c = 0; c < 6; ++c) H[r * 6 + c] += wo * (J[r] * J[c] + J[6 + r] * J[6 + c]);
+          b[r] += J[r] * r0 + J[6 + r] * r1;
+        }
+      }
+      if (it == 0) {
+        double md = 0.0;
+        for (int r = 0; r < 6; ++r) md = fmax(md, fabs(H[r * 7]));
+        lam = tau * md;
+        ni = 2.0;
+        nbad_lm = 0;
+      }
+      double rho = 0.0;
+      int qmax = 0;
+      do {
+        double A[36], x6[6];
+        memcpy(A, H, sizeof(A));
+        for (int r = 0; r < 6; ++r) A[r * 7] += lam;
+        const int ok2 = chol_solve(A, 6, b, x6);
+        if (!ok2) memset(x6, 0, sizeof(x6));
+        pose_oplus(pose, x6, new_pose);
+        double temp_chi = pose_edges(K, new_pose, n, Xw, obs, is2, outlier, NULL, chi2_t, NULL, robust, huber_delta);
+        for (int i = 0; i < n; ++i)
+          if (!outlier[i]) cached[i] = chi2_t[i];
+        if (!ok2) temp_chi = DBL_MAX;
+        double scale = 1e-3;
+        for (int r = 0; r < 6; ++r) scale += x6[r] * (lam * x6[r] + b[r]);
+        rho = (current_chi - temp_chi) / scale;
+        ++trials;
+        if (rho > 0 && isfinite(temp_chi)) {
+          const double alpha = fmin(1.0 - pow(2 * rho - 1, 3), good_hi);
+          lam *= fmax(good_lo, alpha);
+          ni = 2.0;
+          current_chi = temp_chi;
+          memcpy(pose, new_pose, sizeof(pose));
+        } else {
+          lam *= ni;
+          ni *= 2;
+        }
+        ++qmax;
+      } while (rho < 0 && qmax < max_trials);
+      if (qmax == max_trials || rho == 0) break;
+      if ((ini_chi - current_chi) * 1e3 < ini_chi) ++nbad_lm; else nbad_lm = 0;
+      if (nbad_lm >= 3) break;
+    }
+    /* classification: outlier edges are re-evaluated at the round's final pose, inliers keep the cached chi2 */
+    pose_edges(K, pose, n, Xw, obs, is2, NULL, NULL, chi2, NULL, 0, huber_delta);
+    n_bad = 0;
+    for (int i = 0; i < n; ++i) {
+      const double used = outlier[i] ? chi2[i] : cached[i];
+      outlier[i] = (float)used > 5.991f;
+      n_bad += outlier[i];
+    }
+    if (n < 10) break;
+  }
+  memcpy(pose_out, pose, sizeof(pose));
+  memcpy(outlier_out, outlier, (size_t)n);
+  *n_inliers = n - n_bad;
+  *n_trials = trials;
+  free(outlier); free(err); free(chi2); free(chi2_t); free(cached); free(Xc);
+  return 0;
+}

@@ -98,3 +98,17 @@ def resample_reference(data: np.ndarray, warp: np.ndarray) -> Optional[np.ndarra
     out = np.empty((w.shape[0], d.shape[2]), np.float32)
     r.ref_resampler(_p(d, _f32p), _p(w, _f32p), _p(out, _f32p), 1, d.shape[0], d.shape[1], d.shape[2], w.shape[0])
     return out
+
+
+def pose_optimize(K, pose0, Xw, obs, inv_sigma2, huber_delta: float = float(np.sqrt(5.991))):
+    """The C restatement of oracle/lba_ref.pose_optimization -> dict(pose, outlier, n_inliers, trials)."""
+    k = np.ascontiguousarray(K, np.float32)
+    p0 = np.ascontiguousarray(pose0, np.float64).reshape(7)
+    X = np.ascontiguousarray(Xw, np.float64).reshape(-1, 3)
+    o = np.ascontiguousarray(obs, np.float64).reshape(-1, 2)
+    s2 = np.ascontiguousarray(inv_sigma2, np.float64).reshape(-1)
+    out, flags = np.zeros(7, np.float64), np.zeros(max(len(X), 1), np.uint8)
+    ninl, ntr = C.c_int(), C.c_int()
+    lib().ref_pose_optimize(_p(k, _f32p), _p(p0, _f64p), len(X), _p(X, _f64p), _p(o, _f64p), _p(s2, _f64p),
+                            C.c_double(huber_delta), _p(out, _f64p), _p(flags, _u8p), C.byref(ninl), C.byref(ntr))
+    return dict(pose=out, outlier=flags[:len(X)].astype(bool), n_inliers=int(ninl.value), trials=int(ntr.value))
