@@ -44,6 +44,26 @@ int hfb_make_tmap_2d(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint64_t 
   return HFB_OK;
 }
 
+// fp32 [outer][inner] matrix (kind::tf32 operands read fp32 words); box = 32 (inner, 128 bytes) x box_outer, 128B swizzle.
+int hfb_make_tmap_2d_f32(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                         uint64_t row_stride_bytes, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode(ctx);
+  if (!enc) return HFB_ERR_CUDA;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {32, box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctx->set_error("cuTensorMapEncodeTiled(2d, f32) failed: code " + std::to_string((int)r) + " inner " +
+                   std::to_string(inner) + " outer " + std::to_string(outer));
+    return HFB_ERR_CUDA;
+  }
+  return HFB_OK;
+}
+
 // fp16 NHWC tensor viewed as (C, W, H, B); box = 64 channels x 16 x 8 x 1 (one 128-pixel patch).
 int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B) {
   PFN_encodeTiled enc = get_encode(ctx);

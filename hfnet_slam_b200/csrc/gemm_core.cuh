@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(GEMM_THREADS(Epi::kWarps)) gemm_tc_kernel(cons
 struct hfb_ctx;
 int hfb_make_tmap_2d(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                      uint64_t row_stride_bytes, uint32_t box_outer);
+int hfb_make_tmap_2d_f32(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                         uint64_t row_stride_bytes, uint32_t box_outer);
 int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B);
 
 static inline uint32_t tmem_cols_for(int BN) {

@@ -93,6 +93,17 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with kind::tf32: A and B are fp32 words in shared memory of which the tensor core reads the upper 19 bits
+// (sign, 8 exponent, 10 mantissa bits); K = 8 per instruction (32 bytes of the 128-byte swizzled row).
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once every previously issued UMMA of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -148,6 +159,11 @@ __device__ __forceinline__ uint64_t sdesc_advance_k16(uint64_t desc, int k) { re
 // 15 A major (0 = K), 16 B major (0 = K), [17,23) N>>3, [24,29) M>>4.
 __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int n, int bf16 = 0) {
   return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// kind::tf32: A / B format code 2 (tf32), fp32 D, both K-major, M = 128, N = n.
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 }  // namespace tc

@@ -45,6 +45,18 @@ class KeyFrameDatabase:
         d = np.ascontiguousarray(descriptors, dtype=np.float32).reshape(len(ids), self.dim)
         self.ctx.check(self.ctx.lib.hfb_kfdb_add(self.handle, ptr(ids, _i64p), ptr(d, _f32p), len(ids)))
 
+    def add_tagged(self, ids: np.ndarray, map_ids: np.ndarray, descriptors: np.ndarray):
+        """add with KeyFrame::GetMap() recorded (for clear_map)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        maps = np.ascontiguousarray(map_ids, dtype=np.int64)
+        d = np.ascontiguousarray(descriptors, dtype=np.float32).reshape(len(ids), self.dim)
+        self.ctx.check(self.ctx.lib.hfb_kfdb_add_tagged(self.handle, ptr(ids, _i64p), ptr(maps, _i64p), ptr(d, _f32p),
+                                                        len(ids)))
+
+    def clear_map(self, map_id: int):
+        """KeyFrameDatabase::clearMap (src/KeyFrameDatabase.cc:54-68)."""
+        self.ctx.check(self.ctx.lib.hfb_kfdb_clear_map(self.handle, int(map_id)))
+
     def erase(self, kf_id: int):
         self.ctx.check(self.ctx.lib.hfb_kfdb_erase(self.handle, int(kf_id)))
 
@@ -63,6 +75,19 @@ class KeyFrameDatabase:
                                                    ptr(sc, _f32p), cap, C.byref(n), C.byref(best)))
         return ids[:n.value].copy(), sc[:n.value].copy(), float(best.value)
 
+    def query_batch(self, Q: np.ndarray, rel: float = 0.8, floor: float = 0.0, cap: int = 256):
+        """Several queries as one pass over the rows (tensor-core selection + exact re-scoring): list of
+        (candidate ids ascending, scores, best) per query, equal to calling query() for each."""
+        qq = np.ascontiguousarray(Q, dtype=np.float32).reshape(-1, self.dim)
+        nq = qq.shape[0]
+        ids = np.zeros((nq, cap), np.int64)
+        sc = np.zeros((nq, cap), np.float32)
+        n = np.zeros(nq, np.int32)
+        best = np.zeros(nq, np.float32)
+        self.ctx.check(self.ctx.lib.hfb_kfdb_query_batch(self.handle, ptr(qq, _f32p), nq, rel, floor, cap, ptr(ids, _i64p),
+                                                         ptr(sc, _f32p), ptr(n, _i32p), ptr(best, _f32p)))
+        return [(ids[i, :n[i]].copy(), sc[i, :n[i]].copy(), float(best[i])) for i in range(nq)]
+
     def scores_of(self, ids: np.ndarray) -> np.ndarray:
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         out = np.zeros(len(ids), np.float32)
@@ -75,6 +100,55 @@ class KeyFrameDatabase:
         buf = C.create_string_buffer(16 + 16 * k)
         self.ctx.check(self.ctx.lib.hfb_kfdb_query_shard(self.handle, ptr(qq, _f32p), rel, floor, k, buf))
         return buf.raw
+
+    # ------------------------------------------------------------------------------------------------ sharded, on device
+    def shard_setup(self, rank: int, world: int, k: int = 64) -> bytes:
+        """Allocate this rank's inbox; returns the 64-byte IPC handle the other ranks connect with."""
+        h = C.create_string_buffer(64)
+        self.ctx.check(self.ctx.lib.hfb_kfdb_shard_setup(self.handle, rank, world, k, h))
+        self._shard = (rank, world, k)
+        return h.raw
+
+    def connect_shards(self, dist, rank: int, world: int, k: int = 64):
+        """Multi-process start-up: one all_gather of the IPC handles (torch.distributed, any backend), then every rank maps
+        its peers' inboxes."""
+        import torch
+        mine = self.shard_setup(rank, world, k)
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        blob = b"".join(bytes(o.cpu().numpy()) for o in out)
+        self.ctx.check(self.ctx.lib.hfb_kfdb_shard_connect(self.handle, blob))
+
+    @staticmethod
+    def connect_shards_local(shards: Sequence["KeyFrameDatabase"], k: int = 64):
+        """Same-process variant (several shard objects, e.g. one per context on one device)."""
+        world = len(shards)
+        for r, sh in enumerate(shards):
+            sh.shard_setup(r, world, k)
+        arr = (C.c_void_p * world)(*[sh.handle for sh in shards])
+        for sh in shards:
+            sh.ctx.check(sh.ctx.lib.hfb_kfdb_shard_connect_local(sh.handle, arr))
+
+    def query_sharded_begin(self, q: np.ndarray, rel: float = 0.8, floor: float = 0.0):
+        qq = np.ascontiguousarray(q, dtype=np.float32).reshape(self.dim)
+        self.ctx.check(self.ctx.lib.hfb_kfdb_query_sharded_begin(self.handle, ptr(qq, _f32p), rel, floor))
+
+    def query_sharded_end(self):
+        _, world, k = self._shard
+        cap = world * k
+        ids, sc = np.zeros(cap, np.int64), np.zeros(cap, np.float32)
+        n, best, ov = C.c_int32(), C.c_float(), C.c_int32()
+        self.ctx.check(self.ctx.lib.hfb_kfdb_query_sharded_end(self.handle, ptr(ids, _i64p), ptr(sc, _f32p), cap, C.byref(n),
+                                                               C.byref(best), C.byref(ov)))
+        return ids[:n.value].copy(), sc[:n.value].copy(), float(best.value), bool(ov.value)
+
+    def query_sharded(self, q: np.ndarray, rel: float = 0.8, floor: float = 0.0):
+        """Collective query over the sharded database: (global candidate ids ascending, scores, global best, overflow)."""
+        self.query_sharded_begin(q, rel, floor)
+        return self.query_sharded_end()
 
     # ------------------------------------------------------------------------------------------------ host logic
     def _accumulate(self, cand: Sequence[int], sc: Dict[int, float], covisibles: Callable[[int, int], Iterable[int]]):

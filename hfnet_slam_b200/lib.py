@@ -106,10 +106,22 @@ SIGNATURES = {
     "hfb_kfdb_erase": (C.c_int, [C.c_void_p, C.c_int64]),
     "hfb_kfdb_clear": (C.c_int, [C.c_void_p]),
     "hfb_kfdb_size": (C.c_int32, [C.c_void_p]),
+    "hfb_kfdb_add_tagged": (C.c_int, [C.c_void_p, _i64p, _i64p, _f32p, C.c_int32]),
+    "hfb_kfdb_clear_map": (C.c_int, [C.c_void_p, C.c_int64]),
+    "hfb_kfdb_query_batch": (C.c_int, [C.c_void_p, _f32p, C.c_int32, C.c_float, C.c_float, C.c_int32, _i64p, _f32p, _i32p,
+                                       _f32p]),
+    "hfb_kfdb_query_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float]),
     "hfb_kfdb_query": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_float, _i64p, _f32p, C.c_int32, _i32p, _f32p]),
     "hfb_kfdb_scores_of": (C.c_int, [C.c_void_p, _i64p, C.c_int32, _f32p]),
     "hfb_kfdb_scan_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "hfb_kfdb_query_shard": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
+    "hfb_kfdb_shard_setup": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "hfb_kfdb_shard_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hfb_kfdb_shard_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "hfb_kfdb_query_sharded_begin": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_float]),
+    "hfb_kfdb_query_sharded_end": (C.c_int, [C.c_void_p, _i64p, _f32p, C.c_int32, _i32p, _f32p, _i32p]),
+    "hfb_kfdb_query_sharded": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_float, _i64p, _f32p, C.c_int32, _i32p, _f32p,
+                                         _i32p]),
     "hfb_lba_optimize": (C.c_int, [C.c_void_p, C.POINTER(hfb_lba_problem), C.c_int32, C.c_double, _u8p, _f64p, _f64p,
                                    _f64p, _u8p, C.POINTER(hfb_lba_stats)]),
     "hfb_pose_optimize": (C.c_int, [C.c_void_p, _f32p, _f64p, C.c_int32, _f64p, _f64p, _f64p, _f64p, _u8p, _i32p, _i32p]),

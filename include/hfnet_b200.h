@@ -239,6 +239,10 @@ int hfb_kfdb_add(hfb_kfdb* db, const int64_t* ids, const float* descriptors, int
 int hfb_kfdb_add_dev(hfb_kfdb* db, const int64_t* ids /*host*/, const float* d_descriptors, int32_t n);
 int hfb_kfdb_erase(hfb_kfdb* db, int64_t id);
 int hfb_kfdb_clear(hfb_kfdb* db);
+/* KeyFrameDatabase::clearMap(Map*) (src/KeyFrameDatabase.cc:54-68): add with the keyframe's map recorded (map_ids[i] =
+ * any stable identifier of KeyFrame::GetMap(); hfb_kfdb_add records map 0), then drop every keyframe of one map. */
+int hfb_kfdb_add_tagged(hfb_kfdb* db, const int64_t* ids, const int64_t* map_ids, const float* descriptors, int32_t n);
+int hfb_kfdb_clear_map(hfb_kfdb* db, int64_t map_id);
 int32_t hfb_kfdb_size(const hfb_kfdb* db);
 /* One query (src/KeyFrameDatabase.cc:85-104 / :177-192): score_i = max(0, 1 - ||q - d_i||_2) for every row,
  * best = max score, candidates = { i : score_i > max(floor, rel * best) } (strict).  rel = 0.8; floor = 0 for
@@ -246,6 +250,15 @@ int32_t hfb_kfdb_size(const hfb_kfdb* db);
  * *n_cand may exceed cap (then only cap are written and HFB_ERR_CAPACITY is returned). */
 int hfb_kfdb_query(hfb_kfdb* db, const float* query, float rel, float floor, int64_t* cand_ids, float* cand_scores,
                    int32_t cap, int32_t* n_cand, float* best_score);
+/* n_queries queries as ONE pass over the rows (relocalisation of several frames / sessions at once; BASELINE.json
+ * configs[3] with Q = 64): the contraction q . d runs on the tensor cores (kind::tf32) to SELECT the pairs that can be
+ * candidates or the best row under its error bound, those pairs are re-scored exactly, and candidate sets / best scores
+ * are decided on the exact values -- the results equal n_queries calls of hfb_kfdb_query.  Outputs are [n_queries][cap]
+ * (ids ascending per query), n_cand[q] may exceed cap (then HFB_ERR_CAPACITY is returned after filling what fits). */
+int hfb_kfdb_query_batch(hfb_kfdb* db, const float* queries, int32_t n_queries, float rel, float floor, int32_t cap,
+                         int64_t* cand_ids, float* cand_scores, int32_t* n_cand, float* best_scores);
+/* Device-resident queries, enqueue only (throughput measurement): results stay in the database's device buffers. */
+int hfb_kfdb_query_batch_dev(hfb_kfdb* db, const float* d_queries, int32_t n_queries, float rel, float floor);
 /* Scores of arbitrary keyframes under the LAST query (mPlaceRecognitionScore of covisible neighbours,
  * src/KeyFrameDatabase.cc:117-131).  Unknown ids get -1. */
 int hfb_kfdb_scores_of(hfb_kfdb* db, const int64_t* ids, int32_t n, float* scores);
@@ -257,6 +270,25 @@ int hfb_kfdb_scan_dev(hfb_kfdb* db, const float* d_query, int32_t n_queries, flo
  * holding the top-k (by score, ties by id) of { i : score_i > max(floor, rel * local_best) } -- a superset of the
  * shard's share of the global candidate set because local_best <= global_best.  Bytes = 16 + 16*k. */
 int hfb_kfdb_query_shard(hfb_kfdb* db, const float* query, float rel, float floor, int32_t k, void* record);
+/* The same exchange without the host in the loop: every rank's scan is followed by ONE single-CTA kernel that builds the
+ * record on the device, stores it into every peer's inbox over NVLink (peer memory mapped with CUDA IPC), publishes a
+ * flag, waits for the peers' flags and merges by the global best -- the host sees one enqueue and one small D2H.
+ *   hfb_kfdb_shard_setup          allocates this rank's inbox for `world` records of k entries; ipc_handle_out receives the
+ *                                 64-byte cudaIpcMemHandle_t the other ranks need (NULL for same-process use)
+ *   hfb_kfdb_shard_connect        multi-process: the handles of ranks 0 .. world-1, [world][64] bytes, gathered by the
+ *                                 caller (e.g. one torch.distributed all_gather at start-up)
+ *   hfb_kfdb_shard_connect_local  same process: the shard objects of ranks 0 .. world-1
+ *   hfb_kfdb_query_sharded        collective: all ranks call it with the same query, in the same order; returns the GLOBAL
+ *                                 candidate set (ids ascending) and best score on every rank; *overflow = a shard had more
+ *                                 than k rows above the global bar.  _begin enqueues, _end synchronises and copies out. */
+int hfb_kfdb_shard_setup(hfb_kfdb* db, int32_t rank, int32_t world, int32_t k, void* ipc_handle_out);
+int hfb_kfdb_shard_connect(hfb_kfdb* db, const void* all_handles);
+int hfb_kfdb_shard_connect_local(hfb_kfdb* db, hfb_kfdb* const* shards);
+int hfb_kfdb_query_sharded_begin(hfb_kfdb* db, const float* query, float rel, float floor);
+int hfb_kfdb_query_sharded_end(hfb_kfdb* db, int64_t* cand_ids, float* cand_scores, int32_t cap, int32_t* n_cand,
+                               float* best_score, int32_t* overflow);
+int hfb_kfdb_query_sharded(hfb_kfdb* db, const float* query, float rel, float floor, int64_t* cand_ids, float* cand_scores,
+                           int32_t cap, int32_t* n_cand, float* best_score, int32_t* overflow);
 
 /* ------------------------------------------------------------------------------------------------------ local BA
  * Replaces the numeric core of Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1116-1498): everything between

@@ -152,3 +152,141 @@ def test_c4_50k_rows_eight_way_shard_merge(small_ctx, c4_db):
         assert np.abs(m_scores - sc_ref[m_ids]).max() <= TOL
     for sh in shards:
         sh.close()
+
+
+def test_c4_50k_rows_q64_batch_equals_single_queries(small_ctx, c4_db):
+    """BASELINE.json configs[3] with Q = 64: one tensor-core pass + exact re-scoring == 64 single queries (ids, scores and
+    best scores bit-identical: both paths score a pair with the same arithmetic) == the oracle's candidate sets."""
+    db, q, qi = c4_db
+    n = db.shape[0]
+    ids = np.arange(n, dtype=np.int64)
+    kf = KeyFrameDatabase(small_ctx, capacity=n)
+    kf.add_many(ids, db)
+    out = kf.query_batch(q, cap=256)
+    assert len(out) == 64
+    for k in (0, 1, 31, 63):
+        cand, scores, best = kf.query(q[k])
+        assert np.array_equal(out[k][0], cand) and np.array_equal(out[k][1], scores) and out[k][2] == best
+    for k in (5, 40):
+        _check_candidates(out[k][0], out[k][2], kfdb_ref.scores(q[k], db), ids)
+    # a random (unplanted) query: best score 0 -> no candidates, like the single-query path
+    rq = np.random.default_rng(1).standard_normal((3, 4096)).astype(np.float32)
+    rq /= np.linalg.norm(rq, axis=1, keepdims=True)
+    rq[2] = db[123]                                  # an exact duplicate: distance 0, score 1
+    for k, (c, s, b) in enumerate(kf.query_batch(rq)):
+        c1, s1, b1 = kf.query(rq[k])
+        assert np.array_equal(c, c1) and np.array_equal(s, s1) and b == b1
+    assert kf.query_batch(rq)[2][2] == 1.0
+    kf.close()
+
+
+@pytest.mark.parametrize("n,nq", [(1, 2), (130, 3), (2000, 70)])
+def test_query_batch_small_and_ragged(small_ctx, n, nq):
+    db, q, _ = synthetic.keyframe_db(n, 4096, n_planted=min(40, n // 2), seed=9, n_queries=min(nq, max(n // 2, 1)))
+    rng = np.random.default_rng(2)
+    extra = rng.standard_normal((nq - len(q), 4096)).astype(np.float32) if nq > len(q) else np.zeros((0, 4096), np.float32)
+    if len(extra):
+        extra /= np.linalg.norm(extra, axis=1, keepdims=True)
+    Q = np.concatenate([q, extra])[:nq]
+    ids = np.arange(n, dtype=np.int64) * 2 + 1
+    kf = KeyFrameDatabase(small_ctx, capacity=n + 3)
+    kf.add_many(ids, db)
+    for k, (c, s, b) in enumerate(kf.query_batch(Q, cap=64)):
+        c1, s1, b1 = kf.query(Q[k])
+        assert np.array_equal(c, c1) and np.array_equal(s, s1) and b == b1, k
+    kf.close()
+
+
+def test_clear_map(small_ctx):
+    """KeyFrameDatabase::clearMap (src/KeyFrameDatabase.cc:54-68): every keyframe of one map leaves the database."""
+    db, q, _ = synthetic.keyframe_db(90, 4096, n_planted=10, seed=6)
+    ids = np.arange(90, dtype=np.int64) + 100
+    maps = (np.arange(90) % 3).astype(np.int64)
+    kf = KeyFrameDatabase(small_ctx, capacity=90)
+    kf.add_tagged(ids, maps, db)
+    kf.clear_map(1)
+    assert len(kf) == 60
+    keep = maps != 1
+    cand, scores, best = kf.query(q[0])
+    sc_ref = kfdb_ref.scores(q[0], db[keep])
+    assert np.abs(kf.scores_of(ids[keep]) - sc_ref).max() <= TOL
+    assert (kf.scores_of(ids[~keep]) == -1).all()
+    kf.clear_map(7)
+    assert len(kf) == 60
+    kf.close()
+
+
+def test_device_side_shard_exchange_equals_unsharded(native_lib, c4_db):
+    """The host-free sharded query (device record + peer-memory exchange + device merge; here 8 shard objects with one
+    context each in ONE process, inboxes connected by direct pointers) at the full C4 size: every shard returns the
+    unsharded candidate set, scores and best."""
+    from hfnet_slam_b200.lib import Context
+    db, q, _ = c4_db
+    n, world = db.shape[0], 8
+    ids = np.arange(n, dtype=np.int64)
+    ctxs = [Context(height=64, width=64, n_levels=1, max_keypoints=64, max_batch=1, with_global=False) for _ in range(world + 1)]
+    full = KeyFrameDatabase(ctxs[world], capacity=n)
+    full.add_many(ids, db)
+    shards = []
+    for r in range(world):
+        sh = KeyFrameDatabase(ctxs[r], capacity=n // world + 1)
+        m = ids % world == r
+        sh.add_many(ids[m], db[m])
+        shards.append(sh)
+    KeyFrameDatabase.connect_shards_local(shards, k=64)
+    for k in (0, 33, 7):
+        cand, scores, best = full.query(q[k])
+        for sh in shards:                      # all ranks enqueue, then all collect (they wait for one another on the device)
+            sh.query_sharded_begin(q[k])
+        for sh in shards:
+            m_ids, m_sc, m_best, ov = sh.query_sharded_end()
+            assert not ov and m_best == best
+            assert np.array_equal(m_ids, cand) and np.array_equal(m_sc, scores)
+    for sh in shards:
+        sh.close()
+    full.close()
+    for c in ctxs:
+        c.close()
+
+
+_TWO_RANK_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, os.environ["HFB_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from hfnet_slam_b200 import synthetic
+from hfnet_slam_b200.keyframe_database import KeyFrameDatabase
+from hfnet_slam_b200.lib import Context
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+dev = rank % torch.cuda.device_count()
+db, q, _ = synthetic.keyframe_db(6000, 4096, n_planted=120, seed=8, n_queries=6)
+ids = np.arange(6000, dtype=np.int64)
+ctx = Context(height=64, width=64, n_levels=1, max_keypoints=64, max_batch=1, with_global=False, device=dev)
+full = KeyFrameDatabase(ctx, capacity=6000); full.add_many(ids, db)
+sh = KeyFrameDatabase(ctx, capacity=6000 // world + 1)
+m = ids % world == rank
+sh.add_many(ids[m], db[m])
+sh.connect_shards(dist, rank, world, k=64)         # IPC handles exchanged once, peers' inboxes mapped
+for k in range(6):
+    cand, scores, best = full.query(q[k])
+    m_ids, m_sc, m_best, ov = sh.query_sharded(q[k])
+    assert not ov and m_best == best and np.array_equal(m_ids, cand) and np.array_equal(m_sc, scores), (rank, k)
+dist.barrier()
+sh.close(); full.close(); ctx.close()
+print("RANK_OK", rank)
+"""
+
+
+def test_device_side_shard_exchange_two_processes_ipc(native_lib, tmp_path):
+    """The multi-process form of the exchange: two ranks (torchrun, gloo rendezvous; both on the visible GPU(s)) map each
+    other's inbox with CUDA IPC and answer six collective queries identically to an unsharded database."""
+    import os, subprocess, sys
+    from pathlib import Path
+    script = tmp_path / "two_rank.py"
+    script.write_text(_TWO_RANK_SCRIPT)
+    env = dict(os.environ, HFB_ROOT=str(Path(__file__).resolve().parents[1]))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("RANK_OK") == 2
