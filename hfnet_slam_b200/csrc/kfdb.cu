@@ -25,6 +25,8 @@ struct hfb_kfdb {
   std::vector<float> h_scores;   // lazily fetched scores of the last query
   bool h_scores_valid = false;
   long long* d_ids = nullptr;    // [capacity] slot -> id on the device (shard records carry ids)
+  float* h_query = nullptr;      // pinned staging of the host query
+  int* h_head = nullptr;         // pinned: ncand | best bits | first KFDB_HEAD (slot, score) pairs of the candidate list
   // multi-query scan on the tensor cores (hfb_kfdb_query_batch)
   float* d_norm2 = nullptr;      // [capacity] |d|^2 of every row
   float* d_dots = nullptr;       // [capacity][KTC_QN] q . d of the current pass
@@ -54,6 +56,7 @@ struct hfb_kfdb {
 #define KFDB_QB 4  // queries scanned per pass over the rows
 #define KTC_QN 64            // queries per tensor-core pass (UMMA N)
 #define KTC_PAIR_CAP (1 << 18)
+#define KFDB_HEAD 64         // candidates fetched together with the count (one synchronisation in the common case)
 
 template <int QB>
 __global__ void __launch_bounds__(256) kfdb_scan_kernel(const float* __restrict__ rows, int n, int dim,
@@ -485,6 +488,8 @@ static void kfdb_free(hfb_kfdb* db) {
     if (db->peer_opened[r] && db->peer_inbox[r]) cudaIpcCloseMemHandle(db->peer_inbox[r]);
   cudaFree(db->d_inbox); cudaFree(db->d_shard_out); cudaFree(db->d_peer_tab);
   if (db->h_shard_out) cudaFreeHost(db->h_shard_out);
+  if (db->h_query) cudaFreeHost(db->h_query);
+  if (db->h_head) cudaFreeHost(db->h_head);
   delete db;
 }
 
@@ -507,6 +512,8 @@ extern "C" int hfb_kfdb_create(hfb_ctx* ctx, int32_t dim, int32_t capacity, hfb_
   if (e == cudaSuccess) e = cudaMalloc(&db->d_cand_score, (size_t)capacity * 4);
   if (e == cudaSuccess) e = cudaMalloc(&db->d_ids, (size_t)capacity * 8);
   if (e == cudaSuccess) e = cudaMalloc(&db->d_norm2, (size_t)capacity * 4);
+  if (e == cudaSuccess) e = cudaMallocHost(&db->h_query, (size_t)dim * 4);
+  if (e == cudaSuccess) e = cudaMallocHost(&db->h_head, (2 + 2 * KFDB_HEAD) * 4);
   if (e != cudaSuccess) {
     ctx->set_error(std::string("hfb_kfdb_create: ") + cudaGetErrorString(e));
     kfdb_free(db);
@@ -640,24 +647,33 @@ static int kfdb_query_common(hfb_kfdb* db, const float* query, float rel, float 
   *best_score = 0.f;
   db->h_scores_valid = false;
   if (db->size == 0) return HFB_OK;
-  HFB_CUDA(ctx, cudaMemcpyAsync(db->d_query, query, (size_t)db->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+  memcpy(db->h_query, query, (size_t)db->dim * 4);      // page-locked staging: the H2D below is a plain DMA
+  HFB_CUDA(ctx, cudaMemcpyAsync(db->d_query, db->h_query, (size_t)db->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
   HFB_TRY(kfdb_scan(db, db->d_query, 1, db->d_scores, db->capacity, db->d_best));
   HFB_CUDA(ctx, cudaMemsetAsync(db->d_ncand, 0, sizeof(int), ctx->stream));
   kfdb_compact_kernel<<<ceil_div(db->size, 256), 256, 0, ctx->stream>>>(db->d_scores, db->size, db->d_best, rel, floor_,
                                                                        db->d_ncand, db->d_cand_slot, db->d_cand_score);
   HFB_CHECK_LAUNCH(ctx, "kfdb_compact");
-  int nc = 0;
-  unsigned int bu = 0;
-  HFB_CUDA(ctx, cudaMemcpyAsync(&nc, db->d_ncand, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  HFB_CUDA(ctx, cudaMemcpyAsync(&bu, db->d_best, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+  // count, best and the head of the candidate list in one burst, one synchronisation (longer lists: a second fetch)
+  const int head = std::min(KFDB_HEAD, db->size);
+  HFB_CUDA(ctx, cudaMemcpyAsync(db->h_head, db->d_ncand, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(db->h_head + 1, db->d_best, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(db->h_head + 2, db->d_cand_slot, (size_t)head * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(db->h_head + 2 + KFDB_HEAD, db->d_cand_score, (size_t)head * 4, cudaMemcpyDeviceToHost, ctx->stream));
   HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  memcpy(best_score, &bu, 4);
+  const int nc = db->h_head[0];
+  memcpy(best_score, db->h_head + 1, 4);
   if (nc > 0) {
     std::vector<int> slots(nc);
     std::vector<float> sc(nc);
-    HFB_CUDA(ctx, cudaMemcpyAsync(slots.data(), db->d_cand_slot, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaMemcpyAsync(sc.data(), db->d_cand_score, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nc <= head) {
+      memcpy(slots.data(), db->h_head + 2, (size_t)nc * 4);
+      memcpy(sc.data(), db->h_head + 2 + KFDB_HEAD, (size_t)nc * 4);
+    } else {
+      HFB_CUDA(ctx, cudaMemcpyAsync(slots.data(), db->d_cand_slot, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      HFB_CUDA(ctx, cudaMemcpyAsync(sc.data(), db->d_cand_score, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     std::vector<int> order(nc);
     for (int i = 0; i < nc; ++i) order[i] = i;
     std::sort(order.begin(), order.end(), [&](int a, int b) { return db->ids[slots[a]] < db->ids[slots[b]]; });
@@ -1110,7 +1126,8 @@ extern "C" int hfb_kfdb_query_sharded_begin(hfb_kfdb* db, const float* query, fl
   HFB_REQUIRE(ctx, db->d_peer_tab && db->peer_inbox[db->rank], "shard exchange not connected");
   HFB_REQUIRE(ctx, query != nullptr, "null query");
   db->h_scores_valid = false;
-  HFB_CUDA(ctx, cudaMemcpyAsync(db->d_query, query, (size_t)db->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+  memcpy(db->h_query, query, (size_t)db->dim * 4);
+  HFB_CUDA(ctx, cudaMemcpyAsync(db->d_query, db->h_query, (size_t)db->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
   HFB_TRY(kfdb_scan(db, db->d_query, 1, db->d_scores, db->capacity, db->d_best));
   HFB_CUDA(ctx, cudaMemsetAsync(db->d_ncand, 0, sizeof(int), ctx->stream));
   if (db->size > 0) {
