@@ -24,7 +24,7 @@ struct LbaDev {
   int n_cams = 0, n_points = 0, n_edges = 0, n_opt = 0, n_blk = 0, G = 0;
   double *poses = nullptr, *poses_t = nullptr, *points = nullptr, *points_t = nullptr;
   int *edge_cam = nullptr, *pt_ptr = nullptr, *cam_ptr = nullptr, *cam_edges = nullptr, *cam_slot = nullptr,
-      *opt_cams = nullptr;
+      *opt_cams = nullptr, *edge_slot = nullptr;   // edge_slot[e] = cam_slot[edge_cam[e]] (one load instead of a dependent pair)
   double *obs = nullptr, *invs2 = nullptr;
   double *Jc = nullptr, *wo = nullptr, *r = nullptr, *Hpl = nullptr, *chi2_a = nullptr, *chi2_b = nullptr;
   double *Hll = nullptr, *bl = nullptr, *Dinv = nullptr, *rho_pt = nullptr, *scale_pt = nullptr;
@@ -121,20 +121,65 @@ __global__ void lba_linearize_kernel(LbaDev d, const double* __restrict__ poses,
   }
 }
 
-// One CTA per optimisable camera: Hpp (36) and bp (6) summed over the camera's edges in ascending edge order.
-__global__ void lba_camera_kernel(LbaDev d) {
-  const int s = blockIdx.x, c = d.opt_cams[s], t = threadIdx.x;
-  if (t >= 42) return;
-  double acc = 0;
-  const int a = t < 36 ? t / 6 : t - 36, b = t < 36 ? t % 6 : 0;
-  for (int k = d.cam_ptr[c]; k < d.cam_ptr[c + 1]; ++k) {
+__device__ __forceinline__ double lba_shfl_xor(double v, int o) {
+  return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o),
+                          __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
+}
+
+// One CTA per optimisable camera: Hpp (21 upper-triangular entries, mirrored) and bp (6) summed over the camera's edges.
+// Thread t accumulates edges t, t + 256, ... of the camera's (ascending) edge list; the 27 sums are then combined in a
+// fixed order -- register butterfly inside each warp (lane i ends with entry i), warps added in warp order -- so the
+// result is bit-reproducible without a serial walk over the ~10^3 edges of a keyframe.
+__global__ void __launch_bounds__(256) lba_camera_kernel(LbaDev d) {
+  __shared__ double sh[8][32];
+  const int s = blockIdx.x, c = d.opt_cams[s], t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  double v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0;
+  for (int k = d.cam_ptr[c] + t; k < d.cam_ptr[c + 1]; k += 256) {
     const int e = d.cam_edges[k];
     const double* jc = d.Jc + 12 * (size_t)e;
-    if (t < 36) acc += d.wo[e] * (jc[a] * jc[b] + jc[6 + a] * jc[6 + b]);
-    else acc += jc[a] * d.r[2 * e] + jc[6 + a] * d.r[2 * e + 1];
+    double J[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) J[i] = jc[i];
+    const double wo = d.wo[e], r0 = d.r[2 * e], r1 = d.r[2 * e + 1];
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int b2 = a; b2 < 6; ++b2) v[q++] += wo * (J[a] * J[b2] + J[6 + a] * J[6 + b2]);
+      v[21 + a] += J[a] * r0 + J[6 + a] * r1;
+    }
   }
-  if (t < 36) d.Hpp[36 * (size_t)s + t] = acc;
-  else d.bp[6 * (size_t)s + a] = acc;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const double send = up ? v[i] : v[i + o];
+      const double keep = up ? v[i + o] : v[i];
+      v[i] = keep + lba_shfl_xor(send, o);
+    }
+  }
+  sh[warp][lane] = v[0];
+  __syncthreads();
+  if (t < 27) {
+    double tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += sh[w][t];
+    if (t < 21) {
+      int a = 0, rem = t;
+      while (rem >= 6 - a) {
+        rem -= 6 - a;
+        ++a;
+      }
+      const int b2 = a + rem;
+      d.Hpp[36 * (size_t)s + a * 6 + b2] = tot;
+      d.Hpp[36 * (size_t)s + b2 * 6 + a] = tot;
+    } else {
+      d.bp[6 * (size_t)s + (t - 21)] = tot;
+    }
+  }
 }
 
 // Single-CTA fixed-order reductions: out[0] = sum(v[0..n)), optionally out[1] = max |diag| of Hll and Hpp.
@@ -184,8 +229,24 @@ __global__ void __launch_bounds__(256) lba_schur_kernel(LbaDev d, double lambda)
   const int t = threadIdx.x;
   double* part = d.partial + (size_t)blockIdx.x * ((size_t)d.n_blk * 36 + (size_t)d.n_opt * 6);
   double* part_b = part + (size_t)d.n_blk * 36;
+  for (int i = t; i < d.n_blk * 36 + d.n_opt * 6; i += 256) part[i] = 0.0;   // this CTA's private accumulators
+  __syncthreads();
   for (int p = blockIdx.x; p < d.n_points; p += gridDim.x) {
-    if (t == 0) {
+    const int e_begin = d.pt_ptr[p], e_end = d.pt_ptr[p + 1];
+    if (t < 32) {
+      // warp 0: the point's optimisable observations, in edge order (ballot compaction, 32 edges per round)
+      int k = 0;
+      for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+        const int e2 = e0 + t;
+        const int sl = e2 < e_end ? d.edge_slot[e2] : -1;
+        const unsigned m = __ballot_sync(0xffffffffu, sl >= 0);
+        const int pos = k + __popc(m & ((1u << t) - 1u));
+        if (sl >= 0 && pos < LBA_MAX_OBS) sSlot[pos] = sl | (e2 - e_begin) << 16;
+        k += __popc(m);
+      }
+      if (t == 0) sK = k < LBA_MAX_OBS ? k : LBA_MAX_OBS;
+    } else if (t == 32) {
+      // meanwhile one thread of warp 1: Dinv = (Hll + lambda I)^-1 and Dinv bl
       const double* h = d.Hll + 6 * (size_t)p;
       const double a = h[0] + lambda, b = h[1], c = h[2], e = h[3] + lambda, f = h[4], i = h[5] + lambda;
       const double A = e * i - f * f, B = -(b * i - c * f), C = b * f - c * e;
@@ -200,21 +261,12 @@ __global__ void __launch_bounds__(256) lba_schur_kernel(LbaDev d, double lambda)
       sDb[0] = D0 * l0 + D1 * l1 + D2 * l2;
       sDb[1] = D1 * l0 + D3 * l1 + D4 * l2;
       sDb[2] = D2 * l0 + D4 * l1 + D5 * l2;
-      int k = 0;
-      for (int e2 = d.pt_ptr[p]; e2 < d.pt_ptr[p + 1] && k < LBA_MAX_OBS; ++e2) {
-        const int s = d.cam_slot[d.edge_cam[e2]];
-        if (s >= 0) {
-          sSlot[k] = s | (e2 - d.pt_ptr[p]) << 16;
-          ++k;
-        }
-      }
-      sK = k;
     }
     __syncthreads();
     const int k = sK;
     for (int i = t; i < k * 18; i += 256) {
       const int a = i / 18, ij = i % 18;
-      const int e = d.pt_ptr[p] + (sSlot[a] >> 16);
+      const int e = e_begin + (sSlot[a] >> 16);
       sH[a][ij] = d.Hpl[18 * (size_t)e + ij];
     }
     __syncthreads();
@@ -254,27 +306,51 @@ __global__ void __launch_bounds__(256) lba_schur_kernel(LbaDev d, double lambda)
 }
 
 // Hschur = diag(Hpp + lambda I) - sum_g partial_g (mirrored to the full symmetric matrix), bschur = bp - sum_g.
+// Four lanes per output entry: lane q sums the CTA partials g = q, q + 4, ... (eight loads in flight), then the four
+// sums are combined in lane order -- fixed order, so the result stays bit-reproducible.
 __global__ void lba_schur_reduce_kernel(LbaDev d, double lambda, int G) {
   const int N = 6 * d.n_opt;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gi >> 2, q = gi & 3;
   const size_t stride = (size_t)d.n_blk * 36 + (size_t)d.n_opt * 6;
-  if (i < N * N) {
-    const int r = i / N, c = i % N;
+  const bool is_h = i < N * N, is_b = !is_h && i < N * N + N;
+  size_t idx = 0;
+  int r = 0, c = 0;
+  if (is_h) {
+    r = i / N;
+    c = i % N;
     const int br = r / 6, bc = c / 6, ri = r % 6, ci = c % 6;
     // upper triangle is authoritative (also inside diagonal blocks) so that Hschur is bitwise symmetric
     const bool upper = br < bc || (br == bc && ri <= ci);
-    const size_t idx = upper ? (size_t)blk_index(br, bc, d.n_opt) * 36 + ri * 6 + ci
-                             : (size_t)blk_index(bc, br, d.n_opt) * 36 + ci * 6 + ri;
-    double s = 0;
-    for (int g = 0; g < G; ++g) s += d.partial[g * stride + idx];
+    idx = upper ? (size_t)blk_index(br, bc, d.n_opt) * 36 + ri * 6 + ci : (size_t)blk_index(bc, br, d.n_opt) * 36 + ci * 6 + ri;
+  } else if (is_b) {
+    idx = (size_t)d.n_blk * 36 + (i - N * N);
+  }
+  double s = 0;
+  if (is_h || is_b) {
+    int g = q;
+    for (; g + 28 < G; g += 32) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = d.partial[(size_t)(g + 4 * u) * stride + idx];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; g < G; g += 4) s += d.partial[(size_t)g * stride + idx];
+  }
+  // lanes 4k .. 4k+3 hold the four strided sums of one entry (the whole warp takes part in the shuffles)
+  const double s1 = __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(s), 1), __shfl_down_sync(0xffffffffu, __double2loint(s), 1));
+  const double s2 = __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(s), 2), __shfl_down_sync(0xffffffffu, __double2loint(s), 2));
+  const double s3 = __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(s), 3), __shfl_down_sync(0xffffffffu, __double2loint(s), 3));
+  if (q != 0) return;
+  const double tot = ((s + s1) + s2) + s3;
+  if (is_h) {
+    const int br = r / 6, bc = c / 6, ri = r % 6, ci = c % 6;
     double base = 0;
     if (br == bc) base = d.Hpp[36 * (size_t)br + ri * 6 + ci] + (ri == ci ? lambda : 0.0);
-    d.Hs[i] = base - s;
-  } else if (i < N * N + N) {
-    const int r = i - N * N;
-    double s = 0;
-    for (int g = 0; g < G; ++g) s += d.partial[g * stride + (size_t)d.n_blk * 36 + r];
-    d.bs[r] = d.bp[r] - s;
+    d.Hs[i] = base - tot;
+  } else if (is_b) {
+    d.bs[i - N * N] = d.bp[i - N * N] - tot;
   }
 }
 
@@ -305,6 +381,208 @@ __global__ void lba_backsub_kernel(LbaDev d, double lambda) {
   d.points_t[3 * p + 2] = d.points[3 * p + 2] + x2;
   d.scale_pt[p] = x0 * (lambda * x0 + d.bl[3 * p]) + x1 * (lambda * x1 + d.bl[3 * p + 1]) +
                   x2 * (lambda * x2 + d.bl[3 * p + 2]);
+}
+
+__device__ void po_pose_oplus(const double* pose, const double* u, double* out);
+
+// rho and scale sums of one LM trial in one launch (same strided + tree order as lba_reduce_kernel)
+__global__ void lba_reduce2_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ out,
+                                   int ia, int ib) {
+  __shared__ double sh[1024];
+  const int t = threadIdx.x;
+  for (int which = 0; which < 2; ++which) {
+    const double* v = which ? b : a;
+    double acc = 0;
+    for (int i = t; i < n; i += 1024) acc += v[i];
+    __syncthreads();
+    sh[t] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+      if (t < s) sh[t] += sh[t + s];
+      __syncthreads();
+    }
+    if (t == 0) out[which ? ib : ia] = sh[0];
+  }
+}
+
+// The reduced camera system on the device (g2o: LinearSolverEigen::solve, Thirdparty/g2o/g2o/solvers/
+// linear_solver_eigen.h:94-124, a sparse LDLT of the same matrix): one CTA, Hschur as a packed lower triangle in shared
+// memory (N <= 192: 148 KB), right-looking Cholesky (the rank-1 update of the trailing triangle is flattened over the
+// whole CTA), column-oriented forward / backward substitution, then the pose update
+// exp(xp) * T of every optimisable camera (types_six_dof_expmap.h:73-76) and the camera part of the gain-ratio
+// denominator.  scal[4] = sum xp (lambda xp + bp), scal[5] = 1 if the factorisation succeeded (else xp = 0).
+#define LBA_SOLVE_MAX_N 192
+__device__ __forceinline__ int lcol(int k, int N) { return k * N - k * (k - 1) / 2; }   // start of packed column k (rows k..N-1)
+
+__global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda) {
+  extern __shared__ double sL[];                 // lower triangle packed BY COLUMNS: L[i][k] at lcol(k) + i - k, so the
+                                                 // rows i = j + tid of one column step read consecutive words
+  __shared__ double s_b[LBA_SOLVE_MAX_N], s_y[LBA_SOLVE_MAX_N], s_invd[LBA_SOLVE_MAX_N];
+  __shared__ int s_fail;
+  const int N = 6 * d.n_opt, t = threadIdx.x;
+  const int total = N * (N + 1) / 2;
+  unsigned char* col_of = reinterpret_cast<unsigned char*>(sL + total);   // packed index -> column
+  for (int k = 0; k < N; ++k)
+    for (int i = k + t; i < N; i += 256) col_of[lcol(k, N) + i - k] = (unsigned char)k;
+  for (int i = t; i < N; i += 256) s_b[i] = d.bs[i];
+  if (t == 0) s_fail = 0;
+  __syncthreads();
+  for (int q = t; q < total; q += 256) {         // Hs is bitwise symmetric: element (r, c), r >= c, read as Hs[c][r]
+    const int c = col_of[q];
+    sL[q] = d.Hs[(size_t)c * N + c + q - lcol(c, N)];
+  }
+  __syncthreads();
+  // Blocked right-looking Cholesky on the 6 x 6 camera blocks (N = 6 n_opt) with one block of look-ahead: per block
+  // column (i) one thread per row below solves its 1 x 6 panel row, (ii) warps 1..7 apply the rank-6 update to the
+  // trailing triangle -- a CONTIGUOUS range of the column-packed array -- while warp 0 updates just the NEXT diagonal
+  // block and factors it (the only serial part: six dependent pivots), so the pivots hide behind the update.
+  const int lane = t & 31;
+  auto factor_diag = [&](int j0) {                 // warp 0: in-place Cholesky of the 6 x 6 block at (j0, j0)
+    for (int c = 0; c < 6; ++c) {
+      const int j = j0 + c, cj = lcol(j, N);
+      const double dj = sL[cj];
+      const bool bad = !(dj > 0.0) || !isfinite(dj);
+      const double inv = bad ? 0.0 : rsqrt(dj);
+      __syncwarp();
+      if (lane == 0) {
+        if (bad) s_fail = 1;
+        s_invd[j] = inv;
+        sL[cj] = bad ? 1.0 : dj * inv;
+      } else if (lane < 6 - c) {
+        sL[cj + lane] *= inv;                      // rows j + lane of column j inside the diagonal block
+      }
+      __syncwarp();
+      // remaining entries of the diagonal block: columns c2 in (c, 5], rows r2 in [c2, 5] (at most 15)
+      if (lane < 15) {
+        int c2 = c + 1, e = lane;
+        while (c2 < 6 && e >= 6 - c2) {
+          e -= 6 - c2;
+          ++c2;
+        }
+        if (c2 < 6) {
+          const int r2 = c2 + e;
+          sL[lcol(j0 + c2, N) + r2 - c2] -= sL[cj + r2 - c] * sL[cj + c2 - c];
+        }
+      }
+      __syncwarp();
+    }
+  };
+  if (t < 32 && N > 0) factor_diag(0);
+  __syncthreads();
+  for (int j0 = 0; j0 < N; j0 += 6) {
+    if (s_fail) break;                             // uniform: written before the last barrier
+    {
+      const int i = j0 + 6 + t;                    // panel: row i of L[:, j0 .. j0+5]
+      if (i < N) {
+        double l[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double v = sL[lcol(j0 + c, N) + i - (j0 + c)];
+#pragma unroll
+          for (int c1 = 0; c1 < c; ++c1) v -= l[c1] * sL[lcol(j0 + c1, N) + (c - c1)];   // L[j0+c][j0+c1]
+          l[c] = v * s_invd[j0 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sL[lcol(j0 + c, N) + i - (j0 + c)] = l[c];
+      }
+    }
+    __syncthreads();
+    if (j0 + 6 < N) {
+      const double* col[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) col[c] = sL + lcol(j0 + c, N) - (j0 + c);   // col[c][r] = L[r][j0 + c]
+      if (t < 32) {
+        // next diagonal block (rows and columns j0+6 .. j0+11): 21 entries, then its factorisation
+        if (lane < 21) {
+          int c2 = 0, e = lane;
+          while (e >= 6 - c2) {
+            e -= 6 - c2;
+            ++c2;
+          }
+          const int cc = j0 + 6 + c2, r = cc + e;
+          double acc = sL[lcol(cc, N) + r - cc];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc -= col[c][r] * col[c][cc];
+          sL[lcol(cc, N) + r - cc] = acc;
+        }
+        __syncwarp();
+        factor_diag(j0 + 6);
+      } else {
+        for (int q = lcol(j0 + 6, N) + (t - 32); q < total; q += 224) {
+          const int cc = col_of[q];
+          const int r = cc + q - lcol(cc, N);
+          if (r < j0 + 12) continue;               // the next diagonal block belongs to warp 0
+          double acc = sL[q];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc -= col[c][r] * col[c][cc];
+          sL[q] = acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (!s_fail) {
+    // blocked substitutions: thread 0 solves the 6 x 6 triangle of a camera, then every remaining row takes the rank-6
+    // correction; the solved entries go to a second array so nothing that is still being read is overwritten
+    for (int j0 = 0; j0 < N; j0 += 6) {            // forward L y = b
+      if (t == 0) {
+        double y[6];
+        for (int c = 0; c < 6; ++c) {
+          double v = s_b[j0 + c];
+          for (int c1 = 0; c1 < c; ++c1) v -= sL[lcol(j0 + c1, N) + (c - c1)] * y[c1];
+          y[c] = v * s_invd[j0 + c];
+          s_y[j0 + c] = y[c];
+        }
+      }
+      __syncthreads();
+      const int i = j0 + 6 + t;
+      if (i < N) {
+        double v = s_b[i];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v -= sL[lcol(j0 + c, N) + i - (j0 + c)] * s_y[j0 + c];
+        s_b[i] = v;
+      }
+      __syncthreads();
+    }
+    for (int j0 = N - 6; j0 >= 0; j0 -= 6) {       // backward L^T x = y
+      if (t == 0) {
+        double x[6];
+        for (int c = 5; c >= 0; --c) {
+          double v = s_y[j0 + c];
+          for (int c1 = c + 1; c1 < 6; ++c1) v -= sL[lcol(j0 + c, N) + (c1 - c)] * x[c1];   // L[j0+c1][j0+c]
+          x[c] = v * s_invd[j0 + c];
+          s_b[j0 + c] = x[c];
+        }
+      }
+      __syncthreads();
+      if (t < j0) {
+        double v = s_y[t];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v -= sL[lcol(t, N) + (j0 + c) - t] * s_b[j0 + c];        // L[j0+c][t]
+        s_y[t] = v;
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = t; i < N; i += 256) d.xp[i] = s_fail ? 0.0 : s_b[i];
+  __syncthreads();
+  // trial poses: every camera copied, optimisable ones updated
+  for (int i = t; i < d.n_cams * 7; i += 256) d.poses_t[i] = d.poses[i];
+  __syncthreads();
+  if (t < d.n_opt) {
+    double u[6];
+    for (int i = 0; i < 6; ++i) u[i] = s_fail ? 0.0 : s_b[6 * t + i];
+    const int c = d.opt_cams[t];
+    po_pose_oplus(d.poses + 7 * (size_t)c, u, d.poses_t + 7 * (size_t)c);
+  }
+  if (t == 0) {
+    double sc = 0;
+    if (!s_fail)
+      for (int i = 0; i < N; ++i) sc += s_b[i] * (lambda * s_b[i] + d.bp[i]);
+    d.scal[4] = sc;
+    d.scal[5] = s_fail ? 0.0 : 1.0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host helpers
@@ -415,7 +693,7 @@ static void h_pose_oplus(const double* pose, const double* u, double* out) {
 }
 
 struct LbaHost {
-  std::vector<int> pt_ptr, cam_ptr, cam_edges, cam_slot, opt_cams;
+  std::vector<int> pt_ptr, cam_ptr, cam_edges, cam_slot, opt_cams, edge_slot;
 };
 
 static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost& h, uint8_t** arena_out) {
@@ -456,7 +734,9 @@ static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost
   }
   d.n_cams = nc; d.n_points = np; d.n_edges = ne; d.n_opt = no;
   d.n_blk = no * (no + 1) / 2;
-  d.G = std::max(1, std::min(ctx->n_sm, np));
+  d.G = std::max(1, std::min(2 * ctx->n_sm, np));
+  h.edge_slot.resize(ne);
+  for (int e = 0; e < ne; ++e) h.edge_slot[e] = h.cam_slot[pr->edge_cam[e]];
   for (int i = 0; i < 4; ++i) d.K[i] = (double)pr->K[i];
   d.delta = pr->huber_delta;
   // one arena
@@ -471,7 +751,7 @@ static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost
   const size_t o_poses = take(nc * 7 * 8), o_poses_t = take(nc * 7 * 8), o_points = take((size_t)np * 24),
                o_points_t = take((size_t)np * 24), o_ecam = take((size_t)ne * 4), o_ptptr = take((size_t)(np + 1) * 4),
                o_camptr = take((size_t)(nc + 1) * 4), o_camedges = take((size_t)ne * 4), o_slot = take((size_t)nc * 4),
-               o_opt = take((size_t)std::max(no, 1) * 4), o_obs = take((size_t)ne * 16), o_is2 = take((size_t)ne * 8),
+               o_opt = take((size_t)std::max(no, 1) * 4), o_eslot = take((size_t)ne * 4 + 4), o_obs = take((size_t)ne * 16), o_is2 = take((size_t)ne * 8),
                o_Jc = take((size_t)ne * 96), o_wo = take((size_t)ne * 8), o_r = take((size_t)ne * 16),
                o_Hpl = take((size_t)ne * 144), o_chia = take((size_t)ne * 8), o_chib = take((size_t)ne * 8),
                o_Hll = take((size_t)np * 48), o_bl = take((size_t)np * 24), o_Dinv = take((size_t)np * 48),
@@ -486,6 +766,7 @@ static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost
   d.points = (double*)(a + o_points); d.points_t = (double*)(a + o_points_t);
   d.edge_cam = (int*)(a + o_ecam); d.pt_ptr = (int*)(a + o_ptptr); d.cam_ptr = (int*)(a + o_camptr);
   d.cam_edges = (int*)(a + o_camedges); d.cam_slot = (int*)(a + o_slot); d.opt_cams = (int*)(a + o_opt);
+  d.edge_slot = (int*)(a + o_eslot);
   d.obs = (double*)(a + o_obs); d.invs2 = (double*)(a + o_is2);
   d.Jc = (double*)(a + o_Jc); d.wo = (double*)(a + o_wo); d.r = (double*)(a + o_r); d.Hpl = (double*)(a + o_Hpl);
   d.chi2_a = (double*)(a + o_chia); d.chi2_b = (double*)(a + o_chib);
@@ -500,6 +781,7 @@ static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost
   if (ne) {
     HFB_CUDA(ctx, cudaMemcpyAsync(d.edge_cam, pr->edge_cam, (size_t)ne * 4, cudaMemcpyHostToDevice, st));
     HFB_CUDA(ctx, cudaMemcpyAsync(d.cam_edges, h.cam_edges.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(d.edge_slot, h.edge_slot.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, st));
     HFB_CUDA(ctx, cudaMemcpyAsync(d.obs, pr->obs, (size_t)ne * 16, cudaMemcpyHostToDevice, st));
     HFB_CUDA(ctx, cudaMemcpyAsync(d.invs2, pr->inv_sigma2, (size_t)ne * 8, cudaMemcpyHostToDevice, st));
   }
@@ -519,7 +801,7 @@ static int lba_build(hfb_ctx* ctx, LbaDev& d, double* chi2_buf, int want_maxdiag
     HFB_CHECK_LAUNCH(ctx, "lba_linearize");
   }
   if (d.n_opt > 0) {
-    lba_camera_kernel<<<d.n_opt, 64, 0, ctx->stream>>>(d);
+    lba_camera_kernel<<<d.n_opt, 256, 0, ctx->stream>>>(d);
     HFB_CHECK_LAUNCH(ctx, "lba_camera");
   }
   lba_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(d.rho_pt, d.n_points, d.scal, 0, d, want_maxdiag);
@@ -528,15 +810,16 @@ static int lba_build(hfb_ctx* ctx, LbaDev& d, double* chi2_buf, int want_maxdiag
 }
 
 static int lba_schur(hfb_ctx* ctx, LbaDev& d, double lambda) {
-  const size_t part_stride = (size_t)d.n_blk * 36 + (size_t)d.n_opt * 6;
-  HFB_CUDA(ctx, cudaMemsetAsync(d.partial, 0, (size_t)d.G * part_stride * 8, ctx->stream));
   if (d.n_points > 0) {
-    lba_schur_kernel<<<d.G, 256, 0, ctx->stream>>>(d, lambda);
+    lba_schur_kernel<<<d.G, 256, 0, ctx->stream>>>(d, lambda);   // zeroes its CTA-private accumulators itself
     HFB_CHECK_LAUNCH(ctx, "lba_schur");
+  } else {
+    const size_t part_stride = (size_t)d.n_blk * 36 + (size_t)d.n_opt * 6;
+    HFB_CUDA(ctx, cudaMemsetAsync(d.partial, 0, (size_t)d.G * part_stride * 8, ctx->stream));
   }
   const int N = 6 * d.n_opt;
   if (N > 0) {
-    lba_schur_reduce_kernel<<<ceil_div(N * N + N, 256), 256, 0, ctx->stream>>>(d, lambda, d.G);
+    lba_schur_reduce_kernel<<<ceil_div(4 * (N * N + N), 256), 256, 0, ctx->stream>>>(d, lambda, d.G);
     HFB_CHECK_LAUNCH(ctx, "lba_schur_reduce");
   }
   return HFB_OK;
@@ -572,6 +855,15 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   HFB_TRY(lba_setup(ctx, problem, d, h, &arena));
   cudaStream_t st = ctx->stream;
   const int no = d.n_opt, N = 6 * no, nc = d.n_cams;
+  // The reduced system is solved on the device (lba_solve_kernel) unless it does not fit one CTA's shared memory or the
+  // host-solve mode is requested (HFB_LBA_HOST_SOLVE=1: the round-1 path, kept as the cross-check of the device solver).
+  const char* hs_env = getenv("HFB_LBA_HOST_SOLVE");
+  const size_t solve_smem = (size_t)N * (N + 1) / 2 * 9 + 16;   // packed triangle (doubles) + packed-index -> column bytes
+  const bool dev_solve = N > 0 && N <= LBA_SOLVE_MAX_N && !(hs_env && hs_env[0] == '1');
+  if (dev_solve) {
+    static SmemOptIn optin;
+    HFB_CUDA(ctx, optin.ensure(lba_solve_kernel, ctx->device, (size_t)LBA_SOLVE_MAX_N * (LBA_SOLVE_MAX_N + 1) / 2 * 9 + 16));
+  }
   std::vector<double> poses(problem->poses, problem->poses + (size_t)nc * 7), poses_t(poses);
   std::vector<double> Hs((size_t)N * N), bs(N), bp(N), xp(N);
   auto terminate = [&]() { return stop_flag && *stop_flag; };
@@ -582,7 +874,7 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   double* chi2_last = d.chi2_a;   // buffer holding the most recent computeActiveErrors result
   double* chi2_other = d.chi2_b;
   double initial_chi = 0.0, current_chi = 0.0;
-  double scal[4];
+  double scal[6];
   // chi2 at the initial estimate (iterations == 0 or immediate stop still reports it)
   if (d.n_points > 0) {
     lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, d.poses, d.points, chi2_last, 1);
@@ -611,18 +903,23 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
     do {
       HFB_TRY(lba_schur(ctx, d, lambda));
       bool ok2 = true;
-      if (N) {
-        HFB_CUDA(ctx, cudaMemcpyAsync(Hs.data(), d.Hs, (size_t)N * N * 8, cudaMemcpyDeviceToHost, st));
-        HFB_CUDA(ctx, cudaMemcpyAsync(bs.data(), d.bs, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
-        HFB_CUDA(ctx, cudaStreamSynchronize(st));
-        xp = bs;
-        ok2 = cholesky_solve(Hs, xp, N);
-        if (!ok2) std::fill(xp.begin(), xp.end(), 0.0);
-        HFB_CUDA(ctx, cudaMemcpyAsync(d.xp, xp.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
+      if (dev_solve) {
+        lba_solve_kernel<<<1, 256, solve_smem, st>>>(d, lambda);
+        HFB_CHECK_LAUNCH(ctx, "lba_solve");
+      } else {
+        if (N) {
+          HFB_CUDA(ctx, cudaMemcpyAsync(Hs.data(), d.Hs, (size_t)N * N * 8, cudaMemcpyDeviceToHost, st));
+          HFB_CUDA(ctx, cudaMemcpyAsync(bs.data(), d.bs, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+          HFB_CUDA(ctx, cudaStreamSynchronize(st));
+          xp = bs;
+          ok2 = cholesky_solve(Hs, xp, N);
+          if (!ok2) std::fill(xp.begin(), xp.end(), 0.0);
+          HFB_CUDA(ctx, cudaMemcpyAsync(d.xp, xp.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
+        }
+        poses_t = poses;
+        for (int s = 0; s < no; ++s) h_pose_oplus(&poses[(size_t)h.opt_cams[s] * 7], &xp[(size_t)6 * s], &poses_t[(size_t)h.opt_cams[s] * 7]);
+        HFB_CUDA(ctx, cudaMemcpyAsync(d.poses_t, poses_t.data(), (size_t)nc * 56, cudaMemcpyHostToDevice, st));
       }
-      poses_t = poses;
-      for (int s = 0; s < no; ++s) h_pose_oplus(&poses[(size_t)h.opt_cams[s] * 7], &xp[(size_t)6 * s], &poses_t[(size_t)h.opt_cams[s] * 7]);
-      HFB_CUDA(ctx, cudaMemcpyAsync(d.poses_t, poses_t.data(), (size_t)nc * 56, cudaMemcpyHostToDevice, st));
       if (d.n_points > 0) {
         lba_backsub_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, lambda);
         HFB_CHECK_LAUNCH(ctx, "lba_backsub");
@@ -630,16 +927,17 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
         HFB_CHECK_LAUNCH(ctx, "lba_errors");
       }
       std::swap(chi2_last, chi2_other);
-      lba_reduce_kernel<<<1, 1024, 0, st>>>(d.rho_pt, d.n_points, d.scal, 2, d, 0);
-      HFB_CHECK_LAUNCH(ctx, "lba_reduce");
-      lba_reduce_kernel<<<1, 1024, 0, st>>>(d.scale_pt, d.n_points, d.scal, 3, d, 0);
-      HFB_CHECK_LAUNCH(ctx, "lba_reduce");
-      HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 32, cudaMemcpyDeviceToHost, st));
+      lba_reduce2_kernel<<<1, 1024, 0, st>>>(d.rho_pt, d.scale_pt, d.n_points, d.scal, 2, 3);
+      HFB_CHECK_LAUNCH(ctx, "lba_reduce2");
+      HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 48, cudaMemcpyDeviceToHost, st));
       HFB_CUDA(ctx, cudaStreamSynchronize(st));
+      if (dev_solve) ok2 = scal[5] != 0.0;
       ++trials;
       const double temp_chi = ok2 ? scal[2] : 1.7976931348623157e308;
       double scale = scal[3] + 1e-3;
-      for (int i = 0; i < N; ++i) scale += xp[i] * (lambda * xp[i] + bp[i]);
+      if (dev_solve) scale += scal[4];
+      else
+        for (int i = 0; i < N; ++i) scale += xp[i] * (lambda * xp[i] + bp[i]);
       rho = (current_chi - temp_chi) / scale;
       if (rho > 0 && std::isfinite(temp_chi)) {
         double alpha = 1.0 - pow(2 * rho - 1, 3);
@@ -647,7 +945,7 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
         lambda *= std::max(good_lo, alpha);
         ni = 2.0;
         current_chi = temp_chi;
-        poses = poses_t;
+        if (!dev_solve) poses = poses_t;
         std::swap(d.poses, d.poses_t);
         std::swap(d.points, d.points_t);
       } else {
@@ -668,7 +966,10 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
     HFB_CHECK_LAUNCH(ctx, "lba_errors");
     HFB_CUDA(ctx, cudaMemcpyAsync(depth_positive_out, d.depth_ok, (size_t)d.n_edges, cudaMemcpyDeviceToHost, st));
   }
-  if (poses_out) memcpy(poses_out, poses.data(), (size_t)nc * 56);
+  if (poses_out) {
+    if (dev_solve) HFB_CUDA(ctx, cudaMemcpyAsync(poses_out, d.poses, (size_t)nc * 56, cudaMemcpyDeviceToHost, st));
+    else memcpy(poses_out, poses.data(), (size_t)nc * 56);
+  }
   if (points_out && d.n_points)
     HFB_CUDA(ctx, cudaMemcpyAsync(points_out, d.points, (size_t)d.n_points * 24, cudaMemcpyDeviceToHost, st));
   if (chi2_out && d.n_edges)
@@ -693,7 +994,8 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
 // EdgeSE3ProjectXYZOnlyPose edges (src/OptimizableTypes.cpp:49-64), Huber kernel dropped after the third round,
 // inlier re-classification with chi2 > 5.991 after every round -- runs on the device without a host round trip.
 // The problem is a few hundred edges: latency, not bandwidth, so everything (6x6 Cholesky, exp map) stays on chip.
-#define PO_THREADS 256
+#define PO_THREADS 128
+#define PO_WARPS (PO_THREADS / 32)
 #define PO_NV 28   // 21 upper-triangular H entries + 6 b entries + 1 robust chi2
 
 __device__ __forceinline__ void po_edge(const double* R, const double* t, const double* K, const double* Xw,
@@ -707,28 +1009,50 @@ __device__ __forceinline__ void po_edge(const double* R, const double* t, const 
   chi2 = is2 * (e0 * e0 + e1 * e1);
 }
 
-// fixed-order block reduction of NV doubles per thread; result valid in thread 0
-template <int NV>
-__device__ __forceinline__ void po_reduce(double (&v)[NV], double (*sh)[NV]) {
+__device__ __forceinline__ double po_shfl_xor(double v, int o) {
+  return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o),
+                          __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
+}
+
+// Fixed-order block sum of 32 doubles per thread (PO_NV used, the rest zero): a register butterfly inside each warp
+// (recursive halving: 31 exchanges instead of 32 x 5 shuffle reductions; lane i ends up with entry i summed over the
+// warp), then entry i is summed over the warps in warp order.  out[i] valid for every thread after the final barrier.
+__device__ __forceinline__ void po_reduce32(double (&v)[32], double (*sh)[32], double* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], s);
-  }
-  __syncthreads();
-  if (lane == 0)
-#pragma unroll
-    for (int i = 0; i < NV; ++i) sh[warp][i] = v[i];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      double t = 0;
-      for (int w = 0; w < PO_THREADS / 32; ++w) t += sh[w][i];
-      v[i] = t;
+    for (int i = 0; i < o; ++i) {
+      const double send = up ? v[i] : v[i + o];
+      const double keep = up ? v[i + o] : v[i];
+      v[i] = keep + po_shfl_xor(send, o);
     }
   }
+  sh[warp][lane] = v[0];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < PO_WARPS; ++w) t += sh[w][threadIdx.x];
+    out[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+// fixed-order block sum of one double per thread
+__device__ __forceinline__ double po_reduce1(double v, double* sh, double* out) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += po_shfl_xor(v, s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < PO_WARPS; ++w) t += sh[w];
+    *out = t;
+  }
+  __syncthreads();
+  return *out;
 }
 
 __device__ void po_pose_oplus(const double* pose, const double* u, double* out) {
@@ -827,19 +1151,35 @@ __device__ bool po_chol6(const double* Hu, double lambda, const double* b, doubl
   return true;
 }
 
-__global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const double* __restrict__ Xw,
-                                                              const double* __restrict__ obs,
-                                                              const double* __restrict__ invs2, const double* __restrict__ Kd,
-                                                              double delta, const double* __restrict__ pose0,
-                                                              double* __restrict__ cached, unsigned char* __restrict__ outlier,
-                                                              double* __restrict__ pose_out, int* __restrict__ stats) {
-  __shared__ double sh[PO_THREADS / 32][PO_NV];
-  __shared__ double s_pose[7], s_trial[7], s_x[6], s_b[6], s_Hu[21];
+// io: [n*3 Xw | n*2 obs | n invs2 | 4 K | 7 pose0] doubles in, [7 pose | 3 stats (as doubles)] + n outlier bytes out.  The
+// edges are staged in shared memory once (they are re-read ~50 times: every LM trial is one pass over them).
+__global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const double* __restrict__ in, double delta,
+                                                              int edges_in_smem, double* __restrict__ cached_g,
+                                                              unsigned char* __restrict__ outlier_g, double* __restrict__ out) {
+  extern __shared__ double s_dyn[];   // edges_in_smem: [n*3 | n*2 | n | n cached] doubles + n outlier bytes
+  __shared__ double sh[PO_WARPS][32], s_v[32], sh1[PO_WARPS], s_one;
+  __shared__ double s_pose[7], s_trial[7], s_x[6];
   __shared__ double s_lambda, s_ni, s_cur, s_ini, s_rho;
-  __shared__ int s_ok, s_cont, s_stop, s_nbad_lm, s_qmax, s_trials, s_iters, s_nactive;
+  __shared__ int s_ok, s_cont, s_stop, s_nbad_lm, s_qmax, s_trials, s_iters;
   const int tid = threadIdx.x;
-  const double K[4] = {Kd[0], Kd[1], Kd[2], Kd[3]};
+  const double* gX = in;
+  const double* gO = in + (size_t)3 * n;
+  const double* gS = in + (size_t)5 * n;
+  const double* gK = in + (size_t)6 * n;
+  const double* pose0 = gK + 4;
+  const double K[4] = {gK[0], gK[1], gK[2], gK[3]};
   const double dsqr = delta * delta;
+  const double *Xw = gX, *obs = gO, *invs2 = gS;
+  double* cached = cached_g;
+  unsigned char* outlier = outlier_g;
+  if (edges_in_smem) {
+    for (int i = tid; i < 6 * n; i += PO_THREADS) s_dyn[i] = in[i];
+    Xw = s_dyn;
+    obs = s_dyn + (size_t)3 * n;
+    invs2 = s_dyn + (size_t)5 * n;
+    cached = s_dyn + (size_t)6 * n;
+    outlier = reinterpret_cast<unsigned char*>(s_dyn + (size_t)7 * n);
+  }
   if (tid == 0) {
     s_trials = 0;
     s_iters = 0;
@@ -862,13 +1202,12 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
       double R[9];
       quat_to_R(s_pose, R);
       const double t3[3] = {s_pose[4], s_pose[5], s_pose[6]};
-      double v[PO_NV];
+      double v[32];
 #pragma unroll
-      for (int i = 0; i < PO_NV; ++i) v[i] = 0;
-      int nact = 0;
+      for (int i = 0; i < 32; ++i) v[i] = 0;
       for (int e = tid; e < n; e += PO_THREADS) {
         if (outlier[e]) continue;
-        ++nact;
+        v[28] += 1.0;                       // active edges
         double e0, e1, chi2, x, y, z;
         po_edge(R, t3, K, Xw + 3 * e, obs + 2 * e, invs2[e], e0, e1, chi2, x, y, z);
         cached[e] = chi2;
@@ -889,21 +1228,15 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
           v[21 + i] += J0[i] * r0 + J1[i] * r1;
         }
       }
-      double cnt[1] = {(double)nact};
-      po_reduce<PO_NV>(v, sh);
-      __shared__ double sh1[PO_THREADS / 32][1];
-      po_reduce<1>(cnt, sh1);
+      po_reduce32(v, sh, s_v);
       if (tid == 0) {
-        s_nactive = (int)cnt[0];
-        for (int i = 0; i < 21; ++i) s_Hu[i] = v[i];
-        for (int i = 0; i < 6; ++i) s_b[i] = v[21 + i];
-        s_cur = v[27];
-        s_ini = v[27];
+        s_cur = s_v[27];
+        s_ini = s_v[27];
         if (it == 0) {
           double md = 0;
           int k = 0;
           for (int i = 0; i < 6; ++i) {
-            md = fmax(md, fabs(v[k]));
+            md = fmax(md, fabs(s_v[k]));
             k += 6 - i;
           }
           s_lambda = 1e-5 * md;
@@ -914,12 +1247,12 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
         s_rho = 0;
       }
       __syncthreads();
-      if (s_nactive == 0) break;
+      if (s_v[28] == 0.0) break;
       // ---- Levenberg trials
       while (true) {
         if (tid == 0) {
           double x[6];
-          s_ok = po_chol6(s_Hu, s_lambda, s_b, x) ? 1 : 0;
+          s_ok = po_chol6(s_v, s_lambda, s_v + 21, x) ? 1 : 0;
           if (!s_ok)
             for (int i = 0; i < 6; ++i) x[i] = 0;
           for (int i = 0; i < 6; ++i) s_x[i] = x[i];
@@ -929,20 +1262,20 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
         double Rt[9];
         quat_to_R(s_trial, Rt);
         const double tt[3] = {s_trial[4], s_trial[5], s_trial[6]};
-        double c[1] = {0};
+        double c = 0;
         for (int e = tid; e < n; e += PO_THREADS) {
           if (outlier[e]) continue;
           double e0, e1, chi2, x, y, z;
           po_edge(Rt, tt, K, Xw + 3 * e, obs + 2 * e, invs2[e], e0, e1, chi2, x, y, z);
           cached[e] = chi2;
           const bool inl = !robust || chi2 <= dsqr;
-          c[0] += inl ? chi2 : 2 * sqrt(fmax(chi2, 1e-300)) * delta - dsqr;
+          c += inl ? chi2 : 2 * sqrt(fmax(chi2, 1e-300)) * delta - dsqr;
         }
-        po_reduce<1>(c, sh1);
+        c = po_reduce1(c, sh1, &s_one);
         if (tid == 0) {
-          const double temp = s_ok ? c[0] : 1.7976931348623157e308;
+          const double temp = s_ok ? c : 1.7976931348623157e308;
           double scale = 1e-3;
-          for (int i = 0; i < 6; ++i) scale += s_x[i] * (s_lambda * s_x[i] + s_b[i]);
+          for (int i = 0; i < 6; ++i) scale += s_x[i] * (s_lambda * s_x[i] + s_v[21 + i]);
           const double rho = (s_cur - temp) / scale;
           s_rho = rho;
           ++s_trials;
@@ -979,7 +1312,7 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
     double R[9];
     quat_to_R(s_pose, R);
     const double t3[3] = {s_pose[4], s_pose[5], s_pose[6]};
-    double bad[1] = {0};
+    double bad = 0;
     for (int e = tid; e < n; e += PO_THREADS) {
       double chi2 = cached[e];
       if (outlier[e]) {
@@ -988,22 +1321,19 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
       }
       const bool o = (float)chi2 > 5.991f;
       outlier[e] = o ? 1 : 0;
-      bad[0] += o ? 1.0 : 0.0;
+      bad += o ? 1.0 : 0.0;
     }
-    __shared__ double sh2[PO_THREADS / 32][1];
-    po_reduce<1>(bad, sh2);
-    __shared__ int s_bad;
-    if (tid == 0) s_bad = (int)bad[0];
-    __syncthreads();
-    n_bad = s_bad;
+    n_bad = (int)po_reduce1(bad, sh1, &s_one);
     if (n < 10) break;
   }
-  if (tid < 7) pose_out[tid] = s_pose[tid];
+  if (tid < 7) out[tid] = s_pose[tid];
   if (tid == 0) {
-    stats[0] = n - n_bad;
-    stats[1] = s_trials;
-    stats[2] = s_iters;
+    out[7] = n - n_bad;
+    out[8] = s_trials;
+    out[9] = s_iters;
   }
+  if (edges_in_smem)
+    for (int e = tid; e < n; e += PO_THREADS) outlier_g[e] = outlier[e];
 }
 
 extern "C" int hfb_pose_optimize(hfb_ctx* ctx, const float* K, const double* pose_in, int32_t n, const double* Xw,
@@ -1017,29 +1347,35 @@ extern "C" int hfb_pose_optimize(hfb_ctx* ctx, const float* K, const double* pos
     if (n_trials) *n_trials = 0;
     return HFB_OK;
   }
+  // one page-locked block in, one out: [Xw | obs | invs2 | K | pose0] -> [pose | stats] + outlier flags
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t oX = 0, oO = oX + al((size_t)n * 24), oS = oO + al((size_t)n * 16), oK = oS + al((size_t)n * 8),
-               oP = oK + 256, oC = oP + 256, oF = oC + al((size_t)n * 8), oPo = oF + al((size_t)n), oSt = oPo + 256,
-               total = oSt + 256;
+  const size_t in_d = (size_t)6 * n + 4 + 7, in_bytes = al(in_d * 8), out_bytes = al(10 * 8 + (size_t)n);
+  const size_t oIn = 0, oOut = in_bytes, oC = oOut + out_bytes, total = oC + al((size_t)n * 8);
   HFB_TRY(ctx->ensure_scratch(total));
+  HFB_TRY(ctx->ensure_stage(in_bytes + out_bytes));
   uint8_t* a = reinterpret_cast<uint8_t*>(ctx->d_scratch);
+  double* hin = reinterpret_cast<double*>(ctx->h_stage);
+  uint8_t* hout = reinterpret_cast<uint8_t*>(ctx->h_stage) + in_bytes;
+  memcpy(hin, Xw, (size_t)n * 24);
+  memcpy(hin + (size_t)3 * n, obs, (size_t)n * 16);
+  memcpy(hin + (size_t)5 * n, inv_sigma2, (size_t)n * 8);
+  for (int i = 0; i < 4; ++i) hin[(size_t)6 * n + i] = (double)K[i];
+  memcpy(hin + (size_t)6 * n + 4, pose_in, 56);
   cudaStream_t st = ctx->stream;
-  const double Kd[4] = {(double)K[0], (double)K[1], (double)K[2], (double)K[3]};
-  HFB_CUDA(ctx, cudaMemcpyAsync(a + oX, Xw, (size_t)n * 24, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(a + oO, obs, (size_t)n * 16, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(a + oS, inv_sigma2, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(a + oK, Kd, 32, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(a + oP, pose_in, 56, cudaMemcpyHostToDevice, st));
-  pose_opt_kernel<<<1, PO_THREADS, 0, st>>>(n, (const double*)(a + oX), (const double*)(a + oO), (const double*)(a + oS),
-                                           (const double*)(a + oK), sqrt(5.991), (const double*)(a + oP),
-                                           (double*)(a + oC), a + oF, (double*)(a + oPo), (int*)(a + oSt));
+  HFB_CUDA(ctx, cudaMemcpyAsync(a + oIn, hin, in_d * 8, cudaMemcpyHostToDevice, st));
+  const size_t smem = (size_t)7 * n * 8 + (size_t)n + 16;
+  const int in_smem = smem <= 200 * 1024;
+  static SmemOptIn optin;
+  if (in_smem && smem > 48 * 1024) HFB_CUDA(ctx, optin.ensure(pose_opt_kernel, ctx->device, 200 * 1024));
+  pose_opt_kernel<<<1, PO_THREADS, in_smem ? smem : 0, st>>>(n, (const double*)(a + oIn), sqrt(5.991), in_smem,
+                                                            (double*)(a + oC), a + oOut + 80, (double*)(a + oOut));
   HFB_CHECK_LAUNCH(ctx, "pose_opt");
-  int stats[3] = {0, 0, 0};
-  HFB_CUDA(ctx, cudaMemcpyAsync(pose_out, a + oPo, 56, cudaMemcpyDeviceToHost, st));
-  if (outlier_out) HFB_CUDA(ctx, cudaMemcpyAsync(outlier_out, a + oF, (size_t)n, cudaMemcpyDeviceToHost, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(stats, a + oSt, 12, cudaMemcpyDeviceToHost, st));
-  HFB_CUDA(ctx, cudaStreamSynchronize(st));   // Kd / stats are stack variables: must not outlive this frame
-  if (n_inliers) *n_inliers = stats[0];
-  if (n_trials) *n_trials = stats[1];
+  HFB_CUDA(ctx, cudaMemcpyAsync(hout, a + oOut, 80 + (size_t)n, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaStreamSynchronize(st));
+  const double* ho = reinterpret_cast<const double*>(hout);
+  memcpy(pose_out, ho, 56);
+  if (outlier_out) memcpy(outlier_out, hout + 80, (size_t)n);
+  if (n_inliers) *n_inliers = (int)ho[7];
+  if (n_trials) *n_trials = (int)ho[8];
   return HFB_OK;
 }

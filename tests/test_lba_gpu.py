@@ -66,3 +66,24 @@ def test_unsorted_edges_rejected(small_ctx):
     d["pt_idx"] = d["pt_idx"][::-1].copy()
     with pytest.raises(Exception):
         local_bundle_adjustment(small_ctx, d, iterations=1)
+
+
+def test_device_solver_equals_host_solve_mode(small_ctx):
+    """The reduced camera system solved on the device (one-CTA packed Cholesky + pose update) against the host-solve mode
+    (HFB_LBA_HOST_SOLVE=1: dense Cholesky on the host, the round-1 path): same LM path, estimates to 1e-9."""
+    import os
+    d, _ = _problem(n_opt=20, n_fixed=40, n_points=3000, seed=3)
+    a = local_bundle_adjustment(small_ctx, d, iterations=10)
+    os.environ["HFB_LBA_HOST_SOLVE"] = "1"
+    try:
+        b = local_bundle_adjustment(small_ctx, d, iterations=10)
+    finally:
+        del os.environ["HFB_LBA_HOST_SOLVE"]
+    assert a["iterations"] == b["iterations"] and a["trials"] == b["trials"]
+    assert np.abs(a["poses"] - b["poses"]).max() <= 1e-9 and np.abs(a["points"] - b["points"]).max() <= 1e-9
+    assert a["gpu_launches"] > b["gpu_launches"] - 20      # the device path adds one solve launch per trial
+    # a system larger than one CTA's shared memory (33 optimisable cameras -> N = 198 > 192) falls back to the host solve
+    big, prb = _problem(n_opt=33, n_fixed=10, n_points=800, seed=6)
+    ref = lba_ref.optimize(prb, 4)
+    out = local_bundle_adjustment(small_ctx, big, iterations=4)
+    assert out["iterations"] == ref.iterations and np.abs(out["poses"] - ref.poses).max() <= 1e-6
