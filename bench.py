@@ -332,9 +332,10 @@ def c3_gpu(torch, dev, n_frames: int):
             tick("extract+associate", t0)
             if prev is not None and len(desc) and len(prev[0]):
                 t0 = time.perf_counter()
-                q = min(400, len(prev[0]))                                       # SearchByProjection(F, LastFrame)
-                rad = (15.0 * 1.2 ** prev[2][:q]).astype(np.float32)
-                ctx.match_projection(prev[0][:q], prev[1][:q], rad, prev[2][:q] - 1, prev[2][:q] + 1, desc, xy, octv)
+                q = min(400, len(prev[0]))                                       # SearchByProjection(F, LastFrame) on the
+                rad = (15.0 * 1.2 ** prev[2][:q]).astype(np.float32)             # descriptors resident in HBM
+                ctx.match_projection_frame(0, np.arange(q, dtype=np.int32), prev[1][:q], rad, prev[2][:q] - 1,
+                                           prev[2][:q] + 1, nf=len(desc))
                 tick("projection", t0)
             t0 = time.perf_counter()
             for _ in range(2):                                                   # TrackWithMotionModel + TrackLocalMap

@@ -820,6 +820,74 @@ extern "C" int hfb_extract(hfb_ctx* ctx, const uint8_t* image, int32_t height, i
   return hfb_extract_batch(ctx, imgs, 1, stride, n_per_level, threshold, out);
 }
 
+// BaseModel::Detect of ONE pyramid level on a context that holds all levels (src/Extractors/HFNetRTModel.cc:84-110: the
+// reference keeps one engine per level and HFextractor hands every level object its own pre-scaled image,
+// HFextractor.cc:228-243): `image` is the level's image, results are in LEVEL coordinates with octave 0 -- the caller
+// (HFextractor.cc:272-279) applies octave / scale.  The fused multi-level call (hfb_extract) is the fast path; this entry
+// keeps the unmodified per-level flow working on one shared context and one copy of the weights.
+extern "C" int hfb_extract_level(hfb_ctx* ctx, int32_t level, const uint8_t* image, int32_t height, int32_t width,
+                                 int32_t stride, int32_t n_keypoints, float threshold, hfb_features* out) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, ctx->weights_loaded, "weights not loaded");
+  HFB_REQUIRE(ctx, image && out && level >= 0 && level < ctx->n_levels, "bad argument");
+  LevelPlan& lv = ctx->lv[level];
+  HFB_REQUIRE(ctx, height == lv.H && width == lv.W, "image size differs from this level's (one fixed shape per level, BaseModel.cc:35-65)");
+  HFB_REQUIRE(ctx, stride >= width, "stride smaller than the image width");
+  HFB_REQUIRE(ctx, n_keypoints >= 0 && n_keypoints <= ctx->cfg.max_keypoints, "keypoint budget outside [0, max_keypoints]");
+  const size_t img_bytes = (size_t)lv.H * lv.W;
+  const size_t out_bytes = 64 + (size_t)n_keypoints * (16 + HFB_DESC_DIM * 4) + HFB_GLOBAL_DIM * 4;
+  HFB_TRY(ctx->ensure_stage(img_bytes + out_bytes));
+  uint8_t* hs = reinterpret_cast<uint8_t*>(ctx->h_stage);
+  for (int y = 0; y < lv.H; ++y) memcpy(hs + (size_t)y * lv.W, image + (size_t)y * stride, lv.W);
+  cudaStream_t st = ctx->stream;
+  HFB_CUDA(ctx, cudaMemcpyAsync(lv.d_img, hs, img_bytes, cudaMemcpyHostToDevice, st));
+  ctx->last_batch = 1;
+  ctx->last_threshold = threshold;
+  for (int l = 0; l < ctx->n_levels; ++l) ctx->last_budget[l] = l == 0 ? n_keypoints : 0;
+  HFB_CUDA(ctx, cudaMemsetAsync(ctx->d_kcount, 0, HFB_MAX_LEVELS * sizeof(int), st));
+  HFB_CUDA(ctx, cudaMemsetAsync(ctx->d_stream_state, 0, sizeof(int), st));   // no streaming history through this entry
+  HFB_TRY(encoder_forward(ctx, level, 1, threshold));
+  HFB_TRY(launch_select_sample(ctx, lv.d_nms, lv.H8, lv.W8, lv.d_descmap, lv.H8 / 8, lv.W8 / 8, lv.d_cand, lv.d_cand_count,
+                               ctx->cand_cap, ctx->d_sel, ctx->d_nsel, n_keypoints, threshold, 1.0f, 0, 1, ctx->kp_cap,
+                               ctx->d_kx, ctx->d_ky, ctx->d_kresp, ctx->d_koct, ctx->d_kdesc, ctx->d_kcount,
+                               ctx->d_overflow, true));
+  if (ctx->join_pending) {
+    ctx->join_pending = false;
+    HFB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  }
+  uint8_t* ho = hs + img_bytes;
+  int* h_cnt = reinterpret_cast<int*>(ho);
+  float* hx = reinterpret_cast<float*>(ho + 64);
+  float* hy = hx + n_keypoints;
+  float* hr = hy + n_keypoints;
+  int* hoct = reinterpret_cast<int*>(hr + n_keypoints);
+  float* hd = reinterpret_cast<float*>(hoct + n_keypoints);
+  float* hg = hd + (size_t)n_keypoints * HFB_DESC_DIM;
+  HFB_CUDA(ctx, cudaMemcpyAsync(h_cnt, ctx->d_kcount, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (n_keypoints > 0) {
+    HFB_CUDA(ctx, cudaMemcpyAsync(hx, ctx->d_kx, (size_t)n_keypoints * 4, cudaMemcpyDeviceToHost, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(hy, ctx->d_ky, (size_t)n_keypoints * 4, cudaMemcpyDeviceToHost, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(hr, ctx->d_kresp, (size_t)n_keypoints * 4, cudaMemcpyDeviceToHost, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(hoct, ctx->d_koct, (size_t)n_keypoints * 4, cudaMemcpyDeviceToHost, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(hd, ctx->d_kdesc, (size_t)n_keypoints * HFB_DESC_DIM * 4, cudaMemcpyDeviceToHost, st));
+  }
+  const bool want_g = lv.global && out->global_descriptor;
+  if (want_g) HFB_CUDA(ctx, cudaMemcpyAsync(hg, ctx->d_global, HFB_GLOBAL_DIM * 4, cudaMemcpyDeviceToHost, st));
+  HFB_TRY(check_overflow(ctx));   // synchronises
+  const int n = std::min(h_cnt[0], n_keypoints);
+  for (int l = 0; l < HFB_MAX_LEVELS; ++l) out->n_per_level[l] = l == 0 ? n : 0;
+  out->n_total = n;
+  if (n > 0) {
+    memcpy(out->x, hx, (size_t)n * 4);
+    memcpy(out->y, hy, (size_t)n * 4);
+    memcpy(out->response, hr, (size_t)n * 4);
+    memcpy(out->octave, hoct, (size_t)n * 4);
+    memcpy(out->descriptors, hd, (size_t)n * HFB_DESC_DIM * 4);
+  }
+  if (want_g) memcpy(out->global_descriptor, hg, HFB_GLOBAL_DIM * 4);
+  return HFB_OK;
+}
+
 // Per-launch timing of one (un-graphed) extraction of the frames already resident in the context: JSON array of
 // {"name", "ms", "bytes", "flops"} with the launcher-stated algorithmic bytes / flops (bench.py's roofline source).
 extern "C" int hfb_profile_extract(hfb_ctx* ctx, int32_t n_images, const int32_t* n_per_level, float threshold,

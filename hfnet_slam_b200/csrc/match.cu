@@ -663,20 +663,26 @@ __global__ void proj_pack_kernel(const float* __restrict__ uv, const float* __re
   qlev[i] = make_int2(minl[i], maxl[i]);
 }
 
-extern "C" int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, const float* q_uv, const float* q_radius,
-                                    const int32_t* q_min_level, const int32_t* q_max_level, const float* F, int32_t nf,
-                                    const float* f_xy, const int32_t* f_level, const uint8_t* f_skip, int32_t* cand_idx,
-                                    float* cand_dist, int32_t* cand_level) {
-  return hfb_match_projection_gated(ctx, Q, nq, q_uv, q_radius, q_min_level, q_max_level, F, nf, f_xy, f_level, f_skip,
-                                    nullptr, 0.f, cand_idx, cand_dist, cand_level);
+__global__ void proj_gather_rows_kernel(const float* __restrict__ base, const int* __restrict__ index, int n,
+                                        float* __restrict__ out) {
+  const int i = blockIdx.x, t = threadIdx.x;     // one CTA of 64 threads per 1 KB row
+  if (i >= n) return;
+  reinterpret_cast<float4*>(out + (size_t)i * 256)[t] = __ldg(reinterpret_cast<const float4*>(base + (size_t)index[i] * 256) + t);
 }
 
-extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t nq, const float* q_uv,
-                                          const float* q_radius, const int32_t* q_min_level, const int32_t* q_max_level,
-                                          const float* F, int32_t nf, const float* f_xy, const int32_t* f_level,
-                                          const uint8_t* f_skip, const float* f_inv_sigma2, float chi2_max,
-                                          int32_t* cand_idx, float* cand_dist, int32_t* cand_level) {
-  HFB_ENTER(ctx);
+__global__ void proj_pack_xy_kernel(const float* __restrict__ x, const float* __restrict__ y, int n, float2* __restrict__ xy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) xy[i] = make_float2(x[i], y[i]);
+}
+
+// Shared body of the windowed searches.  Queries: host rows (Q) or rows q_index[i] of a resident descriptor block
+// (dQ_base).  Features: host arrays (F, f_xy, f_level) or resident arrays (dF, d_fx, d_fy, d_flevel).
+static int proj_common(hfb_ctx* ctx, const float* Q, const int32_t* q_index, const float* dQ_base, int32_t nq,
+                       const float* q_uv, const float* q_radius, const int32_t* q_min_level, const int32_t* q_max_level,
+                       const float* F, const float* dF_res, const float* d_fx, const float* d_fy, const int* d_flevel,
+                       int32_t nf, const float* f_xy, const int32_t* f_level, const uint8_t* f_skip,
+                       const float* f_inv_sigma2, float chi2_max, int32_t* cand_idx, float* cand_dist,
+                       int32_t* cand_level) {
   HFB_REQUIRE(ctx, nq >= 0 && nf >= 0, "negative size");
   HFB_REQUIRE(ctx, cand_idx && cand_dist && cand_level, "null output");
   for (long long i = 0; i < (long long)nq * PROJ_K; ++i) {
@@ -685,27 +691,47 @@ extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t 
     cand_level[i] = -1;
   }
   if (nq == 0 || nf == 0) return HFB_OK;
-  HFB_REQUIRE(ctx, Q && q_uv && q_radius && q_min_level && q_max_level && F && f_xy && f_level, "null input");
+  const bool q_res = Q == nullptr, f_res = F == nullptr;
+  HFB_REQUIRE(ctx, (q_res ? (q_index && dQ_base) : true) && q_uv && q_radius && q_min_level && q_max_level &&
+                       (f_res ? (dF_res && d_fx && d_fy && d_flevel) : (f_xy && f_level)), "null input");
   auto al = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
   const int n_tiles = ceil_div(nf, MATCH_BN);
-  // io block: Q | F | uv | r | minl | maxl | fxy | flevel | fskip | cand_idx | cand_dist | cand_level
-  const size_t oQ = 0, oF = oQ + al((size_t)nq * 1024), o_uv = oF + al((size_t)nf * 1024), o_r = o_uv + al((size_t)nq * 8),
-               o_mn = o_r + al((size_t)nq * 4), o_mx = o_mn + al((size_t)nq * 4), o_fxy = o_mx + al((size_t)nq * 4),
-               o_fl = o_fxy + al((size_t)nf * 8), o_fs = o_fl + al((size_t)nf * 4), o_fi = o_fs + al((size_t)nf),
-               o_ci = o_fi + al((size_t)nf * 4),
+  // io block: Q | F | uv | r | minl | maxl | fxy | flevel | fskip | finv | q_index | cand_idx | cand_dist | cand_level
+  const size_t oQ = 0, oF = oQ + al((size_t)nq * 1024), o_uv = oF + (f_res ? 0 : al((size_t)nf * 1024)),
+               o_r = o_uv + al((size_t)nq * 8), o_mn = o_r + al((size_t)nq * 4), o_mx = o_mn + al((size_t)nq * 4),
+               o_fxy = o_mx + al((size_t)nq * 4), o_fl = o_fxy + al((size_t)nf * 8), o_fs = o_fl + al((size_t)nf * 4),
+               o_fi = o_fs + al((size_t)nf), o_qi = o_fi + al((size_t)nf * 4), o_ci = o_qi + al((size_t)nq * 4),
                o_cd = o_ci + al((size_t)nq * PROJ_K * 4), o_cl = o_cd + al((size_t)nq * PROJ_K * 4),
                io_total = o_cl + al((size_t)nq * PROJ_K * 4);
   HFB_TRY(ctx->ensure_io(io_total));
   uint8_t* io = reinterpret_cast<uint8_t*>(ctx->d_io);
   cudaStream_t st = ctx->stream;
-  HFB_CUDA(ctx, cudaMemcpyAsync(io + oQ, Q, (size_t)nq * 1024, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(io + oF, F, (size_t)nf * 1024, cudaMemcpyHostToDevice, st));
+  if (q_res) {
+    HFB_CUDA(ctx, cudaMemcpyAsync(io + o_qi, q_index, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+    proj_gather_rows_kernel<<<nq, 64, 0, st>>>(dQ_base, reinterpret_cast<const int*>(io + o_qi), nq,
+                                               reinterpret_cast<float*>(io + oQ));
+    HFB_CHECK_LAUNCH(ctx, "proj_gather");
+  } else {
+    HFB_CUDA(ctx, cudaMemcpyAsync(io + oQ, Q, (size_t)nq * 1024, cudaMemcpyHostToDevice, st));
+  }
   HFB_CUDA(ctx, cudaMemcpyAsync(io + o_uv, q_uv, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
   HFB_CUDA(ctx, cudaMemcpyAsync(io + o_r, q_radius, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
   HFB_CUDA(ctx, cudaMemcpyAsync(io + o_mn, q_min_level, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
   HFB_CUDA(ctx, cudaMemcpyAsync(io + o_mx, q_max_level, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fxy, f_xy, (size_t)nf * 8, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fl, f_level, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+  const float* dF;
+  const int* dFlev;
+  if (f_res) {
+    dF = dF_res;
+    dFlev = d_flevel;
+    proj_pack_xy_kernel<<<ceil_div(nf, 256), 256, 0, st>>>(d_fx, d_fy, nf, reinterpret_cast<float2*>(io + o_fxy));
+    HFB_CHECK_LAUNCH(ctx, "proj_pack_xy");
+  } else {
+    HFB_CUDA(ctx, cudaMemcpyAsync(io + oF, F, (size_t)nf * 1024, cudaMemcpyHostToDevice, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fxy, f_xy, (size_t)nf * 8, cudaMemcpyHostToDevice, st));
+    HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fl, f_level, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    dF = reinterpret_cast<const float*>(io + oF);
+    dFlev = reinterpret_cast<const int*>(io + o_fl);
+  }
   if (f_skip) HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fs, f_skip, (size_t)nf, cudaMemcpyHostToDevice, st));
   if (f_inv_sigma2) HFB_CUDA(ctx, cudaMemcpyAsync(io + o_fi, f_inv_sigma2, (size_t)nf * 4, cudaMemcpyHostToDevice, st));
   // scratch: Q' | F' | hnq | hnf | qwin | qlev | records
@@ -715,7 +741,6 @@ extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t 
   HFB_TRY(ctx->ensure_scratch(s_total));
   uint8_t* sc = reinterpret_cast<uint8_t*>(ctx->d_scratch);
   const float* dQ = reinterpret_cast<const float*>(io + oQ);
-  const float* dF = reinterpret_cast<const float*>(io + oF);
   __half* Q2 = reinterpret_cast<__half*>(sc + sQ);
   __half* F2 = reinterpret_cast<__half*>(sc + sF);
   float* hnq = reinterpret_cast<float*>(sc + s_hq);
@@ -745,21 +770,62 @@ extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t 
   const size_t smem = gemm_smem_bytes(g.BN, g.stages, 0);
   static SmemOptIn optin;
   HFB_CUDA(ctx, optin.ensure(gemm_tc_kernel<EpiProjTopK>, ctx->device, smem));
-  EpiProjTopK::Params ep{hnq, hnf, qwin, qlev, reinterpret_cast<const float2*>(io + o_fxy),
-                         reinterpret_cast<const int*>(io + o_fl), f_skip ? io + o_fs : nullptr,
+  EpiProjTopK::Params ep{hnq, hnf, qwin, qlev, reinterpret_cast<const float2*>(io + o_fxy), dFlev,
+                         f_skip ? io + o_fs : nullptr,
                          f_inv_sigma2 ? reinterpret_cast<const float*>(io + o_fi) : nullptr,
                          f_inv_sigma2 ? chi2_max : 3.402823466e38f, rec, nq};
   gemm_tc_kernel<EpiProjTopK><<<gemm_grid(g, ctx->n_sm, smem), GEMM_THREADS(4), smem, st>>>(tmA, tmB, g, ep);
   HFB_CHECK_LAUNCH(ctx, "proj_gemm_topk");
-  hfb_launch(ctx, proj_finalize_kernel, ceil_div(nq, 8), 256, 0, dQ, dF, rec, n_tiles, nq,
-             reinterpret_cast<const int*>(io + o_fl), reinterpret_cast<int*>(io + o_ci),
-             reinterpret_cast<float*>(io + o_cd), reinterpret_cast<int*>(io + o_cl));
+  hfb_launch(ctx, proj_finalize_kernel, ceil_div(nq, 8), 256, 0, dQ, dF, rec, n_tiles, nq, dFlev,
+             reinterpret_cast<int*>(io + o_ci), reinterpret_cast<float*>(io + o_cd), reinterpret_cast<int*>(io + o_cl));
   HFB_CHECK_LAUNCH(ctx, "proj_finalize");
   HFB_CUDA(ctx, cudaMemcpyAsync(cand_idx, io + o_ci, (size_t)nq * PROJ_K * 4, cudaMemcpyDeviceToHost, st));
   HFB_CUDA(ctx, cudaMemcpyAsync(cand_dist, io + o_cd, (size_t)nq * PROJ_K * 4, cudaMemcpyDeviceToHost, st));
   HFB_CUDA(ctx, cudaMemcpyAsync(cand_level, io + o_cl, (size_t)nq * PROJ_K * 4, cudaMemcpyDeviceToHost, st));
   HFB_CUDA(ctx, cudaStreamSynchronize(st));
   return HFB_OK;
+}
+
+extern "C" int hfb_match_projection(hfb_ctx* ctx, const float* Q, int32_t nq, const float* q_uv, const float* q_radius,
+                                    const int32_t* q_min_level, const int32_t* q_max_level, const float* F, int32_t nf,
+                                    const float* f_xy, const int32_t* f_level, const uint8_t* f_skip, int32_t* cand_idx,
+                                    float* cand_dist, int32_t* cand_level) {
+  return hfb_match_projection_gated(ctx, Q, nq, q_uv, q_radius, q_min_level, q_max_level, F, nf, f_xy, f_level, f_skip,
+                                    nullptr, 0.f, cand_idx, cand_dist, cand_level);
+}
+
+extern "C" int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t nq, const float* q_uv,
+                                          const float* q_radius, const int32_t* q_min_level, const int32_t* q_max_level,
+                                          const float* F, int32_t nf, const float* f_xy, const int32_t* f_level,
+                                          const uint8_t* f_skip, const float* f_inv_sigma2, float chi2_max,
+                                          int32_t* cand_idx, float* cand_dist, int32_t* cand_level) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, nq == 0 || nf == 0 || (Q && F), "null input");
+  return proj_common(ctx, Q, nullptr, nullptr, nq, q_uv, q_radius, q_min_level, q_max_level, F, nullptr, nullptr, nullptr,
+                     nullptr, nf, f_xy, f_level, f_skip, f_inv_sigma2, chi2_max, cand_idx, cand_dist, cand_level);
+}
+
+// SearchByProjection(CurrentFrame, LastFrame) on RESIDENT descriptors: the features are frame
+// `frame_index` of the last extraction (descriptors, positions and octaves as the extraction left them in HBM), the
+// queries are rows q_prev_index[i] of the previous frame of its stream (frame_index - 1 of the same call, or the
+// descriptors carried over from the previous call).  Only the per-query window (24 bytes) goes up.
+extern "C" int hfb_match_projection_frame(hfb_ctx* ctx, int32_t frame_index, const int32_t* q_prev_index, int32_t nq,
+                                          const float* q_uv, const float* q_radius, const int32_t* q_min_level,
+                                          const int32_t* q_max_level, int32_t nf, const uint8_t* f_skip,
+                                          const float* f_inv_sigma2, float chi2_max, int32_t* cand_idx, float* cand_dist,
+                                          int32_t* cand_level) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, ctx->last_batch > 0 && frame_index >= 0 && frame_index < ctx->last_batch, "no such resident frame");
+  HFB_REQUIRE(ctx, nf >= 0 && nf <= ctx->kp_cap, "nf exceeds the frame's keypoint capacity");
+  HFB_REQUIRE(ctx, nq == 0 || q_prev_index, "null query index");
+  for (int i = 0; i < nq; ++i)
+    HFB_REQUIRE(ctx, q_prev_index[i] >= 0 && q_prev_index[i] < ctx->kp_cap, "query index outside the previous frame");
+  const long long prev_slot = ctx->stream_mode == 0 ? (long long)frame_index - 1 : (long long)frame_index - ctx->last_batch;
+  const float* dQ_base = ctx->d_kdesc + prev_slot * ctx->kp_cap * HFB_DESC_DIM;
+  const size_t fo = (size_t)frame_index * ctx->kp_cap;
+  return proj_common(ctx, nullptr, q_prev_index, dQ_base, nq, q_uv, q_radius, q_min_level, q_max_level, nullptr,
+                     ctx->d_kdesc + fo * HFB_DESC_DIM, ctx->d_kx + fo, ctx->d_ky + fo, ctx->d_koct + fo, nf, nullptr, nullptr,
+                     f_skip, f_inv_sigma2, chi2_max, cand_idx, cand_dist, cand_level);
 }
 
 // =============================================================================================== distinctive descriptors

@@ -67,6 +67,8 @@ SIGNATURES = {
     "hfb_load_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "hfb_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, C.c_float,
                               C.POINTER(hfb_features)]),
+    "hfb_extract_level": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                    C.POINTER(hfb_features)]),
     "hfb_extract_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _i32p, C.c_float,
                                     C.POINTER(hfb_features)]),
     "hfb_extract_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _i32p, C.c_float]),
@@ -92,6 +94,8 @@ SIGNATURES = {
                                        _i32p, _u8p, _i32p, _f32p, _i32p]),
     "hfb_match_projection_gated": (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p, _f32p, _i32p, _i32p, _f32p, C.c_int32,
                                              _f32p, _i32p, _u8p, _f32p, C.c_float, _i32p, _f32p, _i32p]),
+    "hfb_match_projection_frame": (C.c_int, [C.c_void_p, C.c_int32, _i32p, C.c_int32, _f32p, _f32p, _i32p, _i32p, C.c_int32,
+                                             _u8p, _f32p, C.c_float, _i32p, _f32p, _i32p]),
     "hfb_match_consecutive_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float]),
     "hfb_fetch_matches": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _f32p, C.c_int32]),
     "hfb_set_stream_mode": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -335,6 +339,14 @@ class Context:
         self.check(self.lib.hfb_extract_match_batch_dev(self.handle, C.c_void_p(d_images_ptr), n_images,
                                                         self._budgets(n_per_level), threshold, mode, thr))
 
+    def extract_level(self, level: int, image, n_keypoints: int, threshold: float) -> dict:
+        """BaseModel::Detect of one pyramid level on the shared context (level coordinates, octave 0)."""
+        im = np.ascontiguousarray(image, dtype=np.uint8)
+        feats, arrs = self._alloc_features(1)
+        self.check(self.lib.hfb_extract_level(self.handle, level, im.ctypes.data, im.shape[0], im.shape[1], im.shape[1],
+                                              n_keypoints, threshold, C.byref(feats[0])))
+        return self._view(feats[0], arrs, 0, self.with_global and level == 0)
+
     def extract(self, image, n_per_level, threshold: float) -> dict:
         return self.extract_batch([image], n_per_level, threshold)[0]
 
@@ -377,6 +389,27 @@ class Context:
     def reset_stream(self):
         """Forget the previous frame of the streaming association (Tracking::Reset)."""
         self.check(self.lib.hfb_reset_stream(self.handle))
+
+    def match_projection_frame(self, frame_index: int, q_prev_index, q_uv, q_radius, q_min_level, q_max_level, nf: int,
+                               f_skip=None, f_inv_sigma2=None, chi2_max: float = 0.0):
+        """match_projection on resident descriptors: features = frame ``frame_index`` of the last extraction, queries =
+        rows ``q_prev_index`` of its stream's previous frame.  Returns (idx [nq,4], dist [nq,4], level [nq,4])."""
+        qi = np.ascontiguousarray(q_prev_index, dtype=np.int32)
+        nq = len(qi)
+        uv, rad = as_f32(q_uv).reshape(-1, 2), as_f32(q_radius).reshape(-1)
+        mn = np.ascontiguousarray(q_min_level, dtype=np.int32)
+        mx = np.ascontiguousarray(q_max_level, dtype=np.int32)
+        fs = np.ascontiguousarray(f_skip, dtype=np.uint8) if f_skip is not None else None
+        fi = as_f32(f_inv_sigma2).reshape(-1) if f_inv_sigma2 is not None else None
+        idx = np.full((nq, 4), -1, np.int32)
+        dist = np.full((nq, 4), np.finfo(np.float32).max, np.float32)
+        lvl = np.full((nq, 4), -1, np.int32)
+        self.check(self.lib.hfb_match_projection_frame(self.handle, frame_index, ptr(qi, _i32p), nq, ptr(uv, _f32p),
+                                                       ptr(rad, _f32p), ptr(mn, _i32p), ptr(mx, _i32p), nf,
+                                                       ptr(fs, _u8p) if fs is not None else None,
+                                                       ptr(fi, _f32p) if fi is not None else None, float(chi2_max),
+                                                       ptr(idx, _i32p), ptr(dist, _f32p), ptr(lvl, _i32p)))
+        return idx, dist, lvl
 
     def match_consecutive_dev(self, n_images: int, mode: int, thr: float):
         self.check(self.lib.hfb_match_consecutive_dev(self.handle, n_images, mode, thr))

@@ -98,6 +98,14 @@ typedef struct hfb_features {
 int hfb_extract(hfb_ctx* ctx, const uint8_t* image, int32_t height, int32_t width, int32_t stride,
                 const int32_t* n_per_level, float threshold, hfb_features* out);
 
+/* BaseModel::Detect of ONE pyramid level on a context that holds all levels (src/Extractors/HFNetRTModel.cc:84-110): the
+ * unmodified HFextractor hands every per-level model object its own pre-scaled image (HFextractor.cc:228-243).  `image`
+ * is level `level`'s image (cvRound(H / s^level) x cvRound(W / s^level)); keypoints come back in LEVEL coordinates with
+ * octave 0, the caller applies octave and scale (HFextractor.cc:272-279).  The global descriptor is produced by level 0
+ * only (kImageToLocalAndGlobal) and only when out->global_descriptor is non-NULL. */
+int hfb_extract_level(hfb_ctx* ctx, int32_t level, const uint8_t* image, int32_t height, int32_t width, int32_t stride,
+                      int32_t n_keypoints, float threshold, hfb_features* out);
+
 /* Same for `n_images` independent frames (one per camera stream); images[i] are host pointers. */
 int hfb_extract_batch(hfb_ctx* ctx, const uint8_t* const* images, int32_t n_images, int32_t stride,
                       const int32_t* n_per_level, float threshold, hfb_features* outs);
@@ -186,6 +194,15 @@ int hfb_match_projection_gated(hfb_ctx* ctx, const float* Q, int32_t nq, const f
                                const float* f_xy, const int32_t* f_level, const uint8_t* f_skip,
                                const float* f_inv_sigma2, float chi2_max, int32_t* cand_idx, float* cand_dist,
                                int32_t* cand_level);
+
+/* The same search on RESIDENT descriptors (SearchByProjection(CurrentFrame, LastFrame), src/Matcher.cc:
+ * 1574-1650, without moving descriptors): features = frame `frame_index` of the last hfb_extract* call as it sits in HBM
+ * (its first nf keypoints), queries = rows q_prev_index[i] of the previous frame of that stream (frame_index - 1 of the
+ * same call, or the frame carried over from the previous call).  Only the query windows are uploaded. */
+int hfb_match_projection_frame(hfb_ctx* ctx, int32_t frame_index, const int32_t* q_prev_index, int32_t nq,
+                               const float* q_uv, const float* q_radius, const int32_t* q_min_level,
+                               const int32_t* q_max_level, int32_t nf, const uint8_t* f_skip, const float* f_inv_sigma2,
+                               float chi2_max, int32_t* cand_idx, float* cand_dist, int32_t* cand_level);
 
 /* Tracking's frame-to-previous-frame descriptor association (the brute-force stage behind
  * Matcher::SearchByBoW / SearchForInitialization call sites, src/Tracking.cc:2030,1796, which match the current frame

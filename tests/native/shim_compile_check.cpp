@@ -1,41 +1,7 @@
-// Compile check of include/HFNetB200Model.h without OpenCV / the reference tree: minimal stand-ins for the few
-// cv:: types and the BaseModel interface (include/Extractors/BaseModel.h:10-54) the shim touches.
-#include <algorithm>
-#include <cstdint>
-#include <cstring>
-#include <string>
-#include <vector>
-#define HFNET_B200_SHIM_STANDALONE
-#define CV_8UC1 0
-#define CV_32F 5
-namespace cv {
-struct Point2f { float x = 0, y = 0; };
-struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
-struct Vec4i { int v[4]; int operator()(int i) const { return v[i]; } };
-struct Mat {
-  int rows = 0, cols = 0, type_ = 0; size_t step = 0; unsigned char* data = nullptr; std::vector<unsigned char> buf;
-  Mat() {}
-  Mat(int r, int c, int t) : rows(r), cols(c), type_(t), step((size_t)c * (t == CV_32F ? 4 : 1)), buf((size_t)r * c * (t == CV_32F ? 4 : 1)) { data = buf.data(); }
-  bool empty() const { return rows == 0 || cols == 0; }
-  int type() const { return type_; }
-  template <class T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + r * step); }
-  Mat rowRange(int a, int b) const { Mat m(b - a, cols, type_); if (b > a) std::memcpy(m.data, data + a * step, (size_t)(b - a) * step); return m; }
-};
-}  // namespace cv
-namespace ORB_SLAM3 {
-enum ModelType { kHFNetTFModel, kHFNetRTModel, kHFNetVINOModel };
-enum ModelDetectionMode { kImageToLocalAndGlobal, kImageToLocal, kImageToLocalAndIntermediate, kIntermediateToGlobal };
-class BaseModel {
- public:
-  virtual ~BaseModel(void) = default;
-  virtual bool Detect(const cv::Mat&, std::vector<cv::KeyPoint>&, cv::Mat&, cv::Mat&, int, float) = 0;
-  virtual bool Detect(const cv::Mat&, std::vector<cv::KeyPoint>&, cv::Mat&, int, float) = 0;
-  virtual bool Detect(const cv::Mat&, cv::Mat&) = 0;
-  virtual bool IsValid(void) = 0;
-  virtual ModelType Type(void) = 0;
-};
-}  // namespace ORB_SLAM3
+// Compile / link check of the reference-side shims without OpenCV / the reference tree (stand-ins in cv_standin.h).
+#include "cv_standin.h"
 #include "HFNetB200Model.h"
+#include "HFNetB200Backends.h"
 
 int main(int argc, char** argv) {
   std::vector<unsigned char> blob(64, 0);
@@ -44,5 +10,16 @@ int main(int argc, char** argv) {
   std::vector<cv::KeyPoint> kps;
   ORB_SLAM3::BaseModel* base = &model;
   bool ok = base->IsValid() && base->Detect(img, kps, desc, g, 100, 0.01f);
+  if (ok) {                                   // never reached without a GPU; keeps the other shims' symbols referenced
+    ORB_SLAM3::HFNetB200Matcher matcher(model.Engine()->ctx);
+    std::vector<int> m;
+    matcher.SearchByBoW(desc, desc, m);
+    ORB_SLAM3::HFNetB200KeyFrameDatabase db(model.Engine()->ctx, 16);
+    db.add(1, 0, g);
+    std::vector<unsigned char> outl;
+    double pose[7] = {0, 0, 0, 1, 0, 0, 0};
+    const float K[4] = {1, 1, 0, 0};
+    ORB_SLAM3::HFNetB200Optimizer::PoseOptimization(model.Engine()->ctx, K, pose, {}, {}, {}, outl);
+  }
   return ok ? 0 : (argc > 1 ? 2 : 0);   // without a GPU / real weights the model is invalid: exit 0 unless asked
 }

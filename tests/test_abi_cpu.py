@@ -89,11 +89,13 @@ def test_reference_side_shim_compiles_and_links(native_lib, tmp_path):
     if not shutil.which("g++"):
         pytest.skip("g++ not on PATH")
     exe = tmp_path / "shim_check"
-    r = subprocess.run(["g++", "-std=c++14", "-Wall", f"-I{ROOT / 'include'}", "-o", str(exe),
-                        str(ROOT / "tests" / "native" / "shim_compile_check.cpp"), str(lib.LIB_PATH),
-                        f"-Wl,-rpath,{lib.LIB_PATH.parent}"], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    assert subprocess.run([str(exe)]).returncode == 0
+    for src in ("shim_compile_check.cpp", "shim_run.cpp"):        # the second one is executed by tests/test_shim_gpu.py
+        r = subprocess.run(["g++", "-std=c++14", "-Wall", f"-I{ROOT / 'include'}", f"-I{ROOT / 'tests' / 'native'}", "-o", str(exe),
+                            str(ROOT / "tests" / "native" / src), str(lib.LIB_PATH),
+                            f"-Wl,-rpath,{lib.LIB_PATH.parent}"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        if src == "shim_compile_check.cpp":
+            assert subprocess.run([str(exe)]).returncode == 0
 
 
 def test_header_is_plain_c():

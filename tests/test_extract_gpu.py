@@ -291,3 +291,12 @@ def test_c5_tumvi_stream_masked_best2(native_lib, weights_blob):
         assert (idx[~has] == -1).all()
         # the shifted copy re-finds its keypoints: the best candidate is a close descriptor for most of them
         assert (bd[has] < 0.6).mean() > 0.5
+        # the same search on RESIDENT descriptors (hfb_match_projection_frame: features = frame 0 of the last call as it sits
+        # in HBM, queries = rows of the frame carried over from the previous call): identical lists, nothing but the windows
+        # uploaded
+        qi = np.arange(len(uv), dtype=np.int32)
+        ridx, rdist, rlvl = ctx.match_projection_frame(0, qi, uv, rad, mn, mx, nf=len(cur["x"]))
+        assert np.array_equal(ridx, idx) and np.array_equal(rdist, dist) and np.array_equal(rlvl, lvl)
+        sub = qi[::3]
+        ridx2, rdist2, _ = ctx.match_projection_frame(0, sub, uv[sub], rad[sub], mn[sub], mx[sub], nf=len(cur["x"]))
+        assert np.array_equal(ridx2, idx[sub]) and np.array_equal(rdist2, dist[sub])
