@@ -301,10 +301,11 @@ def c3_gpu(torch, dev, n_frames: int):
     """BASELINE.json configs[2] call pattern through the public host API on one B200 (see module docstring)."""
     from hfnet_slam_b200 import synthetic, weights
     from hfnet_slam_b200.keyframe_database import KeyFrameDatabase
-    from hfnet_slam_b200.lib import Context, pinned_empty
+    from hfnet_slam_b200.lib import Context, KeyFrameStore, pinned_empty
     from hfnet_slam_b200.optimizer import local_bundle_adjustment, pose_optimization
     ctx = Context(height=H, width=W, n_levels=4, scale_factor=1.2, max_keypoints=675, max_batch=1, with_global=True,
                   device=dev.index or 0)
+    store = KeyFrameStore(ctx, n_slots=16, rows_per_slot=ctx.kp_cap)     # keyframe descriptors stay in HBM
     ctx.load_weights(weights.synthetic_blob(seed=0))
     base = weights.synthetic_image(H, W, seed=1, n_corners=300)
     frame = pinned_empty((H, W), np.uint8)
@@ -343,17 +344,13 @@ def c3_gpu(torch, dev, n_frames: int):
             tick("pose", t0)
             if i % 6 == 0:
                 n_kf += 1
+                t0 = time.perf_counter()
+                store.put_frame(ctx, n_kf, 0, len(desc))                     # device to device, prepared once
                 if kfs:
-                    t0 = time.perf_counter()
-                    nb = kfs[-10:]
-                    A = np.concatenate([desc] * len(nb))
-                    Bm = np.concatenate(nb)
-                    a_cnt = np.full(len(nb), len(desc), np.int32)
-                    a_off = (np.arange(len(nb)) * len(desc)).astype(np.int32)
-                    b_cnt = np.array([len(x) for x in nb], np.int32)
-                    b_off = (np.cumsum(b_cnt) - b_cnt).astype(np.int32)
-                    ctx.match_batch(1, A, Bm, a_off, a_cnt, b_off, b_cnt, 0.71875)   # SearchForTriangulation flavour
-                    tick("kf_match", t0)
+                    store.match_neighbours(ctx, n_kf, kfs[-10:], 1, 0.71875, len(desc))   # SearchForTriangulation flavour
+                if len(kfs) >= 12:
+                    store.erase(kfs[-12])
+                tick("kf_match", t0)
                 t0 = time.perf_counter()
                 kf.add(n_kf, f["global_descriptor"])
                 if n_kf > 1:
@@ -362,12 +359,13 @@ def c3_gpu(torch, dev, n_frames: int):
                 t0 = time.perf_counter()
                 local_bundle_adjustment(ctx, lba_p, iterations=10)
                 tick("lba", t0)
-                kfs.append(desc)
+                kfs.append(n_kf)
             prev = (desc, xy, octv)
         wall = time.perf_counter() - wall0
     n_key = (n_frames + 5) // 6
     stages = {k: (1e3 * v / (n_key if k in ("kf_match", "kfdb", "lba") else n_frames)) for k, v in t.items()}
     kf.close()
+    store.close()
     ctx.close()
     return {"frames": n_frames, "keyframes": n_key, "frames_per_s": n_frames / wall,
             "stage_ms": stages, "stage_ms_note": "kf_match / kfdb / lba per keyframe, the others per frame"}

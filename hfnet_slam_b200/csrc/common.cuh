@@ -301,7 +301,9 @@ int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold);
 // match.cu: pair_tab = device int[4][n_pairs] (a_off | a_cnt | b_off | b_cnt)
 int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB, int n_pairs, const int* d_pair_tab,
                        int max_a, int max_b, float thr, int* d_match_idx, float* d_match_val, int na_total,
-                       int nb_total, int** d_n_matches_out, void* ws = nullptr, size_t ws_bytes = 0, int pad_rows = 0);
+                       int nb_total, int** d_n_matches_out, void* ws = nullptr, size_t ws_bytes = 0, int pad_rows = 0,
+                       const __half* B_img = nullptr, const float* hnb_pre = nullptr);
+int launch_match_prep(hfb_ctx* ctx, const float* d_rows, int n, __half* d_img, float* d_hn_l2);
 size_t match_workspace_bytes(int na_total, int nb_total, int n_pairs, bool same);
 
 int launch_distinctive(hfb_ctx* ctx, const float* d_desc, const int* d_offsets, int n_points, int max_n, int* d_best_idx,

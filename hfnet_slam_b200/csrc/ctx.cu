@@ -1319,3 +1319,160 @@ extern "C" int hfb_match_mutual_cos(hfb_ctx* ctx, const float* A, int32_t na, co
   HFB_ENTER(ctx);
   return match_single(ctx, 1, A, na, B, nb, min_cos, match_idx, match_val, n_matches);
 }
+
+
+// ================================================================================================ keyframe descriptor store
+// Local descriptors of keyframes kept RESIDENT in HBM (fp32 rows for the exact re-evaluation + the split-precision image
+// the tensor-core contraction reads + half squared norms, all prepared once when the keyframe is stored), so that the
+// per-keyframe matching of LocalMapping::CreateNewMapPoints / SearchInNeighbors (current keyframe against <= 30 covisible
+// keyframes, src/LocalMapping.cc:513-893, Matcher::SearchForTriangulation src/Matcher.cc:845-889) moves no descriptors:
+// only keyframe ids go up and match rows come back.  A store may be filled from one context (Tracking's) and read from
+// another one on the same device (LocalMapping's); hfb_kfstore_put synchronises the source stream.
+struct hfb_kfstore {
+  int device = 0, n_slots = 0, rows_per_slot = 0;
+  float* d_rows = nullptr;     // [n_slots][rows_per_slot][256]
+  __half* d_img = nullptr;     // [n_slots][rows_per_slot][512] hi | lo
+  float* d_hn = nullptr;       // [n_slots][rows_per_slot] 0.5 |d|^2
+  float* d_zero = nullptr;     // same shape, zeros (cosine mode)
+  std::unordered_map<int64_t, std::pair<int, int>> slot_of;   // id -> (slot, rows)
+  std::vector<int> free_slots;
+  std::mutex mu;
+};
+
+extern "C" int hfb_kfstore_create(hfb_ctx* ctx, int32_t n_slots, int32_t rows_per_slot, hfb_kfstore** out) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, out && n_slots >= 1 && rows_per_slot >= 1 && rows_per_slot <= 65535, "bad store geometry");
+  hfb_kfstore* s = new hfb_kfstore();
+  s->device = ctx->device;
+  s->n_slots = n_slots;
+  s->rows_per_slot = rows_per_slot;
+  const size_t rows = (size_t)n_slots * rows_per_slot;
+  cudaError_t e = cudaMalloc(&s->d_rows, rows * 1024);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_img, rows * 1024);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_hn, rows * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_zero, rows * 4);
+  if (e == cudaSuccess) e = cudaMemset(s->d_zero, 0, rows * 4);
+  if (e == cudaSuccess) e = cudaMemset(s->d_img, 0, rows * 1024);
+  if (e != cudaSuccess) {
+    ctx->set_error(std::string("hfb_kfstore_create: ") + cudaGetErrorString(e));
+    cudaFree(s->d_rows); cudaFree(s->d_img); cudaFree(s->d_hn); cudaFree(s->d_zero);
+    delete s;
+    return HFB_ERR_CUDA;
+  }
+  for (int i = n_slots - 1; i >= 0; --i) s->free_slots.push_back(i);
+  *out = s;
+  return HFB_OK;
+}
+
+extern "C" void hfb_kfstore_destroy(hfb_kfstore* s) {
+  if (!s) return;
+  DeviceGuard g(s->device);
+  cudaDeviceSynchronize();
+  cudaFree(s->d_rows); cudaFree(s->d_img); cudaFree(s->d_hn); cudaFree(s->d_zero);
+  delete s;
+}
+
+static int kfstore_put_rows(hfb_ctx* ctx, hfb_kfstore* s, int64_t kf_id, const float* src, int n, cudaMemcpyKind kind) {
+  HFB_REQUIRE(ctx, s && s->device == ctx->device, "store lives on another device");
+  HFB_REQUIRE(ctx, n >= 0 && n <= s->rows_per_slot, "more rows than a store slot holds");
+  std::lock_guard<std::mutex> lk(s->mu);
+  HFB_REQUIRE(ctx, !s->slot_of.count(kf_id), "keyframe already stored");
+  if (s->free_slots.empty()) {
+    ctx->set_error("keyframe store is full");
+    return HFB_ERR_CAPACITY;
+  }
+  const int slot = s->free_slots.back();
+  const size_t r0 = (size_t)slot * s->rows_per_slot;
+  if (n > 0) {
+    HFB_CUDA(ctx, cudaMemcpyAsync(s->d_rows + r0 * 256, src, (size_t)n * 1024, kind, ctx->stream));
+    HFB_TRY(launch_match_prep(ctx, s->d_rows + r0 * 256, n, s->d_img + r0 * 512, s->d_hn + r0));
+  }
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // visible to every context from here on
+  s->free_slots.pop_back();
+  s->slot_of[kf_id] = std::make_pair(slot, n);
+  return HFB_OK;
+}
+
+// Store frame `frame_index` of the context's last extraction (its first n keypoints) as keyframe kf_id: device to device.
+extern "C" int hfb_kfstore_put_frame(hfb_ctx* ctx, hfb_kfstore* s, int64_t kf_id, int32_t frame_index, int32_t n) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, ctx->last_batch > 0 && frame_index >= 0 && frame_index < ctx->last_batch && n <= ctx->kp_cap,
+              "no such resident frame");
+  return kfstore_put_rows(ctx, s, kf_id, ctx->d_kdesc + (size_t)frame_index * ctx->kp_cap * HFB_DESC_DIM, n, cudaMemcpyDeviceToDevice);
+}
+// Store host descriptors (keyframes that predate the store, map loading).
+extern "C" int hfb_kfstore_put(hfb_ctx* ctx, hfb_kfstore* s, int64_t kf_id, const float* descriptors, int32_t n) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, n == 0 || descriptors, "null descriptors");
+  return kfstore_put_rows(ctx, s, kf_id, descriptors, n, cudaMemcpyHostToDevice);
+}
+extern "C" int hfb_kfstore_erase(hfb_kfstore* s, int64_t kf_id) {
+  if (!s) return HFB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(s->mu);
+  auto it = s->slot_of.find(kf_id);
+  if (it == s->slot_of.end()) return HFB_OK;
+  s->free_slots.push_back(it->second.first);
+  s->slot_of.erase(it);
+  return HFB_OK;
+}
+extern "C" int32_t hfb_kfstore_size(hfb_kfstore* s) {
+  if (!s) return 0;
+  std::lock_guard<std::mutex> lk(s->mu);
+  return (int32_t)s->slot_of.size();
+}
+
+__global__ void kfstore_replicate_kernel(const float* __restrict__ src, int n, int copies, float* __restrict__ dst) {
+  const size_t total = (size_t)n * 64 * copies;   // float4 units
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i % ((size_t)n * 64));
+}
+
+// Keyframe kf_a against n_b stored keyframes in ONE launch chain (mode 0 = SearchByBoW flavour, thr = max distance;
+// mode 1 = SearchForTriangulation flavour, thr = cosine floor).  match_idx / match_val: [n_b][rows of kf_a], indices into
+// the rows of the respective neighbour, -1 = unmatched.
+extern "C" int hfb_match_kf_neighbours(hfb_ctx* ctx, hfb_kfstore* s, int64_t kf_a, const int64_t* kf_b, int32_t n_b, int32_t mode,
+                                       float thr, int32_t* match_idx, float* match_val, int32_t* rows_a_out) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, s && s->device == ctx->device && kf_b && n_b >= 0 && (mode == 0 || mode == 1), "bad argument");
+  int slot_a, na;
+  std::vector<int> tab((size_t)4 * std::max(n_b, 1));
+  int max_b = 0;
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    auto ia = s->slot_of.find(kf_a);
+    HFB_REQUIRE(ctx, ia != s->slot_of.end(), "keyframe kf_a is not in the store");
+    slot_a = ia->second.first;
+    na = ia->second.second;
+    for (int p = 0; p < n_b; ++p) {
+      auto ib = s->slot_of.find(kf_b[p]);
+      HFB_REQUIRE(ctx, ib != s->slot_of.end(), "a neighbour keyframe is not in the store");
+      tab[p] = p * na;
+      tab[n_b + p] = na;
+      tab[2 * n_b + p] = ib->second.first * s->rows_per_slot;
+      tab[3 * n_b + p] = ib->second.second;
+      max_b = std::max(max_b, ib->second.second);
+    }
+  }
+  if (rows_a_out) *rows_a_out = na;
+  if (n_b == 0 || na == 0) return HFB_OK;
+  HFB_REQUIRE(ctx, match_idx && match_val, "null output");
+  // io block: replicated fp32 rows of kf_a (one copy per pair: the per-row best arrays are indexed like A's rows) | pair
+  // table | outputs
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t rows = (size_t)na * n_b;
+  const size_t oA = 0, oT = oA + al(rows * 1024), oI = oT + al((size_t)n_b * 16), oV = oI + al(rows * 4), total = oV + al(rows * 4);
+  HFB_TRY(ctx->ensure_io(total));
+  uint8_t* io = reinterpret_cast<uint8_t*>(ctx->d_io);
+  cudaStream_t st = ctx->stream;
+  kfstore_replicate_kernel<<<std::min<int>(ctx->n_sm * 4, (int)ceil_div_sz(rows * 64, 256)), 256, 0, st>>>(
+      s->d_rows + (size_t)slot_a * s->rows_per_slot * 256, na, n_b, reinterpret_cast<float*>(io + oA));
+  HFB_CHECK_LAUNCH(ctx, "kfstore_replicate");
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + oT, tab.data(), (size_t)n_b * 16, cudaMemcpyHostToDevice, st));
+  HFB_TRY(launch_match_batch(ctx, mode, reinterpret_cast<const float*>(io + oA), s->d_rows, n_b, reinterpret_cast<const int*>(io + oT),
+                             na, max_b, thr, reinterpret_cast<int*>(io + oI), reinterpret_cast<float*>(io + oV), (int)rows,
+                             s->n_slots * s->rows_per_slot, nullptr, nullptr, 0, 0, s->d_img, mode == 0 ? s->d_hn : s->d_zero));
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_idx, io + oI, rows * 4, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(match_val, io + oV, rows * 4, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaStreamSynchronize(st));   // also keeps `tab` alive until its copy has been consumed
+  return HFB_OK;
+}

@@ -340,6 +340,14 @@ match_ar_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
 }
 
+// Split-precision images of `n` fp32 rows at row offset `row0` of a resident block (keyframe store: prepared once).
+int launch_match_prep(hfb_ctx* ctx, const float* d_rows, int n, __half* d_img, float* d_hn_l2) {
+  if (n <= 0) return HFB_OK;
+  hfb_launch(ctx, match_prep_kernel, ceil_div(n, 8), 256, 0, d_rows, n, d_img, d_hn_l2, 1);
+  HFB_CHECK_LAUNCH(ctx, "match_prep(store)");
+  return HFB_OK;
+}
+
 // ---- finalize: mutual check + exact fp32 value + threshold ----------------------------------------------------------
 __global__ void match_finalize_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                       const u64* __restrict__ rowbest, const u64* __restrict__ colbest,
@@ -418,7 +426,8 @@ size_t match_workspace_bytes(int na_total, int nb_total, int n_pairs, bool same)
 
 int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB, int n_pairs, const int* d_pair_tab,
                        int max_a, int max_b, float thr, int* d_match_idx, float* d_match_val, int na_total,
-                       int nb_total, int** d_n_matches_out, void* ws, size_t ws_bytes, int pad_rows) {
+                       int nb_total, int** d_n_matches_out, void* ws, size_t ws_bytes, int pad_rows,
+                       const __half* B_img, const float* hnb_pre) {
   if (na_total <= 0 || nb_total <= 0 || n_pairs <= 0 || max_a <= 0 || max_b <= 0) {
     if (na_total > 0) {
       HFB_CUDA(ctx, cudaMemsetAsync(d_match_idx, 0xFF, (size_t)na_total * 4, ctx->stream));
@@ -428,10 +437,11 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
     return HFB_OK;
   }
   auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
-  const bool same = dA == dB;
+  const bool same = dA == dB && !B_img;
   const int nmax = same ? std::max(na_total, nb_total) : na_total;
-  const size_t szA = al((size_t)nmax * MATCH_LD * 2), szB = same ? 0 : al((size_t)nb_total * MATCH_LD * 2);
-  const size_t szna = al((size_t)nmax * 4), sznb = same ? 0 : al((size_t)nb_total * 4);
+  // B_img: the B rows already exist as split-precision images (keyframe store): nothing to prepare or to hold for B
+  const size_t szA = al((size_t)nmax * MATCH_LD * 2), szB = (same || B_img) ? 0 : al((size_t)nb_total * MATCH_LD * 2);
+  const size_t szna = al((size_t)nmax * 4), sznb = (same || B_img) ? 0 : al((size_t)nb_total * 4);
   const size_t szrb = al((size_t)na_total * 8), szcb = al((size_t)nb_total * 8), sznm = al((size_t)n_pairs * 4);
   const size_t need = szA + szB + szna + sznb + szrb + szcb + sznm;
   uint8_t* base;
@@ -443,9 +453,9 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
     base = reinterpret_cast<uint8_t*>(ctx->d_scratch);
   }
   __half* A2 = reinterpret_cast<__half*>(base);
-  __half* B2 = same ? A2 : reinterpret_cast<__half*>(base + szA);
+  const __half* B2 = B_img ? B_img : (same ? A2 : reinterpret_cast<__half*>(base + szA));
   float* hna = reinterpret_cast<float*>(base + szA + szB);
-  float* hnb = same ? hna : reinterpret_cast<float*>(base + szA + szB + szna);
+  const float* hnb = B_img ? hnb_pre : (same ? hna : reinterpret_cast<float*>(base + szA + szB + szna));
   u64* rowbest = reinterpret_cast<u64*>(base + szA + szB + szna + sznb);
   u64* colbest = reinterpret_cast<u64*>(base + szA + szB + szna + sznb + szrb);
   int* nm = reinterpret_cast<int*>(base + szA + szB + szna + sznb + szrb + szcb);
@@ -454,8 +464,9 @@ int launch_match_batch(hfb_ctx* ctx, int mode, const float* dA, const float* dB,
   const int l2 = (mode == 0);
   hfb_launch(ctx, match_prep_kernel, ceil_div(nmax, 8), 256, 0, dA, nmax, A2, hna, l2);
   HFB_CHECK_LAUNCH(ctx, "match_prep(A)");
-  if (!same) {
-    hfb_launch(ctx, match_prep_kernel, ceil_div(nb_total, 8), 256, 0, dB, nb_total, B2, hnb, l2);
+  if (!same && !B_img) {
+    hfb_launch(ctx, match_prep_kernel, ceil_div(nb_total, 8), 256, 0, dB, nb_total, const_cast<__half*>(B2),
+               const_cast<float*>(hnb), l2);
     HFB_CHECK_LAUNCH(ctx, "match_prep(B)");
   }
 

@@ -100,6 +100,14 @@ SIGNATURES = {
     "hfb_fetch_matches": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _f32p, C.c_int32]),
     "hfb_set_stream_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "hfb_reset_stream": (C.c_int, [C.c_void_p]),
+    "hfb_kfstore_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "hfb_kfstore_destroy": (None, [C.c_void_p]),
+    "hfb_kfstore_put_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
+    "hfb_kfstore_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _f32p, C.c_int32]),
+    "hfb_kfstore_erase": (C.c_int, [C.c_void_p, C.c_int64]),
+    "hfb_kfstore_size": (C.c_int32, [C.c_void_p]),
+    "hfb_match_kf_neighbours": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _i64p, C.c_int32, C.c_int32, C.c_float, _i32p, _f32p,
+                                          _i32p]),
     "hfb_distinctive_descriptors": (C.c_int, [C.c_void_p, _f32p, _i32p, C.c_int32, _i32p, _f32p]),
     "hfb_match_consecutive": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, _i32p, _f32p]),
     "hfb_profile_extract": (C.c_int, [C.c_void_p, C.c_int32, _i32p, C.c_float, C.c_char_p, C.c_size_t]),
@@ -524,4 +532,50 @@ class Context:
         self.check(self.lib.hfb_match_batch(self.handle, mode, ptr(a, _f32p), a.shape[0], ptr(b, _f32p), b.shape[0],
                                             len(tabs[0]), *[ptr(t, _i32p) for t in tabs], thr, ptr(idx, _i32p),
                                             ptr(val, _f32p)))
+        return idx, val
+
+
+class KeyFrameStore:
+    """Keyframe local descriptors resident in HBM (hfb_kfstore_*): LocalMapping's neighbour matching without descriptor
+    traffic.  ``rows_per_slot`` = the extractor's per-frame keypoint capacity."""
+
+    def __init__(self, ctx: Context, n_slots: int, rows_per_slot: int):
+        self.ctx, self.n_slots, self.rows = ctx, n_slots, rows_per_slot
+        self.handle = C.c_void_p()
+        ctx.check(ctx.lib.hfb_kfstore_create(ctx.handle, n_slots, rows_per_slot, C.byref(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.hfb_kfstore_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.ctx.lib.hfb_kfstore_size(self.handle))
+
+    def put_frame(self, ctx: Context, kf_id: int, frame_index: int, n: int):
+        """Keyframe = frame ``frame_index`` of ``ctx``'s last extraction (first n keypoints), copied device to device."""
+        ctx.check(ctx.lib.hfb_kfstore_put_frame(ctx.handle, self.handle, int(kf_id), frame_index, n))
+
+    def put(self, ctx: Context, kf_id: int, descriptors):
+        d = as_f32(descriptors).reshape(-1, HFB_DESC_DIM)
+        ctx.check(ctx.lib.hfb_kfstore_put(ctx.handle, self.handle, int(kf_id), ptr(d, _f32p), d.shape[0]))
+
+    def erase(self, kf_id: int):
+        self.ctx.lib.hfb_kfstore_erase(self.handle, int(kf_id))
+
+    def match_neighbours(self, ctx: Context, kf_a: int, kf_b, mode: int, thr: float, rows_a: int):
+        """(idx [n_b, rows_a], val [n_b, rows_a]): keyframe kf_a against every stored keyframe of kf_b in one launch."""
+        ids = np.ascontiguousarray(kf_b, dtype=np.int64)
+        idx = np.full((len(ids), rows_a), -1, np.int32)
+        val = np.zeros((len(ids), rows_a), np.float32)
+        na = C.c_int32()
+        ctx.check(ctx.lib.hfb_match_kf_neighbours(ctx.handle, self.handle, int(kf_a), ptr(ids, _i64p), len(ids), mode, thr,
+                                                  ptr(idx, _i32p), ptr(val, _f32p), C.byref(na)))
+        assert na.value == rows_a or len(ids) == 0, (na.value, rows_a)
         return idx, val

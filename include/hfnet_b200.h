@@ -237,6 +237,24 @@ int hfb_match_consecutive(hfb_ctx* ctx, int32_t n_images, int32_t mode, float th
 /* match_idx / match_val of frame `image_index` (indices into the previous frame's keypoints), first n rows. */
 int hfb_fetch_matches(hfb_ctx* ctx, int32_t image_index, int32_t* match_idx, float* match_val, int32_t n);
 
+/* Keyframe descriptor store: the local descriptors of keyframes kept RESIDENT in HBM (fp32 rows + the split-precision image
+ * of the tensor-core contraction, prepared once), so that LocalMapping's per-keyframe matching -- the current keyframe
+ * against <= 30 covisible keyframes in CreateNewMapPoints / SearchInNeighbors (src/LocalMapping.cc:513-893,
+ * Matcher::SearchForTriangulation src/Matcher.cc:763-936) -- moves no descriptors: keyframe ids go up, match rows come
+ * back.  A store lives on one device and may be filled from one context (Tracking's, straight from the extraction that
+ * produced the keyframe: hfb_kfstore_put_frame) and read from another (LocalMapping's).  KeyFrame::SetBadFlag -> erase. */
+typedef struct hfb_kfstore hfb_kfstore;
+int hfb_kfstore_create(hfb_ctx* ctx, int32_t n_slots, int32_t rows_per_slot, hfb_kfstore** out);
+void hfb_kfstore_destroy(hfb_kfstore* store);
+int hfb_kfstore_put_frame(hfb_ctx* ctx, hfb_kfstore* store, int64_t kf_id, int32_t frame_index, int32_t n);
+int hfb_kfstore_put(hfb_ctx* ctx, hfb_kfstore* store, int64_t kf_id, const float* descriptors, int32_t n);
+int hfb_kfstore_erase(hfb_kfstore* store, int64_t kf_id);
+int32_t hfb_kfstore_size(hfb_kfstore* store);
+/* Keyframe kf_a against the n_b stored keyframes kf_b[] as one batched launch (mode / thr as hfb_match_batch).
+ * match_idx / match_val: [n_b][rows of kf_a] (*rows_a_out), indices into the rows of the respective neighbour. */
+int hfb_match_kf_neighbours(hfb_ctx* ctx, hfb_kfstore* store, int64_t kf_a, const int64_t* kf_b, int32_t n_b, int32_t mode,
+                            float thr, int32_t* match_idx, float* match_val, int32_t* rows_a_out);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:331-400) for a ragged batch of map points: point p owns the
  * descriptor rows offsets[p] .. offsets[p+1]-1 (its observations, <= 128); best_index[p] is the row (relative to the
  * point's first) whose median L2 distance to the point's other descriptors is smallest (first such row, the

@@ -78,3 +78,42 @@ def test_non_unit_rows_l2(small_ctx):
     B = (B * rng.uniform(0.8, 1.2, (380, 1))).astype(np.float32)
     idx, val, _ = small_ctx.match_mutual_l2(A, B, 0.6)
     _check(idx, val, match_ref.search_by_bow(A, B, 0.6), 400)
+
+
+def test_keyframe_store_neighbour_matching_equals_batch_call(native_lib):
+    """hfb_match_kf_neighbours on descriptors RESIDENT in the keyframe store == hfb_match_batch on host copies of the same
+    descriptors (both flavours), also across two contexts (store filled by one, read by the other) and after erase / reuse
+    of a slot."""
+    from hfnet_slam_b200.lib import Context, KeyFrameStore
+    rng = np.random.default_rng(4)
+    base = rng.standard_normal((700, 256)).astype(np.float32)
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    kfs = []
+    for k, n in enumerate((675, 640, 700, 1, 333, 675)):
+        d = base[rng.permutation(700)[:n]] + 0.03 * rng.standard_normal((n, 256)).astype(np.float32)
+        kfs.append((d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32))
+    with Context(height=64, width=64, n_levels=1, max_keypoints=64, max_batch=1, with_global=False) as ca, \
+            Context(height=64, width=64, n_levels=1, max_keypoints=64, max_batch=1, with_global=False) as cb:
+        store = KeyFrameStore(ca, n_slots=6, rows_per_slot=700)
+        for k, d in enumerate(kfs):
+            store.put(ca, 10 + k, d)
+        assert len(store) == 6
+        with pytest.raises(Exception):
+            store.put(ca, 99, kfs[0])                      # full
+        A = kfs[0]
+        nb = [1, 2, 3, 4, 5]
+        for mode, thr in ((0, 0.6), (1, 0.71875)):
+            idx, val = store.match_neighbours(cb, 10, [10 + k for k in nb], mode, thr, len(A))
+            A_all = np.concatenate([A] * len(nb))
+            B_all = np.concatenate([kfs[k] for k in nb])
+            cnt_b = np.array([len(kfs[k]) for k in nb], np.int32)
+            ref_i, ref_v = cb.match_batch(mode, A_all, B_all, (np.arange(len(nb)) * len(A)).astype(np.int32),
+                                          np.full(len(nb), len(A), np.int32), (np.cumsum(cnt_b) - cnt_b).astype(np.int32), cnt_b, thr)
+            assert np.array_equal(idx.reshape(-1), ref_i) and np.array_equal(val.reshape(-1), ref_v), mode
+            assert (idx[0] >= 0).sum() > 100
+        store.erase(12)
+        store.put(cb, 50, kfs[2][:100])                    # the freed slot is reused, shorter than before
+        idx, val = store.match_neighbours(ca, 10, [50], 0, 0.6, len(A))
+        ref_i, ref_v, _ = ca.match_mutual_l2(A, kfs[2][:100], 0.6)
+        assert np.array_equal(idx[0], ref_i) and np.array_equal(val[0], ref_v)
+        store.close()
