@@ -271,3 +271,151 @@ class Matcher:
         best_dist[q] = np.where(idx[:, 0] >= 0, dist[:, 0], best_dist[q])
         best_idx[q[hit]] = idx[hit, 0]
         return best_idx, best_dist
+
+    # ------------------------------------------------------------------------------------------------ m4, remaining variants
+    @staticmethod
+    def _predict_levels(max_dist, dist, log_scale_factor, n_levels):
+        """MapPoint::PredictScale (src/MapPoint.cc:518-552), vectorised in fp32; 0 for a single-level pyramid."""
+        if n_levels <= 1:
+            return np.zeros(len(dist), np.int32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = (np.asarray(max_dist, np.float32) / dist).astype(np.float32)
+            lvl = np.ceil(np.log(ratio) / np.float32(log_scale_factor))
+        return np.clip(np.nan_to_num(lvl, nan=0.0, posinf=n_levels - 1, neginf=0.0), 0, n_levels - 1).astype(np.int32)
+
+    @staticmethod
+    def _invariance(min_dist, max_dist, n_levels):
+        """MapPoint::GetMin/MaxDistanceInvariance (src/MapPoint.cc:504-516)."""
+        if n_levels <= 1:
+            return np.zeros(len(min_dist), np.float32), np.full(len(min_dist), 10000.0, np.float32)
+        return ((np.asarray(min_dist, np.float32) / np.float32(1.2)).astype(np.float32),
+                (np.float32(1.2) * np.asarray(max_dist, np.float32)).astype(np.float32))
+
+    def _claim_best(self, q, mp_desc, uv, rad, mn, mx, feat_desc, feat_xy, feat_oct, occupied, threshold):
+        """Sequential best-1 claiming shared by the variants below: queries ``q`` in order, each takes the nearest free
+        in-window feature if its distance <= threshold (device top-4 lists; exact re-scan when a list is exhausted)."""
+        occ = np.array(occupied, bool, copy=True)
+        owner = np.full(feat_desc.shape[0], -1, np.int32)
+        n = 0
+        if len(q) == 0 or feat_desc.shape[0] == 0:
+            return owner, n
+        idx, dist, _ = self.ctx.match_projection(mp_desc[q], uv, rad, mn, mx, feat_desc, feat_xy, feat_oct, occ.astype(np.uint8))
+        for row, i in enumerate(q):
+            cand = [(dist[row, k], int(idx[row, k])) for k in range(idx.shape[1]) if idx[row, k] >= 0]
+            free = [(d, j) for d, j in cand if not occ[j]]
+            if not free and len(cand) == idx.shape[1]:
+                free = [(d, j) for d, _, j in self._rescan_window(mp_desc[i], uv[row], rad[row], mn[row], mx[row], feat_desc,
+                                                                   feat_xy, feat_oct, occ, set())]
+            if free and free[0][0] <= np.float32(threshold):
+                j = free[0][1]
+                owner[j] = i
+                occ[j] = True
+                n += 1
+        return owner, n
+
+    def search_by_projection_keyframe(self, Tcw, K, bounds, scale_factors, log_scale_factor, mp_pos, mp_min_dist, mp_max_dist,
+                                      mp_desc, mp_skip, cur_desc, cur_xy, cur_octave, cur_occupied, th: float, threshold: float):
+        """Matcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, threshold) (src/Matcher.cc:1723-1805,
+        relocalisation): geometry on the host, window search over octaves [pred-1, pred+1] on the device, sequential
+        claiming here.  Returns (assigned: map-point index per frame feature or -1, n_matches)."""
+        Tcw = np.asarray(Tcw, np.float32)
+        fx, fy, cx, cy = [np.float32(v) for v in K]
+        mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+        P = np.asarray(mp_pos, np.float32)
+        sf = np.asarray(scale_factors, np.float32)
+        R, t = Tcw[:, :3], Tcw[:, 3]
+        Ow = (-(R.T @ t)).astype(np.float32)
+        pc = (P @ R.T + t).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = fx * pc[:, 0] / pc[:, 2] + cx
+            v = fy * pc[:, 1] / pc[:, 2] + cy
+        PO = (P - Ow).astype(np.float32)
+        d3 = np.sqrt(np.sum(PO * PO, axis=1, dtype=np.float32)).astype(np.float32)
+        mn_inv, mx_inv = self._invariance(mp_min_dist, mp_max_dist, len(sf))
+        ok = ~np.asarray(mp_skip, bool) & np.isfinite(u) & np.isfinite(v) & ~((u < mnx) | (u > mxx) | (v < mny) | (v > mxy))
+        ok &= ~((d3 < mn_inv) | (d3 > mx_inv))
+        q = np.flatnonzero(ok)
+        lv = self._predict_levels(np.asarray(mp_max_dist, np.float32)[q], d3[q], log_scale_factor, len(sf))
+        rad = (np.float32(th) * sf[lv]).astype(np.float32)
+        uv = np.stack([u[q], v[q]], 1).astype(np.float32)
+        return self._claim_best(q, np.asarray(mp_desc, np.float32), uv, rad, lv - 1, lv + 1, np.asarray(cur_desc, np.float32),
+                                np.asarray(cur_xy, np.float32), np.asarray(cur_octave, np.int32), cur_occupied, threshold)
+
+    def search_by_projection_sim3(self, Tcw, Ow, K, bounds, scale_factors, log_scale_factor, mp_pos, mp_normal, mp_min_dist,
+                                  mp_max_dist, mp_desc, mp_skip, kf_desc, kf_xy, kf_octave, kf_matched, th: float,
+                                  threshold: float):
+        """Matcher::SearchByProjection(pKF, Scw, vpPoints[, vpPointsKFs], vpMatched[, vpMatchedKF], th, threshold)
+        (src/Matcher.cc:265-367, :369-484; loop detection / place recognition): Tcw / Ow derived from the Sim3 by the
+        caller as at :275-276.  Returns (matched: point index per keyframe feature or -1 for the NEW matches, n_matches);
+        the second overload's vpMatchedKF is the caller's lookup of the point's source keyframe."""
+        Tcw = np.asarray(Tcw, np.float32)
+        fx, fy, cx, cy = [np.float32(v) for v in K]
+        mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+        P = np.asarray(mp_pos, np.float32)
+        sf = np.asarray(scale_factors, np.float32)
+        pc = (P @ Tcw[:, :3].T + Tcw[:, 3]).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = fx * pc[:, 0] / pc[:, 2] + cx
+            v = fy * pc[:, 1] / pc[:, 2] + cy
+        PO = (P - np.asarray(Ow, np.float32)).astype(np.float32)
+        d3 = np.sqrt(np.sum(PO * PO, axis=1, dtype=np.float32)).astype(np.float32)
+        mn_inv, mx_inv = self._invariance(mp_min_dist, mp_max_dist, len(sf))
+        ok = ~np.asarray(mp_skip, bool) & ~(pc[:, 2] < 0) & (u >= mnx) & (u < mxx) & (v >= mny) & (v < mxy)
+        ok &= ~((d3 < mn_inv) | (d3 > mx_inv))
+        ok &= ~(np.sum(PO * np.asarray(mp_normal, np.float32), axis=1, dtype=np.float32) < np.float32(0.5) * d3)
+        q = np.flatnonzero(ok)
+        lv = self._predict_levels(np.asarray(mp_max_dist, np.float32)[q], d3[q], log_scale_factor, len(sf))
+        rad = (np.float32(th) * sf[lv]).astype(np.float32)
+        uv = np.stack([u[q], v[q]], 1).astype(np.float32)
+        return self._claim_best(q, np.asarray(mp_desc, np.float32), uv, rad, lv - 1, lv, np.asarray(kf_desc, np.float32),
+                                np.asarray(kf_xy, np.float32), np.asarray(kf_octave, np.int32), kf_matched, threshold)
+
+    def _sim3_directed(self, Tsrc_w, S_dst_src, K, bounds, sf, log_scale_factor, mp_pos, mp_min, mp_max, mp_desc, mp_valid,
+                       already, dst_desc, dst_xy, dst_oct, th):
+        """One direction of SearchBySim3 (src/Matcher.cc:1393-1466): independent queries -> the device's best in-window
+        candidate is the answer."""
+        fx, fy, cx, cy = [np.float32(v) for v in K]
+        mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+        Ts = np.asarray(Tsrc_w, np.float32)
+        s, Rd, td = np.float32(S_dst_src[0]), np.asarray(S_dst_src[1], np.float32), np.asarray(S_dst_src[2], np.float32)
+        P = np.asarray(mp_pos, np.float32)
+        p_src = (P @ Ts[:, :3].T + Ts[:, 3]).astype(np.float32)
+        p = (s * (p_src @ Rd.T) + td).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            invz = (np.float32(1.0) / p[:, 2]).astype(np.float32)
+            u = fx * (p[:, 0] * invz) + cx
+            v = fy * (p[:, 1] * invz) + cy
+        d3 = np.sqrt(np.sum(p * p, axis=1, dtype=np.float32)).astype(np.float32)
+        mn_inv, mx_inv = self._invariance(mp_min, mp_max, len(sf))
+        ok = np.asarray(mp_valid, bool) & ~np.asarray(already, bool) & ~(p[:, 2] < 0) & (u >= mnx) & (u < mxx) & (v >= mny) & (v < mxy)
+        ok &= ~((d3 < mn_inv) | (d3 > mx_inv))
+        out = np.full(P.shape[0], -1, np.int32)
+        q = np.flatnonzero(ok)
+        if len(q) == 0 or np.asarray(dst_desc).shape[0] == 0:
+            return out
+        lv = self._predict_levels(np.asarray(mp_max, np.float32)[q], d3[q], log_scale_factor, len(sf))
+        rad = (np.float32(th) * sf[lv]).astype(np.float32)
+        idx, dist, _ = self.ctx.match_projection(np.asarray(mp_desc, np.float32)[q], np.stack([u[q], v[q]], 1), rad, lv - 1, lv,
+                                                 dst_desc, dst_xy, dst_oct)
+        hit = (idx[:, 0] >= 0) & (dist[:, 0] <= np.float32(TH_HIGH))
+        out[q[hit]] = idx[hit, 0]
+        return out
+
+    def search_by_sim3(self, K, bounds, scale_factors, log_scale_factor, T1w, T2w, S12, S21, mp1_pos, mp1_min, mp1_max, mp1_desc,
+                       mp1_valid, already1, mp2_pos, mp2_min, mp2_max, mp2_desc, mp2_valid, already2, desc1, xy1, oct1, desc2,
+                       xy2, oct2, th: float):
+        """Matcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/Matcher.cc:1355-1572): both directed searches on
+        the device, the agreement check (:1553-1567) here.  S12 / S21 = (scale, R, t).  Returns (match12, n)."""
+        sf = np.asarray(scale_factors, np.float32)
+        d1, d2 = np.asarray(desc1, np.float32), np.asarray(desc2, np.float32)
+        x1, x2 = np.asarray(xy1, np.float32), np.asarray(xy2, np.float32)
+        o1, o2 = np.asarray(oct1, np.int32), np.asarray(oct2, np.int32)
+        m1 = self._sim3_directed(T1w, S21, K, bounds, sf, log_scale_factor, mp1_pos, mp1_min, mp1_max, mp1_desc, mp1_valid,
+                                 already1, d2, x2, o2, th)
+        m2 = self._sim3_directed(T2w, S12, K, bounds, sf, log_scale_factor, mp2_pos, mp2_min, mp2_max, mp2_desc, mp2_valid,
+                                 already2, d1, x1, o1, th)
+        out = np.full(len(m1), -1, np.int32)
+        i1 = np.flatnonzero(m1 >= 0)
+        agree = i1[m2[m1[i1]] == i1]
+        out[agree] = m1[agree]
+        return out, int(len(agree))

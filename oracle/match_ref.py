@@ -314,3 +314,197 @@ def fuse(Tcw: np.ndarray, Ow: np.ndarray, K, bounds, scale_factors, log_scale_fa
         if not best_dist[i] <= np.float32(th_low):
             best_idx[i] = -1
     return best_idx, best_dist
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The remaining members of the projection family, transcribed loop for loop.  Shared helpers:
+def _predict_scale(max_dist, dist, log_scale_factor, n_levels):
+    """MapPoint::PredictScale (src/MapPoint.cc:518-552): ceil(log(mfMaxDistance / dist) / mfLogScaleFactor), clamped;
+    0 for a single-level pyramid."""
+    if n_levels <= 1:
+        return 0
+    ratio = np.float32(max_dist) / np.float32(dist)
+    lvl = int(np.ceil(np.log(ratio) / np.float32(log_scale_factor)))
+    return min(max(lvl, 0), n_levels - 1)
+
+
+def _invariance(min_dist, max_dist, n_levels):
+    """MapPoint::GetMinDistanceInvariance / GetMaxDistanceInvariance (src/MapPoint.cc:504-516)."""
+    if n_levels <= 1:
+        return np.float32(0), np.float32(10000)
+    return np.float32(min_dist) / np.float32(1.2), np.float32(1.2) * np.float32(max_dist)
+
+
+def search_by_projection_keyframe(Tcw, K, bounds, scale_factors, log_scale_factor, mp_pos, mp_min_dist, mp_max_dist,
+                                  mp_desc, mp_skip, cur_desc, cur_xy, cur_octave, cur_occupied, th: float,
+                                  threshold: float):
+    """Matcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, threshold) (src/Matcher.cc:1723-1805), used by
+    relocalisation: the keyframe's map points (``mp_skip`` = null / bad / already found) are projected with the frame's
+    pose; frame bounds [mnMinX, mnMaxX] x [mnMinY, mnMaxY] (both ends inside, :1747-1750; NO positive-depth and NO
+    viewing-angle test in this variant), invariance range, predicted level, window th * scale[level] over octaves
+    [pred-1, pred+1] (Frame::GetFeaturesInArea with level bounds), features that already carry a map point skipped --
+    including the ones claimed earlier in this call (:1795) --, nearest descriptor accepted iff <= threshold.
+    Returns (assigned: map-point index per frame feature or -1, n_matches)."""
+    fx, fy, cx, cy = [np.float32(v) for v in K]
+    mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+    Tcw = np.asarray(Tcw, np.float32)
+    R, t = Tcw[:, :3], Tcw[:, 3]
+    Ow = (-(R.T @ t)).astype(np.float32)
+    sf = np.asarray(scale_factors, np.float32)
+    nl = len(sf)
+    occ = np.array(cur_occupied, bool, copy=True)
+    assigned = np.full(cur_desc.shape[0], -1, np.int32)
+    n = 0
+    for i in range(mp_pos.shape[0]):
+        if mp_skip[i]:
+            continue
+        pw = mp_pos[i].astype(np.float32)
+        pc = (R @ pw + t).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = fx * pc[0] / pc[2] + cx
+            v = fy * pc[1] / pc[2] + cy
+        if u < mnx or u > mxx or v < mny or v > mxy or not (np.isfinite(u) and np.isfinite(v)):
+            continue
+        PO = (pw - Ow).astype(np.float32)
+        dist3d = np.float32(np.sqrt(np.sum(PO * PO, dtype=np.float32)))
+        mn, mx = _invariance(mp_min_dist[i], mp_max_dist[i], nl)
+        if dist3d < mn or dist3d > mx:
+            continue
+        lvl = _predict_scale(mp_max_dist[i], dist3d, log_scale_factor, nl)
+        r = np.float32(th) * sf[lvl]
+        ok = (np.abs(cur_xy[:, 0] - u) < r) & (np.abs(cur_xy[:, 1] - v) < r) & (cur_octave >= lvl - 1) & (cur_octave <= lvl + 1)
+        best, bidx = np.finfo(np.float32).max, -1
+        for j in np.flatnonzero(ok):
+            if occ[j]:
+                continue
+            d = descriptor_distance(mp_desc[i], cur_desc[j])
+            if d < best:
+                best, bidx = d, int(j)
+        if best <= np.float32(threshold):
+            assigned[bidx] = i
+            occ[bidx] = True
+            n += 1
+    return assigned, n
+
+
+def search_by_projection_sim3(Tcw, Ow, K, bounds, scale_factors, log_scale_factor, mp_pos, mp_normal, mp_min_dist,
+                              mp_max_dist, mp_desc, mp_skip, kf_desc, kf_xy, kf_octave, kf_matched, th: float,
+                              threshold: float):
+    """Matcher::SearchByProjection(pKF, Scw, vpPoints[, vpPointsKFs], vpMatched[, vpMatchedKF], th, threshold)
+    (src/Matcher.cc:265-367 and :369-484; the second only also records the source keyframe of each point): Tcw / Ow from
+    the Sim3 as at :275-276; per candidate point (``mp_skip`` = bad / already in vpMatched): positive depth,
+    KeyFrame::IsInImage (min <= . < max), invariance range, viewing angle (PO . Pn >= 0.5 dist), predicted level, window
+    th * scale[level] over ALL octaves, then octave in [pred-1, pred], keyframe features that are already matched skipped
+    -- including those claimed earlier in this call --, nearest descriptor accepted iff <= threshold.
+    Returns (matched: point index per keyframe feature or -1 (only the NEW matches), n_matches)."""
+    fx, fy, cx, cy = [np.float32(v) for v in K]
+    mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+    Tcw = np.asarray(Tcw, np.float32)
+    R, t = Tcw[:, :3], Tcw[:, 3]
+    Ow = np.asarray(Ow, np.float32)
+    sf = np.asarray(scale_factors, np.float32)
+    nl = len(sf)
+    taken = np.array(kf_matched, bool, copy=True)
+    matched = np.full(kf_desc.shape[0], -1, np.int32)
+    n = 0
+    for i in range(mp_pos.shape[0]):
+        if mp_skip[i]:
+            continue
+        pw = mp_pos[i].astype(np.float32)
+        pc = (R @ pw + t).astype(np.float32)
+        if pc[2] < 0:
+            continue
+        u = fx * pc[0] / pc[2] + cx
+        v = fy * pc[1] / pc[2] + cy
+        if not (mnx <= u < mxx and mny <= v < mxy):
+            continue
+        PO = (pw - Ow).astype(np.float32)
+        dist = np.float32(np.sqrt(np.sum(PO * PO, dtype=np.float32)))
+        mn, mx = _invariance(mp_min_dist[i], mp_max_dist[i], nl)
+        if dist < mn or dist > mx:
+            continue
+        if np.float32(PO @ mp_normal[i].astype(np.float32)) < np.float32(0.5) * dist:
+            continue
+        lvl = _predict_scale(mp_max_dist[i], dist, log_scale_factor, nl)
+        r = np.float32(th) * sf[lvl]
+        ok = (np.abs(kf_xy[:, 0] - u) < r) & (np.abs(kf_xy[:, 1] - v) < r)
+        best, bidx = np.finfo(np.float32).max, -1
+        for j in np.flatnonzero(ok):
+            if taken[j]:
+                continue
+            kl = int(kf_octave[j])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            d = descriptor_distance(mp_desc[i], kf_desc[j])
+            if d < best:
+                best, bidx = d, int(j)
+        if best <= np.float32(threshold):
+            matched[bidx] = i
+            taken[bidx] = True
+            n += 1
+    return matched, n
+
+
+def _sim3_directed(Tsrc_w, S_dst_src, K, bounds, sf, log_scale_factor, mp_pos, mp_min, mp_max, mp_desc, mp_valid, already,
+                   dst_desc, dst_xy, dst_oct, th):
+    """One direction of SearchBySim3 (src/Matcher.cc:1393-1466): the source keyframe's map points through the source pose
+    and the similarity into the destination camera; best descriptor in the window, octave in [pred-1, pred], <= TH_HIGH."""
+    fx, fy, cx, cy = [np.float32(v) for v in K]
+    mnx, mxx, mny, mxy = [np.float32(v) for v in bounds]
+    Rs, ts = np.asarray(Tsrc_w, np.float32)[:, :3], np.asarray(Tsrc_w, np.float32)[:, 3]
+    s, Rd, td = np.float32(S_dst_src[0]), np.asarray(S_dst_src[1], np.float32), np.asarray(S_dst_src[2], np.float32)
+    nl = len(sf)
+    out = np.full(mp_pos.shape[0], -1, np.int32)
+    for i in range(mp_pos.shape[0]):
+        if not mp_valid[i] or already[i]:
+            continue
+        pw = mp_pos[i].astype(np.float32)
+        p_src = (Rs @ pw + ts).astype(np.float32)
+        p = (s * (Rd @ p_src) + td).astype(np.float32)
+        if p[2] < 0:
+            continue
+        invz = np.float32(1.0) / p[2]
+        u = fx * (p[0] * invz) + cx
+        v = fy * (p[1] * invz) + cy
+        if not (mnx <= u < mxx and mny <= v < mxy):
+            continue
+        dist3d = np.float32(np.sqrt(np.sum(p * p, dtype=np.float32)))
+        mn, mx = _invariance(mp_min[i], mp_max[i], nl)
+        if dist3d < mn or dist3d > mx:
+            continue
+        lvl = _predict_scale(mp_max[i], dist3d, log_scale_factor, nl)
+        r = np.float32(th) * sf[lvl]
+        ok = (np.abs(dst_xy[:, 0] - u) < r) & (np.abs(dst_xy[:, 1] - v) < r)
+        best, bidx = np.finfo(np.float32).max, -1
+        for j in np.flatnonzero(ok):
+            kl = int(dst_oct[j])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            d = descriptor_distance(mp_desc[i], dst_desc[j])
+            if d < best:
+                best, bidx = d, int(j)
+        if best <= TH_HIGH:
+            out[i] = bidx
+    return out
+
+
+def search_by_sim3(K, bounds, scale_factors, log_scale_factor, T1w, T2w, S12, S21, mp1_pos, mp1_min, mp1_max, mp1_desc,
+                   mp1_valid, already1, mp2_pos, mp2_min, mp2_max, mp2_desc, mp2_valid, already2, desc1, xy1, oct1, desc2,
+                   xy2, oct2, th: float):
+    """Matcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/Matcher.cc:1355-1572): feature i of a keyframe carries
+    map point i (``mp*_valid`` = non-null and not bad; ``already*`` = vbAlreadyMatched*); KF1's points go through T1w and
+    S21 = (scale, R, t) into camera 2 and are matched against KF2's features, KF2's through T2w and S12 against KF1's;
+    a pair is kept iff both directions agree (:1553-1567).  Returns (match12: feature of KF2 per feature of KF1 or -1, n)."""
+    sf = np.asarray(scale_factors, np.float32)
+    m1 = _sim3_directed(T1w, S21, K, bounds, sf, log_scale_factor, mp1_pos, mp1_min, mp1_max, mp1_desc, mp1_valid, already1,
+                        desc2, xy2, oct2, th)
+    m2 = _sim3_directed(T2w, S12, K, bounds, sf, log_scale_factor, mp2_pos, mp2_min, mp2_max, mp2_desc, mp2_valid, already2,
+                        desc1, xy1, oct1, th)
+    out = np.full(len(m1), -1, np.int32)
+    n = 0
+    for i1 in range(len(m1)):
+        i2 = m1[i1]
+        if i2 >= 0 and m2[i2] == i1:
+            out[i1] = i2
+            n += 1
+    return out, n

@@ -341,3 +341,30 @@ def test_onnx_initialiser_import_round_trip(tmp_path):
     oi.write_model(path, [c for c in order if c[0] != "l10.project"], extra)
     with pytest.raises(ValueError):
         oi.convert(path)
+
+
+def test_remaining_projection_variants_replay_equals_oracle():
+    """Host sides of SearchByProjection(F, KF), the Sim3 projection search and SearchBySim3 (src/Matcher.cc:1723-1805,
+    :265-484, :1355-1572) over the numpy stand-in for the device candidates == the literal restatements; k = 2 forces the
+    exhausted-list re-scan."""
+    from hfnet_slam_b200.matcher import Matcher
+    from oracle import match_ref
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from test_projection_gpu import _kf_args, _sim3_scene
+    for k in (4, 2):
+        sc, occ = _kf_args(0)
+        a = (sc["Tcw"], sc["K"], sc["bounds"], sc["scale_factors"], sc["log_scale_factor"], sc["mp_pos"], sc["mp_min_dist"],
+             sc["mp_max_dist"], sc["mp_desc"], sc["mp_skip"], sc["kf_desc"], sc["kf_xy"], sc["kf_octave"], occ, 10.0, 0.75)
+        got, n = Matcher(_FakeProjectionCtx(k)).search_by_projection_keyframe(*a)
+        ref, nr = match_ref.search_by_projection_keyframe(*a)
+        assert nr > 100 and n == nr and np.array_equal(got, ref)
+        b = (sc["Tcw"], sc["Ow"], sc["K"], sc["bounds"], sc["scale_factors"], sc["log_scale_factor"], sc["mp_pos"], sc["mp_normal"],
+             sc["mp_min_dist"], sc["mp_max_dist"], sc["mp_desc"], sc["mp_skip"], sc["kf_desc"], sc["kf_xy"], sc["kf_octave"], occ,
+             8.0, 0.6)
+        got, n = Matcher(_FakeProjectionCtx(k)).search_by_projection_sim3(*b)
+        ref, nr = match_ref.search_by_projection_sim3(*b)
+        assert nr > 40 and n == nr and np.array_equal(got, ref)
+    c = _sim3_scene(3)
+    got, n = Matcher(_FakeProjectionCtx(4)).search_by_sim3(*c)
+    ref, nr = match_ref.search_by_sim3(*c)
+    assert nr > 40 and n == nr and np.array_equal(got, ref)

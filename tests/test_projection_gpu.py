@@ -203,3 +203,105 @@ def test_fuse_matches_oracle(small_ctx, seed):
     assert np.array_equal(got_i, ref_i)
     hit = ref_i >= 0
     assert np.abs(got_d[hit] - ref_d[hit]).max() <= 2e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the remaining members of the projection family
+def _kf_args(seed):
+    sc = _fuse_scene(seed)
+    rng = np.random.default_rng(100 + seed)
+    occ = rng.uniform(size=sc["kf_desc"].shape[0]) < 0.1
+    return sc, occ
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_by_projection_keyframe_matches_oracle(small_ctx, seed):
+    """Matcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, threshold) (src/Matcher.cc:1723-1805)."""
+    sc, occ = _kf_args(seed)
+    args = (sc["Tcw"], sc["K"], sc["bounds"], sc["scale_factors"], sc["log_scale_factor"], sc["mp_pos"], sc["mp_min_dist"],
+            sc["mp_max_dist"], sc["mp_desc"], sc["mp_skip"], sc["kf_desc"], sc["kf_xy"], sc["kf_octave"], occ, 10.0, 0.75)
+    got, n_got = Matcher(small_ctx).search_by_projection_keyframe(*args)
+    ref, n_ref = match_ref.search_by_projection_keyframe(*args)
+    assert n_ref > 100 and n_got == n_ref and np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_by_projection_sim3_matches_oracle(small_ctx, seed):
+    """Matcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, threshold) and its vpMatchedKF overload
+    (src/Matcher.cc:265-484)."""
+    sc, occ = _kf_args(seed)
+    args = (sc["Tcw"], sc["Ow"], sc["K"], sc["bounds"], sc["scale_factors"], sc["log_scale_factor"], sc["mp_pos"], sc["mp_normal"],
+            sc["mp_min_dist"], sc["mp_max_dist"], sc["mp_desc"], sc["mp_skip"], sc["kf_desc"], sc["kf_xy"], sc["kf_octave"], occ,
+            8.0, 0.6)
+    got, n_got = Matcher(small_ctx).search_by_projection_sim3(*args)
+    ref, n_ref = match_ref.search_by_projection_sim3(*args)
+    assert n_ref > 40 and n_got == n_ref and np.array_equal(got, ref)
+    assert not (got[occ] >= 0).any(), "features that were already matched are never claimed"
+
+
+def _sim3_scene(seed):
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = 458.654, 457.296, 367.215, 248.375
+    W, H, M = 752, 480, 450
+
+    def rot(ax, ang):
+        c, s = np.cos(ang), np.sin(ang)
+        return {0: np.array([[1, 0, 0], [0, c, -s], [0, s, c]]), 1: np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])}[ax].astype(np.float32)
+
+    T1w = np.concatenate([rot(1, 0.02), np.array([[0.05], [0.0], [0.1]], np.float32)], 1)
+    T2w = np.concatenate([rot(1, -0.04) @ rot(0, 0.01), np.array([[-0.2], [0.03], [0.05]], np.float32)], 1)
+    R12 = (T1w[:, :3] @ T2w[:, :3].T).astype(np.float32)
+    t12 = (T1w[:, 3] - R12 @ T2w[:, 3]).astype(np.float32)
+    S12 = (np.float32(1.0), R12, t12)
+    S21 = (np.float32(1.0), R12.T.copy(), (-(R12.T @ t12)).astype(np.float32))
+    scale = (1.2 ** np.arange(4)).astype(np.float32)
+
+    def kf(T):
+        Pw = np.stack([rng.uniform(-5, 5, M), rng.uniform(-4, 4, M), rng.uniform(2, 12, M)], 1).astype(np.float32)
+        pc = Pw @ T[:, :3].T + T[:, 3]
+        d3 = np.linalg.norm(pc, axis=1).astype(np.float32)
+        mx = (d3 * rng.uniform(0.9, 1.2 ** 3, M)).astype(np.float32)
+        mn = (mx / 1.2 ** 4 * rng.uniform(0.8, 1.3, M)).astype(np.float32)
+        desc = rng.normal(size=(M, 256)).astype(np.float32)
+        desc /= np.linalg.norm(desc, axis=1, keepdims=True)
+        uv = np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], 1).astype(np.float32)
+        return Pw, mn, mx, desc, uv
+
+    P1, mn1, mx1, md1, uv1 = kf(T1w)
+    # keyframe 2 re-observes the first 300 points of keyframe 1 (as its own map points, at its own feature slots) + clutter
+    P2, mn2, mx2, md2, uv2 = kf(T2w)
+    perm = rng.permutation(M)[:300]
+    P2[:300], mn2[:300], mx2[:300] = P1[perm], mn1[perm], mx1[perm]
+    md2[:300] = md1[perm] + 0.02 * rng.normal(size=(300, 256)).astype(np.float32)
+    md2 /= np.linalg.norm(md2, axis=1, keepdims=True)
+    pc2 = P2 @ T2w[:, :3].T + T2w[:, 3]
+    uv2 = np.stack([fx * pc2[:, 0] / pc2[:, 2] + cx, fy * pc2[:, 1] / pc2[:, 2] + cy], 1).astype(np.float32)
+    xy1 = (uv1 + rng.normal(0, 1.0, uv1.shape)).astype(np.float32)
+    xy2 = (uv2 + rng.normal(0, 1.0, uv2.shape)).astype(np.float32)
+    d1 = (md1 + 0.02 * rng.normal(size=md1.shape)).astype(np.float32)
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    d2 = (md2 + 0.02 * rng.normal(size=md2.shape)).astype(np.float32)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    o1 = rng.integers(0, 4, M).astype(np.int32)
+    o2 = rng.integers(0, 4, M).astype(np.int32)
+
+    def pred(mx, pc):     # MapPoint::PredictScale of the shared points in the OTHER camera: their features sit at that octave
+        lv = np.ceil(np.log(mx / np.linalg.norm(pc, axis=1)) / np.log(1.2))
+        return np.clip(lv, 0, 3).astype(np.int32)
+
+    o2[:300] = pred(mx1[perm], P1[perm] @ T2w[:, :3].T + T2w[:, 3]) - (rng.uniform(size=300) < 0.3)
+    o1[perm] = pred(mx2[:300], P2[:300] @ T1w[:, :3].T + T1w[:, 3]) - (rng.uniform(size=300) < 0.3)
+    o1, o2 = np.clip(o1, 0, 3).astype(np.int32), np.clip(o2, 0, 3).astype(np.int32)
+    v1, v2 = rng.uniform(size=M) > 0.1, rng.uniform(size=M) > 0.1
+    a1, a2 = rng.uniform(size=M) < 0.05, rng.uniform(size=M) < 0.05
+    return ((fx, fy, cx, cy), (0.0, float(W), 0.0, float(H)), scale, float(np.log(1.2)), T1w, T2w, S12, S21, P1, mn1, mx1, md1, v1, a1,
+            P2, mn2, mx2, md2, v2, a2, d1, xy1, o1, d2, xy2, o2, 7.5)
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_search_by_sim3_matches_oracle(small_ctx, seed):
+    """Matcher::SearchBySim3 (src/Matcher.cc:1355-1572): two directed windowed searches + agreement."""
+    args = _sim3_scene(seed)
+    got, n_got = Matcher(small_ctx).search_by_sim3(*args)
+    ref, n_ref = match_ref.search_by_sim3(*args)
+    assert n_ref > 40 and n_got == n_ref and np.array_equal(got, ref)
