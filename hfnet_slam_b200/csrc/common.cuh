@@ -151,6 +151,11 @@ struct hfb_ctx {
   cudaStream_t copy_stream = nullptr;   // in-graph D2H of the local features, concurrent with the matching kernels
   cudaEvent_t ev_local = nullptr, ev_copied = nullptr;
   bool fork_branches = true;            // HFB_FORK=0: everything on one stream
+  // pyramid levels >= 1 run on their own streams (fork after the resize chain, join before the sampling kernels): a
+  // single frame's level grids are far smaller than the machine, so the levels fill each other's idle SMs
+  cudaStream_t level_stream[HFB_MAX_LEVELS] = {nullptr};
+  cudaEvent_t ev_level_fork = nullptr, ev_level_join[HFB_MAX_LEVELS] = {nullptr};
+  bool fork_levels = true;              // HFB_FORK_LEVELS=0: levels one after the other on the main stream
   bool fused_stem = true;               // HFB_STEM=0: layer_1 and layer_2 as two kernels
   bool join_pending = false;            // the global branch is still running on side_stream (joined by enqueue_extract)
   // Host destinations of the extraction results when they can be written by the extraction graph itself (page-locked,
@@ -179,8 +184,8 @@ struct hfb_ctx {
   int n_levels = 0;
   LevelPlan lv[HFB_MAX_LEVELS];
   int cand_cap = 0;
-  u64* d_sel = nullptr;     // [max_batch][8192] sorted top-k keys of the level being processed
-  int* d_nsel = nullptr;    // [max_batch]
+  u64* d_sel = nullptr;     // [n_levels][max_batch][8192] sorted top-k keys per level
+  int* d_nsel = nullptr;    // [n_levels][max_batch]
   int* d_overflow = nullptr;
   bool debug = false;       // HFB_DEBUG=1: keep detector logits for hfb_debug_tensor
   // extraction outputs (device): [max_batch][n_levels*max_keypoints] SoA + global descriptors
@@ -286,9 +291,17 @@ static inline void hfb_launch(hfb_ctx* ctx, K kernel, dim3 grid, dim3 block, siz
 // postproc.cu
 int launch_nms(hfb_ctx* ctx, const float* d_scores, float* d_out, int H, int W, int B, float threshold, u64* d_cand,
                int* d_cand_count, int cand_cap);
+// d_sel / d_nsel: the LEVEL's slice of the selection arrays; d_nsel_levels + l * nsel_stride = counts of level l (the
+// rows of level `level` start after the selected rows of the levels below it)
+int launch_select(hfb_ctx* ctx, const float* d_nms, int H, int W, u64* d_cand, int* d_cand_count, int cand_cap,
+                  u64* d_sel, int* d_nsel, int n_keypoints, float threshold, int B, int* d_overflow,
+                  bool candidates_ready);
+int launch_sample(hfb_ctx* ctx, int H, int W, const float* d_descmap, int Hd, int Wd, const u64* d_sel,
+                  const int* d_nsel_levels, int nsel_stride, int n_keypoints, float level_scale, int level, int B,
+                  int kp_cap, float* d_x, float* d_y, float* d_resp, int* d_oct, float* d_desc, int* d_kcount);
 int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const float* d_descmap, int Hd, int Wd,
                          u64* d_cand, int* d_cand_count, int cand_cap, u64* d_sel, int* d_nsel, int n_keypoints,
-                         float threshold, float level_scale, int level, int B, int kp_cap, float* d_x, float* d_y,
+                         float threshold, float level_scale, int B, int kp_cap, float* d_x, float* d_y,
                          float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow,
                          bool candidates_ready);
 int launch_resize(hfb_ctx* ctx, const uint8_t* d_src, int sh, int sw, uint8_t* d_dst, int dh, int dw, const int* d_xi,

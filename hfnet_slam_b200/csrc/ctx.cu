@@ -131,6 +131,14 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   if (const char* fk = getenv("HFB_FORK")) ctx->fork_branches = !(fk[0] == '0');
+  if (const char* fk = getenv("HFB_FORK_LEVELS")) ctx->fork_levels = !(fk[0] == '0');
+  if (ctx->n_levels > 1) {
+    HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_level_fork, cudaEventDisableTiming));
+    for (int l = 1; l < ctx->n_levels; ++l) {
+      HFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->level_stream[l], cudaStreamNonBlocking));
+      HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_level_join[l], cudaEventDisableTiming));
+    }
+  }
   if (const char* sk = getenv("HFB_STEM")) ctx->fused_stem = !(sk[0] == '0');
   // level shapes: mvScaleFactor[l] = scaleFactor^l accumulated in float (HFextractor.cc:92-103); image size of
   // level l = cvRound(size * 1/scale) (HFextractor.cc:159-173, BaseModel.cc:35-65)
@@ -180,8 +188,9 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   }
   HFB_TRY(ctx->dalloc(&ctx->d_global, nb * HFB_GLOBAL_DIM));
   HFB_TRY(ctx->dalloc(&ctx->d_kcount, nb * HFB_MAX_LEVELS));
-  HFB_TRY(ctx->dalloc(&ctx->d_sel, nb * 8192));
-  HFB_TRY(ctx->dalloc(&ctx->d_nsel, nb));
+  HFB_TRY(ctx->dalloc(&ctx->d_sel, (size_t)ctx->n_levels * nb * 8192));
+  HFB_TRY(ctx->dalloc(&ctx->d_nsel, (size_t)ctx->n_levels * nb));
+  HFB_CUDA(ctx, cudaMemset(ctx->d_nsel, 0, (size_t)ctx->n_levels * nb * sizeof(int)));
   HFB_TRY(ctx->dalloc(&ctx->d_overflow, 1));
   HFB_TRY(ctx->dalloc(&ctx->d_pair_tab, 4));
   HFB_TRY(ctx->dalloc(&ctx->d_cm_tab, 4 * nb));
@@ -224,6 +233,11 @@ extern "C" void hfb_destroy(hfb_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_level_fork) cudaEventDestroy(ctx->ev_level_fork);
+  for (int l = 0; l < HFB_MAX_LEVELS; ++l) {
+    if (ctx->ev_level_join[l]) cudaEventDestroy(ctx->ev_level_join[l]);
+    if (ctx->level_stream[l]) cudaStreamDestroy(ctx->level_stream[l]);
+  }
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -474,17 +488,43 @@ static int enqueue_carry(hfb_ctx* ctx, int B) {
 // Enqueues pyramid + encoder + selection of every level for frames already in lv[0].d_img.
 static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float threshold) {
   HFB_TRY(enqueue_carry(ctx, B));
-  for (int l = 0; l < ctx->n_levels; ++l) {
+  const size_t nb = (size_t)ctx->cfg.max_batch;
+  for (int l = 1; l < ctx->n_levels; ++l) {   // the pyramid first: level l = cv::resize of level l - 1
+    LevelPlan &lv = ctx->lv[l], &pv = ctx->lv[l - 1];
+    HFB_TRY(launch_resize(ctx, pv.d_img, pv.H, pv.W, lv.d_img, lv.H, lv.W, lv.d_xi, lv.d_xa, lv.d_yi, lv.d_ya, B));
+  }
+  // Network + NMS + top-k of every level; levels >= 1 on their own streams (forked here, joined before the sampling
+  // kernels, whose row offsets need the selected counts of the levels below).
+  const bool fork_lv = ctx->n_levels > 1 && ctx->fork_levels && ctx->fork_branches && !ctx->prof_on;
+  cudaStream_t main_stream = ctx->stream;
+  struct StreamGuard {   // error returns must not leave the context on a level stream
+    hfb_ctx* c;
+    cudaStream_t s;
+    ~StreamGuard() { c->stream = s; }
+  } guard{ctx, main_stream};
+  if (fork_lv) HFB_CUDA(ctx, cudaEventRecord(ctx->ev_level_fork, main_stream));
+  for (int l = ctx->n_levels - 1; l >= 0; --l) {   // level 0 last: its enqueue leaves the global branch pending
     LevelPlan& lv = ctx->lv[l];
-    if (l > 0) {
-      LevelPlan& pv = ctx->lv[l - 1];
-      HFB_TRY(launch_resize(ctx, pv.d_img, pv.H, pv.W, lv.d_img, lv.H, lv.W, lv.d_xi, lv.d_xa, lv.d_yi, lv.d_ya, B));
+    const bool own = fork_lv && l > 0;
+    if (own) {
+      HFB_CUDA(ctx, cudaStreamWaitEvent(ctx->level_stream[l], ctx->ev_level_fork, 0));
+      ctx->stream = ctx->level_stream[l];
     }
     HFB_TRY(encoder_forward(ctx, l, B, threshold));
-    HFB_TRY(launch_select_sample(ctx, lv.d_nms, lv.H8, lv.W8, lv.d_descmap, lv.H8 / 8, lv.W8 / 8, lv.d_cand,
-                                 lv.d_cand_count, ctx->cand_cap, ctx->d_sel, ctx->d_nsel, n_per_level[l], threshold,
-                                 lv.scale, l, B, ctx->kp_cap, ctx->d_kx, ctx->d_ky, ctx->d_kresp, ctx->d_koct,
-                                 ctx->d_kdesc, ctx->d_kcount, ctx->d_overflow, true));
+    HFB_TRY(launch_select(ctx, lv.d_nms, lv.H8, lv.W8, lv.d_cand, lv.d_cand_count, ctx->cand_cap,
+                          ctx->d_sel + (size_t)l * nb * 8192, ctx->d_nsel + (size_t)l * nb, n_per_level[l], threshold, B,
+                          ctx->d_overflow, true));
+    if (own) {
+      HFB_CUDA(ctx, cudaEventRecord(ctx->ev_level_join[l], ctx->level_stream[l]));
+      ctx->stream = main_stream;
+    }
+  }
+  for (int l = 1; fork_lv && l < ctx->n_levels; ++l) HFB_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_level_join[l], 0));
+  for (int l = 0; l < ctx->n_levels; ++l) {
+    LevelPlan& lv = ctx->lv[l];
+    HFB_TRY(launch_sample(ctx, lv.H8, lv.W8, lv.d_descmap, lv.H8 / 8, lv.W8 / 8, ctx->d_sel + (size_t)l * nb * 8192,
+                          ctx->d_nsel, (int)nb, n_per_level[l], lv.scale, l, B, ctx->kp_cap, ctx->d_kx, ctx->d_ky,
+                          ctx->d_kresp, ctx->d_koct, ctx->d_kdesc, ctx->d_kcount));
   }
   // everything that does not depend on the global branch happens now (main stream), overlapping the side stream:
   // the optional frame-to-previous-frame association and the transfer of the local features
@@ -848,7 +888,7 @@ extern "C" int hfb_extract_level(hfb_ctx* ctx, int32_t level, const uint8_t* ima
   HFB_CUDA(ctx, cudaMemsetAsync(ctx->d_stream_state, 0, sizeof(int), st));   // no streaming history through this entry
   HFB_TRY(encoder_forward(ctx, level, 1, threshold));
   HFB_TRY(launch_select_sample(ctx, lv.d_nms, lv.H8, lv.W8, lv.d_descmap, lv.H8 / 8, lv.W8 / 8, lv.d_cand, lv.d_cand_count,
-                               ctx->cand_cap, ctx->d_sel, ctx->d_nsel, n_keypoints, threshold, 1.0f, 0, 1, ctx->kp_cap,
+                               ctx->cand_cap, ctx->d_sel, ctx->d_nsel, n_keypoints, threshold, 1.0f, 1, ctx->kp_cap,
                                ctx->d_kx, ctx->d_ky, ctx->d_kresp, ctx->d_koct, ctx->d_kdesc, ctx->d_kcount,
                                ctx->d_overflow, true));
   if (ctx->join_pending) {
@@ -969,7 +1009,7 @@ extern "C" int hfb_select_sample(hfb_ctx* ctx, const float* scores_nms, int32_t 
   HFB_CUDA(ctx, cudaMemcpyAsync(d_dm, desc_map, nd * 4, cudaMemcpyHostToDevice, ctx->stream));
   HFB_CUDA(ctx, cudaMemsetAsync(d_k, 0, HFB_MAX_LEVELS * 4, ctx->stream));
   HFB_TRY(launch_select_sample(ctx, d_nms, height, width, d_dm, desc_h, desc_w, d_cand, d_cnt, cap, ctx->d_sel,
-                               ctx->d_nsel, n_keypoints, threshold, 1.0f, 0, 1, 8192, d_x, d_y, d_r, d_o, d_d, d_k,
+                               ctx->d_nsel, n_keypoints, threshold, 1.0f, 1, 8192, d_x, d_y, d_r, d_o, d_d, d_k,
                                ctx->d_overflow, false));
   int cnt = 0;
   HFB_CUDA(ctx, cudaMemcpyAsync(&cnt, d_k, 4, cudaMemcpyDeviceToHost, ctx->stream));

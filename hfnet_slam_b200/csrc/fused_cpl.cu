@@ -42,7 +42,7 @@ struct CplGeom {
   int rem_vp;        // last chunk holds <= 64 channels: they are replicated every rem_vp (32 | 64) lanes, 0 = no
   uint32_t we_bytes, wp_bytes, blob_bytes;
   uint32_t x_buf_bytes, a2_buf_bytes;
-  uint32_t off_X, off_A2, off_W, off_bars, smem_bytes;
+  uint32_t off_X, off_A2, off_W, off_bars, off_bias, smem_bytes;
   uint32_t tmem_cols;
   long long* dbg;    // HFB_CPL_DBG=<layer>: clock stamps of CTA 0, [role 0..4][chunk or tile 0..63][8]
 };
@@ -163,7 +163,8 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
 
   if (tid == 0) {
     for (int i = 0; i < 44; ++i)
-      tc::mbar_init(&bars[i], (i >= 4 && i < 8) ? CPL_NT / 32 : (i >= 8 && i < 10) ? 4 : (i >= 20 && i < 28) ? 32 : 1);
+      tc::mbar_init(&bars[i], (i >= 4 && i < 8) ? CPL_NT / 32 : (i >= 8 && i < 10) ? 4 : (i >= 20 && i < 28) ? 32 :
+                                  (i >= 28 && i < 36 && g.residual) ? 5 : 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmX);
   }
@@ -339,9 +340,17 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
     // =========================================================================================== epilogue warps
     const int lg = warp - 20;
     const uint32_t tm_lane = (uint32_t)(lg * 32) << 16;
-    tc::pdl_wait();   // residual reads / output writes order after the predecessor
+    // the project bias goes to shared memory once (it does not depend on the predecessor kernel); named barrier 1 is
+    // private to the four epilogue warps
+    float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);
+    for (int i = tid - 20 * 32; i < g.cout_pad; i += 128) s_bias[i] = i < g.Cout ? __ldg(bp + i) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    tc::pdl_wait();   // output writes order after the predecessor
     TilePos ep = pos0;
     const int p = lg * 32 + lane;
+    // residual: the block input at the output pixel is row (y + 1) * IW + x + 1 of the halo tile that is still in shared
+    // memory (stride 1, SAME: pad 1), so it is read from there; the tile's ring slot is released after the last read
+    const int rr = (p / TW + 1) * IW + (p % TW) + 1;
     for (int t = 0; t < my_tiles; ++t) {
       const int b2 = t % ND2;
       if (warp == 20) { CPL_STAMP(4, t, 0); }
@@ -353,6 +362,8 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
         const bool valid = p < NPIX && oy < g.Ho && ox < g.Wo;
         const long long opix = ((long long)ep.img * g.Ho + oy) * g.Wo + ox;
         const uint32_t taddr = tmem_d2 + tm_lane + (uint32_t)(b2 * g.cout_pad);
+        const uint32_t xrow = tc::smem_u32(sX) + (uint32_t)(t % NX) * g.x_buf_bytes +
+                              (g.xrb == 128 ? (uint32_t)rr * 128u : (uint32_t)rr * 64u);
         for (int cc = 0; cc < g.cout_pad; cc += 16) {
           uint32_t v[16];
           tc::tmem_ld16(taddr + (uint32_t)cc, v);
@@ -362,12 +373,16 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
           for (int h = 0; h < 2; ++h) {
             const int n = cc + 8 * h;
             if (n >= g.Cout) break;
-            const float4 bb0 = __ldg(reinterpret_cast<const float4*>(bp + n)), bb1 = __ldg(reinterpret_cast<const float4*>(bp + n) + 1);
+            const float4 bb0 = *reinterpret_cast<const float4*>(s_bias + n), bb1 = *reinterpret_cast<const float4*>(s_bias + n + 4);
             float f[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] += __uint_as_float(v[8 * h + i]);
             if (g.residual) {
-              const uint4 rq = *reinterpret_cast<const uint4*>(in + opix * g.Cin + n);
+              const int u = n >> 3;
+              const uint32_t xa = g.xrb == 128 ? xrow + (uint32_t)(u >> 3) * (uint32_t)(RP * 128) + (uint32_t)(((u & 7) ^ (rr & 7)) << 4)
+                                               : xrow + (uint32_t)((u ^ ((rr >> 1) & 3)) << 4);
+              uint4 rq;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rq.x), "=r"(rq.y), "=r"(rq.z), "=r"(rq.w) : "r"(xa));
               const __half2* hq = reinterpret_cast<const __half2*>(&rq);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -386,7 +401,10 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bar_d2[b2]);
+      if (lane == 0) {
+        tc::mbar_arrive(&bar_d2[b2]);
+        if (g.residual) tc::mbar_arrive(&bar_xf[t % NX]);   // the input tile has been read for the last time
+      }
       if (warp == 20) { CPL_STAMP(4, t, 2); }
       advance(ep);
     }
@@ -627,6 +645,7 @@ static bool cpl_layout(CplGeom& g, int S, int TH, int NS, int NX) {
   g.off_A2 = off; off += 2 * g.a2_buf_bytes;
   g.off_W = off;  off += al((uint32_t)NS * g.blob_bytes);
   g.off_bars = off; off += 512;
+  g.off_bias = off; off += 1024;   // project bias, fp32 [cout_pad <= 256]
   g.smem_bytes = off + 1024;
   g.ND2 = 2 * RP + 2 * g.cout_pad <= 512 ? 2 : 1;
   uint32_t cols = 32;

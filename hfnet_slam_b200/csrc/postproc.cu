@@ -315,9 +315,9 @@ __global__ void __launch_bounds__(1024) select_topk_kernel(const u64* __restrict
 // One warp per keypoint: warp the coordinates to the descriptor grid, bilinear-sample 256 channels with the
 // reference's expression order (BaseModel.cc:540-550; every product / sum individually rounded, no FMA contraction),
 // then cv::normalize(NORM_L2): norm accumulated in double, scale rounded to fp32, fp32 multiply.
-__global__ void sample_kernel(const u64* __restrict__ sel, const int* __restrict__ n_sel, int sel_stride,
-                              const float* __restrict__ descmap, int H, int W, int Hd, int Wd, float level_scale,
-                              int level, const int* __restrict__ kcount_prev, int kp_cap, float* __restrict__ ox,
+__global__ void sample_kernel(const u64* __restrict__ sel, const int* __restrict__ n_sel_levels, int nsel_stride,
+                              int sel_stride, const float* __restrict__ descmap, int H, int W, int Hd, int Wd,
+                              float level_scale, int level, int kp_cap, float* __restrict__ ox,
                               float* __restrict__ oy, float* __restrict__ oresp, int* __restrict__ ooct,
                               float* __restrict__ odesc, int* __restrict__ kcount_out) {
   pdl_launch_dependents();
@@ -325,9 +325,9 @@ __global__ void sample_kernel(const u64* __restrict__ sel, const int* __restrict
   const int b = blockIdx.y;
   const int kp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const int n = n_sel[b];
-  int base = 0;
-  for (int l = 0; l < level; ++l) base += kcount_prev[b * HFB_MAX_LEVELS + l];
+  const int n = n_sel_levels[level * nsel_stride + b];
+  int base = 0;   // rows of the levels below (HFextractor.cc:259-283 concatenates the levels in order)
+  for (int l = 0; l < level; ++l) base += n_sel_levels[l * nsel_stride + b];
   if (kp == 0 && lane == 0) kcount_out[b * HFB_MAX_LEVELS + level] = n;
   if (kp >= n) return;
   const u64 key = sel[(size_t)b * sel_stride + kp];
@@ -391,11 +391,9 @@ __global__ void sample_kernel(const u64* __restrict__ sel, const int* __restrict
   }
 }
 
-int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const float* d_descmap, int Hd, int Wd,
-                         u64* d_cand, int* d_cand_count, int cand_cap, u64* d_sel, int* d_nsel, int n_keypoints,
-                         float threshold, float level_scale, int level, int B, int kp_cap, float* d_x, float* d_y,
-                         float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow,
-                         bool candidates_ready) {
+int launch_select(hfb_ctx* ctx, const float* d_nms, int H, int W, u64* d_cand, int* d_cand_count, int cand_cap,
+                  u64* d_sel, int* d_nsel, int n_keypoints, float threshold, int B, int* d_overflow,
+                  bool candidates_ready) {
   HFB_REQUIRE(ctx, n_keypoints >= 0 && n_keypoints <= SELECT_KMAX, "keypoint budget exceeds SELECT_KMAX (8192)");
   if (!candidates_ready) {   // the in-graph NMS kernel already scanned its own output otherwise
     HFB_CUDA(ctx, cudaMemsetAsync(d_cand_count, 0, sizeof(int) * B, ctx->stream));
@@ -411,19 +409,30 @@ int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const f
   hfb_launch(ctx, select_topk_kernel, B, 1024, smem, d_cand, d_cand_count, cand_cap, n_keypoints, d_sel, d_nsel,
                                                      SELECT_KMAX, d_overflow);
   HFB_CHECK_LAUNCH(ctx, "select_topk");
-  if (n_keypoints > 0) {
-    dim3 g2(ceil_div(n_keypoints, 8), B);
-    hfb_launch(ctx, sample_kernel, g2, 256, 0, d_sel, d_nsel, SELECT_KMAX, d_descmap, H, W, Hd, Wd, level_scale, level,
-                                               d_kcount, kp_cap, d_x, d_y, d_resp, d_oct, d_desc, d_kcount);
-    HFB_CHECK_LAUNCH(ctx, "sample");
-  } else {
-    // budget 0: still publish the count
-    dim3 g2(1, B);
-    hfb_launch(ctx, sample_kernel, g2, 32, 0, d_sel, d_nsel, SELECT_KMAX, d_descmap, H, W, Hd, Wd, level_scale, level,
-                                              d_kcount, kp_cap, d_x, d_y, d_resp, d_oct, d_desc, d_kcount);
-    HFB_CHECK_LAUNCH(ctx, "sample");
-  }
   return HFB_OK;
+}
+
+int launch_sample(hfb_ctx* ctx, int H, int W, const float* d_descmap, int Hd, int Wd, const u64* d_sel,
+                  const int* d_nsel_levels, int nsel_stride, int n_keypoints, float level_scale, int level, int B,
+                  int kp_cap, float* d_x, float* d_y, float* d_resp, int* d_oct, float* d_desc, int* d_kcount) {
+  // budget 0: one warp per frame still publishes the count
+  dim3 g2(n_keypoints > 0 ? ceil_div(n_keypoints, 8) : 1, B);
+  hfb_launch(ctx, sample_kernel, g2, n_keypoints > 0 ? 256 : 32, 0, d_sel, d_nsel_levels, nsel_stride, SELECT_KMAX,
+             d_descmap, H, W, Hd, Wd, level_scale, level, kp_cap, d_x, d_y, d_resp, d_oct, d_desc, d_kcount);
+  HFB_CHECK_LAUNCH(ctx, "sample");
+  return HFB_OK;
+}
+
+// single-level form (level 0 of its own selection arrays)
+int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const float* d_descmap, int Hd, int Wd,
+                         u64* d_cand, int* d_cand_count, int cand_cap, u64* d_sel, int* d_nsel, int n_keypoints,
+                         float threshold, float level_scale, int B, int kp_cap, float* d_x, float* d_y,
+                         float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow,
+                         bool candidates_ready) {
+  HFB_TRY(launch_select(ctx, d_nms, H, W, d_cand, d_cand_count, cand_cap, d_sel, d_nsel, n_keypoints, threshold, B,
+                        d_overflow, candidates_ready));
+  return launch_sample(ctx, H, W, d_descmap, Hd, Wd, d_sel, d_nsel, 0, n_keypoints, level_scale, 0, B, kp_cap, d_x, d_y,
+                       d_resp, d_oct, d_desc, d_kcount);
 }
 
 // =============================================================================================== pyramid
