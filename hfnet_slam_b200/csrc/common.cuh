@@ -98,7 +98,8 @@ struct NetW {
   GemmW desc2;      // 256 -> 256
   GemmW det2;       // 128 -> 65
   const float *vlad_w = nullptr, *vlad_b = nullptr, *vlad_c = nullptr;  // [c_global][C], [C], [C][c_global]
-  const __half* fc_w = nullptr;                                          // [c_global*C][4096] fp16
+  const __half* vlad_wt = nullptr;   // [2][C][c_global + 8]: vlad_w transposed, fp16 high part | fp16 residual (global_head.cu)
+  const __half* fc_w = nullptr;   // [c_global*C][4096] fp16 in mma B-fragment order (fc_pack_host, global_head.cu)
   const float* fc_b = nullptr;
 };
 
@@ -119,7 +120,11 @@ struct LevelPlan {
   float *d_scores = nullptr, *d_nms = nullptr;  // [H8][W8]
   u64* d_cand = nullptr;      // [max_batch][cand_cap] threshold-scan survivors
   int* d_cand_count = nullptr;
-  float *d_memb = nullptr, *d_vlad = nullptr, *d_vladn = nullptr, *d_fc_partial = nullptr;
+  // global head (global_head.cu): per-group NetVLAD partial sums, normalised VLAD (fp32 + the FC's packed fp16 hi/lo
+  // operand), per-tile sums of squares of the FC output, self-resetting completion counters [max_batch + 1]
+  float *d_vlad_part = nullptr, *d_vladn = nullptr, *d_fc_ss = nullptr;
+  uint32_t* d_fc_a = nullptr;
+  int* d_gh_counters = nullptr;
   int *d_xi = nullptr, *d_yi = nullptr;      // resize tables (from previous level)
   short *d_xa = nullptr, *d_ya = nullptr;
 };
@@ -307,6 +312,11 @@ int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const f
 int launch_resize(hfb_ctx* ctx, const uint8_t* d_src, int sh, int sw, uint8_t* d_dst, int dh, int dw, const int* d_xi,
                   const short* d_xa, const int* d_yi, const short* d_ya, int B);
 void build_resize_tables(int sn, int dn, std::vector<int>& idx, std::vector<short>& coef);
+// global_head.cu
+void fc_pack_host(const float* fw, int K, int N, __half* out);
+int global_head_groups(int P);
+int global_head_run(hfb_ctx* ctx, const __half* x, int P, int D, int B, float* d_part, int* d_counters, float* d_vladn,
+                    uint32_t* d_apacked, float* d_ss_part, float* d_out);
 // encoder.cu
 int encoder_plan(hfb_ctx* ctx);
 void encoder_forget(hfb_ctx* ctx);

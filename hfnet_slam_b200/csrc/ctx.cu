@@ -419,10 +419,23 @@ extern "C" int hfb_load_weights(hfb_ctx* ctx, const void* blob, size_t nbytes) {
     TAKE(fw, (size_t)D * C * HFB_GLOBAL_DIM);
     TAKE(fb, (size_t)HFB_GLOBAL_DIM);
     fix((const void**)&net.vlad_w, ab.add(mw, (size_t)D * C * 4));
+    {
+      const int DP = D + 8;
+      std::vector<__half> wt((size_t)2 * C * DP, h_f2h(0.f));
+      for (int d = 0; d < D; ++d)
+        for (int c = 0; c < C; ++c) {
+          const float v = mw[(size_t)d * C + c];
+          const __half hi = h_f2h(v);
+          wt[(size_t)c * DP + d] = hi;
+          wt[(size_t)(C + c) * DP + d] = h_f2h(v - __half2float(hi));
+        }
+      fix((const void**)&net.vlad_wt, ab.add(wt.data(), wt.size() * 2));
+    }
     fix((const void**)&net.vlad_b, ab.add(mb, (size_t)C * 4));
     fix((const void**)&net.vlad_c, ab.add(cl, (size_t)C * D * 4));
+    HFB_REQUIRE(ctx, (D * C) % 16 == 0, "clusters x global channels must be a multiple of 16");
     std::vector<__half> t((size_t)D * C * HFB_GLOBAL_DIM);
-    for (size_t i = 0; i < t.size(); ++i) t[i] = h_f2h(fw[i]);
+    fc_pack_host(fw, D * C, HFB_GLOBAL_DIM, t.data());
     fix((const void**)&net.fc_w, ab.add(t.data(), t.size() * 2));
     fix((const void**)&net.fc_b, ab.add(fb, (size_t)HFB_GLOBAL_DIM * 4));
   }

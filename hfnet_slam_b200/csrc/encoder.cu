@@ -207,237 +207,6 @@ __global__ void __launch_bounds__(128) dw_project_small_kernel(const __half* __r
   }
 }
 
-// ----------------------------------------------------------------------------------------------- NetVLAD
-// (1) memberships: 1x1 conv D -> C + folded BN, softmax over clusters (layers.py:66-71).  One CTA = 32 pixels staged in
-//     shared memory; warp = 4 pixels, lane = cluster (C <= 64: two passes of 32).
-#define VLAD_PIX 32
-__global__ void __launch_bounds__(256) vlad_memberships_kernel(const __half* __restrict__ x, int P, int D, int C,
-                                                               const float* __restrict__ w,
-                                                               const float* __restrict__ bias,
-                                                               float* __restrict__ memb) {
-  extern __shared__ __half s_x[];   // [VLAD_PIX][D]
-  pdl_launch_dependents();
-  pdl_wait();
-  const int b = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pix0 = blockIdx.x * VLAD_PIX;
-  const int npix = min(VLAD_PIX, P - pix0);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * P + pix0) * D);
-    uint4* dst = reinterpret_cast<uint4*>(s_x);
-    const int n16 = npix * D / 8;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
-  __syncthreads();
-  const int p0 = warp * 4;
-  if (p0 >= npix) return;
-  float logit[2][4];
-  for (int cb = 0; cb < C; cb += 32) {
-    const int c = cb + lane;
-    float acc[4];
-    const float bb = c < C ? __ldg(bias + c) : 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = bb;
-    const __half* xp = s_x + (size_t)p0 * D;
-#pragma unroll 4
-    for (int d = 0; d < D; d += 2) {
-      const float w0 = c < C ? __ldg(w + (size_t)d * C + c) : 0.f;
-      const float w1 = c < C ? __ldg(w + (size_t)(d + 1) * C + c) : 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (p0 + q < npix) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(xp + (size_t)q * D + d));
-          acc[q] = fmaf(f.x, w0, acc[q]);
-          acc[q] = fmaf(f.y, w1, acc[q]);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) logit[cb >> 5][q] = c < C ? acc[q] : -INFINITY;
-  }
-  // softmax over the C logits of each pixel (each lane holds up to 2)
-  for (int q = 0; q < 4; ++q) {
-    if (p0 + q >= npix) break;
-    float v0 = logit[0][q], v1 = C > 32 ? logit[1][q] : -INFINITY;
-    float mx = fmaxf(v0, v1);
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-    v0 = lane < C ? expf(v0 - mx) : 0.f;
-    v1 = lane + 32 < C ? expf(v1 - mx) : 0.f;
-    float sum = v0 + v1;
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-    const float inv = 1.f / sum;
-    float* m = memb + ((size_t)b * P + pix0 + p0 + q) * C;
-    if (lane < C) m[lane] = v0 * inv;
-    if (lane + 32 < C) m[lane + 32] = v1 * inv;
-  }
-}
-
-// (2) V[c][d] = (sum_p m[p][c]) * centroid[c][d] - sum_p m[p][c] * x[p][d]   (layers.py:81-86: clusters - x)
-//     One CTA per (cluster, frame); the cluster's membership column is staged in shared memory.
-__global__ void __launch_bounds__(256) vlad_aggregate_kernel(const __half* __restrict__ x, const float* __restrict__ memb,
-                                                             int P, int D, int C, const float* __restrict__ clusters,
-                                                             float* __restrict__ vlad) {
-  extern __shared__ float s_m[];   // [P]
-  pdl_launch_dependents();
-  pdl_wait();
-  const int c = blockIdx.x, b = blockIdx.y;
-  const float* m = memb + (size_t)b * P * C + c;
-  for (int p = threadIdx.x; p < P; p += blockDim.x) s_m[p] = __ldg(m + (size_t)p * C);
-  __syncthreads();
-  const __half* xb = x + (size_t)b * P * D;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float acc = 0.f, msum = 0.f;
-    int p = 0;
-    for (; p + 8 <= P; p += 8) {
-      float xv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) xv[u] = __half2float(xb[(size_t)(p + u) * D + d]);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        msum += s_m[p + u];
-        acc = fmaf(s_m[p + u], xv[u], acc);
-      }
-    }
-    for (; p < P; ++p) {
-      msum += s_m[p];
-      acc = fmaf(s_m[p], __half2float(xb[(size_t)p * D + d]), acc);
-    }
-    vlad[((size_t)b * C + c) * D + d] = msum * __ldg(clusters + (size_t)c * D + d) - acc;
-  }
-}
-
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-  __syncthreads();
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-  for (int i = 0; i < nw; ++i) t += red[i];
-  return t;
-}
-
-// (3) intra-normalisation over the CLUSTER axis (layers.py:87-88, restated literally), flatten [C*D], L2-normalise
-//     (layers.py:89-90) and the L2-normalise at the top of the dimensionality reduction (layers.py:97).
-__global__ void vlad_normalize_kernel(const float* __restrict__ vlad, int C, int D, float* __restrict__ out) {
-  __shared__ float red[32];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int b = blockIdx.x;
-  const float* v = vlad + (size_t)b * C * D;
-  float* o = out + (size_t)b * C * D;
-  float ss = 0.f;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s = fmaf(v[(size_t)c * D + d], v[(size_t)c * D + d], s);
-    const float inv = rsqrtf(fmaxf(s, 1e-12f));
-    for (int c = 0; c < C; ++c) {
-      const float t = v[(size_t)c * D + d] * inv;
-      o[(size_t)c * D + d] = t;
-      ss = fmaf(t, t, ss);
-    }
-  }
-  float tot = block_sum(ss, red);
-  const float inv1 = rsqrtf(fmaxf(tot, 1e-12f));
-  float ss2 = 0.f;
-  for (int i = threadIdx.x; i < C * D; i += blockDim.x) {
-    const float t = o[i] * inv1;
-    o[i] = t;
-    ss2 = fmaf(t, t, ss2);
-  }
-  tot = block_sum(ss2, red);
-  const float inv2 = rsqrtf(fmaxf(tot, 1e-12f));
-  for (int i = threadIdx.x; i < C * D; i += blockDim.x) o[i] *= inv2;
-}
-
-// (4) FC K -> 4096 (layers.py:99-107): split-K GEMV over the fp16 weight [K][4096]; each thread owns 8 columns.
-#define FC_BCH 8
-__global__ void __launch_bounds__(256) fc_partial_kernel(const float* __restrict__ v, int K, int B,
-                                                         const __half* __restrict__ w, int N, int k_per_split,
-                                                         float* __restrict__ partial) {
-  extern __shared__ float s_v[];  // [FC_BCH][k_per_split]
-  pdl_launch_dependents();
-  pdl_wait();
-  const int ks = blockIdx.y;
-  const int k0 = ks * k_per_split;
-  const int kn = min(k_per_split, K - k0);
-  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  for (int b0 = 0; b0 < B; b0 += FC_BCH) {
-    const int nb = min(FC_BCH, B - b0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < FC_BCH * k_per_split; i += blockDim.x) {
-      const int bb = i / k_per_split, kk = i - bb * k_per_split;
-      s_v[i] = (bb < nb && kk < kn) ? v[(size_t)(b0 + bb) * K + k0 + kk] : 0.f;
-    }
-    __syncthreads();
-    if (n < N && kn > 0) {
-      float acc[FC_BCH][8];
-#pragma unroll
-      for (int bb = 0; bb < FC_BCH; ++bb)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[bb][j] = 0.f;
-      const __half* wp = w + (size_t)k0 * N + n;
-#pragma unroll 8
-      for (int kk = 0; kk < kn; ++kk) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)kk * N));
-        const __half2* hq = reinterpret_cast<const __half2*>(&q);
-        float wf[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(hq[j]);
-          wf[2 * j] = f.x;
-          wf[2 * j + 1] = f.y;
-        }
-#pragma unroll
-        for (int bb = 0; bb < FC_BCH; ++bb) {
-          const float xv = s_v[bb * k_per_split + kk];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[bb][j] = fmaf(xv, wf[j], acc[bb][j]);
-        }
-      }
-      for (int bb = 0; bb < nb; ++bb) {
-        float* o = partial + ((size_t)(b0 + bb) * gridDim.y + ks) * N + n;
-        *reinterpret_cast<float4*>(o) = make_float4(acc[bb][0], acc[bb][1], acc[bb][2], acc[bb][3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[bb][4], acc[bb][5], acc[bb][6], acc[bb][7]);
-      }
-    }
-  }
-}
-
-// y = sum of the split-K partials + bias; per-CTA sum of squares.  grid (N/256, B), fixed summation order.
-__global__ void __launch_bounds__(256) fc_finish_kernel(const float* __restrict__ partial, int n_split, int N,
-                                                        const float* __restrict__ bias, float* __restrict__ out,
-                                                        float* __restrict__ ss_part) {
-  __shared__ float red[32];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
-  float y = 0.f;
-  if (n < N) {
-    y = __ldg(bias + n);
-    const float* p = partial + (size_t)b * n_split * N + n;
-    for (int s = 0; s < n_split; ++s) y += p[(size_t)s * N];
-    out[(size_t)b * N + n] = y;
-  }
-  const float tot = block_sum(y * y, red);
-  if (threadIdx.x == 0) ss_part[b * gridDim.x + blockIdx.x] = tot;
-}
-
-// final tf.nn.l2_normalize of the 4096-d global descriptor (layers.py:108)
-__global__ void fc_norm_kernel(float* __restrict__ out, int N, const float* __restrict__ ss_part, int n_part) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int b = blockIdx.y;
-  float tot = 0.f;
-  for (int i = 0; i < n_part; ++i) tot += ss_part[b * n_part + i];
-  const float inv = rsqrtf(fmaxf(tot, 1e-12f));
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < N) out[(size_t)b * N + n] *= inv;
-}
-
 // =============================================================================================== plans
 // N tile: split N into the fewest equal tiles (multiples of 16, <= 256) that still give the machine enough CTAs.
 static int pick_bn(int M, int N, int n_sm) {
@@ -487,7 +256,6 @@ struct LevelExec {
   GemmPlan head1, desc2, det2;
   int Hd, Wd;  // descriptor grid = layer_7 size
   int P, D;    // global endpoint pixels / channels
-  int fc_split, fc_kps;
 };
 
 // Per-context execution plans.  The table is shared by every context of the process and contexts live on different host
@@ -612,13 +380,13 @@ int encoder_plan(hfb_ctx* ctx) {
       le.P = lv.aH[18] * lv.aW[18];
       le.D = lv.aC[18];
       const int C = net.n_clusters, K = C * le.D;
-      HFB_TRY(ctx->dalloc(&lv.d_memb, (size_t)Bm * le.P * C));
-      HFB_TRY(ctx->dalloc(&lv.d_vlad, (size_t)Bm * K));
+      HFB_TRY(ctx->dalloc(&lv.d_vlad_part, (size_t)Bm * global_head_groups(le.P) * (K + C)));
       HFB_TRY(ctx->dalloc(&lv.d_vladn, (size_t)Bm * K));
-      le.fc_split = std::max(1, ctx->n_sm);
-      le.fc_kps = (K + le.fc_split - 1) / le.fc_split;
-      le.fc_split = (K + le.fc_kps - 1) / le.fc_kps;
-      HFB_TRY(ctx->dalloc(&lv.d_fc_partial, (size_t)Bm * le.fc_split * HFB_GLOBAL_DIM + (size_t)Bm * 64));
+      HFB_TRY(ctx->dalloc(&lv.d_fc_a, (size_t)((Bm + 7) / 8) * (K / 16) * 32 * 4));
+      HFB_TRY(ctx->dalloc(&lv.d_fc_ss, (size_t)Bm * (HFB_GLOBAL_DIM / 32)));
+      HFB_TRY(ctx->dalloc(&lv.d_gh_counters, (size_t)Bm + 1));
+      HFB_CUDA(ctx, cudaMemset(lv.d_gh_counters, 0, ((size_t)Bm + 1) * sizeof(int)));
+      HFB_CUDA(ctx, cudaMemset(lv.d_fc_a, 0, (size_t)((Bm + 7) / 8) * (K / 16) * 32 * 16));
     }
   }
   return HFB_OK;
@@ -631,34 +399,10 @@ static int run_plain(hfb_ctx* ctx, const GemmPlan& gp, long long M, void* out, i
   return gemm_store(ctx, gp.tmA, gp.tmB, g, 1, out, ldo, 0, bias, residual, ldr, relu6, 0);
 }
 
-// NetVLAD + dimensionality reduction (layers.py:57-109) on layer_18.
+// NetVLAD + dimensionality reduction (layers.py:57-109) on layer_18 (global_head.cu).
 static int global_head(hfb_ctx* ctx, LevelPlan& lv, LevelExec& le, int B) {
-  const NetW& net = ctx->net;
-  const int C = net.n_clusters, K = C * le.D;
-  dim3 g1(ceil_div(le.P, VLAD_PIX), B);
-  hfb_launch(ctx, vlad_memberships_kernel, g1, 256, (size_t)VLAD_PIX * le.D * 2, lv.act[18], le.P, le.D, C, net.vlad_w,
-                                                                               net.vlad_b, lv.d_memb);
-  HFB_CHECK_LAUNCH(ctx, "vlad_memberships");
-  dim3 g2(C, B);
-  hfb_launch(ctx, vlad_aggregate_kernel, g2, 256, (size_t)le.P * 4, lv.act[18], lv.d_memb, le.P, le.D, C, net.vlad_c,
-                                                                   lv.d_vlad);
-  HFB_CHECK_LAUNCH(ctx, "vlad_aggregate");
-  hfb_launch(ctx, vlad_normalize_kernel, B, 256, 0, lv.d_vlad, C, le.D, lv.d_vladn);
-  HFB_CHECK_LAUNCH(ctx, "vlad_normalize");
-  dim3 g3(ceil_div(HFB_GLOBAL_DIM, 256 * 8), le.fc_split);
-  const size_t smem = (size_t)FC_BCH * le.fc_kps * sizeof(float);
-  ctx->note("global.fc", 2.0 * K * HFB_GLOBAL_DIM + 4.0 * B * K, 2.0 * B * K * HFB_GLOBAL_DIM);
-  hfb_launch(ctx, fc_partial_kernel, g3, 256, smem, lv.d_vladn, K, B, net.fc_w, HFB_GLOBAL_DIM, le.fc_kps,
-                                                    lv.d_fc_partial);
-  HFB_CHECK_LAUNCH(ctx, "fc_partial");
-  const int n_part = ceil_div(HFB_GLOBAL_DIM, 256);
-  float* ss_part = lv.d_fc_partial + (size_t)ctx->cfg.max_batch * le.fc_split * HFB_GLOBAL_DIM;
-  hfb_launch(ctx, fc_finish_kernel, dim3(n_part, B), 256, 0, lv.d_fc_partial, le.fc_split, HFB_GLOBAL_DIM, net.fc_b,
-                                                             ctx->d_global, ss_part);
-  HFB_CHECK_LAUNCH(ctx, "fc_finish");
-  hfb_launch(ctx, fc_norm_kernel, dim3(n_part, B), 256, 0, ctx->d_global, HFB_GLOBAL_DIM, ss_part, n_part);
-  HFB_CHECK_LAUNCH(ctx, "fc_norm");
-  return HFB_OK;
+  return global_head_run(ctx, lv.act[18], le.P, le.D, B, lv.d_vlad_part, lv.d_gh_counters, lv.d_vladn, lv.d_fc_a,
+                         lv.d_fc_ss, ctx->d_global);
 }
 
 // stem.cu: layer_1 + layer_2 in one kernel
