@@ -38,11 +38,11 @@ struct CplGeom {
   int kb_in;         // k-blocks of 64 channels (1 when xrb == 64)
   int nk16;          // K steps of the expand MMA
   int cout_pad;      // Cout rounded up to 16 (project N)
-  int NS, NX, ND2;   // weight ring slots (== n_chunks: resident), input tile buffers, project accumulators
+  int NSe, NSp, NX, ND2;   // expand / project weight ring slots (== n_chunks: resident), input tile buffers, project accumulators
   int rem_vp;        // last chunk holds <= 64 channels: they are replicated every rem_vp (32 | 64) lanes, 0 = no
   uint32_t we_bytes, wp_bytes, blob_bytes;
   uint32_t x_buf_bytes, a2_buf_bytes;
-  uint32_t off_X, off_A2, off_W, off_bars, off_bias, smem_bytes;
+  uint32_t off_X, off_A2, off_WE, off_WP, off_DW, off_bars, off_bias, smem_bytes;
   uint32_t tmem_cols;
   long long* dbg;    // HFB_CPL_DBG=<layer>: clock stamps of CTA 0, [role 0..4][chunk or tile 0..63][8]
 };
@@ -140,7 +140,9 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sX = smem + g.off_X;     // [NX][kb_in][RP rows][xrb B] swizzled K-major (B operand of expand)
   uint8_t* sA2 = smem + g.off_A2;   // [2][16 k-groups][MG][1024 B] swizzled MN-major (A operand of project)
-  uint8_t* sW = smem + g.off_W;     // [NS] chunk images: WE | WP | depthwise taps + bias
+  uint8_t* sWE = smem + g.off_WE;   // [NSe] expand weight images (freed when the chunk's expand has retired)
+  uint8_t* sWP = smem + g.off_WP;   // [NSp] project weight images (freed when the chunk's project has retired)
+  uint8_t* sDW = smem + g.off_DW;   // [n_chunks] depthwise taps + bias, resident
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bars);
   uint64_t* bar_e = bars;            // [2] expand(c) retired              -> D1[c & 1] full
   uint64_t* bar_p = bars + 2;        // [2] project(c) retired             -> A2[c & 1] and the chunk's weight slot free
@@ -148,32 +150,36 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
   uint64_t* bar_a2 = bars + 6;       // [2] A2[c & 1] written (16 arrivals)
   uint64_t* bar_d2 = bars + 8;       // [2] D2[t % ND2] drained by the epilogue warps (4 arrivals)
   uint64_t* bar_f = bars + 10;       // [2] last project of the tile retired -> D2[t % ND2] full
-  uint64_t* bar_w = bars + 12;       // [8] weight chunk image landed (tx)
+  uint64_t* bar_we = bars + 12;      // [8] expand weight image landed (tx)
   uint64_t* bar_x = bars + 20;       // [8] input tile patched (32 arrivals of warp 19) -> expand may read it
   uint64_t* bar_xf = bars + 28;      // [8] every expand reading the input tile has retired -> buffer free
   uint64_t* bar_t = bars + 36;       // [8] TMA of the input tile landed (tx) -> the loaders patch the ones unit
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
+  uint64_t* bar_wp = bars + 44;      // [8] project weight image landed (tx)
+  uint64_t* bar_dw = bars + 52;      // depthwise taps of every chunk landed (tx)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 53);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_chunks = g.n_chunks, NS = g.NS, NX = g.NX, ND2 = g.ND2;
+  if (g.dbg && blockIdx.x == 0 && tid == 0) g.dbg[(4 * 64 + 63) * 8 + 0] = clock64();   // kernel entry
+  const int n_chunks = g.n_chunks, NSe = g.NSe, NSp = g.NSp, NX = g.NX, ND2 = g.ND2;
   const int my_tiles = (g.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int Ctot = my_tiles * n_chunks;
-  const bool streaming = NS < n_chunks;
+  const bool stream_e = NSe < n_chunks, stream_p = NSp < n_chunks;
   tc::pdl_launch_dependents();
 
-  if (tid == 0) {
-    for (int i = 0; i < 44; ++i)
-      tc::mbar_init(&bars[i], (i >= 4 && i < 8) ? CPL_NT / 32 : (i >= 8 && i < 10) ? 4 : (i >= 20 && i < 28) ? 32 :
-                                  (i >= 28 && i < 36 && g.residual) ? 5 : 1);
+  if (tid < 53) {   // one barrier per thread: a single thread initialising all of them costs ~100 cycles apiece
+    const int i = tid;
+    tc::mbar_init(&bars[i], (i >= 4 && i < 8) ? CPL_NT / 32 : (i >= 8 && i < 10) ? 4 : (i >= 20 && i < 28) ? 32 :
+                                (i >= 28 && i < 36 && g.residual) ? 5 : 1);
     tc::fence_barrier_init();
-    tc::prefetch_tmap(&tmX);
   }
+  if (tid == 64) tc::prefetch_tmap(&tmX);
   if (warp == 16) tc::tmem_alloc(tmem_slot, g.tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base + 2u * RP;   // D2[b] at + b * cout_pad
+  if (g.dbg && blockIdx.x == 0 && tid == 0) g.dbg[(4 * 64 + 63) * 8 + 1] = clock64();   // prologue done
 
   // Tile cursors advance by gridDim.x tiles without divisions: (tx, ty, img) += (dx, dy, dimg) with carries.
   struct TilePos { int tx, ty, img; };
@@ -208,13 +214,17 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
     // =========================================================================================== expand issuer
     if (lane == 0) {
       const uint32_t idesc_e = tc::make_idesc_f16(RP);
-      const uint64_t desc_w0 = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(sW)) : tc::make_sdesc_sw64(tc::smem_u32(sW));
+      auto load_we = [&](int slot, int chunk) {   // weights do not depend on the predecessor kernel
+        tc::mbar_expect_tx(&bar_we[slot], g.we_bytes);
+        bulk_load(sWE + (size_t)slot * g.we_bytes, wblob + (size_t)chunk * g.blob_bytes, g.we_bytes, &bar_we[slot]);
+      };
+      const uint64_t desc_w0 = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(sWE)) : tc::make_sdesc_sw64(tc::smem_u32(sWE));
       const uint64_t desc_x0 = g.xrb == 128 ? tc::make_sdesc_sw128(tc::smem_u32(sX)) : tc::make_sdesc_sw64(tc::smem_u32(sX));
       int t = 0, j = 0;
       for (int c = 0; c < Ctot; ++c) {
-        const int slot = streaming ? c % NS : j;
+        const int slot = stream_e ? c % NSe : j;
         CPL_STAMP(1, c, 0);
-        if (streaming || c < n_chunks) tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
+        if (stream_e || c < n_chunks) tc::mbar_wait(&bar_we[slot], stream_e ? (uint32_t)((c / NSe) & 1) : 0u);
         CPL_STAMP(1, c, 1);
         if (j == 0) tc::mbar_wait(&bar_x[t % NX], (uint32_t)((t / NX) & 1));
         CPL_STAMP(1, c, 2);
@@ -223,7 +233,7 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
         tc::fence_after_sync();
         // descriptors: start-address field += bytes >> 4 (k-blocks of 64 channels are 128 rows x 128 B (weights) and
         // RP rows x 128 B (input tile) apart; a K step of 16 is 32 bytes inside the swizzled row)
-        const uint64_t da = desc_w0 + (uint64_t)((slot * g.blob_bytes) >> 4);
+        const uint64_t da = desc_w0 + (uint64_t)((slot * g.we_bytes) >> 4);
         const uint64_t db = desc_x0 + (uint64_t)(((t % NX) * g.x_buf_bytes) >> 4);
         const uint32_t d1 = tmem_base + (uint32_t)((c & 1) * RP);
         for (int k16 = 0; k16 < g.nk16; ++k16) {
@@ -234,39 +244,60 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
         tc::umma_commit(&bar_e[c & 1]);
         if (j == n_chunks - 1) tc::umma_commit(&bar_xf[t % NX]);   // the tile's input buffer may be refilled
         CPL_STAMP(1, c, 4);
+        // the expand image of chunk c-1 is dead once that expand has retired (it has by now: the tensor pipe runs in
+        // order and expand(c) sits behind it): its slot takes the image NSe chunks ahead -- long before the project of
+        // chunk c-1 retires, which is what used to release the whole chunk blob
+        if (stream_e && c >= 1 && c - 1 + NSe < Ctot) {
+          const int k = c - 1;
+          tc::mbar_wait(&bar_e[k & 1], (uint32_t)((k >> 1) & 1));
+          load_we(k % NSe, (k + NSe) % n_chunks);
+        }
         if (++j == n_chunks) { j = 0; ++t; }
       }
     }
   } else if (warp == 17) {
     // =========================================================================================== project issuer
     if (lane == 0) {
-      const int pre = streaming ? min(NS, Ctot) : n_chunks;
-      for (int c = 0; c < pre; ++c) {   // weights do not depend on the predecessor kernel
-        tc::mbar_expect_tx(&bar_w[c], g.blob_bytes);
-        bulk_load(sW + (size_t)c * g.blob_bytes, wblob + (size_t)(c % n_chunks) * g.blob_bytes, g.blob_bytes, &bar_w[c]);
+      auto load_wp = [&](int slot, int chunk) {
+        tc::mbar_expect_tx(&bar_wp[slot], g.wp_bytes);
+        bulk_load(sWP + (size_t)slot * g.wp_bytes, wblob + (size_t)chunk * g.blob_bytes + g.we_bytes, g.wp_bytes, &bar_wp[slot]);
+      };
+      // initial fills in the order they are needed (the copy engine serves them in order): expand image of chunk 0, the
+      // depthwise taps, project image of chunk 0, then the following chunks; refills: WE by the expand issuer, WP here
+      const int pre_e = stream_e ? min(NSe, Ctot) : n_chunks, pre_p = stream_p ? min(NSp, Ctot) : n_chunks;
+      for (int c = 0; c < max(pre_e, pre_p); ++c) {
+        if (c < pre_e) {
+          tc::mbar_expect_tx(&bar_we[c], g.we_bytes);
+          bulk_load(sWE + (size_t)c * g.we_bytes, wblob + (size_t)(c % n_chunks) * g.blob_bytes, g.we_bytes, &bar_we[c]);
+        }
+        if (c == 0) {
+          tc::mbar_expect_tx(bar_dw, (uint32_t)(n_chunks * CPL_DW_BYTES));
+          for (int q = 0; q < n_chunks; ++q)
+            bulk_load(sDW + (size_t)q * CPL_DW_BYTES, wblob + (size_t)q * g.blob_bytes + g.we_bytes + g.wp_bytes, CPL_DW_BYTES, bar_dw);
+        }
+        if (c < pre_p) load_wp(c, c % n_chunks);
       }
       const uint32_t idesc_p = tc::make_idesc_f16(g.cout_pad) | (1u << 15);   // A operand MN-major
       const uint64_t desc_a0 = make_sdesc_mn_sw128(tc::smem_u32(sA2), 1024u, MG * 1024u);
-      const uint64_t desc_p0 = tc::make_sdesc_sw128(tc::smem_u32(sW + g.we_bytes));
+      const uint64_t desc_p0 = tc::make_sdesc_sw128(tc::smem_u32(sWP));
       int t = 0, j = 0;
       for (int c = 0; c < Ctot; ++c) {
-        if (streaming && c >= 1 && c - 1 + NS < Ctot) {   // the slot of chunk c-1 is free once project(c-1) has retired
-          const int k = c - 1, slot = k % NS;
+        if (stream_p && c >= 1 && c - 1 + NSp < Ctot) {   // the slot of chunk c-1 is free once project(c-1) has retired
+          const int k = c - 1;
           tc::mbar_wait(&bar_p[k & 1], (uint32_t)((k >> 1) & 1));
-          tc::mbar_expect_tx(&bar_w[slot], g.blob_bytes);
-          bulk_load(sW + (size_t)slot * g.blob_bytes, wblob + (size_t)((k + NS) % n_chunks) * g.blob_bytes, g.blob_bytes,
-                    &bar_w[slot]);
+          load_wp(k % NSp, (k + NSp) % n_chunks);
         }
         CPL_STAMP(2, c, 0);
         tc::mbar_wait(&bar_a2[c & 1], (uint32_t)((c >> 1) & 1));
         CPL_STAMP(2, c, 1);
         const int b2 = t % ND2;
         if (j == 0 && t >= ND2) tc::mbar_wait(&bar_d2[b2], (uint32_t)(((t / ND2) - 1) & 1));
+        const int slot = stream_p ? c % NSp : j;
+        if (stream_p || c < n_chunks) tc::mbar_wait(&bar_wp[slot], stream_p ? (uint32_t)((c / NSp) & 1) : 0u);
         CPL_STAMP(2, c, 2);
         tc::fence_after_sync();
-        const int slot = streaming ? c % NS : j;
         const uint64_t da = desc_a0 + (uint64_t)(((c & 1) * g.a2_buf_bytes) >> 4);
-        const uint64_t db = desc_p0 + (uint64_t)((slot * g.blob_bytes) >> 4);
+        const uint64_t db = desc_p0 + (uint64_t)((slot * g.wp_bytes) >> 4);
         const int valid = min(128, g.Cexp - j * 128);
         const int nk = (valid + 15) >> 4;
         const uint32_t d2 = tmem_d2 + (uint32_t)(b2 * g.cout_pad);
@@ -413,13 +444,11 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
     const int lg = warp & 3, rg = warp >> 2;
     const uint32_t tm_lane = (uint32_t)(lg * 32) << 16;
     int c = 0;
+    tc::mbar_wait(bar_dw, 0u);   // depthwise taps of every chunk (resident)
     for (int t = 0; t < my_tiles; ++t) {
       for (int j = 0; j < n_chunks; ++j, ++c) {
-        const int slot = streaming ? c % NS : j;
         if (warp == 0) { CPL_STAMP(0, c, 0); }
-        if (streaming || c < n_chunks) tc::mbar_wait(&bar_w[slot], streaming ? (uint32_t)((c / NS) & 1) : 0u);
-        const uint32_t* dwp = reinterpret_cast<const uint32_t*>(sW + (size_t)slot * g.blob_bytes + g.we_bytes + g.wp_bytes) +
-                              lg * 32 + lane;
+        const uint32_t* dwp = reinterpret_cast<const uint32_t*>(sDW + (size_t)j * CPL_DW_BYTES) + lg * 32 + lane;
         uint32_t wv[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) wv[i] = dwp[i * 128];
@@ -549,6 +578,7 @@ fused_block_cpl_kernel(const __grid_constant__ CUtensorMap tmX, const CplGeom g,
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (g.dbg && blockIdx.x == 0 && tid == 0) g.dbg[(4 * 64 + 63) * 8 + 2] = clock64();   // every role done
   if (warp == 16) tc::tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
@@ -629,21 +659,24 @@ int hfb_make_tmap_nhwc_box(hfb_ctx* ctx, CUtensorMap* out, const void* base, int
 CplPlan* cpl_new() { return new CplPlan(); }
 void cpl_delete(CplPlan* p) { delete p; }
 
-static bool cpl_layout(CplGeom& g, int S, int TH, int NS, int NX) {
+static bool cpl_layout(CplGeom& g, int S, int TH, int NSe, int NSp, int NX) {
   const int TW = S == 1 ? 16 : 8;
   const int IW = (TW - 1) * S + 3, IH = (TH - 1) * S + 3;
   const int R = IH * IW, RP = (R + 15) & ~15;
   const int NPIX = TH * TW, MG = NPIX > 64 ? 2 : 1;
   if (RP > 256 || 2 * RP + g.cout_pad > 512) return false;
   auto al = [](uint32_t v) { return (v + 1023u) & ~1023u; };
-  g.NS = NS;
+  g.NSe = NSe;
+  g.NSp = NSp;
   g.NX = NX;
   g.x_buf_bytes = al((uint32_t)(g.kb_in * RP * g.xrb));
   g.a2_buf_bytes = (uint32_t)(16 * MG * 1024);
   uint32_t off = 0;
   g.off_X = off;  off += (uint32_t)NX * g.x_buf_bytes;
   g.off_A2 = off; off += 2 * g.a2_buf_bytes;
-  g.off_W = off;  off += al((uint32_t)NS * g.blob_bytes);
+  g.off_WE = off; off += al((uint32_t)NSe * g.we_bytes);
+  g.off_WP = off; off += al((uint32_t)NSp * g.wp_bytes);
+  g.off_DW = off; off += al((uint32_t)g.n_chunks * CPL_DW_BYTES);
   g.off_bars = off; off += 512;
   g.off_bias = off; off += 1024;   // project bias, fp32 [cout_pad <= 256]
   g.smem_bytes = off + 1024;
@@ -689,7 +722,7 @@ int cpl_plan(hfb_ctx* ctx, CplPlan& cp, const BlockW& bw, const __half* in, int 
   bool ok = false;
   for (int th : {8, 4})
     for (int ns : {g.n_chunks, 2, 1})
-      if (cpl_layout(g, bw.stride, bw.stride == 2 ? 4 : th, std::min(ns, g.n_chunks), 1)) ok = true;
+      if (cpl_layout(g, bw.stride, bw.stride == 2 ? 4 : th, std::min(ns, g.n_chunks), std::min(ns, g.n_chunks), 1)) ok = true;
   if (!ok) return HFB_ERR_CAPACITY;
   {
     const int S = bw.stride, TW = S == 1 ? 16 : 8, IW = (TW - 1) * S + 3;
@@ -722,12 +755,16 @@ static bool cpl_configure(const hfb_ctx* ctx, const CplPlan& cp, int stride, int
     // of cycles per tile), so tiles with few chunks need a deep ring to cover it
     int nx_want = std::min(std::min(per_cta, 8), std::max(2, 6 / g.n_chunks + 1));
     if (cp.pin_nx) nx_want = cp.pin_nx;
-    for (int ns : {g.n_chunks, 4, 3, 2, 1}) {   // resident weights first, then the deepest input ring that fits
-      if (ns > g.n_chunks || ns > 8) continue;
-      if (cp.pin_ns && ns != std::min(cp.pin_ns, g.n_chunks)) continue;
-      if (need_resident && ns < g.n_chunks) continue;
+    // resident weights first, then the deepest weight rings (expand / project) and input ring that fit
+    const int rings[6][2] = {{g.n_chunks, g.n_chunks}, {3, 3}, {3, 2}, {2, 2}, {2, 1}, {1, 1}};
+    for (const auto& r : rings) {
+      const int nse = r[0], nsp = r[1];
+      if (nse > g.n_chunks || nsp > g.n_chunks || nse > 8) continue;
+      if ((nse == g.n_chunks) != (nsp == g.n_chunks)) continue;
+      if (cp.pin_ns && nse != std::min(cp.pin_ns, g.n_chunks)) continue;
+      if (need_resident && nse < g.n_chunks) continue;
       for (int nx = nx_want; nx >= std::min(per_cta, 2); --nx)
-        if (cpl_layout(g, stride, th, ns, nx)) return true;
+        if (cpl_layout(g, stride, th, nse, nsp, nx)) return true;
     }
     return false;
   };
@@ -780,8 +817,8 @@ int cpl_run(hfb_ctx* ctx, const CplPlan& cp, const BlockW& bw, const __half* in,
   static bool traced[32] = {false};
   if (ctx->trace && bw.layer < 32 && !traced[bw.layer]) {
     traced[bw.layer] = true;
-    fprintf(stderr, "hfnet_b200: cpl layer_%d: S=%d TH=%d chunks=%d units=%d xrb=%d NS=%d NX=%d smem=%u tmem=%u tiles=%d\n",
-            bw.layer, bw.stride, TH, g.n_chunks, g.units, g.xrb, g.NS, g.NX, g.smem_bytes, g.tmem_cols, g.total_tiles);
+    fprintf(stderr, "hfnet_b200: cpl layer_%d: S=%d TH=%d chunks=%d units=%d xrb=%d NSe=%d NSp=%d NX=%d smem=%u tmem=%u tiles=%d\n",
+            bw.layer, bw.stride, TH, g.n_chunks, g.units, g.xrb, g.NSe, g.NSp, g.NX, g.smem_bytes, g.tmem_cols, g.total_tiles);
   }
   g.dbg = nullptr;
   static const int dbg_layer = getenv("HFB_CPL_DBG") ? atoi(getenv("HFB_CPL_DBG")) : 0;   // needs HFB_NO_GRAPH=1
@@ -811,6 +848,8 @@ int cpl_run(hfb_ctx* ctx, const CplPlan& cp, const BlockW& bw, const __half* in,
           const long long v = h[(r * 64 + i) * 8 + k];
           if (v && (!t0 || v < t0)) t0 = v;
         }
+    fprintf(stderr, "hfnet_b200: cpl layer_%d CTA 0: entry %lld prologue done %lld exit %lld\n", bw.layer,
+            h[(4 * 64 + 63) * 8 + 0] - t0, h[(4 * 64 + 63) * 8 + 1] - t0, h[(4 * 64 + 63) * 8 + 2] - t0);
     for (int r = 0; r < 5; ++r) {
       fprintf(stderr, "hfnet_b200: cpl layer_%d %s stamps (cycles since first):\n", bw.layer, roles[r]);
       for (int i = 0; i < 14; ++i) {

@@ -7,6 +7,7 @@ falls back to a CPU path: if the library is missing or the device is not a B200 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
@@ -15,7 +16,8 @@ import numpy as np
 HFB_DESC_DIM = 256
 HFB_GLOBAL_DIM = 4096
 HFB_MAX_LEVELS = 8
-LIB_PATH = Path(__file__).resolve().parent / "libhfnet_b200.so"
+# HFB_LIB: A/B experiments against another build of the same library (development only)
+LIB_PATH = Path(os.environ.get("HFB_LIB") or Path(__file__).resolve().parent / "libhfnet_b200.so")
 
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
