@@ -665,8 +665,10 @@ static void h_pose_oplus(const double* pose, const double* u, double* out) {
     for (int i = 0; i < 9; ++i) R[i] = I[i] + Om[i] + Om2[i];
     for (int i = 0; i < 9; ++i) V[i] = R[i];
   } else {
-    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta);
-    const double c = (theta - sin(theta)) / (theta * theta * theta);
+    double sn, cs;
+    sincos(theta, &sn, &cs);   // one argument reduction for both
+    const double a = sn / theta, b = (1 - cs) / (theta * theta);
+    const double c = (theta - sn) / (theta * theta * theta);
     for (int i = 0; i < 9; ++i) {
       R[i] = I[i] + a * Om[i] + b * Om2[i];
       V[i] = I[i] + b * Om[i] + c * Om2[i];
@@ -994,7 +996,7 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
 // EdgeSE3ProjectXYZOnlyPose edges (src/OptimizableTypes.cpp:49-64), Huber kernel dropped after the third round,
 // inlier re-classification with chi2 > 5.991 after every round -- runs on the device without a host round trip.
 // The problem is a few hundred edges: latency, not bandwidth, so everything (6x6 Cholesky, exp map) stays on chip.
-#define PO_THREADS 128
+#define PO_THREADS 256
 #define PO_WARPS (PO_THREADS / 32)
 #define PO_NV 28   // 21 upper-triangular H entries + 6 b entries + 1 robust chi2
 
@@ -1118,36 +1120,57 @@ __device__ void po_pose_oplus(const double* pose, const double* u, double* out) 
   for (int i = 0; i < 4; ++i) out[i] = q[i] / nn;
 }
 
-__device__ bool po_chol6(const double* Hu, double lambda, const double* b, double* x) {   // Hu: 21 upper-tri entries
-  double A[36];
-  int k = 0;
-  for (int i = 0; i < 6; ++i)
-    for (int j = i; j < 6; ++j) {
-      A[6 * i + j] = A[6 * j + i] = Hu[k++];
-    }
+// 6 x 6 Cholesky solve on the one thread everything else waits for: every index is a compile-time constant (the factor
+// lives in registers; a runtime-indexed A[36] sits in local memory) and each column costs one square root and ONE
+// division (the reciprocal of the pivot; the column scaling and both substitutions multiply by it) instead of up to
+// seven dependent fp64 divisions of ~20 instructions each.
+__device__ __forceinline__ bool po_chol6(const double* Hu, double lambda, const double* b, double* x) {   // Hu: 21 upper-tri entries
+  double A[36], inv[6];
+  {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) {
+        A[6 * i + j] = A[6 * j + i] = Hu[k++];
+      }
+  }
+#pragma unroll
   for (int i = 0; i < 6; ++i) A[7 * i] += lambda;
+  bool ok = true;
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     double s = A[7 * j];
+#pragma unroll
     for (int q = 0; q < j; ++q) s -= A[6 * j + q] * A[6 * j + q];
-    if (!(s > 0.0) || !isfinite(s)) return false;
-    const double l = sqrt(s);
-    A[7 * j] = l;
+    if (!(s > 0.0) || !isfinite(s)) ok = false;
+    inv[j] = 1.0 / sqrt(s);
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double t = A[6 * i + j];
+#pragma unroll
       for (int q = 0; q < j; ++q) t -= A[6 * i + q] * A[6 * j + q];
-      A[6 * i + j] = t / l;
+      A[6 * i + j] = t * inv[j];
     }
   }
+  if (!ok) return false;
+  double y[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double t = b[i];
-    for (int q = 0; q < i; ++q) t -= A[6 * i + q] * x[q];
-    x[i] = t / A[7 * i];
+#pragma unroll
+    for (int q = 0; q < i; ++q) t -= A[6 * i + q] * y[q];
+    y[i] = t * inv[i];
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
-    double t = x[i];
-    for (int q = i + 1; q < 6; ++q) t -= A[6 * q + i] * x[q];
-    x[i] = t / A[7 * i];
+    double t = y[i];
+#pragma unroll
+    for (int q = i + 1; q < 6; ++q) t -= A[6 * q + i] * y[q];
+    y[i] = t * inv[i];
   }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = y[i];
   return true;
 }
 
@@ -1155,7 +1178,9 @@ __device__ bool po_chol6(const double* Hu, double lambda, const double* b, doubl
 // edges are staged in shared memory once (they are re-read ~50 times: every LM trial is one pass over them).
 __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const double* __restrict__ in, double delta,
                                                               int edges_in_smem, double* __restrict__ cached_g,
-                                                              unsigned char* __restrict__ outlier_g, double* __restrict__ out) {
+                                                              unsigned char* __restrict__ outlier_g, double* __restrict__ out,
+                                                              int dbg) {
+  long long t_lin = 0, t_red = 0, t_solve = 0, t_trial = 0, t_mark = 0, t_all = clock64();   // HFB_PO_DBG: thread 0's cycles
   extern __shared__ double s_dyn[];   // edges_in_smem: [n*3 | n*2 | n | n cached] doubles + n outlier bytes
   __shared__ double sh[PO_WARPS][32], s_v[32], sh1[PO_WARPS], s_one;
   __shared__ double s_pose[7], s_trial[7], s_x[6];
@@ -1166,7 +1191,9 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
   const double* gO = in + (size_t)3 * n;
   const double* gS = in + (size_t)5 * n;
   const double* gK = in + (size_t)6 * n;
-  const double* pose0 = gK + 4;
+  __shared__ double s_pose0[7];   // the inputs may sit in page-locked host memory: read them once
+  if (threadIdx.x < 7) s_pose0[threadIdx.x] = gK[4 + threadIdx.x];
+  const double* pose0 = s_pose0;
   const double K[4] = {gK[0], gK[1], gK[2], gK[3]};
   const double dsqr = delta * delta;
   const double *Xw = gX, *obs = gO, *invs2 = gS;
@@ -1199,6 +1226,7 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
     __syncthreads();
     for (int it = 0; it < 10; ++it) {
       // ---- computeActiveErrors + buildSystem at s_pose
+      t_mark = clock64();
       double R[9];
       quat_to_R(s_pose, R);
       const double t3[3] = {s_pose[4], s_pose[5], s_pose[6]};
@@ -1228,7 +1256,10 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
           v[21 + i] += J0[i] * r0 + J1[i] * r1;
         }
       }
+      t_lin += clock64() - t_mark;
+      t_mark = clock64();
       po_reduce32(v, sh, s_v);
+      t_red += clock64() - t_mark;
       if (tid == 0) {
         s_cur = s_v[27];
         s_ini = s_v[27];
@@ -1250,6 +1281,7 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
       if (s_v[28] == 0.0) break;
       // ---- Levenberg trials
       while (true) {
+        t_mark = clock64();
         if (tid == 0) {
           double x[6];
           s_ok = po_chol6(s_v, s_lambda, s_v + 21, x) ? 1 : 0;
@@ -1259,6 +1291,8 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
           po_pose_oplus(s_pose, x, s_trial);
         }
         __syncthreads();
+        t_solve += clock64() - t_mark;
+        t_mark = clock64();
         double Rt[9];
         quat_to_R(s_trial, Rt);
         const double tt[3] = {s_trial[4], s_trial[5], s_trial[6]};
@@ -1272,6 +1306,7 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
           c += inl ? chi2 : 2 * sqrt(fmax(chi2, 1e-300)) * delta - dsqr;
         }
         c = po_reduce1(c, sh1, &s_one);
+        t_trial += clock64() - t_mark;
         if (tid == 0) {
           const double temp = s_ok ? c : 1.7976931348623157e308;
           double scale = 1e-3;
@@ -1334,6 +1369,9 @@ __global__ void __launch_bounds__(PO_THREADS) pose_opt_kernel(int n, const doubl
   }
   if (edges_in_smem)
     for (int e = tid; e < n; e += PO_THREADS) outlier_g[e] = outlier[e];
+  if (dbg && tid == 0)
+    printf("pose_opt cycles: total %lld linearize %lld reduce %lld solve+oplus %lld trial %lld (trials %d iters %d)\n",
+           clock64() - t_all, t_lin, t_red, t_solve, t_trial, s_trials, s_iters);
 }
 
 extern "C" int hfb_pose_optimize(hfb_ctx* ctx, const float* K, const double* pose_in, int32_t n, const double* Xw,
@@ -1362,15 +1400,25 @@ extern "C" int hfb_pose_optimize(hfb_ctx* ctx, const float* K, const double* pos
   for (int i = 0; i < 4; ++i) hin[(size_t)6 * n + i] = (double)K[i];
   memcpy(hin + (size_t)6 * n + 4, pose_in, 56);
   cudaStream_t st = ctx->stream;
-  HFB_CUDA(ctx, cudaMemcpyAsync(a + oIn, hin, in_d * 8, cudaMemcpyHostToDevice, st));
   const size_t smem = (size_t)7 * n * 8 + (size_t)n + 16;
   const int in_smem = smem <= 200 * 1024;
   static SmemOptIn optin;
   if (in_smem && smem > 48 * 1024) HFB_CUDA(ctx, optin.ensure(pose_opt_kernel, ctx->device, 200 * 1024));
-  pose_opt_kernel<<<1, PO_THREADS, in_smem ? smem : 0, st>>>(n, (const double*)(a + oIn), sqrt(5.991), in_smem,
-                                                            (double*)(a + oC), a + oOut + 80, (double*)(a + oOut));
-  HFB_CHECK_LAUNCH(ctx, "pose_opt");
-  HFB_CUDA(ctx, cudaMemcpyAsync(hout, a + oOut, 80 + (size_t)n, cudaMemcpyDeviceToHost, st));
+  const int dbg = getenv("HFB_PO_DBG") ? 1 : 0;
+  if (in_smem) {
+    // The edges are read exactly once (into shared memory) and the result is 80 + n bytes: the kernel reads the
+    // page-locked block and writes the result block in place (unified addressing), which saves the two copy operations
+    // -- a third of the wall time of a call on a problem this small.
+    pose_opt_kernel<<<1, PO_THREADS, smem, st>>>(n, hin, sqrt(5.991), 1, (double*)(a + oC), hout + 80,
+                                                 reinterpret_cast<double*>(hout), dbg);
+    HFB_CHECK_LAUNCH(ctx, "pose_opt");
+  } else {
+    HFB_CUDA(ctx, cudaMemcpyAsync(a + oIn, hin, in_d * 8, cudaMemcpyHostToDevice, st));
+    pose_opt_kernel<<<1, PO_THREADS, 0, st>>>(n, (const double*)(a + oIn), sqrt(5.991), 0, (double*)(a + oC), a + oOut + 80,
+                                              (double*)(a + oOut), dbg);
+    HFB_CHECK_LAUNCH(ctx, "pose_opt");
+    HFB_CUDA(ctx, cudaMemcpyAsync(hout, a + oOut, 80 + (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
   HFB_CUDA(ctx, cudaStreamSynchronize(st));
   const double* ho = reinterpret_cast<const double*>(hout);
   memcpy(pose_out, ho, 56);

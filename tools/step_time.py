@@ -14,14 +14,17 @@ from hfnet_slam_b200.lib import Context
 
 B = int(os.environ.get("BATCH", "8"))
 reps = int(os.environ.get("REPS", "200"))
-ctx = Context(height=H, width=W, n_levels=1, max_keypoints=NKP, max_batch=B, with_global=True)
+ctx = Context(height=H, width=W, n_levels=1, max_keypoints=NKP, max_batch=B, with_global=os.environ.get("GLOBAL", "1") == "1")
 ctx.load_weights(weights.synthetic_blob(seed=0))
 ring = [torch.from_numpy(np.stack(synthetic_frames(B, 100 * i))).cuda() for i in range(8)]
 stream = torch.cuda.ExternalStream(ctx.stream)
 
 
 def step(i):
-    ctx.extract_match_batch_dev(ring[i % len(ring)].data_ptr(), B, [NKP], THR, 0, 0.6)
+    if os.environ.get("MATCH", "1") == "1":
+        ctx.extract_match_batch_dev(ring[i % len(ring)].data_ptr(), B, [NKP], THR, 0, 0.6)
+    else:
+        ctx.extract_batch_dev(ring[i % len(ring)].data_ptr(), B, [NKP], THR)
 
 
 for i in range(10):
