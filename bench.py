@@ -40,13 +40,16 @@ L2_FLUSH_BYTES = 256 << 20
 C3_BUDGETS = [217, 181, 151, 126]        # 675 features over 4 levels (src/Extractors/HFextractor.cc:108-119)
 
 
-def workload_config(batch: int, batches: int, world: int = 1) -> dict:
+def workload_config(batch: int, batches: int, world: int = 1, streams: int = 1) -> dict:
     """The ``config`` object both arms print (the reference arm runs a bounded sample of the same workload)."""
     return {"workload": "HF-Net extract single 752x480 grayscale -> 1000 kpts + 256-d local + 4096-d global + mutual-NN L2 "
                         "match vs the previous frame of the stream (BASELINE.json configs[1] + configs[0])",
             "frames_per_step": batch * batches, "frames_per_call": batch, "threshold": THR, "levels": 1,
             "weights": "seeded random init",
             "l2": "inputs larger than L2 (ring of distinct frames, 144 MB at the defaults) + 256 MiB flush between steps",
+            "streams_per_gpu": streams,
+            "streams_note": "camera streams served concurrently by one GPU: one library context + CUDA stream each, every call "
+                            "carries frames_per_call consecutive frames of its stream (the CPU arm is one stream)",
             "parallelism": f"replicas x{world}"}
 
 
@@ -162,7 +165,7 @@ def main_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.batch, args.batches, max(args.gpus, 1)),
+            "config": workload_config(args.batch, args.batches, max(args.gpus, 1), args.streams),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -560,8 +563,17 @@ def main_gpu(args):
     pk = peaks()
     cpu_arms = rank == 0 and world == 1 and not args.skip_cpu
 
-    ctx = Context(height=H, width=W, n_levels=1, max_keypoints=NKP, max_batch=B, with_global=True, device=local)
-    ctx.load_weights(weights.synthetic_blob(seed=0))
+    # S camera streams per GPU: one context (weights, activations, CUDA stream, captured graph) each.  The kernels of
+    # different contexts overlap on the device: the late layers' 64..96-CTA grids and every launch's ramp / tail leave
+    # SMs idle that another stream's kernels fill.
+    S = max(1, min(args.streams, NB))
+    blob = weights.synthetic_blob(seed=0)
+    ctxs = []
+    for _ in range(S):
+        c = Context(height=H, width=W, n_levels=1, max_keypoints=NKP, max_batch=B, with_global=True, device=local)
+        c.load_weights(blob)
+        ctxs.append(c)
+    ctx = ctxs[0]
     frames = synthetic_frames(B * NB, 1000 * rank)
     pinned_ring = pinned_empty((NB, B, H, W), np.uint8)              # e2e arm: frames arrive in page-locked host memory
     for i in range(NB):                                              # (slots of one capture ring: one H2D transfer per call)
@@ -571,8 +583,16 @@ def main_gpu(args):
     d_ptrs = [d_ring[i].data_ptr() for i in range(NB)]
     host_batches = [[pinned_ring[i, b] for b in range(B)] for i in range(NB)]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
+    stream = streams[0]
     budgets = [NKP]
+
+    def join_streams():
+        """stream 0 waits for the work enqueued on the other contexts' streams (device-side, no host synchronisation)"""
+        for st in streams[1:]:
+            e = torch.cuda.Event()
+            e.record(st)
+            stream.wait_event(e)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -583,51 +603,78 @@ def main_gpu(args):
     def step_dev():
         # per batch: extraction + frame-to-previous-frame association as one enqueue; the matching runs on the main stream
         # while the global branch (layer_8 .. FC) finishes on the side stream
+        # batch i belongs to stream i % S (consecutive batches of one stream: i, i + S, ...)
+        for i, p in enumerate(d_ptrs):
+            ctxs[i % S].extract_match_batch_dev(p, B, budgets, THR, 0, 0.6)
+
+    def step_dev_one():
         for p in d_ptrs:
             ctx.extract_match_batch_dev(p, B, budgets, THR, 0, 0.6)
 
-    match_out = (pinned_empty((B, ctx.kp_cap), np.int32), pinned_empty((B, ctx.kp_cap), np.float32))
+    match_outs = [(pinned_empty((B, c.kp_cap), np.int32), pinned_empty((B, c.kp_cap), np.float32)) for c in ctxs]
+    match_out = match_outs[0]
     host_stats = {"kp": 0, "matches": 0}
 
-    def step_host():
+    def host_stream(si, res):
         # HFextractor::operator() on host frames (H2D of the u8 frames, D2H of keypoints / descriptors / global
         # descriptors) + the association on the descriptors still resident in HBM (D2H of the match rows) through
-        # hfb_extract_match_batch, batch after batch
-        kp = 0
-        for hb in host_batches:
-            feats, idx, val = ctx.extract_match_batch(hb, budgets, THR, 0, 0.6, pinned=True, out=match_out)
+        # the synchronous hfb_extract_match_batch, batch after batch of stream si (ctypes releases the GIL in the call)
+        kp, idx = 0, None
+        for i in range(si, NB, S):
+            feats, idx, val = ctxs[si].extract_match_batch(host_batches[i], budgets, THR, 0, 0.6, pinned=True, out=match_outs[si])
             kp += sum(len(f["x"]) for f in feats)
-        host_stats["kp"] = kp
-        host_stats["matches"] = int((idx >= 0).sum())
+        res[si] = (kp, int((idx >= 0).sum()) if idx is not None else 0)
+
+    def step_host():
+        import threading
+        res = [None] * S
+        if S == 1:
+            host_stream(0, res)
+        else:
+            th = [threading.Thread(target=host_stream, args=(si, res)) for si in range(S)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        host_stats["kp"] = sum(r[0] for r in res)
+        host_stats["matches"] = res[(NB - 1) % S][1]
 
     def timed(fn, steps, warm):
         for _ in range(warm):
             fn()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
-        lc0 = ctx.launch_count
+        lc0 = sum(c.launch_count for c in ctxs)
         wall0 = time.perf_counter()
         for s in range(steps):
             flush.fill_(s & 0xFF)                                    # L2 flush between timed iterations (untimed)
             torch.cuda.synchronize(dev)
             ev[s][0].record(stream)
             fn()
+            join_streams()                                           # the end event waits for every context's stream
             ev[s][1].record(stream)
         barrier()
         wall1 = time.perf_counter()
         ms = float(sum(a.elapsed_time(b) for a, b in ev))
-        return ms, (wall0, wall1), ctx.launch_count - lc0
+        return ms, (wall0, wall1), sum(c.launch_count for c in ctxs) - lc0
 
     warm = max(args.warmup, 3)
     n_host = max(3, min(args.steps, 10))
-    ctx.reset_stream()
+    for c in ctxs:
+        c.reset_stream()
     with ClockSampler(local) as cs:
         time.sleep(0.05)
         ms_dev, (w0, w1), launches = timed(step_dev, args.steps, warm)
     clocks = cs.summary(w0, w1)
     clocks["note"] = "nvidia-smi sampled every 20 ms inside the timed device loop"
-    ctx.reset_stream()
+    for c in ctxs:
+        c.reset_stream()
     ms_host, (h0, h1), _ = timed(step_host, n_host, 2)
+    ms_one = None
+    if S > 1:                                                        # the same step on ONE context / stream, for continuity
+        ctx.reset_stream()
+        ms_one, _, _ = timed(step_dev_one, max(3, args.steps // 4), 2)
+        ms_one /= max(3, args.steps // 4)
     # sanity inside the bench: the device chain produced real keypoints and matches
     f0 = ctx.fetch_features(0)
     midx, _ = ctx.fetch_matches(1 if B > 1 else 0, len(ctx.fetch_features(1 if B > 1 else 0)["x"]))
@@ -640,6 +687,8 @@ def main_gpu(args):
         return float(t.item())
 
     ms_dev, ms_host = maxred(ms_dev), maxred(ms_host)
+    if ms_one is not None:
+        ms_one = maxred(ms_one)
     value = world * B * NB * args.steps / (ms_dev / 1e3)
     e2e = world * B * NB * n_host / (ms_host / 1e3)
     h2d = B * NB * H * W
@@ -678,6 +727,10 @@ def main_gpu(args):
              "host_keypoints_per_step": host_stats["kp"], "host_matches_last_batch": host_stats["matches"],
              "ungraphed_batch_ms": total_ms, "kernels": kernels,
              "whole_batch_tensor_frac": step_flops / (ms_dev / 1e3 / (args.steps * NB)) / 1e12 / pk["tf"]}
+    if ms_one is not None:
+        extra["single_context"] = {"frames_per_s": world * B * NB / (ms_one / 1e3), "ms_per_batch": ms_one / NB,
+                                   "note": "the same device-resident step with every batch on ONE context / CUDA stream "
+                                           "(the round-1 configuration)"}
 
     # ---- single-stream latency: a batch of ONE frame per call == the reference's per-frame TrackMonocular loop (every
     # frame is matched against the frame of the previous call)
@@ -738,14 +791,15 @@ def main_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (network), f32 (select, match recheck)",
-                "data": "synthetic", "config": workload_config(B, NB, world),
+                "data": "synthetic", "config": workload_config(B, NB, world, S),
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_host / n_host, "steps": n_host},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extra": extra,
                 "ms_per_batch": ms_dev / (args.steps * NB),
                 "wall_s": {"device_loop": w1 - w0, "host_loop": h1 - h0}}
         print(json.dumps(line))
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -758,6 +812,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="frames per call and GPU")
     ap.add_argument("--batches", type=int, default=50, help="calls per step (ring of distinct frame batches)")
+    ap.add_argument("--streams", type=int, default=4, help="camera streams (library contexts) served concurrently per GPU")
     ap.add_argument("--db-rows", type=int, default=50000)
     ap.add_argument("--cpu-frames", type=int, default=80)
     ap.add_argument("--ref-frames", type=int, default=8, help="reference arm: frames per step (bounded sample)")

@@ -210,10 +210,8 @@ struct hfb_ctx {
   void* d_io = nullptr;        // persistent device staging of the host-pointer matcher entry points
   size_t d_io_bytes = 0;
   bool pdl = true;             // HFB_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
-  int fused_min_tiles = 37;    // HFB_FUSED_MIN_TILES: fewer tiles than this -> three-kernel path
-  int fused_impl = 0;          // HFB_FUSED_IMPL: 0 = channel-per-lane kernel where it applies, 1 = pixel-per-lane kernel only
   int cpl_min_tiles = 1;       // HFB_CPL_MIN_TILES
-  bool fused_blocks = true;    // HFB_FUSED=0: inverted-residual blocks run as three kernels (expand, dw, project)
+  bool fused_blocks = true;    // HFB_FUSED=0: every inverted-residual block on the generic path (expand GEMM, depthwise, project GEMM): parity cross-check of the fused kernel
   bool trace = false;          // HFB_TRACE=1: host-side stage timings of the host-pointer calls on stderr
   std::vector<void*> allocs;
   bool use_graph = true;

@@ -102,9 +102,7 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   ctx->debug = dbg && dbg[0] == '1';
   const char* fu = getenv("HFB_FUSED");
   ctx->fused_blocks = !(fu && fu[0] == '0');
-  if (const char* fi = getenv("HFB_FUSED_IMPL")) ctx->fused_impl = atoi(fi);
   if (const char* mt = getenv("HFB_CPL_MIN_TILES")) ctx->cpl_min_tiles = atoi(mt);
-  if (const char* mt = getenv("HFB_FUSED_MIN_TILES")) ctx->fused_min_tiles = atoi(mt);   // default on; HFB_FUSED=0 keeps the three-kernel blocks
   const char* pd = getenv("HFB_PDL");
   ctx->pdl = !(pd && pd[0] == '0');
   const char* tr = getenv("HFB_TRACE");

@@ -224,17 +224,7 @@ struct GemmPlan {
   CUtensorMap tmA, tmB;
   GemmGeom g;
 };
-// fused_block.cu
-struct FusedPlan;
-FusedPlan* fused_block_new();
-void fused_block_delete(FusedPlan* p);
-int fused_block_plan(hfb_ctx* ctx, FusedPlan& fp, const BlockW& bw, const __half* in, int Bmax, int Hi, int Wi, int Ho,
-                     int Wo, int pad_t, int pad_l);
-int fused_block_run(hfb_ctx* ctx, const FusedPlan& fp, const BlockW& bw, const __half* in, __half* out, int B);
-int fused_block_tiles(const FusedPlan& fp, int B);
-double fused_block_bytes(const FusedPlan& fp, int B);
-double fused_block_flops(const FusedPlan& fp, int B);
-// fused_cpl.cu (channel-per-lane formulation of the same block)
+// fused_cpl.cu: one inverted-residual block as one kernel (channel-per-lane formulation)
 struct CplPlan;
 CplPlan* cpl_new();
 void cpl_delete(CplPlan* p);
@@ -247,8 +237,7 @@ double cpl_flops(const CplPlan& cp, int B);
 struct BlockPlan {
   GemmPlan expand, project;
   int Hi, Wi, Ho, Wo, pad_t, pad_l;
-  FusedPlan* fused = nullptr;   // non-null: the whole block can run as one fused kernel (pixel-per-lane, fused_block.cu)
-  CplPlan* cpl = nullptr;       // non-null: ... as one fused kernel in the channel-per-lane formulation (fused_cpl.cu)
+  CplPlan* cpl = nullptr;       // non-null: the whole block runs as one fused kernel (fused_cpl.cu)
 };
 struct LevelExec {
   int H1, W1, pad_t1, pad_l1;
@@ -270,7 +259,6 @@ void encoder_forget(hfb_ctx* ctx) {
   for (LevelExec& le : execs(ctx))
     for (BlockPlan& bp : le.blocks)
     {
-      if (bp.fused) fused_block_delete(bp.fused);
       if (bp.cpl) cpl_delete(bp.cpl);
     }
   execs(ctx).clear();
@@ -329,24 +317,13 @@ int encoder_plan(hfb_ctx* ctx) {
       HFB_TRY(make_plain(ctx, bp.project, lv.d_dw, bw.cexp, 0, Mout, bw.project, ctx->n_sm, 0));
       // HFB_CPL_LAYERS=<bit mask of layers> restricts the channel-per-lane kernel to some layers (experiments)
       static const long cpl_mask = getenv("HFB_CPL_LAYERS") ? strtol(getenv("HFB_CPL_LAYERS"), nullptr, 0) : -1L;
-      if (ctx->fused_blocks && ctx->fused_impl != 1 && ((cpl_mask >> bw.layer) & 1)) {
+      if (ctx->fused_blocks && ((cpl_mask >> bw.layer) & 1)) {
         bp.cpl = cpl_new();
         const int rc = cpl_plan(ctx, *bp.cpl, bw, lv.act[bw.layer - 1], Bm, bp.Hi, bp.Wi, bp.Ho, bp.Wo, bp.pad_t,
                                 bp.pad_l);
         if (rc == HFB_ERR_CAPACITY) {
           cpl_delete(bp.cpl);
           bp.cpl = nullptr;
-        } else if (rc != HFB_OK) {
-          return rc;
-        }
-      }
-      if (ctx->fused_blocks && !bp.cpl) {
-        bp.fused = fused_block_new();
-        const int rc = fused_block_plan(ctx, *bp.fused, bw, lv.act[bw.layer - 1], Bm, bp.Hi, bp.Wi, bp.Ho, bp.Wo,
-                                        bp.pad_t, bp.pad_l);
-        if (rc == HFB_ERR_CAPACITY) {   // does not fit on chip: this block keeps the three-kernel path
-          fused_block_delete(bp.fused);
-          bp.fused = nullptr;
         } else if (rc != HFB_OK) {
           return rc;
         }
@@ -463,18 +440,13 @@ int encoder_forward(hfb_ctx* ctx, int level, int B, float threshold) {
       HFB_CHECK_LAUNCH(ctx, "dw_project_small");
       continue;
     }
-    // one fused kernel per block unless the batch leaves it only a handful of tiles (single frames at 15 x 24 pixels
-    // run faster as three small launches that spread over the output channels)
     if (bp.cpl && cpl_tiles(ctx, *bp.cpl, bw.stride, B) >= ctx->cpl_min_tiles) {
       ctx->note(ln + ".fused", cpl_bytes(*bp.cpl, B), cpl_flops(*bp.cpl, B));
       HFB_TRY(cpl_run(ctx, *bp.cpl, bw, in, lv.act[bw.layer], B));
       continue;
     }
-    if (bp.fused && fused_block_tiles(*bp.fused, B) >= ctx->fused_min_tiles) {
-      ctx->note(ln + ".fused", fused_block_bytes(*bp.fused, B), fused_block_flops(*bp.fused, B));
-      HFB_TRY(fused_block_run(ctx, *bp.fused, bw, in, lv.act[bw.layer], B));
-      continue;
-    }
+    // block shapes outside the fused kernel's limits (more than 112 input channels, channel counts that are not
+    // multiples of 8) keep the generic path: expand GEMM, depthwise kernel, project GEMM
     if (bw.has_expand) {
       ctx->note(ln + ".expand", 2.0 * Min * (bw.cin + bw.cexp) + 2.0 * bw.cin * bw.cexp, 2.0 * Min * bw.cin * bw.cexp);
       HFB_TRY(run_plain(ctx, bp.expand, Min, lv.d_exp, bw.cexp, bw.expand.b, nullptr, 0, 1));

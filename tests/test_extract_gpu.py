@@ -300,3 +300,24 @@ def test_c5_tumvi_stream_masked_best2(native_lib, weights_blob):
         sub = qi[::3]
         ridx2, rdist2, _ = ctx.match_projection_frame(0, sub, uv[sub], rad[sub], mn[sub], mx[sub], nf=len(cur["x"]))
         assert np.array_equal(ridx2, idx[sub]) and np.array_equal(rdist2, dist[sub])
+
+
+def test_concurrent_pyramid_levels_equal_sequential_levels(native_lib, weights_blob, monkeypatch):
+    """Levels >= 1 run on their own streams (fork after the resize chain, join before the sampling kernels whose row
+    offsets need the counts of the levels below): every output equals the one-stream schedule bit for bit, on the warm
+    run, the captured graph and its replay (src/Extractors/HFextractor.cc:228-283 concatenates the levels in order)."""
+    imgs = [weights.synthetic_image(480, 752, seed=s, n_corners=200) for s in (3, 4)]
+    budgets = select_ref.features_per_level(675, 4, 1.2)
+
+    def run(fork):
+        monkeypatch.setenv("HFB_FORK_LEVELS", "1" if fork else "0")
+        with Context(height=480, width=752, n_levels=4, scale_factor=1.2, max_keypoints=675, max_batch=2) as ctx:
+            ctx.load_weights(weights_blob)
+            return [ctx.extract_batch(imgs, budgets, 0.01) for _ in range(3)]
+
+    seq, par = run(False), run(True)
+    for rep in range(3):
+        for i in range(2):
+            assert seq[0][i]["n_per_level"] == par[rep][i]["n_per_level"]
+            for k in ("x", "y", "response", "octave", "descriptors", "global_descriptor"):
+                assert np.array_equal(seq[0][i][k], par[rep][i][k]), (rep, i, k)
