@@ -300,20 +300,29 @@ def extra_lba(ctx, cpu: bool):
     return r
 
 
-def c3_gpu(torch, dev, n_frames: int):
-    """BASELINE.json configs[2] call pattern through the public host API on one B200 (see module docstring)."""
+def c3_gpu(torch, dev, n_frames: int, threads: int = 2):
+    """BASELINE.json configs[2] call pattern through the public host API on one B200 (see module docstring).
+    threads = 2: tracking (extract + associate + windowed search + 2 pose optimisations per frame) on the calling thread
+    and local mapping (neighbour matching + place recognition + local BA per keyframe) on a second host thread with its
+    own library context, as the reference runs them (src/System.cc starts LocalMapping::Run on its own thread; keyframes
+    are handed over through a queue, src/LocalMapping.cc:InsertKeyFrame).  threads = 1: everything serialised."""
+    import queue
+    import threading
     from hfnet_slam_b200 import synthetic, weights
     from hfnet_slam_b200.keyframe_database import KeyFrameDatabase
     from hfnet_slam_b200.lib import Context, KeyFrameStore, pinned_empty
     from hfnet_slam_b200.optimizer import local_bundle_adjustment, pose_optimization
     ctx = Context(height=H, width=W, n_levels=4, scale_factor=1.2, max_keypoints=675, max_batch=1, with_global=True,
                   device=dev.index or 0)
+    # LocalMapping's context: matcher / database / BA workspaces only (no extraction)
+    ctx_map = ctx if threads < 2 else Context(height=64, width=64, n_levels=1, max_keypoints=64, max_batch=1,
+                                              with_global=False, device=dev.index or 0)
     store = KeyFrameStore(ctx, n_slots=16, rows_per_slot=ctx.kp_cap)     # keyframe descriptors stay in HBM
     ctx.load_weights(weights.synthetic_blob(seed=0))
     base = weights.synthetic_image(H, W, seed=1, n_corners=300)
     frame = pinned_empty((H, W), np.uint8)
     match_out = (pinned_empty((1, ctx.kp_cap), np.int32), pinned_empty((1, ctx.kp_cap), np.float32))
-    kf = KeyFrameDatabase(ctx, capacity=4096)
+    kf = KeyFrameDatabase(ctx_map, capacity=4096)
     pose_p = synthetic.pose_problem(n=300, seed=11)
     lba_p = synthetic.lba_problem(n_opt=20, n_fixed=40, n_points=3000, seed=3)
     t = {}
@@ -322,6 +331,39 @@ def c3_gpu(torch, dev, n_frames: int):
     def tick(key, t0):
         t[key] = t.get(key, 0.0) + time.perf_counter() - t0
 
+    def map_keyframe(job):
+        kid, n_desc, gdesc = job
+        t0 = time.perf_counter()
+        if kfs:
+            store.match_neighbours(ctx_map, kid, kfs[-10:], 1, 0.71875, n_desc)   # SearchForTriangulation flavour
+        if len(kfs) >= 12:
+            store.erase(kfs[-12])
+        tick("kf_match", t0)
+        t0 = time.perf_counter()
+        kf.add(kid, gdesc)
+        if kid > 1:
+            kf.query(gdesc)
+        tick("kfdb", t0)
+        t0 = time.perf_counter()
+        local_bundle_adjustment(ctx_map, lba_p, iterations=10)
+        tick("lba", t0)
+        kfs.append(kid)
+
+    jobs = queue.Queue()
+
+    def mapping_thread():
+        while True:
+            job = jobs.get()
+            if job is None:
+                jobs.task_done()
+                return
+            map_keyframe(job)
+            jobs.task_done()
+
+    worker = None
+    if threads >= 2:
+        worker = threading.Thread(target=mapping_thread, daemon=True)
+        worker.start()
     wall = 0.0
     for warm in (True, False):
         n = 72 if warm else n_frames      # the warm-up also fills the 10-neighbour window
@@ -349,29 +391,28 @@ def c3_gpu(torch, dev, n_frames: int):
                 n_kf += 1
                 t0 = time.perf_counter()
                 store.put_frame(ctx, n_kf, 0, len(desc))                     # device to device, prepared once
-                if kfs:
-                    store.match_neighbours(ctx, n_kf, kfs[-10:], 1, 0.71875, len(desc))   # SearchForTriangulation flavour
-                if len(kfs) >= 12:
-                    store.erase(kfs[-12])
-                tick("kf_match", t0)
-                t0 = time.perf_counter()
-                kf.add(n_kf, f["global_descriptor"])
-                if n_kf > 1:
-                    kf.query(f["global_descriptor"])
-                tick("kfdb", t0)
-                t0 = time.perf_counter()
-                local_bundle_adjustment(ctx, lba_p, iterations=10)
-                tick("lba", t0)
-                kfs.append(n_kf)
+                tick("kf_insert", t0)
+                job = (n_kf, len(desc), f["global_descriptor"].copy())
+                if worker is not None:
+                    jobs.put(job)                                            # LocalMapping::InsertKeyFrame
+                else:
+                    map_keyframe(job)
             prev = (desc, xy, octv)
+        jobs.join()                                                          # local mapping has caught up
         wall = time.perf_counter() - wall0
+    if worker is not None:
+        jobs.put(None)
+        worker.join()
     n_key = (n_frames + 5) // 6
-    stages = {k: (1e3 * v / (n_key if k in ("kf_match", "kfdb", "lba") else n_frames)) for k, v in t.items()}
+    stages = {k: (1e3 * v / (n_key if k in ("kf_match", "kfdb", "lba", "kf_insert") else n_frames)) for k, v in t.items()}
     kf.close()
     store.close()
+    if ctx_map is not ctx:
+        ctx_map.close()
     ctx.close()
-    return {"frames": n_frames, "keyframes": n_key, "frames_per_s": n_frames / wall,
-            "stage_ms": stages, "stage_ms_note": "kf_match / kfdb / lba per keyframe, the others per frame"}
+    return {"frames": n_frames, "keyframes": n_key, "frames_per_s": n_frames / wall, "host_threads": threads,
+            "stage_ms": stages, "stage_ms_note": "kf_insert / kf_match / kfdb / lba per keyframe, the others per frame; with two "
+                                               "host threads the per-keyframe stages run beside the per-frame ones"}
 
 
 def c3_cpu(n_frames: int):
@@ -760,13 +801,16 @@ def main_gpu(args):
             extra["lba"] = extra_lba(ctx, cpu_arms)
         extra["loopdb"] = extra_loopdb(torch, dist, ctx, dev, pk, world, rank, args.db_rows, barrier, maxred, stream, cpu_arms)
         if world == 1:
-            c3 = {"gpu": c3_gpu(torch, dev, args.c3_frames)}
+            c3 = {"gpu": c3_gpu(torch, dev, args.c3_frames, 2), "gpu_one_thread": c3_gpu(torch, dev, args.c3_frames, 1)}
             if cpu_arms:
                 c3["cpu"] = c3_cpu(args.c3_cpu_frames)
                 c3["speedup_vs_cpu_arm"] = c3["gpu"]["frames_per_s"] / c3["cpu"]["frames_per_s"]
             c3["vs_published_50fps"] = c3["gpu"]["frames_per_s"] / 50.0
-            c3["note"] = ("BASELINE.json configs[2] schedule on synthetic frames through the public host API, tracking + mapping work "
-                          "serialised on one host thread; 'published' = the reference's own 50 FPS claim (README.md:17, RTX 2070)")
+            c3["note"] = ("BASELINE.json configs[2] schedule on synthetic frames through the public host API; 'gpu' = tracking and "
+                          "local mapping on two host threads / two contexts as in the reference (src/System.cc), "
+                          "'gpu_one_thread' = the same work serialised on one host thread (the CPU arm is serialised too); "
+                          "'published' = the reference's own 50 FPS claim (README.md:17, RTX 2070)")
+            c3["one_thread_vs_published_50fps"] = c3["gpu_one_thread"]["frames_per_s"] / 50.0
             extra["c3"] = c3
             try:
                 sys.path.insert(0, str(ROOT / "tools"))

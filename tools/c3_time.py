@@ -43,4 +43,5 @@ if os.environ.get("AB", "1") == "1":
             assert a[0][i]["n_per_level"] == b[rep][i]["n_per_level"]
     print("levels A/B identical:", a[0][0]["n_per_level"], a[0][1]["n_per_level"])
 dev = torch.device("cuda:0")
-print(json.dumps(bench.c3_gpu(torch, dev, int(os.environ.get("FRAMES", "120")))))
+for th in (2, 1):
+    print(json.dumps(bench.c3_gpu(torch, dev, int(os.environ.get("FRAMES", "120")), th)))

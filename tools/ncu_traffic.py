@@ -53,7 +53,7 @@ for r in rows[2:]:
         label = "match.argmax"
     else:
         label = {"nms_kernel": "nms", "conv1_kernel": "conv1", "dw_project_small_kernel<24, 16>": "l2.dw+project",
-                 "fc_partial_kernel": "global.fc", "select_topk_kernel": "select_topk",
+                 "fc_mma_kernel": "global.fc", "vlad_kernel": "global.netvlad", "select_topk_kernel": "select_topk",
                  "stem_kernel": "stem.conv1+l2"}.get(name, name)
     rd, wr = val(r, "dram__bytes_read.sum") or 0.0, val(r, "dram__bytes_write.sum") or 0.0
     rec = {"kernel": name, "label": label, "ncu_us": val(r, "gpu__time_duration.sum"),
