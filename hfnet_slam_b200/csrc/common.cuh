@@ -198,6 +198,15 @@ struct hfb_ctx {
   float *d_kx = nullptr, *d_ky = nullptr, *d_kresp = nullptr, *d_kdesc = nullptr, *d_global = nullptr;
   int* d_koct = nullptr;
   int* d_kcount = nullptr;  // [max_batch][HFB_MAX_LEVELS]
+  // Frame's calibration (hfb_set_camera): with distortion every extraction also writes the undistorted coordinates
+  // (Frame::mvKeysUn, src/Frame.cc:760-793) of its keypoints; coefficients widened to double as OpenCV does
+  struct Camera {
+    bool on = false;            // dist[0] != 0
+    double fx = 1, fy = 1, cx = 0, cy = 0;
+    double k[12] = {0};
+  } cam;
+  float *d_kxu = nullptr, *d_kyu = nullptr;   // [max_batch][kp_cap]
+  bool kun_valid = false;      // the last extraction filled them (hfb_extract_level works in level coordinates and does not)
   int last_budget[HFB_MAX_LEVELS] = {0};
   int last_batch = 0;
   float last_threshold = 0.f;
@@ -307,6 +316,11 @@ int launch_select_sample(hfb_ctx* ctx, const float* d_nms, int H, int W, const f
                          float threshold, float level_scale, int B, int kp_cap, float* d_x, float* d_y,
                          float* d_resp, int* d_oct, float* d_desc, int* d_kcount, int* d_overflow,
                          bool candidates_ready);
+// cv::undistortPoints with P = K on n points, or (d_kcount != nullptr) on the first sum(d_kcount[b][:]) keypoints of each of
+// B frames laid out [B][kp_cap]
+struct UndistortParams { double fx, fy, cx, cy, ifx, ify, k[12]; };
+int launch_undistort(hfb_ctx* ctx, const float* d_x, const float* d_y, float* d_xu, float* d_yu, int n, int B, int kp_cap,
+                     const int* d_kcount);
 int launch_resize(hfb_ctx* ctx, const uint8_t* d_src, int sh, int sw, uint8_t* d_dst, int dh, int dw, const int* d_xi,
                   const short* d_xa, const int* d_yi, const short* d_ya, int B);
 void build_resize_tables(int sn, int dn, std::vector<int>& idx, std::vector<short>& coef);

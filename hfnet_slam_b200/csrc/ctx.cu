@@ -177,6 +177,8 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   HFB_TRY(ctx->dalloc(&ctx->d_kx, nb * ctx->kp_cap));
   HFB_TRY(ctx->dalloc(&ctx->d_ky, nb * ctx->kp_cap));
   HFB_TRY(ctx->dalloc(&ctx->d_kresp, nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_kxu, nb * ctx->kp_cap));
+  HFB_TRY(ctx->dalloc(&ctx->d_kyu, nb * ctx->kp_cap));
   HFB_TRY(ctx->dalloc(&ctx->d_koct, nb * ctx->kp_cap));
   {
     // 2 * max_batch frame slots: the carried descriptors of the previous call sit right below the current frames
@@ -537,6 +539,8 @@ static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, floa
                           ctx->d_nsel, (int)nb, n_per_level[l], lv.scale, l, B, ctx->kp_cap, ctx->d_kx, ctx->d_ky,
                           ctx->d_kresp, ctx->d_koct, ctx->d_kdesc, ctx->d_kcount));
   }
+  if (ctx->cam.on)   // Frame::UndistortKeyPoints: mvKeysUn next to mvKeys (one launch over all frames)
+    HFB_TRY(launch_undistort(ctx, ctx->d_kx, ctx->d_ky, ctx->d_kxu, ctx->d_kyu, ctx->kp_cap, B, ctx->kp_cap, ctx->d_kcount));
   // everything that does not depend on the global branch happens now (main stream), overlapping the side stream:
   // the optional frame-to-previous-frame association and the transfer of the local features
   const hfb_ctx::D2HPlan& d = ctx->d2h;
@@ -589,6 +593,7 @@ static int run_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, float th
                 "per-level keypoint budget outside [0, max_keypoints]");
   ctx->last_batch = B;
   ctx->last_threshold = threshold;
+  ctx->kun_valid = ctx->cam.on;
   for (int l = 0; l < ctx->n_levels; ++l) ctx->last_budget[l] = n_per_level[l];
   if (!ctx->use_graph) return enqueue_extract(ctx, B, n_per_level, threshold);
   std::vector<int> key;
@@ -894,6 +899,7 @@ extern "C" int hfb_extract_level(hfb_ctx* ctx, int32_t level, const uint8_t* ima
   HFB_CUDA(ctx, cudaMemcpyAsync(lv.d_img, hs, img_bytes, cudaMemcpyHostToDevice, st));
   ctx->last_batch = 1;
   ctx->last_threshold = threshold;
+  ctx->kun_valid = false;   // level coordinates: the caller scales, then undistorts (hfb_undistort_points)
   for (int l = 0; l < ctx->n_levels; ++l) ctx->last_budget[l] = l == 0 ? n_keypoints : 0;
   HFB_CUDA(ctx, cudaMemsetAsync(ctx->d_kcount, 0, HFB_MAX_LEVELS * sizeof(int), st));
   HFB_CUDA(ctx, cudaMemsetAsync(ctx->d_stream_state, 0, sizeof(int), st));   // no streaming history through this entry
@@ -1211,6 +1217,75 @@ static int enqueue_match_consecutive(hfb_ctx* ctx, int n_images, int mode, float
 
 // Stream layout of a batch and the reset of the association's history (Tracking::Reset / a new map start from an empty
 // mLastFrame, src/Tracking.cc:3256-3330).
+// --------------------------------------------------------------------------------------------------- calibration
+extern "C" int hfb_set_camera(hfb_ctx* ctx, const float* K, const float* dist, int32_t n_dist) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, K && K[0] != 0.f && K[1] != 0.f, "K = (fx, fy, cx, cy) with non-zero focal lengths");
+  HFB_REQUIRE(ctx, n_dist == 0 || n_dist == 4 || n_dist == 5 || n_dist == 8 || n_dist == 12,
+              "n_dist must be 0, 4, 5, 8 or 12 (OpenCV's coefficient vectors without the tilt terms)");
+  HFB_REQUIRE(ctx, n_dist == 0 || dist, "null distortion vector");
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  drop_graphs(ctx);   // the calibration is a kernel argument of the captured extraction
+  hfb_ctx::Camera& c = ctx->cam;
+  c.fx = K[0]; c.fy = K[1]; c.cx = K[2]; c.cy = K[3];
+  for (int i = 0; i < 12; ++i) c.k[i] = i < n_dist ? (double)dist[i] : 0.0;
+  c.on = n_dist > 0 && dist[0] != 0.f;   // src/Frame.cc:762: only the first coefficient is tested
+  ctx->kun_valid = false;
+  return HFB_OK;
+}
+
+extern "C" int hfb_undistort_points(hfb_ctx* ctx, const float* x, const float* y, int32_t n, float* x_un, float* y_un) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, n >= 0 && (n == 0 || (x && y && x_un && y_un)), "bad argument");
+  if (n == 0) return HFB_OK;
+  if (!ctx->cam.on) {   // mvKeysUn = mvKeys
+    if (x_un != x) memmove(x_un, x, (size_t)n * 4);
+    if (y_un != y) memmove(y_un, y, (size_t)n * 4);
+    return HFB_OK;
+  }
+  HFB_TRY(ctx->ensure_scratch((size_t)n * 16));
+  float* d = reinterpret_cast<float*>(ctx->d_scratch);
+  HFB_CUDA(ctx, cudaMemcpyAsync(d, x, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(d + n, y, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  HFB_TRY(launch_undistort(ctx, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, n, 1, 0, nullptr));
+  HFB_CUDA(ctx, cudaMemcpyAsync(x_un, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(y_un, d + 3 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
+}
+
+extern "C" int hfb_fetch_undistorted(hfb_ctx* ctx, int32_t image_index, float* x_un, float* y_un, int32_t n) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, image_index >= 0 && image_index < ctx->last_batch, "bad image index");
+  HFB_REQUIRE(ctx, n >= 0 && n <= ctx->kp_cap && (n == 0 || (x_un && y_un)), "bad argument");
+  if (n == 0) return HFB_OK;
+  HFB_REQUIRE(ctx, !ctx->cam.on || ctx->kun_valid,
+              "the last extraction did not produce undistorted coordinates (hfb_extract_level, or the camera was set afterwards)");
+  const size_t o = (size_t)image_index * ctx->kp_cap;
+  const float *sx = ctx->cam.on ? ctx->d_kxu : ctx->d_kx, *sy = ctx->cam.on ? ctx->d_kyu : ctx->d_ky;
+  HFB_CUDA(ctx, cudaMemcpyAsync(x_un, sx + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaMemcpyAsync(y_un, sy + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HFB_OK;
+}
+
+extern "C" int hfb_image_bounds(hfb_ctx* ctx, int32_t width, int32_t height, float* bounds) {
+  HFB_ENTER(ctx);
+  HFB_REQUIRE(ctx, bounds && width > 0 && height > 0, "bad argument");
+  if (!ctx->cam.on) {
+    bounds[0] = 0.f; bounds[1] = (float)width; bounds[2] = 0.f; bounds[3] = (float)height;
+    return HFB_OK;
+  }
+  const float cx[4] = {0.f, (float)width, 0.f, (float)width}, cy[4] = {0.f, 0.f, (float)height, (float)height};
+  float ux[4], uy[4];
+  HFB_TRY(hfb_undistort_points(ctx, cx, cy, 4, ux, uy));
+  bounds[0] = std::min(ux[0], ux[2]);
+  bounds[1] = std::max(ux[1], ux[3]);
+  bounds[2] = std::min(uy[0], uy[1]);
+  bounds[3] = std::max(uy[2], uy[3]);
+  return HFB_OK;
+}
+
 extern "C" int hfb_set_stream_mode(hfb_ctx* ctx, int32_t mode) {
   HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, mode == 0 || mode == 1, "stream mode must be 0 (one stream per batch) or 1 (one stream per batch slot)");

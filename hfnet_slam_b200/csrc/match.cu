@@ -828,6 +828,7 @@ extern "C" int hfb_match_projection_frame(hfb_ctx* ctx, int32_t frame_index, con
   HFB_ENTER(ctx);
   HFB_REQUIRE(ctx, ctx->last_batch > 0 && frame_index >= 0 && frame_index < ctx->last_batch, "no such resident frame");
   HFB_REQUIRE(ctx, nf >= 0 && nf <= ctx->kp_cap, "nf exceeds the frame's keypoint capacity");
+  HFB_REQUIRE(ctx, !ctx->cam.on || ctx->kun_valid, "the resident frame has no undistorted coordinates (camera set after its extraction)");
   HFB_REQUIRE(ctx, nq == 0 || q_prev_index, "null query index");
   for (int i = 0; i < nq; ++i)
     HFB_REQUIRE(ctx, q_prev_index[i] >= 0 && q_prev_index[i] < ctx->kp_cap, "query index outside the previous frame");
@@ -835,7 +836,8 @@ extern "C" int hfb_match_projection_frame(hfb_ctx* ctx, int32_t frame_index, con
   const float* dQ_base = ctx->d_kdesc + prev_slot * ctx->kp_cap * HFB_DESC_DIM;
   const size_t fo = (size_t)frame_index * ctx->kp_cap;
   return proj_common(ctx, nullptr, q_prev_index, dQ_base, nq, q_uv, q_radius, q_min_level, q_max_level, nullptr,
-                     ctx->d_kdesc + fo * HFB_DESC_DIM, ctx->d_kx + fo, ctx->d_ky + fo, ctx->d_koct + fo, nf, nullptr, nullptr,
+                     ctx->d_kdesc + fo * HFB_DESC_DIM, (ctx->cam.on ? ctx->d_kxu : ctx->d_kx) + fo,
+                     (ctx->cam.on ? ctx->d_kyu : ctx->d_ky) + fo, ctx->d_koct + fo, nf, nullptr, nullptr,
                      f_skip, f_inv_sigma2, chi2_max, cand_idx, cand_dist, cand_level);
 }
 

@@ -480,3 +480,70 @@ int launch_resize(hfb_ctx* ctx, const uint8_t* d_src, int sh, int sw, uint8_t* d
   HFB_CHECK_LAUNCH(ctx, "resize");
   return HFB_OK;
 }
+
+// ======================================================================================================= undistortion
+// Frame::UndistortKeyPoints (src/Frame.cc:760-793) = cv::undistortPoints(pts, pts, K, dist, noArray(), K): normalise with K,
+// five fixed-point iterations of the inverse Brown-Conrady model (OpenCV 4 calib3d, criteria COUNT = 5), re-project with
+// P = K, round to float.  All in double, every operation rounded on its own (no contraction) in OpenCV's expression
+// order, so the result equals cv2.undistortPoints bit for bit (tests/test_undistort_gpu.py).
+__global__ void undistort_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ xu,
+                                 float* __restrict__ yu, int n, int kp_cap, const int* __restrict__ kcount,
+                                 UndistortParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int lim = n;
+  if (kcount) {   // frame blockIdx.y of a batch: only its selected keypoints
+    lim = 0;
+    for (int l = 0; l < HFB_MAX_LEVELS; ++l) lim += kcount[blockIdx.y * HFB_MAX_LEVELS + l];
+    lim = min(lim, kp_cap);
+  }
+  if (i >= lim) return;
+  const size_t o = (size_t)blockIdx.y * kp_cap + i;
+#define MUL(a, b) __dmul_rn((a), (b))
+#define ADD(a, b) __dadd_rn((a), (b))
+#define SUB(a, b) __dsub_rn((a), (b))
+  double xn = MUL(SUB((double)x[o], p.cx), p.ifx), yn = MUL(SUB((double)y[o], p.cy), p.ify);
+  const double x0 = xn, y0 = yn;
+  const double* k = p.k;
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    const double r2 = ADD(MUL(xn, xn), MUL(yn, yn));
+    const double num = ADD(1.0, MUL(ADD(MUL(ADD(MUL(k[7], r2), k[6]), r2), k[5]), r2));
+    const double den = ADD(1.0, MUL(ADD(MUL(ADD(MUL(k[4], r2), k[1]), r2), k[0]), r2));
+    const double icdist = __ddiv_rn(num, den);
+    if (icdist < 0) {   // OpenCV gives up on the point and keeps the normalised coordinates
+      xn = x0;
+      yn = y0;
+      break;
+    }
+    const double dx = ADD(ADD(ADD(MUL(MUL(MUL(2.0, k[2]), xn), yn), MUL(k[3], ADD(r2, MUL(MUL(2.0, xn), xn)))),
+                              MUL(k[8], r2)), MUL(MUL(k[9], r2), r2));
+    const double dy = ADD(ADD(ADD(MUL(k[2], ADD(r2, MUL(MUL(2.0, yn), yn))), MUL(MUL(MUL(2.0, k[3]), xn), yn)),
+                              MUL(k[10], r2)), MUL(MUL(k[11], r2), r2));
+    xn = MUL(SUB(x0, dx), icdist);
+    yn = MUL(SUB(y0, dy), icdist);
+  }
+  // P = K as the full 3 x 3 product (the zero entries only matter for diverged points: 0 * inf)
+  const double xx = ADD(ADD(MUL(p.fx, xn), MUL(0.0, yn)), p.cx), yy = ADD(ADD(MUL(0.0, xn), MUL(p.fy, yn)), p.cy);
+  const double ww = __ddiv_rn(1.0, ADD(ADD(MUL(0.0, xn), MUL(0.0, yn)), 1.0));
+  xu[o] = __double2float_rn(MUL(xx, ww));
+  yu[o] = __double2float_rn(MUL(yy, ww));
+#undef MUL
+#undef ADD
+#undef SUB
+}
+
+int launch_undistort(hfb_ctx* ctx, const float* d_x, const float* d_y, float* d_xu, float* d_yu, int n, int B, int kp_cap,
+                     const int* d_kcount) {
+  const hfb_ctx::Camera& c = ctx->cam;
+  UndistortParams p;
+  p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
+  p.ifx = 1.0 / c.fx; p.ify = 1.0 / c.fy;
+  for (int i = 0; i < 12; ++i) p.k[i] = c.k[i];
+  if (n <= 0) return HFB_OK;
+  dim3 grid(ceil_div(n, 128), B);
+  hfb_launch(ctx, undistort_kernel, grid, 128, 0, d_x, d_y, d_xu, d_yu, n, kp_cap, d_kcount, p);
+  HFB_CHECK_LAUNCH(ctx, "undistort");
+  return HFB_OK;
+}

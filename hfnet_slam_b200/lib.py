@@ -82,6 +82,10 @@ SIGNATURES = {
     "hfb_select_sample": (C.c_int, [C.c_void_p, _f32p, C.c_int32, C.c_int32, _f32p, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_float, _f32p, _f32p, _f32p, _f32p, _i32p]),
     "hfb_resize_linear_u8": (C.c_int, [C.c_void_p, _u8p, C.c_int32, C.c_int32, _u8p, C.c_int32, C.c_int32]),
+    "hfb_set_camera": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int32]),
+    "hfb_undistort_points": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int32, _f32p, _f32p]),
+    "hfb_fetch_undistorted": (C.c_int, [C.c_void_p, C.c_int32, _f32p, _f32p, C.c_int32]),
+    "hfb_image_bounds": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _f32p]),
     "hfb_debug_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, _f32p, C.c_size_t,
                                    C.POINTER(C.c_size_t), _i32p]),
     "hfb_debug_gemm": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _f32p,
@@ -493,6 +497,33 @@ class Context:
         self.check(self.lib.hfb_resize_linear_u8(self.handle, ptr(s, _u8p), s.shape[0], s.shape[1], ptr(out, _u8p),
                                                  dh, dw))
         return out
+
+    # ------------------------------------------------------------------------------------------ calibration (Frame)
+    def set_camera(self, K, dist=()) -> None:
+        """Frame's mK = (fx, fy, cx, cy) and mDistCoef; with dist[0] != 0 every extraction also produces mvKeysUn."""
+        k = as_f32(K).reshape(4)
+        d = as_f32(dist).reshape(-1)
+        self.check(self.lib.hfb_set_camera(self.handle, ptr(k, _f32p), ptr(d, _f32p) if d.size else None, d.size))
+
+    def undistort_points(self, x, y):
+        """cv::undistortPoints(pts, pts, K, dist, noArray(), K) (Frame::UndistortKeyPoints, src/Frame.cc:760-793)."""
+        xs, ys = as_f32(x).reshape(-1), as_f32(y).reshape(-1)
+        xu, yu = np.empty_like(xs), np.empty_like(ys)
+        self.check(self.lib.hfb_undistort_points(self.handle, ptr(xs, _f32p), ptr(ys, _f32p), xs.size, ptr(xu, _f32p),
+                                                 ptr(yu, _f32p)))
+        return xu, yu
+
+    def fetch_undistorted(self, image_index: int, n: int):
+        """mvKeysUn coordinates of the first n keypoints of frame ``image_index`` of the last extraction."""
+        xu, yu = np.empty(n, np.float32), np.empty(n, np.float32)
+        self.check(self.lib.hfb_fetch_undistorted(self.handle, image_index, ptr(xu, _f32p), ptr(yu, _f32p), n))
+        return xu, yu
+
+    def image_bounds(self, width: int, height: int) -> np.ndarray:
+        """Frame::ComputeImageBounds: (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
+        b = np.empty(4, np.float32)
+        self.check(self.lib.hfb_image_bounds(self.handle, width, height, ptr(b, _f32p)))
+        return b
 
     def debug_gemm(self, A: np.ndarray, Wt: np.ndarray, bias=None, relu6=False, conv3x3=False, use_tc=True,
                    BN: int = 0) -> np.ndarray:

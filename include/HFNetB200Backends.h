@@ -5,6 +5,7 @@
  *                               SearchForTriangulation, the windowed SearchByProjection family
  *   HFNetB200KeyFrameDatabase   KeyFrameDatabase::add / erase / clear / clearMap and the scan behind DetectNBestCandidates /
  *                               DetectRelocalizationCandidates (include/KeyFrameDatabase.h:59-69)
+ *   HFNetB200Frame              Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:760-825)
  *   HFNetB200Optimizer          the numeric cores of Optimizer::LocalBundleAdjustment and Optimizer::PoseOptimization
  *                               (include/Optimizer.h:59,61)
  *
@@ -141,6 +142,40 @@ public:
 
 private:
     hfb_kfdb *mDb;
+};
+
+/* Frame's two calibration-dependent steps.  SetCamera once per context (Frame's static mK / mDistCoef, src/Frame.cc:
+ * 358-372); from then on the fused extraction also leaves mvKeysUn resident for the windowed searches. */
+class HFNetB200Frame
+{
+public:
+    static bool SetCamera(hfb_ctx *ctx, float fx, float fy, float cx, float cy, const cv::Mat &distCoef)
+    {
+        const float K[4] = {fx, fy, cx, cy};
+        const int n = distCoef.rows * distCoef.cols;
+        return hfb_set_camera(ctx, K, n > 0 ? distCoef.ptr<float>() : nullptr, n) == HFB_OK;
+    }
+
+    /* Frame::UndistortKeyPoints (src/Frame.cc:760-793): mvKeysUn = mvKeys with undistorted pt. */
+    static bool UndistortKeyPoints(hfb_ctx *ctx, const std::vector<cv::KeyPoint> &vKeys, std::vector<cv::KeyPoint> &vKeysUn)
+    {
+        const size_t N = vKeys.size();
+        std::vector<float> x(N), y(N), xu(N), yu(N);
+        for (size_t i = 0; i < N; ++i) { x[i] = vKeys[i].pt.x; y[i] = vKeys[i].pt.y; }
+        if (hfb_undistort_points(ctx, x.data(), y.data(), (int32_t)N, xu.data(), yu.data()) != HFB_OK) return false;
+        vKeysUn = vKeys;
+        for (size_t i = 0; i < N; ++i) { vKeysUn[i].pt.x = xu[i]; vKeysUn[i].pt.y = yu[i]; }
+        return true;
+    }
+
+    /* Frame::ComputeImageBounds (src/Frame.cc:796-825). */
+    static bool ComputeImageBounds(hfb_ctx *ctx, int cols, int rows, float &mnMinX, float &mnMaxX, float &mnMinY, float &mnMaxY)
+    {
+        float b[4];
+        if (hfb_image_bounds(ctx, cols, rows, b) != HFB_OK) return false;
+        mnMinX = b[0]; mnMaxX = b[1]; mnMinY = b[2]; mnMaxY = b[3];
+        return true;
+    }
 };
 
 class HFNetB200Optimizer

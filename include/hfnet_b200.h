@@ -135,6 +135,20 @@ int hfb_select_sample(hfb_ctx* ctx, const float* scores_nms, int32_t height, int
 int hfb_resize_linear_u8(hfb_ctx* ctx, const uint8_t* src, int32_t sh, int32_t sw, uint8_t* dst, int32_t dh,
                          int32_t dw);
 
+/* Frame's calibration (mK, mDistCoef; src/Frame.cc:760-825).  K = (fx, fy, cx, cy); dist = OpenCV's (k1, k2, p1, p2[, k3
+ * [, k4, k5, k6[, s1, s2, s3, s4]]]), n_dist in {0, 4, 5, 8, 12}.  With dist[0] != 0 every extraction also leaves the
+ * undistorted keypoint coordinates (Frame::mvKeysUn) resident next to the distorted ones, and the searches on resident
+ * frames (hfb_match_projection_frame) use them -- as the reference's do.  dist[0] == 0 (or n_dist == 0) is the
+ * reference's early return: mvKeysUn = mvKeys (:762-766).
+ * hfb_undistort_points   == cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) on N x 2 floats (:778), bit-exact
+ *                           with OpenCV 4's 5-iteration fixed point in double.
+ * hfb_fetch_undistorted  : mvKeysUn coordinates of frame `image_index` of the last extraction (first n keypoints).
+ * hfb_image_bounds       == Frame::ComputeImageBounds (:796-825): {mnMinX, mnMaxX, mnMinY, mnMaxY}. */
+int hfb_set_camera(hfb_ctx* ctx, const float* K, const float* dist, int32_t n_dist);
+int hfb_undistort_points(hfb_ctx* ctx, const float* x, const float* y, int32_t n, float* x_un, float* y_un);
+int hfb_fetch_undistorted(hfb_ctx* ctx, int32_t image_index, float* x_un, float* y_un, int32_t n);
+int hfb_image_bounds(hfb_ctx* ctx, int32_t width, int32_t height, float* bounds);
+
 /* Debug / parity hook: the tensor-core GEMM primitive on caller data (fp16 operands, fp32 result [B*H*W][N]).
  * A: [B*H*W][K] (NHWC when conv3x3), Wt: [N][conv3x3 ? 9K : K]; use_tc = 0 runs the CUDA-core cross-check kernel. */
 int hfb_debug_gemm(hfb_ctx* ctx, const float* A, int B, int H, int W, int K, const float* Wt, int N, const float* bias,

@@ -177,3 +177,53 @@ def concat_levels(per_level: list, scale_factor: float):
         ds.append(f["descriptors"])
     return {"x": np.concatenate(xs), "y": np.concatenate(ys), "response": np.concatenate(rs),
             "octave": np.concatenate(octs), "descriptors": np.concatenate(ds, axis=0)}
+
+
+def image_bounds(width, height, K, dist):
+    """Frame::ComputeImageBounds (src/Frame.cc:796-825): (mnMinX, mnMaxX, mnMinY, mnMaxY) from the undistorted image corners
+    (0,0), (cols,0), (0,rows), (cols,rows); the plain rectangle without distortion."""
+    dist = np.asarray(dist, np.float32).reshape(-1)
+    if dist.size == 0 or dist[0] == 0.0:
+        return np.array([0.0, width, 0.0, height], np.float32)
+    cx = np.array([0, width, 0, width], np.float32)
+    cy = np.array([0, 0, height, height], np.float32)
+    ux, uy = undistort_points(cx, cy, K, dist)
+    return np.array([min(ux[0], ux[2]), max(ux[1], ux[3]), min(uy[0], uy[1]), max(uy[2], uy[3])], np.float32)
+
+
+def undistort_points(x, y, K, dist):
+    """Frame::UndistortKeyPoints (src/Frame.cc:760-793): ``cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK)`` on the
+    N x 2 float keypoint coordinates; the identity when ``dist[0] == 0`` (:762-766).  OpenCV is a third-party dependency of
+    the reference (CMakeLists.txt: OpenCV 4.x; not under /root/reference), so this restates its published algorithm
+    (``cvUndistortPointsInternal``, calib3d/src/undistort.dispatch.cpp: normalise, 5 fixed-point iterations of the inverse
+    Brown-Conrady model in double -- the 6-argument overload's criteria are TermCriteria(COUNT, 5, 0.01) -- re-project with
+    P = K, round to float) and is pinned bit for bit to ``cv2.undistortPoints`` in tests/test_oracle_pins.py.
+    K = (fx, fy, cx, cy) float32, dist = (k1, k2, p1, p2[, k3]) float32."""
+    x = np.asarray(x, np.float32)
+    y = np.asarray(y, np.float32)
+    dist = np.asarray(dist, np.float32).reshape(-1)
+    if dist.size == 0 or dist[0] == 0.0:
+        return x.copy(), y.copy()
+    fx, fy, cx, cy = [float(np.float32(v)) for v in K]
+    k = np.zeros(12, np.float64)
+    k[:dist.size] = dist.astype(np.float64)
+    ifx, ify = 1.0 / fx, 1.0 / fy
+    u, v = x.astype(np.float64), y.astype(np.float64)
+    xn = (u - cx) * ifx
+    yn = (v - cy) * ify
+    x0, y0 = xn.copy(), yn.copy()
+    alive = np.ones(xn.shape, bool)
+    for _ in range(5):
+        r2 = xn * xn + yn * yn
+        icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+        gave_up = alive & (icdist < 0)       # OpenCV: x = (u - cx) * ifx; y = (v - cy) * ify; break
+        dx = 2 * k[2] * xn * yn + k[3] * (r2 + 2 * xn * xn) + k[8] * r2 + k[9] * r2 * r2
+        dy = k[2] * (r2 + 2 * yn * yn) + 2 * k[3] * xn * yn + k[10] * r2 + k[11] * r2 * r2
+        step = alive & ~gave_up
+        xn = np.where(step, (x0 - dx) * icdist, np.where(gave_up, x0, xn))
+        yn = np.where(step, (y0 - dy) * icdist, np.where(gave_up, y0, yn))
+        alive = step
+    xx = fx * xn + 0.0 * yn + cx
+    yy = 0.0 * xn + fy * yn + cy
+    ww = 1.0 / (0.0 * xn + 0.0 * yn + 1.0)
+    return (xx * ww).astype(np.float32), (yy * ww).astype(np.float32)

@@ -167,6 +167,23 @@ int main(int argc, char** argv) {
     wr(dir + "/out_lba_points.bin", points.data(), points.size());
     wr(dir + "/out_lba_outlier.bin", lout.data(), lout.size());
   }
+  // 7. Frame: calibration-dependent steps on the single-level keypoints
+  {
+    const std::vector<float> cam = rd<float>(dir + "/in_cam.bin");      // fx fy cx cy k1 k2 p1 p2
+    cv::Mat dist(4, 1, CV_32F);
+    std::memcpy(dist.data, cam.data() + 4, 16);
+    if (!HFNetB200Frame::SetCamera(ctx, cam[0], cam[1], cam[2], cam[3], dist)) return 11;
+    const std::vector<float> xyr = rd<float>(dir + "/out_single_xyr.bin");   // mvKeys of the single-level Detect above
+    std::vector<cv::KeyPoint> kps(xyr.size() / 3), un;
+    for (size_t i = 0; i < kps.size(); ++i) { kps[i].pt.x = xyr[3 * i]; kps[i].pt.y = xyr[3 * i + 1]; kps[i].response = xyr[3 * i + 2]; }
+    if (!HFNetB200Frame::UndistortKeyPoints(ctx, kps, un)) return 13;
+    std::vector<float> o;
+    for (size_t i = 0; i < un.size(); ++i) { o.push_back(un[i].pt.x); o.push_back(un[i].pt.y); o.push_back(un[i].response); }
+    float b[4];
+    if (!HFNetB200Frame::ComputeImageBounds(ctx, W, H, b[0], b[1], b[2], b[3])) return 14;
+    o.insert(o.end(), b, b + 4);
+    wr(dir + "/out_undistorted.bin", o.data(), o.size());
+  }
   for (BaseModel* m : models) delete m;
   std::printf("SHIM_RUN_OK\n");
   return 0;

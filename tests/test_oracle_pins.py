@@ -246,3 +246,32 @@ def test_c_pose_optimization_equals_numpy_oracle():
         # does not
         assert c["n_inliers"] == ninl
         assert np.array_equal(c["outlier"], outl) and np.abs(c["pose"] - pose).max() < 1e-9
+
+
+def test_undistort_points_equals_cv2_bit_exact():
+    """select_ref.undistort_points restates cv::undistortPoints(pts, pts, K, dist, noArray(), K) -- the call of
+    Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:778, 809); OpenCV is not in /root/reference, so the pin is
+    the installed cv2 itself: 4-, 5-, 8- and 12-coefficient vectors, points outside the image, and a lens strong enough
+    to reach OpenCV's icdist < 0 bail-out."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    cams = [((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)),
+            ((190.978, 190.973, 254.932, 256.897), (-0.1, 0.02, 0.001, -0.0005, 0.003)),
+            ((300.0, 300.0, 320.0, 240.0), (-0.9, 0.1, 0.01, 0.01, 0.0, 0.3, 0.01, 0.002)),
+            ((300.0, 300.0, 320.0, 240.0), (-0.4, 0.1, 0.01, 0.01, 0.0, 0.3, 0.01, 0.002, 1e-3, 2e-3, -1e-3, 5e-4))]
+    for K, dist in cams:
+        x = rng.uniform(-50, 800, 4000).astype(np.float32)
+        y = rng.uniform(-50, 530, 4000).astype(np.float32)
+        Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float32)
+        d = np.array(dist, np.float32)
+        ref = cv2.undistortPoints(np.stack([x, y], 1).reshape(-1, 1, 2), Km, d, None, Km).reshape(-1, 2)
+        with np.errstate(all="ignore"):
+            ux, uy = select_ref.undistort_points(x, y, K, d)
+            b = select_ref.image_bounds(752, 480, K, d)
+        assert np.array_equal(ux, ref[:, 0], equal_nan=True) and np.array_equal(uy, ref[:, 1], equal_nan=True)
+        corners = cv2.undistortPoints(np.array([[[0, 0]], [[752, 0]], [[0, 480]], [[752, 480]]], np.float32), Km, d, None, Km)
+        c = corners.reshape(4, 2)
+        exp = [min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])]
+        assert np.array_equal(b, np.array(exp, np.float32), equal_nan=True)
+    ux, uy = select_ref.undistort_points(x, y, cams[0][0], (0.0, 0.3, 0.0, 0.0))          # src/Frame.cc:762-766
+    assert np.array_equal(ux, x) and np.array_equal(uy, y)

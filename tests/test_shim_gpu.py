@@ -54,6 +54,9 @@ def test_cpp_shims_run_and_equal_the_ctypes_path(native_lib, weights_blob, tmp_p
     lp["fixed"].astype(np.uint8).tofile(d / "in_lba_fixed.bin"); lp["cam_idx"].astype(np.int32).tofile(d / "in_lba_cam.bin")
     lp["pt_idx"].astype(np.int32).tofile(d / "in_lba_pt.bin"); lp["obs"].astype(np.float64).tofile(d / "in_lba_obs.bin")
     lp["inv_sigma2"].astype(np.float64).tofile(d / "in_lba_is2.bin")
+    cam = np.array([458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)
+    cam[:4] *= W / 752.0
+    cam.tofile(d / "in_cam.bin")
     r = subprocess.run([str(exe), str(d), str(H), str(W), str(L), str(n_single), str(thr)] + [str(b) for b in budgets],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "SHIM_RUN_OK" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-2000:])
@@ -69,7 +72,13 @@ def test_cpp_shims_run_and_equal_the_ctypes_path(native_lib, weights_blob, tmp_p
 
     with Context(height=H, width=W, n_levels=1, max_keypoints=8192, max_batch=1) as c1:
         c1.load_weights(weights_blob)
-        check("single", c1.extract(img, [n_single], thr))
+        single = c1.extract(img, [n_single], thr)
+        check("single", single)
+        c1.set_camera(cam[:4], cam[4:])
+        xu, yu = c1.undistort_points(single["x"], single["y"])
+        und = _read(d, "undistorted", np.float32)
+        assert np.array_equal(und[:-4].reshape(-1, 3), np.stack([xu, yu, single["response"]], 1))
+        assert np.array_equal(und[-4:], c1.image_bounds(W, H)) and not np.array_equal(xu, single["x"])
     with Context(height=H, width=W, n_levels=L, scale_factor=1.2, max_keypoints=1024, max_batch=1) as c4:
         c4.load_weights(weights_blob)
         fused = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in c4.extract(img, budgets, thr).items()}
