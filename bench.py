@@ -576,6 +576,35 @@ def extra_loopdb(torch, dist, ctx, dev, pk, world, rank, n_db, barrier, maxred, 
     return out
 
 
+def host_transfer_ceiling(torch, dev, barrier, maxred, d2h_bytes: int, h2d_bytes: int, reps: int = 200):
+    """What the box's host path gives every rank when all ranks move one call's results device to host and one call's frames
+    host to device at the same time (page-locked buffers, both directions concurrently, nothing else running): the upper
+    bound of the end-to-end arm at this GPU count (tools/pcie_bw.py is the stand-alone version)."""
+    h_out = [torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h_in = [torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def loop(n):
+        for i in range(n):
+            with torch.cuda.stream(s1):
+                h_out[i & 1].copy_(d_out, non_blocking=True)
+            with torch.cuda.stream(s2):
+                d_in.copy_(h_in[i & 1], non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    loop(10)
+    barrier()
+    t0 = time.perf_counter()
+    loop(reps)
+    dt = maxred(time.perf_counter() - t0)
+    return {"gbs_per_gpu": reps * (d2h_bytes + h2d_bytes) / dt / 1e9, "ms_per_call_transfers": 1e3 * dt / reps,
+            "bytes_per_call": d2h_bytes + h2d_bytes,
+            "note": "every rank copies one call's outputs D2H and inputs H2D concurrently (pinned memory, slowest rank); the "
+                    "end-to-end arm cannot finish a call faster than this on this box"}
+
+
 # ---------------------------------------------------------------------------------------------------- B200 arm
 def main_gpu(args):
     import torch
@@ -794,6 +823,11 @@ def main_gpu(args):
     extra["single_stream"] = {"device_ms_per_frame": ms1_dev, "host_api_ms_per_frame": ms1_host,
                               "frames_per_s_host_api": 1e3 / ms1_host,
                               "note": "one frame per call, streaming association with the previous call's frame"}
+
+    ceil = host_transfer_ceiling(torch, dev, barrier, maxred, d2h // NB, h2d // NB)
+    ceil["frames_per_s_bound"] = world * B / (ceil["ms_per_call_transfers"] / 1e3)
+    ceil["e2e_fraction_of_bound"] = e2e / ceil["frames_per_s_bound"]
+    extra["host_transfer_ceiling"] = ceil
 
     if not args.skip_extra:
         if world == 1:

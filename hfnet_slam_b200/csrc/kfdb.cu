@@ -16,7 +16,9 @@ struct hfb_kfdb {
   float* d_scores = nullptr;     // [KFDB_QB][capacity] scores of the last scan
   float* d_query = nullptr;      // [KFDB_QB][dim]
   unsigned int* d_best = nullptr;  // [KFDB_QB] ordered-uint max score
-  int* d_ncand = nullptr;
+  int* d_ncand = nullptr;        // [0] candidate count, [1] completion ticket of the single-query tail
+  // d_best[0] and d_ncand[0..1] are ZERO at rest: the last kernel of a query (compact tail / shard finish) resets them, so
+  // a query costs no memset launches
   int* d_cand_slot = nullptr;    // [capacity]
   float* d_cand_score = nullptr; // [capacity]
   std::vector<int64_t> ids;      // slot -> id
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(256) kfdb_scan_kernel(const float* __restrict_
                                                         const float* __restrict__ q, int nq, float* __restrict__ scores,
                                                         int score_stride, unsigned int* __restrict__ best) {
   extern __shared__ float s_q[];  // [QB][dim]
+  pdl_launch_dependents();        // the successors wait (griddepcontrol.wait) for this grid to finish: only their launch overlaps
+  pdl_wait();
   for (int i = threadIdx.x; i < QB * dim; i += blockDim.x) s_q[i] = (i / dim) < nq ? q[i] : 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -437,24 +441,52 @@ __global__ void kfdb_pair_select_kernel(const int2* __restrict__ pairs, const in
 }
 
 // candidates of query 0: score > max(floor, rel*best), strict (KeyFrameDatabase.cc:98-104, 190-192)
-__global__ void kfdb_compact_kernel(const float* __restrict__ scores, int n, const unsigned int* __restrict__ best,
+// head != null (single-GPU query): the block that finishes last writes {count, best bits, first KFDB_HEAD slots, their
+// scores} straight into the caller's page-locked host block (mapped memory: no copy operation) and puts best / count /
+// ticket back to zero for the next query.
+__global__ void kfdb_compact_kernel(const float* __restrict__ scores, int n, unsigned int* __restrict__ best,
                                     float rel, float floor_, int* __restrict__ ncand, int* __restrict__ slot,
-                                    float* __restrict__ sc) {
+                                    float* __restrict__ sc, int* __restrict__ head) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float b = __uint_as_float(best[0]);
-  const float thr = fmaxf(floor_, __fmul_rn(b, rel));
-  const float s = scores[i];
-  if (s > thr) {
-    const int p = atomicAdd(ncand, 1);
-    slot[p] = i;
-    sc[p] = s;
+  const unsigned int bb = best[0];
+  if (i < n) {
+    const float thr = fmaxf(floor_, __fmul_rn(__uint_as_float(bb), rel));
+    const float s = scores[i];
+    if (s > thr) {
+      const int p = atomicAdd(ncand, 1);
+      slot[p] = i;
+      sc[p] = s;
+    }
   }
+  if (!head) return;
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ncand + 1, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nc = *reinterpret_cast<volatile int*>(ncand);
+  for (int j = threadIdx.x; j < min(nc, KFDB_HEAD); j += blockDim.x) {
+    head[2 + j] = __ldcg(slot + j);
+    head[2 + KFDB_HEAD + j] = __float_as_int(__ldcg(sc + j));
+  }
+  if (threadIdx.x == 0) {
+    head[0] = nc;
+    head[1] = (int)bb;
+    best[0] = 0u;
+    ncand[0] = 0;
+    ncand[1] = 0;
+  }
+  __threadfence_system();
 }
 
-static int kfdb_scan(hfb_kfdb* db, const float* d_query, int nq, float* d_scores, int stride, unsigned int* d_best) {
+static int kfdb_scan(hfb_kfdb* db, const float* d_query, int nq, float* d_scores, int stride, unsigned int* d_best,
+                     bool zero_best = true) {
   hfb_ctx* ctx = db->ctx;
-  HFB_CUDA(ctx, cudaMemsetAsync(d_best, 0, sizeof(unsigned int) * nq, ctx->stream));
+  if (zero_best) HFB_CUDA(ctx, cudaMemsetAsync(d_best, 0, sizeof(unsigned int) * nq, ctx->stream));
   if (db->size == 0) return HFB_OK;
   const size_t smem = (size_t)KFDB_QB * db->dim * sizeof(float);
   static SmemOptIn optin_batch, optin_one;
@@ -466,13 +498,11 @@ static int kfdb_scan(hfb_kfdb* db, const float* d_query, int nq, float* d_scores
     int blocks = std::min(ctx->n_sm * 4, ceil_div(db->size, 8));
     if (blocks >= ctx->n_sm) blocks = blocks / ctx->n_sm * ctx->n_sm;
     if (nb == 1)
-      kfdb_scan_kernel<1><<<blocks, 256, (size_t)db->dim * 4, ctx->stream>>>(
-          db->d_rows, db->size, db->dim, d_query + (size_t)q0 * db->dim, 1, d_scores + (size_t)q0 * stride, stride,
-          d_best + q0);
+      hfb_launch(ctx, kfdb_scan_kernel<1>, dim3(blocks), dim3(256), (size_t)db->dim * 4, (const float*)db->d_rows, db->size,
+                 db->dim, d_query + (size_t)q0 * db->dim, 1, d_scores + (size_t)q0 * stride, stride, d_best + q0);
     else
-      kfdb_scan_kernel<KFDB_QB><<<blocks, 256, smem, ctx->stream>>>(db->d_rows, db->size, db->dim,
-                                                                   d_query + (size_t)q0 * db->dim, nb,
-                                                                   d_scores + (size_t)q0 * stride, stride, d_best + q0);
+      hfb_launch(ctx, kfdb_scan_kernel<KFDB_QB>, dim3(blocks), dim3(256), smem, (const float*)db->d_rows, db->size, db->dim,
+                 d_query + (size_t)q0 * db->dim, nb, d_scores + (size_t)q0 * stride, stride, d_best + q0);
     HFB_CHECK_LAUNCH(ctx, "kfdb_scan");
   }
   return HFB_OK;
@@ -507,7 +537,9 @@ extern "C" int hfb_kfdb_create(hfb_ctx* ctx, int32_t dim, int32_t capacity, hfb_
   if (e == cudaSuccess) e = cudaMalloc(&db->d_scores, (size_t)KFDB_QB * capacity * 4);
   if (e == cudaSuccess) e = cudaMalloc(&db->d_query, (size_t)KFDB_QB * dim * 4);
   if (e == cudaSuccess) e = cudaMalloc(&db->d_best, KFDB_QB * sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMalloc(&db->d_ncand, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&db->d_ncand, 2 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(db->d_best, 0, KFDB_QB * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(db->d_ncand, 0, 2 * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&db->d_cand_slot, (size_t)capacity * 4);
   if (e == cudaSuccess) e = cudaMalloc(&db->d_cand_score, (size_t)capacity * 4);
   if (e == cudaSuccess) e = cudaMalloc(&db->d_ids, (size_t)capacity * 8);
@@ -649,18 +681,22 @@ static int kfdb_query_common(hfb_kfdb* db, const float* query, float rel, float 
   if (db->size == 0) return HFB_OK;
   memcpy(db->h_query, query, (size_t)db->dim * 4);      // page-locked staging: the H2D below is a plain DMA
   HFB_CUDA(ctx, cudaMemcpyAsync(db->d_query, db->h_query, (size_t)db->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
-  HFB_TRY(kfdb_scan(db, db->d_query, 1, db->d_scores, db->capacity, db->d_best));
-  HFB_CUDA(ctx, cudaMemsetAsync(db->d_ncand, 0, sizeof(int), ctx->stream));
-  kfdb_compact_kernel<<<ceil_div(db->size, 256), 256, 0, ctx->stream>>>(db->d_scores, db->size, db->d_best, rel, floor_,
-                                                                       db->d_ncand, db->d_cand_slot, db->d_cand_score);
+  // three stream operations per query: the scan finds best[0] zeroed by the previous query's tail, the compaction's last
+  // block writes count, best and the head of the candidate list into the page-locked block itself and re-zeroes the state
+  HFB_TRY(kfdb_scan(db, db->d_query, 1, db->d_scores, db->capacity, db->d_best, false));
+  hfb_launch(ctx, kfdb_compact_kernel, dim3(ceil_div(db->size, 256)), dim3(256), 0, (const float*)db->d_scores, db->size,
+             db->d_best, rel, floor_, db->d_ncand, db->d_cand_slot, db->d_cand_score, db->h_head);
   HFB_CHECK_LAUNCH(ctx, "kfdb_compact");
-  // count, best and the head of the candidate list in one burst, one synchronisation (longer lists: a second fetch)
   const int head = std::min(KFDB_HEAD, db->size);
-  HFB_CUDA(ctx, cudaMemcpyAsync(db->h_head, db->d_ncand, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  HFB_CUDA(ctx, cudaMemcpyAsync(db->h_head + 1, db->d_best, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-  HFB_CUDA(ctx, cudaMemcpyAsync(db->h_head + 2, db->d_cand_slot, (size_t)head * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  HFB_CUDA(ctx, cudaMemcpyAsync(db->h_head + 2 + KFDB_HEAD, db->d_cand_score, (size_t)head * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  HFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  {
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {   // the zero-at-rest invariant may be broken: restore it before reporting
+      cudaMemsetAsync(db->d_best, 0, KFDB_QB * sizeof(unsigned int), ctx->stream);
+      cudaMemsetAsync(db->d_ncand, 0, 2 * sizeof(int), ctx->stream);
+      ctx->set_error(std::string("kfdb query: ") + cudaGetErrorString(e));
+      return HFB_ERR_CUDA;
+    }
+  }
   const int nc = db->h_head[0];
   memcpy(best_score, db->h_head + 1, 4);
   if (nc > 0) {
@@ -940,7 +976,7 @@ extern "C" int hfb_kfdb_query_batch(hfb_kfdb* db, const float* queries, int32_t 
 struct ShardRecHdr { float best; int count; int overflow; int pad; };
 struct ShardEntry { float score; int pad; long long id; };
 
-__global__ void __launch_bounds__(256) kfdb_shard_finish_kernel(const unsigned int* __restrict__ best, const int* __restrict__ ncand,
+__global__ void __launch_bounds__(256) kfdb_shard_finish_kernel(unsigned int* __restrict__ best, int* __restrict__ ncand,
                                                                 const int* __restrict__ cand_slot, const float* __restrict__ cand_score,
                                                                 const long long* __restrict__ ids, int k, float rel, float floor_,
                                                                 int rank, int world, unsigned int epoch, uint8_t* const* peers,
@@ -949,9 +985,12 @@ __global__ void __launch_bounds__(256) kfdb_shard_finish_kernel(const unsigned i
   __shared__ int s_count, s_timeout;
   __shared__ float s_best;
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   ShardRecHdr* hdr = reinterpret_cast<ShardRecHdr*>(s_rec);
   ShardEntry* ent = reinterpret_cast<ShardEntry*>(s_rec + 16);
   const int n = ncand[0];
+  const unsigned int my_best = best[0];
   for (int i = tid; i < rec_bytes / 4; i += blockDim.x) reinterpret_cast<int*>(s_rec)[i] = 0;
   if (tid == 0) { s_count = 0; s_timeout = 0; }
   __syncthreads();
@@ -977,11 +1016,15 @@ __global__ void __launch_bounds__(256) kfdb_shard_finish_kernel(const unsigned i
     }
   }
   if (tid == 0) {
-    hdr->best = __uint_as_float(best[0]);
+    hdr->best = __uint_as_float(my_best);
     hdr->count = min(n, k);
     hdr->overflow = n > k;
   }
   __syncthreads();
+  if (tid == 0) {   // every read of the scan's state is done: zero at rest for the next query
+    best[0] = 0u;
+    ncand[0] = 0;
+  }
   // push to every rank's inbox slot [parity][rank] (own inbox included), then publish the epoch
   const int parity = epoch & 1u;
   const size_t slot_off = ((size_t)parity * world + rank) * rec_bytes;
@@ -1049,6 +1092,7 @@ __global__ void __launch_bounds__(256) kfdb_shard_finish_kernel(const unsigned i
     oh->overflow = overflow;
     oh->pad = s_timeout;
   }
+  __threadfence_system();   // `out` is page-locked host memory
 }
 
 extern "C" int hfb_kfdb_shard_setup(hfb_kfdb* db, int32_t rank, int32_t world, int32_t k, void* ipc_handle_out) {
@@ -1128,21 +1172,19 @@ extern "C" int hfb_kfdb_query_sharded_begin(hfb_kfdb* db, const float* query, fl
   db->h_scores_valid = false;
   memcpy(db->h_query, query, (size_t)db->dim * 4);
   HFB_CUDA(ctx, cudaMemcpyAsync(db->d_query, db->h_query, (size_t)db->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
-  HFB_TRY(kfdb_scan(db, db->d_query, 1, db->d_scores, db->capacity, db->d_best));
-  HFB_CUDA(ctx, cudaMemsetAsync(db->d_ncand, 0, sizeof(int), ctx->stream));
+  // four stream operations: H2D of the query, scan, compaction, finish (record exchange + merge; it writes the merged
+  // list straight into the page-locked result block and puts best / count back to zero for the next query)
+  HFB_TRY(kfdb_scan(db, db->d_query, 1, db->d_scores, db->capacity, db->d_best, false));
   if (db->size > 0) {
-    kfdb_compact_kernel<<<ceil_div(db->size, 256), 256, 0, ctx->stream>>>(db->d_scores, db->size, db->d_best, rel, floor_,
-                                                                         db->d_ncand, db->d_cand_slot, db->d_cand_score);
+    hfb_launch(ctx, kfdb_compact_kernel, dim3(ceil_div(db->size, 256)), dim3(256), 0, (const float*)db->d_scores, db->size,
+               db->d_best, rel, floor_, db->d_ncand, db->d_cand_slot, db->d_cand_score, (int*)nullptr);
     HFB_CHECK_LAUNCH(ctx, "kfdb_compact");
   }
   ++db->epoch;
-  kfdb_shard_finish_kernel<<<1, 256, db->rec_bytes, ctx->stream>>>(db->d_best, db->d_ncand, db->d_cand_slot, db->d_cand_score,
-                                                                  db->d_ids, db->shard_k, rel, floor_, db->rank, db->world,
-                                                                  db->epoch, db->d_peer_tab, db->d_inbox, (int)db->rec_bytes,
-                                                                  db->d_shard_out);
+  hfb_launch(ctx, kfdb_shard_finish_kernel, dim3(1), dim3(256), db->rec_bytes, db->d_best, db->d_ncand,
+             (const int*)db->d_cand_slot, (const float*)db->d_cand_score, (const long long*)db->d_ids, db->shard_k, rel, floor_,
+             db->rank, db->world, db->epoch, (uint8_t* const*)db->d_peer_tab, db->d_inbox, (int)db->rec_bytes, db->h_shard_out);
   HFB_CHECK_LAUNCH(ctx, "kfdb_shard_finish");
-  HFB_CUDA(ctx, cudaMemcpyAsync(db->h_shard_out, db->d_shard_out, 16 + 16 * (size_t)db->world * db->shard_k,
-                                cudaMemcpyDeviceToHost, ctx->stream));
   return HFB_OK;
 }
 

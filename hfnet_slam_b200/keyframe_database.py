@@ -68,11 +68,13 @@ class KeyFrameDatabase:
         """Returns (candidate ids ascending, their scores, best score): score > max(floor, rel*best), strict."""
         qq = np.ascontiguousarray(q, dtype=np.float32).reshape(self.dim)
         cap = max(len(self), 1)
-        ids = np.zeros(cap, np.int64)
-        sc = np.zeros(cap, np.float32)
+        buf = getattr(self, "_query_out", None)
+        if buf is None or len(buf[0]) < cap:       # output arrays kept across calls (a fresh 600 KB block per query costs more
+            buf = self._query_out = (np.zeros(max(cap, 1024), np.int64), np.zeros(max(cap, 1024), np.float32))   # than the call)
+        ids, sc = buf
         n, best = C.c_int32(), C.c_float()
         self.ctx.check(self.ctx.lib.hfb_kfdb_query(self.handle, ptr(qq, _f32p), rel, floor, ptr(ids, _i64p),
-                                                   ptr(sc, _f32p), cap, C.byref(n), C.byref(best)))
+                                                   ptr(sc, _f32p), len(ids), C.byref(n), C.byref(best)))
         return ids[:n.value].copy(), sc[:n.value].copy(), float(best.value)
 
     def query_batch(self, Q: np.ndarray, rel: float = 0.8, floor: float = 0.0, cap: int = 256):
