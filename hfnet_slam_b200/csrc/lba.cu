@@ -414,60 +414,81 @@ __global__ void lba_reduce2_kernel(const double* __restrict__ a, const double* _
 #define LBA_SOLVE_MAX_N 192
 __device__ __forceinline__ int lcol(int k, int N) { return k * N - k * (k - 1) / 2; }   // start of packed column k (rows k..N-1)
 
+// packed index -> column: lcol(k) = k (2N + 1 - k) / 2 <= q, closed form + integer fix-up
+__device__ __forceinline__ int lcol_inv(int q, int N) {
+  const float b = (float)(2 * N + 1);
+  int k = (int)((b - sqrtf(fmaxf(b * b - 8.f * (float)q, 0.f))) * 0.5f);
+  k = max(0, min(k, N - 1));
+  while (k > 0 && lcol(k, N) > q) --k;
+  while (k + 1 < N && lcol(k + 1, N) <= q) ++k;
+  return k;
+}
+#define T6(c, r) ((c) * 6 - (c) * ((c) - 1) / 2 + (r) - (c))   // 6 x 6 lower triangle packed by columns, r >= c
+
+#ifdef HFB_SOLVE_CLK   // phase cycle counters of the last launch (tools/ba_time.py prints them when the symbol exists)
+__device__ long long g_solve_clk[8];
+extern "C" int hfb_debug_solve_clocks(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_solve_clk, sizeof(g_solve_clk)); }
+#define SOLVE_CLK(i) do { if (threadIdx.x == 0) g_solve_clk[i] = clock64(); } while (0)
+#else
+#define SOLVE_CLK(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda) {
   extern __shared__ double sL[];                 // lower triangle packed BY COLUMNS: L[i][k] at lcol(k) + i - k, so the
                                                  // rows i = j + tid of one column step read consecutive words
   __shared__ double s_b[LBA_SOLVE_MAX_N], s_y[LBA_SOLVE_MAX_N], s_invd[LBA_SOLVE_MAX_N];
+  __shared__ double s_linv[LBA_SOLVE_MAX_N / 6][21];   // inverses of the factored diagonal blocks (backward substitution)
   __shared__ int s_fail;
   const int N = 6 * d.n_opt, t = threadIdx.x;
   const int total = N * (N + 1) / 2;
   unsigned char* col_of = reinterpret_cast<unsigned char*>(sL + total);   // packed index -> column
-  for (int k = 0; k < N; ++k)
-    for (int i = k + t; i < N; i += 256) col_of[lcol(k, N) + i - k] = (unsigned char)k;
+  SOLVE_CLK(0);
+  for (int q = t; q < total; q += 256) col_of[q] = (unsigned char)lcol_inv(q, N);
   for (int i = t; i < N; i += 256) s_b[i] = d.bs[i];
   if (t == 0) s_fail = 0;
-  __syncthreads();
-  for (int q = t; q < total; q += 256) {         // Hs is bitwise symmetric: element (r, c), r >= c, read as Hs[c][r]
-    const int c = col_of[q];
-    sL[q] = d.Hs[(size_t)c * N + c + q - lcol(c, N)];
+  // Hs is bitwise symmetric: the lower triangle is read row by row (coalesced), eight loads in flight per thread
+#pragma unroll 8
+  for (int q = t; q < N * N; q += 256) {
+    const int r = q / N, c = q - r * N;
+    if (c <= r) sL[lcol(c, N) + r - c] = __ldg(d.Hs + q);
   }
   __syncthreads();
-  // Blocked right-looking Cholesky on the 6 x 6 camera blocks (N = 6 n_opt) with one block of look-ahead: per block
-  // column (i) one thread per row below solves its 1 x 6 panel row, (ii) warps 1..7 apply the rank-6 update to the
-  // trailing triangle -- a CONTIGUOUS range of the column-packed array -- while warp 0 updates just the NEXT diagonal
-  // block and factors it (the only serial part: six dependent pivots), so the pivots hide behind the update.
+  // Blocked right-looking Cholesky on the 6 x 6 camera blocks (N = 6 n_opt) with one block of look-ahead.  Per block
+  // column: (i) one thread per row below solves its 1 x 6 panel row while thread 255 runs the forward substitution of
+  // this block (b is carried along like one more matrix row, so L y = b costs no pass of its own); (ii) warps 1..7 apply
+  // the rank-6 update to the trailing triangle -- a CONTIGUOUS range of the column-packed array -- and to b, while warp
+  // 0 updates just the NEXT diagonal block and one of its lanes factors it in registers (the only serial part: six
+  // dependent pivots), so the pivots hide behind the update.
   const int lane = t & 31;
-  auto factor_diag = [&](int j0) {                 // warp 0: in-place Cholesky of the 6 x 6 block at (j0, j0)
+  auto factor_diag = [&](int j0) {                 // ONE thread: in-place Cholesky of the 6 x 6 block at (j0, j0)
+    double a[21];
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int r = c; r < 6; ++r) a[T6(c, r)] = sL[lcol(j0 + c, N) + r - c];
+    bool fail = false;
+#pragma unroll
     for (int c = 0; c < 6; ++c) {
-      const int j = j0 + c, cj = lcol(j, N);
-      const double dj = sL[cj];
+      const double dj = a[T6(c, c)];
       const bool bad = !(dj > 0.0) || !isfinite(dj);
       const double inv = bad ? 0.0 : rsqrt(dj);
-      __syncwarp();
-      if (lane == 0) {
-        if (bad) s_fail = 1;
-        s_invd[j] = inv;
-        sL[cj] = bad ? 1.0 : dj * inv;
-      } else if (lane < 6 - c) {
-        sL[cj + lane] *= inv;                      // rows j + lane of column j inside the diagonal block
-      }
-      __syncwarp();
-      // remaining entries of the diagonal block: columns c2 in (c, 5], rows r2 in [c2, 5] (at most 15)
-      if (lane < 15) {
-        int c2 = c + 1, e = lane;
-        while (c2 < 6 && e >= 6 - c2) {
-          e -= 6 - c2;
-          ++c2;
-        }
-        if (c2 < 6) {
-          const int r2 = c2 + e;
-          sL[lcol(j0 + c2, N) + r2 - c2] -= sL[cj + r2 - c] * sL[cj + c2 - c];
-        }
-      }
-      __syncwarp();
+      fail |= bad;
+      s_invd[j0 + c] = inv;
+      a[T6(c, c)] = bad ? 1.0 : dj * inv;
+#pragma unroll
+      for (int r = c + 1; r < 6; ++r) a[T6(c, r)] *= inv;
+#pragma unroll
+      for (int c2 = c + 1; c2 < 6; ++c2)
+#pragma unroll
+        for (int r2 = c2; r2 < 6; ++r2) a[T6(c2, r2)] -= a[T6(c, r2)] * a[T6(c, c2)];
     }
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int r = c; r < 6; ++r) sL[lcol(j0 + c, N) + r - c] = a[T6(c, r)];
+    if (fail) s_fail = 1;
   };
-  if (t < 32 && N > 0) factor_diag(0);
+  SOLVE_CLK(1);
+  if (t == 0 && N > 0) factor_diag(0);
   __syncthreads();
   for (int j0 = 0; j0 < N; j0 += 6) {
     if (s_fail) break;                             // uniform: written before the last barrier
@@ -484,6 +505,16 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
         }
 #pragma unroll
         for (int c = 0; c < 6; ++c) sL[lcol(j0 + c, N) + i - (j0 + c)] = l[c];
+      } else if (t == 255) {                       // forward substitution of this block: y = L_jj^-1 b_j (N - 6 < 255)
+        double y[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          double v = s_b[j0 + c];
+#pragma unroll
+          for (int c1 = 0; c1 < c; ++c1) v -= sL[lcol(j0 + c1, N) + (c - c1)] * y[c1];
+          y[c] = v * s_invd[j0 + c];
+          s_y[j0 + c] = y[c];
+        }
       }
     }
     __syncthreads();
@@ -506,8 +537,17 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
           sL[lcol(cc, N) + r - cc] = acc;
         }
         __syncwarp();
-        factor_diag(j0 + 6);
+        if (lane == 0) factor_diag(j0 + 6);
       } else {
+        {
+          const int i = j0 + 6 + (t - 32);         // b below this block (N - 6 <= 186 rows: one pass of the 224 threads)
+          if (i < N) {
+            double v = s_b[i];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) v -= col[c][i] * s_y[j0 + c];
+            s_b[i] = v;
+          }
+        }
         for (int q = lcol(j0 + 6, N) + (t - 32); q < total; q += 224) {
           const int cc = col_of[q];
           const int r = cc + q - lcol(cc, N);
@@ -522,38 +562,42 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
     __syncthreads();
   }
   __syncthreads();
+  SOLVE_CLK(2);
   if (!s_fail) {
-    // blocked substitutions: thread 0 solves the 6 x 6 triangle of a camera, then every remaining row takes the rank-6
-    // correction; the solved entries go to a second array so nothing that is still being read is overwritten
-    for (int j0 = 0; j0 < N; j0 += 6) {            // forward L y = b
-      if (t == 0) {
-        double y[6];
-        for (int c = 0; c < 6; ++c) {
-          double v = s_b[j0 + c];
-          for (int c1 = 0; c1 < c; ++c1) v -= sL[lcol(j0 + c1, N) + (c - c1)] * y[c1];
-          y[c] = v * s_invd[j0 + c];
-          s_y[j0 + c] = y[c];
-        }
-      }
-      __syncthreads();
-      const int i = j0 + 6 + t;
-      if (i < N) {
-        double v = s_b[i];
+    // inverses of the diagonal blocks, one thread per camera (lower triangular, column by column)
+    if (t < d.n_opt) {
+      const int j0 = 6 * t;
+      double l[21], m[21];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) v -= sL[lcol(j0 + c, N) + i - (j0 + c)] * s_y[j0 + c];
-        s_b[i] = v;
-      }
-      __syncthreads();
-    }
-    for (int j0 = N - 6; j0 >= 0; j0 -= 6) {       // backward L^T x = y
-      if (t == 0) {
-        double x[6];
-        for (int c = 5; c >= 0; --c) {
-          double v = s_y[j0 + c];
-          for (int c1 = c + 1; c1 < 6; ++c1) v -= sL[lcol(j0 + c, N) + (c1 - c)] * x[c1];   // L[j0+c1][j0+c]
-          x[c] = v * s_invd[j0 + c];
-          s_b[j0 + c] = x[c];
+      for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int r = c; r < 6; ++r) l[T6(c, r)] = sL[lcol(j0 + c, N) + r - c];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        m[T6(c, c)] = s_invd[j0 + c];
+#pragma unroll
+        for (int r = c + 1; r < 6; ++r) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = c; k < r; ++k) acc += l[T6(k, r)] * m[T6(c, k)];
+          m[T6(c, r)] = -acc * s_invd[j0 + r];
         }
+      }
+#pragma unroll
+      for (int e = 0; e < 21; ++e) s_linv[t][e] = m[e];
+    }
+    __syncthreads();
+    SOLVE_CLK(3);
+    // backward L^T x = y by blocks: six threads apply the block inverse (x_c = sum_{r >= c} Linv[r][c] v_r), then every
+    // row above takes the rank-6 correction
+    for (int j0 = N - 6; j0 >= 0; j0 -= 6) {
+      if (t < 6) {
+        const double* m = s_linv[j0 / 6];
+        double x = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+          if (r >= t) x += m[T6(t, r)] * s_y[j0 + r];
+        s_b[j0 + t] = x;
       }
       __syncthreads();
       if (t < j0) {
@@ -565,8 +609,8 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
       __syncthreads();
     }
   }
+  SOLVE_CLK(4);
   for (int i = t; i < N; i += 256) d.xp[i] = s_fail ? 0.0 : s_b[i];
-  __syncthreads();
   // trial poses: every camera copied, optimisable ones updated
   for (int i = t; i < d.n_cams * 7; i += 256) d.poses_t[i] = d.poses[i];
   __syncthreads();
@@ -575,14 +619,20 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
     for (int i = 0; i < 6; ++i) u[i] = s_fail ? 0.0 : s_b[6 * t + i];
     const int c = d.opt_cams[t];
     po_pose_oplus(d.poses + 7 * (size_t)c, u, d.poses_t + 7 * (size_t)c);
-  }
-  if (t == 0) {
+  } else if (t >= 224) {                           // the camera part of the gain-ratio denominator: fixed-order warp sum
     double sc = 0;
     if (!s_fail)
-      for (int i = 0; i < N; ++i) sc += s_b[i] * (lambda * s_b[i] + d.bp[i]);
-    d.scal[4] = sc;
-    d.scal[5] = s_fail ? 0.0 : 1.0;
+      for (int i = lane; i < N; i += 32) sc += s_b[i] * (lambda * s_b[i] + d.bp[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      sc += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(sc), o), __shfl_xor_sync(0xffffffffu, __double2loint(sc), o));
+    if (lane == 0) {
+      d.scal[4] = sc;
+      d.scal[5] = s_fail ? 0.0 : 1.0;
+    }
   }
+  __syncthreads();
+  SOLVE_CLK(5);
 }
 
 // ------------------------------------------------------------------------------------------------ host helpers
@@ -877,23 +927,33 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   double* chi2_other = d.chi2_b;
   double initial_chi = 0.0, current_chi = 0.0;
   double scal[6];
-  // chi2 at the initial estimate (iterations == 0 or immediate stop still reports it)
-  if (d.n_points > 0) {
-    lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, d.poses, d.points, chi2_last, 1);
-    HFB_CHECK_LAUNCH(ctx, "lba_errors");
-  }
-  lba_reduce_kernel<<<1, 1024, 0, st>>>(d.rho_pt, d.n_points, d.scal, 0, d, 0);
-  HFB_CHECK_LAUNCH(ctx, "lba_reduce");
-  HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 8, cudaMemcpyDeviceToHost, st));
-  HFB_CUDA(ctx, cudaStreamSynchronize(st));
-  initial_chi = current_chi = scal[0];
-  for (int it = 0; it < iterations; ++it) {
-    if (terminate()) break;
-    HFB_TRY(lba_build(ctx, d, chi2_last, it == 0));
-    HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 16, cudaMemcpyDeviceToHost, st));
-    if (N) HFB_CUDA(ctx, cudaMemcpyAsync(bp.data(), d.bp, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+  // chi2 at the initial estimate: the first linearisation computes it too, so the separate evaluation only runs when
+  // there is no first iteration (iterations == 0 or an immediate stop still report it)
+  const bool first_build_has_chi = iterations > 0 && !terminate();
+  if (!first_build_has_chi) {
+    if (d.n_points > 0) {
+      lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, d.poses, d.points, chi2_last, 1);
+      HFB_CHECK_LAUNCH(ctx, "lba_errors");
+    }
+    lba_reduce_kernel<<<1, 1024, 0, st>>>(d.rho_pt, d.n_points, d.scal, 0, d, 0);
+    HFB_CHECK_LAUNCH(ctx, "lba_reduce");
+    HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 8, cudaMemcpyDeviceToHost, st));
     HFB_CUDA(ctx, cudaStreamSynchronize(st));
-    current_chi = scal[0];
+    initial_chi = current_chi = scal[0];
+  }
+  for (int it = 0; it < iterations; ++it) {
+    if (!(it == 0 && first_build_has_chi) && terminate()) break;
+    HFB_TRY(lba_build(ctx, d, chi2_last, it == 0));
+    // The host needs the linearisation's scalars only at the first iteration (lambda from the largest diagonal entry) or
+    // when it solves the reduced system itself: afterwards the robust chi2 of the estimate IS the accepted trial's
+    // (same kernel, same summation order: bitwise equal), so later iterations enqueue straight through to the trial.
+    if (it == 0 || !dev_solve) {
+      HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 16, cudaMemcpyDeviceToHost, st));
+      if (N && !dev_solve) HFB_CUDA(ctx, cudaMemcpyAsync(bp.data(), d.bp, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+      HFB_CUDA(ctx, cudaStreamSynchronize(st));
+      current_chi = scal[0];
+      if (it == 0 && first_build_has_chi) initial_chi = current_chi;
+    }
     const double ini_chi = current_chi;
     if (it == 0) {
       lambda = user_lambda_init > 0 ? user_lambda_init : tau * scal[1];
