@@ -46,17 +46,29 @@ __device__ __forceinline__ void quat_to_R(const double* q, double* R) {
   R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
 }
 
-// One thread per landmark: errors, robust weights, Jacobians, Hll/bl, per-edge camera terms.
+__device__ __forceinline__ double lba_shfl_xor(double v, int o) {
+  return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o),
+                          __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
+}
+
+// LBA_PL lanes per landmark: errors, robust weights, Jacobians, per-edge camera terms; lane j of a landmark takes its edges
+// j, j + LBA_PL, ... and the landmark's sums (Hll, bl, rho) are joined by a fixed xor butterfly (bit-reproducible).
 // mode 0 = full linearisation; mode 1 = error evaluation only (chi2, rho).
+#define LBA_PL 8
 __global__ void lba_linearize_kernel(LbaDev d, const double* __restrict__ poses, const double* __restrict__ points,
                                      double* __restrict__ chi2_out, int mode) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= d.n_points) return;
-  const double X0 = points[3 * p], X1 = points[3 * p + 1], X2 = points[3 * p + 2];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = gt / LBA_PL, sub = gt % LBA_PL;
+  const bool live = p < d.n_points;            // whole groups of LBA_PL lanes are live or not; dead ones still shuffle
+  const int pp = live ? p : 0;
+  const double X0 = points[3 * pp], X1 = points[3 * pp + 1], X2 = points[3 * pp + 2];
   const double fx = d.K[0], fy = d.K[1], cx = d.K[2], cy = d.K[3];
   const double dsqr = d.delta * d.delta;
   double H0 = 0, H1 = 0, H2 = 0, H3 = 0, H4 = 0, H5 = 0, b0 = 0, b1 = 0, b2 = 0, rho_sum = 0;
-  for (int e = d.pt_ptr[p]; e < d.pt_ptr[p + 1]; ++e) {
+  const int e_end = live ? d.pt_ptr[pp + 1] : 0;
+  for (int e = (live ? d.pt_ptr[pp] : 0) + sub; e < e_end; e += LBA_PL) {
     const int c = d.edge_cam[e];
     const double* ps = poses + 7 * c;
     double R[9];
@@ -113,6 +125,16 @@ __global__ void lba_linearize_kernel(LbaDev d, const double* __restrict__ poses,
         for (int j = 0; j < 3; ++j) hpl[3 * i + j] = wo * (Jc[i] * Jp[j] + Jc[6 + i] * Jp[3 + j]);
     }
   }
+#pragma unroll
+  for (int o = LBA_PL / 2; o > 0; o >>= 1) {
+    rho_sum += lba_shfl_xor(rho_sum, o);
+    if (mode == 0) {                             // warp-uniform
+      H0 += lba_shfl_xor(H0, o); H1 += lba_shfl_xor(H1, o); H2 += lba_shfl_xor(H2, o);
+      H3 += lba_shfl_xor(H3, o); H4 += lba_shfl_xor(H4, o); H5 += lba_shfl_xor(H5, o);
+      b0 += lba_shfl_xor(b0, o); b1 += lba_shfl_xor(b1, o); b2 += lba_shfl_xor(b2, o);
+    }
+  }
+  if (!live || sub != 0) return;
   d.rho_pt[p] = rho_sum;
   if (mode == 0) {
     double* h = d.Hll + 6 * (size_t)p;
@@ -121,17 +143,14 @@ __global__ void lba_linearize_kernel(LbaDev d, const double* __restrict__ poses,
   }
 }
 
-__device__ __forceinline__ double lba_shfl_xor(double v, int o) {
-  return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o),
-                          __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
-}
-
 // One CTA per optimisable camera: Hpp (21 upper-triangular entries, mirrored) and bp (6) summed over the camera's edges.
 // Thread t accumulates edges t, t + 256, ... of the camera's (ascending) edge list; the 27 sums are then combined in a
 // fixed order -- register butterfly inside each warp (lane i ends with entry i), warps added in warp order -- so the
 // result is bit-reproducible without a serial walk over the ~10^3 edges of a keyframe.
 __global__ void __launch_bounds__(256) lba_camera_kernel(LbaDev d) {
   __shared__ double sh[8][32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int s = blockIdx.x, c = d.opt_cams[s], t = threadIdx.x, lane = t & 31, warp = t >> 5;
   double v[32];
 #pragma unroll
@@ -186,6 +205,8 @@ __global__ void __launch_bounds__(256) lba_camera_kernel(LbaDev d) {
 __global__ void lba_reduce_kernel(const double* __restrict__ v, int n, double* __restrict__ out, int out_idx,
                                   LbaDev d, int want_maxdiag) {
   __shared__ double sh[1024];
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = threadIdx.x;
   double acc = 0;
   for (int i = t; i < n; i += 1024) acc += v[i];
@@ -220,16 +241,24 @@ __device__ __forceinline__ int blk_index(int a, int b, int n) { return a * n - a
 
 // Schur complement: CTA g walks points g, g+G, ...; for every point adds Hpl_a Dinv Hpl_b^T to block (a,b) of its
 // private upper-triangular buffer and Hpl_a Dinv bl to its private right-hand side.
-__global__ void __launch_bounds__(256) lba_schur_kernel(LbaDev d, double lambda) {
+// acc_smem != 0: the CTA's accumulators live in (dynamic) shared memory for the whole walk and are written out once at the
+// end -- the read-modify-write of every block entry costs a shared-memory round trip instead of an L2 one; otherwise
+// (more cameras than fit) they are accumulated in the CTA's slice of `partial` directly.  Same order either way.
+__global__ void __launch_bounds__(256) lba_schur_kernel(LbaDev d, double lambda, int acc_smem) {
+  extern __shared__ double s_acc[];
   __shared__ double sBD[LBA_MAX_OBS][18];
   __shared__ double sH[LBA_MAX_OBS][18];
   __shared__ int sSlot[LBA_MAX_OBS];
   __shared__ double sDinv[6], sDb[3];
   __shared__ int sK;
   const int t = threadIdx.x;
-  double* part = d.partial + (size_t)blockIdx.x * ((size_t)d.n_blk * 36 + (size_t)d.n_opt * 6);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int acc_n = d.n_blk * 36 + d.n_opt * 6;
+  double* gpart = d.partial + (size_t)blockIdx.x * acc_n;
+  double* part = acc_smem ? s_acc : gpart;
   double* part_b = part + (size_t)d.n_blk * 36;
-  for (int i = t; i < d.n_blk * 36 + d.n_opt * 6; i += 256) part[i] = 0.0;   // this CTA's private accumulators
+  for (int i = t; i < acc_n; i += 256) part[i] = 0.0;   // this CTA's private accumulators
   __syncthreads();
   for (int p = blockIdx.x; p < d.n_points; p += gridDim.x) {
     const int e_begin = d.pt_ptr[p], e_end = d.pt_ptr[p + 1];
@@ -303,6 +332,8 @@ __global__ void __launch_bounds__(256) lba_schur_kernel(LbaDev d, double lambda)
     }
     __syncthreads();
   }
+  if (acc_smem)
+    for (int i = t; i < acc_n; i += 256) gpart[i] = s_acc[i];
 }
 
 // Hschur = diag(Hpp + lambda I) - sum_g partial_g (mirrored to the full symmetric matrix), bschur = bp - sum_g.
@@ -310,6 +341,8 @@ __global__ void __launch_bounds__(256) lba_schur_kernel(LbaDev d, double lambda)
 // sums are combined in lane order -- fixed order, so the result stays bit-reproducible.
 __global__ void lba_schur_reduce_kernel(LbaDev d, double lambda, int G) {
   const int N = 6 * d.n_opt;
+  pdl_launch_dependents();
+  pdl_wait();
   const int gi = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gi >> 2, q = gi & 3;
   const size_t stride = (size_t)d.n_blk * 36 + (size_t)d.n_opt * 6;
@@ -357,11 +390,15 @@ __global__ void lba_schur_reduce_kernel(LbaDev d, double lambda, int G) {
 // Landmark back-substitution xl = Dinv (bl - sum_a Hpl_a^T xp_a), trial point = point + xl, and the landmark part of
 // the gain-ratio denominator sum x (lambda x + b)  (optimization_algorithm_levenberg.cpp:186-199).
 __global__ void lba_backsub_kernel(LbaDev d, double lambda) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= d.n_points) return;
-  double c0 = d.bl[3 * p], c1 = d.bl[3 * p + 1], c2 = d.bl[3 * p + 2];
-  for (int e = d.pt_ptr[p]; e < d.pt_ptr[p + 1]; ++e) {
-    const int s = d.cam_slot[d.edge_cam[e]];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = gt / LBA_PL, sub = gt % LBA_PL;
+  const bool live = p < d.n_points;
+  double c0 = 0, c1 = 0, c2 = 0;                 // lane j: edges j, j + LBA_PL, ... of the landmark
+  const int e_end = live ? d.pt_ptr[p + 1] : 0;
+  for (int e = (live ? d.pt_ptr[p] : 0) + sub; e < e_end; e += LBA_PL) {
+    const int s = d.edge_slot[e];
     if (s < 0) continue;
     const double* h = d.Hpl + 18 * (size_t)e;
     const double* x = d.xp + 6 * (size_t)s;
@@ -372,6 +409,14 @@ __global__ void lba_backsub_kernel(LbaDev d, double lambda) {
       c2 -= h[3 * i + 2] * x[i];
     }
   }
+#pragma unroll
+  for (int o = LBA_PL / 2; o > 0; o >>= 1) {     // fixed butterfly: bit-reproducible
+    c0 += lba_shfl_xor(c0, o);
+    c1 += lba_shfl_xor(c1, o);
+    c2 += lba_shfl_xor(c2, o);
+  }
+  if (!live || sub != 0) return;
+  c0 += d.bl[3 * p]; c1 += d.bl[3 * p + 1]; c2 += d.bl[3 * p + 2];
   const double* D = d.Dinv + 6 * (size_t)p;
   const double x0 = D[0] * c0 + D[1] * c1 + D[2] * c2;
   const double x1 = D[1] * c0 + D[3] * c1 + D[4] * c2;
@@ -389,6 +434,8 @@ __device__ void po_pose_oplus(const double* pose, const double* u, double* out);
 __global__ void lba_reduce2_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ out,
                                    int ia, int ib) {
   __shared__ double sh[1024];
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = threadIdx.x;
   for (int which = 0; which < 2; ++which) {
     const double* v = which ? b : a;
@@ -441,6 +488,8 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
   const int N = 6 * d.n_opt, t = threadIdx.x;
   const int total = N * (N + 1) / 2;
   unsigned char* col_of = reinterpret_cast<unsigned char*>(sL + total);   // packed index -> column
+  pdl_launch_dependents();
+  pdl_wait();
   SOLVE_CLK(0);
   for (int q = t; q < total; q += 256) col_of[q] = (unsigned char)lcol_inv(q, N);
   for (int i = t; i < N; i += 256) s_b[i] = d.bs[i];
@@ -849,21 +898,28 @@ static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost
 // scal[0] = robust chi2, scal[1] = max |diag|.
 static int lba_build(hfb_ctx* ctx, LbaDev& d, double* chi2_buf, int want_maxdiag) {
   if (d.n_points > 0) {
-    lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, ctx->stream>>>(d, d.poses, d.points, chi2_buf, 0);
+    hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses, (const double*)d.points, chi2_buf, 0);
     HFB_CHECK_LAUNCH(ctx, "lba_linearize");
   }
   if (d.n_opt > 0) {
-    lba_camera_kernel<<<d.n_opt, 256, 0, ctx->stream>>>(d);
+    hfb_launch(ctx, lba_camera_kernel, dim3(d.n_opt), dim3(256), 0, d);
     HFB_CHECK_LAUNCH(ctx, "lba_camera");
   }
-  lba_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(d.rho_pt, d.n_points, d.scal, 0, d, want_maxdiag);
+  hfb_launch(ctx, lba_reduce_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, d.n_points, d.scal, 0, d, want_maxdiag);
   HFB_CHECK_LAUNCH(ctx, "lba_reduce");
   return HFB_OK;
 }
 
 static int lba_schur(hfb_ctx* ctx, LbaDev& d, double lambda) {
   if (d.n_points > 0) {
-    lba_schur_kernel<<<d.G, 256, 0, ctx->stream>>>(d, lambda);   // zeroes its CTA-private accumulators itself
+    // zeroes its CTA-private accumulators itself; they sit in shared memory when they fit beside a second CTA
+    const size_t acc_bytes = ((size_t)d.n_blk * 36 + (size_t)d.n_opt * 6) * 8;
+    const int acc_smem = acc_bytes <= 90 * 1024 ? 1 : 0;
+    if (acc_smem) {
+      static SmemOptIn optin;
+      HFB_CUDA(ctx, optin.ensure(lba_schur_kernel, ctx->device, 90 * 1024));
+    }
+    hfb_launch(ctx, lba_schur_kernel, dim3(d.G), dim3(256), acc_smem ? acc_bytes : 0, d, lambda, acc_smem);
     HFB_CHECK_LAUNCH(ctx, "lba_schur");
   } else {
     const size_t part_stride = (size_t)d.n_blk * 36 + (size_t)d.n_opt * 6;
@@ -871,7 +927,7 @@ static int lba_schur(hfb_ctx* ctx, LbaDev& d, double lambda) {
   }
   const int N = 6 * d.n_opt;
   if (N > 0) {
-    lba_schur_reduce_kernel<<<ceil_div(4 * (N * N + N), 256), 256, 0, ctx->stream>>>(d, lambda, d.G);
+    hfb_launch(ctx, lba_schur_reduce_kernel, dim3(ceil_div(4 * (N * N + N), 256)), dim3(256), 0, d, lambda, d.G);
     HFB_CHECK_LAUNCH(ctx, "lba_schur_reduce");
   }
   return HFB_OK;
@@ -932,10 +988,10 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   const bool first_build_has_chi = iterations > 0 && !terminate();
   if (!first_build_has_chi) {
     if (d.n_points > 0) {
-      lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, d.poses, d.points, chi2_last, 1);
+      hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses, (const double*)d.points, chi2_last, 1);
       HFB_CHECK_LAUNCH(ctx, "lba_errors");
     }
-    lba_reduce_kernel<<<1, 1024, 0, st>>>(d.rho_pt, d.n_points, d.scal, 0, d, 0);
+    hfb_launch(ctx, lba_reduce_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, d.n_points, d.scal, 0, d, 0);
     HFB_CHECK_LAUNCH(ctx, "lba_reduce");
     HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 8, cudaMemcpyDeviceToHost, st));
     HFB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -966,7 +1022,7 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
       HFB_TRY(lba_schur(ctx, d, lambda));
       bool ok2 = true;
       if (dev_solve) {
-        lba_solve_kernel<<<1, 256, solve_smem, st>>>(d, lambda);
+        hfb_launch(ctx, lba_solve_kernel, dim3(1), dim3(256), solve_smem, d, lambda);
         HFB_CHECK_LAUNCH(ctx, "lba_solve");
       } else {
         if (N) {
@@ -983,13 +1039,13 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
         HFB_CUDA(ctx, cudaMemcpyAsync(d.poses_t, poses_t.data(), (size_t)nc * 56, cudaMemcpyHostToDevice, st));
       }
       if (d.n_points > 0) {
-        lba_backsub_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, lambda);
+        hfb_launch(ctx, lba_backsub_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, lambda);
         HFB_CHECK_LAUNCH(ctx, "lba_backsub");
-        lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, d.poses_t, d.points_t, chi2_other, 1);
+        hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses_t, (const double*)d.points_t, chi2_other, 1);
         HFB_CHECK_LAUNCH(ctx, "lba_errors");
       }
       std::swap(chi2_last, chi2_other);
-      lba_reduce2_kernel<<<1, 1024, 0, st>>>(d.rho_pt, d.scale_pt, d.n_points, d.scal, 2, 3);
+      hfb_launch(ctx, lba_reduce2_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, (const double*)d.scale_pt, d.n_points, d.scal, 2, 3);
       HFB_CHECK_LAUNCH(ctx, "lba_reduce2");
       HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 48, cudaMemcpyDeviceToHost, st));
       HFB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1024,7 +1080,7 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   }
   // outputs: final estimate, cached chi2 of the LAST error evaluation (src/Optimizer.cc:1425 quirk), depth test
   if (d.n_points > 0 && depth_positive_out) {
-    lba_linearize_kernel<<<ceil_div(d.n_points, 128), 128, 0, st>>>(d, d.poses, d.points, chi2_other, 1);
+    hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses, (const double*)d.points, chi2_other, 1);
     HFB_CHECK_LAUNCH(ctx, "lba_errors");
     HFB_CUDA(ctx, cudaMemcpyAsync(depth_positive_out, d.depth_ok, (size_t)d.n_edges, cudaMemcpyDeviceToHost, st));
   }
