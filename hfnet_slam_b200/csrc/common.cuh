@@ -213,6 +213,8 @@ struct hfb_ctx {
   // pinned staging
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
+  double* h_post = nullptr;    // 8 page-locked doubles a kernel posts its scalars into (mapped memory) + a sequence number:
+  uint64_t post_seq = 0;       // the LM loop of local BA polls it instead of copying and synchronising per trial
   // generic device scratch (matcher / lba), grown on demand
   void* d_scratch = nullptr;
   size_t d_scratch_bytes = 0;

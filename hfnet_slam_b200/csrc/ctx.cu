@@ -228,6 +228,7 @@ extern "C" void hfb_destroy(hfb_ctx* ctx) {
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_io) cudaFree(ctx->d_io);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_post) cudaFreeHost(ctx->h_post);
   if (ctx->ev_local) cudaEventDestroy(ctx->ev_local);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -18,6 +18,8 @@
 
 #include <algorithm>
 
+#include <atomic>
+
 #include "common.cuh"
 
 struct LbaDev {
@@ -431,8 +433,9 @@ __global__ void lba_backsub_kernel(LbaDev d, double lambda) {
 __device__ void po_pose_oplus(const double* pose, const double* u, double* out);
 
 // rho and scale sums of one LM trial in one launch (same strided + tree order as lba_reduce_kernel)
+// post != null: thread 0 then posts out[0..5] and the sequence number into page-locked host memory (the host polls it).
 __global__ void lba_reduce2_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ out,
-                                   int ia, int ib) {
+                                   int ia, int ib, volatile double* post, double seq) {
   __shared__ double sh[1024];
   pdl_launch_dependents();
   pdl_wait();
@@ -450,6 +453,13 @@ __global__ void lba_reduce2_kernel(const double* __restrict__ a, const double* _
     }
     if (t == 0) out[which ? ib : ia] = sh[0];
   }
+  if (t == 0 && post) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) post[i] = out[i];
+    __threadfence_system();
+    post[6] = seq;
+    __threadfence_system();
+  }
 }
 
 // The reduced camera system on the device (g2o: LinearSolverEigen::solve, Thirdparty/g2o/g2o/solvers/
@@ -461,24 +471,8 @@ __global__ void lba_reduce2_kernel(const double* __restrict__ a, const double* _
 #define LBA_SOLVE_MAX_N 192
 __device__ __forceinline__ int lcol(int k, int N) { return k * N - k * (k - 1) / 2; }   // start of packed column k (rows k..N-1)
 
-// packed index -> column: lcol(k) = k (2N + 1 - k) / 2 <= q, closed form + integer fix-up
-__device__ __forceinline__ int lcol_inv(int q, int N) {
-  const float b = (float)(2 * N + 1);
-  int k = (int)((b - sqrtf(fmaxf(b * b - 8.f * (float)q, 0.f))) * 0.5f);
-  k = max(0, min(k, N - 1));
-  while (k > 0 && lcol(k, N) > q) --k;
-  while (k + 1 < N && lcol(k + 1, N) <= q) ++k;
-  return k;
-}
 #define T6(c, r) ((c) * 6 - (c) * ((c) - 1) / 2 + (r) - (c))   // 6 x 6 lower triangle packed by columns, r >= c
 
-#ifdef HFB_SOLVE_CLK   // phase cycle counters of the last launch (tools/ba_time.py prints them when the symbol exists)
-__device__ long long g_solve_clk[8];
-extern "C" int hfb_debug_solve_clocks(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_solve_clk, sizeof(g_solve_clk)); }
-#define SOLVE_CLK(i) do { if (threadIdx.x == 0) g_solve_clk[i] = clock64(); } while (0)
-#else
-#define SOLVE_CLK(i) do { } while (0)
-#endif
 __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda) {
   extern __shared__ double sL[];                 // lower triangle packed BY COLUMNS: L[i][k] at lcol(k) + i - k, so the
                                                  // rows i = j + tid of one column step read consecutive words
@@ -486,12 +480,8 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
   __shared__ double s_linv[LBA_SOLVE_MAX_N / 6][21];   // inverses of the factored diagonal blocks (backward substitution)
   __shared__ int s_fail;
   const int N = 6 * d.n_opt, t = threadIdx.x;
-  const int total = N * (N + 1) / 2;
-  unsigned char* col_of = reinterpret_cast<unsigned char*>(sL + total);   // packed index -> column
   pdl_launch_dependents();
   pdl_wait();
-  SOLVE_CLK(0);
-  for (int q = t; q < total; q += 256) col_of[q] = (unsigned char)lcol_inv(q, N);
   for (int i = t; i < N; i += 256) s_b[i] = d.bs[i];
   if (t == 0) s_fail = 0;
   // Hs is bitwise symmetric: the lower triangle is read row by row (coalesced), eight loads in flight per thread
@@ -536,7 +526,6 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
       for (int r = c; r < 6; ++r) sL[lcol(j0 + c, N) + r - c] = a[T6(c, r)];
     if (fail) s_fail = 1;
   };
-  SOLVE_CLK(1);
   if (t == 0 && N > 0) factor_diag(0);
   __syncthreads();
   for (int j0 = 0; j0 < N; j0 += 6) {
@@ -597,21 +586,42 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
             s_b[i] = v;
           }
         }
-        for (int q = lcol(j0 + 6, N) + (t - 32); q < total; q += 224) {
-          const int cc = col_of[q];
-          const int r = cc + q - lcol(cc, N);
-          if (r < j0 + 12) continue;               // the next diagonal block belongs to warp 0
-          double acc = sL[q];
+        // trailing triangle by 6-wide block columns: warps 1..7 deal them round-robin; a warp keeps the block column's
+        // 6 x 6 factor rows W[k][c] = L[6 bj + k][j0 + c] in registers and its lanes walk down the rows below, so an
+        // element costs 1 + 1/6 shared-memory operand loads instead of 12 (the rank-6 update was LSU-bound)
+        const int jb = j0 / 6, nbk = N / 6, w = (t >> 5) - 1;
+        for (int bj = jb + 1 + w; bj < nbk; bj += 7) {
+          double W[6][6];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) acc -= col[c][r] * col[c][cc];
-          sL[q] = acc;
+          for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) W[k][c] = col[c][6 * bj + k];
+          const int cbase = 6 * bj;
+          double* dcol[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) dcol[k] = sL + lcol(cbase + k, N) - (cbase + k);   // dcol[k][r] = A[r][cbase + k]
+          for (int r = (bj == jb + 1 ? j0 + 12 : cbase) + lane; r < N; r += 32) {   // the next diagonal block is warp 0's
+            // all six outputs of the row at once (six independent accumulation chains; a branch per output would
+            // serialise them): entries above the diagonal (inside this column's diagonal block) are computed on a
+            // dummy and not stored
+            double a[6], acc[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) a[c] = col[c][r];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[k] = cbase + k <= r ? dcol[k][r] : 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+#pragma unroll
+              for (int k = 0; k < 6; ++k) acc[k] -= a[c] * W[k][c];
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+              if (cbase + k <= r) dcol[k][r] = acc[k];
+          }
         }
       }
     }
     __syncthreads();
   }
-  __syncthreads();
-  SOLVE_CLK(2);
   if (!s_fail) {
     // inverses of the diagonal blocks, one thread per camera (lower triangular, column by column)
     if (t < d.n_opt) {
@@ -636,7 +646,6 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
       for (int e = 0; e < 21; ++e) s_linv[t][e] = m[e];
     }
     __syncthreads();
-    SOLVE_CLK(3);
     // backward L^T x = y by blocks: six threads apply the block inverse (x_c = sum_{r >= c} Linv[r][c] v_r), then every
     // row above takes the rank-6 correction
     for (int j0 = N - 6; j0 >= 0; j0 -= 6) {
@@ -658,7 +667,6 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
       __syncthreads();
     }
   }
-  SOLVE_CLK(4);
   for (int i = t; i < N; i += 256) d.xp[i] = s_fail ? 0.0 : s_b[i];
   // trial poses: every camera copied, optimisable ones updated
   for (int i = t; i < d.n_cams * 7; i += 256) d.poses_t[i] = d.poses[i];
@@ -680,8 +688,6 @@ __global__ void __launch_bounds__(256) lba_solve_kernel(LbaDev d, double lambda)
       d.scal[5] = s_fail ? 0.0 : 1.0;
     }
   }
-  __syncthreads();
-  SOLVE_CLK(5);
 }
 
 // ------------------------------------------------------------------------------------------------ host helpers
@@ -962,6 +968,10 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   const uint64_t launches0 = ctx->launches;
   HFB_TRY(lba_setup(ctx, problem, d, h, &arena));
   cudaStream_t st = ctx->stream;
+  if (!ctx->h_post) {
+    HFB_CUDA(ctx, cudaMallocHost(&ctx->h_post, 8 * sizeof(double)));
+    memset(ctx->h_post, 0, 8 * sizeof(double));
+  }
   const int no = d.n_opt, N = 6 * no, nc = d.n_cams;
   // The reduced system is solved on the device (lba_solve_kernel) unless it does not fit one CTA's shared memory or the
   // host-solve mode is requested (HFB_LBA_HOST_SOLVE=1: the round-1 path, kept as the cross-check of the device solver).
@@ -1045,10 +1055,32 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
         HFB_CHECK_LAUNCH(ctx, "lba_errors");
       }
       std::swap(chi2_last, chi2_other);
-      hfb_launch(ctx, lba_reduce2_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, (const double*)d.scale_pt, d.n_points, d.scal, 2, 3);
+      // the trial's scalars come back through page-locked memory the kernel writes itself; the host polls the sequence
+      // number (no copy operation, no stream synchronisation per trial)
+      const double seq = (double)(++ctx->post_seq);
+      hfb_launch(ctx, lba_reduce2_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, (const double*)d.scale_pt, d.n_points, d.scal, 2, 3,
+                 (volatile double*)ctx->h_post, seq);
       HFB_CHECK_LAUNCH(ctx, "lba_reduce2");
-      HFB_CUDA(ctx, cudaMemcpyAsync(scal, d.scal, 48, cudaMemcpyDeviceToHost, st));
-      HFB_CUDA(ctx, cudaStreamSynchronize(st));
+      {
+        volatile double* hp = ctx->h_post;
+        uint32_t spins = 0;
+        while (hp[6] != seq) {
+          if ((++spins & 0x3ff) == 0) {          // every ~1000 polls: has the stream died or finished without posting?
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaSuccess) {
+              if (hp[6] == seq) break;
+              ctx->set_error("local BA: the trial finished without posting its result");
+              return HFB_ERR_CUDA;
+            }
+            if (q != cudaErrorNotReady) {
+              ctx->set_error(std::string("local BA trial: ") + cudaGetErrorString(q));
+              return HFB_ERR_CUDA;
+            }
+          }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        for (int i = 0; i < 6; ++i) scal[i] = hp[i];
+      }
       if (dev_solve) ok2 = scal[5] != 0.0;
       ++trials;
       const double temp_chi = ok2 ? scal[2] : 1.7976931348623157e308;

@@ -11,14 +11,3 @@ with Context(height=64, width=64, n_levels=1, max_keypoints=64, max_batch=1, wit
     r = bench.extra_lba(ctx, cpu=False)
     r2 = bench.extra_lba(ctx, cpu=False)
 print(json.dumps({k: r2[k] for k in ("ms_per_iter", "ms_total", "iterations", "trials", "gpu_launches", "pose_optimization_ms")}))
-try:   # phase clocks of the last lba_solve_kernel launch (debug build only)
-    import ctypes as C
-    from hfnet_slam_b200 import lib as _l
-    clk = (C.c_longlong * 8)()
-    if _l.load().hfb_debug_solve_clocks(clk) == 0:
-        v = list(clk)
-        print("solve phases (cycles): init+load %d, factor %d, forward %d, backward %d, xp %d, poses+scale %d" %
-              tuple(v[i + 1] - v[i] for i in range(5)) + (0,) if False else
-              "solve phases (cycles): " + ", ".join(str(v[i + 1] - v[i]) for i in range(5)))
-except AttributeError:
-    pass
