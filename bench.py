@@ -685,13 +685,16 @@ def main_gpu(args):
     match_out = match_outs[0]
     host_stats = {"kp": 0, "matches": 0}
 
+    host_mode = {"descriptors": True}
+
     def host_stream(si, res):
         # HFextractor::operator() on host frames (H2D of the u8 frames, D2H of keypoints / descriptors / global
         # descriptors) + the association on the descriptors still resident in HBM (D2H of the match rows) through
         # the synchronous hfb_extract_match_batch, batch after batch of stream si (ctypes releases the GIL in the call)
         kp, idx = 0, None
         for i in range(si, NB, S):
-            feats, idx, val = ctxs[si].extract_match_batch(host_batches[i], budgets, THR, 0, 0.6, pinned=True, out=match_outs[si])
+            feats, idx, val = ctxs[si].extract_match_batch(host_batches[i], budgets, THR, 0, 0.6, pinned=True, out=match_outs[si],
+                                                           descriptors=host_mode["descriptors"])
             kp += sum(len(f["x"]) for f in feats)
         res[si] = (kp, int((idx >= 0).sum()) if idx is not None else 0)
 
@@ -740,6 +743,15 @@ def main_gpu(args):
     for c in ctxs:
         c.reset_stream()
     ms_host, (h0, h1), _ = timed(step_host, n_host, 2)
+    # the same host-buffer call with the 256-d local descriptors left resident in HBM (hfb_features.descriptors = NULL):
+    # keypoints, global descriptors and match rows come back; the matcher, the resident windowed search and the keyframe
+    # store read the descriptors where the extraction left them
+    for c in ctxs:
+        c.reset_stream()
+    host_mode["descriptors"] = False
+    ms_host_res, _, _ = timed(step_host, n_host, 2)
+    host_mode["descriptors"] = True
+    kp_res = host_stats["kp"]
     ms_one = None
     if S > 1:                                                        # the same step on ONE context / stream, for continuity
         ctx.reset_stream()
@@ -756,7 +768,7 @@ def main_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ms_dev, ms_host = maxred(ms_dev), maxred(ms_host)
+    ms_dev, ms_host, ms_host_res = maxred(ms_dev), maxred(ms_host), maxred(ms_host_res)
     if ms_one is not None:
         ms_one = maxred(ms_one)
     value = world * B * NB * args.steps / (ms_dev / 1e3)
@@ -797,6 +809,12 @@ def main_gpu(args):
              "host_keypoints_per_step": host_stats["kp"], "host_matches_last_batch": host_stats["matches"],
              "ungraphed_batch_ms": total_ms, "kernels": kernels,
              "whole_batch_tensor_frac": step_flops / (ms_dev / 1e3 / (args.steps * NB)) / 1e12 / pk["tf"]}
+    extra["e2e_resident_descriptors"] = {
+        "value": world * B * NB * n_host / (ms_host_res / 1e3), "unit": "frames/s", "ms_per_step": ms_host_res / n_host,
+        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": kp_res * 16 + B * NB * (4096 * 4 + 32) + 2 * NB * B * NKP * 4,
+        "note": "the end-to-end arm with hfb_features.descriptors = NULL: frames in, keypoints + global descriptors + match "
+                "rows out, the 256-d local descriptors stay in HBM for the device-side consumers (association, resident "
+                "windowed search, keyframe store); the headline e2e above moves them to the host as the reference's Frame holds them"}
     if ms_one is not None:
         extra["single_context"] = {"frames_per_s": world * B * NB / (ms_one / 1e3), "ms_per_batch": ms_one / NB,
                                    "note": "the same device-resident step with every batch on ONE context / CUDA stream "

@@ -565,7 +565,7 @@ static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, floa
     HFB_CUDA(ctx, rows_d2h(d.y, ctx->d_ky, 4, cs));
     HFB_CUDA(ctx, rows_d2h(d.r, ctx->d_kresp, 4, cs));
     HFB_CUDA(ctx, rows_d2h(d.o, ctx->d_koct, 4, cs));
-    HFB_CUDA(ctx, rows_d2h(d.d, ctx->d_kdesc, (size_t)HFB_DESC_DIM * 4, cs));
+    if (d.d) HFB_CUDA(ctx, rows_d2h(d.d, ctx->d_kdesc, (size_t)HFB_DESC_DIM * 4, cs));   // NULL: descriptors stay resident
     HFB_CUDA(ctx, cudaEventRecord(ctx->ev_copied, cs));
   }
   if (ctx->fmatch.on) HFB_TRY(enqueue_match_consecutive(ctx, B, ctx->fmatch.mode, ctx->fmatch.thr));
@@ -686,8 +686,9 @@ extern "C" int hfb_fetch_features(hfb_ctx* ctx, int32_t image_index, hfb_feature
     HFB_CUDA(ctx, cudaMemcpyAsync(out->y, ctx->d_ky + o, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
     HFB_CUDA(ctx, cudaMemcpyAsync(out->response, ctx->d_kresp + o, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
     HFB_CUDA(ctx, cudaMemcpyAsync(out->octave, ctx->d_koct + o, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    HFB_CUDA(ctx, cudaMemcpyAsync(out->descriptors, ctx->d_kdesc + o * HFB_DESC_DIM, (size_t)total * HFB_DESC_DIM * 4,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->descriptors)
+      HFB_CUDA(ctx, cudaMemcpyAsync(out->descriptors, ctx->d_kdesc + o * HFB_DESC_DIM, (size_t)total * HFB_DESC_DIM * 4,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (out->global_descriptor && ctx->cfg.with_global)
     HFB_CUDA(ctx, cudaMemcpyAsync(out->global_descriptor, ctx->d_global + (size_t)image_index * HFB_GLOBAL_DIM,
@@ -758,13 +759,13 @@ extern "C" int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* image
       const hfb_features& f = outs[b];
       const size_t o = (size_t)b * ctx->kp_cap;
       fast = f.x == f0.x + o && f.y == f0.y + o && f.response == f0.response + o && f.octave == f0.octave + o &&
-             f.descriptors == f0.descriptors + o * HFB_DESC_DIM &&
+             (f0.descriptors ? f.descriptors == f0.descriptors + o * HFB_DESC_DIM : f.descriptors == nullptr) &&
              (!ctx->cfg.with_global ? true
                                     : (f0.global_descriptor ? f.global_descriptor == f0.global_descriptor + (size_t)b * HFB_GLOBAL_DIM
                                                             : f.global_descriptor == nullptr));
     }
     fast = fast && is_pinned(f0.x) && is_pinned(f0.y) && is_pinned(f0.response) && is_pinned(f0.octave) &&
-           is_pinned(f0.descriptors) && (!f0.global_descriptor || is_pinned(f0.global_descriptor)) &&
+           (!f0.descriptors || is_pinned(f0.descriptors)) && (!f0.global_descriptor || is_pinned(f0.global_descriptor)) &&
            (!want_match || (is_pinned(match_idx) && is_pinned(match_val)));
     if (fast) {
       int* hc = reinterpret_cast<int*>(hs + (size_t)n_images * img_bytes);   // counts + overflow flag in the pinned stage
@@ -816,7 +817,7 @@ extern "C" int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* image
     uint8_t* q = ho + (size_t)b * per_frame_out;
     Slot& s = slots[b];
     hfb_features& f = outs[b];
-    s.direct = is_pinned(f.descriptors) && is_pinned(f.x) && is_pinned(f.y) && is_pinned(f.response) &&
+    s.direct = (!f.descriptors || is_pinned(f.descriptors)) && is_pinned(f.x) && is_pinned(f.y) && is_pinned(f.response) &&
                is_pinned(f.octave) && (!f.global_descriptor || is_pinned(f.global_descriptor));
     s.counts = reinterpret_cast<int*>(q); q += 64;
     s.x = s.direct ? f.x : reinterpret_cast<float*>(q); q += (size_t)ctx->kp_cap * 4;
@@ -833,8 +834,9 @@ extern "C" int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* image
       HFB_CUDA(ctx, cudaMemcpyAsync(s.y, ctx->d_ky + o, (size_t)budget * 4, cudaMemcpyDeviceToHost, ctx->stream));
       HFB_CUDA(ctx, cudaMemcpyAsync(s.r, ctx->d_kresp + o, (size_t)budget * 4, cudaMemcpyDeviceToHost, ctx->stream));
       HFB_CUDA(ctx, cudaMemcpyAsync(s.o, ctx->d_koct + o, (size_t)budget * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      HFB_CUDA(ctx, cudaMemcpyAsync(s.d, ctx->d_kdesc + o * HFB_DESC_DIM, (size_t)budget * HFB_DESC_DIM * 4,
-                                    cudaMemcpyDeviceToHost, ctx->stream));
+      if (f.descriptors)
+        HFB_CUDA(ctx, cudaMemcpyAsync(s.d, ctx->d_kdesc + o * HFB_DESC_DIM, (size_t)budget * HFB_DESC_DIM * 4,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (ctx->cfg.with_global && (f.global_descriptor || !s.direct))
       HFB_CUDA(ctx, cudaMemcpyAsync(s.g, ctx->d_global + (size_t)b * HFB_GLOBAL_DIM, HFB_GLOBAL_DIM * 4,
@@ -858,7 +860,7 @@ extern "C" int hfb_extract_match_batch(hfb_ctx* ctx, const uint8_t* const* image
       memcpy(f.y, s.y, (size_t)total * 4);
       memcpy(f.response, s.r, (size_t)total * 4);
       memcpy(f.octave, s.o, (size_t)total * 4);
-      memcpy(f.descriptors, s.d, (size_t)total * HFB_DESC_DIM * 4);
+      if (f.descriptors) memcpy(f.descriptors, s.d, (size_t)total * HFB_DESC_DIM * 4);
     }
     if (f.global_descriptor && ctx->cfg.with_global) memcpy(f.global_descriptor, s.g, HFB_GLOBAL_DIM * 4);
   }

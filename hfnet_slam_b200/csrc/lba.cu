@@ -842,6 +842,7 @@ static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost
   d.n_cams = nc; d.n_points = np; d.n_edges = ne; d.n_opt = no;
   d.n_blk = no * (no + 1) / 2;
   d.G = std::max(1, std::min(2 * ctx->n_sm, np));
+  if (const char* ge = getenv("HFB_LBA_G")) d.G = std::max(1, std::min(atoi(ge), np));   // experiment: CTAs (= partial buffers) of the Schur kernel
   h.edge_slot.resize(ne);
   for (int e = 0; e < ne; ++e) h.edge_slot[e] = h.cam_slot[pr->edge_cam[e]];
   for (int i = 0; i < 4; ++i) d.K[i] = (double)pr->K[i];

@@ -273,22 +273,24 @@ class Context:
         self.check(self.lib.hfb_load_weights(self.handle, C.cast(buf, C.c_void_p), len(blob)))
 
     # ------------------------------------------------------------------------------------------ extraction
-    def _alloc_features(self, n: int = 1, pinned: bool = False):
+    def _alloc_features(self, n: int = 1, pinned: bool = False, descriptors: bool = True):
         """One contiguous host block per field for n frames (frame b's rows start at b * kp_cap).  pinned=True reuses a
-        page-locked block owned by the context (results are valid until the next pinned call)."""
+        page-locked block owned by the context (results are valid until the next pinned call).  descriptors=False: the
+        struct carries a NULL descriptor pointer -- the local descriptors stay resident in HBM."""
         cap = self.kp_cap
         if pinned:
             cache = self.__dict__.setdefault("_pinned_out", {})
-            if n not in cache:
-                cache[n] = dict(x=pinned_empty((n, cap), np.float32), y=pinned_empty((n, cap), np.float32),
-                                response=pinned_empty((n, cap), np.float32), octave=pinned_empty((n, cap), np.int32),
-                                descriptors=pinned_empty((n, cap, HFB_DESC_DIM), np.float32),
-                                global_descriptor=pinned_empty((n, HFB_GLOBAL_DIM), np.float32))
-            arrs = cache[n]
+            key = (n, descriptors)
+            if key not in cache:
+                cache[key] = dict(x=pinned_empty((n, cap), np.float32), y=pinned_empty((n, cap), np.float32),
+                                  response=pinned_empty((n, cap), np.float32), octave=pinned_empty((n, cap), np.int32),
+                                  descriptors=pinned_empty((n, cap if descriptors else 0, HFB_DESC_DIM), np.float32),
+                                  global_descriptor=pinned_empty((n, HFB_GLOBAL_DIM), np.float32))
+            arrs = cache[key]
         else:
             arrs = dict(x=np.empty((n, cap), np.float32), y=np.empty((n, cap), np.float32),
                         response=np.empty((n, cap), np.float32), octave=np.empty((n, cap), np.int32),
-                        descriptors=np.empty((n, cap, HFB_DESC_DIM), np.float32),
+                        descriptors=np.empty((n, cap if descriptors else 0, HFB_DESC_DIM), np.float32),
                         global_descriptor=np.empty((n, HFB_GLOBAL_DIM), np.float32))
         if pinned and "_feats" in arrs:
             return arrs["_feats"], arrs          # same page-locked arrays, same struct array: nothing to rebuild
@@ -297,7 +299,7 @@ class Context:
             f = feats[b]
             f.x, f.y = ptr(arrs["x"][b], _f32p), ptr(arrs["y"][b], _f32p)
             f.response, f.octave = ptr(arrs["response"][b], _f32p), ptr(arrs["octave"][b], _i32p)
-            f.descriptors = ptr(arrs["descriptors"][b], _f32p)
+            f.descriptors = ptr(arrs["descriptors"][b], _f32p) if descriptors else None
             f.global_descriptor = ptr(arrs["global_descriptor"][b], _f32p) if self.with_global else None
         if pinned:
             arrs["_feats"] = feats
@@ -306,7 +308,7 @@ class Context:
     @staticmethod
     def _view(f: hfb_features, arrs: dict, b: int, with_global: bool) -> dict:
         n = int(f.n_total)
-        out = {k: arrs[k][b, :n] for k in ("x", "y", "response", "octave", "descriptors")}
+        out = {k: arrs[k][b, :n] for k in ("x", "y", "response", "octave", "descriptors")}   # descriptors: empty when resident
         out["n_per_level"] = [int(v) for v in f.n_per_level]
         out["global_descriptor"] = arrs["global_descriptor"][b] if with_global else None
         return out
@@ -330,16 +332,18 @@ class Context:
         return (out, arrs) if return_block else out
 
     def extract_match_batch(self, images, n_per_level, threshold: float, mode: int, thr: float, pinned: bool = False,
-                            out=None):
+                            out=None, descriptors: bool = True):
         """extract_batch + match_consecutive as one call (hfb_extract_match_batch): returns (features, idx, val) with
-        idx / val [n][kp_cap] (row b: frame b -> frame b-1).  pinned=True: page-locked outputs written by the graph."""
+        idx / val [n][kp_cap] (row b: frame b -> frame b-1).  pinned=True: page-locked outputs written by the graph.
+        descriptors=False: keypoints, global descriptors and match rows come back, the 256-d local descriptors stay
+        resident in HBM (the matcher, the resident windowed search and the keyframe store read them there)."""
         imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
         for im in imgs:
             if im.ndim != 2 or im.shape != (self.height, self.width):
                 raise HfbError(1, f"image shape {im.shape} differs from the context's {(self.height, self.width)}")
         n = len(imgs)
         ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
-        feats, arrs = self._alloc_features(n, pinned)
+        feats, arrs = self._alloc_features(n, pinned, descriptors)
         if out is None:
             mk = pinned_empty if pinned else np.empty
             out = (mk((n, self.kp_cap), np.int32), mk((n, self.kp_cap), np.float32))

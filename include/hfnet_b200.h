@@ -86,7 +86,9 @@ typedef struct hfb_features {
   float* y;                 /* [cap] row    * scaleFactor^level */
   float* response;          /* [cap] */
   int32_t* octave;          /* [cap] */
-  float* descriptors;       /* [cap * 256] */
+  float* descriptors;       /* [cap * 256], or NULL: the local descriptors stay resident in HBM (the association, the
+                               windowed searches on resident frames and the keyframe store read them there; fetch later
+                               with hfb_fetch_features if a caller needs them on the host) */
   float* global_descriptor; /* [4096] or NULL */
   int32_t n_per_level[HFB_MAX_LEVELS]; /* out: keypoints found per level (<= requested) */
   int32_t n_total;          /* out */

@@ -321,3 +321,26 @@ def test_concurrent_pyramid_levels_equal_sequential_levels(native_lib, weights_b
             assert seq[0][i]["n_per_level"] == par[rep][i]["n_per_level"]
             for k in ("x", "y", "response", "octave", "descriptors", "global_descriptor"):
                 assert np.array_equal(seq[0][i][k], par[rep][i][k]), (rep, i, k)
+
+
+def test_resident_descriptors_mode(ctx_euroc, oracle_euroc):
+    """hfb_features.descriptors = NULL: keypoints, global descriptors and match rows come back, the 256-d local descriptors
+    stay in HBM -- same keypoints and matches as the full call (page-locked and staged paths), and hfb_fetch_features
+    still delivers the identical descriptor rows afterwards."""
+    img, _ = oracle_euroc
+    imgs = [img, np.roll(img, (4, 7), axis=(0, 1))]          # the fixture's context holds two frames per call
+    ctx_euroc.reset_stream()
+    full, idx_f, val_f = ctx_euroc.extract_match_batch(imgs, [1000], 0.01, 0, 0.6)
+    full = [{k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in f.items()} for f in full]
+    idx_f, val_f = idx_f.copy(), val_f.copy()
+    for pinned in (False, True):
+        ctx_euroc.reset_stream()
+        lean, idx_l, val_l = ctx_euroc.extract_match_batch(imgs, [1000], 0.01, 0, 0.6, pinned=pinned, descriptors=False)
+        for b in range(2):
+            assert lean[b]["descriptors"].shape[0] == 0
+            for k in ("x", "y", "response", "octave", "global_descriptor"):
+                assert np.array_equal(lean[b][k], full[b][k]), (pinned, b, k)
+            n = len(full[b]["x"])
+            assert np.array_equal(idx_l[b, :n], idx_f[b, :n]) and np.array_equal(val_l[b, :n], val_f[b, :n])
+            assert np.array_equal(ctx_euroc.fetch_features(b)["descriptors"], full[b]["descriptors"])
+    assert (idx_f[1, :len(full[1]["x"])] >= 0).sum() > 20
