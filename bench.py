@@ -415,6 +415,53 @@ def c3_gpu(torch, dev, n_frames: int, threads: int = 2):
                                                "host threads the per-keyframe stages run beside the per-frame ones"}
 
 
+def c5_stream(torch, dev, n_frames: int, barrier, maxred, world: int):
+    """BASELINE.json configs[4]: one 512 x 512 TUM-VI-shaped camera stream per GPU (Examples/Monocular/TUM-VI.yaml:66-67 -> 850
+    features, 4 levels, 1.2, threshold 0.02), frame by frame through the host API: 4-level extraction + association with
+    the previous frame (one call, frame from page-locked memory, keypoints / descriptors / global descriptor / match row
+    back) + the masked best-2 search of SearchByProjection(CurrentFrame, LastFrame) on the resident descriptors.  All ranks
+    run their stream at the same time; the figure is frames/s over all streams (slowest rank's wall clock)."""
+    from hfnet_slam_b200 import weights
+    from hfnet_slam_b200.extractor import features_per_level
+    from hfnet_slam_b200.lib import Context, pinned_empty
+    Hc = Wc = 512
+    budgets = features_per_level(850, 4, 1.2)
+    ctx = Context(height=Hc, width=Wc, n_levels=4, scale_factor=1.2, max_keypoints=850, max_batch=1, with_global=True,
+                  device=dev.index or 0)
+    ctx.load_weights(weights.synthetic_blob(seed=0))
+    base = weights.synthetic_image(Hc, Wc, seed=12, n_corners=250)
+    frame = pinned_empty((Hc, Wc), np.uint8)
+    match_out = (pinned_empty((1, ctx.kp_cap), np.int32), pinned_empty((1, ctx.kp_cap), np.float32))
+    prev, n_kp, n_cand, dt = None, 0, 0, 0.0
+    for warm in (True, False):
+        n = 10 if warm else n_frames
+        if not warm:
+            barrier()
+        t0 = time.perf_counter()
+        for i in range(n):
+            frame[...] = np.roll(base, (2 * i, 3 * i), axis=(0, 1))
+            f, midx, _ = ctx.extract_match_batch([frame], budgets, 0.02, 0, 0.6, pinned=True, out=match_out)
+            f = f[0]
+            xy, octv = np.stack([f["x"], f["y"]], 1), f["octave"].copy()
+            if prev is not None and len(xy) and len(prev[0]):
+                q = len(prev[0])
+                uv = prev[0] + np.float32([3.0, 2.0])
+                rad = (np.float32(15.0) * np.float32(1.2) ** prev[1]).astype(np.float32)
+                idx, _, _ = ctx.match_projection_frame(0, np.arange(q, dtype=np.int32), uv, rad, prev[1] - 1, prev[1] + 1, nf=len(xy))
+                if not warm:
+                    n_cand += int((idx[:, 0] >= 0).sum())
+            if not warm:
+                n_kp += len(xy)
+            prev = (xy, octv)
+        if not warm:
+            dt = maxred(time.perf_counter() - t0)
+    ctx.close()
+    return {"frames_per_s": world * n_frames / dt, "streams": world, "ms_per_frame_per_stream": 1e3 * dt / n_frames,
+            "keypoints_per_frame": n_kp / n_frames, "windowed_matches_per_frame": n_cand / max(n_frames - 0, 1),
+            "frames": n_frames, "note": "512x512, 4 levels, 850 keypoints, threshold 0.02, one stream per GPU; host API, "
+                                        "one frame per call (H2D of the frame, D2H of the features and match row inside)"}
+
+
 def c3_cpu(n_frames: int):
     """The same per-frame / per-keyframe schedule restated on the CPU (oracle/): the reference's CPU stages as they are
     (cv::resize pyramid, threshold / top-k / Resampler, cv::BFMatcher, C restatements of the matcher, database scan, pose
@@ -851,6 +898,7 @@ def main_gpu(args):
         if world == 1:
             extra["match_c1"] = extra_match_c1(torch, dev, pk, cpu_arms)
             extra["lba"] = extra_lba(ctx, cpu_arms)
+        extra["c5"] = c5_stream(torch, dev, args.c5_frames, barrier, maxred, world)
         extra["loopdb"] = extra_loopdb(torch, dist, ctx, dev, pk, world, rank, args.db_rows, barrier, maxred, stream, cpu_arms)
         if world == 1:
             c3 = {"gpu": c3_gpu(torch, dev, args.c3_frames, 2), "gpu_one_thread": c3_gpu(torch, dev, args.c3_frames, 1)}
@@ -914,6 +962,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=8, help="reference arm: frames per step (bounded sample)")
     ap.add_argument("--c3-frames", type=int, default=120)
     ap.add_argument("--c3-cpu-frames", type=int, default=13)
+    ap.add_argument("--c5-frames", type=int, default=200)
     ap.add_argument("--skip-extra", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
