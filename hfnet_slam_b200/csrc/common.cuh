@@ -155,7 +155,9 @@ struct hfb_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t copy_stream = nullptr;   // in-graph D2H of the local features, concurrent with the matching kernels
   cudaEvent_t ev_local = nullptr, ev_copied = nullptr;
+  cudaEvent_t ev_carry_fork = nullptr, ev_carry = nullptr;   // the carry of the previous call's descriptors runs beside the encoder
   bool fork_branches = true;            // HFB_FORK=0: everything on one stream
+  bool carry_side = false;              // HFB_CARRY_SIDE=1: the carry of the previous call's descriptors on the copy stream beside the encoder (ctx.cu)
   // pyramid levels >= 1 run on their own streams (fork after the resize chain, join before the sampling kernels): a
   // single frame's level grids are far smaller than the machine, so the levels fill each other's idle SMs
   cudaStream_t level_stream[HFB_MAX_LEVELS] = {nullptr};

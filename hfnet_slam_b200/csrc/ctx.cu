@@ -126,9 +126,12 @@ extern "C" int hfb_create(const hfb_config* cfg, hfb_ctx** out) {
   HFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_local, cudaEventDisableTiming));
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+  HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_carry_fork, cudaEventDisableTiming));
+  HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_carry, cudaEventDisableTiming));
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   if (const char* fk = getenv("HFB_FORK")) ctx->fork_branches = !(fk[0] == '0');
+  if (const char* cs = getenv("HFB_CARRY_SIDE")) ctx->carry_side = !(cs[0] == '0');
   if (const char* fk = getenv("HFB_FORK_LEVELS")) ctx->fork_levels = !(fk[0] == '0');
   if (ctx->n_levels > 1) {
     HFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_level_fork, cudaEventDisableTiming));
@@ -231,6 +234,8 @@ extern "C" void hfb_destroy(hfb_ctx* ctx) {
   if (ctx->h_post) cudaFreeHost(ctx->h_post);
   if (ctx->ev_local) cudaEventDestroy(ctx->ev_local);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+  if (ctx->ev_carry_fork) cudaEventDestroy(ctx->ev_carry_fork);
+  if (ctx->ev_carry) cudaEventDestroy(ctx->ev_carry);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -490,12 +495,24 @@ __global__ void carry_prev_kernel(float* __restrict__ kdesc, const int* __restri
   if (blockIdx.x == 0 && threadIdx.x == 0) state[1 + s] = cnt;
 }
 
+// The carry only feeds the association at the end of the call and must be done before the sampling kernels overwrite the
+// frame slots it reads.  HFB_CARRY_SIDE=1 runs it on the copy stream beside the encoder (fork here, join before the
+// sampling kernels) instead of ahead of the first layer: measured -10 us on the device-resident single-context call
+// (0.563 -> 0.552 ms per 8 frames, 0.264 -> 0.258 ms single frame) but +19 us on the host-buffer call, whose in-graph
+// D2H of the descriptors shares that branch (end to end 16.1 k -> 14.3 k frames/s) -- so it stays off by default.
 static int enqueue_carry(hfb_ctx* ctx, int B) {
   const int slots = ctx->stream_mode == 0 ? 1 : B;
   dim3 grid(std::max(1, std::min(32, ctx->kp_cap / 32)), slots);
-  carry_prev_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_kdesc, ctx->d_kcount, ctx->d_stream_state, ctx->n_levels,
-                                                  ctx->kp_cap, ctx->stream_mode, B);
+  const bool side = ctx->carry_side && ctx->fork_branches && !ctx->prof_on;
+  cudaStream_t cs = side ? ctx->copy_stream : ctx->stream;
+  if (side) {
+    HFB_CUDA(ctx, cudaEventRecord(ctx->ev_carry_fork, ctx->stream));
+    HFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_carry_fork, 0));
+  }
+  carry_prev_kernel<<<grid, 256, 0, cs>>>(ctx->d_kdesc, ctx->d_kcount, ctx->d_stream_state, ctx->n_levels, ctx->kp_cap,
+                                         ctx->stream_mode, B);
   HFB_CHECK_LAUNCH(ctx, "carry_prev");
+  if (side) HFB_CUDA(ctx, cudaEventRecord(ctx->ev_carry, cs));
   return HFB_OK;
 }
 
@@ -534,6 +551,7 @@ static int enqueue_extract(hfb_ctx* ctx, int B, const int32_t* n_per_level, floa
     }
   }
   for (int l = 1; fork_lv && l < ctx->n_levels; ++l) HFB_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_level_join[l], 0));
+  if (ctx->carry_side && ctx->fork_branches && !ctx->prof_on) HFB_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_carry, 0));   // join the carry
   for (int l = 0; l < ctx->n_levels; ++l) {
     LevelPlan& lv = ctx->lv[l];
     HFB_TRY(launch_sample(ctx, lv.H8, lv.W8, lv.d_descmap, lv.H8 / 8, lv.W8 / 8, ctx->d_sel + (size_t)l * nb * 8192,

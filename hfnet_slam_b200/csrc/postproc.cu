@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(1024) select_topk_kernel(const u64* __restrict
   extern __shared__ u64 s_keys[];  // [P]
   __shared__ int s_hist[256];
   __shared__ u64 s_prefix;
-  __shared__ int s_remaining, s_fill;
+  __shared__ int s_remaining, s_fill, s_done;
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(1024) select_topk_kernel(const u64* __restrict
     if (tid == 0) {
       s_prefix = 0ull;
       s_remaining = k;
+      s_done = 0;
     }
     for (int pass = 0; pass < 8; ++pass) {
       const int shift = 56 - 8 * pass;
@@ -272,10 +273,14 @@ __global__ void __launch_bounds__(1024) select_topk_kernel(const u64* __restrict
           if (suffix_incl >= rem && suffix_excl < rem) {    // exactly one bin qualifies
             s_prefix = prefix | ((u64)tid << shift);
             s_remaining = rem - suffix_excl;
+            // the whole bin is wanted: every key with this prefix is selected, the threshold is the prefix itself (low
+            // bits zero) and the remaining passes would only refine inside a bin that is taken completely
+            if (suffix_incl == rem) s_done = 1;
           }
         }
       }
       __syncthreads();
+      if (s_done) break;
     }
     kth = s_prefix;
   }
