@@ -115,7 +115,8 @@ public:
      * library as one CUDA graph with one H2D of the frame and one D2H of the results.  vnFeaturesPerLevel is
      * HFextractor::mnFeaturesPerLevel.  Returns the number of keypoints, -1 on a bad image like :145. */
     int ExtractPyramid(const cv::Mat &image, const std::vector<int> &vnFeaturesPerLevel, float threshold,
-                       std::vector<cv::KeyPoint> &vKeyPoints, cv::Mat &localDescriptors, cv::Mat &globalDescriptors)
+                       std::vector<cv::KeyPoint> &vKeyPoints, cv::Mat &localDescriptors, cv::Mat &globalDescriptors,
+                       bool bKeepDescriptorsOnDevice = false)   /* true: localDescriptors comes back empty, the rows stay in HBM */
     {
         if (image.empty() || image.type() != CV_8UC1) return -1;
         HFNetB200Engine &e = *mEngine;
@@ -126,11 +127,11 @@ public:
         for (int l = 0; l < e.nLevels; ++l) { budget[l] = vnFeaturesPerLevel[l]; total += vnFeaturesPerLevel[l]; }
         std::vector<float> x(total), y(total), r(total);
         std::vector<int32_t> o(total);
-        localDescriptors = cv::Mat(std::max(total, 1), HFB_DESC_DIM, CV_32F);
+        localDescriptors = bKeepDescriptorsOnDevice ? cv::Mat() : cv::Mat(std::max(total, 1), HFB_DESC_DIM, CV_32F);
         cv::Mat g(HFB_GLOBAL_DIM, 1, CV_32F);
         hfb_features f;
         f.x = x.data(); f.y = y.data(); f.response = r.data(); f.octave = o.data();
-        f.descriptors = localDescriptors.ptr<float>();
+        f.descriptors = bKeepDescriptorsOnDevice ? nullptr : localDescriptors.ptr<float>();
         f.global_descriptor = g.ptr<float>();
         int status;
         {
@@ -140,7 +141,7 @@ public:
         }
         if (status != HFB_OK) return -1;
         Fill(f, x, y, r, o, vKeyPoints);
-        localDescriptors = localDescriptors.rowRange(0, f.n_total);
+        if (!bKeepDescriptorsOnDevice) localDescriptors = localDescriptors.rowRange(0, f.n_total);
         globalDescriptors = g;
         return f.n_total;
     }

@@ -110,6 +110,13 @@ int main(int argc, char** argv) {
     const int n = static_cast<HFNetB200Model*>(models[0])->ExtractPyramid(image, budget, thr, kps, desc, g);
     if (n < 0) return 9;
     dump_features(dir, "pyramid", kps, desc, &g);
+    // the same call with the local descriptors left on the device: same keypoints and global descriptor, no descriptor rows
+    std::vector<cv::KeyPoint> kps2;
+    cv::Mat desc2, g2;
+    const int n2 = static_cast<HFNetB200Model*>(models[0])->ExtractPyramid(image, budget, thr, kps2, desc2, g2, true);
+    if (n2 != n || !desc2.empty() || std::memcmp(g2.data, g.data, HFB_GLOBAL_DIM * 4) != 0) return 15;
+    for (int i = 0; i < n; ++i)
+      if (kps2[i].pt.x != kps[i].pt.x || kps2[i].pt.y != kps[i].pt.y || kps2[i].octave != kps[i].octave) return 16;
   }
   hfb_ctx* ctx = static_cast<HFNetB200Model*>(models[0])->Engine()->ctx;
   // 4. Matcher
