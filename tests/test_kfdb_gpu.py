@@ -290,3 +290,46 @@ def test_device_side_shard_exchange_two_processes_ipc(native_lib, tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("RANK_OK") == 2
+
+
+def test_repeated_queries_leave_no_state_behind(small_ctx):
+    """A query costs no memset: the scan finds best / count zeroed by the PREVIOUS query's last block.  Alternating
+    queries with a high best (planted near-duplicate), a low best (random direction), long candidate lists (> 64: the
+    second fetch), erasures and insertions in between must each equal the oracle on the current rows."""
+    n = 1500
+    db, q, qi = synthetic.keyframe_db(n, 4096, n_planted=40, seed=21, n_queries=2)
+    rng = np.random.default_rng(3)
+    rand_q = rng.standard_normal(4096).astype(np.float32)
+    rand_q /= np.linalg.norm(rand_q)
+    ids = np.arange(n, dtype=np.int64) + 11
+    kf = KeyFrameDatabase(small_ctx, capacity=n + 4)
+    kf.add_many(ids, db)
+    live = np.ones(n, bool)
+
+    def check(query, rel, floor):
+        cand, scores, best = kf.query(query, rel=rel, floor=floor)
+        sc_ref = kfdb_ref.scores(query, db[live])
+        lids = ids[live]
+        best_ref = float(sc_ref.max())
+        assert abs(best - best_ref) <= TOL, (best, best_ref)
+        thr = max(floor, rel * best_ref)
+        sure = {int(i) for i in lids[sc_ref > thr + 5e-6]}
+        maybe = {int(i) for i in lids[np.abs(sc_ref - thr) <= 5e-6]}
+        got = {int(c) for c in cand}
+        assert sure <= got <= (sure | maybe), (len(got), len(sure))
+        return len(got), best
+
+    n_hi, b_hi = check(q[0], 0.8, 0.0)
+    n_lo, b_lo = check(rand_q, 0.8, 0.0)            # a much lower best right after a high one
+    assert b_lo < 0.5 * b_hi
+    n_long, _ = check(rand_q, 0.05, 0.0)            # hundreds of candidates: longer than the head of the list
+    assert n_long > 64
+    for victim in (int(ids[qi[0]]), int(ids[3]), int(ids[n - 1])):
+        kf.erase(victim)
+        live[victim - 11] = False
+    n_hi2, b_hi2 = check(q[0], 0.8, 0.0)
+    assert b_hi2 <= b_hi
+    check(q[1], 0.8, 0.5)
+    check(rand_q, 0.8, 0.0)
+    check(q[0], 0.3, 0.0)
+    kf.close()
