@@ -301,6 +301,9 @@ def test_repeated_queries_leave_no_state_behind(small_ctx):
     rng = np.random.default_rng(3)
     rand_q = rng.standard_normal(4096).astype(np.float32)
     rand_q /= np.linalg.norm(rand_q)
+    for k, sc in enumerate(np.linspace(0.1, 0.9, 300)):          # 300 rows at graded distances from query 0
+        v = q[0] + np.float32(sc / 64.0) * rng.standard_normal(4096).astype(np.float32)
+        db[100 + k] = v / np.linalg.norm(v)
     ids = np.arange(n, dtype=np.int64) + 11
     kf = KeyFrameDatabase(small_ctx, capacity=n + 4)
     kf.add_many(ids, db)
@@ -322,9 +325,9 @@ def test_repeated_queries_leave_no_state_behind(small_ctx):
     n_hi, b_hi = check(q[0], 0.8, 0.0)
     n_lo, b_lo = check(rand_q, 0.8, 0.0)            # a much lower best right after a high one
     assert b_lo < 0.5 * b_hi
-    n_long, _ = check(rand_q, 0.05, 0.0)            # hundreds of candidates: longer than the head of the list
+    n_long, _ = check(q[0], 0.05, 0.0)              # hundreds of candidates: longer than the head of the list
     assert n_long > 64
-    for victim in (int(ids[qi[0]]), int(ids[3]), int(ids[n - 1])):
+    for victim in (int(ids[qi[0]]), int(ids[100]), int(ids[3]), int(ids[n - 1])):
         kf.erase(victim)
         live[victim - 11] = False
     n_hi2, b_hi2 = check(q[0], 0.8, 0.0)
