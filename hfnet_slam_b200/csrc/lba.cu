@@ -464,8 +464,8 @@ __global__ void lba_reduce2_kernel(const double* __restrict__ a, const double* _
 
 // The reduced camera system on the device (g2o: LinearSolverEigen::solve, Thirdparty/g2o/g2o/solvers/
 // linear_solver_eigen.h:94-124, a sparse LDLT of the same matrix): one CTA, Hschur as a packed lower triangle in shared
-// memory (N <= 192: 148 KB), right-looking Cholesky (the rank-1 update of the trailing triangle is flattened over the
-// whole CTA), column-oriented forward / backward substitution, then the pose update
+// memory (N <= 192: 148 KB), blocked right-looking Cholesky with the forward substitution carried along, backward
+// substitution by block inverses, then the pose update
 // exp(xp) * T of every optimisable camera (types_six_dof_expmap.h:73-76) and the camera part of the gain-ratio
 // denominator.  scal[4] = sum xp (lambda xp + bp), scal[5] = 1 if the factorisation succeeded (else xp = 0).
 #define LBA_SOLVE_MAX_N 192
@@ -977,11 +977,11 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   // The reduced system is solved on the device (lba_solve_kernel) unless it does not fit one CTA's shared memory or the
   // host-solve mode is requested (HFB_LBA_HOST_SOLVE=1: the round-1 path, kept as the cross-check of the device solver).
   const char* hs_env = getenv("HFB_LBA_HOST_SOLVE");
-  const size_t solve_smem = (size_t)N * (N + 1) / 2 * 9 + 16;   // packed triangle (doubles) + packed-index -> column bytes
+  const size_t solve_smem = (size_t)N * (N + 1) / 2 * 8 + 16;   // packed triangle (doubles)
   const bool dev_solve = N > 0 && N <= LBA_SOLVE_MAX_N && !(hs_env && hs_env[0] == '1');
   if (dev_solve) {
     static SmemOptIn optin;
-    HFB_CUDA(ctx, optin.ensure(lba_solve_kernel, ctx->device, (size_t)LBA_SOLVE_MAX_N * (LBA_SOLVE_MAX_N + 1) / 2 * 9 + 16));
+    HFB_CUDA(ctx, optin.ensure(lba_solve_kernel, ctx->device, (size_t)LBA_SOLVE_MAX_N * (LBA_SOLVE_MAX_N + 1) / 2 * 8 + 16));
   }
   std::vector<double> poses(problem->poses, problem->poses + (size_t)nc * 7), poses_t(poses);
   std::vector<double> Hs((size_t)N * N), bs(N), bp(N), xp(N);
