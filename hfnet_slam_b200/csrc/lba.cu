@@ -57,8 +57,11 @@ __device__ __forceinline__ double lba_shfl_xor(double v, int o) {
 // j, j + LBA_PL, ... and the landmark's sums (Hll, bl, rho) are joined by a fixed xor butterfly (bit-reproducible).
 // mode 0 = full linearisation; mode 1 = error evaluation only (chi2, rho).
 #define LBA_PL 8
+// tail != 0 (LM trial, mode 1): the block that finishes last also sums the trial's robust chi2 (rho_pt) and the landmark
+// part of the gain-ratio denominator (scale_pt, from the back-substitution before) in a fixed order into scal[2] / scal[3]
+// and posts scal[0..5] + the sequence number into page-locked host memory -- the trial needs no reduction launch.
 __global__ void lba_linearize_kernel(LbaDev d, const double* __restrict__ poses, const double* __restrict__ points,
-                                     double* __restrict__ chi2_out, int mode) {
+                                     double* __restrict__ chi2_out, int mode, int tail, volatile double* post, double seq) {
   pdl_launch_dependents();
   pdl_wait();
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,12 +139,51 @@ __global__ void lba_linearize_kernel(LbaDev d, const double* __restrict__ poses,
       b0 += lba_shfl_xor(b0, o); b1 += lba_shfl_xor(b1, o); b2 += lba_shfl_xor(b2, o);
     }
   }
-  if (!live || sub != 0) return;
-  d.rho_pt[p] = rho_sum;
-  if (mode == 0) {
-    double* h = d.Hll + 6 * (size_t)p;
-    h[0] = H0; h[1] = H1; h[2] = H2; h[3] = H3; h[4] = H4; h[5] = H5;
-    d.bl[3 * p] = b0; d.bl[3 * p + 1] = b1; d.bl[3 * p + 2] = b2;
+  if (live && sub == 0) {
+    d.rho_pt[p] = rho_sum;
+    if (mode == 0) {
+      double* h = d.Hll + 6 * (size_t)p;
+      h[0] = H0; h[1] = H1; h[2] = H2; h[3] = H3; h[4] = H4; h[5] = H5;
+      d.bl[3 * p] = b0; d.bl[3 * p + 1] = b1; d.bl[3 * p + 2] = b2;
+    }
+  }
+  if (!tail) return;
+  __shared__ int s_last;
+  __shared__ double s_red[2][128];
+  int* ticket = reinterpret_cast<int*>(d.scal + 8);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int t = threadIdx.x;                     // 128 threads: strided partial sums, then a fixed tree
+  double a0 = 0, a1 = 0;
+  for (int i = t; i < d.n_points; i += 128) {
+    a0 += __ldcg(d.rho_pt + i);
+    a1 += __ldcg(d.scale_pt + i);
+  }
+  s_red[0][t] = a0;
+  s_red[1][t] = a1;
+  __syncthreads();
+  for (int s2 = 64; s2 > 0; s2 >>= 1) {
+    if (t < s2) {
+      s_red[0][t] += s_red[0][t + s2];
+      s_red[1][t] += s_red[1][t + s2];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    d.scal[2] = s_red[0][0];
+    d.scal[3] = s_red[1][0];
+    *ticket = 0;
+    if (post) {
+      post[0] = d.scal[0]; post[1] = d.scal[1]; post[2] = s_red[0][0]; post[3] = s_red[1][0];
+      post[4] = __ldcg(d.scal + 4); post[5] = __ldcg(d.scal + 5);
+      __threadfence_system();
+      post[6] = seq;
+      __threadfence_system();
+    }
   }
 }
 
@@ -865,7 +907,7 @@ static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost
                o_Hll = take((size_t)np * 48), o_bl = take((size_t)np * 24), o_Dinv = take((size_t)np * 48),
                o_rho = take((size_t)np * 8), o_scale = take((size_t)np * 8), o_Hpp = take((size_t)no * 288 + 8),
                o_bp = take((size_t)no * 48 + 8), o_part = take((size_t)d.G * part_stride * 8 + 8),
-               o_Hs = take(N * N * 8 + 8), o_bs = take(N * 8 + 8), o_xp = take(N * 8 + 8), o_scal = take(64),
+               o_Hs = take(N * N * 8 + 8), o_bs = take(N * 8 + 8), o_xp = take(N * 8 + 8), o_scal = take(256),
                o_depth = take((size_t)ne + 8);
   HFB_TRY(ctx->ensure_scratch(off));
   uint8_t* a = reinterpret_cast<uint8_t*>(ctx->d_scratch);
@@ -884,6 +926,7 @@ static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost
   d.Hs = (double*)(a + o_Hs); d.bs = (double*)(a + o_bs); d.xp = (double*)(a + o_xp); d.scal = (double*)(a + o_scal);
   d.depth_ok = (unsigned char*)(a + o_depth);
   cudaStream_t st = ctx->stream;
+  HFB_CUDA(ctx, cudaMemsetAsync(d.scal, 0, 256, st));   // scalars + the completion ticket of the trial's last kernel (scal + 8)
   HFB_CUDA(ctx, cudaMemcpyAsync(d.poses, pr->poses, (size_t)nc * 56, cudaMemcpyHostToDevice, st));
   if (np) HFB_CUDA(ctx, cudaMemcpyAsync(d.points, pr->points, (size_t)np * 24, cudaMemcpyHostToDevice, st));
   if (ne) {
@@ -903,17 +946,19 @@ static int lba_setup(hfb_ctx* ctx, const hfb_lba_problem* pr, LbaDev& d, LbaHost
 
 // computeActiveErrors + buildSystem at (d.poses, d.points): fills Hll/bl/Hpl/Hpp/bp, chi2 into chi2_buf,
 // scal[0] = robust chi2, scal[1] = max |diag|.
-static int lba_build(hfb_ctx* ctx, LbaDev& d, double* chi2_buf, int want_maxdiag) {
+static int lba_build(hfb_ctx* ctx, LbaDev& d, double* chi2_buf, int want_maxdiag, bool need_scalars = true) {
   if (d.n_points > 0) {
-    hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses, (const double*)d.points, chi2_buf, 0);
+    hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses, (const double*)d.points, chi2_buf, 0, 0, (volatile double*)nullptr, 0.0);
     HFB_CHECK_LAUNCH(ctx, "lba_linearize");
   }
   if (d.n_opt > 0) {
     hfb_launch(ctx, lba_camera_kernel, dim3(d.n_opt), dim3(256), 0, d);
     HFB_CHECK_LAUNCH(ctx, "lba_camera");
   }
-  hfb_launch(ctx, lba_reduce_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, d.n_points, d.scal, 0, d, want_maxdiag);
-  HFB_CHECK_LAUNCH(ctx, "lba_reduce");
+  if (need_scalars) {   // robust chi2 / largest diagonal entry of the linearisation: nobody reads them after iteration 0
+    hfb_launch(ctx, lba_reduce_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, d.n_points, d.scal, 0, d, want_maxdiag);
+    HFB_CHECK_LAUNCH(ctx, "lba_reduce");
+  }
   return HFB_OK;
 }
 
@@ -999,7 +1044,7 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   const bool first_build_has_chi = iterations > 0 && !terminate();
   if (!first_build_has_chi) {
     if (d.n_points > 0) {
-      hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses, (const double*)d.points, chi2_last, 1);
+      hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses, (const double*)d.points, chi2_last, 1, 0, (volatile double*)nullptr, 0.0);
       HFB_CHECK_LAUNCH(ctx, "lba_errors");
     }
     hfb_launch(ctx, lba_reduce_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, d.n_points, d.scal, 0, d, 0);
@@ -1010,7 +1055,7 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   }
   for (int it = 0; it < iterations; ++it) {
     if (!(it == 0 && first_build_has_chi) && terminate()) break;
-    HFB_TRY(lba_build(ctx, d, chi2_last, it == 0));
+    HFB_TRY(lba_build(ctx, d, chi2_last, it == 0, it == 0 || !dev_solve));
     // The host needs the linearisation's scalars only at the first iteration (lambda from the largest diagonal entry) or
     // when it solves the reduced system itself: afterwards the robust chi2 of the estimate IS the accepted trial's
     // (same kernel, same summation order: bitwise equal), so later iterations enqueue straight through to the trial.
@@ -1049,19 +1094,21 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
         for (int s = 0; s < no; ++s) h_pose_oplus(&poses[(size_t)h.opt_cams[s] * 7], &xp[(size_t)6 * s], &poses_t[(size_t)h.opt_cams[s] * 7]);
         HFB_CUDA(ctx, cudaMemcpyAsync(d.poses_t, poses_t.data(), (size_t)nc * 56, cudaMemcpyHostToDevice, st));
       }
+      // the trial's scalars come back through page-locked memory the last kernel writes itself; the host polls the
+      // sequence number (no copy operation, no stream synchronisation, no reduction launch per trial)
+      const double seq = (double)(++ctx->post_seq);
       if (d.n_points > 0) {
         hfb_launch(ctx, lba_backsub_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, lambda);
         HFB_CHECK_LAUNCH(ctx, "lba_backsub");
-        hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses_t, (const double*)d.points_t, chi2_other, 1);
+        hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses_t,
+                   (const double*)d.points_t, chi2_other, 1, 1, (volatile double*)ctx->h_post, seq);
         HFB_CHECK_LAUNCH(ctx, "lba_errors");
+      } else {
+        hfb_launch(ctx, lba_reduce2_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, (const double*)d.scale_pt, d.n_points, d.scal, 2, 3,
+                   (volatile double*)ctx->h_post, seq);
+        HFB_CHECK_LAUNCH(ctx, "lba_reduce2");
       }
       std::swap(chi2_last, chi2_other);
-      // the trial's scalars come back through page-locked memory the kernel writes itself; the host polls the sequence
-      // number (no copy operation, no stream synchronisation per trial)
-      const double seq = (double)(++ctx->post_seq);
-      hfb_launch(ctx, lba_reduce2_kernel, dim3(1), dim3(1024), 0, (const double*)d.rho_pt, (const double*)d.scale_pt, d.n_points, d.scal, 2, 3,
-                 (volatile double*)ctx->h_post, seq);
-      HFB_CHECK_LAUNCH(ctx, "lba_reduce2");
       {
         volatile double* hp = ctx->h_post;
         uint32_t spins = 0;
@@ -1113,7 +1160,7 @@ extern "C" int hfb_lba_optimize(hfb_ctx* ctx, const hfb_lba_problem* problem, in
   }
   // outputs: final estimate, cached chi2 of the LAST error evaluation (src/Optimizer.cc:1425 quirk), depth test
   if (d.n_points > 0 && depth_positive_out) {
-    hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses, (const double*)d.points, chi2_other, 1);
+    hfb_launch(ctx, lba_linearize_kernel, dim3(ceil_div(d.n_points * LBA_PL, 128)), dim3(128), 0, d, (const double*)d.poses, (const double*)d.points, chi2_other, 1, 0, (volatile double*)nullptr, 0.0);
     HFB_CHECK_LAUNCH(ctx, "lba_errors");
     HFB_CUDA(ctx, cudaMemcpyAsync(depth_positive_out, d.depth_ok, (size_t)d.n_edges, cudaMemcpyDeviceToHost, st));
   }
