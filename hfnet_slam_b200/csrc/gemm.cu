@@ -294,6 +294,83 @@ static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
   return HFB_OK;
 }
 
+// Descriptor head (hf_net.py:78-80): bias + tf.nn.l2_normalize over the N = BN = 256 columns -> fp32 rows.  Its own
+// epilogue type (= its own kernel instantiation: the 128 values a thread keeps in registers must not raise the register
+// count of the 3x3 head conv, which runs two CTAs per SM).  The two warps of a TMEM lane group take alternate 32-column
+// slabs; each reads its 128 accumulator columns ONCE (eight tcgen05.ld, one wait), adds the bias, sums the squares of
+// its half, the halves meet through the 16-byte pad of the staging rows (double-buffered by tile parity, one 64-thread
+// named barrier), then the scaled values go out through the staging area with lanes running along the output row.
+struct EpiL2Norm {
+  static constexpr int kWarps = 8;
+  struct Params {
+    float* out;
+    int ldo;
+    const float* bias;
+  };
+  static __device__ __forceinline__ const float* bias(const Params& p) { return p.bias; }
+
+  static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
+    const int lane = threadIdx.x & 31;
+    uint8_t* my = tr.stage + (size_t)lane * EPI_PITCH;
+    uint32_t v[4][32];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t c = (uint32_t)((tr.sub + 2 * k) * EPI_SLAB);
+      uint32_t(&lo)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[k][0]);
+      uint32_t(&hi)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[k][16]);
+      tc::tmem_ld16(tr.taddr + c, lo);
+      tc::tmem_ld16(tr.taddr + c + 16, hi);
+    }
+    tc::tmem_ld_wait();
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4* b4 = reinterpret_cast<const float4*>(tr.s_bias + (tr.sub + 2 * k) * EPI_SLAB);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 b = b4[q];
+        const float x0 = __uint_as_float(v[k][4 * q]) + b.x, x1 = __uint_as_float(v[k][4 * q + 1]) + b.y;
+        const float x2 = __uint_as_float(v[k][4 * q + 2]) + b.z, x3 = __uint_as_float(v[k][4 * q + 3]) + b.w;
+        ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+        v[k][4 * q] = __float_as_uint(x0); v[k][4 * q + 1] = __float_as_uint(x1);
+        v[k][4 * q + 2] = __float_as_uint(x2); v[k][4 * q + 3] = __float_as_uint(x3);
+      }
+    }
+    // halves of the row meet: pad word (tile parity) of my staging row, partner = the other warp of this lane group
+    const int par = (int)(((tr.taddr & 0xFFFFu) / (uint32_t)g.BN) & 1u);   // accumulator stage 0 / 1 alternates with the tiles
+    *reinterpret_cast<float*>(my + EPI_SLAB * 4 + 4 * par) = ss;
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + tr.ewarp) : "memory");
+    const uint8_t* partner = my + (tr.sub ? -4 : 4) * (long long)g.epi_warp_bytes;
+    const float so = *reinterpret_cast<const float*>(partner + EPI_SLAB * 4 + 4 * par);
+    const float s0 = tr.sub ? so : ss, s1 = tr.sub ? ss : so;      // same order in both warps
+    const float inv = rsqrtf(fmaxf(s0 + s1, 1e-12f));
+    // rows this lane writes out: chunk ch of rows (lane >> 3) + 4 i
+    const int ch = lane & 7;
+    const int orow = tr.valid ? (int)tr.row : -1;
+    int drow[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) drow[i] = __shfl_sync(0xffffffffu, orow, (lane >> 3) + 4 * i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4* d = reinterpret_cast<float4*>(my);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        d[q] = make_float4(__uint_as_float(v[k][4 * q]) * inv, __uint_as_float(v[k][4 * q + 1]) * inv,
+                           __uint_as_float(v[k][4 * q + 2]) * inv, __uint_as_float(v[k][4 * q + 3]) * inv);
+      __syncwarp();
+      const int col = tr.n0 + (tr.sub + 2 * k) * EPI_SLAB + ch * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = (lane >> 3) + 4 * i;
+        if (drow[i] < 0) continue;
+        const uint4 q4 = *reinterpret_cast<const uint4*>(tr.stage + (size_t)row * EPI_PITCH + (size_t)ch * 16);
+        *reinterpret_cast<uint4*>(p.out + (long long)drow[i] * p.ldo + col) = q4;
+      }
+      __syncwarp();
+    }
+  }
+};
+
 int gemm_store(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, int B, void* out,
                int ldo, int col_off, const float* bias, const __half* residual, int ldr, int relu6, int f32) {
   EpiStore::Params p{out, ldo, col_off, bias, residual, ldr, relu6, f32, 0};
@@ -305,8 +382,12 @@ int gemm_l2norm(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, co
     ctx->set_error("gemm_l2norm needs BN == N");
     return HFB_ERR_INVALID;
   }
-  EpiStore::Params p{out, g.N, 0, bias, nullptr, 0, 0, 1, 1};
-  return launch_tc<EpiStore>(ctx, tmA, tmB, g, 1, p, "gemm_l2norm", EPI_WARP_BYTES, true);
+  if (g.N != 8 * EPI_SLAB || !bias) {   // general shapes: the two-pass path of EpiStore
+    EpiStore::Params p{out, g.N, 0, bias, nullptr, 0, 0, 1, 1};
+    return launch_tc<EpiStore>(ctx, tmA, tmB, g, 1, p, "gemm_l2norm", EPI_WARP_BYTES, true);
+  }
+  EpiL2Norm::Params p{out, g.N, bias};
+  return launch_tc<EpiL2Norm>(ctx, tmA, tmB, g, 1, p, "gemm_l2norm", EPI_WARP_BYTES, true);
 }
 int gemm_softmax_d2s(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* scores,
                      float* logits, const float* bias, int Hc, int Wc) {
