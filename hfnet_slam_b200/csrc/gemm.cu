@@ -64,13 +64,22 @@ int hfb_make_tmap_2d_f32(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint6
   return HFB_OK;
 }
 
-// fp16 NHWC tensor viewed as (C, W, H, B); box = 64 channels x 16 x 8 x 1 (one 128-pixel patch).
+int hfb_conv_halo() {
+  static const int v = [] {
+    const char* e = getenv("HFB_CONV_HALO");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return v;
+}
+
+// fp16 NHWC tensor viewed as (C, W, H, B); box = 64 channels x 16 x 8 x 1 (one 128-pixel patch), or x 10 rows (the patch
+// with its upper and lower halo row) in halo mode.
 int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B) {
   PFN_encodeTiled enc = get_encode(ctx);
   if (!enc) return HFB_ERR_CUDA;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
-  cuuint32_t box[4] = {64, 16, 8, 1};
+  cuuint32_t box[4] = {64, 16, (cuuint32_t)(hfb_conv_halo() ? 10 : 8), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -129,7 +138,8 @@ struct EpiStore {
   static __device__ __forceinline__ void run(const Params& p, const GemmGeom& g, const TileRow& tr) {
     const int lane = threadIdx.x & 31;
     const int esz = (p.f32 || p.residual) ? 4 : 2;   // staging element size
-    uint8_t* my = tr.stage + (size_t)lane * EPI_PITCH;
+    const int pitch = (int)(g.epi_warp_bytes >> 5);   // bytes per staged row: 144 (fp32 slabs) or 80 (fp16 slabs), odd multiples of 16
+    uint8_t* my = tr.stage + (size_t)lane * pitch;
     const int orow = tr.valid ? (int)tr.row : -1;     // rows < 2^31 (B*H*W pixels)
     float inv = 1.f;
     if (p.l2norm) {
@@ -191,7 +201,7 @@ struct EpiStore {
       for (int row = lane >> sh; row < 32; row += rstep) {
         const int dst_row = __shfl_sync(0xffffffffu, orow, row);
         if (dst_row < 0 || ch >= cpr) continue;
-        const uint4 q = *reinterpret_cast<const uint4*>(tr.stage + (size_t)row * EPI_PITCH + (size_t)ch * 16);
+        const uint4 q = *reinterpret_cast<const uint4*>(tr.stage + (size_t)row * pitch + (size_t)ch * 16);
         if (esz == 2) {
           *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + (long long)dst_row * p.ldo + col + ch * 8) = q;
         } else if (p.f32) {
@@ -280,11 +290,12 @@ static int launch_tc(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tm
   g.bias_bytes = stage_bias ? (uint32_t)((g.N * 4 + 15) & ~15) : 0u;
   const size_t epi_bytes = (size_t)Epi::kWarps * epi_warp_bytes + g.bias_bytes;
   // ring depth: keep the CTA near 110 KB so that two persistent CTAs (8 epilogue warps) share an SM when TMEM allows
-  const size_t stage = GEMM_TILE_A_BYTES + (size_t)g.BN * 128;
-  int st = (int)((110 * 1024 - epi_bytes) / stage);
+  const int halo = g.conv && g.halo;
+  const size_t stage = halo ? (size_t)g.BN * 128 : GEMM_TILE_A_BYTES + (size_t)g.BN * 128;
+  int st = (int)((110 * 1024 - epi_bytes - (halo ? 2 * GEMM_HALO_A_BYTES : 0)) / stage);
   g.stages = st < 2 ? 2 : (st > 4 ? 4 : st);
-  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages);
-  const size_t smem = gemm_smem_bytes(g.BN, g.stages, epi_bytes);
+  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages, halo);
+  const size_t smem = gemm_smem_bytes(g.BN, g.stages, epi_bytes, halo);
   static SmemOptIn optin;  // per instantiation
   HFB_CUDA(ctx, optin.ensure(gemm_tc_kernel<Epi>, ctx->device, smem));
   if (g.total_tiles <= 0) return HFB_OK;
@@ -374,7 +385,9 @@ struct EpiL2Norm {
 int gemm_store(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, int B, void* out,
                int ldo, int col_off, const float* bias, const __half* residual, int ldr, int relu6, int f32) {
   EpiStore::Params p{out, ldo, col_off, bias, residual, ldr, relu6, f32, 0};
-  return launch_tc<EpiStore>(ctx, tmA, tmB, g, B, p, "gemm_store", EPI_WARP_BYTES, bias != nullptr);
+  // fp16 slabs need 64 B per staged row: the smaller staging area buys the 3x3 head conv a third B stage beside a second CTA
+  const uint32_t epi_warp_bytes = (f32 || residual) ? EPI_WARP_BYTES : 32 * (EPI_SLAB * 2 + 16);
+  return launch_tc<EpiStore>(ctx, tmA, tmB, g, B, p, "gemm_store", epi_warp_bytes, bias != nullptr);
 }
 int gemm_l2norm(hfb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmGeom& g, float* out,
                 const float* bias) {

@@ -20,6 +20,8 @@ struct GemmGeom {
   int BN;             // N tile: multiple of 16, <= 256
   int a_k_off;        // first K coordinate inside A's map
   int conv;           // 1 = implicit 3x3
+  int halo;           // conv: 1 = A comes as 10-row halo boxes, one per (64-channel block, dx); the three dy taps of a box are
+                      // sub-views 16 pixel rows (= 2 KB = two swizzle atoms) apart -- 2.4x less A traffic than a box per tap
   int H, W;           // conv: image size; tiles are 8 rows x 16 cols
   int tiles_x, tiles_y;
   int kb_per_row;     // k-blocks per tap (conv) / in total (plain) = ceil(K/64)
@@ -99,11 +101,13 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int tile) {
   return t;
 }
 
-static inline size_t gemm_ring_bytes(int BN, int stages) {
+#define GEMM_HALO_A_BYTES 20480   // 10 x 16 pixels x 128 B
+static inline size_t gemm_ring_bytes(int BN, int stages, int halo = 0) {
+  if (halo) return 2 * (size_t)GEMM_HALO_A_BYTES + (size_t)stages * ((size_t)BN * 128);   // two A boxes + a ring of B tiles
   return (size_t)stages * (GEMM_TILE_A_BYTES + (size_t)BN * 128);
 }
-static inline size_t gemm_smem_bytes(int BN, int stages, size_t epi_bytes) {
-  return 1024 + gemm_ring_bytes(BN, stages) + epi_bytes + 256;
+static inline size_t gemm_smem_bytes(int BN, int stages, size_t epi_bytes, int halo = 0) {
+  return 1024 + gemm_ring_bytes(BN, stages, halo) + epi_bytes + 256;
 }
 
 template <class Epi>
@@ -121,7 +125,9 @@ __global__ void __launch_bounds__(GEMM_THREADS(Epi::kWarps)) gemm_tc_kernel(cons
   uint64_t* empty = bars + 8;       // [8]
   uint64_t* acc_full = bars + 16;   // [2]
   uint64_t* acc_empty = bars + 18;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* a_full = bars + 20;     // [2] halo mode: the two A boxes
+  uint64_t* a_empty = bars + 22;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   tc::pdl_launch_dependents();
@@ -136,6 +142,8 @@ __global__ void __launch_bounds__(GEMM_THREADS(Epi::kWarps)) gemm_tc_kernel(cons
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&acc_full[s], 1);
       tc::mbar_init(&acc_empty[s], Epi::kWarps);   // one arrival per epilogue warp
+      tc::mbar_init(&a_full[s], 1);
+      tc::mbar_init(&a_empty[s], 1);
     }
     tc::fence_barrier_init();
   }
@@ -150,7 +158,82 @@ __global__ void __launch_bounds__(GEMM_THREADS(Epi::kWarps)) gemm_tc_kernel(cons
   tc::pdl_wait();   // prologue done (barriers, TMEM, bias = weights only); operands / residuals come from predecessors
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 0 && g.halo) {
+    // ------------------------------------------------------------------ TMA producer, halo boxes
+    // Groups (64-channel block cb, dx) in order, flattened over this CTA's tiles.  Per group one A box (64 ch x 16 x 10
+    // pixels from (x0 + dx - 1, y0 - 1): out-of-range pixels / channels arrive as zeros = SAME padding) and three B
+    // tiles (taps dy = 0..2).  Issue order B(g,0) B(g,1) A(g+1) B(g,2): each load is issued when its slot frees up.
+    if (lane == 0) {
+      const int groups = 3 * g.kb_per_row;
+      uint8_t* sB = smem + 2 * GEMM_HALO_A_BYTES;
+      const uint32_t b_bytes = (uint32_t)g.BN * 128u;
+      uint32_t ia = 0, ib = 0;
+      auto load_a = [&](int tile, int grp) {
+        const TileCoord t = decode_tile(g, tile);
+        const int cb = grp / 3, dx = grp - cb * 3;
+        const uint32_t sl = ia & 1u;
+        tc::mbar_wait(&a_empty[sl], ((ia >> 1) & 1u) ^ 1u);
+        tc::mbar_expect_tx(&a_full[sl], GEMM_HALO_A_BYTES);
+        tc::tma_load_4d(smem + (size_t)sl * GEMM_HALO_A_BYTES, &tmA, &a_full[sl], cb * 64, t.x0 + dx - 1, t.y0 - 1, t.img);
+        ++ia;
+      };
+      auto load_b = [&](const TileCoord& t, int grp, int dy) {
+        const int cb = grp / 3, dx = grp - cb * 3;
+        const int s = ib % g.stages;
+        tc::mbar_wait(&empty[s], ((ib / g.stages) & 1u) ^ 1u);
+        tc::mbar_expect_tx(&full[s], b_bytes);
+        tc::tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], (dy * 3 + dx) * g.K + cb * 64, t.n0);
+        ++ib;
+      };
+      if ((int)blockIdx.x < g.total_tiles) load_a(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(g, tile);
+        for (int grp = 0; grp < groups; ++grp) {
+          load_b(t, grp, 0);
+          load_b(t, grp, 1);
+          if (grp + 1 < groups) load_a(tile, grp + 1);
+          else if (tile + (int)gridDim.x < g.total_tiles) load_a(tile + gridDim.x, 0);
+          load_b(t, grp, 2);
+        }
+      }
+    }
+  } else if (warp == 1 && g.halo) {
+    // ------------------------------------------------------------------ UMMA issuer, halo boxes
+    if (lane == 0) {
+      const int groups = 3 * g.kb_per_row;
+      const uint32_t sA0 = tc::smem_u32(smem), sB0 = sA0 + 2 * GEMM_HALO_A_BYTES;
+      const uint32_t b_bytes = (uint32_t)g.BN * 128u;
+      uint32_t ia = 0, ib = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        tc::mbar_wait(&acc_empty[as], aph ^ 1u);       // epilogue has drained this accumulator stage
+        tc::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)g.BN;
+        for (int grp = 0; grp < groups; ++grp, ++ia) {
+          const int cb = grp / 3;
+          const int krem = g.K - cb * 64;
+          const int nk = krem >= 64 ? 4 : (krem + 15) >> 4;     // zero-filled channel tail needs no MMA
+          const uint32_t sl = ia & 1u;
+          tc::mbar_wait(&a_full[sl], (ia >> 1) & 1u);
+          for (int dy = 0; dy < 3; ++dy, ++ib) {
+            const int s = ib % g.stages;
+            tc::mbar_wait(&full[s], (ib / g.stages) & 1u);
+            tc::fence_after_sync();
+            // tap dy = rows dy*16 .. dy*16 + 127 of the box: 2 KB = two whole swizzle atoms further
+            const uint64_t da = tc::make_sdesc_sw128(sA0 + sl * GEMM_HALO_A_BYTES + (uint32_t)dy * 2048u);
+            const uint64_t db = tc::make_sdesc_sw128(sB0 + (uint32_t)s * b_bytes);
+            for (int k = 0; k < nk; ++k)
+              tc::umma_f16(d_tmem, tc::sdesc_advance_k16(da, k), tc::sdesc_advance_k16(db, k), g.idesc,
+                           (grp > 0 || dy > 0 || k > 0) ? 1u : 0u);
+            tc::umma_commit(&empty[s]);
+          }
+          tc::umma_commit(&a_empty[sl]);                          // the box is free once all three taps have retired
+        }
+        tc::umma_commit(&acc_full[as]);
+        ++acc_it;
+      }
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
@@ -264,6 +347,7 @@ int hfb_make_tmap_2d(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint64_t 
 int hfb_make_tmap_2d_f32(hfb_ctx* ctx, CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                          uint64_t row_stride_bytes, uint32_t box_outer);
 int hfb_make_tmap_nhwc(hfb_ctx* ctx, CUtensorMap* out, const void* base, int C, int W, int H, int B);
+int hfb_conv_halo();   // 1 (default): 3x3 convolutions load 10-row halo boxes (HFB_CONV_HALO=0: one 8-row box per tap)
 
 static inline uint32_t tmem_cols_for(int BN) {
   uint32_t c = 32;
@@ -277,12 +361,12 @@ static inline void gemm_finish_geom(GemmGeom& g, int m_tiles) {
   g.total_tiles = g.m_tiles * g.n_tiles * (g.pair_tab ? g.n_pairs : 1);
   g.idesc = tc::make_idesc_f16(g.BN);
   g.tmem_cols = tmem_cols_for(g.BN);
-  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages);
+  g.ring_bytes = (uint32_t)gemm_ring_bytes(g.BN, g.stages, g.halo);
 }
 
 static inline void gemm_fill_geom(GemmGeom& g, int M, int N, int K, int BN, int a_k_off) {
   g.M = M; g.N = N; g.K = K; g.BN = BN; g.a_k_off = a_k_off;
-  g.conv = 0; g.H = g.W = 0; g.tiles_x = g.tiles_y = 0;
+  g.conv = 0; g.halo = 0; g.H = g.W = 0; g.tiles_x = g.tiles_y = 0;
   g.kb_per_row = (K + 63) / 64;
   g.num_kb = g.kb_per_row;
   g.stages = 4;
@@ -294,7 +378,7 @@ static inline void gemm_fill_geom(GemmGeom& g, int M, int N, int K, int BN, int 
 }
 static inline void gemm_fill_geom_conv(GemmGeom& g, int B, int H, int W, int C, int N, int BN) {
   g.M = B * H * W; g.N = N; g.K = C; g.BN = BN; g.a_k_off = 0;
-  g.conv = 1; g.H = H; g.W = W; g.tiles_x = (W + 15) / 16; g.tiles_y = (H + 7) / 8;
+  g.conv = 1; g.halo = hfb_conv_halo(); g.H = H; g.W = W; g.tiles_x = (W + 15) / 16; g.tiles_y = (H + 7) / 8;
   g.kb_per_row = (C + 63) / 64;
   g.num_kb = 9 * g.kb_per_row;
   g.stages = 4;
