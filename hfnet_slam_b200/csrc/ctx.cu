@@ -502,7 +502,7 @@ __global__ void carry_prev_kernel(float* __restrict__ kdesc, const int* __restri
 // D2H of the descriptors shares that branch (end to end 16.1 k -> 14.3 k frames/s) -- so it stays off by default.
 static int enqueue_carry(hfb_ctx* ctx, int B) {
   const int slots = ctx->stream_mode == 0 ? 1 : B;
-  dim3 grid(std::max(1, std::min(32, ctx->kp_cap / 32)), slots);
+  dim3 grid(std::max(1, std::min(128, ctx->kp_cap / 8)), slots);   // 1 MB per slot at the default capacity: enough CTAs to move it in ~3 us
   const bool side = ctx->carry_side && ctx->fork_branches && !ctx->prof_on;
   cudaStream_t cs = side ? ctx->copy_stream : ctx->stream;
   if (side) {
