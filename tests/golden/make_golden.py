@@ -15,11 +15,35 @@ sys.path.insert(0, str(ROOT))
 OUT = Path(__file__).resolve().parent
 
 
+def undistort_fixture(cv2):
+    """Frame::UndistortKeyPoints / ComputeImageBounds: outputs of cv2.undistortPoints ITSELF (the function the reference
+    calls, src/Frame.cc:778,809) for EuRoC cam0 and a 5-coefficient fisheye-ish lens on seeded points."""
+    rng = np.random.default_rng(17)
+    x = rng.uniform(-20, 772, 256).astype(np.float32)
+    y = rng.uniform(-20, 500, 256).astype(np.float32)
+    cams = np.array([[458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0],
+                     [380.0, 381.0, 376.0, 240.0, -0.31, 0.12, 0.0007, -0.0004, -0.02]], np.float32)
+    out, bounds = [], []
+    for c in cams:
+        Km = np.array([[c[0], 0, c[2]], [0, c[1], c[3]], [0, 0, 1]], np.float32)
+        d = c[4:] if c[8] != 0 else c[4:8]
+        out.append(cv2.undistortPoints(np.stack([x, y], 1).reshape(-1, 1, 2), Km, d, None, Km).reshape(-1, 2))
+        cr = cv2.undistortPoints(np.array([[[0, 0]], [[752, 0]], [[0, 480]], [[752, 480]]], np.float32), Km, d, None, Km).reshape(4, 2)
+        bounds.append([min(cr[0, 0], cr[2, 0]), max(cr[1, 0], cr[3, 0]), min(cr[0, 1], cr[1, 1]), max(cr[2, 1], cr[3, 1])])
+    np.savez_compressed(OUT / "undistort.npz", seed=np.array([17]), cams=cams, xy_un=np.stack(out).astype(np.float32),
+                        bounds=np.array(bounds, np.float32))
+
+
 def main():
     import cv2
     import torch
     from hfnet_slam_b200 import synthetic, weights
     from oracle import hfnet_ref, kfdb_ref, lba_ref, match_ref, select_ref
+
+    if len(sys.argv) > 1 and sys.argv[1] == "undistort":     # only this fixture (the others stay byte-identical)
+        undistort_fixture(cv2)
+        return
+    undistort_fixture(cv2)
 
     # --- matcher (C1-shaped, smaller): cv2.BFMatcher is the function the reference calls
     A, B = synthetic.descriptor_pair(400, 380, n_true=150, seed=1)

@@ -77,3 +77,19 @@ def test_hfnet_golden():
     assert np.abs(o["scores_dense"][0] - g["scores_dense"].astype(np.float32)).max() < 2e-3
     gd = o["global_descriptor"][0]
     assert float(gd @ g["global_descriptor"]) > 0.9999
+
+
+def undistort_inputs():
+    rng = np.random.default_rng(17)
+    return rng.uniform(-20, 772, 256).astype(np.float32), rng.uniform(-20, 500, 256).astype(np.float32)
+
+
+def test_undistort_golden():
+    """tests/golden/undistort.npz holds cv2.undistortPoints' own outputs: the oracle must reproduce them bit for bit."""
+    g = np.load(G / "undistort.npz")
+    x, y = undistort_inputs()
+    for c, xy, b in zip(g["cams"], g["xy_un"], g["bounds"]):
+        dist = c[4:] if c[8] != 0 else c[4:8]
+        ux, uy = select_ref.undistort_points(x, y, c[:4], dist)
+        assert np.array_equal(ux, xy[:, 0]) and np.array_equal(uy, xy[:, 1])
+        assert np.array_equal(select_ref.image_bounds(752, 480, c[:4], dist), b)

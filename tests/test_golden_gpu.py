@@ -75,3 +75,15 @@ def test_hfnet_golden(native_lib, weights_blob):
         assert np.abs(sc - g["scores_dense"].astype(np.float32)).max() <= 4e-3
         gd = out["global_descriptor"]
         assert float(gd @ g["global_descriptor"]) / np.linalg.norm(gd) >= 0.999
+
+
+def test_undistort_golden(small_ctx):
+    """The device kernel against cv2.undistortPoints' own outputs (tests/golden/undistort.npz), bit for bit."""
+    from tests.test_golden_cpu import undistort_inputs
+    g = np.load(G / "undistort.npz")
+    x, y = undistort_inputs()
+    for c, xy, b in zip(g["cams"], g["xy_un"], g["bounds"]):
+        small_ctx.set_camera(c[:4], c[4:] if c[8] != 0 else c[4:8])
+        ux, uy = small_ctx.undistort_points(x, y)
+        assert np.array_equal(ux, xy[:, 0]) and np.array_equal(uy, xy[:, 1])
+        assert np.array_equal(small_ctx.image_bounds(752, 480), b)
