@@ -707,28 +707,34 @@ static int proj_common(hfb_ctx* ctx, const float* Q, const int32_t* q_index, con
                        (f_res ? (dF_res && d_fx && d_fy && d_flevel) : (f_xy && f_level)), "null input");
   auto al = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
   const int n_tiles = ceil_div(nf, MATCH_BN);
-  // io block: Q | F | uv | r | minl | maxl | fxy | flevel | fskip | finv | q_index | cand_idx | cand_dist | cand_level
+  // io block: Q | F | [uv | r | minl | maxl | q_index] | fxy | flevel | fskip | finv | [cand_idx | cand_dist | cand_level]
+  // The bracketed groups are contiguous: the per-query windows go up as ONE copy out of a page-locked staging block and
+  // the candidate lists come back as ONE copy into it (eight small pageable copies cost ~50 us of a ~170 us call).
   const size_t oQ = 0, oF = oQ + al((size_t)nq * 1024), o_uv = oF + (f_res ? 0 : al((size_t)nf * 1024)),
                o_r = o_uv + al((size_t)nq * 8), o_mn = o_r + al((size_t)nq * 4), o_mx = o_mn + al((size_t)nq * 4),
-               o_fxy = o_mx + al((size_t)nq * 4), o_fl = o_fxy + al((size_t)nf * 8), o_fs = o_fl + al((size_t)nf * 4),
-               o_fi = o_fs + al((size_t)nf), o_qi = o_fi + al((size_t)nf * 4), o_ci = o_qi + al((size_t)nq * 4),
+               o_qi = o_mx + al((size_t)nq * 4), o_fxy = o_qi + al((size_t)nq * 4), o_fl = o_fxy + al((size_t)nf * 8),
+               o_fs = o_fl + al((size_t)nf * 4), o_fi = o_fs + al((size_t)nf), o_ci = o_fi + al((size_t)nf * 4),
                o_cd = o_ci + al((size_t)nq * PROJ_K * 4), o_cl = o_cd + al((size_t)nq * PROJ_K * 4),
                io_total = o_cl + al((size_t)nq * PROJ_K * 4);
+  const size_t q_blk = o_fxy - o_uv, out_blk = io_total - o_ci;
   HFB_TRY(ctx->ensure_io(io_total));
+  HFB_TRY(ctx->ensure_stage(q_blk + out_blk));
   uint8_t* io = reinterpret_cast<uint8_t*>(ctx->d_io);
+  uint8_t* hs = reinterpret_cast<uint8_t*>(ctx->h_stage);
   cudaStream_t st = ctx->stream;
+  memcpy(hs, q_uv, (size_t)nq * 8);
+  memcpy(hs + (o_r - o_uv), q_radius, (size_t)nq * 4);
+  memcpy(hs + (o_mn - o_uv), q_min_level, (size_t)nq * 4);
+  memcpy(hs + (o_mx - o_uv), q_max_level, (size_t)nq * 4);
+  if (q_res) memcpy(hs + (o_qi - o_uv), q_index, (size_t)nq * 4);
+  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_uv, hs, q_blk, cudaMemcpyHostToDevice, st));
   if (q_res) {
-    HFB_CUDA(ctx, cudaMemcpyAsync(io + o_qi, q_index, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
     proj_gather_rows_kernel<<<nq, 64, 0, st>>>(dQ_base, reinterpret_cast<const int*>(io + o_qi), nq,
                                                reinterpret_cast<float*>(io + oQ));
     HFB_CHECK_LAUNCH(ctx, "proj_gather");
   } else {
     HFB_CUDA(ctx, cudaMemcpyAsync(io + oQ, Q, (size_t)nq * 1024, cudaMemcpyHostToDevice, st));
   }
-  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_uv, q_uv, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_r, q_radius, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_mn, q_min_level, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(io + o_mx, q_max_level, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
   const float* dF;
   const int* dFlev;
   if (f_res) {
@@ -790,10 +796,11 @@ static int proj_common(hfb_ctx* ctx, const float* Q, const int32_t* q_index, con
   hfb_launch(ctx, proj_finalize_kernel, ceil_div(nq, 8), 256, 0, dQ, dF, rec, n_tiles, nq, dFlev,
              reinterpret_cast<int*>(io + o_ci), reinterpret_cast<float*>(io + o_cd), reinterpret_cast<int*>(io + o_cl));
   HFB_CHECK_LAUNCH(ctx, "proj_finalize");
-  HFB_CUDA(ctx, cudaMemcpyAsync(cand_idx, io + o_ci, (size_t)nq * PROJ_K * 4, cudaMemcpyDeviceToHost, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(cand_dist, io + o_cd, (size_t)nq * PROJ_K * 4, cudaMemcpyDeviceToHost, st));
-  HFB_CUDA(ctx, cudaMemcpyAsync(cand_level, io + o_cl, (size_t)nq * PROJ_K * 4, cudaMemcpyDeviceToHost, st));
+  HFB_CUDA(ctx, cudaMemcpyAsync(hs + q_blk, io + o_ci, out_blk, cudaMemcpyDeviceToHost, st));
   HFB_CUDA(ctx, cudaStreamSynchronize(st));
+  memcpy(cand_idx, hs + q_blk, (size_t)nq * PROJ_K * 4);
+  memcpy(cand_dist, hs + q_blk + (o_cd - o_ci), (size_t)nq * PROJ_K * 4);
+  memcpy(cand_level, hs + q_blk + (o_cl - o_ci), (size_t)nq * PROJ_K * 4);
   return HFB_OK;
 }
 
